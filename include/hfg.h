@@ -1,0 +1,182 @@
+/*
+ * hfg.h -- C-ABI of libhfg (HMM-Flagger on B200): the drop-in boundary.
+ *
+ * This library replaces ONE path of mobinasri/flagger v1.2.0: the per-chunk HMM
+ * E-step of the `hmm_flagger` binary (scaled forward/backward, pair statistics,
+ * posterior-argmax decode), i.e. the two functions
+ *
+ *     void EM_runOneIterationForList(stList *emList, HMM *model, int threads);  // hmm.h:109, hmm.c:739-780
+ *     void EM_runForwardForList   (stList *emList, HMM *model, int threads);   // hmm.h:113, hmm.c:790-816
+ *
+ * plus thin host mirrors of the O(#parameters) functions that sit on either side of
+ * that seam (model construction and the M-step) so that a complete EM run can be
+ * driven through this header alone.  Everything is plain C: opaque handle, plain
+ * pointers and sizes, caller-owned host buffers, int status codes.  There is no CPU
+ * fallback: every compute entry point fails with HFG_ERR_CUDA when no sm_100 device /
+ * CUDA runtime is usable.
+ *
+ * Citations are file:line under the reference tree (programs/...).
+ */
+#ifndef HFG_H
+#define HFG_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFG_NUM_STATES 4   /* Err, Dup, Hap, Col  (submodules/hmm_utils/hmm_utils.h:19-25; MSJ excluded, src/hmm_flagger.c:235) */
+#define HFG_MAX_COMPS 16   /* mixture components per state; the CLI clamps the auto value to [2,10] (src/hmm_flagger.c:1012-1013) */
+#define HFG_MAX_REGIONS 64 /* region index lives in 6 bits of the annotation flag (submodules/ptBlock/ptBlock.c:294-304) */
+
+enum hfg_state { HFG_STATE_ERR = 0, HFG_STATE_DUP = 1, HFG_STATE_HAP = 2, HFG_STATE_COL = 3 };
+
+/* submodules/hmm_utils/hmm_utils.h:43-48 (negative_binomial is out of scope) */
+enum hfg_model_type { HFG_MODEL_TRUNC_EXP_GAUSSIAN = 0, HFG_MODEL_GAUSSIAN = 1 };
+
+enum hfg_status {
+    HFG_OK = 0,
+    HFG_ERR_INVALID = 1,         /* bad argument / call order */
+    HFG_ERR_CUDA = 2,            /* CUDA runtime error, or no usable device (no CPU fallback) */
+    HFG_ERR_SCALE_UNDERFLOW = 3, /* a forward scale fell below 1e-50: the reference exits here (hmm.c:412-415,521-524) */
+    HFG_ERR_NAN = 4,             /* an emission pdf evaluated to NaN: the reference exits here (hmm_utils.c:782-786) */
+    HFG_ERR_NOMEM = 5
+};
+
+typedef struct hfg_ctx hfg_ctx;
+
+/* Run-constant configuration: what EM_construct / HMM_construct / EM_setMinReadFractionAtEnds fix
+ * for the lifetime of a run (hmm.c:22-77,253-278; src/hmm_flagger.c:164-237). */
+typedef struct hfg_config {
+    int32_t model_type;                 /* enum hfg_model_type */
+    int32_t n_regions;                  /* 1..HFG_MAX_REGIONS */
+    int32_t n_comps[HFG_NUM_STATES];    /* {1,1,1,K} for the shipped models */
+    int32_t adjust_contig_ends;         /* 0 = --disableAdjustContigEnds (beta == 1) */
+    int32_t mean_read_length;           /* header #avg_alignment_len (em->meanReadLength) */
+    double min_read_fraction_at_ends;   /* --minReadFractionAtEnds */
+    double max_high_mapq_ratio;         /* --maxHighMapqRatio, Dup invalid above it (default 0.25) */
+    double min_high_mapq_ratio;         /* --minHighMapqRatio, Col invalid below it (default 0.75) */
+    double min_highly_clipped_ratio;    /* END column valid at or above it (fixed 1.0, src/hmm_flagger.c:222) */
+    int32_t device;                     /* CUDA device ordinal */
+    int32_t reserved;
+} hfg_config;
+
+/* One chain (the reference's Chunk, submodules/chunk/chunk.h:11-34). `offset` is the index of the
+ * chunk's first window in the flat observation arrays handed to hfg_set_chunks. */
+typedef struct hfg_chunk_desc {
+    int32_t ctg_len;
+    int32_t s;          /* 0-based inclusive start on the contig */
+    int32_t e;          /* 0-based inclusive end */
+    int32_t window_len;
+    int32_t n_windows;  /* coverageInfoSeqLen */
+    int32_t reserved;
+    int64_t offset;
+} hfg_chunk_desc;
+
+/* Parameters of one region (EmissionDistSeries + Transition of that region; hmm.h:14-25).
+ * Row index of mean/var/weight is the state; row HFG_STATE_ERR is used only by HFG_MODEL_GAUSSIAN.
+ * trans is the 5x5 matrix with row 4 = start and column 4 = end (hmm_utils.c:2109-2128). */
+typedef struct hfg_region_params {
+    double lambda;      /* TruncExponential.lambda     (hmm_utils.h:393-397) */
+    double trunc_point; /* TruncExponential.truncPoint */
+    double mean[HFG_NUM_STATES][HFG_MAX_COMPS];
+    double var[HFG_NUM_STATES][HFG_MAX_COMPS];
+    double weight[HFG_NUM_STATES][HFG_MAX_COMPS];
+    double trans[HFG_NUM_STATES + 1][HFG_NUM_STATES + 1];
+} hfg_region_params;
+
+/* E-step sufficient statistics of one region, laid out as the reference's estimator arrays
+ * (ParameterEstimator.{numeratorPerComp,denominatorPerComp}, hmm_utils.h:~90; TransitionCountData.countMatrix,
+ * hmm_utils.h:768-778).  hfg_em_iteration OVERWRITES these with this call's sums; the adapter adds them
+ * into the model's estimators (EM_updateModelEstimators, hmm.c:548-560). */
+typedef struct hfg_region_stats {
+    double trans_count[HFG_NUM_STATES][HFG_NUM_STATES]; /* [pre][state] */
+    double lambda_num, lambda_den;
+    double mean_num[HFG_NUM_STATES][HFG_MAX_COMPS], mean_den[HFG_NUM_STATES][HFG_MAX_COMPS];
+    double var_num[HFG_NUM_STATES][HFG_MAX_COMPS], var_den[HFG_NUM_STATES][HFG_MAX_COMPS];
+    double weight_num[HFG_NUM_STATES][HFG_MAX_COMPS], weight_den[HFG_NUM_STATES][HFG_MAX_COMPS];
+} hfg_region_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+
+/* Creates a context bound to cfg->device.  Replaces the per-chunk EM_construct loop (src/hmm_flagger.c:320-330). */
+int hfg_create(hfg_ctx **ctx, const hfg_config *cfg);
+void hfg_destroy(hfg_ctx *ctx);
+/* Message of the last failing call on this context ("" if none); ctx may be NULL for hfg_create failures. */
+const char *hfg_last_error(const hfg_ctx *ctx);
+
+/* Uploads all chains once.  cov / cov_high_mapq / cov_high_clip are the u16 window values of CoverageInfo
+ * (ptBlock.h:79-92; already averaged, rounded and clipped to 250 by Chunk_addWindow, chunk.c:393-441) and
+ * region is CoverageInfo_getRegionIndex per window; each array has sum(n_windows) entries, chunk after chunk
+ * in list order.  Replaces the CoverageInfo** walk of hmm.c:344-345,382-385. */
+int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_desc *chunks,
+                   const uint16_t *cov, const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip,
+                   const uint8_t *region);
+
+int64_t hfg_num_windows(const hfg_ctx *ctx);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+
+/* One E-step over all chunks == EM_runOneIterationForList (hmm.c:739-780):
+ *   forward + backward + pair statistics + per-window posterior-argmax label.
+ * alpha: 4x4 row-major [pre][state] (model->alpha).  params/stats: n_regions entries.
+ * *loglik = sum over chunks of sum_i log(scale_i)  (model->loglikelihood).
+ * labels: sum(n_windows) int8 (Inference.prediction, hmm.c:730-736) or NULL to skip the copy.
+ * All pointers are HOST memory; the call blocks until the results are in them. */
+int hfg_em_iteration(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params,
+                     hfg_region_stats *stats, double *loglik, int8_t *labels);
+
+/* Forward pass only == EM_runForwardForList (hmm.c:790-816), used by SQUAREM (hmm.c:900,912). */
+int hfg_forward_only(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params, double *loglik);
+
+/* Normalised posteriors (EM_getPosterior, hmm.c:671-685) of the LAST hfg_em_iteration, W x 4 row-major,
+ * for --writePosteriorProbs (src/hmm_flagger.c:240-282). */
+int hfg_get_posteriors(hfg_ctx *ctx, double *posteriors);
+
+/* Per-chunk forward log-likelihoods (em->loglikelihood, hmm.c:428) of the last E-step / forward pass. */
+int hfg_get_chunk_logliks(hfg_ctx *ctx, double *logliks);
+
+/* Device-resident variant for multi-GPU drivers: enqueues the E-step on `stream` (a cudaStream_t, may be NULL
+ * for the context's own stream) and leaves  [n_regions x hfg_region_stats | loglik]  (doubles) in the DEVICE
+ * buffer stats_dev, ready for a sum all-reduce; labels stay on the device.  Does not synchronise. */
+int hfg_em_iteration_device(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params,
+                            void *stats_dev, void *stream);
+size_t hfg_stats_device_bytes(const hfg_ctx *ctx);
+/* Copies the labels of the last E-step to the host (blocking). */
+int hfg_get_labels(hfg_ctx *ctx, int8_t *labels);
+
+/* ---- host mirrors of the O(#parameters) neighbours of the seam ---------------------------------- */
+
+/* max(2, min(10, maxCov / min(regionCov) + 1))  (src/hmm_flagger.c:105-111,1008-1013). */
+int hfg_best_num_collapsed_comps(int max_coverage, const int32_t *region_coverages, int n_regions);
+
+/* Initial model == createModel + HMM_construct (src/hmm_flagger.c:164-237, hmm.c:22-77,
+ * hmm_utils.c:1605-1652,2109-2128) with --initialRandomDev 0.  start_only_mode scales the baseline by
+ * window_len / avg_alignment_len (src/hmm_flagger.c:190-195). */
+int hfg_model_init(const hfg_config *cfg, const int32_t *region_coverages, int window_len,
+                   int start_only_mode, hfg_region_params *params);
+
+/* M-step == HMM_estimateParameters (hmm.c:120-127; hmm_utils.c:1791-1903,2185-2219).
+ * Updates params in place from stats; *converged is the reference's return value. */
+int hfg_mstep(const hfg_config *cfg, hfg_region_params *params, const hfg_region_stats *stats,
+              double convergence_tol, int *converged);
+
+/* Whole EM loop of runHMMFlagger without its file outputs (src/hmm_flagger.c:337-467): up to max_iterations x
+ * (E-step, M-step) while not converged, then the final-inference E-step.  logliks receives one value per E-step
+ * (capacity max_iterations + 1); *n_esteps the number run.  labels (nullable) are those of the final E-step. */
+int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,
+               double convergence_tol, double *logliks, int *n_esteps, int8_t *labels);
+
+/* ---- instrumentation ---------------------------------------------------------------------------- */
+
+/* Number of kernels this context has launched so far. */
+int64_t hfg_kernel_launches(const hfg_ctx *ctx);
+/* Device time (ms, CUDA events on the launching stream) of the E-step kernel in the last hfg_em_iteration*. */
+double hfg_last_estep_kernel_ms(hfg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFG_H */

@@ -1,0 +1,36 @@
+/*
+ * oracle/hmm_oracle.h -- TEST INFRASTRUCTURE ONLY (see hmm_oracle.c).
+ * CPU restatement of the reference E-step / M-step, and (ref_*) the same entry points served by the
+ * UNMODIFIED reference objects when oracle/_ref/libref_harness.so has been built (oracle/ref_harness.c).
+ */
+#ifndef HFG_ORACLE_H
+#define HFG_ORACLE_H
+#include "../include/hfg.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+double orc_beta(const hfg_config *cfg, const hfg_chunk_desc *ch, int i);
+
+int orc_estep(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+              const uint16_t *mapq, const uint16_t *clip, const uint8_t *region, const double *alpha,
+              const hfg_region_params *params, hfg_region_stats *stats, double *loglik, double *chunk_logliks,
+              int8_t *labels, double *posteriors, double *fwd, double *bwd, double *scales_out, int forward_only);
+
+int orc_best_num_collapsed_comps(int max_coverage, const int32_t *region_coverages, int n_regions);
+
+int orc_model_init(const hfg_config *cfg, const int32_t *region_coverages, int window_len, int start_only_mode,
+                   hfg_region_params *params);
+
+int orc_mstep(const hfg_config *cfg, hfg_region_params *params, const hfg_region_stats *stats, double tol,
+              int *converged_out);
+
+int orc_run_em(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+               const uint16_t *mapq, const uint16_t *clip, const uint8_t *region, const double *alpha,
+               hfg_region_params *params, int max_iterations, double tol, double *logliks, int *n_esteps,
+               int8_t *labels);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

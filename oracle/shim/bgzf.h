@@ -1,0 +1,2 @@
+/* oracle/shim/bgzf.h -- TEST INFRASTRUCTURE ONLY: empty stand-in for the htslib header (see sam.h). */
+#include "sam.h"

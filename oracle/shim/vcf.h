@@ -1,0 +1,2 @@
+/* oracle/shim/vcf.h -- TEST INFRASTRUCTURE ONLY: empty stand-in for the htslib header (see sam.h). */
+#include "sam.h"

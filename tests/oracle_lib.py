@@ -1,0 +1,105 @@
+"""ctypes access to the CHECKERS: oracle/liborc.so (C restatement) and oracle/_ref/libref_harness.so
+(unmodified reference objects).  Test infrastructure only -- never imported by flagger_b200/."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from flagger_b200 import _abi
+from flagger_b200._abi import ptr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_BIN = os.path.join(ORACLE_DIR, "_ref", "hmm_flagger_ref")
+
+
+def build_oracle():
+    """Compile the restatement (and the reference build when /root/reference is mounted)."""
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True, stdout=subprocess.DEVNULL)
+
+
+def _load(path):
+    return C.CDLL(path) if os.path.exists(path) else None
+
+
+class _Checker:
+    """Common numpy-facing API over orc_* / ref_* entry points."""
+
+    def __init__(self, lib, prefix, threads=None):
+        self.lib = lib
+        self.prefix = prefix
+        self.threads = threads
+
+    def _fn(self, name):
+        f = getattr(self.lib, f"{self.prefix}_{name}")
+        f.restype = C.c_int
+        return f
+
+    def estep(self, cfg, wl, alpha, params, forward_only=False, want_fb=False):
+        W, Cn, R = wl.n_windows, wl.n_chunks, int(cfg["n_regions"][0])
+        stats = np.zeros(R, dtype=_abi.region_stats_dtype)
+        loglik = C.c_double(0.0)
+        chunk_ll = np.zeros(Cn, np.float64)
+        labels = np.full(W, -1, np.int8)
+        post = np.zeros((W, 4), np.float64)
+        fwd = np.zeros((W, 4), np.float64) if want_fb else None
+        bwd = np.zeros((W, 4), np.float64) if want_fb else None
+        scales = np.zeros(W, np.float64) if want_fb else None
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        args = [ptr(cfg), C.c_int(Cn), ptr(wl.chunks), ptr(wl.cov), ptr(wl.cov_high_mapq), ptr(wl.cov_high_clip),
+                ptr(wl.region), ptr(alpha), ptr(params), ptr(stats), C.byref(loglik), ptr(chunk_ll), ptr(labels),
+                ptr(post), ptr(fwd), ptr(bwd), ptr(scales), C.c_int(1 if forward_only else 0)]
+        if self.threads is not None:
+            args.append(C.c_int(self.threads))
+        rc = self._fn("estep")(*args)
+        return dict(rc=rc, stats=stats, loglik=loglik.value, chunk_logliks=chunk_ll, labels=labels, posteriors=post,
+                    fwd=fwd, bwd=bwd, scales=scales)
+
+    def model_init(self, cfg, region_coverages, window_len, start_only=False):
+        params = np.zeros(int(cfg["n_regions"][0]), dtype=_abi.region_params_dtype)
+        rc_ = np.ascontiguousarray(region_coverages, np.int32)
+        rc = self._fn("model_init")(ptr(cfg), ptr(rc_), C.c_int(window_len), C.c_int(1 if start_only else 0),
+                                    ptr(params))
+        assert rc == 0
+        return params
+
+    def mstep(self, cfg, params, stats, tol=1e-3):
+        params = params.copy()
+        conv = C.c_int(0)
+        rc = self._fn("mstep")(ptr(cfg), ptr(params), ptr(stats), C.c_double(tol), C.byref(conv))
+        assert rc == 0
+        return params, bool(conv.value)
+
+    def run_em(self, cfg, wl, alpha, params, max_iterations, tol=1e-12, threads=None):
+        params = params.copy()
+        logliks = np.zeros(max_iterations + 1, np.float64)
+        n = C.c_int(0)
+        labels = np.full(wl.n_windows, -1, np.int8)
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        args = [ptr(cfg), C.c_int(wl.n_chunks), ptr(wl.chunks), ptr(wl.cov), ptr(wl.cov_high_mapq),
+                ptr(wl.cov_high_clip), ptr(wl.region), ptr(alpha), ptr(params), C.c_int(max_iterations),
+                C.c_double(tol), ptr(logliks), C.byref(n), ptr(labels)]
+        secs = C.c_double(0.0)
+        if self.threads is not None:
+            args += [C.c_int(threads or self.threads), C.byref(secs)]
+        rc = self._fn("run_em")(*args)
+        return dict(rc=rc, params=params, logliks=logliks[:n.value].copy(), labels=labels, estep_seconds=secs.value)
+
+    def best_num_collapsed_comps(self, max_cov, region_coverages):
+        rc_ = np.ascontiguousarray(region_coverages, np.int32)
+        return self._fn("best_num_collapsed_comps")(C.c_int(int(max_cov)), ptr(rc_), C.c_int(len(rc_)))
+
+
+def oracle():
+    """The C restatement (always available once built)."""
+    path = os.path.join(ORACLE_DIR, "liborc.so")
+    if not os.path.exists(path):
+        build_oracle()
+    return _Checker(C.CDLL(path), "orc")
+
+
+def reference(threads=1):
+    """The unmodified reference behind ref_harness.c, or None when oracle/_ref has not been built."""
+    lib = _load(os.path.join(ORACLE_DIR, "_ref", "libref_harness.so"))
+    return _Checker(lib, "ref", threads=threads) if lib is not None else None
