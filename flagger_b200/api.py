@@ -1,0 +1,177 @@
+"""Python host side of libhfg: a thin ctypes binding over the C-ABI of include/hfg.h.
+
+Mirrors the reference's operator surface for this path (names and meaning follow
+submodules/hmm/hmm.h): `em_iteration` == EM_runOneIterationForList, `forward_only` ==
+EM_runForwardForList, `mstep` == HMM_estimateParameters, `model_init` == createModel/HMM_construct.
+There is no fallback of any kind: if libhfg.so is missing or CUDA is unusable, this raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import ptr
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhfg.so")
+_lib = None
+
+
+class HfgError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libhfg error {code}: {message}")
+        self.code = code
+
+
+def lib():
+    """Load libhfg.so (built in-tree by __graft_entry__.build() / flagger_b200/csrc/Makefile)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise HfgError(_abi.ERR_CUDA, f"{_LIB_PATH} is missing: build it with `make -C flagger_b200/csrc` "
+                                          "(there is no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        L.hfg_last_error.restype = C.c_char_p
+        L.hfg_last_error.argtypes = [C.c_void_p]
+        L.hfg_num_windows.restype = C.c_int64
+        L.hfg_kernel_launches.restype = C.c_int64
+        L.hfg_last_estep_kernel_ms.restype = C.c_double
+        L.hfg_stats_device_bytes.restype = C.c_size_t
+        for name in ("hfg_num_windows", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_stats_device_bytes",
+                     "hfg_destroy"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.hfg_destroy.restype = None
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = (
+    "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_chunks", "hfg_num_windows", "hfg_em_iteration",
+    "hfg_forward_only", "hfg_get_posteriors", "hfg_get_chunk_logliks", "hfg_em_iteration_device",
+    "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
+    "hfg_run_em", "hfg_kernel_launches", "hfg_last_estep_kernel_ms",
+)
+
+
+def best_num_collapsed_comps(max_coverage, region_coverages):
+    rc = np.ascontiguousarray(region_coverages, np.int32)
+    return int(lib().hfg_best_num_collapsed_comps(C.c_int(int(max_coverage)), ptr(rc), C.c_int(len(rc))))
+
+
+def model_init(cfg, region_coverages, window_len, start_only=False):
+    params = np.zeros(int(cfg["n_regions"][0]), dtype=_abi.region_params_dtype)
+    rc_ = np.ascontiguousarray(region_coverages, np.int32)
+    rc = lib().hfg_model_init(ptr(cfg), ptr(rc_), C.c_int(int(window_len)), C.c_int(1 if start_only else 0),
+                              ptr(params))
+    if rc != 0:
+        raise HfgError(rc, "hfg_model_init: invalid configuration")
+    return params
+
+
+def mstep(cfg, params, stats, tol=1e-3):
+    params = params.copy()
+    conv = C.c_int(0)
+    rc = lib().hfg_mstep(ptr(cfg), ptr(params), ptr(stats), C.c_double(tol), C.byref(conv))
+    if rc != 0:
+        raise HfgError(rc, "hfg_mstep: invalid arguments")
+    return params, bool(conv.value)
+
+
+class HmmFlaggerGPU:
+    """One libhfg context: a set of chunks resident on one GPU."""
+
+    def __init__(self, cfg, workload=None):
+        self.cfg = np.ascontiguousarray(cfg)
+        self._h = C.c_void_p()
+        rc = lib().hfg_create(C.byref(self._h), ptr(self.cfg))
+        if rc != 0:
+            raise HfgError(rc, lib().hfg_last_error(None).decode())
+        self.n_regions = int(self.cfg["n_regions"][0])
+        self.n_windows = 0
+        self.n_chunks = 0
+        if workload is not None:
+            self.set_chunks(workload)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HfgError(rc, lib().hfg_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().hfg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_chunks(self, wl):
+        chunks = np.ascontiguousarray(wl.chunks)
+        self._check(lib().hfg_set_chunks(self._h, C.c_int32(len(chunks)), ptr(chunks),
+                                         ptr(np.ascontiguousarray(wl.cov, np.uint16)),
+                                         ptr(np.ascontiguousarray(wl.cov_high_mapq, np.uint16)),
+                                         ptr(np.ascontiguousarray(wl.cov_high_clip, np.uint16)),
+                                         ptr(np.ascontiguousarray(wl.region, np.uint8))))
+        self.n_windows = int(lib().hfg_num_windows(self._h))
+        self.n_chunks = len(chunks)
+
+    def em_iteration(self, alpha, params, want_labels=True, stats=None, labels=None):
+        """EM_runOneIterationForList: returns (stats, loglik, labels)."""
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        if stats is None:
+            stats = np.zeros(self.n_regions, dtype=_abi.region_stats_dtype)
+        if labels is None and want_labels:
+            labels = np.empty(self.n_windows, np.int8)
+        ll = C.c_double(0.0)
+        self._check(lib().hfg_em_iteration(self._h, ptr(alpha), ptr(params), ptr(stats), C.byref(ll),
+                                           ptr(labels) if want_labels else None))
+        return stats, ll.value, labels
+
+    def forward_only(self, alpha, params):
+        """EM_runForwardForList: returns the total log-likelihood."""
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        ll = C.c_double(0.0)
+        self._check(lib().hfg_forward_only(self._h, ptr(alpha), ptr(params), C.byref(ll)))
+        return ll.value
+
+    def em_iteration_device(self, alpha, params, stats_dev_ptr, stream_ptr=0):
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        self._check(lib().hfg_em_iteration_device(self._h, ptr(alpha), ptr(params), C.c_void_p(stats_dev_ptr),
+                                                  C.c_void_p(stream_ptr)))
+
+    def stats_device_bytes(self):
+        return int(lib().hfg_stats_device_bytes(self._h))
+
+    def labels(self):
+        out = np.empty(self.n_windows, np.int8)
+        self._check(lib().hfg_get_labels(self._h, ptr(out)))
+        return out
+
+    def posteriors(self):
+        out = np.empty((self.n_windows, 4), np.float64)
+        self._check(lib().hfg_get_posteriors(self._h, ptr(out)))
+        return out
+
+    def chunk_logliks(self):
+        out = np.empty(self.n_chunks, np.float64)
+        self._check(lib().hfg_get_chunk_logliks(self._h, ptr(out)))
+        return out
+
+    def run_em(self, alpha, params, max_iterations, tol=1e-3, want_labels=True):
+        """The EM loop of runHMMFlagger (src/hmm_flagger.c:337-467): returns (params, logliks, labels)."""
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        params = params.copy()
+        logliks = np.zeros(max_iterations + 1, np.float64)
+        n = C.c_int(0)
+        labels = np.empty(self.n_windows, np.int8) if want_labels else None
+        self._check(lib().hfg_run_em(self._h, ptr(alpha), ptr(params), C.c_int(max_iterations), C.c_double(tol),
+                                     ptr(logliks), C.byref(n), ptr(labels)))
+        return params, logliks[:n.value].copy(), labels
+
+    def kernel_launches(self):
+        return int(lib().hfg_kernel_launches(self._h))
+
+    def last_estep_kernel_ms(self):
+        return float(lib().hfg_last_estep_kernel_ms(self._h))

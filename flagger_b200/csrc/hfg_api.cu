@@ -1,0 +1,448 @@
+/*
+ * hfg_api.cu -- the C-ABI of libhfg (include/hfg.h): context, device memory, launches.
+ *
+ * The compute entry points stand where the reference has EM_runOneIterationForList / EM_runForwardForList
+ * (submodules/hmm/hmm.c:739-816).  There is NO CPU fallback: without a usable CUDA device every entry point
+ * returns HFG_ERR_CUDA with a message.
+ */
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "hfg_estep.cuh"
+#include "hfg_internal.h"
+
+#define STAGE_SLOTS 4
+#define STATS_DOUBLES ((int) (sizeof(hfg_region_stats) / sizeof(double)))
+
+struct hfg_ctx {
+    hfg_config cfg;
+    hfg_layout lay;
+    int have_chunks;
+    int device, num_sms, max_blocks, grid;
+    size_t smem_bytes;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    int ev_valid;
+    /* device */
+    uint32_t *d_obsT;
+    int32_t *d_seg_start, *d_seg_len, *d_seg_edge_begin, *d_block_reset, *d_err;
+    double *d_edge_beta, *d_scrE, *d_scrF, *d_scrC, *d_block_tot, *d_partials, *d_out, *d_seg_loglik, *d_post;
+    hfg_region_params *d_params[STAGE_SLOTS];
+    int8_t *d_labels;
+    /* pinned host staging */
+    hfg_region_params *h_params[STAGE_SLOTS];
+    cudaEvent_t stage_ev[STAGE_SLOTS];
+    int stage_next;
+    double *h_out;
+    /* last call (for hfg_get_posteriors) */
+    int have_last;
+    double last_alpha[16];
+    hfg_region_params *last_params;
+    int64_t launches;
+    char err[512];
+};
+
+static char g_create_err[512] = "";
+
+static int fail(hfg_ctx *ctx, int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx ? ctx->err : g_create_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail(ctx, HFG_ERR_CUDA, "%s failed: %s (no CPU fallback exists)", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static size_t smem_bytes_for(int R, int G) {
+    size_t doubles = (size_t) R * RT_STRIDE(G) + 3 * HFG_WARPS * 16 + 8 + (size_t) hfg_nstat(G) * (HFG_THREADS + 1);
+    return doubles * sizeof(double) + HFG_THREADS * sizeof(int);
+}
+
+static int total_gauss_comps(const hfg_config *cfg) {
+    int G = 0;
+    for (int s = 0; s < HFG_NS; s++)
+        if (!(cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && s == HFG_STATE_ERR)) G += cfg->n_comps[s];
+    return G;
+}
+
+extern "C" const char *hfg_last_error(const hfg_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
+    hfg_ctx *ctx = NULL;
+    if (!out || !cfg) return fail(NULL, HFG_ERR_INVALID, "hfg_create: NULL argument");
+    *out = NULL;
+    if (cfg->model_type != HFG_MODEL_TRUNC_EXP_GAUSSIAN && cfg->model_type != HFG_MODEL_GAUSSIAN)
+        return fail(NULL, HFG_ERR_INVALID, "hfg_create: model_type %d not supported (negative_binomial is out of scope)",
+                    cfg->model_type);
+    if (cfg->n_regions < 1 || cfg->n_regions > HFG_MAX_REGIONS)
+        return fail(NULL, HFG_ERR_INVALID, "hfg_create: n_regions %d outside 1..%d", cfg->n_regions, HFG_MAX_REGIONS);
+    for (int s = 0; s < HFG_NS; s++)
+        if (cfg->n_comps[s] < 1 || cfg->n_comps[s] > HFG_MAX_COMPS)
+            return fail(NULL, HFG_ERR_INVALID, "hfg_create: n_comps[%d]=%d outside 1..%d", s, cfg->n_comps[s], HFG_MAX_COMPS);
+    {
+        cudaError_t e = cudaSetDevice(cfg->device);
+        if (e != cudaSuccess)
+            return fail(NULL, HFG_ERR_CUDA, "cudaSetDevice(%d) failed: %s (libhfg has no CPU fallback)", cfg->device,
+                        cudaGetErrorString(e));
+    }
+    ctx = (hfg_ctx *) calloc(1, sizeof(hfg_ctx));
+    if (!ctx) return fail(NULL, HFG_ERR_NOMEM, "hfg_create: out of memory");
+    ctx->cfg = *cfg;
+    ctx->device = cfg->device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) {
+        fail(NULL, HFG_ERR_CUDA, "cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+        free(ctx);
+        return HFG_ERR_CUDA;
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    const int G = total_gauss_comps(cfg);
+    ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G);
+    if (ctx->smem_bytes > (size_t) prop.sharedMemPerBlockOptin) {
+        fail(NULL, HFG_ERR_INVALID, "model too large for shared memory: %zu bytes needed for %d regions x %d components, %zu available",
+             ctx->smem_bytes, cfg->n_regions, G, (size_t) prop.sharedMemPerBlockOptin);
+        free(ctx);
+        return HFG_ERR_INVALID;
+    }
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
+    e = cudaFuncSetAttribute(hfg_estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
+    int per_sm = 0;
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hfg_estep_kernel, HFG_THREADS, ctx->smem_bytes);
+    if (e != cudaSuccess || !coop || per_sm < 1) {
+        fail(NULL, HFG_ERR_CUDA, "E-step kernel cannot be launched cooperatively on device %d (%s; coop=%d, blocks/SM=%d)",
+             cfg->device, cudaGetErrorString(e), coop, per_sm);
+        free(ctx);
+        return HFG_ERR_CUDA;
+    }
+    ctx->max_blocks = ctx->num_sms; /* one persistent CTA per SM (__launch_bounds__(256, 1)) */
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        fail(NULL, HFG_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        free(ctx);
+        return HFG_ERR_CUDA;
+    }
+    const size_t pbytes = sizeof(hfg_region_params) * (size_t) cfg->n_regions;
+    for (int i = 0; i < STAGE_SLOTS; i++) {
+        if (cudaMallocHost((void **) &ctx->h_params[i], pbytes) != cudaSuccess ||
+            cudaMalloc((void **) &ctx->d_params[i], pbytes) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+            fail(NULL, HFG_ERR_CUDA, "parameter staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            free(ctx);
+            return HFG_ERR_CUDA;
+        }
+    }
+    ctx->last_params = (hfg_region_params *) malloc(pbytes);
+    *out = ctx;
+    return HFG_OK;
+}
+
+static void free_device(hfg_ctx *ctx) {
+    cudaFree(ctx->d_obsT); cudaFree(ctx->d_seg_start); cudaFree(ctx->d_seg_len); cudaFree(ctx->d_seg_edge_begin);
+    cudaFree(ctx->d_block_reset); cudaFree(ctx->d_err); cudaFree(ctx->d_edge_beta); cudaFree(ctx->d_scrE);
+    cudaFree(ctx->d_scrF); cudaFree(ctx->d_scrC); cudaFree(ctx->d_block_tot); cudaFree(ctx->d_partials);
+    cudaFree(ctx->d_out); cudaFree(ctx->d_seg_loglik); cudaFree(ctx->d_post); cudaFree(ctx->d_labels);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    ctx->d_obsT = NULL; ctx->d_seg_start = ctx->d_seg_len = ctx->d_seg_edge_begin = ctx->d_block_reset = ctx->d_err = NULL;
+    ctx->d_edge_beta = ctx->d_scrE = ctx->d_scrF = ctx->d_scrC = ctx->d_block_tot = ctx->d_partials = NULL;
+    ctx->d_out = ctx->d_seg_loglik = ctx->d_post = NULL;
+    ctx->d_labels = NULL;
+    ctx->h_out = NULL;
+    hfg_layout_free(&ctx->lay);
+    ctx->have_chunks = 0;
+}
+
+extern "C" void hfg_destroy(hfg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_device(ctx);
+    for (int i = 0; i < STAGE_SLOTS; i++) {
+        cudaFreeHost(ctx->h_params[i]);
+        cudaFree(ctx->d_params[i]);
+        cudaEventDestroy(ctx->stage_ev[i]);
+    }
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    free(ctx->last_params);
+    free(ctx);
+}
+
+extern "C" int64_t hfg_num_windows(const hfg_ctx *ctx) { return ctx && ctx->have_chunks ? ctx->lay.n_windows : 0; }
+extern "C" int64_t hfg_kernel_launches(const hfg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" size_t hfg_stats_device_bytes(const hfg_ctx *ctx) {
+    return ctx ? ((size_t) ctx->cfg.n_regions * STATS_DOUBLES + 2) * sizeof(double) : 0;
+}
+
+extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                              const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region) {
+    if (!ctx) return HFG_ERR_INVALID;
+    if (n_chunks < 1 || !chunks || !cov || !cov_high_mapq || !cov_high_clip || !region)
+        return fail(ctx, HFG_ERR_INVALID, "hfg_set_chunks: NULL or empty input");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    free_device(ctx);
+    int64_t W = 0;
+    for (int32_t c = 0; c < n_chunks; c++) W += chunks[c].n_windows;
+    /* persistent grid: one CTA per SM, but do not spread a tiny input over the whole chip */
+    int64_t blocks = (W + (int64_t) HFG_THREADS * 4 - 1) / ((int64_t) HFG_THREADS * 4);
+    if (blocks < 1) blocks = 1;
+    if (blocks > ctx->max_blocks) blocks = ctx->max_blocks;
+    ctx->grid = (int) blocks;
+    const int32_t cap = ctx->grid * HFG_THREADS;
+    int rc = hfg_layout_build(&ctx->cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, cap, &ctx->lay,
+                              ctx->err, sizeof(ctx->err));
+    if (rc != HFG_OK) return rc;
+    const hfg_layout *l = &ctx->lay;
+    const size_t slots = (size_t) l->smax * cap;
+    const int R = ctx->cfg.n_regions, G = total_gauss_comps(&ctx->cfg);
+    const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
+    CU(cudaMalloc((void **) &ctx->d_obsT, slots * sizeof(uint32_t)));
+    CU(cudaMalloc((void **) &ctx->d_seg_start, cap * sizeof(int32_t)));
+    CU(cudaMalloc((void **) &ctx->d_seg_len, cap * sizeof(int32_t)));
+    CU(cudaMalloc((void **) &ctx->d_seg_edge_begin, ((size_t) cap + 1) * sizeof(int32_t)));
+    CU(cudaMalloc((void **) &ctx->d_edge_beta, (size_t) (l->n_edge > 0 ? l->n_edge : 1) * sizeof(double)));
+    CU(cudaMalloc((void **) &ctx->d_scrE, slots * HFG_MAX_CLASSES * sizeof(double)));
+    CU(cudaMalloc((void **) &ctx->d_scrF, slots * 4 * sizeof(double)));
+    CU(cudaMalloc((void **) &ctx->d_scrC, slots * sizeof(double)));
+    CU(cudaMalloc((void **) &ctx->d_block_tot, (size_t) ctx->grid * 16 * sizeof(double)));
+    CU(cudaMalloc((void **) &ctx->d_block_reset, (size_t) ctx->grid * sizeof(int32_t)));
+    CU(cudaMalloc((void **) &ctx->d_partials, (size_t) ctx->grid * R * hfg_nstat(G) * sizeof(double)));
+    CU(cudaMalloc((void **) &ctx->d_out, out_doubles * sizeof(double)));
+    CU(cudaMalloc((void **) &ctx->d_seg_loglik, cap * sizeof(double)));
+    CU(cudaMalloc((void **) &ctx->d_labels, (size_t) l->n_windows));
+    CU(cudaMalloc((void **) &ctx->d_err, sizeof(int32_t)));
+    CU(cudaMallocHost((void **) &ctx->h_out, out_doubles * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->d_obsT, l->obsT, slots * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_seg_start, l->seg_start, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_seg_len, l->seg_len, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_seg_edge_begin, l->seg_edge_begin, ((size_t) cap + 1) * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    if (l->n_edge > 0)
+        CU(cudaMemcpyAsync(ctx->d_edge_beta, l->edge_beta, (size_t) l->n_edge * sizeof(double), cudaMemcpyHostToDevice,
+                           ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_labels, 0xff, (size_t) l->n_windows, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    free(ctx->lay.obsT); /* the packed words now live on the device */
+    ctx->lay.obsT = NULL;
+    ctx->have_chunks = 1;
+    ctx->have_last = 0;
+    return HFG_OK;
+}
+
+/* Enqueue one E-step (or forward pass) on `stream`; results land in out_dev = [stats | loglik | error flags]. */
+static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params, double *out_dev,
+                         double *post_dev, int forward_only, cudaStream_t stream, int timed) {
+    if (!ctx->have_chunks) return fail(ctx, HFG_ERR_INVALID, "hfg_set_chunks must be called first");
+    if (!alpha || !params) return fail(ctx, HFG_ERR_INVALID, "NULL alpha/params");
+    CU(cudaSetDevice(ctx->device));
+    const hfg_config *cfg = &ctx->cfg;
+    const hfg_layout *l = &ctx->lay;
+    const int R = cfg->n_regions;
+
+    hfg_classes cl;
+    hfg_classes_build(cfg, alpha, &cl);
+
+    /* stage the parameters (ring of pinned buffers so that back-to-back asynchronous calls never race) */
+    const int slot = ctx->stage_next;
+    ctx->stage_next = (slot + 1) % STAGE_SLOTS;
+    CU(cudaEventSynchronize(ctx->stage_ev[slot]));
+    memcpy(ctx->h_params[slot], params, sizeof(hfg_region_params) * (size_t) R);
+    CU(cudaMemcpyAsync(ctx->d_params[slot], ctx->h_params[slot], sizeof(hfg_region_params) * (size_t) R,
+                       cudaMemcpyHostToDevice, stream));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), stream));
+
+    EstepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.obsT = ctx->d_obsT;
+    a.seg_start = ctx->d_seg_start;
+    a.seg_len = ctx->d_seg_len;
+    a.seg_edge_begin = ctx->d_seg_edge_begin;
+    a.edge_beta = ctx->d_edge_beta;
+    a.capacity = l->capacity;
+    a.smax = l->smax;
+    a.n_regions = R;
+    a.beta0 = l->beta0;
+    a.n_classes = cl.n_classes;
+    int g = 0;
+    for (int s = 0; s < HFG_NS; s++) {
+        a.is_gauss[s] = cl.is_gaussian[s];
+        a.ncomp[s] = cfg->n_comps[s];
+        a.gbase[s] = g;
+        if (cl.is_gaussian[s]) g += cfg->n_comps[s];
+        a.zero_slot_used[s] = 0;
+        for (int pre = 0; pre < HFG_NS; pre++) {
+            a.cls[pre][s] = cl.cls[pre][s];
+            a.alpha[pre][s] = cl.is_gaussian[s] ? alpha[pre * HFG_NS + s] : 0.0;
+            if (cl.cls[pre][s] == s) a.zero_slot_used[s] = 1;
+        }
+    }
+    a.G = g;
+    for (int d = 0; d < HFG_MAX_CLASSES; d++) {
+        a.class_state[d] = cl.class_state[d];
+        a.class_alpha[d] = cl.class_alpha[d];
+    }
+    a.params = ctx->d_params[slot];
+    a.scrE = ctx->d_scrE;
+    a.scrF = ctx->d_scrF;
+    a.scrC = ctx->d_scrC;
+    a.block_tot = ctx->d_block_tot;
+    a.block_reset = ctx->d_block_reset;
+    a.partials = ctx->d_partials;
+    a.out = out_dev;
+    a.seg_loglik = ctx->d_seg_loglik;
+    a.labels = ctx->d_labels;
+    a.posteriors = post_dev;
+    a.err_flags = ctx->d_err;
+    a.forward_only = forward_only;
+
+    void *kargs[] = {(void *) &a};
+    if (timed) CU(cudaEventRecord(ctx->ev0, stream));
+    CU(cudaLaunchCooperativeKernel((void *) hfg_estep_kernel, dim3(ctx->grid), dim3(HFG_THREADS), kargs,
+                                   ctx->smem_bytes, stream));
+    if (timed) {
+        CU(cudaEventRecord(ctx->ev1, stream));
+        ctx->ev_valid = 1;
+    }
+    CU(cudaEventRecord(ctx->stage_ev[slot], stream));
+    ctx->launches += 1;
+
+    memcpy(ctx->last_alpha, alpha, sizeof(double) * 16);
+    memcpy(ctx->last_params, params, sizeof(hfg_region_params) * (size_t) R);
+    ctx->have_last = 1;
+    return HFG_OK;
+}
+
+/* fetch [stats | loglik | flags] from the context's own output buffer and translate the error flags */
+static int fetch_out(hfg_ctx *ctx, hfg_region_stats *stats, double *loglik, int8_t *labels, int with_labels) {
+    const int R = ctx->cfg.n_regions;
+    const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
+    CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (with_labels && labels)
+        CU(cudaMemcpyAsync(labels, ctx->d_labels, (size_t) ctx->lay.n_windows, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int flags = (int) ctx->h_out[out_doubles - 1];
+    if (flags & 1)
+        return fail(ctx, HFG_ERR_SCALE_UNDERFLOW, "scale is very low! (a forward scale fell below 1e-50; hmm.c:412-415)");
+    if (flags & 2) return fail(ctx, HFG_ERR_NAN, "[Error] prob is NAN (an emission pdf evaluated to NaN; hmm_utils.c:782-786)");
+    if (stats) memcpy(stats, ctx->h_out, sizeof(hfg_region_stats) * (size_t) R);
+    if (loglik) *loglik = ctx->h_out[out_doubles - 2];
+    return HFG_OK;
+}
+
+extern "C" int hfg_em_iteration(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params,
+                                hfg_region_stats *stats, double *loglik, int8_t *labels) {
+    if (!ctx) return HFG_ERR_INVALID;
+    int rc = enqueue_estep(ctx, alpha, params, ctx->d_out, NULL, 0, ctx->stream, 1);
+    if (rc != HFG_OK) return rc;
+    return fetch_out(ctx, stats, loglik, labels, 1);
+}
+
+extern "C" int hfg_forward_only(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params, double *loglik) {
+    if (!ctx) return HFG_ERR_INVALID;
+    int rc = enqueue_estep(ctx, alpha, params, ctx->d_out, NULL, 1, ctx->stream, 1);
+    if (rc != HFG_OK) return rc;
+    return fetch_out(ctx, NULL, loglik, NULL, 0);
+}
+
+extern "C" int hfg_em_iteration_device(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params,
+                                       void *stats_dev, void *stream) {
+    if (!ctx) return HFG_ERR_INVALID;
+    if (!stats_dev) return fail(ctx, HFG_ERR_INVALID, "hfg_em_iteration_device: NULL stats_dev");
+    cudaStream_t s = stream ? (cudaStream_t) stream : ctx->stream;
+    return enqueue_estep(ctx, alpha, params, (double *) stats_dev, NULL, 0, s, 1);
+}
+
+extern "C" int hfg_get_labels(hfg_ctx *ctx, int8_t *labels) {
+    if (!ctx || !labels) return HFG_ERR_INVALID;
+    if (!ctx->have_last) return fail(ctx, HFG_ERR_INVALID, "no E-step has run yet");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(labels, ctx->d_labels, (size_t) ctx->lay.n_windows, cudaMemcpyDeviceToHost));
+    return HFG_OK;
+}
+
+extern "C" int hfg_get_posteriors(hfg_ctx *ctx, double *posteriors) {
+    if (!ctx || !posteriors) return HFG_ERR_INVALID;
+    if (!ctx->have_last) return fail(ctx, HFG_ERR_INVALID, "no E-step has run yet");
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t) ctx->lay.n_windows * 4 * sizeof(double);
+    if (!ctx->d_post) CU(cudaMalloc((void **) &ctx->d_post, bytes));
+    /* the E-step is deterministic: re-running it with the same parameters reproduces the same f^, b^, scales */
+    hfg_region_params *p = (hfg_region_params *) malloc(sizeof(hfg_region_params) * (size_t) ctx->cfg.n_regions);
+    double al[16];
+    memcpy(p, ctx->last_params, sizeof(hfg_region_params) * (size_t) ctx->cfg.n_regions);
+    memcpy(al, ctx->last_alpha, sizeof(al));
+    int rc = enqueue_estep(ctx, al, p, ctx->d_out, ctx->d_post, 0, ctx->stream, 0);
+    free(p);
+    if (rc != HFG_OK) return rc;
+    CU(cudaMemcpyAsync(posteriors, ctx->d_post, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return HFG_OK;
+}
+
+extern "C" int hfg_get_chunk_logliks(hfg_ctx *ctx, double *logliks) {
+    if (!ctx || !logliks) return HFG_ERR_INVALID;
+    if (!ctx->have_last) return fail(ctx, HFG_ERR_INVALID, "no E-step has run yet");
+    CU(cudaSetDevice(ctx->device));
+    const hfg_layout *l = &ctx->lay;
+    double *seg = (double *) malloc(sizeof(double) * (size_t) l->capacity);
+    if (!seg) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+    CU(cudaDeviceSynchronize());
+    cudaError_t e = cudaMemcpy(seg, ctx->d_seg_loglik, sizeof(double) * (size_t) l->capacity, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+        free(seg);
+        return fail(ctx, HFG_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+    }
+    for (int c = 0; c < l->n_chunks; c++) logliks[c] = 0.0;
+    for (int j = 0; j < l->n_seg; j++) logliks[l->seg_chunk[j]] += seg[j]; /* segments are in window order */
+    free(seg);
+    return HFG_OK;
+}
+
+extern "C" double hfg_last_estep_kernel_ms(hfg_ctx *ctx) {
+    if (!ctx || !ctx->ev_valid) return -1.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0;
+    return (double) ms;
+}
+
+extern "C" int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,
+                          double convergence_tol, double *logliks, int *n_esteps, int8_t *labels) {
+    if (!ctx || !params || !logliks || !n_esteps) return HFG_ERR_INVALID;
+    const int R = ctx->cfg.n_regions;
+    hfg_region_stats *stats = (hfg_region_stats *) malloc(sizeof(hfg_region_stats) * (size_t) R);
+    if (!stats) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+    int iter = 1, converged = 0, k = 0, rc = HFG_OK;
+    /* while (iter <= numberOfIterations && converged == false) { E-step; M-step }  (src/hmm_flagger.c:337-431) */
+    while (iter <= max_iterations && !converged) {
+        rc = hfg_em_iteration(ctx, alpha, params, stats, &logliks[k], NULL);
+        if (rc != HFG_OK) break;
+        k++;
+        rc = hfg_mstep(&ctx->cfg, params, stats, convergence_tol, &converged);
+        if (rc != HFG_OK) break;
+        iter++;
+    }
+    /* final inference with the final parameters (src/hmm_flagger.c:464) */
+    if (rc == HFG_OK) {
+        rc = hfg_em_iteration(ctx, alpha, params, stats, &logliks[k], labels);
+        if (rc == HFG_OK) k++;
+    }
+    *n_esteps = k;
+    free(stats);
+    return rc;
+}

@@ -1,0 +1,827 @@
+/*
+ * hfg_estep.cuh -- the E-step kernel of libhfg (sm_100a, fp64, no tensor cores: a 4-state trellis is not a
+ * dense contraction).
+ *
+ * What it replaces: the per-chunk worker of the reference, EM_runForward + EM_runBackward + EM_updateEstimators +
+ * the EM_getMostProbableState loop (submodules/hmm/hmm.c:423-434, 535-545, 638-650, 715-737), for ALL chunks of
+ * one EM_runOneIterationForList call (hmm.c:739-780), in ONE persistent cooperative launch.
+ *
+ * Shape of the computation:
+ *   The reference walks every chunk serially (5-10k dependent 4x4 steps).  Here the whole genome is one sequence
+ *   of windows cut into segments (<= smax windows, never straddling a chunk or a region change); global thread j
+ *   owns segment j.  A chunk start is just a window whose transfer matrix is rank-1 (all rows = the start column),
+ *   so chunks need no special casing in the scan.
+ *     phase A   per thread: evaluate the emission row of each window ONCE (stored segment-transposed for the
+ *               later sweeps) and multiply the window transfer matrices M_i = T_i (.) E_i into the segment
+ *               product P_j (power-of-two rescaled, so the product is exact up to the matmul roundings).
+ *     phase B   matrix scans: warp shuffles -> warps of a block through shared memory -> blocks through global
+ *               memory and ONE grid-wide barrier.  Yields for every segment the forward message entering it and
+ *               the backward message entering it from the right (directions only; see below).
+ *     phase C   per thread: the reference's own scaled forward recurrence inside the segment (f^, c_i and
+ *               sum log c_i), then the backward recurrence fused with the posterior-argmax decode and the pair
+ *               statistics.  The absolute scale of the backward message is recovered from the invariant
+ *               sum_s f^_i[s] b^_i[s] c_i = terminationProb, which holds for every window of the reference's scaling
+ *               (b^_{L-1} = term / c_{L-1}, hmm.c:452-467).
+ *     phase D   deterministic reduction of the statistics: per-thread -> per-block (fixed order) -> grid (fixed
+ *               order, block 0 after a second grid barrier).  No floating-point atomics anywhere.
+ *
+ * Inside a segment the operation ORDER of the reference is kept ((f*t)*e accumulated over preState, etc.); the
+ * results differ from the reference only through the rounding of the entering messages (~1e-16 relative) and
+ * libdevice exp/log (<= 1-2 ulp from glibc).
+ */
+#pragma once
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hfg_internal.h"
+
+namespace cg = cooperative_groups;
+
+#define HFG_THREADS 256
+#define HFG_WARPS (HFG_THREADS / 32)
+
+/* Per-region derived tables in shared memory (doubles):
+ *   [0,128)    conditional transition  Tc[mask][pre*4+s]          (Transition_getProbConditional, hmm_utils.c:2278-2292)
+ *   [128,132)  start probabilities trans[4][s]
+ *   [132,136)  termination probabilities trans[s][4]
+ *   [136,140)  lambda, truncPoint, lambda/beta0, 1-exp(-(lambda/beta0)*(beta0*truncPoint))
+ *   then 6 arrays of G doubles over the flattened Gaussian components g: mu, var, w, var*beta0, 1/(var*beta0),
+ *   w/sqrt(var*beta0*2*PI). */
+#define RT_TC 0
+#define RT_START 128
+#define RT_TERM 132
+#define RT_TEXP 136
+#define RT_GAUSS 140
+#define RT_STRIDE(G) (RT_GAUSS + 6 * (G))
+
+struct EstepArgs {
+    /* run-constant layout */
+    const uint32_t *obsT;
+    const int32_t *seg_start, *seg_len, *seg_edge_begin;
+    const double *edge_beta;
+    int32_t capacity, smax, n_regions;
+    double beta0;
+    /* model structure */
+    int32_t n_classes;              /* D */
+    int32_t cls[HFG_NS][HFG_NS];    /* [pre][s] -> slot */
+    double alpha[HFG_NS][HFG_NS];   /* [pre][s]; 0 for non-Gaussian states */
+    int32_t class_state[HFG_MAX_CLASSES];
+    double class_alpha[HFG_MAX_CLASSES];
+    int32_t zero_slot_used[HFG_NS]; /* does any preState use the alpha==0 slot of state s */
+    int32_t is_gauss[HFG_NS], ncomp[HFG_NS], gbase[HFG_NS];
+    int32_t G;                      /* total Gaussian components */
+    /* per-call inputs / scratch / outputs (device) */
+    const hfg_region_params *params;
+    double *scrE;  /* [smax][D][capacity]  emission rows */
+    double *scrF;  /* [smax][4][capacity]  scaled forward */
+    double *scrC;  /* [smax][capacity]     scales */
+    double *block_tot;   /* [grid][16] */
+    int32_t *block_reset; /* [grid] */
+    double *partials;    /* [grid][R][NSTAT] */
+    double *out;         /* [R * sizeof(hfg_region_stats)/8 + 2]: stats | loglik | error flags (as double) */
+    double *seg_loglik;  /* [capacity] */
+    int8_t *labels;      /* [W] */
+    double *posteriors;  /* [W][4] or NULL */
+    int32_t *err_flags;  /* bit0 scale underflow, bit1 NaN */
+    int32_t forward_only;
+};
+
+/* statistic columns per (block, region): 16 transition counts, lambda num/den, then per Gaussian component
+ * (meanNum, den, varNum), then the log-likelihood (kept in region 0's row). */
+__host__ __device__ inline int hfg_nstat(int G) { return 18 + 3 * G + 1; }
+
+namespace hfgk {
+
+__device__ __forceinline__ double pow2_rescale_factor(double m) {
+    /* 2^-floor(log2 m): an exact scaling, so rescaled products stay exact up to the matmul roundings */
+    const int hi = __double2hiint(m);
+    const int e = (hi >> 20) & 0x7ff;
+    return __hiloint2double((2046 - e) << 20, 0);
+}
+
+__device__ __forceinline__ void mat_rescale(double (&P)[16]) {
+    double m = P[0];
+#pragma unroll
+    for (int i = 1; i < 16; i++) m = fmax(m, P[i]);
+    const double s = pow2_rescale_factor(m);
+#pragma unroll
+    for (int i = 0; i < 16; i++) P[i] *= s;
+}
+
+/* C = A * B (row-major 4x4); scan arithmetic uses fused multiply-adds: no reference order exists for it */
+__device__ __forceinline__ void mat_mul(const double (&A)[16], const double (&B)[16], double (&C)[16]) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            double acc = A[r * 4] * B[c];
+            acc = fma(A[r * 4 + 1], B[4 + c], acc);
+            acc = fma(A[r * 4 + 2], B[8 + c], acc);
+            acc = fma(A[r * 4 + 3], B[12 + c], acc);
+            C[r * 4 + c] = acc;
+        }
+    }
+}
+
+__device__ __forceinline__ void mat_identity(double (&P)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) P[i] = (i % 5 == 0) ? 1.0 : 0.0;
+}
+
+__device__ __forceinline__ void vec_normalize(double (&v)[4]) {
+    const double s = 1.0 / (((v[0] + v[1]) + v[2]) + v[3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) v[i] *= s;
+}
+
+/* v <- v * A */
+__device__ __forceinline__ void vec_mat(double (&v)[4], const double (&A)[16]) {
+    double o[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) o[c] = fma(v[3], A[12 + c], fma(v[2], A[8 + c], fma(v[1], A[4 + c], v[0] * A[c])));
+#pragma unroll
+    for (int c = 0; c < 4; c++) v[c] = o[c];
+}
+
+/* u <- A * u */
+__device__ __forceinline__ void mat_vec(const double (&A)[16], double (&u)[4]) {
+    double o[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        o[r] = fma(A[r * 4 + 3], u[3], fma(A[r * 4 + 2], u[2], fma(A[r * 4 + 1], u[1], A[r * 4] * u[0])));
+#pragma unroll
+    for (int r = 0; r < 4; r++) u[r] = o[r];
+}
+
+__device__ __forceinline__ void mat_shfl_up(const double (&P)[16], double (&Q)[16], int off) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) Q[i] = __shfl_up_sync(0xffffffffu, P[i], off);
+}
+__device__ __forceinline__ void mat_shfl_down(const double (&P)[16], double (&Q)[16], int off) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) Q[i] = __shfl_down_sync(0xffffffffu, P[i], off);
+}
+
+/* inclusive prefix products over the lanes of a warp: P_l <- P_0 * ... * P_l */
+__device__ __forceinline__ void warp_scan_prefix(double (&P)[16], int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        double Q[16], R[16];
+        mat_shfl_up(P, Q, off);
+        if (lane >= off) {
+            mat_mul(Q, P, R);
+            mat_rescale(R);
+#pragma unroll
+            for (int i = 0; i < 16; i++) P[i] = R[i];
+        }
+    }
+}
+
+/* inclusive suffix products: P_l <- P_l * ... * P_31 */
+__device__ __forceinline__ void warp_scan_suffix(double (&P)[16], int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        double Q[16], R[16];
+        mat_shfl_down(P, Q, off);
+        if (lane + off < 32) {
+            mat_mul(P, Q, R);
+            mat_rescale(R);
+#pragma unroll
+            for (int i = 0; i < 16; i++) P[i] = R[i];
+        }
+    }
+}
+
+/* ---- emissions ------------------------------------------------------------------------------------------ */
+
+struct Win {
+    double x, px, beta;
+    int region, mask;
+    bool edge, start, second, region_change, chunk_end;
+};
+
+__device__ __forceinline__ Win decode_word(uint32_t w, double beta0) {
+    Win o;
+    o.x = (double) HFG_OBS_X(w);
+    o.px = (double) HFG_OBS_PX(w);
+    o.region = (int) HFG_OBS_REGION(w);
+    o.mask = (int) HFG_OBS_MASK(w);
+    o.edge = (w & HFG_OBS_EDGE) != 0;
+    o.start = (w & HFG_OBS_CHUNK_START) != 0;
+    o.second = (w & HFG_OBS_SECOND) != 0;
+    o.region_change = (w & HFG_OBS_REGION_CHANGE) != 0;
+    o.chunk_end = (w & HFG_OBS_CHUNK_END) != 0;
+    o.beta = beta0;
+    return o;
+}
+
+/* TruncExponential_getProb (hmm_utils.c:941-947) */
+__device__ __forceinline__ double trunc_exp_prob(const double *rt, const Win &w) {
+    const double trunc = rt[RT_TEXP + 1];
+    if (trunc < w.x) return 0.0;
+    double lam, norm;
+    if (!w.edge) {
+        lam = rt[RT_TEXP + 2];
+        norm = rt[RT_TEXP + 3];
+    } else {
+        lam = rt[RT_TEXP] / w.beta;
+        const double b = w.beta * trunc;
+        norm = 1 - exp(-lam * b);
+    }
+    return lam * exp(-lam * w.x) / norm;
+}
+
+/* one mixture component of Gaussian_getComponentProbs (hmm_utils.c:768-793): mean=((1-a)*mu + a*px)*beta,
+ * var*=beta, w/sqrt(var*2*PI)*exp(-0.5*(x-mean)^2/var), floored at 1e-40; PI is the reference's 3.14159 */
+__device__ __forceinline__ double gauss_comp(const double *rt, int G, int g, double a, const Win &w, int *nan) {
+    const double *ga = rt + RT_GAUSS;
+    double mean = (1 - a) * ga[g] + a * w.px;
+    mean *= w.beta;
+    double inv, coef;
+    if (!w.edge) {
+        inv = ga[4 * G + g];
+        coef = ga[5 * G + g];
+    } else {
+        const double vb = ga[G + g] * w.beta;
+        inv = 1.0 / vb;
+        coef = ga[2 * G + g] / sqrt(vb * 2 * HFG_PI);
+    }
+    const double d = w.x - mean;
+    double p = coef * exp((-0.5 * (d * d)) * inv);
+    if (p != p) *nan = 1;
+    if (p < 1e-40) p = 1e-40;
+    return p;
+}
+
+/* emission of state s under dependency factor a (EmissionDist_getProb, hmm_utils.c:1409-1417) */
+__device__ __forceinline__ double emission(const EstepArgs &A, const double *rt, int s, double a, const Win &w,
+                                           int *nan) {
+    if (!A.is_gauss[s]) return trunc_exp_prob(rt, w);
+    double tot = 0.0;
+    const int n = A.ncomp[s], g0 = A.gbase[s];
+    for (int c = 0; c < n; c++) tot += gauss_comp(rt, A.G, g0 + c, a, w, nan);
+    return tot;
+}
+
+/* transition probability into window w: 1/(N+1) at a region change (hmm.c:398-400), else the masked row */
+__device__ __forceinline__ double trans_prob(const double *rt, const Win &w, int pre, int s) {
+    return w.region_change ? 1.0 / (HFG_NS + 1) : rt[RT_TC + w.mask * 16 + pre * 4 + s];
+}
+
+}  // namespace hfgk
+
+/* ---------------------------------------------------------------------------------------------------------- */
+
+__global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepArgs A) {
+    using namespace hfgk;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double smem[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j = blockIdx.x * HFG_THREADS + tid; /* segment owned by this thread */
+    const int cap = A.capacity, D = A.n_classes, G = A.G, R = A.n_regions;
+    const int rt_stride = RT_STRIDE(G);
+    const int NSTAT = hfg_nstat(G);
+
+    /* shared memory carve-up */
+    double *rtab = smem;                                   /* [R][rt_stride] */
+    double *warp_tot = rtab + (size_t) R * rt_stride;      /* [WARPS][16] warp products */
+    double *warp_pre = warp_tot + HFG_WARPS * 16;          /* [WARPS][16] exclusive prefix over warps */
+    double *warp_suf = warp_pre + HFG_WARPS * 16;          /* [WARPS][16] exclusive suffix over warps */
+    double *blk_vec = warp_suf + HFG_WARPS * 16;           /* [8] entering forward / backward message of the block */
+    double *acc = blk_vec + 8;                             /* [NSTAT][THREADS+1] per-thread statistics */
+    int *treg = (int *) (acc + (size_t) NSTAT * (HFG_THREADS + 1)); /* [THREADS] region of each thread's segment */
+    __shared__ int s_reset;
+
+    /* ---- prologue: derived per-region tables (redundantly per block; O(R*K) work) ---- */
+    if (tid == 0) s_reset = 0;
+    for (int idx = tid; idx < R * 32; idx += HFG_THREADS) {
+        /* one (region, mask, pre) row of the conditional transition table */
+        const int r = idx >> 5, mask = (idx >> 2) & 7, pre = idx & 3;
+        const hfg_region_params &p = A.params[r];
+        bool valid[5] = {true, (mask & 1) == 0, true, (mask & 2) == 0, (mask & 4) != 0};
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+            if (valid[k]) tot += p.trans[pre][k];
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+            rtab[(size_t) r * rt_stride + RT_TC + mask * 16 + pre * 4 + s] = valid[s] ? p.trans[pre][s] / tot : 0.0;
+    }
+    for (int idx = tid; idx < R * (12 + G); idx += HFG_THREADS) {
+        const int r = idx / (12 + G), q = idx % (12 + G);
+        const hfg_region_params &p = A.params[r];
+        double *rt = rtab + (size_t) r * rt_stride;
+        if (q < 4) rt[RT_START + q] = p.trans[HFG_NS][q];
+        else if (q < 8) rt[RT_TERM + q - 4] = p.trans[q - 4][HFG_NS];
+        else if (q == 8) rt[RT_TEXP] = p.lambda;
+        else if (q == 9) rt[RT_TEXP + 1] = p.trunc_point;
+        else if (q == 10) rt[RT_TEXP + 2] = p.lambda / A.beta0;
+        else if (q == 11) {
+            const double lam = p.lambda / A.beta0;
+            const double b = A.beta0 * p.trunc_point;
+            rt[RT_TEXP + 3] = 1 - exp(-lam * b);
+        } else {
+            const int g = q - 12;
+            int s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (A.is_gauss[k] && g >= A.gbase[k] && g < A.gbase[k] + A.ncomp[k]) s = k;
+            const int c = g - A.gbase[s];
+            double *ga = rt + RT_GAUSS;
+            const double vb = p.var[s][c] * A.beta0;
+            ga[g] = p.mean[s][c];
+            ga[G + g] = p.var[s][c];
+            ga[2 * G + g] = p.weight[s][c];
+            ga[3 * G + g] = vb;
+            ga[4 * G + g] = 1.0 / vb;
+            ga[5 * G + g] = p.weight[s][c] / sqrt(vb * 2 * HFG_PI);
+        }
+    }
+    __syncthreads();
+
+    const int len = (j < cap) ? A.seg_len[j] : 0;
+    const int seg_first = (j < cap) ? A.seg_start[j] : 0;
+    int nan_flag = 0, uf_flag = 0;
+    int my_region = 0;
+
+    /* =========================== phase A: emission rows + segment transfer product =========================== */
+    double P[16];
+    mat_identity(P);
+    {
+        int eidx = (j < cap) ? A.seg_edge_begin[j] : 0;
+        bool has_start = false;
+        for (int k = 0; k < len; k++) {
+            const uint32_t word = A.obsT[(size_t) k * cap + j];
+            Win w = decode_word(word, A.beta0);
+            if (w.edge) w.beta = A.edge_beta[eidx++];
+            my_region = w.region;
+            const double *rt = rtab + (size_t) w.region * rt_stride;
+            double *erow = A.scrE + (size_t) k * D * cap + j;
+            double M[16];
+            if (w.start) {
+                /* EM_fillFirstColumnForward (hmm.c:333-364): preX = 0, alpha = 0, start probabilities, no mask */
+                has_start = true;
+                double f0[4];
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    const double e = emission(A, rt, s, 0.0, w, &nan_flag);
+                    erow[(size_t) s * cap] = e;
+                    f0[s] = e * rt[RT_START + s];
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) M[i] = f0[i & 3];
+            } else {
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    double e0 = 0.0;
+                    if (A.zero_slot_used[s]) {
+                        e0 = emission(A, rt, s, 0.0, w, &nan_flag);
+                        erow[(size_t) s * cap] = e0;
+                    }
+#pragma unroll
+                    for (int pre = 0; pre < 4; pre++) M[pre * 4 + s] = e0; /* overwritten below unless slot s */
+                }
+                for (int d = 4; d < D; d++) {
+                    const int s = A.class_state[d];
+                    const double e = emission(A, rt, s, A.class_alpha[d], w, &nan_flag);
+                    erow[(size_t) d * cap] = e;
+#pragma unroll
+                    for (int pre = 0; pre < 4; pre++)
+#pragma unroll
+                        for (int ss = 0; ss < 4; ss++)
+                            if (ss == s && A.cls[pre][ss] == d) M[pre * 4 + ss] = e;
+                }
+#pragma unroll
+                for (int pre = 0; pre < 4; pre++)
+#pragma unroll
+                    for (int s = 0; s < 4; s++) M[pre * 4 + s] = trans_prob(rt, w, pre, s) * M[pre * 4 + s];
+            }
+            double Pn[16];
+            mat_mul(P, M, Pn);
+            mat_rescale(Pn);
+#pragma unroll
+            for (int i = 0; i < 16; i++) P[i] = Pn[i];
+        }
+        if (has_start) s_reset = 1; /* benign race: every writer stores 1 */
+    }
+    treg[tid] = my_region;
+
+    /* =========================== phase B: scans ============================================================= */
+    double v_in[4], u_in[4];
+    {
+        double X[16]; /* exclusive prefix inside the warp, later exclusive suffix */
+        double S[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) S[i] = P[i];
+        warp_scan_prefix(S, lane);
+        if (lane == 31) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) warp_tot[warp * 16 + i] = S[i];
+        }
+        mat_shfl_up(S, X, 1);
+        if (lane == 0) mat_identity(X);
+        /* keep the exclusive prefix in X; build the suffix scan in S */
+#pragma unroll
+        for (int i = 0; i < 16; i++) S[i] = P[i];
+        warp_scan_suffix(S, lane);
+        double Y[16];
+        mat_shfl_down(S, Y, 1);
+        if (lane == 31) mat_identity(Y);
+        __syncthreads();
+
+        /* warp 0: scan the warp products of this block */
+        if (warp == 0) {
+            double Wm[16];
+            if (lane < HFG_WARPS) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) Wm[i] = warp_tot[lane * 16 + i];
+            } else {
+                mat_identity(Wm);
+            }
+            double Sp[16], Ss[16], Q[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) Sp[i] = Ss[i] = Wm[i];
+            warp_scan_prefix(Sp, lane);
+            warp_scan_suffix(Ss, lane);
+            if (lane == HFG_WARPS - 1) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) A.block_tot[(size_t) blockIdx.x * 16 + i] = Sp[i];
+                A.block_reset[blockIdx.x] = s_reset;
+            }
+            mat_shfl_up(Sp, Q, 1);
+            if (lane == 0) mat_identity(Q);
+            if (lane < HFG_WARPS) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) warp_pre[lane * 16 + i] = Q[i];
+            }
+            mat_shfl_down(Ss, Q, 1);
+            if (lane >= HFG_WARPS - 1) mat_identity(Q);
+            if (lane < HFG_WARPS) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) warp_suf[lane * 16 + i] = Q[i];
+            }
+        }
+        __threadfence();
+        grid.sync();
+
+        /* messages entering this block: walk to the nearest block that contains a chunk start (its product is
+         * rank-1, so nothing beyond it matters) */
+        if (tid == 0) {
+            const int b = blockIdx.x, nb = gridDim.x;
+            double v[4] = {0.25, 0.25, 0.25, 0.25};
+            int b0 = b; /* first block whose product is applied */
+            while (b0 > 0) {
+                b0--;
+                if (A.block_reset[b0]) break;
+            }
+            for (int q = b0; q < b; q++) {
+                double T[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
+                vec_mat(v, T);
+                vec_normalize(v);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) blk_vec[i] = v[i];
+        }
+        if (tid == 32) {
+            const int b = blockIdx.x, nb = gridDim.x;
+            double u[4] = {1.0, 1.0, 1.0, 1.0};
+            int b1 = b; /* last block whose product is applied */
+            while (b1 < nb - 1) {
+                b1++;
+                if (A.block_reset[b1]) break;
+            }
+            for (int q = b1; q > b; q--) {
+                double T[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
+                mat_vec(T, u);
+                vec_normalize(u);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) blk_vec[4 + i] = u[i];
+        }
+        __syncthreads();
+
+        double T[16];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v_in[i] = blk_vec[i];
+#pragma unroll
+        for (int i = 0; i < 16; i++) T[i] = warp_pre[warp * 16 + i];
+        vec_mat(v_in, T);
+        vec_normalize(v_in);
+        vec_mat(v_in, X);
+        vec_normalize(v_in);
+
+#pragma unroll
+        for (int i = 0; i < 4; i++) u_in[i] = blk_vec[4 + i];
+#pragma unroll
+        for (int i = 0; i < 16; i++) T[i] = warp_suf[warp * 16 + i];
+        mat_vec(T, u_in);
+        vec_normalize(u_in);
+        mat_vec(Y, u_in);
+        vec_normalize(u_in);
+    }
+
+    /* =========================== phase C1: forward inside the segment ======================================== */
+    double loglik = 0.0;
+    {
+        double f[4] = {v_in[0], v_in[1], v_in[2], v_in[3]};
+        for (int k = 0; k < len; k++) {
+            const uint32_t word = A.obsT[(size_t) k * cap + j];
+            const Win w = decode_word(word, A.beta0);
+            const double *rt = rtab + (size_t) w.region * rt_stride;
+            const double *erow = A.scrE + (size_t) k * D * cap + j;
+            double fn[4];
+            if (w.start) {
+#pragma unroll
+                for (int s = 0; s < 4; s++) fn[s] = erow[(size_t) s * cap] * rt[RT_START + s];
+            } else {
+                double E[16];
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    const double e0 = A.zero_slot_used[s] ? erow[(size_t) s * cap] : 0.0;
+#pragma unroll
+                    for (int pre = 0; pre < 4; pre++) E[pre * 4 + s] = e0;
+                }
+                for (int d = 4; d < D; d++) {
+                    const int s = A.class_state[d];
+                    const double e = erow[(size_t) d * cap];
+#pragma unroll
+                    for (int pre = 0; pre < 4; pre++)
+#pragma unroll
+                        for (int ss = 0; ss < 4; ss++)
+                            if (ss == s && A.cls[pre][ss] == d) E[pre * 4 + ss] = e;
+                }
+                /* f[i][s] = sum_pre (f[i-1][pre] * tProb) * eProb, preState ascending (hmm.c:386-408) */
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    double a = 0.0;
+#pragma unroll
+                    for (int pre = 0; pre < 4; pre++) a += (f[pre] * trans_prob(rt, w, pre, s)) * E[pre * 4 + s];
+                    fn[s] = a;
+                }
+            }
+            const double c = ((fn[0] + fn[1]) + fn[2]) + fn[3];
+            if (!w.start && c < 1e-50) uf_flag = 1; /* "scale is very low" (hmm.c:412-415) */
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                f[s] = fn[s] / c;
+                A.scrF[((size_t) k * 4 + s) * cap + j] = f[s];
+            }
+            A.scrC[(size_t) k * cap + j] = c;
+            loglik += log(c);
+        }
+        if (j < cap) A.seg_loglik[j] = loglik;
+    }
+
+    /* per-thread statistics: registers for the 4x4 counts and the truncated exponential, shared memory
+     * (column tid of acc) for the Gaussian components */
+    double tc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) tc[i] = 0.0;
+    double lam_num = 0.0, lam_den = 0.0;
+    for (int q = 0; q < 3 * G; q++) acc[(size_t) (18 + q) * (HFG_THREADS + 1) + tid] = 0.0;
+
+    /* =========================== phase C2: backward + decode + statistics ===================================== */
+    if (!A.forward_only && len > 0) {
+        int eidx = A.seg_edge_begin[j + 1] - 1;
+        double bh[4];
+        double fh[4], c;
+        {
+            const int k = len - 1;
+#pragma unroll
+            for (int s = 0; s < 4; s++) fh[s] = A.scrF[((size_t) k * 4 + s) * cap + j];
+            c = A.scrC[(size_t) k * cap + j];
+            const uint32_t word = A.obsT[(size_t) k * cap + j];
+            if (word & HFG_OBS_CHUNK_END) {
+                /* EM_fillLastColumnBackward (hmm.c:452-467): b = terminationProb / scale */
+                const double *rt = rtab + (size_t) HFG_OBS_REGION(word) * rt_stride;
+#pragma unroll
+                for (int s = 0; s < 4; s++) bh[s] = rt[RT_TERM + s] / c;
+            } else {
+                /* scale of the entering message from  sum_s f^[s] b^[s] c = terminationProb */
+                const double dot = ((fh[0] * u_in[0] + fh[1] * u_in[1]) + fh[2] * u_in[2]) + fh[3] * u_in[3];
+                const double sc = HFG_TERM_PROB / (c * dot);
+#pragma unroll
+                for (int s = 0; s < 4; s++) bh[s] = u_in[s] * sc;
+            }
+        }
+        for (int k = len - 1; k >= 0; k--) {
+            const uint32_t word = A.obsT[(size_t) k * cap + j];
+            Win w = decode_word(word, A.beta0);
+            if (w.edge) w.beta = A.edge_beta[eidx--];
+            const double *rt = rtab + (size_t) w.region * rt_stride;
+            const int gi = seg_first + k;
+
+            /* decode: EM_getPosterior / EM_getMostProbableState (hmm.c:671-692), first maximum (common.c:292-303) */
+            {
+                double g[4];
+#pragma unroll
+                for (int s = 0; s < 4; s++) g[s] = fh[s] * bh[s] * c;
+                const double tot = ((g[0] + g[1]) + g[2]) + g[3];
+#pragma unroll
+                for (int s = 0; s < 4; s++) g[s] /= tot;
+                int best = 0;
+#pragma unroll
+                for (int s = 1; s < 4; s++)
+                    if (g[best] < g[s]) best = s;
+                A.labels[gi] = (int8_t) best;
+                if (A.posteriors) {
+#pragma unroll
+                    for (int s = 0; s < 4; s++) A.posteriors[(size_t) gi * 4 + s] = g[s];
+                }
+            }
+            if (w.start) break; /* first window of a chunk: nothing to the left */
+
+            /* f^ and scale of the previous window (last window of the previous segment == the entering message) */
+            double fp[4], cp = 1.0;
+            if (k > 0) {
+#pragma unroll
+                for (int s = 0; s < 4; s++) fp[s] = A.scrF[((size_t) (k - 1) * 4 + s) * cap + j];
+                cp = A.scrC[(size_t) (k - 1) * cap + j];
+            } else {
+#pragma unroll
+                for (int s = 0; s < 4; s++) fp[s] = v_in[s];
+            }
+
+            const double *erow = A.scrE + (size_t) k * D * cap + j;
+            double E[16];
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const double e0 = A.zero_slot_used[s] ? erow[(size_t) s * cap] : 0.0;
+#pragma unroll
+                for (int pre = 0; pre < 4; pre++) E[pre * 4 + s] = e0;
+            }
+            for (int d = 4; d < D; d++) {
+                const int s = A.class_state[d];
+                const double e = erow[(size_t) d * cap];
+#pragma unroll
+                for (int pre = 0; pre < 4; pre++)
+#pragma unroll
+                    for (int ss = 0; ss < 4; ss++)
+                        if (ss == s && A.cls[pre][ss] == d) E[pre * 4 + ss] = e;
+            }
+            double Tm[16];
+#pragma unroll
+            for (int pre = 0; pre < 4; pre++)
+#pragma unroll
+                for (int s = 0; s < 4; s++) Tm[pre * 4 + s] = trans_prob(rt, w, pre, s);
+
+            /* pair statistics for (i-1 -> i); the pair 0 -> 1 of every chunk is skipped (hmm.c:638-642) */
+            if (!w.second) {
+                double xi[16];
+#pragma unroll
+                for (int pre = 0; pre < 4; pre++)
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        /* count = f[i][pre] * tProb * eProb * b[i+1][s]; adjusted = count / terminationProb (hmm.c:613-614) */
+                        const double cnt = ((fp[pre] * Tm[pre * 4 + s]) * E[pre * 4 + s]) * bh[s];
+                        xi[pre * 4 + s] = cnt / HFG_TERM_PROB;
+                    }
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    if (!A.is_gauss[s]) {
+                        /* TruncExponential_updateEstimator (hmm_utils.c:1027-1034), preState ascending */
+#pragma unroll
+                        for (int pre = 0; pre < 4; pre++) {
+                            lam_num += xi[pre * 4 + s] * w.x;
+                            lam_den += xi[pre * 4 + s];
+                        }
+                    } else {
+                        /* Gaussian_updateEstimator (hmm_utils.c:812-839) */
+                        const int n = A.ncomp[s], g0 = A.gbase[s];
+                        double pc[HFG_MAX_COMPS]; /* component pdfs of the current (state, alpha) class */
+                        double tot = 0.0;
+#pragma unroll
+                        for (int pre = 0; pre < 4; pre++) {
+                            const double a = A.alpha[pre][s];
+                            const double x_adj = (w.x - a * w.px) / (1.0 - a);
+                            const double cnt = xi[pre * 4 + s];
+                            if (n > 1 && (pre == 0 || A.cls[pre][s] != A.cls[pre - 1][s])) {
+                                /* the reference re-evaluates the component pdfs here (hmm_utils.c:819); preStates that
+                                 * share alpha share them */
+                                tot = 0.0;
+                                for (int cc = 0; cc < n; cc++) {
+                                    pc[cc] = gauss_comp(rt, G, g0 + cc, a, w, &nan_flag);
+                                    tot += pc[cc];
+                                }
+                            }
+                            for (int cc = 0; cc < n; cc++) {
+                                const int g = g0 + cc;
+                                double wgt = cnt;
+                                if (n > 1) wgt = cnt * pc[cc] / tot;
+                                const double z = (x_adj - rt[RT_GAUSS + g]) * (1.0 - a);
+                                double *col = acc + (size_t) (18 + 3 * g) * (HFG_THREADS + 1) + tid;
+                                col[0] += wgt * x_adj;
+                                col[HFG_THREADS + 1] += wgt;
+                                col[2 * (HFG_THREADS + 1)] += wgt * z * z;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) tc[i] += xi[i]; /* TransitionCountData_increment (hmm_utils.c:2010-2015) */
+            }
+
+            if (k > 0) {
+                /* b[i-1][pre] = sum_s tProb*eProb*b[i][s] (state outer, preState inner: hmm.c:493-520), then / scale */
+                double bn[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+#pragma unroll
+                    for (int pre = 0; pre < 4; pre++) bn[pre] += Tm[pre * 4 + s] * E[pre * 4 + s] * bh[s];
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    bh[s] = bn[s] / cp;
+                    fh[s] = fp[s];
+                }
+                c = cp;
+            }
+        }
+    }
+    if (uf_flag) atomicOr(A.err_flags, 1);
+    if (nan_flag) atomicOr(A.err_flags, 2);
+
+    /* =========================== phase D: deterministic reduction ============================================ */
+    {
+        const int ld = HFG_THREADS + 1;
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[(size_t) i * ld + tid] = tc[i];
+        acc[(size_t) 16 * ld + tid] = lam_num;
+        acc[(size_t) 17 * ld + tid] = lam_den;
+        acc[(size_t) (NSTAT - 1) * ld + tid] = loglik;
+        __syncthreads();
+        for (int q = tid; q < R * NSTAT; q += HFG_THREADS) {
+            const int r = q / NSTAT, st = q % NSTAT;
+            const bool is_ll = (st == NSTAT - 1);
+            double sum = 0.0;
+            if (!is_ll || r == 0) {
+                const double *col = acc + (size_t) st * ld;
+                for (int t = 0; t < HFG_THREADS; t++)
+                    if (is_ll || treg[t] == r) sum += col[t];
+            }
+            A.partials[((size_t) blockIdx.x * R + r) * NSTAT + st] = sum;
+        }
+        __threadfence();
+        grid.sync();
+        if (blockIdx.x == 0) {
+            const int SD = (int) (sizeof(hfg_region_stats) / sizeof(double));
+            const int nb = gridDim.x;
+            for (int q = tid; q < R * NSTAT; q += HFG_THREADS) {
+                const int r = q / NSTAT, st = q % NSTAT;
+                double sum = 0.0;
+                for (int b = 0; b < nb; b++) sum += __ldcg(&A.partials[((size_t) b * R + r) * NSTAT + st]);
+                acc[q] = sum; /* reuse shared memory: [R][NSTAT] totals */
+            }
+            __syncthreads();
+            /* scatter into the hfg_region_stats layout (include/hfg.h) */
+            for (int q = tid; q < R * SD; q += HFG_THREADS) A.out[q] = 0.0;
+            __syncthreads();
+            for (int q = tid; q < R * NSTAT; q += HFG_THREADS) {
+                const int r = q / NSTAT, st = q % NSTAT;
+                double *o = A.out + (size_t) r * SD;
+                const double v = acc[q];
+                const int MC = HFG_MAX_COMPS, BL = HFG_NS * HFG_MAX_COMPS;
+                if (st < 16) o[st] = v;                         /* trans_count[pre][s] */
+                else if (st == 16) o[16] = v;                   /* lambda_num */
+                else if (st == 17) o[17] = v;                   /* lambda_den */
+                else if (st == NSTAT - 1) {
+                    if (r == 0) A.out[(size_t) R * SD] = v;     /* log-likelihood */
+                } else {
+                    const int g = (st - 18) / 3, kind = (st - 18) % 3;
+                    int s = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (A.is_gauss[k] && g >= A.gbase[k] && g < A.gbase[k] + A.ncomp[k]) s = k;
+                    const int cc = g - A.gbase[s];
+                    const int at = s * MC + cc;
+                    if (kind == 0) o[18 + 0 * BL + at] = v;      /* mean_num */
+                    else if (kind == 2) o[18 + 2 * BL + at] = v; /* var_num */
+                    else {
+                        o[18 + 1 * BL + at] = v;                 /* mean_den */
+                        o[18 + 3 * BL + at] = v;                 /* var_den  (same addends, same order) */
+                        o[18 + 4 * BL + at] = v;                 /* weight_num */
+                    }
+                }
+            }
+            __syncthreads();
+            /* weight_den[s][c'] = sum over the components of s (ParameterEstimator_incrementDenominatorForAllComps) */
+            if (tid < HFG_NS * R) {
+                const int r = tid / HFG_NS, s = tid % HFG_NS;
+                if (A.is_gauss[s]) {
+                    double *o = A.out + (size_t) r * SD;
+                    const int MC = HFG_MAX_COMPS, BL = HFG_NS * HFG_MAX_COMPS;
+                    double tot = 0.0;
+                    for (int cc = 0; cc < A.ncomp[s]; cc++) tot += o[18 + 1 * BL + s * MC + cc];
+                    for (int cc = 0; cc < A.ncomp[s]; cc++) o[18 + 5 * BL + s * MC + cc] = tot;
+                }
+            }
+            if (tid == 0) A.out[(size_t) R * SD + 1] = (double) __ldcg(A.err_flags);
+        }
+    }
+}

@@ -1,0 +1,205 @@
+/*
+ * hfg_layout.c -- host side of the data layout for the CUDA E-step (plain C, like the reference's host code).
+ *
+ * Turns the reference's per-chunk CoverageInfo sequences (flat u16 arrays at the C-ABI, include/hfg.h) into the
+ * run-constant, segment-transposed packed observation words the kernel streams.  Everything that depends only on
+ * the data -- validity masks (hmm_utils.c:2229-2264), region-change flags (hmm.c:398-400), the contig-end factor
+ * beta (hmm.c:301-316) -- is evaluated ONCE here instead of 3x per window per iteration as in the reference.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+#include "hfg_internal.h"
+
+/* submodules/common/common.c:142-148: min/max are int functions; double arguments are truncated at the call */
+static int imin_(int a, int b) { return a < b ? a : b; }
+static int imax_(int a, int b) { return a < b ? b : a; }
+
+double hfg_beta(const hfg_config *cfg, const hfg_chunk_desc *ch, int i) {
+    if (!cfg->adjust_contig_ends) return 1.0;
+    const double frac = cfg->min_read_fraction_at_ends;
+    const int Lr = cfg->mean_read_length;
+    const int mid = imin_((int) (ch->s + (double) ch->window_len * (i + 0.5)),
+                          (int) ((ch->s + (double) ch->window_len * i + ch->e) / 2));
+    const int lo = imax_(mid - Lr + 1, (int) (-(1 - frac) * Lr));
+    const int hi = imin_(mid, (int) (ch->ctg_len - frac * Lr));
+    const double b = (double) (hi - lo) / Lr;
+    return b <= 0.25 ? 0.25 : b;
+}
+
+static uint32_t validity_mask(const hfg_config *cfg, uint16_t cov, uint16_t mapq, uint16_t clip) {
+    const double rm = (double) mapq / (0.1 + cov);
+    const double rc = (double) clip / (0.1 + cov);
+    uint32_t m = 0;
+    if (rm > cfg->max_high_mapq_ratio) m |= 1u;          /* Dup invalid */
+    if (rm < cfg->min_high_mapq_ratio) m |= 2u;          /* Col invalid */
+    if (!(rc < cfg->min_highly_clipped_ratio)) m |= 4u;  /* END column valid */
+    return m;
+}
+
+void hfg_layout_free(hfg_layout *l) {
+    if (!l) return;
+    free(l->obsT);
+    free(l->seg_start);
+    free(l->seg_len);
+    free(l->seg_chunk);
+    free(l->seg_edge_begin);
+    free(l->edge_beta);
+    free(l->chunk_offset);
+    memset(l, 0, sizeof(*l));
+}
+
+/* number of segments when every (chunk, region-run) is cut into pieces of at most smax windows */
+static int64_t count_segments(int32_t n_chunks, const hfg_chunk_desc *chunks, const uint8_t *region, int smax) {
+    int64_t n = 0;
+    for (int32_t c = 0; c < n_chunks; c++) {
+        const uint8_t *r = region + chunks[c].offset;
+        const int L = chunks[c].n_windows;
+        int i = 0;
+        while (i < L) {
+            int j = i + 1;
+            while (j < L && r[j] == r[i]) j++;
+            n += (j - i + smax - 1) / smax;
+            i = j;
+        }
+    }
+    return n;
+}
+
+int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                     const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
+                     int32_t capacity, hfg_layout *out, char *err, size_t errlen) {
+    memset(out, 0, sizeof(*out));
+    int64_t W = 0;
+    for (int32_t c = 0; c < n_chunks; c++) {
+        if (chunks[c].n_windows <= 0 || chunks[c].offset != W || chunks[c].window_len <= 0) {
+            snprintf(err, errlen, "chunk %d: n_windows must be > 0 and offsets contiguous in list order", c);
+            return HFG_ERR_INVALID;
+        }
+        W += chunks[c].n_windows;
+    }
+    if (W <= 0 || W >= 0x7fffffffLL) {
+        snprintf(err, errlen, "number of windows (%lld) out of range", (long long) W);
+        return HFG_ERR_INVALID;
+    }
+    for (int64_t i = 0; i < W; i++) {
+        if (region[i] >= cfg->n_regions) {
+            snprintf(err, errlen, "window %lld has region %d >= n_regions %d", (long long) i, region[i], cfg->n_regions);
+            return HFG_ERR_INVALID;
+        }
+    }
+    /* smallest smax whose segment count fits the persistent grid */
+    int smax = (int) ((W + capacity - 1) / capacity);
+    if (smax < 1) smax = 1;
+    while (count_segments(n_chunks, chunks, region, smax) > capacity) smax += (smax + 7) / 8;
+    const int64_t n_seg = count_segments(n_chunks, chunks, region, smax);
+
+    out->n_windows = W;
+    out->n_chunks = n_chunks;
+    out->capacity = capacity;
+    out->smax = smax;
+    out->n_seg = (int32_t) n_seg;
+    out->beta0 = !cfg->adjust_contig_ends ? 1.0
+                 : (cfg->mean_read_length > 0 ? (double) (cfg->mean_read_length - 1) / cfg->mean_read_length : 0.25);
+    out->obsT = calloc((size_t) smax * capacity, sizeof(uint32_t));
+    out->seg_start = calloc((size_t) capacity, sizeof(int32_t));
+    out->seg_len = calloc((size_t) capacity, sizeof(int32_t));
+    out->seg_chunk = calloc((size_t) capacity, sizeof(int32_t));
+    out->seg_edge_begin = calloc((size_t) capacity + 1, sizeof(int32_t));
+    out->chunk_offset = calloc((size_t) n_chunks + 1, sizeof(int64_t));
+    int64_t edge_cap = 1024, n_edge = 0;
+    out->edge_beta = malloc(sizeof(double) * (size_t) edge_cap);
+    if (!out->obsT || !out->seg_start || !out->seg_len || !out->seg_chunk || !out->seg_edge_begin ||
+        !out->edge_beta || !out->chunk_offset) {
+        hfg_layout_free(out);
+        snprintf(err, errlen, "out of host memory building the layout");
+        return HFG_ERR_NOMEM;
+    }
+
+    int32_t seg = 0;
+    for (int32_t c = 0; c < n_chunks; c++) {
+        const hfg_chunk_desc *ch = &chunks[c];
+        const int64_t o = ch->offset;
+        const int L = ch->n_windows;
+        out->chunk_offset[c] = o;
+        int i = 0;
+        while (i < L) {
+            int run_end = i + 1;
+            while (run_end < L && region[o + run_end] == region[o + i]) run_end++;
+            for (int a = i; a < run_end; a += smax) {
+                const int len = (run_end - a) < smax ? (run_end - a) : smax;
+                out->seg_start[seg] = (int32_t) (o + a);
+                out->seg_len[seg] = len;
+                out->seg_chunk[seg] = c;
+                out->seg_edge_begin[seg] = (int32_t) n_edge;
+                for (int k = 0; k < len; k++) {
+                    const int w = a + k; /* window index inside the chunk */
+                    const int64_t g = o + w;
+                    uint32_t word = HFG_OBS_VALID;
+                    word |= (uint32_t) (uint8_t) cov[g];
+                    if (w > 0) word |= (uint32_t) (uint8_t) cov[g - 1] << 8;
+                    word |= (uint32_t) region[g] << 16;
+                    word |= validity_mask(cfg, cov[g], cov_high_mapq[g], cov_high_clip[g]) << 22;
+                    if (w > 0 && region[g] != region[g - 1]) word |= HFG_OBS_REGION_CHANGE;
+                    if (w == 0) word |= HFG_OBS_CHUNK_START;
+                    if (w == 1) word |= HFG_OBS_SECOND;
+                    if (w == L - 1) word |= HFG_OBS_CHUNK_END;
+                    const double b = hfg_beta(cfg, ch, w);
+                    if (memcmp(&b, &out->beta0, sizeof(double)) != 0) {
+                        word |= HFG_OBS_EDGE;
+                        if (n_edge == edge_cap) {
+                            edge_cap *= 2;
+                            double *nb = realloc(out->edge_beta, sizeof(double) * (size_t) edge_cap);
+                            if (!nb) {
+                                hfg_layout_free(out);
+                                snprintf(err, errlen, "out of host memory building the layout");
+                                return HFG_ERR_NOMEM;
+                            }
+                            out->edge_beta = nb;
+                        }
+                        out->edge_beta[n_edge++] = b;
+                    }
+                    out->obsT[(size_t) k * capacity + seg] = word;
+                }
+                seg++;
+            }
+            i = run_end;
+        }
+    }
+    out->chunk_offset[n_chunks] = W;
+    for (int32_t j = seg; j <= capacity; j++) out->seg_edge_begin[j] = (int32_t) n_edge;
+    out->n_edge = n_edge;
+    return HFG_OK;
+}
+
+void hfg_classes_build(const hfg_config *cfg, const double *alpha, hfg_classes *out) {
+    memset(out, 0, sizeof(*out));
+    int d = 0;
+    for (int s = 0; s < HFG_NS; s++) {
+        out->is_gaussian[s] = !(cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && s == HFG_STATE_ERR);
+        out->first_class_of_state[s] = d;
+        /* slot s (0..3) must be the alpha == 0 class of state s; so lay the four alpha-0 classes out first */
+        out->class_state[d] = s;
+        out->class_alpha[d] = 0.0;
+        d++;
+    }
+    for (int s = 0; s < HFG_NS; s++) {
+        out->n_class_of_state[s] = 1;
+        for (int pre = 0; pre < HFG_NS; pre++) {
+            const double a = out->is_gaussian[s] ? alpha[pre * HFG_NS + s] : 0.0; /* TruncExp ignores alpha */
+            int slot = -1;
+            if (a == 0.0) slot = s;
+            for (int k = HFG_NS; k < d && slot < 0; k++)
+                if (out->class_state[k] == s && out->class_alpha[k] == a) slot = k;
+            if (slot < 0) {
+                slot = d++;
+                out->class_state[slot] = s;
+                out->class_alpha[slot] = a;
+                out->n_class_of_state[s]++;
+            }
+            out->cls[pre][s] = slot;
+        }
+    }
+    out->n_classes = d;
+}

@@ -1,0 +1,139 @@
+"""GPU parity: the CUDA E-step (through the C-ABI of include/hfg.h) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): per-window labels bit-exact; forward log-likelihoods and posteriors within
+1e-5 relative (we assert far tighter, see TOL_*); statistics and parameters after the M-step likewise.
+"""
+import numpy as np
+import pytest
+
+from flagger_b200 import _abi, api, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_LOGLIK = 1e-9   # relative; north_star allows 1e-5
+TOL_POST = 1e-5     # relative, as north_star states
+TOL_STATS = 1e-9    # relative to the largest statistic of the region
+
+
+def _rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def _check_estep(gpu, oracle_out, wl, alpha, params, label_exact=True):
+    stats, ll, labels = gpu.em_iteration(alpha, params)
+    assert oracle_out["rc"] == 0
+    assert abs(ll - oracle_out["loglik"]) <= TOL_LOGLIK * abs(oracle_out["loglik"])
+    cl = gpu.chunk_logliks()
+    assert np.all(np.abs(cl - oracle_out["chunk_logliks"]) <= 1e-9 * np.abs(oracle_out["chunk_logliks"]) + 1e-9)
+    mism = int((labels != oracle_out["labels"]).sum())
+    if label_exact:
+        assert mism == 0, f"{mism} label mismatches of {wl.n_windows}"
+    post = gpu.posteriors()
+    # relative agreement wherever the posterior is not vanishing; absolute below that
+    big = oracle_out["posteriors"] > 1e-200
+    assert np.all(_rel(post[big], oracle_out["posteriors"][big]) <= TOL_POST)
+    assert np.all(post[~big] <= 1e-190)
+    sg, so = _abi.stats_as_flat(stats), _abi.stats_as_flat(oracle_out["stats"])
+    scale = np.abs(so).max()
+    assert np.all(np.abs(sg - so) <= TOL_STATS * scale), np.abs(sg - so).max() / scale
+    return stats, ll, labels, mism
+
+
+@pytest.mark.parametrize("n_regions,adjust,alpha_name", [
+    (1, True, "hifi"), (3, True, "hifi"), (3, False, "zero"), (1, True, "zero"), (7, True, "hifi"),
+])
+def test_estep_matches_oracle_small(orc, n_regions, adjust, alpha_name):
+    wl = synth.small_mixed(n_regions=n_regions, seed=11 + n_regions)
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=n_regions, n_col_comps=K, adjust_contig_ends=adjust)
+    alpha = synth.HIFI_ALPHA if alpha_name == "hifi" else np.zeros((4, 4))
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    out = orc.estep(cfg, wl, alpha, params)
+    stats, ll, labels, _ = _check_estep(gpu, out, wl, alpha, params)
+    # second iteration from the M-step of the first (parameters no longer symmetric)
+    p2, _ = api.mstep(cfg, params, stats)
+    p2o, _ = orc.mstep(cfg, params, out["stats"])
+    assert np.allclose(_abi.params_as_flat(p2), _abi.params_as_flat(p2o), rtol=1e-9, atol=0)
+    out2 = orc.estep(cfg, wl, alpha, p2o)
+    _check_estep(gpu, out2, wl, alpha, p2o)
+    gpu.close()
+
+
+def test_forward_only_matches(orc):
+    wl = synth.small_mixed(n_regions=3, seed=3)
+    cfg = _abi.make_config(n_regions=3, n_col_comps=4)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    ll = gpu.forward_only(synth.HIFI_ALPHA, params)
+    out = orc.estep(cfg, wl, synth.HIFI_ALPHA, params, forward_only=True)
+    assert abs(ll - out["loglik"]) <= TOL_LOGLIK * abs(out["loglik"])
+    gpu.close()
+
+
+def test_gaussian_model_type(orc):
+    wl = synth.small_mixed(n_regions=1, seed=8)
+    cfg = _abi.make_config(n_regions=1, n_col_comps=3, model_type=_abi.MODEL_GAUSSIAN)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    out = orc.estep(cfg, wl, synth.HIFI_ALPHA, params)
+    _check_estep(gpu, out, wl, synth.HIFI_ALPHA, params)
+    gpu.close()
+
+
+def test_config1_full_em_matches_oracle(orc):
+    """BASELINE.json configs[0]: 1 Mbp contig, 250 windows, 5 EM iterations + final decode."""
+    wl = synth.config1()
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=1, n_col_comps=K)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    pg, llg, labg = gpu.run_em(synth.HIFI_ALPHA, params, 5, tol=1e-12)
+    eo = orc.run_em(cfg, wl, synth.HIFI_ALPHA, params, 5, tol=1e-12)
+    assert len(llg) == len(eo["logliks"]) == 6
+    assert np.all(np.abs(llg - eo["logliks"]) <= TOL_LOGLIK * np.abs(eo["logliks"]))
+    assert np.array_equal(labg, eo["labels"])
+    assert np.allclose(_abi.params_as_flat(pg), _abi.params_as_flat(eo["params"]), rtol=1e-8, atol=0)
+    gpu.close()
+
+
+def test_medium_many_chunks_em(orc):
+    """cfg3 shape at reduced size: 400 contigs x 75 windows, 3 EM iterations, labels bit-exact."""
+    wl = synth.config3(n_contigs=400, seed=21)
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=1, n_col_comps=K)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    pg, llg, labg = gpu.run_em(synth.HIFI_ALPHA, params, 3, tol=1e-12)
+    eo = orc.run_em(cfg, wl, synth.HIFI_ALPHA, params, 3, tol=1e-12)
+    assert np.all(np.abs(llg - eo["logliks"]) <= TOL_LOGLIK * np.abs(eo["logliks"]))
+    assert np.array_equal(labg, eo["labels"])
+    gpu.close()
+
+
+def test_long_chunks_em(orc):
+    """cfg2 shape at reduced size: chr-like contigs cut into 20 Mb chunks (up to 9999 windows per chunk)."""
+    wl = synth.config2(total_bp=300_000_000, seed=22)
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=1, n_col_comps=K)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    out = orc.estep(cfg, wl, synth.HIFI_ALPHA, params)
+    stats, ll, labels, _ = _check_estep(gpu, out, wl, synth.HIFI_ALPHA, params)
+    pg, llg, labg = gpu.run_em(synth.HIFI_ALPHA, params, 3, tol=1e-12)
+    eo = orc.run_em(cfg, wl, synth.HIFI_ALPHA, params, 3, tol=1e-12)
+    assert np.all(np.abs(llg - eo["logliks"]) <= TOL_LOGLIK * np.abs(eo["logliks"]))
+    assert np.array_equal(labg, eo["labels"])
+    gpu.close()
+
+
+def test_determinism():
+    wl = synth.small_mixed(n_regions=3, seed=5)
+    cfg = _abi.make_config(n_regions=3, n_col_comps=4)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    s1, l1, b1 = gpu.em_iteration(synth.HIFI_ALPHA, params)
+    s2, l2, b2 = gpu.em_iteration(synth.HIFI_ALPHA, params)
+    assert l1 == l2 and np.array_equal(b1, b2)
+    assert np.array_equal(_abi.stats_as_flat(s1), _abi.stats_as_flat(s2))
+    gpu.close()
