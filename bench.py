@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- HMM windows/sec for EM iterations of the HMM-Flagger E-step path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|...]
+
+A *step* is one EM iteration over the whole synthetic workload: the E-step of every chunk (forward, backward, pair
+statistics, posterior-argmax labels) plus the host M-step -- what runHMMFlagger does once per iteration
+(reference src/hmm_flagger.c:337-431).  The default K=51 is the job BASELINE.json names: 50 EM iterations + the
+final decode pass, on configs[1] (3 Gbp diploid, 46 chr-sized contigs, 40x, w=4000; ~750k windows).
+
+Prints ONE JSON line (rank 0).  `value` = windows x steps / time with the windows resident in HBM; `e2e` = the same
+through the blocking C-ABI call a host program makes (hfg_set_chunks once + hfg_em_iteration per step: host
+parameters in, host statistics + labels out).  `--impl reference` times the reference's own CPU implementation
+(oracle/_ref, all host threads) on the same workload/metric.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALGO_BYTES_PER_WINDOW = 87  # 3 B obs x 2 sweeps + 40 B f^/scale written + 40 B read + 1 B label
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=51)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "small"])
+    ap.add_argument("--total-bp", type=float, default=3e9)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    return ap.parse_args()
+
+
+def make_workload(name, total_bp):
+    from flagger_b200 import synth
+    if name == "cfg1":
+        return synth.config1()
+    if name == "cfg2":
+        return synth.config2(total_bp=int(total_bp))
+    if name == "cfg3":
+        return synth.config3(n_contigs=int(total_bp // 300_000))
+    if name == "cfg4":
+        return synth.config4(total_bp=int(total_bp))
+    return synth.small_mixed()
+
+
+def shard_chunks(wl, rank, world):
+    """Contiguous chunk ranges in list order, balanced by window count."""
+    if world == 1:
+        return wl
+    n = wl.chunks["n_windows"].astype(np.int64)
+    cum = np.cumsum(n)
+    total = int(cum[-1])
+    bounds = [int(np.searchsorted(cum, total * r / world, side="left")) for r in range(world + 1)]
+    bounds[0], bounds[-1] = 0, len(n)
+    for r in range(1, world + 1):
+        bounds[r] = max(bounds[r], bounds[r - 1])
+    return wl.subset(range(bounds[rank], bounds[rank + 1]), name=f"{wl.name}[rank{rank}/{world}]")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def model_setup(wl):
+    from flagger_b200 import _abi, api, synth
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=wl.n_regions, n_col_comps=K, mean_read_length=wl.avg_alignment_len)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    return cfg, params, synth.HIFI_ALPHA.copy(), K
+
+
+def time_cpu(cfg, wl, alpha, params, steps, warmup, budget_s=90.0):
+    """Reference CPU implementation (oracle/_ref when built, else the restatement): whole EM iterations with all host
+    threads on a bounded sample of the workload (a prefix of its chunks sized to the time budget)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    cores = host_threads()
+    # calibrate the rate on a small prefix
+    n = wl.chunks["n_windows"].astype(np.int64)
+    cum = np.cumsum(n)
+    k0 = int(np.searchsorted(cum, min(40_000, int(cum[-1])), side="left")) + 1
+    probe = wl.subset(range(min(k0, len(n))))
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(2)
+    os.dup2(devnull, 2)  # the reference prints two warnings per M-step
+    try:
+        run = oracle_lib.CpuRun(cfg, probe, alpha, params, cores)
+        run.step()
+        secs, _ = run.step()
+        run.close()
+        rate = probe.n_windows / max(secs, 1e-6)
+        # the largest chunk prefix whose (steps + warmup) iterations fit the budget
+        max_windows = int(rate * budget_s / max(steps + warmup, 1))
+        ks = int(np.searchsorted(cum, max_windows, side="right"))
+        ks = min(max(ks, 1), len(n))
+        sample = wl.subset(range(ks)) if ks < len(n) else wl
+        run = oracle_lib.CpuRun(cfg, sample, alpha, params, cores)
+        for _ in range(warmup):
+            run.step()
+        total = 0.0
+        for _ in range(steps):
+            s, _ = run.step()
+            total += s
+        kind, used = run.kind, run.cores
+        run.close()
+    finally:
+        os.dup2(saved, 2)
+        os.close(devnull)
+        os.close(saved)
+    value = sample.n_windows * steps / total
+    desc = (f"{sample.n_chunks}/{wl.n_chunks} chunks ({sample.n_windows} of {wl.n_windows} windows) of {wl.name}, "
+            f"{steps} EM iterations after {warmup} warm-up, E-step (pthread pool, {used} threads) + M-step")
+    return {"value": value, "unit": "windows/s", "cores": used, "kind": kind, "sample": desc,
+            "ms_per_step": 1e3 * total / steps}, sample
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload(args.workload, args.total_bp)
+    cfg, params, alpha, K = model_setup(wl)
+    cpu, sample = time_cpu(cfg, wl, alpha, params, args.steps, args.warmup, budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": "HMM windows/sec (EM iter + Viterbi), 3 Gbp @40x w=4000; achieved HBM GB/s",
+        "value": cpu["value"], "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.name, "windows": wl.n_windows, "chunks": wl.n_chunks, "regions": wl.n_regions,
+                   "col_components": K, "window_len": wl.window_len, "sample_windows": sample.n_windows,
+                   "note": "CPU reference path; windows/s is size-independent (per-window cost is constant)"},
+        "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cpu["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from flagger_b200 import _abi, api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl_full = make_workload(args.workload, args.total_bp)
+    cfg, params0, alpha, K = model_setup(wl_full)
+    cfg["device"] = local_rank
+    wl = shard_chunks(wl_full, rank, world)
+    W_total = wl_full.n_windows
+    R = wl_full.n_regions
+
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    stats_bytes = gpu.stats_device_bytes()
+    n_d = stats_bytes // 8
+    stats_dev = torch.zeros(n_d, dtype=torch.float64, device=dev)
+    stats_host = torch.zeros(n_d, dtype=torch.float64).pin_memory()
+    stream = torch.cuda.Stream(device=dev)  # an explicit stream: its handle is what the C-ABI launches on
+    torch.cuda.set_stream(stream)
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    SD = _abi.region_stats_dtype.itemsize // 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step(params):
+        """E-step on the device -> [all-reduce over ranks] -> statistics to the host -> host M-step."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        gpu.em_iteration_device(alpha, params, stats_dev.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(stats_dev, op=dist.ReduceOp.SUM)  # one NCCL all-reduce of the EM statistics per iteration
+        stats_host.copy_(stats_dev, non_blocking=True)
+        e1.record(stream)
+        e1.synchronize()
+        t0 = time.perf_counter()
+        flat = stats_host.numpy()
+        if flat[n_d - 1] != 0:
+            raise SystemExit(f"E-step reported error flags {flat[n_d - 1]}")
+        stats = flat[: R * SD].view(_abi.region_stats_dtype)
+        new_params, _ = api.mstep(cfg, params, stats, tol=1e-12)
+        t_host = time.perf_counter() - t0
+        return new_params, e0.elapsed_time(e1) * 1e-3 + t_host, float(flat[n_d - 2]), gpu.last_estep_kernel_ms()
+
+    # ---- resident (value) ----
+    params = params0.copy()
+    for _ in range(args.warmup):
+        params, _, _, _ = resident_step(params)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = gpu.kernel_launches()
+    barrier()
+    step_s, kern_ms, logliks = [], [], []
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1)  # 256 MiB > 126 MB L2: evicts the working set; outside the timed interval
+            torch.cuda.synchronize()
+        params, s, ll, kms = resident_step(params)
+        step_s.append(s)
+        kern_ms.append(kms)
+        logliks.append(ll)
+    barrier()
+    launches = gpu.kernel_launches() - launches0
+    t_total = torch.tensor([sum(step_s)], dtype=torch.float64, device=dev)
+    k_total = torch.tensor([sum(kern_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+        dist.all_reduce(k_total, op=dist.ReduceOp.MAX)
+    t_total, k_total = float(t_total.item()), float(k_total.item())
+
+    # ---- end to end through the blocking C-ABI call with host buffers ----
+    params = params0.copy()
+    labels = np.empty(wl.n_windows, np.int8)
+    stats = np.zeros(R, dtype=_abi.region_stats_dtype)
+    gpu2 = None
+    barrier()
+    t0 = time.perf_counter()
+    gpu2 = api.HmmFlaggerGPU(cfg)
+    gpu2.set_chunks(wl)  # host windows -> packed, segment-transposed words -> HBM (once per job)
+    t_upload = time.perf_counter() - t0
+    e2e_s = []
+    for i in range(args.steps):
+        if flush is not None:
+            flush.fill_(1)
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        stats, ll, labels = gpu2.em_iteration(alpha, params, stats=stats, labels=labels)
+        if world > 1:
+            t = torch.from_numpy(_abi.stats_as_flat(stats)).to(dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            stats = t.cpu().numpy().view(_abi.region_stats_dtype)
+        params, _ = api.mstep(cfg, params, stats, tol=1e-12)
+        e2e_s.append(time.perf_counter() - t0)
+    e2e_total = torch.tensor([sum(e2e_s) + t_upload], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_total = float(e2e_total.item())
+    gpu2.close()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        value = W_total * args.steps / t_total
+        kernel_s = k_total / args.steps * 1e-3
+        achieved = ALGO_BYTES_PER_WINDOW * wl.n_windows / kernel_s / 1e9  # this rank's kernel over its own windows
+        obs_bytes = wl.n_windows * 7  # u16 x3 + u8 region per window handed to hfg_set_chunks
+        line = {
+            "metric": "HMM windows/sec (EM iter + Viterbi), 3 Gbp @40x w=4000; achieved HBM GB/s",
+            "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_full.name, "windows": W_total, "chunks": wl_full.n_chunks, "regions": R,
+                       "col_components": K, "window_len": wl_full.window_len, "alpha": "HiFi_DC_1.2",
+                       "step": "one EM iteration = E-step of all chunks (fwd+bwd+statistics+labels) + host M-step",
+                       "parallelism": f"chunks sharded over {world} GPU(s), one NCCL all-reduce of the statistics per "
+                                      "iteration" if world > 1 else "1 GPU",
+                       "l2": "not flushed" if args.no_flush else "flushed between timed steps (256 MiB fill, untimed)",
+                       "timing": "sum over steps of [CUDA-event interval on the launching stream + host M-step], "
+                                 "max over ranks"},
+            "e2e": {"value": W_total * args.steps / e2e_total, "unit": "windows/s",
+                    "h2d_bytes_per_step": int(params.nbytes + obs_bytes / args.steps),
+                    "d2h_bytes_per_step": int(stats.nbytes + 16 + wl.n_windows),
+                    "includes": "hfg_create + hfg_set_chunks once, then hfg_em_iteration (host params in, host "
+                                "statistics + labels out) + host M-step per step"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "hfg_estep_kernel", "kernel_ms": kernel_s * 1e3,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_WINDOW * wl.n_windows, "peak_source": peak_src},
+            "clocks": clocks,
+            "loglik_first_last": [logliks[0], logliks[-1]],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _ = time_cpu(cfg, wl_full, alpha, params0, steps=2, warmup=1, budget_s=25.0)
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,7 +63,7 @@ static int fail(hfg_ctx *ctx, int code, const char *fmt, ...) {
     } while (0)
 
 static size_t smem_bytes_for(int R, int G) {
-    size_t doubles = (size_t) R * RT_STRIDE(G) + 3 * HFG_WARPS * 16 + 8 + (size_t) hfg_nstat(G) * (HFG_THREADS + 1);
+    size_t doubles = (size_t) R * RT_STRIDE(G) + 3 * HFG_WARPS * 16 + 8 + (size_t) hfg_acc_rows(G) * (HFG_THREADS + 1);
     return doubles * sizeof(double) + HFG_THREADS * sizeof(int);
 }
 
@@ -126,7 +126,7 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         free(ctx);
         return HFG_ERR_CUDA;
     }
-    ctx->max_blocks = ctx->num_sms; /* one persistent CTA per SM (__launch_bounds__(256, 1)) */
+    ctx->max_blocks = ctx->num_sms * (per_sm >= 2 ? 2 : 1); /* persistent CTAs: all co-resident (cooperative launch) */
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         fail(NULL, HFG_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -291,6 +291,18 @@ static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_par
         }
     }
     a.G = g;
+    a.slots_start = 0xfu;
+    a.slots_other = 0;
+    for (int s = 0; s < HFG_NS; s++) {
+        for (int pre = 0; pre < HFG_NS; pre++) {
+            a.slots_other |= 1u << cl.cls[pre][s];
+            a.inv_one_minus_alpha[pre][s] = 1.0 / (1.0 - a.alpha[pre][s]);
+            int first = pre;
+            for (int q = pre - 1; q >= 0; q--)
+                if (cl.cls[q][s] == cl.cls[pre][s]) first = q;
+            a.first_pre_of_class[pre][s] = first;
+        }
+    }
     for (int d = 0; d < HFG_MAX_CLASSES; d++) {
         a.class_state[d] = cl.class_state[d];
         a.class_alpha[d] = cl.class_alpha[d];

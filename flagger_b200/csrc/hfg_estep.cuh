@@ -55,6 +55,7 @@ namespace cg = cooperative_groups;
 #define RT_TEXP 136
 #define RT_GAUSS 140
 #define RT_STRIDE(G) (RT_GAUSS + 6 * (G))
+#define HFG_INV_TERM 1e4 /* 1 / terminationProb */
 
 struct EstepArgs {
     /* run-constant layout */
@@ -72,6 +73,9 @@ struct EstepArgs {
     int32_t zero_slot_used[HFG_NS]; /* does any preState use the alpha==0 slot of state s */
     int32_t is_gauss[HFG_NS], ncomp[HFG_NS], gbase[HFG_NS];
     int32_t G;                      /* total Gaussian components */
+    double inv_one_minus_alpha[HFG_NS][HFG_NS]; /* 1 / (1 - alpha[pre][s]) */
+    int32_t first_pre_of_class[HFG_NS][HFG_NS];  /* [pre][s]: smallest preState sharing the class of (pre, s) */
+    uint32_t slots_start, slots_other;           /* emission slots evaluated at a chunk start / elsewhere */
     /* per-call inputs / scratch / outputs (device) */
     const hfg_region_params *params;
     double *scrE;  /* [smax][D][capacity]  emission rows */
@@ -91,6 +95,8 @@ struct EstepArgs {
 /* statistic columns per (block, region): 16 transition counts, lambda num/den, then per Gaussian component
  * (meanNum, den, varNum), then the log-likelihood (kept in region 0's row). */
 __host__ __device__ inline int hfg_nstat(int G) { return 18 + 3 * G + 1; }
+/* rows of the shared staging area: statistics, or the 32-row scan stash, whichever is larger */
+__host__ __device__ inline int hfg_acc_rows(int G) { return hfg_nstat(G) > 32 ? hfg_nstat(G) : 32; }
 
 namespace hfgk {
 
@@ -164,32 +170,43 @@ __device__ __forceinline__ void mat_shfl_down(const double (&P)[16], double (&Q)
     for (int i = 0; i < 16; i++) Q[i] = __shfl_down_sync(0xffffffffu, P[i], off);
 }
 
+/* A <- A * B, row by row in place (keeps the live set at two matrices + one row) */
+__device__ __forceinline__ void mat_mul_inplace_left(double (&A)[16], const double (&B)[16]) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        double t[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            t[c] = fma(A[r * 4 + 3], B[12 + c], fma(A[r * 4 + 2], B[8 + c], fma(A[r * 4 + 1], B[4 + c], A[r * 4] * B[c])));
+#pragma unroll
+        for (int c = 0; c < 4; c++) A[r * 4 + c] = t[c];
+    }
+}
+
 /* inclusive prefix products over the lanes of a warp: P_l <- P_0 * ... * P_l */
 __device__ __forceinline__ void warp_scan_prefix(double (&P)[16], int lane) {
-#pragma unroll
+#pragma unroll 1
     for (int off = 1; off < 32; off <<= 1) {
-        double Q[16], R[16];
+        double Q[16];
         mat_shfl_up(P, Q, off);
         if (lane >= off) {
-            mat_mul(Q, P, R);
-            mat_rescale(R);
+            mat_mul_inplace_left(Q, P); /* Q <- Q * P : earlier lanes on the left */
+            mat_rescale(Q);
 #pragma unroll
-            for (int i = 0; i < 16; i++) P[i] = R[i];
+            for (int i = 0; i < 16; i++) P[i] = Q[i];
         }
     }
 }
 
 /* inclusive suffix products: P_l <- P_l * ... * P_31 */
 __device__ __forceinline__ void warp_scan_suffix(double (&P)[16], int lane) {
-#pragma unroll
+#pragma unroll 1
     for (int off = 1; off < 32; off <<= 1) {
-        double Q[16], R[16];
+        double Q[16];
         mat_shfl_down(P, Q, off);
         if (lane + off < 32) {
-            mat_mul(P, Q, R);
-            mat_rescale(R);
-#pragma unroll
-            for (int i = 0; i < 16; i++) P[i] = R[i];
+            mat_mul_inplace_left(P, Q);
+            mat_rescale(P);
         }
     }
 }
@@ -274,7 +291,7 @@ __device__ __forceinline__ double trans_prob(const double *rt, const Win &w, int
 
 /* ---------------------------------------------------------------------------------------------------------- */
 
-__global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepArgs A) {
+__global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepArgs A) {
     using namespace hfgk;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double smem[];
@@ -284,6 +301,7 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
     const int cap = A.capacity, D = A.n_classes, G = A.G, R = A.n_regions;
     const int rt_stride = RT_STRIDE(G);
     const int NSTAT = hfg_nstat(G);
+    const int LD = HFG_THREADS + 1;
 
     /* shared memory carve-up */
     double *rtab = smem;                                   /* [R][rt_stride] */
@@ -291,8 +309,9 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
     double *warp_pre = warp_tot + HFG_WARPS * 16;          /* [WARPS][16] exclusive prefix over warps */
     double *warp_suf = warp_pre + HFG_WARPS * 16;          /* [WARPS][16] exclusive suffix over warps */
     double *blk_vec = warp_suf + HFG_WARPS * 16;           /* [8] entering forward / backward message of the block */
-    double *acc = blk_vec + 8;                             /* [NSTAT][THREADS+1] per-thread statistics */
-    int *treg = (int *) (acc + (size_t) NSTAT * (HFG_THREADS + 1)); /* [THREADS] region of each thread's segment */
+    double *acc = blk_vec + 8;                             /* [max(NSTAT,32)][LD]: emission staging (phase A), scan stash
+                                                              (phase B), per-thread statistics (phases C, D) */
+    int *treg = (int *) (acc + (size_t) hfg_acc_rows(G) * LD); /* [THREADS] region of each thread's segment */
     __shared__ int s_reset;
 
     /* ---- prologue: derived per-region tables (redundantly per block; O(R*K) work) ---- */
@@ -342,17 +361,18 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
     }
     __syncthreads();
 
-    const int len = (j < cap) ? A.seg_len[j] : 0;
-    const int seg_first = (j < cap) ? A.seg_start[j] : 0;
+    const int len = A.seg_len[j];
+    const int seg_first = A.seg_start[j];
     int nan_flag = 0, uf_flag = 0;
     int my_region = 0;
 
     /* =========================== phase A: emission rows + segment transfer product =========================== */
-    double P[16];
-    mat_identity(P);
     {
-        int eidx = (j < cap) ? A.seg_edge_begin[j] : 0;
+        double P[16];
+        mat_identity(P);
+        int eidx = A.seg_edge_begin[j];
         bool has_start = false;
+        double *es = acc + tid; /* es[d * LD]: this thread's emission row of the current window */
         for (int k = 0; k < len; k++) {
             const uint32_t word = A.obsT[(size_t) k * cap + j];
             Win w = decode_word(word, A.beta0);
@@ -360,60 +380,42 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
             my_region = w.region;
             const double *rt = rtab + (size_t) w.region * rt_stride;
             double *erow = A.scrE + (size_t) k * D * cap + j;
+            /* evaluate every distinct (state, alpha) class once (the reference evaluates all 16 (pre,state) pairs,
+             * three times per iteration) */
+            const uint32_t slots = w.start ? A.slots_start : A.slots_other;
+            for (int d = 0; d < D; d++) {
+                if (!((slots >> d) & 1u)) continue;
+                const double e = emission(A, rt, A.class_state[d], A.class_alpha[d], w, &nan_flag);
+                erow[(size_t) d * cap] = e;
+                es[d * LD] = e;
+            }
             double M[16];
             if (w.start) {
-                /* EM_fillFirstColumnForward (hmm.c:333-364): preX = 0, alpha = 0, start probabilities, no mask */
+                /* EM_fillFirstColumnForward (hmm.c:333-364): preX = 0, alpha = 0, start probabilities, no mask:
+                 * a rank-1 transfer matrix, every row = the unnormalised first column */
                 has_start = true;
-                double f0[4];
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
-                    const double e = emission(A, rt, s, 0.0, w, &nan_flag);
-                    erow[(size_t) s * cap] = e;
-                    f0[s] = e * rt[RT_START + s];
-                }
+                    const double f0 = es[s * LD] * rt[RT_START + s];
 #pragma unroll
-                for (int i = 0; i < 16; i++) M[i] = f0[i & 3];
+                    for (int pre = 0; pre < 4; pre++) M[pre * 4 + s] = f0;
+                }
             } else {
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    double e0 = 0.0;
-                    if (A.zero_slot_used[s]) {
-                        e0 = emission(A, rt, s, 0.0, w, &nan_flag);
-                        erow[(size_t) s * cap] = e0;
-                    }
-#pragma unroll
-                    for (int pre = 0; pre < 4; pre++) M[pre * 4 + s] = e0; /* overwritten below unless slot s */
-                }
-                for (int d = 4; d < D; d++) {
-                    const int s = A.class_state[d];
-                    const double e = emission(A, rt, s, A.class_alpha[d], w, &nan_flag);
-                    erow[(size_t) d * cap] = e;
-#pragma unroll
-                    for (int pre = 0; pre < 4; pre++)
-#pragma unroll
-                        for (int ss = 0; ss < 4; ss++)
-                            if (ss == s && A.cls[pre][ss] == d) M[pre * 4 + ss] = e;
-                }
 #pragma unroll
                 for (int pre = 0; pre < 4; pre++)
 #pragma unroll
-                    for (int s = 0; s < 4; s++) M[pre * 4 + s] = trans_prob(rt, w, pre, s) * M[pre * 4 + s];
+                    for (int s = 0; s < 4; s++) M[pre * 4 + s] = trans_prob(rt, w, pre, s) * es[A.cls[pre][s] * LD];
             }
-            double Pn[16];
-            mat_mul(P, M, Pn);
-            mat_rescale(Pn);
-#pragma unroll
-            for (int i = 0; i < 16; i++) P[i] = Pn[i];
+            mat_mul_inplace_left(P, M);
+            if ((k & 3) == 3) mat_rescale(P); /* a window shrinks the product by < 1e-50: every 4th step is ample */
         }
+        mat_rescale(P);
         if (has_start) s_reset = 1; /* benign race: every writer stores 1 */
-    }
-    treg[tid] = my_region;
+        treg[tid] = my_region;
+        __syncthreads(); /* the emission staging area is reused as the scan stash below */
 
-    /* =========================== phase B: scans ============================================================= */
-    double v_in[4], u_in[4];
-    {
-        double X[16]; /* exclusive prefix inside the warp, later exclusive suffix */
-        double S[16];
+        /* ======================= phase B: scans ============================================================== */
+        double S[16], Q[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) S[i] = P[i];
         warp_scan_prefix(S, lane);
@@ -421,92 +423,92 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
 #pragma unroll
             for (int i = 0; i < 16; i++) warp_tot[warp * 16 + i] = S[i];
         }
-        mat_shfl_up(S, X, 1);
-        if (lane == 0) mat_identity(X);
-        /* keep the exclusive prefix in X; build the suffix scan in S */
+        mat_shfl_up(S, Q, 1);
+        if (lane == 0) mat_identity(Q);
 #pragma unroll
-        for (int i = 0; i < 16; i++) S[i] = P[i];
-        warp_scan_suffix(S, lane);
-        double Y[16];
-        mat_shfl_down(S, Y, 1);
-        if (lane == 31) mat_identity(Y);
-        __syncthreads();
-
-        /* warp 0: scan the warp products of this block */
-        if (warp == 0) {
-            double Wm[16];
-            if (lane < HFG_WARPS) {
+        for (int i = 0; i < 16; i++) acc[(size_t) i * LD + tid] = Q[i]; /* exclusive prefix inside the warp */
+        warp_scan_suffix(P, lane);
+        mat_shfl_down(P, Q, 1);
+        if (lane == 31) mat_identity(Q);
 #pragma unroll
-                for (int i = 0; i < 16; i++) Wm[i] = warp_tot[lane * 16 + i];
-            } else {
-                mat_identity(Wm);
-            }
-            double Sp[16], Ss[16], Q[16];
+        for (int i = 0; i < 16; i++) acc[(size_t) (16 + i) * LD + tid] = Q[i]; /* exclusive suffix inside the warp */
+    }
+    __syncthreads();
+    /* warp 0: scan the warp products of this block */
+    if (warp == 0) {
+        double Sp[16], Ss[16], Q[16];
+        if (lane < HFG_WARPS) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) Sp[i] = Ss[i] = Wm[i];
-            warp_scan_prefix(Sp, lane);
-            warp_scan_suffix(Ss, lane);
-            if (lane == HFG_WARPS - 1) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) A.block_tot[(size_t) blockIdx.x * 16 + i] = Sp[i];
-                A.block_reset[blockIdx.x] = s_reset;
-            }
-            mat_shfl_up(Sp, Q, 1);
-            if (lane == 0) mat_identity(Q);
-            if (lane < HFG_WARPS) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) warp_pre[lane * 16 + i] = Q[i];
-            }
-            mat_shfl_down(Ss, Q, 1);
-            if (lane >= HFG_WARPS - 1) mat_identity(Q);
-            if (lane < HFG_WARPS) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) warp_suf[lane * 16 + i] = Q[i];
-            }
+            for (int i = 0; i < 16; i++) Sp[i] = Ss[i] = warp_tot[lane * 16 + i];
+        } else {
+            mat_identity(Sp);
+            mat_identity(Ss);
         }
-        __threadfence();
-        grid.sync();
-
-        /* messages entering this block: walk to the nearest block that contains a chunk start (its product is
-         * rank-1, so nothing beyond it matters) */
-        if (tid == 0) {
-            const int b = blockIdx.x, nb = gridDim.x;
-            double v[4] = {0.25, 0.25, 0.25, 0.25};
-            int b0 = b; /* first block whose product is applied */
-            while (b0 > 0) {
-                b0--;
-                if (A.block_reset[b0]) break;
-            }
-            for (int q = b0; q < b; q++) {
-                double T[16];
+        warp_scan_prefix(Sp, lane);
+        warp_scan_suffix(Ss, lane);
+        if (lane == HFG_WARPS - 1) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
-                vec_mat(v, T);
-                vec_normalize(v);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) blk_vec[i] = v[i];
+            for (int i = 0; i < 16; i++) A.block_tot[(size_t) blockIdx.x * 16 + i] = Sp[i];
+            A.block_reset[blockIdx.x] = s_reset;
         }
-        if (tid == 32) {
-            const int b = blockIdx.x, nb = gridDim.x;
-            double u[4] = {1.0, 1.0, 1.0, 1.0};
-            int b1 = b; /* last block whose product is applied */
-            while (b1 < nb - 1) {
-                b1++;
-                if (A.block_reset[b1]) break;
-            }
-            for (int q = b1; q > b; q--) {
-                double T[16];
+        mat_shfl_up(Sp, Q, 1);
+        if (lane == 0) mat_identity(Q);
+        if (lane < HFG_WARPS) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
-                mat_vec(T, u);
-                vec_normalize(u);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) blk_vec[4 + i] = u[i];
+            for (int i = 0; i < 16; i++) warp_pre[lane * 16 + i] = Q[i];
         }
-        __syncthreads();
+        mat_shfl_down(Ss, Q, 1);
+        if (lane >= HFG_WARPS - 1) mat_identity(Q);
+        if (lane < HFG_WARPS) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) warp_suf[lane * 16 + i] = Q[i];
+        }
+    }
+    __threadfence();
+    grid.sync();
 
+    /* messages entering this block: walk to the nearest block that contains a chunk start (its product is rank-1,
+     * so nothing beyond it matters) */
+    if (tid == 0) {
+        const int b = blockIdx.x;
+        double v[4] = {0.25, 0.25, 0.25, 0.25};
+        int b0 = b; /* first block whose product is applied */
+        while (b0 > 0) {
+            b0--;
+            if (__ldcg(&A.block_reset[b0])) break;
+        }
+        for (int q = b0; q < b; q++) {
+            double T[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
+            vec_mat(v, T);
+            vec_normalize(v);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) blk_vec[i] = v[i];
+    }
+    if (tid == 32) {
+        const int b = blockIdx.x, nb = gridDim.x;
+        double u[4] = {1.0, 1.0, 1.0, 1.0};
+        int b1 = b; /* last block whose product is applied */
+        while (b1 < nb - 1) {
+            b1++;
+            if (__ldcg(&A.block_reset[b1])) break;
+        }
+        for (int q = b1; q > b; q--) {
+            double T[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
+            mat_vec(T, u);
+            vec_normalize(u);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) blk_vec[4 + i] = u[i];
+    }
+    __syncthreads();
+
+    double v_in[4], u_in[4];
+    {
         double T[16];
 #pragma unroll
         for (int i = 0; i < 4; i++) v_in[i] = blk_vec[i];
@@ -514,18 +516,22 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
         for (int i = 0; i < 16; i++) T[i] = warp_pre[warp * 16 + i];
         vec_mat(v_in, T);
         vec_normalize(v_in);
-        vec_mat(v_in, X);
+#pragma unroll
+        for (int i = 0; i < 16; i++) T[i] = acc[(size_t) i * LD + tid];
+        vec_mat(v_in, T);
         vec_normalize(v_in);
-
 #pragma unroll
         for (int i = 0; i < 4; i++) u_in[i] = blk_vec[4 + i];
 #pragma unroll
         for (int i = 0; i < 16; i++) T[i] = warp_suf[warp * 16 + i];
         mat_vec(T, u_in);
         vec_normalize(u_in);
-        mat_vec(Y, u_in);
+#pragma unroll
+        for (int i = 0; i < 16; i++) T[i] = acc[(size_t) (16 + i) * LD + tid];
+        mat_vec(T, u_in);
         vec_normalize(u_in);
     }
+    __syncthreads(); /* the stash becomes the statistics area */
 
     /* =========================== phase C1: forward inside the segment ======================================== */
     double loglik = 0.0;
@@ -541,28 +547,13 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
 #pragma unroll
                 for (int s = 0; s < 4; s++) fn[s] = erow[(size_t) s * cap] * rt[RT_START + s];
             } else {
-                double E[16];
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    const double e0 = A.zero_slot_used[s] ? erow[(size_t) s * cap] : 0.0;
-#pragma unroll
-                    for (int pre = 0; pre < 4; pre++) E[pre * 4 + s] = e0;
-                }
-                for (int d = 4; d < D; d++) {
-                    const int s = A.class_state[d];
-                    const double e = erow[(size_t) d * cap];
-#pragma unroll
-                    for (int pre = 0; pre < 4; pre++)
-#pragma unroll
-                        for (int ss = 0; ss < 4; ss++)
-                            if (ss == s && A.cls[pre][ss] == d) E[pre * 4 + ss] = e;
-                }
                 /* f[i][s] = sum_pre (f[i-1][pre] * tProb) * eProb, preState ascending (hmm.c:386-408) */
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
                     double a = 0.0;
 #pragma unroll
-                    for (int pre = 0; pre < 4; pre++) a += (f[pre] * trans_prob(rt, w, pre, s)) * E[pre * 4 + s];
+                    for (int pre = 0; pre < 4; pre++)
+                        a += (f[pre] * trans_prob(rt, w, pre, s)) * erow[(size_t) A.cls[pre][s] * cap];
                     fn[s] = a;
                 }
             }
@@ -576,22 +567,18 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
             A.scrC[(size_t) k * cap + j] = c;
             loglik += log(c);
         }
-        if (j < cap) A.seg_loglik[j] = loglik;
+        A.seg_loglik[j] = loglik;
     }
 
-    /* per-thread statistics: registers for the 4x4 counts and the truncated exponential, shared memory
-     * (column tid of acc) for the Gaussian components */
-    double tc[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) tc[i] = 0.0;
-    double lam_num = 0.0, lam_den = 0.0;
-    for (int q = 0; q < 3 * G; q++) acc[(size_t) (18 + q) * (HFG_THREADS + 1) + tid] = 0.0;
+    /* per-thread statistics live in column tid of acc: rows 0..15 transition counts, 16..17 truncated exponential,
+     * 18+3g.. (meanNum, den, varNum) of Gaussian component g, last row the log-likelihood */
+    for (int q = 0; q < NSTAT; q++) acc[(size_t) q * LD + tid] = 0.0;
+    double *col = acc + tid;
 
     /* =========================== phase C2: backward + decode + statistics ===================================== */
     if (!A.forward_only && len > 0) {
         int eidx = A.seg_edge_begin[j + 1] - 1;
-        double bh[4];
-        double fh[4], c;
+        double bh[4], fh[4], c;
         {
             const int k = len - 1;
 #pragma unroll
@@ -623,18 +610,20 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
                 double g[4];
 #pragma unroll
                 for (int s = 0; s < 4; s++) g[s] = fh[s] * bh[s] * c;
-                const double tot = ((g[0] + g[1]) + g[2]) + g[3];
+                if (A.posteriors) {
+                    const double tot = ((g[0] + g[1]) + g[2]) + g[3];
 #pragma unroll
-                for (int s = 0; s < 4; s++) g[s] /= tot;
+                    for (int s = 0; s < 4; s++) {
+                        g[s] /= tot;
+                        A.posteriors[(size_t) gi * 4 + s] = g[s];
+                    }
+                }
+                /* dividing all four by the same total does not change their order */
                 int best = 0;
 #pragma unroll
                 for (int s = 1; s < 4; s++)
                     if (g[best] < g[s]) best = s;
                 A.labels[gi] = (int8_t) best;
-                if (A.posteriors) {
-#pragma unroll
-                    for (int s = 0; s < 4; s++) A.posteriors[(size_t) gi * 4 + s] = g[s];
-                }
             }
             if (w.start) break; /* first window of a chunk: nothing to the left */
 
@@ -648,93 +637,70 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
 #pragma unroll
                 for (int s = 0; s < 4; s++) fp[s] = v_in[s];
             }
-
             const double *erow = A.scrE + (size_t) k * D * cap + j;
-            double E[16];
+            double bn[4] = {0.0, 0.0, 0.0, 0.0};
+            const bool do_stats = !w.second; /* the pair 0 -> 1 of every chunk is skipped (hmm.c:638-642) */
 #pragma unroll
             for (int s = 0; s < 4; s++) {
-                const double e0 = A.zero_slot_used[s] ? erow[(size_t) s * cap] : 0.0;
+                double xi[4]; /* adjusted pair counts into state s, by preState */
 #pragma unroll
-                for (int pre = 0; pre < 4; pre++) E[pre * 4 + s] = e0;
-            }
-            for (int d = 4; d < D; d++) {
-                const int s = A.class_state[d];
-                const double e = erow[(size_t) d * cap];
+                for (int pre = 0; pre < 4; pre++) {
+                    const double t = trans_prob(rt, w, pre, s);
+                    const double e = erow[(size_t) A.cls[pre][s] * cap];
+                    /* b[i-1][pre] += tProb*eProb*b[i][s] (state outer, preState inner: hmm.c:493-520) */
+                    bn[pre] += t * e * bh[s];
+                    /* count = f[i][pre]*tProb*eProb*b[i+1][s]; adjusted = count / terminationProb (hmm.c:613-614) */
+                    xi[pre] = (((fp[pre] * t) * e) * bh[s]) * HFG_INV_TERM;
+                }
+                if (!do_stats) continue;
 #pragma unroll
-                for (int pre = 0; pre < 4; pre++)
+                for (int pre = 0; pre < 4; pre++) col[(pre * 4 + s) * LD] += xi[pre]; /* hmm_utils.c:2010-2015 */
+                if (!A.is_gauss[s]) {
+                    /* TruncExponential_updateEstimator (hmm_utils.c:1027-1034) */
+                    const double sum = ((xi[0] + xi[1]) + xi[2]) + xi[3];
+                    col[16 * LD] += sum * w.x;
+                    col[17 * LD] += sum;
+                } else {
+                    /* Gaussian_updateEstimator (hmm_utils.c:812-839), grouped by (state, alpha) class: preStates that
+                     * share alpha share x_adjusted, z and the component responsibilities */
+                    const int n = A.ncomp[s], g0 = A.gbase[s];
 #pragma unroll
-                    for (int ss = 0; ss < 4; ss++)
-                        if (ss == s && A.cls[pre][ss] == d) E[pre * 4 + ss] = e;
-            }
-            double Tm[16];
+                    for (int pre = 0; pre < 4; pre++) {
+                        if (A.first_pre_of_class[pre][s] != pre) continue;
+                        double cnt = xi[pre];
 #pragma unroll
-            for (int pre = 0; pre < 4; pre++)
-#pragma unroll
-                for (int s = 0; s < 4; s++) Tm[pre * 4 + s] = trans_prob(rt, w, pre, s);
-
-            /* pair statistics for (i-1 -> i); the pair 0 -> 1 of every chunk is skipped (hmm.c:638-642) */
-            if (!w.second) {
-                double xi[16];
-#pragma unroll
-                for (int pre = 0; pre < 4; pre++)
-#pragma unroll
-                    for (int s = 0; s < 4; s++) {
-                        /* count = f[i][pre] * tProb * eProb * b[i+1][s]; adjusted = count / terminationProb (hmm.c:613-614) */
-                        const double cnt = ((fp[pre] * Tm[pre * 4 + s]) * E[pre * 4 + s]) * bh[s];
-                        xi[pre * 4 + s] = cnt / HFG_TERM_PROB;
-                    }
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    if (!A.is_gauss[s]) {
-                        /* TruncExponential_updateEstimator (hmm_utils.c:1027-1034), preState ascending */
-#pragma unroll
-                        for (int pre = 0; pre < 4; pre++) {
-                            lam_num += xi[pre * 4 + s] * w.x;
-                            lam_den += xi[pre * 4 + s];
-                        }
-                    } else {
-                        /* Gaussian_updateEstimator (hmm_utils.c:812-839) */
-                        const int n = A.ncomp[s], g0 = A.gbase[s];
-                        double pc[HFG_MAX_COMPS]; /* component pdfs of the current (state, alpha) class */
-                        double tot = 0.0;
-#pragma unroll
-                        for (int pre = 0; pre < 4; pre++) {
-                            const double a = A.alpha[pre][s];
-                            const double x_adj = (w.x - a * w.px) / (1.0 - a);
-                            const double cnt = xi[pre * 4 + s];
-                            if (n > 1 && (pre == 0 || A.cls[pre][s] != A.cls[pre - 1][s])) {
-                                /* the reference re-evaluates the component pdfs here (hmm_utils.c:819); preStates that
-                                 * share alpha share them */
-                                tot = 0.0;
-                                for (int cc = 0; cc < n; cc++) {
-                                    pc[cc] = gauss_comp(rt, G, g0 + cc, a, w, &nan_flag);
-                                    tot += pc[cc];
-                                }
-                            }
+                        for (int p2 = pre + 1; p2 < 4; p2++)
+                            if (A.first_pre_of_class[p2][s] == pre) cnt += xi[p2];
+                        const double a = A.alpha[pre][s];
+                        const double x_adj = (w.x - a * w.px) * A.inv_one_minus_alpha[pre][s];
+                        if (n == 1) {
+                            const double z = (x_adj - rt[RT_GAUSS + g0]) * (1.0 - a);
+                            double *cg_ = col + (size_t) (18 + 3 * g0) * LD;
+                            cg_[0] += cnt * x_adj;
+                            cg_[LD] += cnt;
+                            cg_[2 * LD] += cnt * z * z;
+                        } else {
+                            /* responsibilities need the component pdfs again (hmm_utils.c:819) */
+                            double pc[HFG_MAX_COMPS];
+                            double tot = 0.0;
                             for (int cc = 0; cc < n; cc++) {
-                                const int g = g0 + cc;
-                                double wgt = cnt;
-                                if (n > 1) wgt = cnt * pc[cc] / tot;
-                                const double z = (x_adj - rt[RT_GAUSS + g]) * (1.0 - a);
-                                double *col = acc + (size_t) (18 + 3 * g) * (HFG_THREADS + 1) + tid;
-                                col[0] += wgt * x_adj;
-                                col[HFG_THREADS + 1] += wgt;
-                                col[2 * (HFG_THREADS + 1)] += wgt * z * z;
+                                pc[cc] = gauss_comp(rt, G, g0 + cc, a, w, &nan_flag);
+                                tot += pc[cc];
+                            }
+                            const double scale = cnt / tot;
+                            for (int cc = 0; cc < n; cc++) {
+                                const double wgt = scale * pc[cc];
+                                const double z = (x_adj - rt[RT_GAUSS + g0 + cc]) * (1.0 - a);
+                                double *cg_ = col + (size_t) (18 + 3 * (g0 + cc)) * LD;
+                                cg_[0] += wgt * x_adj;
+                                cg_[LD] += wgt;
+                                cg_[2 * LD] += wgt * z * z;
                             }
                         }
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < 16; i++) tc[i] += xi[i]; /* TransitionCountData_increment (hmm_utils.c:2010-2015) */
             }
-
             if (k > 0) {
-                /* b[i-1][pre] = sum_s tProb*eProb*b[i][s] (state outer, preState inner: hmm.c:493-520), then / scale */
-                double bn[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-                for (int s = 0; s < 4; s++)
-#pragma unroll
-                    for (int pre = 0; pre < 4; pre++) bn[pre] += Tm[pre * 4 + s] * E[pre * 4 + s] * bh[s];
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
                     bh[s] = bn[s] / cp;
@@ -749,21 +715,16 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
 
     /* =========================== phase D: deterministic reduction ============================================ */
     {
-        const int ld = HFG_THREADS + 1;
-#pragma unroll
-        for (int i = 0; i < 16; i++) acc[(size_t) i * ld + tid] = tc[i];
-        acc[(size_t) 16 * ld + tid] = lam_num;
-        acc[(size_t) 17 * ld + tid] = lam_den;
-        acc[(size_t) (NSTAT - 1) * ld + tid] = loglik;
+        col[(size_t) (NSTAT - 1) * LD] = loglik;
         __syncthreads();
         for (int q = tid; q < R * NSTAT; q += HFG_THREADS) {
             const int r = q / NSTAT, st = q % NSTAT;
             const bool is_ll = (st == NSTAT - 1);
             double sum = 0.0;
             if (!is_ll || r == 0) {
-                const double *col = acc + (size_t) st * ld;
+                const double *cl = acc + (size_t) st * LD;
                 for (int t = 0; t < HFG_THREADS; t++)
-                    if (is_ll || treg[t] == r) sum += col[t];
+                    if (is_ll || treg[t] == r) sum += cl[t];
             }
             A.partials[((size_t) blockIdx.x * R + r) * NSTAT + st] = sum;
         }
@@ -778,10 +739,9 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
                 for (int b = 0; b < nb; b++) sum += __ldcg(&A.partials[((size_t) b * R + r) * NSTAT + st]);
                 acc[q] = sum; /* reuse shared memory: [R][NSTAT] totals */
             }
-            __syncthreads();
-            /* scatter into the hfg_region_stats layout (include/hfg.h) */
             for (int q = tid; q < R * SD; q += HFG_THREADS) A.out[q] = 0.0;
             __syncthreads();
+            /* scatter into the hfg_region_stats layout (include/hfg.h) */
             for (int q = tid; q < R * NSTAT; q += HFG_THREADS) {
                 const int r = q / NSTAT, st = q % NSTAT;
                 double *o = A.out + (size_t) r * SD;

@@ -493,3 +493,55 @@ done:
     free(stats);
     return status;
 }
+
+/* persistent handle for benchmarking (mirrors ref_open/ref_step/ref_close of ref_harness.c): whole EM iterations
+ * of the restatement, single-threaded */
+typedef struct OrcRun {
+    hfg_config cfg;
+    int n_chunks;
+    const hfg_chunk_desc *chunks;
+    const uint16_t *cov, *mapq, *clip;
+    const uint8_t *region;
+    double alpha[16];
+    hfg_region_params *params;
+    hfg_region_stats *stats;
+} OrcRun;
+
+void *orc_open(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *cd, const uint16_t *cov,
+               const uint16_t *mapq, const uint16_t *clip, const uint8_t *region, const double *alpha,
+               const hfg_region_params *params) {
+    OrcRun *r = calloc(1, sizeof(OrcRun));
+    r->cfg = *cfg;
+    r->n_chunks = n_chunks;
+    r->chunks = cd;
+    r->cov = cov;
+    r->mapq = mapq;
+    r->clip = clip;
+    r->region = region;
+    memcpy(r->alpha, alpha, sizeof(r->alpha));
+    r->params = malloc(sizeof(hfg_region_params) * (size_t) cfg->n_regions);
+    memcpy(r->params, params, sizeof(hfg_region_params) * (size_t) cfg->n_regions);
+    r->stats = calloc((size_t) cfg->n_regions, sizeof(hfg_region_stats));
+    return r;
+}
+
+#include <time.h>
+double orc_step(void *handle, int threads, double tol, double *loglik) {
+    (void) threads;
+    OrcRun *r = handle;
+    struct timespec t0, t1;
+    int conv = 0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    orc_estep(&r->cfg, r->n_chunks, r->chunks, r->cov, r->mapq, r->clip, r->region, r->alpha, r->params, r->stats,
+              loglik, NULL, NULL, NULL, NULL, NULL, NULL, 0);
+    orc_mstep(&r->cfg, r->params, r->stats, tol, &conv);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+void orc_close(void *handle) {
+    OrcRun *r = handle;
+    free(r->params);
+    free(r->stats);
+    free(r);
+}

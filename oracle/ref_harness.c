@@ -313,3 +313,25 @@ int ref_run_em(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *cd, co
     teardown(d);
     return 0;
 }
+
+/* persistent handle for benchmarking: build the reference structs once, then time whole EM iterations
+ * (EM_runOneIterationForList + HMM_estimateParameters + HMM_resetEstimators, src/hmm_flagger.c:344,419,425) */
+void *ref_open(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *cd, const uint16_t *cov,
+               const uint16_t *mapq, const uint16_t *clip, const uint8_t *region, const double *alpha,
+               const hfg_region_params *params) {
+    return build(cfg, n_chunks, cd, cov, mapq, clip, region, alpha, params);
+}
+
+double ref_step(void *handle, int threads, double tol, double *loglik) {
+    RefData *d = handle;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    EM_runOneIterationForList(d->ems, d->model, threads);
+    if (loglik) *loglik = d->model->loglikelihood;
+    HMM_estimateParameters(d->model, tol);
+    HMM_resetEstimators(d->model);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
+
+void ref_close(void *handle) { teardown(handle); }

@@ -103,3 +103,35 @@ def reference(threads=1):
     """The unmodified reference behind ref_harness.c, or None when oracle/_ref has not been built."""
     lib = _load(os.path.join(ORACLE_DIR, "_ref", "libref_harness.so"))
     return _Checker(lib, "ref", threads=threads) if lib is not None else None
+
+
+class CpuRun:
+    """Persistent CPU run (reference objects when available, else the restatement) for timing whole EM iterations.
+    Used only by bench.py's cpu_baseline / `--impl reference` legs."""
+
+    def __init__(self, cfg, wl, alpha, params, threads):
+        ref_lib = _load(os.path.join(ORACLE_DIR, "_ref", "libref_harness.so"))
+        if ref_lib is not None:
+            self.lib, self.prefix, self.kind, self.cores = ref_lib, "ref", "reference", int(threads)
+        else:
+            self.lib, self.prefix, self.kind, self.cores = oracle().lib, "orc", "port", 1
+        self.wl = wl  # keep the arrays alive
+        self.cfg = np.ascontiguousarray(cfg)
+        self.alpha = np.ascontiguousarray(alpha, np.float64)
+        self.params = np.ascontiguousarray(params)
+        fn = getattr(self.lib, f"{self.prefix}_open")
+        fn.restype = C.c_void_p
+        self.h = C.c_void_p(fn(ptr(self.cfg), C.c_int(wl.n_chunks), ptr(wl.chunks), ptr(wl.cov), ptr(wl.cov_high_mapq),
+                               ptr(wl.cov_high_clip), ptr(wl.region), ptr(self.alpha), ptr(self.params)))
+        self._step = getattr(self.lib, f"{self.prefix}_step")
+        self._step.restype = C.c_double
+
+    def step(self, tol=1e-12):
+        ll = C.c_double(0.0)
+        secs = self._step(self.h, C.c_int(self.cores), C.c_double(tol), C.byref(ll))
+        return float(secs), ll.value
+
+    def close(self):
+        if self.h:
+            getattr(self.lib, f"{self.prefix}_close")(self.h)
+            self.h = None
