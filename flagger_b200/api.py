@@ -49,7 +49,7 @@ EXPORTED_SYMBOLS = (
     "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_chunks", "hfg_num_windows", "hfg_em_iteration",
     "hfg_forward_only", "hfg_get_posteriors", "hfg_get_chunk_logliks", "hfg_em_iteration_device",
     "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
-    "hfg_run_em", "hfg_kernel_launches", "hfg_last_estep_kernel_ms",
+    "hfg_run_em", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_debug_phase_clocks", "hfg_debug_exp",
 )
 
 
@@ -169,6 +169,18 @@ class HmmFlaggerGPU:
         self._check(lib().hfg_run_em(self._h, ptr(alpha), ptr(params), C.c_int(max_iterations), C.c_double(tol),
                                      ptr(logliks), C.byref(n), ptr(labels)))
         return params, logliks[:n.value].copy(), labels
+
+    def debug_exp(self, q):
+        q = np.ascontiguousarray(q, np.float64)
+        out = np.empty_like(q)
+        self._check(lib().hfg_debug_exp(self._h, ptr(q), ptr(out), C.c_int(q.size)))
+        return out
+
+    def debug_phase_clocks(self):
+        buf = np.zeros((4096, 10), np.int64)
+        g = C.c_int(0)
+        self._check(lib().hfg_debug_phase_clocks(self._h, ptr(buf), C.byref(g)))
+        return buf[: g.value].copy()
 
     def kernel_launches(self):
         return int(lib().hfg_kernel_launches(self._h))

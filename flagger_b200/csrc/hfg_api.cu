@@ -32,6 +32,7 @@ struct hfg_ctx {
     double *d_edge_beta, *d_scrE, *d_scrF, *d_scrC, *d_block_tot, *d_partials, *d_out, *d_seg_loglik, *d_post;
     hfg_region_params *d_params[STAGE_SLOTS];
     int8_t *d_labels;
+    long long *d_phase_clock;
     /* pinned host staging */
     hfg_region_params *h_params[STAGE_SLOTS];
     cudaEvent_t stage_ev[STAGE_SLOTS];
@@ -62,8 +63,16 @@ static int fail(hfg_ctx *ctx, int code, const char *fmt, ...) {
             return fail(ctx, HFG_ERR_CUDA, "%s failed: %s (no CPU fallback exists)", #call, cudaGetErrorString(e_)); \
     } while (0)
 
-static size_t smem_bytes_for(int R, int G) {
-    size_t doubles = (size_t) R * RT_STRIDE(G) + 3 * HFG_WARPS * 16 + 8 + (size_t) hfg_acc_rows(G) * (HFG_THREADS + 1);
+/* worst-case number of component evaluations of an ordinary window: every Gaussian state with four distinct alphas */
+static int max_tasks(const hfg_config *cfg) {
+    int n = 0;
+    for (int s = 0; s < HFG_NS; s++)
+        if (!(cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && s == HFG_STATE_ERR)) n += 4 * cfg->n_comps[s];
+    return n;
+}
+
+static size_t smem_bytes_for(int R, int G, int NT) {
+    size_t doubles = (size_t) R * RT_STRIDE2(G, NT) + 3 * HFG_WARPS * 16 + 8 + (size_t) hfg_acc_rows(G) * (HFG_THREADS + 1);
     return doubles * sizeof(double) + HFG_THREADS * sizeof(int);
 }
 
@@ -107,7 +116,12 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     }
     ctx->num_sms = prop.multiProcessorCount;
     const int G = total_gauss_comps(cfg);
-    ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G);
+    ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg));
+    if (max_tasks(cfg) > HFG_MAX_TASKS) {
+        fail(NULL, HFG_ERR_INVALID, "too many mixture components (%d component evaluations per window, limit %d)", max_tasks(cfg), HFG_MAX_TASKS);
+        free(ctx);
+        return HFG_ERR_INVALID;
+    }
     if (ctx->smem_bytes > (size_t) prop.sharedMemPerBlockOptin) {
         fail(NULL, HFG_ERR_INVALID, "model too large for shared memory: %zu bytes needed for %d regions x %d components, %zu available",
              ctx->smem_bytes, cfg->n_regions, G, (size_t) prop.sharedMemPerBlockOptin);
@@ -153,6 +167,7 @@ static void free_device(hfg_ctx *ctx) {
     cudaFree(ctx->d_block_reset); cudaFree(ctx->d_err); cudaFree(ctx->d_edge_beta); cudaFree(ctx->d_scrE);
     cudaFree(ctx->d_scrF); cudaFree(ctx->d_scrC); cudaFree(ctx->d_block_tot); cudaFree(ctx->d_partials);
     cudaFree(ctx->d_out); cudaFree(ctx->d_seg_loglik); cudaFree(ctx->d_post); cudaFree(ctx->d_labels);
+    cudaFree(ctx->d_phase_clock); ctx->d_phase_clock = NULL;
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     ctx->d_obsT = NULL; ctx->d_seg_start = ctx->d_seg_len = ctx->d_seg_edge_begin = ctx->d_block_reset = ctx->d_err = NULL;
     ctx->d_edge_beta = ctx->d_scrE = ctx->d_scrF = ctx->d_scrC = ctx->d_block_tot = ctx->d_partials = NULL;
@@ -214,7 +229,7 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     CU(cudaMalloc((void **) &ctx->d_seg_start, cap * sizeof(int32_t)));
     CU(cudaMalloc((void **) &ctx->d_seg_len, cap * sizeof(int32_t)));
     CU(cudaMalloc((void **) &ctx->d_seg_edge_begin, ((size_t) cap + 1) * sizeof(int32_t)));
-    CU(cudaMalloc((void **) &ctx->d_edge_beta, (size_t) (l->n_edge > 0 ? l->n_edge : 1) * sizeof(double)));
+    CU(cudaMalloc((void **) &ctx->d_edge_beta, (size_t) (l->n_edge > 0 ? l->n_edge : 1) * 3 * sizeof(double)));
     CU(cudaMalloc((void **) &ctx->d_scrE, slots * HFG_MAX_CLASSES * sizeof(double)));
     CU(cudaMalloc((void **) &ctx->d_scrF, slots * 4 * sizeof(double)));
     CU(cudaMalloc((void **) &ctx->d_scrC, slots * sizeof(double)));
@@ -225,6 +240,7 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     CU(cudaMalloc((void **) &ctx->d_seg_loglik, cap * sizeof(double)));
     CU(cudaMalloc((void **) &ctx->d_labels, (size_t) l->n_windows));
     CU(cudaMalloc((void **) &ctx->d_err, sizeof(int32_t)));
+    CU(cudaMalloc((void **) &ctx->d_phase_clock, (size_t) ctx->grid * 10 * sizeof(long long)));
     CU(cudaMallocHost((void **) &ctx->h_out, out_doubles * sizeof(double)));
     CU(cudaMemcpyAsync(ctx->d_obsT, l->obsT, slots * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_start, l->seg_start, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -232,7 +248,7 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     CU(cudaMemcpyAsync(ctx->d_seg_edge_begin, l->seg_edge_begin, ((size_t) cap + 1) * sizeof(int32_t),
                        cudaMemcpyHostToDevice, ctx->stream));
     if (l->n_edge > 0)
-        CU(cudaMemcpyAsync(ctx->d_edge_beta, l->edge_beta, (size_t) l->n_edge * sizeof(double), cudaMemcpyHostToDevice,
+        CU(cudaMemcpyAsync(ctx->d_edge_beta, l->edge_beta, (size_t) l->n_edge * 3 * sizeof(double), cudaMemcpyHostToDevice,
                            ctx->stream));
     CU(cudaMemsetAsync(ctx->d_labels, 0xff, (size_t) l->n_windows, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -291,6 +307,8 @@ static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_par
         }
     }
     a.G = g;
+    a.n_tasks = 0;
+    a.texp_slot = -1;
     a.slots_start = 0xfu;
     a.slots_other = 0;
     for (int s = 0; s < HFG_NS; s++) {
@@ -307,6 +325,23 @@ static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_par
         a.class_state[d] = cl.class_state[d];
         a.class_alpha[d] = cl.class_alpha[d];
     }
+    for (int d = 0; d < cl.n_classes; d++) {
+        if (!((a.slots_other >> d) & 1u)) continue;
+        const int s = cl.class_state[d];
+        if (!cl.is_gaussian[s]) {
+            a.texp_slot = d;
+            continue;
+        }
+        for (int c = 0; c < cfg->n_comps[s]; c++) {
+            a.task_class[a.n_tasks] = (uint8_t) d;
+            a.task_comp[a.n_tasks] = (uint8_t) c;
+            a.n_tasks++;
+        }
+    }
+    if (a.n_tasks == 0) { /* keep the table non-empty */
+        a.task_class[0] = 0;
+        a.task_comp[0] = 0;
+    }
     a.params = ctx->d_params[slot];
     a.scrE = ctx->d_scrE;
     a.scrF = ctx->d_scrF;
@@ -320,6 +355,7 @@ static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_par
     a.posteriors = post_dev;
     a.err_flags = ctx->d_err;
     a.forward_only = forward_only;
+    a.phase_clock = ctx->d_phase_clock;
 
     void *kargs[] = {(void *) &a};
     if (timed) CU(cudaEventRecord(ctx->ev0, stream));
@@ -457,4 +493,39 @@ extern "C" int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *
     *n_esteps = k;
     free(stats);
     return rc;
+}
+
+/* ---- instrumentation / test hooks (not part of the reference-facing surface) ------------------------------------- */
+
+/* clock64() of thread 0 of every CTA at the six phase boundaries of the last E-step kernel: start, end of phase A,
+ * arrival at the grid barrier, release, end of C1 (thread 0 only), end of phase C, arrival at the second barrier (block
+ * reduction done), its release, and the SM id.  out: [grid][10]. */
+extern "C" int hfg_debug_phase_clocks(hfg_ctx *ctx, long long *out, int *grid) {
+    if (!ctx || !out || !grid || !ctx->have_chunks) return HFG_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, ctx->d_phase_clock, (size_t) ctx->grid * 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+    *grid = ctx->grid;
+    return HFG_OK;
+}
+
+__global__ void hfg_debug_exp_kernel(const double *in, double *out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = hfgk::exp_nonpos(in[i]);
+}
+
+/* Applies the kernel's exp_nonpos() to n host values (accuracy test of the custom exponential). */
+extern "C" int hfg_debug_exp(hfg_ctx *ctx, const double *in, double *out, int n) {
+    if (!ctx || !in || !out || n < 1) return HFG_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    double *d_in = NULL, *d_out = NULL;
+    CU(cudaMalloc((void **) &d_in, sizeof(double) * (size_t) n));
+    CU(cudaMalloc((void **) &d_out, sizeof(double) * (size_t) n));
+    CU(cudaMemcpy(d_in, in, sizeof(double) * (size_t) n, cudaMemcpyHostToDevice));
+    hfg_debug_exp_kernel<<<(n + 255) / 256, 256>>>(d_in, d_out, n);
+    ctx->launches += 1;
+    CU(cudaMemcpy(out, d_out, sizeof(double) * (size_t) n, cudaMemcpyDeviceToHost));
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return HFG_OK;
 }

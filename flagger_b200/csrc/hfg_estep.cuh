@@ -56,6 +56,11 @@ namespace cg = cooperative_groups;
 #define RT_GAUSS 140
 #define RT_STRIDE(G) (RT_GAUSS + 6 * (G))
 #define HFG_INV_TERM 1e4 /* 1 / terminationProb */
+#define HFG_MAX_TASKS 160
+/* per-(region, task) table after the Gaussian arrays: (1-a)*mu, a, 1/(var*beta0), w/sqrt(var*beta0*2*PI) */
+#define RT_TASK(G) (RT_GAUSS + 6 * (G))
+#undef RT_STRIDE
+#define RT_STRIDE2(G, NT) (RT_TASK(G) + 4 * (NT))
 
 struct EstepArgs {
     /* run-constant layout */
@@ -76,6 +81,11 @@ struct EstepArgs {
     double inv_one_minus_alpha[HFG_NS][HFG_NS]; /* 1 / (1 - alpha[pre][s]) */
     int32_t first_pre_of_class[HFG_NS][HFG_NS];  /* [pre][s]: smallest preState sharing the class of (pre, s) */
     uint32_t slots_start, slots_other;           /* emission slots evaluated at a chunk start / elsewhere */
+    /* flat list of the Gaussian component evaluations of an ordinary window, ordered by (class, component): the kernel
+     * runs them four at a time so that four independent exp() chains are in flight per thread */
+    int32_t n_tasks;
+    uint8_t task_class[HFG_MAX_TASKS], task_comp[HFG_MAX_TASKS];
+    int32_t texp_slot;                           /* emission slot of the truncated-exponential state, or -1 */
     /* per-call inputs / scratch / outputs (device) */
     const hfg_region_params *params;
     double *scrE;  /* [smax][D][capacity]  emission rows */
@@ -90,6 +100,7 @@ struct EstepArgs {
     double *posteriors;  /* [W][4] or NULL */
     int32_t *err_flags;  /* bit0 scale underflow, bit1 NaN */
     int32_t forward_only;
+    long long *phase_clock; /* [grid][10] clock64() of thread 0 at the phase boundaries + SM id (instrumentation) */
 };
 
 /* statistic columns per (block, region): 16 transition counts, lambda num/den, then per Gaussian component
@@ -108,10 +119,11 @@ __device__ __forceinline__ double pow2_rescale_factor(double m) {
 }
 
 __device__ __forceinline__ void mat_rescale(double (&P)[16]) {
-    double m = P[0];
+    /* entries are non-negative, so their order is the order of their high words as integers */
+    int hi = __double2hiint(P[0]);
 #pragma unroll
-    for (int i = 1; i < 16; i++) m = fmax(m, P[i]);
-    const double s = pow2_rescale_factor(m);
+    for (int i = 1; i < 16; i++) hi = max(hi, __double2hiint(P[i]));
+    const double s = __hiloint2double((2046 - ((hi >> 20) & 0x7ff)) << 20, 0);
 #pragma unroll
     for (int i = 0; i < 16; i++) P[i] *= s;
 }
@@ -213,8 +225,38 @@ __device__ __forceinline__ void warp_scan_suffix(double (&P)[16], int lane) {
 
 /* ---- emissions ------------------------------------------------------------------------------------------ */
 
+/* exp(q) for q <= 0 (every exponential on this path has a non-positive argument: -0.5*d^2/var, -lambda*x).
+ * q is clamped at -708 (e^-708 ~ 1e-308 is far below the 1e-40 floor applied to every pdf), which removes the
+ * denormal/overflow handling of the generic routine; 2^n by exponent arithmetic; the degree-11 polynomial is the
+ * Chebyshev interpolant of e^r on |r| <= ln2/2 (max relative error 1.6e-17 before rounding), evaluated with Estrin's
+ * scheme for instruction-level parallelism.  Measured <= 1 ulp from glibc on the test grid (tests/test_gpu_parity.py). */
+__device__ __forceinline__ double exp_nonpos(double q) {
+    q = fmax(q, -708.0);
+    const double t = fma(q, 1.4426950408889634, 6755399441055744.0); /* q*log2(e) + 1.5*2^52: integer in the low word */
+    const int n = __double2loint(t);
+    const double nf = t - 6755399441055744.0;
+    double r = fma(nf, -6.9314718036912382e-01, q);
+    r = fma(nf, -1.9082149292705877e-10, r);
+    const double r2 = r * r;
+    const double p01 = 1.0 + r; /* c0 + c1*r with c0 = c1 = 1 */
+    const double p23 = fma(0.1666666666666668, r, 0.5000000000000019);
+    const double p45 = fma(0.008333333333319589, r, 0.04166666666648795);
+    const double p67 = fma(0.00019841269890076403, r, 0.0013888888952352863);
+    const double p89 = fma(2.755724088722987e-06, r, 2.4801485441561313e-05);
+    const double pab = fma(2.5110049204818658e-08, r, 2.763265472252779e-07);
+    const double r4 = r2 * r2;
+    const double q0 = fma(p23, r2, p01);
+    const double q1 = fma(p67, r2, p45);
+    const double q2 = fma(pab, r2, p89);
+    const double r8 = r4 * r4;
+    const double h = fma(q1, r4, q0);
+    const double p = fma(q2, r8, h);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
 struct Win {
     double x, px, beta;
+    double rb, sq; /* beta0/beta and its square root: rescale the tabulated 1/(var*beta0) and w/sqrt(var*beta0*2*PI) */
     int region, mask;
     bool edge, start, second, region_change, chunk_end;
 };
@@ -231,6 +273,8 @@ __device__ __forceinline__ Win decode_word(uint32_t w, double beta0) {
     o.region_change = (w & HFG_OBS_REGION_CHANGE) != 0;
     o.chunk_end = (w & HFG_OBS_CHUNK_END) != 0;
     o.beta = beta0;
+    o.rb = 1.0;
+    o.sq = 1.0;
     return o;
 }
 
@@ -245,9 +289,9 @@ __device__ __forceinline__ double trunc_exp_prob(const double *rt, const Win &w)
     } else {
         lam = rt[RT_TEXP] / w.beta;
         const double b = w.beta * trunc;
-        norm = 1 - exp(-lam * b);
+        norm = 1 - exp_nonpos(-lam * b);
     }
-    return lam * exp(-lam * w.x) / norm;
+    return lam * exp_nonpos(-lam * w.x) / norm;
 }
 
 /* one mixture component of Gaussian_getComponentProbs (hmm_utils.c:768-793): mean=((1-a)*mu + a*px)*beta,
@@ -256,30 +300,90 @@ __device__ __forceinline__ double gauss_comp(const double *rt, int G, int g, dou
     const double *ga = rt + RT_GAUSS;
     double mean = (1 - a) * ga[g] + a * w.px;
     mean *= w.beta;
-    double inv, coef;
-    if (!w.edge) {
-        inv = ga[4 * G + g];
-        coef = ga[5 * G + g];
-    } else {
-        const double vb = ga[G + g] * w.beta;
-        inv = 1.0 / vb;
-        coef = ga[2 * G + g] / sqrt(vb * 2 * HFG_PI);
-    }
+    /* contig-end windows (beta != beta0) reuse the tabulated constants through beta0/beta: 1/(var*beta) =
+     * (1/(var*beta0))*(beta0/beta) and w/sqrt(var*beta*2*PI) = (w/sqrt(var*beta0*2*PI))*sqrt(beta0/beta); both factors
+     * are exactly 1 for ordinary windows */
+    const double inv = ga[4 * G + g] * w.rb;
+    const double coef = ga[5 * G + g] * w.sq;
     const double d = w.x - mean;
-    double p = coef * exp((-0.5 * (d * d)) * inv);
+    double p = coef * exp_nonpos((-0.5 * (d * d)) * inv);
     if (p != p) *nan = 1;
     if (p < 1e-40) p = 1e-40;
     return p;
+}
+
+/* all components of a Gaussian state under dependency factor a: returns their sum (Gaussian_getProb,
+ * hmm_utils.c:753-758) and, when pc != NULL, the component pdfs.  Deliberately NOT inlined: one copy of the
+ * exponential / edge-window code for the whole kernel keeps the instruction footprint inside the I-cache. */
+__device__ __noinline__ double gauss_class(const double *rt, int G, int g0, int n, double a, double x, double px,
+                                           double beta, double rb, double sq, double *pc, int *nan) {
+    Win w;
+    w.x = x;
+    w.px = px;
+    w.beta = beta;
+    w.rb = rb;
+    w.sq = sq;
+    double tot = 0.0;
+    for (int c = 0; c < n; c++) {
+        const double p = gauss_comp(rt, G, g0 + c, a, w, nan);
+        if (pc) pc[c] = p;
+        tot += p;
+    }
+    return tot;
+}
+
+/* Gaussian_updateEstimator (hmm_utils.c:812-839) for one (state, alpha) class with pooled count cnt: adds
+ * (w*x_adj, w, w*z*z) per component into the thread's statistics column (three rows per component, stride ld). */
+__device__ __noinline__ void gauss_stats(const double *rt, int G, int g0, int n, double a, double inv_1ma, double cnt,
+                                         double x, double px, double beta, double rb, double sq, double *colg, int ld,
+                                         int *nan) {
+    const double x_adj = (x - a * px) * inv_1ma;
+    const double oma = 1.0 - a;
+    if (n == 1) {
+        const double z = (x_adj - rt[RT_GAUSS + g0]) * oma;
+        colg[0] += cnt * x_adj;
+        colg[ld] += cnt;
+        colg[2 * ld] += cnt * z * z;
+        return;
+    }
+    /* responsibilities need the component pdfs again (hmm_utils.c:819) */
+    Win w;
+    w.x = x;
+    w.px = px;
+    w.beta = beta;
+    w.rb = rb;
+    w.sq = sq;
+    double pc[HFG_MAX_COMPS];
+    double tot = 0.0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < n; c0 += 4) {
+        double pv[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) pv[u] = gauss_comp(rt, G, g0 + min(c0 + u, n - 1), a, w, nan); /* 4 chains in flight */
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (c0 + u < n) {
+                pc[c0 + u] = pv[u];
+                tot += pv[u];
+            }
+    }
+    const double scale = cnt / tot;
+#pragma unroll 1
+    for (int c = 0; c < n; c++) {
+        const double wgt = scale * pc[c];
+        const double z = (x_adj - rt[RT_GAUSS + g0 + c]) * oma;
+        double *cg_ = colg + (size_t) 3 * c * ld;
+        cg_[0] += wgt * x_adj;
+        cg_[ld] += wgt;
+        cg_[2 * ld] += wgt * z * z;
+    }
 }
 
 /* emission of state s under dependency factor a (EmissionDist_getProb, hmm_utils.c:1409-1417) */
 __device__ __forceinline__ double emission(const EstepArgs &A, const double *rt, int s, double a, const Win &w,
                                            int *nan) {
     if (!A.is_gauss[s]) return trunc_exp_prob(rt, w);
-    double tot = 0.0;
-    const int n = A.ncomp[s], g0 = A.gbase[s];
-    for (int c = 0; c < n; c++) tot += gauss_comp(rt, A.G, g0 + c, a, w, nan);
-    return tot;
+    return gauss_class(rt, A.G, A.gbase[s], A.ncomp[s], a, w.x, w.px, w.beta, w.rb, w.sq, NULL, nan);
 }
 
 /* transition probability into window w: 1/(N+1) at a region change (hmm.c:398-400), else the masked row */
@@ -299,7 +403,7 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j = blockIdx.x * HFG_THREADS + tid; /* segment owned by this thread */
     const int cap = A.capacity, D = A.n_classes, G = A.G, R = A.n_regions;
-    const int rt_stride = RT_STRIDE(G);
+    const int rt_stride = RT_STRIDE2(G, A.n_tasks);
     const int NSTAT = hfg_nstat(G);
     const int LD = HFG_THREADS + 1;
 
@@ -341,7 +445,7 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
         else if (q == 11) {
             const double lam = p.lambda / A.beta0;
             const double b = A.beta0 * p.trunc_point;
-            rt[RT_TEXP + 3] = 1 - exp(-lam * b);
+            rt[RT_TEXP + 3] = 1 - exp_nonpos(-lam * b);
         } else {
             const int g = q - 12;
             int s = 0;
@@ -359,8 +463,21 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
             ga[5 * G + g] = p.weight[s][c] / sqrt(vb * 2 * HFG_PI);
         }
     }
+    for (int idx = tid; idx < R * A.n_tasks; idx += HFG_THREADS) {
+        const int r = idx / A.n_tasks, t = idx % A.n_tasks;
+        const hfg_region_params &p = A.params[r];
+        const int d = A.task_class[t], c = A.task_comp[t], s = A.class_state[d];
+        const double a = A.class_alpha[d];
+        const double vb = p.var[s][c] * A.beta0;
+        double *tk = rtab + (size_t) r * rt_stride + RT_TASK(G) + 4 * t;
+        tk[0] = (1 - a) * p.mean[s][c];
+        tk[1] = a;
+        tk[2] = 1.0 / vb;
+        tk[3] = p.weight[s][c] / sqrt(vb * 2 * HFG_PI);
+    }
     __syncthreads();
 
+    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 0] = clock64();
     const int len = A.seg_len[j];
     const int seg_first = A.seg_start[j];
     int nan_flag = 0, uf_flag = 0;
@@ -376,18 +493,51 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
         for (int k = 0; k < len; k++) {
             const uint32_t word = A.obsT[(size_t) k * cap + j];
             Win w = decode_word(word, A.beta0);
-            if (w.edge) w.beta = A.edge_beta[eidx++];
+            if (w.edge) {
+                w.beta = A.edge_beta[3 * eidx];
+                w.rb = A.edge_beta[3 * eidx + 1];
+                w.sq = A.edge_beta[3 * eidx + 2];
+                eidx++;
+            }
             my_region = w.region;
             const double *rt = rtab + (size_t) w.region * rt_stride;
             double *erow = A.scrE + (size_t) k * D * cap + j;
             /* evaluate every distinct (state, alpha) class once (the reference evaluates all 16 (pre,state) pairs,
              * three times per iteration) */
-            const uint32_t slots = w.start ? A.slots_start : A.slots_other;
-            for (int d = 0; d < D; d++) {
-                if (!((slots >> d) & 1u)) continue;
-                const double e = emission(A, rt, A.class_state[d], A.class_alpha[d], w, &nan_flag);
-                erow[(size_t) d * cap] = e;
-                es[d * LD] = e;
+            if (w.start) {
+                /* chunk starts (alpha = 0, preX = 0 for every state): generic path */
+                const uint32_t slots = w.start ? A.slots_start : A.slots_other;
+                for (int d = 0; d < D; d++) {
+                    if (!((slots >> d) & 1u)) continue;
+                    const double e = emission(A, rt, A.class_state[d], A.class_alpha[d], w, &nan_flag);
+                    erow[(size_t) d * cap] = e;
+                    es[d * LD] = e;
+                }
+            } else {
+                /* per-component constants tabulated for the interior beta; four evaluations in flight */
+                for (int d = 0; d < D; d++) es[d * LD] = 0.0;
+                if (A.texp_slot >= 0) es[A.texp_slot * LD] = trunc_exp_prob(rt, w);
+                const double *tk = rt + RT_TASK(G);
+                const int NT = A.n_tasks;
+                for (int t0 = 0; t0 < NT; t0 += 4) {
+                    double pv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int t = min(t0 + u, NT - 1);
+                        const double4 c4 = *reinterpret_cast<const double4 *>(tk + 4 * t);
+                        double mean = c4.x + c4.y * w.px; /* (1-a)*mu + a*px */
+                        mean *= w.beta;
+                        const double dd = w.x - mean;
+                        double pp = (c4.w * w.sq) * exp_nonpos((-0.5 * (dd * dd)) * (c4.z * w.rb));
+                        if (pp != pp) nan_flag = 1;
+                        pv[u] = pp < 1e-40 ? 1e-40 : pp;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (t0 + u < NT) es[A.task_class[t0 + u] * LD] += pv[u]; /* component order, as Gaussian_getProb */
+                }
+                for (int d = 0; d < D; d++)
+                    if ((A.slots_other >> d) & 1u) erow[(size_t) d * cap] = es[d * LD];
             }
             double M[16];
             if (w.start) {
@@ -413,6 +563,7 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
         if (has_start) s_reset = 1; /* benign race: every writer stores 1 */
         treg[tid] = my_region;
         __syncthreads(); /* the emission staging area is reused as the scan stash below */
+        if (tid == 0) A.phase_clock[blockIdx.x * 10 + 1] = clock64();
 
         /* ======================= phase B: scans ============================================================== */
         double S[16], Q[16];
@@ -465,7 +616,9 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
         }
     }
     __threadfence();
+    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 2] = clock64();
     grid.sync();
+    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 3] = clock64();
 
     /* messages entering this block: walk to the nearest block that contains a chunk start (its product is rank-1,
      * so nothing beyond it matters) */
@@ -536,6 +689,10 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
     /* =========================== phase C1: forward inside the segment ======================================== */
     double loglik = 0.0;
     {
+        /* sum_i log(c_i) = log(prod c_i): the product is carried as mantissa x 2^exponent (exact rescaling), one log
+         * per segment instead of one per window */
+        double cprod = 1.0;
+        int cexp = 0;
         double f[4] = {v_in[0], v_in[1], v_in[2], v_in[3]};
         for (int k = 0; k < len; k++) {
             const uint32_t word = A.obsT[(size_t) k * cap + j];
@@ -565,10 +722,18 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
                 A.scrF[((size_t) k * 4 + s) * cap + j] = f[s];
             }
             A.scrC[(size_t) k * cap + j] = c;
-            loglik += log(c);
+            cprod *= c;
+            {
+                const int hi = __double2hiint(cprod);
+                const int e = ((hi >> 20) & 0x7ff) - 1023;
+                cexp += e;
+                cprod = __hiloint2double(hi - (e << 20), __double2loint(cprod));
+            }
         }
+        loglik = log(cprod) + (double) cexp * 0.6931471805599453;
         A.seg_loglik[j] = loglik;
     }
+    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 4] = clock64(); /* thread 0's own C1 end (no barrier here) */
 
     /* per-thread statistics live in column tid of acc: rows 0..15 transition counts, 16..17 truncated exponential,
      * 18+3g.. (meanNum, den, varNum) of Gaussian component g, last row the log-likelihood */
@@ -601,7 +766,12 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
         for (int k = len - 1; k >= 0; k--) {
             const uint32_t word = A.obsT[(size_t) k * cap + j];
             Win w = decode_word(word, A.beta0);
-            if (w.edge) w.beta = A.edge_beta[eidx--];
+            if (w.edge) {
+                w.beta = A.edge_beta[3 * eidx];
+                w.rb = A.edge_beta[3 * eidx + 1];
+                w.sq = A.edge_beta[3 * eidx + 2];
+                eidx--;
+            }
             const double *rt = rtab + (size_t) w.region * rt_stride;
             const int gi = seg_first + k;
 
@@ -664,38 +834,34 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
                     /* Gaussian_updateEstimator (hmm_utils.c:812-839), grouped by (state, alpha) class: preStates that
                      * share alpha share x_adjusted, z and the component responsibilities */
                     const int n = A.ncomp[s], g0 = A.gbase[s];
+                    if (n == 1) {
+                        /* single component: the responsibility is 1, so (w*x_adj, w, w*z*z) with w = the pair count;
+                         * summed over the four preStates, then one update of the thread's column */
+                        const double mu = rt[RT_GAUSS + g0];
+                        double s1 = 0.0, s0 = 0.0, s2 = 0.0;
 #pragma unroll
-                    for (int pre = 0; pre < 4; pre++) {
-                        if (A.first_pre_of_class[pre][s] != pre) continue;
-                        double cnt = xi[pre];
+                        for (int pre = 0; pre < 4; pre++) {
+                            const double a = A.alpha[pre][s];
+                            const double x_adj = (w.x - a * w.px) * A.inv_one_minus_alpha[pre][s];
+                            const double z = (x_adj - mu) * (1.0 - a);
+                            s1 += xi[pre] * x_adj;
+                            s0 += xi[pre];
+                            s2 += xi[pre] * z * z;
+                        }
+                        double *cg_ = col + (size_t) (18 + 3 * g0) * LD;
+                        cg_[0] += s1;
+                        cg_[LD] += s0;
+                        cg_[2 * LD] += s2;
+                    } else {
 #pragma unroll
-                        for (int p2 = pre + 1; p2 < 4; p2++)
-                            if (A.first_pre_of_class[p2][s] == pre) cnt += xi[p2];
-                        const double a = A.alpha[pre][s];
-                        const double x_adj = (w.x - a * w.px) * A.inv_one_minus_alpha[pre][s];
-                        if (n == 1) {
-                            const double z = (x_adj - rt[RT_GAUSS + g0]) * (1.0 - a);
-                            double *cg_ = col + (size_t) (18 + 3 * g0) * LD;
-                            cg_[0] += cnt * x_adj;
-                            cg_[LD] += cnt;
-                            cg_[2 * LD] += cnt * z * z;
-                        } else {
-                            /* responsibilities need the component pdfs again (hmm_utils.c:819) */
-                            double pc[HFG_MAX_COMPS];
-                            double tot = 0.0;
-                            for (int cc = 0; cc < n; cc++) {
-                                pc[cc] = gauss_comp(rt, G, g0 + cc, a, w, &nan_flag);
-                                tot += pc[cc];
-                            }
-                            const double scale = cnt / tot;
-                            for (int cc = 0; cc < n; cc++) {
-                                const double wgt = scale * pc[cc];
-                                const double z = (x_adj - rt[RT_GAUSS + g0 + cc]) * (1.0 - a);
-                                double *cg_ = col + (size_t) (18 + 3 * (g0 + cc)) * LD;
-                                cg_[0] += wgt * x_adj;
-                                cg_[LD] += wgt;
-                                cg_[2 * LD] += wgt * z * z;
-                            }
+                        for (int pre = 0; pre < 4; pre++) {
+                            if (A.first_pre_of_class[pre][s] != pre) continue;
+                            double cnt = xi[pre];
+#pragma unroll
+                            for (int p2 = pre + 1; p2 < 4; p2++)
+                                if (A.first_pre_of_class[p2][s] == pre) cnt += xi[p2];
+                            gauss_stats(rt, G, g0, n, A.alpha[pre][s], A.inv_one_minus_alpha[pre][s], cnt, w.x, w.px,
+                                        w.beta, w.rb, w.sq, col + (size_t) (18 + 3 * g0) * LD, LD, &nan_flag);
                         }
                     }
                 }
@@ -717,19 +883,32 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
     {
         col[(size_t) (NSTAT - 1) * LD] = loglik;
         __syncthreads();
-        for (int q = tid; q < R * NSTAT; q += HFG_THREADS) {
+        if (tid == 0) A.phase_clock[blockIdx.x * 10 + 5] = clock64();
+        /* one warp per (region, statistic) column: each lane adds its 8 entries in index order, then a fixed
+         * xor-shuffle tree -- the same association on every run */
+        for (int q = warp; q < R * NSTAT; q += HFG_WARPS) {
             const int r = q / NSTAT, st = q % NSTAT;
             const bool is_ll = (st == NSTAT - 1);
             double sum = 0.0;
             if (!is_ll || r == 0) {
                 const double *cl = acc + (size_t) st * LD;
-                for (int t = 0; t < HFG_THREADS; t++)
+#pragma unroll
+                for (int t = lane; t < HFG_THREADS; t += 32)
                     if (is_ll || treg[t] == r) sum += cl[t];
             }
-            A.partials[((size_t) blockIdx.x * R + r) * NSTAT + st] = sum;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            if (lane == 0) A.partials[((size_t) blockIdx.x * R + r) * NSTAT + st] = sum;
         }
         __threadfence();
+        if (tid == 0) A.phase_clock[blockIdx.x * 10 + 6] = clock64();
         grid.sync();
+        if (tid == 0) {
+            A.phase_clock[blockIdx.x * 10 + 7] = clock64();
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            A.phase_clock[blockIdx.x * 10 + 8] = (long long) smid;
+        }
         if (blockIdx.x == 0) {
             const int SD = (int) (sizeof(hfg_region_stats) / sizeof(double));
             const int nb = gridDim.x;

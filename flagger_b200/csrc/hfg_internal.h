@@ -56,7 +56,7 @@ typedef struct hfg_layout {
     int32_t *seg_len;        /* [capacity] 0 for idle slots */
     int32_t *seg_chunk;      /* [capacity] */
     int32_t *seg_edge_begin; /* [capacity + 1] first entry of edge_beta that belongs to segment j or later */
-    double *edge_beta;       /* [n_edge] beta of every edge window, in window order */
+    double *edge_beta;       /* [n_edge][3] (beta, beta0/beta, sqrt(beta0/beta)) of every edge window, in window order */
     int64_t n_edge;
     int64_t *chunk_offset;   /* [n_chunks + 1] */
 } hfg_layout;

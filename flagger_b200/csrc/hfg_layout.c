@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <math.h>
 
 #include "hfg_internal.h"
 
@@ -50,19 +51,25 @@ void hfg_layout_free(hfg_layout *l) {
     memset(l, 0, sizeof(*l));
 }
 
-/* number of segments when every (chunk, region-run) is cut into pieces of at most smax windows */
-static int64_t count_segments(int32_t n_chunks, const hfg_chunk_desc *chunks, const uint8_t *region, int smax) {
+/* Cost of a window in units of an ordinary window: contig-end (edge) windows take the generic emission path
+ * with per-window factors; the kernel folds them into the tabulated constants, so they cost the same as any other
+ * window (HFG_EDGE_COST 1).  The cost-based cut is kept so that a costlier special path can be balanced by data. */
+#define HFG_EDGE_COST 1
+
+/* end (exclusive) of the segment that starts at window i of a chunk: same region, accumulated cost <= smax */
+static int segment_end(const uint8_t *region, const uint8_t *cost, int L, int i, int smax) {
+    int j = i + 1, acc = cost[i] & 0x7f; /* bit 7 of cost[] flags an edge window, the low bits are the cost */
+    while (j < L && region[j] == region[i] && acc + (cost[j] & 0x7f) <= smax) acc += cost[j++] & 0x7f;
+    return j;
+}
+
+static int64_t count_segments(int32_t n_chunks, const hfg_chunk_desc *chunks, const uint8_t *region,
+                              const uint8_t *cost, int smax) {
     int64_t n = 0;
     for (int32_t c = 0; c < n_chunks; c++) {
-        const uint8_t *r = region + chunks[c].offset;
+        const int64_t o = chunks[c].offset;
         const int L = chunks[c].n_windows;
-        int i = 0;
-        while (i < L) {
-            int j = i + 1;
-            while (j < L && r[j] == r[i]) j++;
-            n += (j - i + smax - 1) / smax;
-            i = j;
-        }
+        for (int i = 0; i < L; n++) i = segment_end(region + o, cost + o, L, i, smax);
     }
     return n;
 }
@@ -89,19 +96,33 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
             return HFG_ERR_INVALID;
         }
     }
-    /* smallest smax whose segment count fits the persistent grid */
-    int smax = (int) ((W + capacity - 1) / capacity);
-    if (smax < 1) smax = 1;
-    while (count_segments(n_chunks, chunks, region, smax) > capacity) smax += (smax + 7) / 8;
-    const int64_t n_seg = count_segments(n_chunks, chunks, region, smax);
+    const double beta0 = !cfg->adjust_contig_ends ? 1.0
+                         : (cfg->mean_read_length > 0 ? (double) (cfg->mean_read_length - 1) / cfg->mean_read_length : 0.25);
+    uint8_t *cost = malloc((size_t) W);
+    if (!cost) {
+        snprintf(err, errlen, "out of host memory building the layout");
+        return HFG_ERR_NOMEM;
+    }
+    int64_t total_cost = 0;
+    for (int32_t c = 0; c < n_chunks; c++) {
+        for (int i = 0; i < chunks[c].n_windows; i++) {
+            const double b = hfg_beta(cfg, &chunks[c], i);
+            cost[chunks[c].offset + i] = memcmp(&b, &beta0, sizeof(double)) != 0 ? (0x80 | HFG_EDGE_COST) : 1;
+            total_cost += cost[chunks[c].offset + i] & 0x7f;
+        }
+    }
+    /* smallest cost budget whose segment count fits the persistent grid */
+    int smax = (int) ((total_cost + capacity - 1) / capacity);
+    if (smax < HFG_EDGE_COST) smax = HFG_EDGE_COST;
+    while (count_segments(n_chunks, chunks, region, cost, smax) > capacity) smax += (smax + 7) / 8;
+    const int64_t n_seg = count_segments(n_chunks, chunks, region, cost, smax);
 
     out->n_windows = W;
     out->n_chunks = n_chunks;
     out->capacity = capacity;
     out->smax = smax;
     out->n_seg = (int32_t) n_seg;
-    out->beta0 = !cfg->adjust_contig_ends ? 1.0
-                 : (cfg->mean_read_length > 0 ? (double) (cfg->mean_read_length - 1) / cfg->mean_read_length : 0.25);
+    out->beta0 = beta0;
     out->obsT = calloc((size_t) smax * capacity, sizeof(uint32_t));
     out->seg_start = calloc((size_t) capacity, sizeof(int32_t));
     out->seg_len = calloc((size_t) capacity, sizeof(int32_t));
@@ -109,9 +130,10 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
     out->seg_edge_begin = calloc((size_t) capacity + 1, sizeof(int32_t));
     out->chunk_offset = calloc((size_t) n_chunks + 1, sizeof(int64_t));
     int64_t edge_cap = 1024, n_edge = 0;
-    out->edge_beta = malloc(sizeof(double) * (size_t) edge_cap);
+    out->edge_beta = malloc(sizeof(double) * 3 * (size_t) edge_cap);
     if (!out->obsT || !out->seg_start || !out->seg_len || !out->seg_chunk || !out->seg_edge_begin ||
         !out->edge_beta || !out->chunk_offset) {
+        free(cost);
         hfg_layout_free(out);
         snprintf(err, errlen, "out of host memory building the layout");
         return HFG_ERR_NOMEM;
@@ -123,50 +145,54 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
         const int64_t o = ch->offset;
         const int L = ch->n_windows;
         out->chunk_offset[c] = o;
-        int i = 0;
-        while (i < L) {
-            int run_end = i + 1;
-            while (run_end < L && region[o + run_end] == region[o + i]) run_end++;
-            for (int a = i; a < run_end; a += smax) {
-                const int len = (run_end - a) < smax ? (run_end - a) : smax;
-                out->seg_start[seg] = (int32_t) (o + a);
-                out->seg_len[seg] = len;
-                out->seg_chunk[seg] = c;
-                out->seg_edge_begin[seg] = (int32_t) n_edge;
-                for (int k = 0; k < len; k++) {
-                    const int w = a + k; /* window index inside the chunk */
-                    const int64_t g = o + w;
-                    uint32_t word = HFG_OBS_VALID;
-                    word |= (uint32_t) (uint8_t) cov[g];
-                    if (w > 0) word |= (uint32_t) (uint8_t) cov[g - 1] << 8;
-                    word |= (uint32_t) region[g] << 16;
-                    word |= validity_mask(cfg, cov[g], cov_high_mapq[g], cov_high_clip[g]) << 22;
-                    if (w > 0 && region[g] != region[g - 1]) word |= HFG_OBS_REGION_CHANGE;
-                    if (w == 0) word |= HFG_OBS_CHUNK_START;
-                    if (w == 1) word |= HFG_OBS_SECOND;
-                    if (w == L - 1) word |= HFG_OBS_CHUNK_END;
-                    const double b = hfg_beta(cfg, ch, w);
-                    if (memcmp(&b, &out->beta0, sizeof(double)) != 0) {
-                        word |= HFG_OBS_EDGE;
-                        if (n_edge == edge_cap) {
-                            edge_cap *= 2;
-                            double *nb = realloc(out->edge_beta, sizeof(double) * (size_t) edge_cap);
-                            if (!nb) {
-                                hfg_layout_free(out);
-                                snprintf(err, errlen, "out of host memory building the layout");
-                                return HFG_ERR_NOMEM;
-                            }
-                            out->edge_beta = nb;
+        for (int a = 0; a < L;) {
+            const int end = segment_end(region + o, cost + o, L, a, smax);
+            const int len = end - a;
+            out->seg_start[seg] = (int32_t) (o + a);
+            out->seg_len[seg] = len;
+            out->seg_chunk[seg] = c;
+            out->seg_edge_begin[seg] = (int32_t) n_edge;
+            for (int k = 0; k < len; k++) {
+                const int w = a + k; /* window index inside the chunk */
+                const int64_t g = o + w;
+                uint32_t word = HFG_OBS_VALID;
+                word |= (uint32_t) (uint8_t) cov[g];
+                if (w > 0) word |= (uint32_t) (uint8_t) cov[g - 1] << 8;
+                word |= (uint32_t) region[g] << 16;
+                word |= validity_mask(cfg, cov[g], cov_high_mapq[g], cov_high_clip[g]) << 22;
+                if (w > 0 && region[g] != region[g - 1]) word |= HFG_OBS_REGION_CHANGE;
+                if (w == 0) word |= HFG_OBS_CHUNK_START;
+                if (w == 1) word |= HFG_OBS_SECOND;
+                if (w == L - 1) word |= HFG_OBS_CHUNK_END;
+                if (cost[g] & 0x80) {
+                    word |= HFG_OBS_EDGE;
+                    if (n_edge == edge_cap) {
+                        edge_cap *= 2;
+                        double *nb = realloc(out->edge_beta, sizeof(double) * 3 * (size_t) edge_cap);
+                        if (!nb) {
+                            free(cost);
+                            hfg_layout_free(out);
+                            snprintf(err, errlen, "out of host memory building the layout");
+                            return HFG_ERR_NOMEM;
                         }
-                        out->edge_beta[n_edge++] = b;
+                        out->edge_beta = nb;
                     }
-                    out->obsT[(size_t) k * capacity + seg] = word;
+                    {
+                        /* (beta, beta0/beta, sqrt(beta0/beta)) */
+                        const double b = hfg_beta(cfg, ch, w);
+                        out->edge_beta[3 * n_edge] = b;
+                        out->edge_beta[3 * n_edge + 1] = beta0 / b;
+                        out->edge_beta[3 * n_edge + 2] = sqrt(beta0 / b);
+                        n_edge++;
+                    }
                 }
-                seg++;
+                out->obsT[(size_t) k * capacity + seg] = word;
             }
-            i = run_end;
+            seg++;
+            a = end;
         }
     }
+    free(cost);
     out->chunk_offset[n_chunks] = W;
     for (int32_t j = seg; j <= capacity; j++) out->seg_edge_begin[j] = (int32_t) n_edge;
     out->n_edge = n_edge;

@@ -176,6 +176,11 @@ int64_t hfg_kernel_launches(const hfg_ctx *ctx);
 /* Device time (ms, CUDA events on the launching stream) of the E-step kernel in the last hfg_em_iteration*. */
 double hfg_last_estep_kernel_ms(hfg_ctx *ctx);
 
+/* Test / profiling hooks (no reference counterpart): phase timeline of the last E-step kernel ([grid][10]: eight clock64
+ * values + SM id) and the kernel's exponential applied to n host values. */
+int hfg_debug_phase_clocks(hfg_ctx *ctx, long long *out, int *grid);
+int hfg_debug_exp(hfg_ctx *ctx, const double *in, double *out, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,3 +137,18 @@ def test_determinism():
     assert l1 == l2 and np.array_equal(b1, b2)
     assert np.array_equal(_abi.stats_as_flat(s1), _abi.stats_as_flat(s2))
     gpu.close()
+
+
+def test_custom_exp_accuracy():
+    """The kernel's exp_nonpos() against numpy (glibc) exp over the argument range the path produces."""
+    cfg = _abi.make_config()
+    gpu = api.HmmFlaggerGPU(cfg)
+    rng = np.random.default_rng(0)
+    q = -np.concatenate([np.linspace(0.0, 120.0, 200001), rng.exponential(5.0, 200000), [0.0, 1e-300, 1e-17, 700.0, 708.0]])
+    got = gpu.debug_exp(q)
+    want = np.exp(q)
+    ulp = np.abs(got - want) / np.spacing(want)
+    assert ulp.max() <= 2.0, ulp.max()  # Estrin evaluation: <= 2 ulp from glibc (libdevice exp itself is 1 ulp)
+    # below the clamp the result is the clamp value (far under the 1e-40 floor applied to every pdf)
+    assert gpu.debug_exp(np.array([-1e4]))[0] == gpu.debug_exp(np.array([-708.0]))[0] < 1e-300
+    gpu.close()
