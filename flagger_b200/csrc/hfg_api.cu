@@ -140,7 +140,7 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         free(ctx);
         return HFG_ERR_CUDA;
     }
-    ctx->max_blocks = ctx->num_sms * (per_sm >= 2 ? 2 : 1); /* persistent CTAs: all co-resident (cooperative launch) */
+    ctx->max_blocks = ctx->num_sms; /* one persistent 512-thread CTA per SM, all co-resident (cooperative launch) */
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
         fail(NULL, HFG_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));

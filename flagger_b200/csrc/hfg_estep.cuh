@@ -39,7 +39,7 @@
 
 namespace cg = cooperative_groups;
 
-#define HFG_THREADS 256
+#define HFG_THREADS 512
 #define HFG_WARPS (HFG_THREADS / 32)
 
 /* Per-region derived tables in shared memory (doubles):
@@ -195,10 +195,11 @@ __device__ __forceinline__ void mat_mul_inplace_left(double (&A)[16], const doub
     }
 }
 
-/* inclusive prefix products over the lanes of a warp: P_l <- P_0 * ... * P_l */
+/* inclusive prefix products over the first N lanes of a warp: P_l <- P_0 * ... * P_l */
+template <int N>
 __device__ __forceinline__ void warp_scan_prefix(double (&P)[16], int lane) {
 #pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
+    for (int off = 1; off < N; off <<= 1) {
         double Q[16];
         mat_shfl_up(P, Q, off);
         if (lane >= off) {
@@ -210,13 +211,14 @@ __device__ __forceinline__ void warp_scan_prefix(double (&P)[16], int lane) {
     }
 }
 
-/* inclusive suffix products: P_l <- P_l * ... * P_31 */
+/* inclusive suffix products over the first N lanes: P_l <- P_l * ... * P_{N-1} */
+template <int N>
 __device__ __forceinline__ void warp_scan_suffix(double (&P)[16], int lane) {
 #pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
+    for (int off = 1; off < N; off <<= 1) {
         double Q[16];
         mat_shfl_down(P, Q, off);
-        if (lane + off < 32) {
+        if (lane + off < N) {
             mat_mul_inplace_left(P, Q);
             mat_rescale(P);
         }
@@ -395,7 +397,7 @@ __device__ __forceinline__ double trans_prob(const double *rt, const Win &w, int
 
 /* ---------------------------------------------------------------------------------------------------------- */
 
-__global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepArgs A) {
+__global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepArgs A) {
     using namespace hfgk;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double smem[];
@@ -569,7 +571,7 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
         double S[16], Q[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) S[i] = P[i];
-        warp_scan_prefix(S, lane);
+        warp_scan_prefix<32>(S, lane);
         if (lane == 31) {
 #pragma unroll
             for (int i = 0; i < 16; i++) warp_tot[warp * 16 + i] = S[i];
@@ -578,25 +580,24 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
         if (lane == 0) mat_identity(Q);
 #pragma unroll
         for (int i = 0; i < 16; i++) acc[(size_t) i * LD + tid] = Q[i]; /* exclusive prefix inside the warp */
-        warp_scan_suffix(P, lane);
+        warp_scan_suffix<32>(P, lane);
         mat_shfl_down(P, Q, 1);
         if (lane == 31) mat_identity(Q);
 #pragma unroll
         for (int i = 0; i < 16; i++) acc[(size_t) (16 + i) * LD + tid] = Q[i]; /* exclusive suffix inside the warp */
     }
     __syncthreads();
-    /* warp 0: scan the warp products of this block */
+    /* second level over the HFG_WARPS warp products of this block: warp 0 builds the prefixes (and the block total),
+     * warp 1 the suffixes, concurrently */
     if (warp == 0) {
-        double Sp[16], Ss[16], Q[16];
+        double Sp[16], Q[16];
         if (lane < HFG_WARPS) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) Sp[i] = Ss[i] = warp_tot[lane * 16 + i];
+            for (int i = 0; i < 16; i++) Sp[i] = warp_tot[lane * 16 + i];
         } else {
             mat_identity(Sp);
-            mat_identity(Ss);
         }
-        warp_scan_prefix(Sp, lane);
-        warp_scan_suffix(Ss, lane);
+        warp_scan_prefix<HFG_WARPS>(Sp, lane);
         if (lane == HFG_WARPS - 1) {
 #pragma unroll
             for (int i = 0; i < 16; i++) A.block_tot[(size_t) blockIdx.x * 16 + i] = Sp[i];
@@ -608,6 +609,15 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
 #pragma unroll
             for (int i = 0; i < 16; i++) warp_pre[lane * 16 + i] = Q[i];
         }
+    } else if (warp == 1) {
+        double Ss[16], Q[16];
+        if (lane < HFG_WARPS) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) Ss[i] = warp_tot[lane * 16 + i];
+        } else {
+            mat_identity(Ss);
+        }
+        warp_scan_suffix<HFG_WARPS>(Ss, lane);
         mat_shfl_down(Ss, Q, 1);
         if (lane >= HFG_WARPS - 1) mat_identity(Q);
         if (lane < HFG_WARPS) {
@@ -615,9 +625,8 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
             for (int i = 0; i < 16; i++) warp_suf[lane * 16 + i] = Q[i];
         }
     }
-    __threadfence();
     if (tid == 0) A.phase_clock[blockIdx.x * 10 + 2] = clock64();
-    grid.sync();
+    grid.sync(); /* orders the block totals written above (the barrier fences) */
     if (tid == 0) A.phase_clock[blockIdx.x * 10 + 3] = clock64();
 
     /* messages entering this block: walk to the nearest block that contains a chunk start (its product is rank-1,
@@ -900,7 +909,6 @@ __global__ void __launch_bounds__(HFG_THREADS, 2) hfg_estep_kernel(const EstepAr
             for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
             if (lane == 0) A.partials[((size_t) blockIdx.x * R + r) * NSTAT + st] = sum;
         }
-        __threadfence();
         if (tid == 0) A.phase_clock[blockIdx.x * 10 + 6] = clock64();
         grid.sync();
         if (tid == 0) {
