@@ -58,16 +58,8 @@ def make_workload(name, total_bp):
 
 def shard_chunks(wl, rank, world):
     """Contiguous chunk ranges in list order, balanced by window count."""
-    if world == 1:
-        return wl
-    n = wl.chunks["n_windows"].astype(np.int64)
-    cum = np.cumsum(n)
-    total = int(cum[-1])
-    bounds = [int(np.searchsorted(cum, total * r / world, side="left")) for r in range(world + 1)]
-    bounds[0], bounds[-1] = 0, len(n)
-    for r in range(1, world + 1):
-        bounds[r] = max(bounds[r], bounds[r - 1])
-    return wl.subset(range(bounds[rank], bounds[rank + 1]), name=f"{wl.name}[rank{rank}/{world}]")
+    from flagger_b200 import dist as hdist
+    return hdist.shard_chunks(wl, rank, world)
 
 
 class ClockSampler:

@@ -49,8 +49,26 @@ EXPORTED_SYMBOLS = (
     "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_chunks", "hfg_num_windows", "hfg_em_iteration",
     "hfg_forward_only", "hfg_get_posteriors", "hfg_get_chunk_logliks", "hfg_em_iteration_device",
     "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
-    "hfg_run_em", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_debug_phase_clocks", "hfg_debug_exp",
+    "hfg_run_em", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
 )
+
+
+def layout_check(cfg, wl, capacity):
+    """Host-only self-check of the segment layout (returns (ok, summary[n_seg, smax, n_edge, windows]))."""
+    summary = np.zeros(4, np.int64)
+    chunks = np.ascontiguousarray(wl.chunks)
+    rc = lib().hfg_debug_layout_check(ptr(np.ascontiguousarray(cfg)), C.c_int32(len(chunks)), ptr(chunks),
+                                      ptr(np.ascontiguousarray(wl.cov, np.uint16)),
+                                      ptr(np.ascontiguousarray(wl.cov_high_mapq, np.uint16)),
+                                      ptr(np.ascontiguousarray(wl.cov_high_clip, np.uint16)),
+                                      ptr(np.ascontiguousarray(wl.region, np.uint8)), C.c_int32(capacity), ptr(summary))
+    return rc == 0, summary
+
+
+def beta(cfg, chunk_desc, window):
+    f = lib().hfg_debug_beta
+    f.restype = C.c_double
+    return float(f(ptr(np.ascontiguousarray(cfg)), ptr(np.ascontiguousarray(chunk_desc)), C.c_int(window)))
 
 
 def best_num_collapsed_comps(max_coverage, region_coverages):

@@ -63,8 +63,10 @@ int hfg_model_init(const hfg_config *cfg, const int32_t *region_coverages, int w
                 p->weight[s][c] = 1.0 / cfg->n_comps[s];   /* hmm_utils.c:667 */
             }
         }
-        p->lambda = 1.0;                                   /* hmm_utils.c:1619 */
-        p->trunc_point = hap * region_scale * TRUNC_POINT_FRACTION;
+        if (cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN) {
+            p->lambda = 1.0;                               /* hmm_utils.c:1619 */
+            p->trunc_point = hap * region_scale * TRUNC_POINT_FRACTION;
+        }
         for (int i = 0; i <= HFG_NS; i++)
             for (int j = 0; j <= HFG_NS; j++) p->trans[i][j] = i == j ? on_diag : off_diag; /* hmm_utils.c:2113-2116 */
         for (int s = 0; s < HFG_NS; s++) {

@@ -229,3 +229,60 @@ void hfg_classes_build(const hfg_config *cfg, const double *alpha, hfg_classes *
     }
     out->n_classes = d;
 }
+
+/* Host-only self-check of the layout builder (no GPU): rebuilds the layout for `capacity` segment slots and verifies
+ * that every window appears exactly once, in order, with the right packed fields, and that no segment straddles a chunk
+ * or a region change.  summary = {n_seg, smax, n_edge, windows}.  Returns HFG_OK or HFG_ERR_INVALID. */
+int hfg_debug_layout_check(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                           const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
+                           int32_t capacity, int64_t *summary) {
+    hfg_layout l;
+    char err[256];
+    int rc = hfg_layout_build(cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, capacity, &l, err,
+                              sizeof(err));
+    if (rc != HFG_OK) return rc;
+    int64_t next = 0, edges = 0;
+    int bad = 0;
+    for (int32_t j = 0; j < l.n_seg && !bad; j++) {
+        const int c = l.seg_chunk[j];
+        if (l.seg_start[j] != next || l.seg_len[j] < 1 || l.seg_len[j] > l.smax) bad = 1;
+        if (l.seg_edge_begin[j] != edges) bad = 1;
+        for (int k = 0; k < l.seg_len[j] && !bad; k++) {
+            const int64_t g = l.seg_start[j] + k;
+            const int w = (int) (g - chunks[c].offset);
+            const uint32_t word = l.obsT[(size_t) k * capacity + j];
+            if (w < 0 || w >= chunks[c].n_windows) bad = 1;
+            if (!(word & HFG_OBS_VALID) || HFG_OBS_X(word) != (uint8_t) cov[g] || HFG_OBS_REGION(word) != region[g]) bad = 1;
+            if (HFG_OBS_REGION(word) != region[l.seg_start[j]]) bad = 1; /* one region per segment */
+            if (HFG_OBS_PX(word) != (w > 0 ? (uint8_t) cov[g - 1] : 0)) bad = 1;
+            if (((word & HFG_OBS_CHUNK_START) != 0) != (w == 0) || (w == 0 && k != 0)) bad = 1;
+            if (((word & HFG_OBS_SECOND) != 0) != (w == 1)) bad = 1;
+            if (((word & HFG_OBS_CHUNK_END) != 0) != (w == chunks[c].n_windows - 1)) bad = 1;
+            if (((word & HFG_OBS_REGION_CHANGE) != 0) != (w > 0 && region[g] != region[g - 1])) bad = 1;
+            if ((word & HFG_OBS_REGION_CHANGE) && k != 0) bad = 1; /* a region change starts a segment */
+            if (HFG_OBS_MASK(word) != validity_mask(cfg, cov[g], cov_high_mapq[g], cov_high_clip[g])) bad = 1;
+            if (word & HFG_OBS_EDGE) {
+                const double b = hfg_beta(cfg, &chunks[c], w);
+                if (l.edge_beta[3 * edges] != b || b == l.beta0) bad = 1;
+                edges++;
+            } else if (hfg_beta(cfg, &chunks[c], w) != l.beta0) bad = 1;
+        }
+        for (int k = l.seg_len[j]; k < l.smax && !bad; k++)
+            if (l.obsT[(size_t) k * capacity + j] != 0) bad = 1; /* padding */
+        next += l.seg_len[j];
+    }
+    for (int32_t j = l.n_seg; j < capacity && !bad; j++)
+        if (l.seg_len[j] != 0) bad = 1;
+    if (next != l.n_windows || edges != l.n_edge || l.n_seg > capacity) bad = 1;
+    if (summary) {
+        summary[0] = l.n_seg;
+        summary[1] = l.smax;
+        summary[2] = l.n_edge;
+        summary[3] = l.n_windows;
+    }
+    hfg_layout_free(&l);
+    return bad ? HFG_ERR_INVALID : HFG_OK;
+}
+
+/* EM_computeAdjustmentBeta through the C-ABI, for tests */
+double hfg_debug_beta(const hfg_config *cfg, const hfg_chunk_desc *chunk, int window) { return hfg_beta(cfg, chunk, window); }

@@ -329,8 +329,10 @@ int orc_model_init(const hfg_config *cfg, const int32_t *region_coverages, int w
                 p->weight[s][c] = 1.0 / cfg->n_comps[s]; /* hmm_utils.c:667 */
             }
         }
-        p->lambda = 1.0;                                            /* hmm_utils.c:1619 */
-        p->trunc_point = p->mean[HFG_STATE_HAP][0] * ORC_TRUNC_FRACTION;
+        if (cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN) {
+            p->lambda = 1.0;                                        /* hmm_utils.c:1619 */
+            p->trunc_point = p->mean[HFG_STATE_HAP][0] * ORC_TRUNC_FRACTION;
+        }
         double off = (1.0 - ORC_DIAG) / (NS - 1) * (1.0 - ORC_TERM);
         double diag = ORC_DIAG * (1.0 - ORC_TERM);
         for (int i = 0; i < NS + 1; i++)

@@ -335,3 +335,28 @@ double ref_step(void *handle, int threads, double tol, double *loglik) {
 }
 
 void ref_close(void *handle) { teardown(handle); }
+
+/* getBestNumberOfCollapsedComps (src/hmm_flagger.c:105-111) on a one-window stand-in chunk that carries the maximum
+ * coverage, followed by the clamp that main() applies (src/hmm_flagger.c:1012-1013). */
+int ref_best_num_collapsed_comps(int max_coverage, const int32_t *region_coverages, int n_regions) {
+    ChunksCreator cc;
+    memset(&cc, 0, sizeof(cc));
+    CoverageHeader header;
+    memset(&header, 0, sizeof(header));
+    header.numberOfRegions = n_regions;
+    header.regionCoverages = malloc(sizeof(int) * n_regions);
+    for (int r = 0; r < n_regions; r++) header.regionCoverages[r] = region_coverages[r];
+    cc.header = &header;
+    cc.chunks = stList_construct3(0, NULL);
+    Chunk *chunk = Chunk_constructWithAllocatedSeq(20000000, 4000, 1);
+    chunk->coverageInfoSeqLen = 1;
+    chunk->coverageInfoSeq[0]->coverage = (u_int16_t) max_coverage;
+    stList_append(cc.chunks, chunk);
+    int k = getBestNumberOfCollapsedComps(&cc);
+    k = k < 2 ? 2 : k;
+    k = k > 10 ? 10 : k;
+    Chunk_destruct(chunk);
+    stList_destruct(cc.chunks);
+    free(header.regionCoverages);
+    return k;
+}

@@ -1,0 +1,19 @@
+"""Load a golden fixture (tests/golden/*.npz, made by tests/golden/make_golden.py from the unmodified reference)."""
+import glob
+import os
+
+import numpy as np
+
+from flagger_b200 import synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    wl = synth.Workload(name, int(g["window_len"]), 0, int(g["cfg"]["mean_read_length"][0]), g["region_coverages"],
+                        ["ctg"] * len(g["chunks"]), g["chunks"], g["cov"], g["cov_high_mapq"], g["cov_high_clip"],
+                        g["region"], np.full(len(g["cov"]), -1, np.int8))
+    return g, wl

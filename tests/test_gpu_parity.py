@@ -152,3 +152,48 @@ def test_custom_exp_accuracy():
     # below the clamp the result is the clamp value (far under the 1e-40 floor applied to every pdf)
     assert gpu.debug_exp(np.array([-1e4]))[0] == gpu.debug_exp(np.array([-708.0]))[0] < 1e-300
     gpu.close()
+
+
+import golden_util  # noqa: E402
+
+
+@pytest.mark.parametrize("name", golden_util.NAMES)
+def test_gpu_against_reference_golden(name):
+    """CUDA path against vectors produced by the UNMODIFIED reference (tests/golden/make_golden.py)."""
+    g, wl = golden_util.load(name)
+    cfg, alpha = g["cfg"].copy(), g["alpha"]
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    stats, ll, labels = gpu.em_iteration(alpha, g["params0"])
+    assert abs(ll - float(g["loglik"])) <= TOL_LOGLIK * abs(float(g["loglik"]))
+    assert np.array_equal(labels, g["labels"])
+    post = gpu.posteriors()
+    big = g["posteriors"] > 1e-200
+    assert np.all(_rel(post[big], g["posteriors"][big]) <= TOL_POST)
+    so = _abi.stats_as_flat(g["stats"])
+    assert np.all(np.abs(_abi.stats_as_flat(stats) - so) <= TOL_STATS * np.abs(so).max())
+    cl = gpu.chunk_logliks()
+    assert np.all(np.abs(cl - g["chunk_logliks"]) <= 1e-9 * np.abs(g["chunk_logliks"]) + 1e-9)
+    assert abs(gpu.forward_only(alpha, g["params1"]) - float(g["fwd_only_loglik"])) <= TOL_LOGLIK * abs(float(g["fwd_only_loglik"]))
+    pg, llg, labg = gpu.run_em(alpha, g["params0"], 5, tol=1e-12)
+    assert np.all(np.abs(llg - g["em_logliks"]) <= TOL_LOGLIK * np.abs(g["em_logliks"]))
+    assert np.array_equal(labg, g["em_labels"])
+    assert np.allclose(_abi.params_as_flat(pg), _abi.params_as_flat(g["em_params"]), rtol=1e-8, atol=0)
+    gpu.close()
+
+
+def test_error_scale_underflow_is_reported(orc):
+    """The reference exits with "scale is very low" when a forward scale drops below 1e-50 (hmm.c:412-415).  Reachable
+    only with degenerate inputs: here Dup and Col are masked out by the MAPQ ratio, Err has zero density above its
+    truncation point and every transition into Hap is zero, so no path survives."""
+    wl = synth.small_mixed(n_regions=1, seed=4)
+    wl.cov[:] = 40
+    wl.cov_high_mapq[:] = 20  # ratio ~0.5: Dup invalid (> 0.25) and Col invalid (< 0.75)
+    cfg = _abi.make_config(n_col_comps=3)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    params["trans"][0, :4, 2] = 0.0
+    assert orc.estep(cfg, wl, np.zeros((4, 4)), params)["rc"] == _abi.ERR_SCALE_UNDERFLOW
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    with pytest.raises(api.HfgError) as e:
+        gpu.em_iteration(np.zeros((4, 4)), params)
+    assert e.value.code == _abi.ERR_SCALE_UNDERFLOW and "scale is very low" in str(e.value)
+    gpu.close()
