@@ -33,6 +33,8 @@ struct hfg_ctx {
     hfg_region_params *d_params[STAGE_SLOTS];
     int8_t *d_labels;
     long long *d_phase_clock;
+    void *d_arena;   /* one device allocation behind all per-run buffers */
+    int8_t *h_labels; /* pinned staging for the label read-back */
     /* pinned host staging */
     hfg_region_params *h_params[STAGE_SLOTS];
     cudaEvent_t stage_ev[STAGE_SLOTS];
@@ -107,13 +109,17 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     if (!ctx) return fail(NULL, HFG_ERR_NOMEM, "hfg_create: out of memory");
     ctx->cfg = *cfg;
     ctx->device = cfg->device;
-    cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, cfg->device);
+    /* individual attributes: cudaGetDeviceProperties costs about a millisecond */
+    struct { int multiProcessorCount; size_t sharedMemPerBlockOptin; } prop = {0, 0};
+    int optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&prop.multiProcessorCount, cudaDevAttrMultiProcessorCount, cfg->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     if (e != cudaSuccess) {
-        fail(NULL, HFG_ERR_CUDA, "cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+        fail(NULL, HFG_ERR_CUDA, "cudaDeviceGetAttribute failed: %s", cudaGetErrorString(e));
         free(ctx);
         return HFG_ERR_CUDA;
     }
+    prop.sharedMemPerBlockOptin = (size_t) optin;
     ctx->num_sms = prop.multiProcessorCount;
     const int G = total_gauss_comps(cfg);
     ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg));
@@ -148,13 +154,23 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         return HFG_ERR_CUDA;
     }
     const size_t pbytes = sizeof(hfg_region_params) * (size_t) cfg->n_regions;
-    for (int i = 0; i < STAGE_SLOTS; i++) {
-        if (cudaMallocHost((void **) &ctx->h_params[i], pbytes) != cudaSuccess ||
-            cudaMalloc((void **) &ctx->d_params[i], pbytes) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+    {
+        /* one pinned and one device block for the ring of parameter staging slots */
+        char *hp = NULL, *dp = NULL;
+        if (cudaMallocHost((void **) &hp, pbytes * STAGE_SLOTS) != cudaSuccess ||
+            cudaMalloc((void **) &dp, pbytes * STAGE_SLOTS) != cudaSuccess) {
             fail(NULL, HFG_ERR_CUDA, "parameter staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
             free(ctx);
             return HFG_ERR_CUDA;
+        }
+        for (int i = 0; i < STAGE_SLOTS; i++) {
+            ctx->h_params[i] = (hfg_region_params *) (hp + pbytes * i);
+            ctx->d_params[i] = (hfg_region_params *) (dp + pbytes * i);
+            if (cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming) != cudaSuccess) {
+                fail(NULL, HFG_ERR_CUDA, "event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+                free(ctx);
+                return HFG_ERR_CUDA;
+            }
         }
     }
     ctx->last_params = (hfg_region_params *) malloc(pbytes);
@@ -163,17 +179,18 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
 }
 
 static void free_device(hfg_ctx *ctx) {
-    cudaFree(ctx->d_obsT); cudaFree(ctx->d_seg_start); cudaFree(ctx->d_seg_len); cudaFree(ctx->d_seg_edge_begin);
-    cudaFree(ctx->d_block_reset); cudaFree(ctx->d_err); cudaFree(ctx->d_edge_beta); cudaFree(ctx->d_scrE);
-    cudaFree(ctx->d_scrF); cudaFree(ctx->d_scrC); cudaFree(ctx->d_block_tot); cudaFree(ctx->d_partials);
-    cudaFree(ctx->d_out); cudaFree(ctx->d_seg_loglik); cudaFree(ctx->d_post); cudaFree(ctx->d_labels);
-    cudaFree(ctx->d_phase_clock); ctx->d_phase_clock = NULL;
+    cudaFree(ctx->d_arena);
+    cudaFree(ctx->d_post);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_labels) cudaFreeHost(ctx->h_labels);
+    ctx->d_arena = NULL;
     ctx->d_obsT = NULL; ctx->d_seg_start = ctx->d_seg_len = ctx->d_seg_edge_begin = ctx->d_block_reset = ctx->d_err = NULL;
     ctx->d_edge_beta = ctx->d_scrE = ctx->d_scrF = ctx->d_scrC = ctx->d_block_tot = ctx->d_partials = NULL;
     ctx->d_out = ctx->d_seg_loglik = ctx->d_post = NULL;
     ctx->d_labels = NULL;
+    ctx->d_phase_clock = NULL;
     ctx->h_out = NULL;
+    ctx->h_labels = NULL;
     hfg_layout_free(&ctx->lay);
     ctx->have_chunks = 0;
 }
@@ -183,11 +200,9 @@ extern "C" void hfg_destroy(hfg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_device(ctx);
-    for (int i = 0; i < STAGE_SLOTS; i++) {
-        cudaFreeHost(ctx->h_params[i]);
-        cudaFree(ctx->d_params[i]);
-        cudaEventDestroy(ctx->stage_ev[i]);
-    }
+    cudaFreeHost(ctx->h_params[0]);
+    cudaFree(ctx->d_params[0]);
+    for (int i = 0; i < STAGE_SLOTS; i++) cudaEventDestroy(ctx->stage_ev[i]);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -225,23 +240,46 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     const size_t slots = (size_t) l->smax * cap;
     const int R = ctx->cfg.n_regions, G = total_gauss_comps(&ctx->cfg);
     const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
-    CU(cudaMalloc((void **) &ctx->d_obsT, slots * sizeof(uint32_t)));
-    CU(cudaMalloc((void **) &ctx->d_seg_start, cap * sizeof(int32_t)));
-    CU(cudaMalloc((void **) &ctx->d_seg_len, cap * sizeof(int32_t)));
-    CU(cudaMalloc((void **) &ctx->d_seg_edge_begin, ((size_t) cap + 1) * sizeof(int32_t)));
-    CU(cudaMalloc((void **) &ctx->d_edge_beta, (size_t) (l->n_edge > 0 ? l->n_edge : 1) * 3 * sizeof(double)));
-    CU(cudaMalloc((void **) &ctx->d_scrE, slots * HFG_MAX_CLASSES * sizeof(double)));
-    CU(cudaMalloc((void **) &ctx->d_scrF, slots * 4 * sizeof(double)));
-    CU(cudaMalloc((void **) &ctx->d_scrC, slots * sizeof(double)));
-    CU(cudaMalloc((void **) &ctx->d_block_tot, (size_t) ctx->grid * 16 * sizeof(double)));
-    CU(cudaMalloc((void **) &ctx->d_block_reset, (size_t) ctx->grid * sizeof(int32_t)));
-    CU(cudaMalloc((void **) &ctx->d_partials, (size_t) ctx->grid * R * hfg_nstat(G) * sizeof(double)));
-    CU(cudaMalloc((void **) &ctx->d_out, out_doubles * sizeof(double)));
-    CU(cudaMalloc((void **) &ctx->d_seg_loglik, cap * sizeof(double)));
-    CU(cudaMalloc((void **) &ctx->d_labels, (size_t) l->n_windows));
-    CU(cudaMalloc((void **) &ctx->d_err, sizeof(int32_t)));
-    CU(cudaMalloc((void **) &ctx->d_phase_clock, (size_t) ctx->grid * 10 * sizeof(long long)));
+    /* one device allocation carved into the per-run buffers (cudaMalloc is the slow part of a short job) */
+    {
+        size_t off = 0;
+#define CARVE(bytes) (off = (off + 255) & ~(size_t) 255, off += (bytes), off - (bytes))
+        const size_t o_obs = CARVE(slots * sizeof(uint32_t));
+        const size_t o_ss = CARVE(cap * sizeof(int32_t)), o_sl = CARVE(cap * sizeof(int32_t));
+        const size_t o_se = CARVE(((size_t) cap + 1) * sizeof(int32_t));
+        const size_t o_eb = CARVE((size_t) (l->n_edge > 0 ? l->n_edge : 1) * 3 * sizeof(double));
+        const size_t o_E = CARVE(slots * HFG_MAX_CLASSES * sizeof(double));
+        const size_t o_F = CARVE(slots * 4 * sizeof(double)), o_C = CARVE(slots * sizeof(double));
+        const size_t o_bt = CARVE((size_t) ctx->grid * 16 * sizeof(double));
+        const size_t o_br = CARVE((size_t) ctx->grid * sizeof(int32_t));
+        const size_t o_pa = CARVE((size_t) ctx->grid * R * hfg_nstat(G) * sizeof(double));
+        const size_t o_out = CARVE(out_doubles * sizeof(double));
+        const size_t o_ll = CARVE(cap * sizeof(double));
+        const size_t o_lab = CARVE((size_t) l->n_windows);
+        const size_t o_err = CARVE(sizeof(int32_t));
+        const size_t o_pc = CARVE((size_t) ctx->grid * 10 * sizeof(long long));
+#undef CARVE
+        CU(cudaMalloc(&ctx->d_arena, off));
+        char *base = (char *) ctx->d_arena;
+        ctx->d_obsT = (uint32_t *) (base + o_obs);
+        ctx->d_seg_start = (int32_t *) (base + o_ss);
+        ctx->d_seg_len = (int32_t *) (base + o_sl);
+        ctx->d_seg_edge_begin = (int32_t *) (base + o_se);
+        ctx->d_edge_beta = (double *) (base + o_eb);
+        ctx->d_scrE = (double *) (base + o_E);
+        ctx->d_scrF = (double *) (base + o_F);
+        ctx->d_scrC = (double *) (base + o_C);
+        ctx->d_block_tot = (double *) (base + o_bt);
+        ctx->d_block_reset = (int32_t *) (base + o_br);
+        ctx->d_partials = (double *) (base + o_pa);
+        ctx->d_out = (double *) (base + o_out);
+        ctx->d_seg_loglik = (double *) (base + o_ll);
+        ctx->d_labels = (int8_t *) (base + o_lab);
+        ctx->d_err = (int32_t *) (base + o_err);
+        ctx->d_phase_clock = (long long *) (base + o_pc);
+    }
     CU(cudaMallocHost((void **) &ctx->h_out, out_doubles * sizeof(double)));
+    CU(cudaMallocHost((void **) &ctx->h_labels, (size_t) l->n_windows));
     CU(cudaMemcpyAsync(ctx->d_obsT, l->obsT, slots * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_start, l->seg_start, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_len, l->seg_len, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -380,8 +418,9 @@ static int fetch_out(hfg_ctx *ctx, hfg_region_stats *stats, double *loglik, int8
     const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
     CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (with_labels && labels)
-        CU(cudaMemcpyAsync(labels, ctx->d_labels, (size_t) ctx->lay.n_windows, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_labels, ctx->d_labels, (size_t) ctx->lay.n_windows, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (with_labels && labels) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
     const int flags = (int) ctx->h_out[out_doubles - 1];
     if (flags & 1)
         return fail(ctx, HFG_ERR_SCALE_UNDERFLOW, "scale is very low! (a forward scale fell below 1e-50; hmm.c:412-415)");

@@ -10,8 +10,11 @@
 #include <string.h>
 #include <stdio.h>
 #include <math.h>
+#include <pthread.h>
 
 #include "hfg_internal.h"
+
+#define HFG_PACK_THREADS 16
 
 /* submodules/common/common.c:142-148: min/max are int functions; double arguments are truncated at the call */
 static int imin_(int a, int b) { return a < b ? a : b; }
@@ -51,26 +54,76 @@ void hfg_layout_free(hfg_layout *l) {
     memset(l, 0, sizeof(*l));
 }
 
-/* Cost of a window in units of an ordinary window: contig-end (edge) windows take the generic emission path
- * with per-window factors; the kernel folds them into the tabulated constants, so they cost the same as any other
- * window (HFG_EDGE_COST 1).  The cost-based cut is kept so that a costlier special path can be balanced by data. */
-#define HFG_EDGE_COST 1
+/* ---- segmentation ------------------------------------------------------------------------------------------------
+ * A "run" is a maximal stretch of windows of one chunk with one region index; segments are the runs cut into pieces of
+ * at most smax windows.  Contig-end ("edge") windows -- beta different from the interior constant -- form a prefix and a
+ * suffix of their chunk: beta(i) = (min(mid,U) - max(mid-Lr+1,Lo))/Lr is concave piecewise linear in mid, mid is
+ * non-decreasing in i, so the windows that reach the plateau (Lr-1)/Lr are contiguous. */
 
-/* end (exclusive) of the segment that starts at window i of a chunk: same region, accumulated cost <= smax */
-static int segment_end(const uint8_t *region, const uint8_t *cost, int L, int i, int smax) {
-    int j = i + 1, acc = cost[i] & 0x7f; /* bit 7 of cost[] flags an edge window, the low bits are the cost */
-    while (j < L && region[j] == region[i] && acc + (cost[j] & 0x7f) <= smax) acc += cost[j++] & 0x7f;
-    return j;
+typedef struct Run {
+    int32_t chunk;
+    int32_t first; /* window index inside the chunk */
+    int32_t len;
+} Run;
+
+static int64_t segments_for(const Run *runs, int64_t n_runs, int smax) {
+    int64_t n = 0;
+    for (int64_t i = 0; i < n_runs; i++) n += (runs[i].len + smax - 1) / smax;
+    return n;
 }
 
-static int64_t count_segments(int32_t n_chunks, const hfg_chunk_desc *chunks, const uint8_t *region,
-                              const uint8_t *cost, int smax) {
-    int64_t n = 0;
-    for (int32_t c = 0; c < n_chunks; c++) {
-        const int64_t o = chunks[c].offset;
-        const int L = chunks[c].n_windows;
-        for (int i = 0; i < L; n++) i = segment_end(region + o, cost + o, L, i, smax);
+typedef struct PackJob {
+    const hfg_config *cfg;
+    const hfg_chunk_desc *chunks;
+    const uint16_t *cov, *mapq, *clip;
+    const uint8_t *region;
+    const int32_t *edge_head, *edge_tail; /* per chunk: number of leading / trailing edge windows */
+    hfg_layout *out;
+    int32_t seg_begin, seg_end;
+} PackJob;
+
+/* fills the packed words (and edge factors) of segments [seg_begin, seg_end) -- independent across segments */
+static void *pack_segments(void *arg) {
+    PackJob *jb = arg;
+    hfg_layout *out = jb->out;
+    const int capacity = out->capacity;
+    for (int32_t seg = jb->seg_begin; seg < jb->seg_end; seg++) {
+        const int c = out->seg_chunk[seg];
+        const hfg_chunk_desc *ch = &jb->chunks[c];
+        const int64_t o = ch->offset;
+        const int L = ch->n_windows, a = (int) (out->seg_start[seg] - o), len = out->seg_len[seg];
+        int64_t e = out->seg_edge_begin[seg];
+        for (int k = 0; k < len; k++) {
+            const int w = a + k;
+            const int64_t g = o + w;
+            uint32_t word = HFG_OBS_VALID;
+            word |= (uint32_t) (uint8_t) jb->cov[g];
+            if (w > 0) word |= (uint32_t) (uint8_t) jb->cov[g - 1] << 8;
+            word |= (uint32_t) jb->region[g] << 16;
+            word |= validity_mask(jb->cfg, jb->cov[g], jb->mapq[g], jb->clip[g]) << 22;
+            if (w > 0 && jb->region[g] != jb->region[g - 1]) word |= HFG_OBS_REGION_CHANGE;
+            if (w == 0) word |= HFG_OBS_CHUNK_START;
+            if (w == 1) word |= HFG_OBS_SECOND;
+            if (w == L - 1) word |= HFG_OBS_CHUNK_END;
+            if (w < jb->edge_head[c] || w >= L - jb->edge_tail[c]) {
+                /* (beta, beta0/beta, sqrt(beta0/beta)) */
+                const double b = hfg_beta(jb->cfg, ch, w);
+                word |= HFG_OBS_EDGE;
+                out->edge_beta[3 * e] = b;
+                out->edge_beta[3 * e + 1] = out->beta0 / b;
+                out->edge_beta[3 * e + 2] = sqrt(out->beta0 / b);
+                e++;
+            }
+            out->obsT[(size_t) k * capacity + seg] = word;
+        }
     }
+    return NULL;
+}
+
+/* number of edge windows among the first w windows of chunk c */
+static int64_t edges_before(int head, int tail, int L, int w) {
+    int64_t n = w < head ? w : head;
+    if (w > L - tail) n += w - (L - tail);
     return n;
 }
 
@@ -90,32 +143,62 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
         snprintf(err, errlen, "number of windows (%lld) out of range", (long long) W);
         return HFG_ERR_INVALID;
     }
-    for (int64_t i = 0; i < W; i++) {
-        if (region[i] >= cfg->n_regions) {
-            snprintf(err, errlen, "window %lld has region %d >= n_regions %d", (long long) i, region[i], cfg->n_regions);
-            return HFG_ERR_INVALID;
-        }
-    }
     const double beta0 = !cfg->adjust_contig_ends ? 1.0
                          : (cfg->mean_read_length > 0 ? (double) (cfg->mean_read_length - 1) / cfg->mean_read_length : 0.25);
-    uint8_t *cost = malloc((size_t) W);
-    if (!cost) {
-        snprintf(err, errlen, "out of host memory building the layout");
-        return HFG_ERR_NOMEM;
-    }
-    int64_t total_cost = 0;
+
+    /* pass 1: runs (one byte scan over the region indices) and the edge prefix / suffix of every chunk */
+    int64_t run_cap = 2 * (int64_t) n_chunks + 1024, n_runs = 0, n_edge = 0;
+    Run *runs = malloc(sizeof(Run) * (size_t) run_cap);
+    int32_t *edge_head = malloc(sizeof(int32_t) * (size_t) n_chunks), *edge_tail = malloc(sizeof(int32_t) * (size_t) n_chunks);
+    int64_t *chunk_edge_base = malloc(sizeof(int64_t) * ((size_t) n_chunks + 1));
+    if (!runs || !edge_head || !edge_tail || !chunk_edge_base) goto nomem;
     for (int32_t c = 0; c < n_chunks; c++) {
-        for (int i = 0; i < chunks[c].n_windows; i++) {
-            const double b = hfg_beta(cfg, &chunks[c], i);
-            cost[chunks[c].offset + i] = memcmp(&b, &beta0, sizeof(double)) != 0 ? (0x80 | HFG_EDGE_COST) : 1;
-            total_cost += cost[chunks[c].offset + i] & 0x7f;
+        const uint8_t *r = region + chunks[c].offset;
+        const int L = chunks[c].n_windows;
+        for (int i = 0; i < L;) {
+            if (r[i] >= cfg->n_regions) {
+                snprintf(err, errlen, "window %lld has region %d >= n_regions %d", (long long) (chunks[c].offset + i), r[i],
+                         cfg->n_regions);
+                free(runs); free(edge_head); free(edge_tail); free(chunk_edge_base);
+                return HFG_ERR_INVALID;
+            }
+            int j = i + 1;
+            while (j < L && r[j] == r[i]) j++;
+            if (n_runs == run_cap) {
+                run_cap *= 2;
+                Run *nr = realloc(runs, sizeof(Run) * (size_t) run_cap);
+                if (!nr) goto nomem;
+                runs = nr;
+            }
+            runs[n_runs].chunk = c;
+            runs[n_runs].first = i;
+            runs[n_runs].len = j - i;
+            n_runs++;
+            i = j;
         }
+        int head = 0, tail = 0;
+        while (head < L) {
+            const double b = hfg_beta(cfg, &chunks[c], head);
+            if (memcmp(&b, &beta0, sizeof(double)) == 0) break;
+            head++;
+        }
+        while (tail < L - head) {
+            const double b = hfg_beta(cfg, &chunks[c], L - 1 - tail);
+            if (memcmp(&b, &beta0, sizeof(double)) == 0) break;
+            tail++;
+        }
+        edge_head[c] = head;
+        edge_tail[c] = tail;
+        chunk_edge_base[c] = n_edge;
+        n_edge += head + tail;
     }
-    /* smallest cost budget whose segment count fits the persistent grid */
-    int smax = (int) ((total_cost + capacity - 1) / capacity);
-    if (smax < HFG_EDGE_COST) smax = HFG_EDGE_COST;
-    while (count_segments(n_chunks, chunks, region, cost, smax) > capacity) smax += (smax + 7) / 8;
-    const int64_t n_seg = count_segments(n_chunks, chunks, region, cost, smax);
+    chunk_edge_base[n_chunks] = n_edge;
+
+    /* smallest smax whose segment count fits the persistent grid */
+    int smax = (int) ((W + capacity - 1) / capacity);
+    if (smax < 1) smax = 1;
+    while (segments_for(runs, n_runs, smax) > capacity) smax += (smax + 7) / 8;
+    const int64_t n_seg = segments_for(runs, n_runs, smax);
 
     out->n_windows = W;
     out->n_chunks = n_chunks;
@@ -123,80 +206,60 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
     out->smax = smax;
     out->n_seg = (int32_t) n_seg;
     out->beta0 = beta0;
+    out->n_edge = n_edge;
     out->obsT = calloc((size_t) smax * capacity, sizeof(uint32_t));
     out->seg_start = calloc((size_t) capacity, sizeof(int32_t));
     out->seg_len = calloc((size_t) capacity, sizeof(int32_t));
     out->seg_chunk = calloc((size_t) capacity, sizeof(int32_t));
     out->seg_edge_begin = calloc((size_t) capacity + 1, sizeof(int32_t));
     out->chunk_offset = calloc((size_t) n_chunks + 1, sizeof(int64_t));
-    int64_t edge_cap = 1024, n_edge = 0;
-    out->edge_beta = malloc(sizeof(double) * 3 * (size_t) edge_cap);
-    if (!out->obsT || !out->seg_start || !out->seg_len || !out->seg_chunk || !out->seg_edge_begin ||
-        !out->edge_beta || !out->chunk_offset) {
-        free(cost);
-        hfg_layout_free(out);
-        snprintf(err, errlen, "out of host memory building the layout");
-        return HFG_ERR_NOMEM;
-    }
+    out->edge_beta = malloc(sizeof(double) * 3 * (size_t) (n_edge > 0 ? n_edge : 1));
+    if (!out->obsT || !out->seg_start || !out->seg_len || !out->seg_chunk || !out->seg_edge_begin || !out->edge_beta ||
+        !out->chunk_offset)
+        goto nomem;
 
-    int32_t seg = 0;
-    for (int32_t c = 0; c < n_chunks; c++) {
-        const hfg_chunk_desc *ch = &chunks[c];
-        const int64_t o = ch->offset;
-        const int L = ch->n_windows;
-        out->chunk_offset[c] = o;
-        for (int a = 0; a < L;) {
-            const int end = segment_end(region + o, cost + o, L, a, smax);
-            const int len = end - a;
-            out->seg_start[seg] = (int32_t) (o + a);
-            out->seg_len[seg] = len;
-            out->seg_chunk[seg] = c;
-            out->seg_edge_begin[seg] = (int32_t) n_edge;
-            for (int k = 0; k < len; k++) {
-                const int w = a + k; /* window index inside the chunk */
-                const int64_t g = o + w;
-                uint32_t word = HFG_OBS_VALID;
-                word |= (uint32_t) (uint8_t) cov[g];
-                if (w > 0) word |= (uint32_t) (uint8_t) cov[g - 1] << 8;
-                word |= (uint32_t) region[g] << 16;
-                word |= validity_mask(cfg, cov[g], cov_high_mapq[g], cov_high_clip[g]) << 22;
-                if (w > 0 && region[g] != region[g - 1]) word |= HFG_OBS_REGION_CHANGE;
-                if (w == 0) word |= HFG_OBS_CHUNK_START;
-                if (w == 1) word |= HFG_OBS_SECOND;
-                if (w == L - 1) word |= HFG_OBS_CHUNK_END;
-                if (cost[g] & 0x80) {
-                    word |= HFG_OBS_EDGE;
-                    if (n_edge == edge_cap) {
-                        edge_cap *= 2;
-                        double *nb = realloc(out->edge_beta, sizeof(double) * 3 * (size_t) edge_cap);
-                        if (!nb) {
-                            free(cost);
-                            hfg_layout_free(out);
-                            snprintf(err, errlen, "out of host memory building the layout");
-                            return HFG_ERR_NOMEM;
-                        }
-                        out->edge_beta = nb;
-                    }
-                    {
-                        /* (beta, beta0/beta, sqrt(beta0/beta)) */
-                        const double b = hfg_beta(cfg, ch, w);
-                        out->edge_beta[3 * n_edge] = b;
-                        out->edge_beta[3 * n_edge + 1] = beta0 / b;
-                        out->edge_beta[3 * n_edge + 2] = sqrt(beta0 / b);
-                        n_edge++;
-                    }
-                }
-                out->obsT[(size_t) k * capacity + seg] = word;
+    /* pass 2: the segment table (O(#segments)) */
+    {
+        int32_t seg = 0;
+        for (int64_t i = 0; i < n_runs; i++) {
+            const int c = runs[i].chunk, L = chunks[c].n_windows;
+            for (int a = 0; a < runs[i].len; a += smax, seg++) {
+                const int w = runs[i].first + a;
+                out->seg_start[seg] = (int32_t) (chunks[c].offset + w);
+                out->seg_len[seg] = runs[i].len - a < smax ? runs[i].len - a : smax;
+                out->seg_chunk[seg] = c;
+                out->seg_edge_begin[seg] = (int32_t) (chunk_edge_base[c] + edges_before(edge_head[c], edge_tail[c], L, w));
             }
-            seg++;
-            a = end;
         }
+        for (int32_t j = seg; j <= capacity; j++) out->seg_edge_begin[j] = (int32_t) n_edge;
     }
-    free(cost);
-    out->chunk_offset[n_chunks] = W;
-    for (int32_t j = seg; j <= capacity; j++) out->seg_edge_begin[j] = (int32_t) n_edge;
-    out->n_edge = n_edge;
+    for (int32_t c = 0; c <= n_chunks; c++) out->chunk_offset[c] = c < n_chunks ? chunks[c].offset : W;
+
+    /* pass 3: pack the observation words, in parallel over segments (pthreads, as the reference's own parser) */
+    {
+        int n_threads = (int) (W / 65536) + 1;
+        if (n_threads > HFG_PACK_THREADS) n_threads = HFG_PACK_THREADS;
+        PackJob jobs[HFG_PACK_THREADS];
+        pthread_t tids[HFG_PACK_THREADS];
+        for (int t = 0; t < n_threads; t++) {
+            jobs[t] = (PackJob){cfg, chunks, cov, cov_high_mapq, cov_high_clip, region, edge_head, edge_tail, out,
+                                (int32_t) (n_seg * t / n_threads), (int32_t) (n_seg * (t + 1) / n_threads)};
+            if (t > 0 && pthread_create(&tids[t], NULL, pack_segments, &jobs[t]) != 0) {
+                pack_segments(&jobs[t]); /* could not spawn: do the slice here */
+                tids[t] = 0;
+            }
+        }
+        pack_segments(&jobs[0]);
+        for (int t = 1; t < n_threads; t++)
+            if (tids[t]) pthread_join(tids[t], NULL);
+    }
+    free(runs); free(edge_head); free(edge_tail); free(chunk_edge_base);
     return HFG_OK;
+nomem:
+    free(runs); free(edge_head); free(edge_tail); free(chunk_edge_base);
+    hfg_layout_free(out);
+    snprintf(err, errlen, "out of host memory building the layout");
+    return HFG_ERR_NOMEM;
 }
 
 void hfg_classes_build(const hfg_config *cfg, const double *alpha, hfg_classes *out) {
