@@ -44,6 +44,11 @@ struct hfg_ctx {
     int have_last;
     double last_alpha[16];
     hfg_region_params *last_params;
+    /* the blocking entry points replay a captured graph (parameter upload -> kernel -> result read-back): one launch
+     * call per E-step instead of six */
+    cudaGraphExec_t gexec;
+    int graph_disabled, graph_labels;
+    EstepArgs graph_args;
     int64_t launches;
     char err[512];
 };
@@ -174,11 +179,16 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         }
     }
     ctx->last_params = (hfg_region_params *) malloc(pbytes);
+    ctx->graph_disabled = getenv("HFG_NO_GRAPH") != NULL; /* A/B switch: plain stream launches instead of graph replay */
     *out = ctx;
     return HFG_OK;
 }
 
 static void free_device(hfg_ctx *ctx) {
+    if (ctx->gexec) { /* the captured graph holds pointers into the buffers released below */
+        cudaGraphExecDestroy(ctx->gexec);
+        ctx->gexec = NULL;
+    }
     cudaFree(ctx->d_arena);
     cudaFree(ctx->d_post);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -298,28 +308,15 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
 }
 
 /* Enqueue one E-step (or forward pass) on `stream`; results land in out_dev = [stats | loglik | error flags]. */
-static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params, double *out_dev,
-                         double *post_dev, int forward_only, cudaStream_t stream, int timed) {
-    if (!ctx->have_chunks) return fail(ctx, HFG_ERR_INVALID, "hfg_set_chunks must be called first");
-    if (!alpha || !params) return fail(ctx, HFG_ERR_INVALID, "NULL alpha/params");
-    CU(cudaSetDevice(ctx->device));
+/* kernel arguments of one E-step (or forward pass) reading its parameters from staging slot `slot` */
+static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, double *post_dev, int forward_only, int slot,
+                       EstepArgs *out_args) {
     const hfg_config *cfg = &ctx->cfg;
     const hfg_layout *l = &ctx->lay;
     const int R = cfg->n_regions;
-
     hfg_classes cl;
     hfg_classes_build(cfg, alpha, &cl);
-
-    /* stage the parameters (ring of pinned buffers so that back-to-back asynchronous calls never race) */
-    const int slot = ctx->stage_next;
-    ctx->stage_next = (slot + 1) % STAGE_SLOTS;
-    CU(cudaEventSynchronize(ctx->stage_ev[slot]));
-    memcpy(ctx->h_params[slot], params, sizeof(hfg_region_params) * (size_t) R);
-    CU(cudaMemcpyAsync(ctx->d_params[slot], ctx->h_params[slot], sizeof(hfg_region_params) * (size_t) R,
-                       cudaMemcpyHostToDevice, stream));
-    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), stream));
-
-    EstepArgs a;
+    EstepArgs &a = *out_args;
     memset(&a, 0, sizeof(a));
     a.obsT = ctx->d_obsT;
     a.seg_start = ctx->d_seg_start;
@@ -394,6 +391,27 @@ static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_par
     a.err_flags = ctx->d_err;
     a.forward_only = forward_only;
     a.phase_clock = ctx->d_phase_clock;
+}
+
+/* Enqueue one E-step (or forward pass) on `stream`; results land in out_dev = [stats | loglik | error flags]. */
+static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params, double *out_dev,
+                         double *post_dev, int forward_only, cudaStream_t stream, int timed) {
+    if (!ctx->have_chunks) return fail(ctx, HFG_ERR_INVALID, "hfg_set_chunks must be called first");
+    if (!alpha || !params) return fail(ctx, HFG_ERR_INVALID, "NULL alpha/params");
+    CU(cudaSetDevice(ctx->device));
+    const int R = ctx->cfg.n_regions;
+
+    /* stage the parameters (ring of pinned buffers so that back-to-back asynchronous calls never race) */
+    const int slot = ctx->stage_next;
+    ctx->stage_next = (slot + 1) % STAGE_SLOTS;
+    CU(cudaEventSynchronize(ctx->stage_ev[slot]));
+    memcpy(ctx->h_params[slot], params, sizeof(hfg_region_params) * (size_t) R);
+    CU(cudaMemcpyAsync(ctx->d_params[slot], ctx->h_params[slot], sizeof(hfg_region_params) * (size_t) R,
+                       cudaMemcpyHostToDevice, stream));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), stream));
+
+    EstepArgs a;
+    build_args(ctx, alpha, out_dev, post_dev, forward_only, slot, &a);
 
     void *kargs[] = {(void *) &a};
     if (timed) CU(cudaEventRecord(ctx->ev0, stream));
@@ -430,19 +448,97 @@ static int fetch_out(hfg_ctx *ctx, hfg_region_stats *stats, double *loglik, int8
     return HFG_OK;
 }
 
+/* translate [stats | loglik | flags] sitting in the pinned output block */
+static int parse_out(hfg_ctx *ctx, hfg_region_stats *stats, double *loglik) {
+    const int R = ctx->cfg.n_regions;
+    const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
+    const int flags = (int) ctx->h_out[out_doubles - 1];
+    if (flags & 1)
+        return fail(ctx, HFG_ERR_SCALE_UNDERFLOW, "scale is very low! (a forward scale fell below 1e-50; hmm.c:412-415)");
+    if (flags & 2) return fail(ctx, HFG_ERR_NAN, "[Error] prob is NAN (an emission pdf evaluated to NaN; hmm_utils.c:782-786)");
+    if (stats) memcpy(stats, ctx->h_out, sizeof(hfg_region_stats) * (size_t) R);
+    if (loglik) *loglik = ctx->h_out[out_doubles - 2];
+    return HFG_OK;
+}
+
+/* (re)capture  upload params -> clear flags -> kernel -> read back results [-> read back labels]  as one graph */
+static int capture_graph(hfg_ctx *ctx, const EstepArgs *a, int with_labels) {
+    const int R = ctx->cfg.n_regions;
+    const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
+    if (ctx->gexec) {
+        cudaGraphExecDestroy(ctx->gexec);
+        ctx->gexec = NULL;
+    }
+    cudaGraph_t graph = NULL;
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) return 0;
+    EstepArgs copy = *a;
+    void *kargs[] = {(void *) &copy};
+    e = cudaMemcpyAsync(ctx->d_params[0], ctx->h_params[0], sizeof(hfg_region_params) * (size_t) R, cudaMemcpyHostToDevice,
+                        ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaLaunchCooperativeKernel((void *) hfg_estep_kernel, dim3(ctx->grid), dim3(HFG_THREADS), kargs, ctx->smem_bytes,
+                                        ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ctx->h_out, ctx->d_out, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && with_labels)
+        e = cudaMemcpyAsync(ctx->h_labels, ctx->d_labels, (size_t) ctx->lay.n_windows, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
+    if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&ctx->gexec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        cudaGetLastError(); /* clear; the direct launch path is used instead */
+        ctx->gexec = NULL;
+        return 0;
+    }
+    ctx->graph_args = *a;
+    ctx->graph_labels = with_labels;
+    return 1;
+}
+
+/* blocking E-step with host buffers: graph replay when possible, plain launches otherwise (same kernel either way) */
+static int run_blocking(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params, int forward_only,
+                        hfg_region_stats *stats, double *loglik, int8_t *labels) {
+    if (!ctx->have_chunks) return fail(ctx, HFG_ERR_INVALID, "hfg_set_chunks must be called first");
+    if (!alpha || !params) return fail(ctx, HFG_ERR_INVALID, "NULL alpha/params");
+    const int with_labels = labels != NULL;
+    if (!ctx->graph_disabled) {
+        CU(cudaSetDevice(ctx->device));
+        const int R = ctx->cfg.n_regions;
+        EstepArgs a;
+        build_args(ctx, alpha, ctx->d_out, NULL, forward_only, 0, &a);
+        CU(cudaEventSynchronize(ctx->stage_ev[0])); /* slot 0 may still feed an asynchronous device-variant call */
+        memcpy(ctx->h_params[0], params, sizeof(hfg_region_params) * (size_t) R);
+        if (!ctx->gexec || ctx->graph_labels != with_labels || memcmp(&a, &ctx->graph_args, sizeof(a)) != 0) {
+            if (!capture_graph(ctx, &a, with_labels)) ctx->graph_disabled = 1;
+        }
+        if (ctx->gexec) {
+            CU(cudaGraphLaunch(ctx->gexec, ctx->stream));
+            ctx->launches += 1;
+            memcpy(ctx->last_alpha, alpha, sizeof(double) * 16);
+            memcpy(ctx->last_params, params, sizeof(hfg_region_params) * (size_t) R);
+            ctx->have_last = 1;
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (with_labels) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
+            return parse_out(ctx, stats, loglik);
+        }
+    }
+    int rc = enqueue_estep(ctx, alpha, params, ctx->d_out, NULL, forward_only, ctx->stream, 1);
+    if (rc != HFG_OK) return rc;
+    return fetch_out(ctx, stats, loglik, labels, with_labels);
+}
+
 extern "C" int hfg_em_iteration(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params,
                                 hfg_region_stats *stats, double *loglik, int8_t *labels) {
     if (!ctx) return HFG_ERR_INVALID;
-    int rc = enqueue_estep(ctx, alpha, params, ctx->d_out, NULL, 0, ctx->stream, 1);
-    if (rc != HFG_OK) return rc;
-    return fetch_out(ctx, stats, loglik, labels, 1);
+    return run_blocking(ctx, alpha, params, 0, stats, loglik, labels);
 }
 
 extern "C" int hfg_forward_only(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params, double *loglik) {
     if (!ctx) return HFG_ERR_INVALID;
-    int rc = enqueue_estep(ctx, alpha, params, ctx->d_out, NULL, 1, ctx->stream, 1);
-    if (rc != HFG_OK) return rc;
-    return fetch_out(ctx, NULL, loglik, NULL, 0);
+    return run_blocking(ctx, alpha, params, 1, NULL, loglik, NULL);
 }
 
 extern "C" int hfg_em_iteration_device(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params,
