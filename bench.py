@@ -116,6 +116,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the E-step kernel per launch, from the committed `ncu --set full`
+    capture of this workload (profiles/ncu_traffic.json), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(workload_name)
+    except Exception:
+        return None
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -255,6 +264,21 @@ def run_ours(args):
         t_host = time.perf_counter() - t0
         return new_params, e0.elapsed_time(e1) * 1e-3 + t_host, float(flat[n_d - 2]), gpu.last_estep_kernel_ms()
 
+    stats1 = np.zeros(R, dtype=_abi.region_stats_dtype)
+
+    def resident_step_single(params):
+        """N = 1: the blocking C-ABI call without the label read-back (parameters in, statistics out; the windows stay
+        in HBM), timed on the device with the library's own CUDA events on its launching stream."""
+        s1, ll, _ = gpu.em_iteration(alpha, params, want_labels=False, stats=stats1)
+        dev_ms = gpu.last_call_device_ms()
+        t0 = time.perf_counter()
+        new_params, _ = api.mstep(cfg, params, s1, tol=1e-12)
+        t_host = time.perf_counter() - t0
+        return new_params, dev_ms * 1e-3 + t_host, ll, gpu.last_estep_kernel_ms()
+
+    if world == 1:
+        resident_step = resident_step_single
+
     # ---- resident (value) ----
     params = params0.copy()
     for _ in range(args.warmup):
@@ -305,6 +329,9 @@ def run_ours(args):
             stats = t.cpu().numpy().view(_abi.region_stats_dtype)
         params, _ = api.mstep(cfg, params, stats, tol=1e-12)
         e2e_s.append(time.perf_counter() - t0)
+    if rank == 0:
+        print(f"[bench] e2e: setup {1e3 * t_upload:.2f} ms, steps mean {1e3 * np.mean(e2e_s):.3f} ms, max "
+              f"{1e3 * np.max(e2e_s):.3f} ms", file=sys.stderr)
     e2e_total = torch.tensor([sum(e2e_s) + t_upload], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
@@ -330,8 +357,8 @@ def run_ours(args):
                        "parallelism": f"chunks sharded over {world} GPU(s), one NCCL all-reduce of the statistics per "
                                       "iteration" if world > 1 else "1 GPU",
                        "l2": "not flushed" if args.no_flush else "flushed between timed steps (256 MiB fill, untimed)",
-                       "timing": "sum over steps of [CUDA-event interval on the launching stream + host M-step], "
-                                 "max over ranks"},
+                       "timing": "sum over steps of [CUDA-event interval on the launching stream (parameter upload, "
+                                 "kernel, statistics read-back) + host M-step], max over ranks"},
             "e2e": {"value": W_total * args.steps / e2e_total, "unit": "windows/s",
                     "h2d_bytes_per_step": int(params.nbytes + obs_bytes / args.steps),
                     "d2h_bytes_per_step": int(stats.nbytes + 16 + wl.n_windows),
@@ -339,7 +366,7 @@ def run_ours(args):
                                 "statistics + labels out) + host M-step per step"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "hfg_estep_kernel", "kernel_ms": kernel_s * 1e3,
+                         "traffic": ncu_traffic(wl_full.name), "kernel": "hfg_estep_kernel", "kernel_ms": kernel_s * 1e3,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_WINDOW * wl.n_windows, "peak_source": peak_src},
             "clocks": clocks,
             "loglik_first_last": [logliks[0], logliks[-1]],

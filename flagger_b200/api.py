@@ -36,8 +36,10 @@ def lib():
         L.hfg_num_windows.restype = C.c_int64
         L.hfg_kernel_launches.restype = C.c_int64
         L.hfg_last_estep_kernel_ms.restype = C.c_double
+        L.hfg_last_call_device_ms.restype = C.c_double
         L.hfg_stats_device_bytes.restype = C.c_size_t
-        for name in ("hfg_num_windows", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_stats_device_bytes",
+        for name in ("hfg_num_windows", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_last_call_device_ms",
+                     "hfg_stats_device_bytes",
                      "hfg_destroy"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.hfg_destroy.restype = None
@@ -49,7 +51,7 @@ EXPORTED_SYMBOLS = (
     "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_chunks", "hfg_num_windows", "hfg_em_iteration",
     "hfg_forward_only", "hfg_get_posteriors", "hfg_get_chunk_logliks", "hfg_em_iteration_device",
     "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
-    "hfg_run_em", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
+    "hfg_run_em", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
 )
 
 
@@ -202,6 +204,9 @@ class HmmFlaggerGPU:
 
     def kernel_launches(self):
         return int(lib().hfg_kernel_launches(self._h))
+
+    def last_call_device_ms(self):
+        return float(lib().hfg_last_call_device_ms(self._h))
 
     def last_estep_kernel_ms(self):
         return float(lib().hfg_last_estep_kernel_ms(self._h))

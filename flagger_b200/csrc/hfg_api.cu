@@ -24,8 +24,9 @@ struct hfg_ctx {
     int device, num_sms, max_blocks, grid;
     size_t smem_bytes;
     cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
-    int ev_valid;
+    cudaEvent_t ev0, ev1; /* around the E-step kernel */
+    cudaEvent_t ev2, ev3; /* around the whole device side of the last blocking call */
+    int ev_valid, span_valid;
     /* device */
     uint32_t *d_obsT;
     int32_t *d_seg_start, *d_seg_len, *d_seg_edge_begin, *d_block_reset, *d_err;
@@ -153,7 +154,8 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     }
     ctx->max_blocks = ctx->num_sms; /* one persistent 512-thread CTA per SM, all co-resident (cooperative launch) */
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess) {
         fail(NULL, HFG_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         free(ctx);
         return HFG_ERR_CUDA;
@@ -215,6 +217,8 @@ extern "C" void hfg_destroy(hfg_ctx *ctx) {
     for (int i = 0; i < STAGE_SLOTS; i++) cudaEventDestroy(ctx->stage_ev[i]);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev2);
+    cudaEventDestroy(ctx->ev3);
     cudaStreamDestroy(ctx->stream);
     free(ctx->last_params);
     free(ctx);
@@ -477,9 +481,11 @@ static int capture_graph(hfg_ctx *ctx, const EstepArgs *a, int with_labels) {
     e = cudaMemcpyAsync(ctx->d_params[0], ctx->h_params[0], sizeof(hfg_region_params) * (size_t) R, cudaMemcpyHostToDevice,
                         ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecordWithFlags(ctx->ev0, ctx->stream, cudaEventRecordExternal); /* event-record node */
     if (e == cudaSuccess)
         e = cudaLaunchCooperativeKernel((void *) hfg_estep_kernel, dim3(ctx->grid), dim3(HFG_THREADS), kargs, ctx->smem_bytes,
                                         ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecordWithFlags(ctx->ev1, ctx->stream, cudaEventRecordExternal);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(ctx->h_out, ctx->d_out, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && with_labels)
@@ -515,7 +521,10 @@ static int run_blocking(hfg_ctx *ctx, const double *alpha, const hfg_region_para
             if (!capture_graph(ctx, &a, with_labels)) ctx->graph_disabled = 1;
         }
         if (ctx->gexec) {
+            CU(cudaEventRecord(ctx->ev2, ctx->stream));
             CU(cudaGraphLaunch(ctx->gexec, ctx->stream));
+            CU(cudaEventRecord(ctx->ev3, ctx->stream));
+            ctx->ev_valid = ctx->span_valid = 1;
             ctx->launches += 1;
             memcpy(ctx->last_alpha, alpha, sizeof(double) * 16);
             memcpy(ctx->last_params, params, sizeof(hfg_region_params) * (size_t) R);
@@ -525,9 +534,12 @@ static int run_blocking(hfg_ctx *ctx, const double *alpha, const hfg_region_para
             return parse_out(ctx, stats, loglik);
         }
     }
+    CU(cudaEventRecord(ctx->ev2, ctx->stream));
     int rc = enqueue_estep(ctx, alpha, params, ctx->d_out, NULL, forward_only, ctx->stream, 1);
     if (rc != HFG_OK) return rc;
-    return fetch_out(ctx, stats, loglik, labels, with_labels);
+    rc = fetch_out(ctx, stats, loglik, labels, with_labels);
+    if (cudaEventRecord(ctx->ev3, ctx->stream) == cudaSuccess) ctx->span_valid = 1;
+    return rc;
 }
 
 extern "C" int hfg_em_iteration(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params,
@@ -594,6 +606,14 @@ extern "C" int hfg_get_chunk_logliks(hfg_ctx *ctx, double *logliks) {
     for (int j = 0; j < l->n_seg; j++) logliks[l->seg_chunk[j]] += seg[j]; /* segments are in window order */
     free(seg);
     return HFG_OK;
+}
+
+extern "C" double hfg_last_call_device_ms(hfg_ctx *ctx) {
+    if (!ctx || !ctx->span_valid) return -1.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->ev3) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) != cudaSuccess) return -1.0;
+    return (double) ms;
 }
 
 extern "C" double hfg_last_estep_kernel_ms(hfg_ctx *ctx) {

@@ -175,6 +175,9 @@ int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int
 int64_t hfg_kernel_launches(const hfg_ctx *ctx);
 /* Device time (ms, CUDA events on the launching stream) of the E-step kernel in the last hfg_em_iteration*. */
 double hfg_last_estep_kernel_ms(hfg_ctx *ctx);
+/* Device time (ms, CUDA events on the context's stream) of the whole last blocking call: parameter upload, kernel,
+ * read-back of statistics (and labels). */
+double hfg_last_call_device_ms(hfg_ctx *ctx);
 
 /* Test / profiling hooks (no reference counterpart): phase timeline of the last E-step kernel ([grid][10]: eight clock64
  * values + SM id) and the kernel's exponential applied to n host values. */
