@@ -52,6 +52,7 @@ EXPORTED_SYMBOLS = (
     "hfg_forward_only", "hfg_get_posteriors", "hfg_get_chunk_logliks", "hfg_em_iteration_device",
     "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
     "hfg_run_em", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
+    "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect",
 )
 
 
@@ -160,6 +161,24 @@ class HmmFlaggerGPU:
         alpha = np.ascontiguousarray(alpha, np.float64)
         self._check(lib().hfg_em_iteration_device(self._h, ptr(alpha), ptr(params), C.c_void_p(stats_dev_ptr),
                                                   C.c_void_p(stream_ptr)))
+
+    def peer_connect(self, dist):
+        """Wire this context to the contexts of all other ranks of a torch.distributed group (one process per GPU):
+        exchanges the CUDA-IPC mailbox handles with an all-gather, after which every E-step call returns statistics
+        and log-likelihood summed over the ranks by the kernel itself."""
+        import torch
+        L = lib()
+        L.hfg_peer_handle_bytes.restype = C.c_size_t
+        nb = int(L.hfg_peer_handle_bytes())
+        mine = np.zeros(nb, np.uint8)
+        self._check(L.hfg_peer_export(self._h, ptr(mine)))
+        world, rank = dist.get_world_size(), dist.get_rank()
+        dev = torch.device("cuda", int(self.cfg["device"][0])) if dist.get_backend() == "nccl" else torch.device("cpu")
+        gathered = [torch.zeros(nb, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(mine).to(dev))
+        handles = np.ascontiguousarray(np.concatenate([g.cpu().numpy() for g in gathered]))
+        self._check(L.hfg_peer_connect(self._h, C.c_int(world), C.c_int(rank), ptr(handles)))
+        dist.barrier()
 
     def stats_device_bytes(self):
         return int(lib().hfg_stats_device_bytes(self._h))

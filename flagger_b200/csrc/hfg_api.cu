@@ -50,6 +50,11 @@ struct hfg_ctx {
     cudaGraphExec_t gexec;
     int graph_disabled, graph_labels;
     EstepArgs graph_args;
+    /* multi-GPU peer exchange (hfg_peer_export / hfg_peer_connect) */
+    int n_ranks, rank;
+    double *d_mailbox;                 /* own mailbox (its own allocation: it is shared through CUDA IPC) */
+    double *peer_box[HFG_MAX_PEERS];   /* every rank's mailbox as mapped into this process */
+    unsigned long long *d_epoch;
     int64_t launches;
     char err[512];
 };
@@ -181,6 +186,7 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         }
     }
     ctx->last_params = (hfg_region_params *) malloc(pbytes);
+    ctx->n_ranks = 1;
     ctx->graph_disabled = getenv("HFG_NO_GRAPH") != NULL; /* A/B switch: plain stream launches instead of graph replay */
     *out = ctx;
     return HFG_OK;
@@ -219,6 +225,10 @@ extern "C" void hfg_destroy(hfg_ctx *ctx) {
     cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev2);
     cudaEventDestroy(ctx->ev3);
+    for (int p = 0; p < ctx->n_ranks; p++)
+        if (p != ctx->rank && ctx->peer_box[p]) cudaIpcCloseMemHandle(ctx->peer_box[p]);
+    cudaFree(ctx->d_mailbox);
+    cudaFree(ctx->d_epoch);
     cudaStreamDestroy(ctx->stream);
     free(ctx->last_params);
     free(ctx);
@@ -395,6 +405,12 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     a.err_flags = ctx->d_err;
     a.forward_only = forward_only;
     a.phase_clock = ctx->d_phase_clock;
+    a.out_doubles = R * STATS_DOUBLES + 2;
+    /* the posterior re-run (post_dev != NULL) is local to this rank: no exchange */
+    a.n_ranks = (ctx->n_ranks > 1 && post_dev == NULL) ? ctx->n_ranks : 1;
+    a.rank = ctx->rank;
+    for (int p = 0; p < HFG_MAX_PEERS; p++) a.peer_box[p] = ctx->peer_box[p];
+    a.epoch = ctx->d_epoch;
 }
 
 /* Enqueue one E-step (or forward pass) on `stream`; results land in out_dev = [stats | loglik | error flags]. */
@@ -434,6 +450,20 @@ static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_par
     return HFG_OK;
 }
 
+/* translate [stats | loglik | flags] sitting in the pinned output block */
+static int parse_out(hfg_ctx *ctx, hfg_region_stats *stats, double *loglik) {
+    const int R = ctx->cfg.n_regions;
+    const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
+    const int flags = (int) ctx->h_out[out_doubles - 1];
+    if (flags & 1)
+        return fail(ctx, HFG_ERR_SCALE_UNDERFLOW, "scale is very low! (a forward scale fell below 1e-50; hmm.c:412-415)");
+    if (flags & 2) return fail(ctx, HFG_ERR_NAN, "[Error] prob is NAN (an emission pdf evaluated to NaN; hmm_utils.c:782-786)");
+    if (flags & 4) return fail(ctx, HFG_ERR_CUDA, "peer all-reduce timed out: a rank did not reach the exchange");
+    if (stats) memcpy(stats, ctx->h_out, sizeof(hfg_region_stats) * (size_t) R);
+    if (loglik) *loglik = ctx->h_out[out_doubles - 2];
+    return HFG_OK;
+}
+
 /* fetch [stats | loglik | flags] from the context's own output buffer and translate the error flags */
 static int fetch_out(hfg_ctx *ctx, hfg_region_stats *stats, double *loglik, int8_t *labels, int with_labels) {
     const int R = ctx->cfg.n_regions;
@@ -443,26 +473,7 @@ static int fetch_out(hfg_ctx *ctx, hfg_region_stats *stats, double *loglik, int8
         CU(cudaMemcpyAsync(ctx->h_labels, ctx->d_labels, (size_t) ctx->lay.n_windows, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     if (with_labels && labels) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
-    const int flags = (int) ctx->h_out[out_doubles - 1];
-    if (flags & 1)
-        return fail(ctx, HFG_ERR_SCALE_UNDERFLOW, "scale is very low! (a forward scale fell below 1e-50; hmm.c:412-415)");
-    if (flags & 2) return fail(ctx, HFG_ERR_NAN, "[Error] prob is NAN (an emission pdf evaluated to NaN; hmm_utils.c:782-786)");
-    if (stats) memcpy(stats, ctx->h_out, sizeof(hfg_region_stats) * (size_t) R);
-    if (loglik) *loglik = ctx->h_out[out_doubles - 2];
-    return HFG_OK;
-}
-
-/* translate [stats | loglik | flags] sitting in the pinned output block */
-static int parse_out(hfg_ctx *ctx, hfg_region_stats *stats, double *loglik) {
-    const int R = ctx->cfg.n_regions;
-    const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
-    const int flags = (int) ctx->h_out[out_doubles - 1];
-    if (flags & 1)
-        return fail(ctx, HFG_ERR_SCALE_UNDERFLOW, "scale is very low! (a forward scale fell below 1e-50; hmm.c:412-415)");
-    if (flags & 2) return fail(ctx, HFG_ERR_NAN, "[Error] prob is NAN (an emission pdf evaluated to NaN; hmm_utils.c:782-786)");
-    if (stats) memcpy(stats, ctx->h_out, sizeof(hfg_region_stats) * (size_t) R);
-    if (loglik) *loglik = ctx->h_out[out_doubles - 2];
-    return HFG_OK;
+    return parse_out(ctx, stats, loglik);
 }
 
 /* (re)capture  upload params -> clear flags -> kernel -> read back results [-> read back labels]  as one graph */
@@ -682,5 +693,57 @@ extern "C" int hfg_debug_exp(hfg_ctx *ctx, const double *in, double *out, int n)
     CU(cudaMemcpy(out, d_out, sizeof(double) * (size_t) n, cudaMemcpyDeviceToHost));
     cudaFree(d_in);
     cudaFree(d_out);
+    return HFG_OK;
+}
+
+/* ---- multi-GPU: peer exchange set-up ------------------------------------------------------------------------------- */
+
+static size_t mailbox_bytes(const hfg_ctx *ctx) {
+    const size_t n = (size_t) ctx->cfg.n_regions * STATS_DOUBLES + 2;
+    return (2 * HFG_MAX_PEERS * n + 2 * HFG_MAX_PEERS) * sizeof(double);
+}
+
+extern "C" size_t hfg_peer_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+extern "C" int hfg_peer_export(hfg_ctx *ctx, void *handle_out) {
+    if (!ctx || !handle_out) return HFG_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->d_mailbox) {
+        CU(cudaMalloc((void **) &ctx->d_mailbox, mailbox_bytes(ctx)));
+        CU(cudaMemset(ctx->d_mailbox, 0, mailbox_bytes(ctx)));
+    }
+    if (!ctx->d_epoch) {
+        CU(cudaMalloc((void **) &ctx->d_epoch, sizeof(unsigned long long)));
+        CU(cudaMemset(ctx->d_epoch, 0, sizeof(unsigned long long)));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, ctx->d_mailbox));
+    memcpy(handle_out, &h, sizeof(h));
+    return HFG_OK;
+}
+
+extern "C" int hfg_peer_connect(hfg_ctx *ctx, int n_ranks, int rank, const void *handles) {
+    if (!ctx || !handles) return HFG_ERR_INVALID;
+    if (n_ranks < 1 || n_ranks > HFG_MAX_PEERS || rank < 0 || rank >= n_ranks)
+        return fail(ctx, HFG_ERR_INVALID, "hfg_peer_connect: %d ranks (limit %d), rank %d", n_ranks, HFG_MAX_PEERS, rank);
+    if (!ctx->d_mailbox) return fail(ctx, HFG_ERR_INVALID, "hfg_peer_connect: call hfg_peer_export first");
+    CU(cudaSetDevice(ctx->device));
+    for (int p = 0; p < n_ranks; p++) {
+        if (p == rank) {
+            ctx->peer_box[p] = ctx->d_mailbox;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *) handles + (size_t) p * sizeof(h), sizeof(h));
+        void *ptr = NULL;
+        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_box[p] = (double *) ptr;
+    }
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    if (ctx->gexec) { /* the captured graph was built without the exchange */
+        cudaGraphExecDestroy(ctx->gexec);
+        ctx->gexec = NULL;
+    }
     return HFG_OK;
 }

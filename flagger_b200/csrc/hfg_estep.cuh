@@ -56,6 +56,7 @@ namespace cg = cooperative_groups;
 #define RT_GAUSS 140
 #define RT_STRIDE(G) (RT_GAUSS + 6 * (G))
 #define HFG_INV_TERM 1e4 /* 1 / terminationProb */
+#define HFG_MAX_PEERS 8
 #define HFG_MAX_TASKS 160
 /* per-(region, task) table after the Gaussian arrays: (1-a)*mu, a, 1/(var*beta0), w/sqrt(var*beta0*2*PI) */
 #define RT_TASK(G) (RT_GAUSS + 6 * (G))
@@ -101,6 +102,12 @@ struct EstepArgs {
     int32_t *err_flags;  /* bit0 scale underflow, bit1 NaN */
     int32_t forward_only;
     long long *phase_clock; /* [grid][10] clock64() of thread 0 at the phase boundaries + SM id (instrumentation) */
+    /* multi-GPU: in-kernel sum all-reduce of [stats | loglik | flags] over peer memory (NVLink P2P).  Every rank owns a
+     * mailbox  [2 epochs][HFG_MAX_PEERS senders][out_doubles]  followed by  [2][HFG_MAX_PEERS]  arrival counters;
+     * peer_box[r] is rank r's mailbox as mapped into this process (peer_box[rank] is the local one). */
+    int32_t n_ranks, rank, out_doubles;
+    double *peer_box[HFG_MAX_PEERS];
+    unsigned long long *epoch; /* device counter of exchanges done so far (identical on every rank) */
 };
 
 /* statistic columns per (block, region): 16 transition counts, lambda num/den, then per Gaussian component
@@ -969,6 +976,61 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
                 }
             }
             if (tid == 0) A.out[(size_t) R * SD + 1] = (double) __ldcg(A.err_flags);
+
+            /* ---- fused collective: sum the block over all ranks through peer memory ------------------------------
+             * Each rank stores its vector into slot [rank] of every peer's mailbox (plain coalesced stores over
+             * NVLink), publishes an arrival counter with system scope, waits for the N counters of its own mailbox, and
+             * adds the N vectors in rank order -- the same association on every rank, so all ranks end with the same
+             * bits and run the same host M-step.  Two epochs alternate so that a fast rank can never overwrite a slot
+             * a slow rank is still reading. */
+            if (A.n_ranks > 1) {
+                __syncthreads();
+                const int n = A.out_doubles, N = A.n_ranks;
+                const unsigned long long e = *A.epoch + 1;
+                const size_t box = (size_t) (e & 1) * HFG_MAX_PEERS * n;
+                const size_t cnt_base = (size_t) 2 * HFG_MAX_PEERS * n; /* counters live behind the slots (as u64) */
+                for (int p = 0; p < N; p++) {
+                    double *dst = A.peer_box[p] + box + (size_t) A.rank * n;
+                    for (int q = tid; q < n; q += HFG_THREADS) dst[q] = A.out[q];
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (tid < N) {
+                    volatile unsigned long long *c =
+                        (volatile unsigned long long *) (A.peer_box[tid] + cnt_base) + (e & 1) * HFG_MAX_PEERS + A.rank;
+                    *c = e;
+                    __threadfence_system();
+                    /* wait for sender `tid` in the local mailbox (bounded: a lost peer becomes an error, not a hang) */
+                    volatile unsigned long long *mine =
+                        (volatile unsigned long long *) (A.peer_box[A.rank] + cnt_base) + (e & 1) * HFG_MAX_PEERS + tid;
+                    const long long t0 = clock64();
+                    while (*mine < e) {
+                        if (clock64() - t0 > 4000000000LL) { /* ~2 s */
+                            atomicOr(A.err_flags, 4);
+                            break;
+                        }
+                    }
+                }
+                __threadfence_system();
+                __syncthreads();
+                const double *in = A.peer_box[A.rank] + box;
+                for (int q = tid; q < n; q += HFG_THREADS) {
+                    double sum = 0.0;
+                    if (q == n - 1) { /* error flags: bitwise OR over ranks */
+                        int f = 0;
+                        for (int p = 0; p < N; p++) f |= (int) __ldcv(in + (size_t) p * n + q);
+                        sum = (double) f;
+                    } else {
+                        for (int p = 0; p < N; p++) sum += __ldcv(in + (size_t) p * n + q);
+                    }
+                    A.out[q] = sum;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    if (__ldcg(A.err_flags) & 4) A.out[n - 1] = (double) ((int) A.out[n - 1] | 4);
+                    *A.epoch = e;
+                }
+            }
         }
     }
 }

@@ -147,6 +147,17 @@ size_t hfg_stats_device_bytes(const hfg_ctx *ctx);
 /* Copies the labels of the last E-step to the host (blocking). */
 int hfg_get_labels(hfg_ctx *ctx, int8_t *labels);
 
+/* Multi-GPU, one process per GPU: after this set-up every hfg_em_iteration / hfg_forward_only call returns statistics
+ * and log-likelihood already SUMMED over all ranks -- the E-step kernel ends with a sum all-reduce of its result block
+ * through peer memory (NVLink P2P stores into the peers' mailboxes, counters with system scope), in rank order, so all
+ * ranks hold identical bits.  Labels / posteriors stay per-rank (each rank's own chunks).  Protocol: every rank calls
+ * hfg_peer_export, the hfg_peer_handle_bytes()-sized handles are all-gathered by the host program (torch.distributed,
+ * MPI, ...), every rank calls hfg_peer_connect with all of them in rank order.  All ranks must then make the same
+ * sequence of E-step calls.  A rank that never arrives turns into HFG_ERR_CUDA after ~2 s, not a hang. */
+size_t hfg_peer_handle_bytes(void);
+int hfg_peer_export(hfg_ctx *ctx, void *handle_out);
+int hfg_peer_connect(hfg_ctx *ctx, int n_ranks, int rank, const void *handles);
+
 /* ---- host mirrors of the O(#parameters) neighbours of the seam ---------------------------------- */
 
 /* max(2, min(10, maxCov / min(regionCov) + 1))  (src/hmm_flagger.c:105-111,1008-1013). */

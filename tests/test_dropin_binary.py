@@ -71,3 +71,25 @@ def test_cli_outputs_match_reference(tmp_path, kind):
     pa = [ln.split("\t")[-1] for ln in open(os.path.join(ref_out, "posterior_prediction_final.bed"))]
     pb = [ln.split("\t")[-1] for ln in open(os.path.join(gpu_out, "posterior_prediction_final.bed"))]
     assert pa == pb
+
+
+def test_cli_accelerate_matches_reference(tmp_path):
+    """--accelerate (SQUAREM, hmm.c:820-1098) runs 3 E-steps and >= 1 forward-only pass per outer iteration through the
+    seam (EM_runForwardForList -> hfg_forward_only); the host extrapolation stays the reference's code."""
+    if not (os.path.exists(REF) and os.path.exists(GPU)):
+        pytest.skip("oracle/_ref binaries were not built (reference tree not mounted at build time)")
+    wl = synth.small_mixed(n_regions=1, seed=56)
+    inp = str(tmp_path / "in.bin")
+    binfmt.write_bin(wl, inp)
+    alpha = str(tmp_path / "alpha.tsv")
+    binfmt.write_alpha_tsv(synth.HIFI_ALPHA, alpha)
+    ref_out, gpu_out = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    _run(REF, inp, ref_out, alpha, extra=("-s",))
+    _run(GPU, inp, gpu_out, alpha, extra=("-s",))
+    assert open(os.path.join(ref_out, "final_flagger_prediction.bed")).read() == \
+        open(os.path.join(gpu_out, "final_flagger_prediction.bed")).read()
+    a, b = _table(os.path.join(ref_out, "loglikelihood.tsv")), _table(os.path.join(gpu_out, "loglikelihood.tsv"))
+    assert a.shape == b.shape and np.all(np.abs(a - b) <= 2e-4)
+    for name in ("emission_final.tsv", "transition_final.tsv"):
+        a, b = _table(os.path.join(ref_out, name)), _table(os.path.join(gpu_out, name))
+        assert a.shape == b.shape and np.allclose(a, b, rtol=2e-5, atol=1e-12), name
