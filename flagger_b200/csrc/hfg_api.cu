@@ -22,6 +22,8 @@ struct hfg_ctx {
     hfg_layout lay;
     int have_chunks;
     int device, num_sms, max_blocks, grid;
+    int threads;          /* CTA size: 512, or 256 when the model needs the shared memory */
+    const void *kernel;   /* the matching instantiation of hfg_estep_kernel */
     size_t smem_bytes;
     cudaStream_t stream;
     cudaEvent_t ev0, ev1; /* around the E-step kernel */
@@ -84,9 +86,9 @@ static int max_tasks(const hfg_config *cfg) {
     return n;
 }
 
-static size_t smem_bytes_for(int R, int G, int NT) {
-    size_t doubles = (size_t) R * RT_STRIDE2(G, NT) + 3 * HFG_WARPS * 16 + 8 + (size_t) hfg_acc_rows(G) * (HFG_THREADS + 1);
-    return doubles * sizeof(double) + HFG_THREADS * sizeof(int);
+static size_t smem_bytes_for(int R, int G, int NT, int threads) {
+    size_t doubles = (size_t) R * RT_STRIDE2(G, NT) + 3 * (threads / 32) * 16 + 8 + (size_t) hfg_acc_rows(G) * (threads + 1);
+    return doubles * sizeof(double) + threads * sizeof(int);
 }
 
 static int total_gauss_comps(const hfg_config *cfg) {
@@ -133,7 +135,14 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     prop.sharedMemPerBlockOptin = (size_t) optin;
     ctx->num_sms = prop.multiProcessorCount;
     const int G = total_gauss_comps(cfg);
-    ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg));
+    ctx->threads = HFG_THREADS_MAX;
+    ctx->kernel = (const void *) hfg_estep_kernel<HFG_THREADS_MAX>;
+    ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg), ctx->threads);
+    if (ctx->smem_bytes > (size_t) optin) { /* many components / regions: halve the CTA, halving the statistics area */
+        ctx->threads = HFG_THREADS_MIN;
+        ctx->kernel = (const void *) hfg_estep_kernel<HFG_THREADS_MIN>;
+        ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg), ctx->threads);
+    }
     if (max_tasks(cfg) > HFG_MAX_TASKS) {
         fail(NULL, HFG_ERR_INVALID, "too many mixture components (%d component evaluations per window, limit %d)", max_tasks(cfg), HFG_MAX_TASKS);
         free(ctx);
@@ -147,10 +156,10 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     }
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, cfg->device);
-    e = cudaFuncSetAttribute(hfg_estep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
+    e = cudaFuncSetAttribute(ctx->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ctx->smem_bytes);
     int per_sm = 0;
     if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hfg_estep_kernel, HFG_THREADS, ctx->smem_bytes);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctx->kernel, ctx->threads, ctx->smem_bytes);
     if (e != cudaSuccess || !coop || per_sm < 1) {
         fail(NULL, HFG_ERR_CUDA, "E-step kernel cannot be launched cooperatively on device %d (%s; coop=%d, blocks/SM=%d)",
              cfg->device, cudaGetErrorString(e), coop, per_sm);
@@ -252,11 +261,11 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     int64_t W = 0;
     for (int32_t c = 0; c < n_chunks; c++) W += chunks[c].n_windows;
     /* persistent grid: one CTA per SM, but do not spread a tiny input over the whole chip */
-    int64_t blocks = (W + (int64_t) HFG_THREADS * 4 - 1) / ((int64_t) HFG_THREADS * 4);
+    int64_t blocks = (W + (int64_t) ctx->threads * 4 - 1) / ((int64_t) ctx->threads * 4);
     if (blocks < 1) blocks = 1;
     if (blocks > ctx->max_blocks) blocks = ctx->max_blocks;
     ctx->grid = (int) blocks;
-    const int32_t cap = ctx->grid * HFG_THREADS;
+    const int32_t cap = ctx->grid * ctx->threads;
     int rc = hfg_layout_build(&ctx->cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, cap, &ctx->lay,
                               ctx->err, sizeof(ctx->err));
     if (rc != HFG_OK) return rc;
@@ -435,7 +444,7 @@ static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_par
 
     void *kargs[] = {(void *) &a};
     if (timed) CU(cudaEventRecord(ctx->ev0, stream));
-    CU(cudaLaunchCooperativeKernel((void *) hfg_estep_kernel, dim3(ctx->grid), dim3(HFG_THREADS), kargs,
+    CU(cudaLaunchCooperativeKernel(ctx->kernel, dim3(ctx->grid), dim3(ctx->threads), kargs,
                                    ctx->smem_bytes, stream));
     if (timed) {
         CU(cudaEventRecord(ctx->ev1, stream));
@@ -494,7 +503,7 @@ static int capture_graph(hfg_ctx *ctx, const EstepArgs *a, int with_labels) {
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecordWithFlags(ctx->ev0, ctx->stream, cudaEventRecordExternal); /* event-record node */
     if (e == cudaSuccess)
-        e = cudaLaunchCooperativeKernel((void *) hfg_estep_kernel, dim3(ctx->grid), dim3(HFG_THREADS), kargs, ctx->smem_bytes,
+        e = cudaLaunchCooperativeKernel(ctx->kernel, dim3(ctx->grid), dim3(ctx->threads), kargs, ctx->smem_bytes,
                                         ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecordWithFlags(ctx->ev1, ctx->stream, cudaEventRecordExternal);
     if (e == cudaSuccess)

@@ -39,8 +39,10 @@
 
 namespace cg = cooperative_groups;
 
-#define HFG_THREADS 512
-#define HFG_WARPS (HFG_THREADS / 32)
+/* threads per CTA: 512 when the per-thread statistics columns fit shared memory, else 256 (more mixture components /
+ * regions); one persistent CTA per SM either way */
+#define HFG_THREADS_MAX 512
+#define HFG_THREADS_MIN 256
 
 /* Per-region derived tables in shared memory (doubles):
  *   [0,128)    conditional transition  Tc[mask][pre*4+s]          (Transition_getProbConditional, hmm_utils.c:2278-2292)
@@ -404,24 +406,26 @@ __device__ __forceinline__ double trans_prob(const double *rt, const Win &w, int
 
 /* ---------------------------------------------------------------------------------------------------------- */
 
-__global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepArgs A) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A) {
+    constexpr int WARPS = THREADS / 32;
     using namespace hfgk;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double smem[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int j = blockIdx.x * HFG_THREADS + tid; /* segment owned by this thread */
+    const int j = blockIdx.x * THREADS + tid; /* segment owned by this thread */
     const int cap = A.capacity, D = A.n_classes, G = A.G, R = A.n_regions;
     const int rt_stride = RT_STRIDE2(G, A.n_tasks);
     const int NSTAT = hfg_nstat(G);
-    const int LD = HFG_THREADS + 1;
+    const int LD = THREADS + 1;
 
     /* shared memory carve-up */
     double *rtab = smem;                                   /* [R][rt_stride] */
     double *warp_tot = rtab + (size_t) R * rt_stride;      /* [WARPS][16] warp products */
-    double *warp_pre = warp_tot + HFG_WARPS * 16;          /* [WARPS][16] exclusive prefix over warps */
-    double *warp_suf = warp_pre + HFG_WARPS * 16;          /* [WARPS][16] exclusive suffix over warps */
-    double *blk_vec = warp_suf + HFG_WARPS * 16;           /* [8] entering forward / backward message of the block */
+    double *warp_pre = warp_tot + WARPS * 16;          /* [WARPS][16] exclusive prefix over warps */
+    double *warp_suf = warp_pre + WARPS * 16;          /* [WARPS][16] exclusive suffix over warps */
+    double *blk_vec = warp_suf + WARPS * 16;           /* [8] entering forward / backward message of the block */
     double *acc = blk_vec + 8;                             /* [max(NSTAT,32)][LD]: emission staging (phase A), scan stash
                                                               (phase B), per-thread statistics (phases C, D) */
     int *treg = (int *) (acc + (size_t) hfg_acc_rows(G) * LD); /* [THREADS] region of each thread's segment */
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
 
     /* ---- prologue: derived per-region tables (redundantly per block; O(R*K) work) ---- */
     if (tid == 0) s_reset = 0;
-    for (int idx = tid; idx < R * 32; idx += HFG_THREADS) {
+    for (int idx = tid; idx < R * 32; idx += THREADS) {
         /* one (region, mask, pre) row of the conditional transition table */
         const int r = idx >> 5, mask = (idx >> 2) & 7, pre = idx & 3;
         const hfg_region_params &p = A.params[r];
@@ -442,7 +446,7 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
         for (int s = 0; s < 4; s++)
             rtab[(size_t) r * rt_stride + RT_TC + mask * 16 + pre * 4 + s] = valid[s] ? p.trans[pre][s] / tot : 0.0;
     }
-    for (int idx = tid; idx < R * (12 + G); idx += HFG_THREADS) {
+    for (int idx = tid; idx < R * (12 + G); idx += THREADS) {
         const int r = idx / (12 + G), q = idx % (12 + G);
         const hfg_region_params &p = A.params[r];
         double *rt = rtab + (size_t) r * rt_stride;
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
             ga[5 * G + g] = p.weight[s][c] / sqrt(vb * 2 * HFG_PI);
         }
     }
-    for (int idx = tid; idx < R * A.n_tasks; idx += HFG_THREADS) {
+    for (int idx = tid; idx < R * A.n_tasks; idx += THREADS) {
         const int r = idx / A.n_tasks, t = idx % A.n_tasks;
         const hfg_region_params &p = A.params[r];
         const int d = A.task_class[t], c = A.task_comp[t], s = A.class_state[d];
@@ -594,40 +598,40 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
         for (int i = 0; i < 16; i++) acc[(size_t) (16 + i) * LD + tid] = Q[i]; /* exclusive suffix inside the warp */
     }
     __syncthreads();
-    /* second level over the HFG_WARPS warp products of this block: warp 0 builds the prefixes (and the block total),
+    /* second level over the WARPS warp products of this block: warp 0 builds the prefixes (and the block total),
      * warp 1 the suffixes, concurrently */
     if (warp == 0) {
         double Sp[16], Q[16];
-        if (lane < HFG_WARPS) {
+        if (lane < WARPS) {
 #pragma unroll
             for (int i = 0; i < 16; i++) Sp[i] = warp_tot[lane * 16 + i];
         } else {
             mat_identity(Sp);
         }
-        warp_scan_prefix<HFG_WARPS>(Sp, lane);
-        if (lane == HFG_WARPS - 1) {
+        warp_scan_prefix<WARPS>(Sp, lane);
+        if (lane == WARPS - 1) {
 #pragma unroll
             for (int i = 0; i < 16; i++) A.block_tot[(size_t) blockIdx.x * 16 + i] = Sp[i];
             A.block_reset[blockIdx.x] = s_reset;
         }
         mat_shfl_up(Sp, Q, 1);
         if (lane == 0) mat_identity(Q);
-        if (lane < HFG_WARPS) {
+        if (lane < WARPS) {
 #pragma unroll
             for (int i = 0; i < 16; i++) warp_pre[lane * 16 + i] = Q[i];
         }
     } else if (warp == 1) {
         double Ss[16], Q[16];
-        if (lane < HFG_WARPS) {
+        if (lane < WARPS) {
 #pragma unroll
             for (int i = 0; i < 16; i++) Ss[i] = warp_tot[lane * 16 + i];
         } else {
             mat_identity(Ss);
         }
-        warp_scan_suffix<HFG_WARPS>(Ss, lane);
+        warp_scan_suffix<WARPS>(Ss, lane);
         mat_shfl_down(Ss, Q, 1);
-        if (lane >= HFG_WARPS - 1) mat_identity(Q);
-        if (lane < HFG_WARPS) {
+        if (lane >= WARPS - 1) mat_identity(Q);
+        if (lane < WARPS) {
 #pragma unroll
             for (int i = 0; i < 16; i++) warp_suf[lane * 16 + i] = Q[i];
         }
@@ -902,14 +906,14 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
         if (tid == 0) A.phase_clock[blockIdx.x * 10 + 5] = clock64();
         /* one warp per (region, statistic) column: each lane adds its 8 entries in index order, then a fixed
          * xor-shuffle tree -- the same association on every run */
-        for (int q = warp; q < R * NSTAT; q += HFG_WARPS) {
+        for (int q = warp; q < R * NSTAT; q += WARPS) {
             const int r = q / NSTAT, st = q % NSTAT;
             const bool is_ll = (st == NSTAT - 1);
             double sum = 0.0;
             if (!is_ll || r == 0) {
                 const double *cl = acc + (size_t) st * LD;
 #pragma unroll
-                for (int t = lane; t < HFG_THREADS; t += 32)
+                for (int t = lane; t < THREADS; t += 32)
                     if (is_ll || treg[t] == r) sum += cl[t];
             }
 #pragma unroll
@@ -927,16 +931,16 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
         if (blockIdx.x == 0) {
             const int SD = (int) (sizeof(hfg_region_stats) / sizeof(double));
             const int nb = gridDim.x;
-            for (int q = tid; q < R * NSTAT; q += HFG_THREADS) {
+            for (int q = tid; q < R * NSTAT; q += THREADS) {
                 const int r = q / NSTAT, st = q % NSTAT;
                 double sum = 0.0;
                 for (int b = 0; b < nb; b++) sum += __ldcg(&A.partials[((size_t) b * R + r) * NSTAT + st]);
                 acc[q] = sum; /* reuse shared memory: [R][NSTAT] totals */
             }
-            for (int q = tid; q < R * SD; q += HFG_THREADS) A.out[q] = 0.0;
+            for (int q = tid; q < R * SD; q += THREADS) A.out[q] = 0.0;
             __syncthreads();
             /* scatter into the hfg_region_stats layout (include/hfg.h) */
-            for (int q = tid; q < R * NSTAT; q += HFG_THREADS) {
+            for (int q = tid; q < R * NSTAT; q += THREADS) {
                 const int r = q / NSTAT, st = q % NSTAT;
                 double *o = A.out + (size_t) r * SD;
                 const double v = acc[q];
@@ -991,7 +995,7 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
                 const size_t cnt_base = (size_t) 2 * HFG_MAX_PEERS * n; /* counters live behind the slots (as u64) */
                 for (int p = 0; p < N; p++) {
                     double *dst = A.peer_box[p] + box + (size_t) A.rank * n;
-                    for (int q = tid; q < n; q += HFG_THREADS) dst[q] = A.out[q];
+                    for (int q = tid; q < n; q += THREADS) dst[q] = A.out[q];
                 }
                 __threadfence_system();
                 __syncthreads();
@@ -1014,7 +1018,7 @@ __global__ void __launch_bounds__(HFG_THREADS, 1) hfg_estep_kernel(const EstepAr
                 __threadfence_system();
                 __syncthreads();
                 const double *in = A.peer_box[A.rank] + box;
-                for (int q = tid; q < n; q += HFG_THREADS) {
+                for (int q = tid; q < n; q += THREADS) {
                     double sum = 0.0;
                     if (q == n - 1) { /* error flags: bitwise OR over ranks */
                         int f = 0;

@@ -197,3 +197,23 @@ def test_error_scale_underflow_is_reported(orc):
         gpu.em_iteration(np.zeros((4, 4)), params)
     assert e.value.code == _abi.ERR_SCALE_UNDERFLOW and "scale is very low" in str(e.value)
     gpu.close()
+
+
+@pytest.mark.parametrize("n_regions,K", [(1, 10), (7, 10), (20, 4), (32, 6)])
+def test_large_models_use_the_smaller_cta(orc, n_regions, K):
+    """Many mixture components / regions: the per-thread statistics columns no longer fit shared memory with 512-thread
+    CTAs, the library switches to the 256-thread instantiation of the same kernel.  K = 10 is the CLI's upper clamp
+    (src/hmm_flagger.c:1012-1013); region indices go up to 63 (ptBlock.c:294-304)."""
+    rng = np.random.default_rng(n_regions * 100 + K)
+    wl = synth.small_mixed(n_regions=1, seed=60 + K)
+    wl.region[:] = np.repeat(rng.integers(0, n_regions, size=wl.n_windows // 7 + 1), 7)[:wl.n_windows].astype(np.uint8)
+    wl.region_coverages = rng.integers(25, 60, size=n_regions).astype(np.int32)
+    cfg = _abi.make_config(n_regions=n_regions, n_col_comps=K)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    out = orc.estep(cfg, wl, synth.HIFI_ALPHA, params)
+    stats, ll, labels, _ = _check_estep(gpu, out, wl, synth.HIFI_ALPHA, params)
+    p2, _ = api.mstep(cfg, params, stats)
+    out2 = orc.estep(cfg, wl, synth.HIFI_ALPHA, p2)
+    _check_estep(gpu, out2, wl, synth.HIFI_ALPHA, p2)
+    gpu.close()
