@@ -46,16 +46,18 @@ namespace cg = cooperative_groups;
 
 /* Per-region derived tables in shared memory (doubles):
  *   [0,128)    conditional transition  Tc[mask][pre*4+s]          (Transition_getProbConditional, hmm_utils.c:2278-2292)
- *   [128,132)  start probabilities trans[4][s]
- *   [132,136)  termination probabilities trans[s][4]
- *   [136,140)  lambda, truncPoint, lambda/beta0, 1-exp(-(lambda/beta0)*(beta0*truncPoint))
+ *   [128,144)  the constant 1/(N+1) of a region-change window, laid out as a ninth mask
+ *   [144,148)  start probabilities trans[4][s]
+ *   [148,152)  termination probabilities trans[s][4]
+ *   [152,156)  lambda, truncPoint, lambda/beta0, 1-exp(-(lambda/beta0)*(beta0*truncPoint))
  *   then 6 arrays of G doubles over the flattened Gaussian components g: mu, var, w, var*beta0, 1/(var*beta0),
  *   w/sqrt(var*beta0*2*PI). */
 #define RT_TC 0
-#define RT_START 128
-#define RT_TERM 132
-#define RT_TEXP 136
-#define RT_GAUSS 140
+#define RT_UNI 128 /* 16 x 1/(N+1): the transition "matrix" of a region-change window (hmm.c:398-400), as mask index 8 */
+#define RT_START 144
+#define RT_TERM 148
+#define RT_TEXP 152
+#define RT_GAUSS 156
 #define RT_STRIDE(G) (RT_GAUSS + 6 * (G))
 #define HFG_INV_TERM 1e4 /* 1 / terminationProb */
 #define HFG_MAX_PEERS 8
@@ -277,7 +279,7 @@ __device__ __forceinline__ Win decode_word(uint32_t w, double beta0) {
     o.x = (double) HFG_OBS_X(w);
     o.px = (double) HFG_OBS_PX(w);
     o.region = (int) HFG_OBS_REGION(w);
-    o.mask = (int) HFG_OBS_MASK(w);
+    o.mask = (w & HFG_OBS_REGION_CHANGE) ? 8 : (int) HFG_OBS_MASK(w); /* 8 = the constant 1/(N+1) table */
     o.edge = (w & HFG_OBS_EDGE) != 0;
     o.start = (w & HFG_OBS_CHUNK_START) != 0;
     o.second = (w & HFG_OBS_SECOND) != 0;
@@ -399,7 +401,7 @@ __device__ __forceinline__ double emission(const EstepArgs &A, const double *rt,
 
 /* transition probability into window w: 1/(N+1) at a region change (hmm.c:398-400), else the masked row */
 __device__ __forceinline__ double trans_prob(const double *rt, const Win &w, int pre, int s) {
-    return w.region_change ? 1.0 / (HFG_NS + 1) : rt[RT_TC + w.mask * 16 + pre * 4 + s];
+    return rt[RT_TC + w.mask * 16 + pre * 4 + s]; /* w.mask == 8 selects the constant table at a region change */
 }
 
 }  // namespace hfgk
@@ -450,7 +452,11 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
         const int r = idx / (12 + G), q = idx % (12 + G);
         const hfg_region_params &p = A.params[r];
         double *rt = rtab + (size_t) r * rt_stride;
-        if (q < 4) rt[RT_START + q] = p.trans[HFG_NS][q];
+        if (q < 4) {
+            rt[RT_START + q] = p.trans[HFG_NS][q];
+#pragma unroll
+            for (int i = 0; i < 4; i++) rt[RT_UNI + q * 4 + i] = 1.0 / (HFG_NS + 1);
+        }
         else if (q < 8) rt[RT_TERM + q - 4] = p.trans[q - 4][HFG_NS];
         else if (q == 8) rt[RT_TEXP] = p.lambda;
         else if (q == 9) rt[RT_TEXP + 1] = p.trunc_point;
@@ -736,9 +742,12 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
             }
             const double c = ((fn[0] + fn[1]) + fn[2]) + fn[3];
             if (!w.start && c < 1e-50) uf_flag = 1; /* "scale is very low" (hmm.c:412-415) */
+            /* f^ = f / c as one correctly rounded reciprocal and four products (<= 1 ulp from the four divisions of
+             * hmm.c:417-419; the divisions were a third of this loop's instructions) */
+            const double rc = __drcp_rn(c);
 #pragma unroll
             for (int s = 0; s < 4; s++) {
-                f[s] = fn[s] / c;
+                f[s] = fn[s] * rc;
                 A.scrF[((size_t) k * 4 + s) * cap + j] = f[s];
             }
             A.scrC[(size_t) k * cap + j] = c;
@@ -887,9 +896,10 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                 }
             }
             if (k > 0) {
+                const double rcp = __drcp_rn(cp); /* b^ = b / scale (hmm.c:526-528), as reciprocal x product */
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
-                    bh[s] = bn[s] / cp;
+                    bh[s] = bn[s] * rcp;
                     fh[s] = fp[s];
                 }
                 c = cp;
