@@ -345,50 +345,49 @@ __device__ __noinline__ double gauss_class(const double *rt, int G, int g0, int 
     return tot;
 }
 
-/* Gaussian_updateEstimator (hmm_utils.c:812-839) for one (state, alpha) class with pooled count cnt: adds
- * (w*x_adj, w, w*z*z) per component into the thread's statistics column (three rows per component, stride ld). */
-__device__ __noinline__ void gauss_stats(const double *rt, int G, int g0, int n, double a, double inv_1ma, double cnt,
-                                         double x, double px, double beta, double rb, double sq, double *colg, int ld,
-                                         int *nan) {
-    const double x_adj = (x - a * px) * inv_1ma;
-    const double oma = 1.0 - a;
-    if (n == 1) {
-        const double z = (x_adj - rt[RT_GAUSS + g0]) * oma;
-        colg[0] += cnt * x_adj;
-        colg[ld] += cnt;
-        colg[2 * ld] += cnt * z * z;
-        return;
-    }
-    /* responsibilities need the component pdfs again (hmm_utils.c:819) */
-    Win w;
-    w.x = x;
-    w.px = px;
-    w.beta = beta;
-    w.rb = rb;
-    w.sq = sq;
-    double pc[HFG_MAX_COMPS];
-    double tot = 0.0;
-#pragma unroll 1
-    for (int c0 = 0; c0 < n; c0 += 4) {
-        double pv[4];
+/* Gaussian_updateEstimator (hmm_utils.c:812-839) for ALL (state, alpha) classes of one multi-component state at one
+ * window.  The reference adds, per preState and component c,  w = count * p_c / sum_c p_c  with count = f*t*e*b/term and
+ * e = sum_c p_c: the class emission cancels, w = H * p_c with H = (f*t) * b / term pooled over the preStates of the class.
+ * So no division and no second pass: for each component the (<= 4) classes are evaluated side by side (independent
+ * exponential chains), their (w*x_adj, w, w*z*z) are summed in registers and the thread's statistics column is updated
+ * once per component (three rows per component, stride ld). */
+__device__ __noinline__ void gauss_state_stats(const double *rt, int G, int g0, int n, int nd, double H0, double H1,
+                                               double H2, double H3, double a0, double a1, double a2, double a3, double x,
+                                               double px, double beta, double rb, double sq, double *colg, int ld,
+                                               int *nan) {
+    const double H[4] = {H0, H1, H2, H3}, a[4] = {a0, a1, a2, a3};
+    double xa[4], oma[4], base[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) pv[u] = gauss_comp(rt, G, g0 + min(c0 + u, n - 1), a, w, nan); /* 4 chains in flight */
-#pragma unroll
-        for (int u = 0; u < 4; u++)
-            if (c0 + u < n) {
-                pc[c0 + u] = pv[u];
-                tot += pv[u];
-            }
+    for (int d = 0; d < 4; d++) {
+        oma[d] = 1.0 - a[d];
+        xa[d] = (x - a[d] * px) / oma[d]; /* x_adjusted, hmm_utils.c:818 */
+        base[d] = a[d] * px;
     }
-    const double scale = cnt / tot;
+    const double *ga = rt + RT_GAUSS;
 #pragma unroll 1
     for (int c = 0; c < n; c++) {
-        const double wgt = scale * pc[c];
-        const double z = (x_adj - rt[RT_GAUSS + g0 + c]) * oma;
+        const int g = g0 + c;
+        const double mu = ga[g], inv = ga[4 * G + g] * rb, coef = ga[5 * G + g] * sq;
+        double s1 = 0.0, s0 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            if (d >= nd) break;
+            double mean = oma[d] * mu + base[d]; /* (1-a)*mu + a*px */
+            mean *= beta;
+            const double dd = x - mean;
+            double p = coef * exp_nonpos((-0.5 * (dd * dd)) * inv);
+            if (p != p) *nan = 1;
+            if (p < 1e-40) p = 1e-40;
+            const double wgt = H[d] * p;
+            const double z = (xa[d] - mu) * oma[d];
+            s1 += wgt * xa[d];
+            s0 += wgt;
+            s2 += wgt * z * z;
+        }
         double *cg_ = colg + (size_t) 3 * c * ld;
-        cg_[0] += wgt * x_adj;
-        cg_[ld] += wgt;
-        cg_[2 * ld] += wgt * z * z;
+        cg_[0] += s1;
+        cg_[ld] += s0;
+        cg_[2 * ld] += s2;
     }
 }
 
@@ -842,6 +841,7 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 double xi[4]; /* adjusted pair counts into state s, by preState */
+                double hh[4]; /* the same without the emission factor (multi-component statistics) */
 #pragma unroll
                 for (int pre = 0; pre < 4; pre++) {
                     const double t = trans_prob(rt, w, pre, s);
@@ -849,7 +849,9 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                     /* b[i-1][pre] += tProb*eProb*b[i][s] (state outer, preState inner: hmm.c:493-520) */
                     bn[pre] += t * e * bh[s];
                     /* count = f[i][pre]*tProb*eProb*b[i+1][s]; adjusted = count / terminationProb (hmm.c:613-614) */
-                    xi[pre] = (((fp[pre] * t) * e) * bh[s]) * HFG_INV_TERM;
+                    const double ft = fp[pre] * t;
+                    xi[pre] = ((ft * e) * bh[s]) * HFG_INV_TERM;
+                    hh[pre] = (ft * bh[s]) * HFG_INV_TERM;
                 }
                 if (!do_stats) continue;
 #pragma unroll
@@ -882,16 +884,26 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                         cg_[LD] += s0;
                         cg_[2 * LD] += s2;
                     } else {
+                        /* pool H = (f*t)*b/term over the preStates of each (state, alpha) class */
+                        double Hc[4] = {0.0, 0.0, 0.0, 0.0}, ac[4] = {0.0, 0.0, 0.0, 0.0};
+                        int nd = 0;
 #pragma unroll
                         for (int pre = 0; pre < 4; pre++) {
                             if (A.first_pre_of_class[pre][s] != pre) continue;
-                            double cnt = xi[pre];
+                            double hsum = hh[pre];
 #pragma unroll
                             for (int p2 = pre + 1; p2 < 4; p2++)
-                                if (A.first_pre_of_class[p2][s] == pre) cnt += xi[p2];
-                            gauss_stats(rt, G, g0, n, A.alpha[pre][s], A.inv_one_minus_alpha[pre][s], cnt, w.x, w.px,
-                                        w.beta, w.rb, w.sq, col + (size_t) (18 + 3 * g0) * LD, LD, &nan_flag);
+                                if (A.first_pre_of_class[p2][s] == pre) hsum += hh[p2];
+#pragma unroll
+                            for (int q = 0; q < 4; q++)
+                                if (q == nd) {
+                                    Hc[q] = hsum;
+                                    ac[q] = A.alpha[pre][s];
+                                }
+                            nd++;
                         }
+                        gauss_state_stats(rt, G, g0, n, nd, Hc[0], Hc[1], Hc[2], Hc[3], ac[0], ac[1], ac[2], ac[3], w.x,
+                                          w.px, w.beta, w.rb, w.sq, col + (size_t) (18 + 3 * g0) * LD, LD, &nan_flag);
                     }
                 }
             }
