@@ -143,3 +143,112 @@ def write_alpha_tsv(alpha, path):
     with open(path, "w") as f:
         for row in np.asarray(alpha).reshape(4, 4):
             f.write("\t".join(f"{v:.3f}" for v in row) + "\n")
+
+
+# ---- native readers (flagger_b200/csrc/hfg_cov_reader.c through include/hfg_io.h) --------------------------------------
+
+import ctypes as _C
+
+
+class _CovData(_C.Structure):
+    _fields_ = [
+        ("n_annotations", _C.c_int32), ("annotation_names", _C.POINTER(_C.c_char_p)),
+        ("n_regions", _C.c_int32), ("region_coverages", _C.POINTER(_C.c_int32)),
+        ("n_labels", _C.c_int32), ("truth_available", _C.c_int32), ("prediction_available", _C.c_int32),
+        ("start_only", _C.c_int32), ("avg_alignment_len", _C.c_int32),
+        ("chunk_len", _C.c_int32), ("window_len", _C.c_int32),
+        ("n_chunks", _C.c_int32), ("chunks", _C.c_void_p), ("contig_names", _C.c_void_p),
+        ("n_windows", _C.c_int64),
+        ("cov", _C.POINTER(_C.c_uint16)), ("cov_high_mapq", _C.POINTER(_C.c_uint16)),
+        ("cov_high_clip", _C.POINTER(_C.c_uint16)), ("annotation_flag", _C.POINTER(_C.c_uint64)),
+        ("region", _C.POINTER(_C.c_uint8)), ("truth", _C.POINTER(_C.c_int8)), ("prediction", _C.POINTER(_C.c_int8)),
+    ]
+
+
+def _to_workload(lib, dptr, name):
+    d = dptr.contents
+    W, Cn = int(d.n_windows), int(d.n_chunks)
+    arr = lambda p, dt: np.ctypeslib.as_array(p, shape=(W,)).astype(dt, copy=True) if W else np.zeros(0, dt)
+    chunks = np.frombuffer(_C.string_at(d.chunks, Cn * _abi.chunk_desc_dtype.itemsize), dtype=_abi.chunk_desc_dtype).copy()
+    raw = _C.string_at(d.contig_names, Cn * 200)
+    names = [raw[i * 200:(i + 1) * 200].split(b"\0", 1)[0].decode() for i in range(Cn)]
+    wl = Workload(name, int(d.window_len), int(d.chunk_len), int(d.avg_alignment_len),
+                  np.array([d.region_coverages[i] for i in range(d.n_regions)], np.int32), names, chunks,
+                  arr(d.cov, np.uint16), arr(d.cov_high_mapq, np.uint16), arr(d.cov_high_clip, np.uint16),
+                  arr(d.region, np.uint8), arr(d.truth, np.int8),
+                  [d.annotation_names[i].decode() for i in range(d.n_annotations)])
+    hdr = dict(n_labels=int(d.n_labels), truth=bool(d.truth_available), prediction=bool(d.prediction_available),
+               start_only=bool(d.start_only), annotation_flag=arr(d.annotation_flag, np.uint64),
+               prediction_labels=arr(d.prediction, np.int8))
+    lib.hfg_cov_free(dptr)
+    return wl, hdr
+
+
+def _io_lib():
+    from .api import lib
+    L = lib()
+    L.hfg_cov_free.restype = None
+    L.hfg_cov_free.argtypes = [_C.POINTER(_CovData)]
+    return L
+
+
+def read_cov_native(path, chunk_len=20_000_000, window_len=4000):
+    """`.cov` / `.cov.gz` -> Workload via the C reader (hfg_read_cov): one pass, run-length aware."""
+    L = _io_lib()
+    out = _C.POINTER(_CovData)()
+    err = _C.create_string_buffer(512)
+    rc = L.hfg_read_cov(str(path).encode(), _C.c_int32(chunk_len), _C.c_int32(window_len), _C.byref(out), err, _C.c_size_t(512))
+    if rc != 0:
+        raise ValueError(f"hfg_read_cov: {err.value.decode()}")
+    return _to_workload(L, out, str(path))
+
+
+def read_bin_native(path):
+    """`.bin` chunk dump -> Workload via the C reader (hfg_read_bin)."""
+    L = _io_lib()
+    out = _C.POINTER(_CovData)()
+    err = _C.create_string_buffer(512)
+    rc = L.hfg_read_bin(str(path).encode(), _C.byref(out), err, _C.c_size_t(512))
+    if rc != 0:
+        raise ValueError(f"hfg_read_bin: {err.value.decode()}")
+    return _to_workload(L, out, str(path))
+
+
+def write_random_rle_cov(path, contig_lens, seed=0, n_regions=3, with_truth=True, float_values=False,
+                         avg_alignment_len=15000):
+    """A `.cov`/`.cov.gz` whose run-length blocks do NOT line up with windows or chunks (lengths 1..3000), with several
+    annotations per block, regions and truth labels: exercises the window builder's averaging / mode / OR logic."""
+    rng = np.random.default_rng(seed)
+    opener = gzip.open if str(path).endswith(".gz") else open
+    region_cov = [40, 52, 30, 61, 25, 48, 36][:n_regions]
+    with opener(path, "wt") as f:
+        f.write("#annotation:len:5\n")
+        for i, nm in enumerate(["no_annotation", "whole_genome", "sat_a", "sat_b", "sat_c"]):
+            f.write(f"#annotation:name:{i}:{nm}\n")
+        f.write(f"#region:len:{n_regions}\n")
+        for i, c in enumerate(region_cov):
+            f.write(f"#region:coverage:{i}:{c}\n")
+        f.write(f"#label:len:{4 if with_truth else 0}\n")
+        if with_truth:
+            for i, nm in enumerate(_abi.STATE_NAMES):
+                f.write(f"#label:name:{i}:{nm}\n")
+        f.write(f"#truth:{'true' if with_truth else 'false'}\n#prediction:false\n")
+        f.write(f"#avg_alignment_len:{avg_alignment_len}\n#start-only:false\n")
+        for ci, L in enumerate(contig_lens):
+            f.write(f">ctg{ci + 1} {int(L)}\n")
+            pos = 1
+            while pos <= L:
+                ln = int(min(rng.integers(1, 3001), L - pos + 1))
+                cov = float(rng.integers(0, 300))
+                if float_values:
+                    cov += float(rng.integers(0, 4)) / 4 + (0.1 if rng.random() < 0.3 else 0.0)
+                mq = cov * float(rng.choice([0.0, 0.1, 0.5, 1.0]))
+                cl = cov * float(rng.choice([0.0, 0.0, 1.0]))
+                fmt = (lambda v: f"{v:.2f}") if float_values else (lambda v: f"{int(v)}")
+                r = int(rng.integers(0, n_regions))
+                annots = sorted(set([1] + list(rng.integers(1, 5, size=int(rng.integers(0, 3))))))
+                line = f"{pos}\t{pos + ln - 1}\t{fmt(cov)}\t{fmt(mq)}\t{fmt(cl)}\t{','.join(str(a) for a in annots)}\t{r}"
+                if with_truth:
+                    line += f"\t{int(rng.integers(-1, 4))}"
+                f.write(line + "\n")
+                pos += ln

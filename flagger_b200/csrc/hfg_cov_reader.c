@@ -1,0 +1,438 @@
+/*
+ * hfg_cov_reader.c -- the data formats upstream of the hot path: `.cov` / `.cov.gz` -> chunks of windows, and the
+ * `.bin` chunk dump.
+ *
+ * Same window semantics as the reference's chunk builder, restated for speed:
+ *   reference                                                   here
+ *   ChunksCreator_createCovIndex (chunk.c:240-294)              chunk layout computed from the contig length alone
+ *   ChunksCreator_parseOneChunk  (chunk.c:506-547): every chunk  ONE sequential pass over the (gz) file
+ *     job re-opens the file and gzseeks from its start
+ *   Chunk_addTrack (chunk.c:444-481): a loop over every BASE     one step per (block x window) overlap: run-length aware,
+ *     of a block with 3 atof + a Splitter allocation each        O(blocks + windows) instead of O(bases)
+ *   Chunk_addWindow (chunk.c:393-441)                            identical: mean -> round -> clip 250; OR of annotation
+ *                                                                flags; region / truth / prediction = mode, ties -> lowest
+ * Integer-valued coverages (what bam2cov writes) make n*value exact, so the window sums are bit-identical to the
+ * reference's base-by-base accumulation; non-integer values fall back to repeated addition to stay so.
+ * No `<input>.index` side file is written (chunk.c:154-162 writes one; it is only a cache of the layout).
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include "../../include/hfg_io.h"
+
+#define MAX_COVERAGE 250.0 /* chunk.c:8 */
+#define LINE_CAP (1 << 16)
+#define REGION_BINS 101    /* Int_getModeValue1DArray(.., 0, 100), chunk.c:388-390 */
+#define LABEL_BINS 12      /* Int_getModeValue1DArray(.., -1, 10), chunk.c:376-385 */
+
+typedef struct Growable {
+    hfg_cov_data *d;
+    int64_t win_cap;
+    int32_t chunk_cap;
+} Growable;
+
+static int grow_windows(Growable *g, int64_t need) {
+    if (need <= g->win_cap) return 1;
+    int64_t cap = g->win_cap ? g->win_cap : 4096;
+    while (cap < need) cap *= 2;
+    hfg_cov_data *d = g->d;
+#define GROW(field, type)                                                  \
+    do {                                                                   \
+        type *p_ = realloc(d->field, sizeof(type) * (size_t) cap);         \
+        if (!p_) return 0;                                                 \
+        d->field = p_;                                                     \
+    } while (0)
+    GROW(cov, uint16_t);
+    GROW(cov_high_mapq, uint16_t);
+    GROW(cov_high_clip, uint16_t);
+    GROW(annotation_flag, uint64_t);
+    GROW(region, uint8_t);
+    GROW(truth, int8_t);
+    GROW(prediction, int8_t);
+#undef GROW
+    g->win_cap = cap;
+    return 1;
+}
+
+static int grow_chunks(Growable *g, int32_t need) {
+    if (need <= g->chunk_cap) return 1;
+    int32_t cap = g->chunk_cap ? g->chunk_cap : 256;
+    while (cap < need) cap *= 2;
+    hfg_chunk_desc *c = realloc(g->d->chunks, sizeof(hfg_chunk_desc) * (size_t) cap);
+    if (!c) return 0;
+    g->d->chunks = c;
+    char(*n)[HFG_CONTIG_NAME_MAX] = realloc(g->d->contig_names, (size_t) cap * HFG_CONTIG_NAME_MAX);
+    if (!n) return 0;
+    g->d->contig_names = n;
+    g->chunk_cap = cap;
+    return 1;
+}
+
+void hfg_cov_free(hfg_cov_data *d) {
+    if (!d) return;
+    for (int i = 0; i < d->n_annotations; i++) free(d->annotation_names ? d->annotation_names[i] : NULL);
+    free(d->annotation_names);
+    free(d->region_coverages);
+    free(d->chunks);
+    free(d->contig_names);
+    free(d->cov);
+    free(d->cov_high_mapq);
+    free(d->cov_high_clip);
+    free(d->annotation_flag);
+    free(d->region);
+    free(d->truth);
+    free(d->prediction);
+    free(d);
+}
+
+/* accumulator of the window being filled (Chunk.windowSum*, windowAnnotationFlag, window*Array) */
+typedef struct Window {
+    int n; /* bases so far (windowItr + 1) */
+    double sum_cov, sum_mapq, sum_clip;
+    uint64_t flag;
+    int32_t region_count[REGION_BINS], truth_count[LABEL_BINS], pred_count[LABEL_BINS];
+} Window;
+
+static void window_reset(Window *w) { memset(w, 0, sizeof(*w)); }
+
+/* sum += n copies of v, bit-identical to adding v n times */
+static void add_n(double *sum, double v, int n) {
+    if (v == floor(v) && fabs(v) < 1e6) {
+        *sum += v * n; /* integers: every partial sum is exact */
+    } else {
+        for (int i = 0; i < n; i++) *sum += v;
+    }
+}
+
+static int mode_of(const int32_t *counts, int bins, int min_value) {
+    int best = 0;
+    for (int i = 1; i < bins; i++)
+        if (counts[best] < counts[i]) best = i;
+    return min_value + best;
+}
+
+static int bin_of(int value, int min_value, int bins) {
+    int idx = value < min_value ? 0 : value - min_value;
+    return idx >= bins ? bins - 1 : idx;
+}
+
+static uint16_t clip_round(double v) {
+    const double r = round(v);
+    return (uint16_t) (MAX_COVERAGE < r ? MAX_COVERAGE : r);
+}
+
+/* Chunk_addWindow, chunk.c:393-441 */
+static int emit_window(Growable *g, Window *w, int window_len, int start_only) {
+    hfg_cov_data *d = g->d;
+    if (!grow_windows(g, d->n_windows + 1)) return 0;
+    const int64_t i = d->n_windows++;
+    double c, m, k;
+    if (start_only) {
+        c = w->sum_cov * window_len / w->n;
+        m = w->sum_mapq * window_len / w->n;
+        k = w->sum_clip * window_len / w->n;
+    } else {
+        c = w->sum_cov / w->n;
+        m = w->sum_mapq / w->n;
+        k = w->sum_clip / w->n;
+    }
+    d->cov[i] = clip_round(c);
+    d->cov_high_mapq[i] = clip_round(m);
+    d->cov_high_clip[i] = clip_round(k);
+    const int region = mode_of(w->region_count, REGION_BINS, 0);
+    d->region[i] = (uint8_t) region;
+    /* CoverageInfo_setRegionIndex, ptBlock.c:300-304 */
+    d->annotation_flag[i] = (w->flag & 0x03FFFFFFFFFFFFFFULL) | ((uint64_t) region << 58);
+    d->truth[i] = (int8_t) mode_of(w->truth_count, LABEL_BINS, -1);
+    d->prediction[i] = (int8_t) mode_of(w->pred_count, LABEL_BINS, -1);
+    d->chunks[d->n_chunks - 1].n_windows++;
+    window_reset(w);
+    return 1;
+}
+
+static int starts_with(const char *s, const char *p) { return strncmp(s, p, strlen(p)) == 0; }
+
+static const char *nth_field(const char *line, char sep, int n) {
+    const char *p = line;
+    for (int i = 0; i < n && p; i++) {
+        p = strchr(p, sep);
+        if (p) p++;
+    }
+    return p;
+}
+
+static int fail_io(char *err, size_t errlen, const char *fmt, const char *a, long b) {
+    snprintf(err, errlen, fmt, a, b);
+    return HFG_ERR_INVALID;
+}
+
+int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_cov_data **out, char *err,
+                 size_t errlen) {
+    if (!path || !out || chunk_len <= 0 || window_len <= 0) return fail_io(err, errlen, "hfg_read_cov: bad argument%s%ld", "", 0);
+    gzFile fp = gzopen(path, "rb"); /* transparently reads plain text as well */
+    if (!fp) return fail_io(err, errlen, "cannot open %s%.0ld", path, 0);
+    gzbuffer(fp, 1 << 20);
+    hfg_cov_data *d = calloc(1, sizeof(*d));
+    Growable g = {d, 0, 0};
+    char *line = malloc(LINE_CAP);
+    Window *win = malloc(sizeof(Window));
+    int status = HFG_OK;
+    if (!d || !line || !win) {
+        status = HFG_ERR_NOMEM;
+        goto done;
+    }
+    d->chunk_len = chunk_len;
+    d->window_len = window_len;
+    window_reset(win);
+
+    char ctg[HFG_CONTIG_NAME_MAX] = "";
+    long ctg_len = 0, next_base = 0; /* next base of the contig that must come */
+    int have_chunk = 0;
+    long line_no = 0;
+    while (gzgets(fp, line, LINE_CAP)) {
+        line_no++;
+        size_t n = strlen(line);
+        while (n && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = '\0';
+        if (n == 0) continue;
+        if (line[0] == '#') { /* header keys, track_reader.c:220-457 */
+            if (starts_with(line, "#annotation:len:")) {
+                d->n_annotations = atoi(line + 16);
+                d->annotation_names = calloc((size_t) (d->n_annotations > 0 ? d->n_annotations : 1), sizeof(char *));
+                for (int i = 0; i < d->n_annotations; i++) d->annotation_names[i] = strdup("NA");
+            } else if (starts_with(line, "#annotation:name:")) {
+                const int idx = atoi(line + 17);
+                const char *name = nth_field(line, ':', 3);
+                if (name && idx >= 0 && idx < d->n_annotations) {
+                    free(d->annotation_names[idx]);
+                    d->annotation_names[idx] = strdup(name);
+                }
+            } else if (starts_with(line, "#region:len:")) {
+                d->n_regions = atoi(line + 12);
+                d->region_coverages = calloc((size_t) (d->n_regions > 0 ? d->n_regions : 1), sizeof(int32_t));
+            } else if (starts_with(line, "#region:coverage:")) {
+                const int idx = atoi(line + 17);
+                const char *v = nth_field(line, ':', 3);
+                if (v && idx >= 0 && idx < d->n_regions) d->region_coverages[idx] = atoi(v);
+            } else if (starts_with(line, "#label:len:")) {
+                d->n_labels = atoi(line + 11);
+            } else if (starts_with(line, "#truth:true")) {
+                d->truth_available = 1;
+            } else if (starts_with(line, "#prediction:true")) {
+                d->prediction_available = 1;
+            } else if (starts_with(line, "#start-only:true")) {
+                d->start_only = 1;
+            } else if (starts_with(line, "#avg_alignment_len:")) {
+                d->avg_alignment_len = atoi(line + 19);
+            }
+            continue;
+        }
+        if (line[0] == '>') { /* ">name length" */
+            if (have_chunk && next_base != ctg_len) {
+                status = fail_io(err, errlen, "%s: contig ended before its declared length (line %ld)", ctg, line_no);
+                goto done;
+            }
+            char *sp = strchr(line, ' ');
+            if (!sp) {
+                status = fail_io(err, errlen, "malformed contig line%s at line %ld", "", line_no);
+                goto done;
+            }
+            *sp = '\0';
+            snprintf(ctg, sizeof(ctg), "%s", line + 1);
+            ctg_len = atol(sp + 1);
+            next_base = 0;
+            have_chunk = 0;
+            continue;
+        }
+        /* data line: start end cov cov_high_mapq cov_high_clip annot[,annot..] region [truth [prediction]] (1-based) */
+        char *f[9];
+        int nf = 0;
+        for (char *p = line; p && nf < 9;) {
+            f[nf++] = p;
+            p = strchr(p, '\t');
+            if (p) *p++ = '\0';
+        }
+        if (nf < 7 || ctg[0] == '\0') {
+            status = fail_io(err, errlen, "malformed data line%s at line %ld", "", line_no);
+            goto done;
+        }
+        long s = atol(f[0]) - 1, e = atol(f[1]) - 1;
+        if (s != next_base || e < s || e >= ctg_len) {
+            status = fail_io(err, errlen, "%s: blocks must tile the contig in order (line %ld)", ctg, line_no);
+            goto done;
+        }
+        const double v_cov = atof(f[2]), v_mapq = atof(f[3]), v_clip = atof(f[4]);
+        uint64_t flag = 0; /* CoverageInfo_getAnnotationFlagFromArray, ptBlock.c:225-236 */
+        for (char *p = f[5]; p && *p;) {
+            const int a = atoi(p);
+            if (a > 0) flag |= 1ULL << (a - 1);
+            p = strchr(p, ',');
+            if (p) p++;
+        }
+        const int rbin = bin_of(atoi(f[6]), 0, REGION_BINS);
+        const int tbin = bin_of(nf >= 8 ? atoi(f[7]) : -1, -1, LABEL_BINS);
+        const int pbin = bin_of(nf >= 9 ? atoi(f[8]) : -1, -1, LABEL_BINS);
+        long pos = s;
+        while (pos <= e) {
+            if (!have_chunk || pos > d->chunks[d->n_chunks - 1].e) {
+                /* next chunk of this contig (ChunksCreator_createCovIndex, chunk.c:260-287): canonical length, the last
+                 * one absorbs a remainder shorter than a full chunk */
+                if (!grow_chunks(&g, d->n_chunks + 1)) {
+                    status = HFG_ERR_NOMEM;
+                    goto done;
+                }
+                hfg_chunk_desc *c = &d->chunks[d->n_chunks];
+                memset(c, 0, sizeof(*c));
+                c->ctg_len = (int32_t) ctg_len;
+                c->s = (int32_t) pos;
+                c->e = (int32_t) (ctg_len < (pos - 1) + 2L * chunk_len ? ctg_len - 1 : (pos - 1) + chunk_len);
+                if (pos == 0) c->e = (int32_t) (ctg_len < 2L * chunk_len ? ctg_len - 1 : chunk_len - 1);
+                c->window_len = window_len;
+                c->offset = d->n_windows;
+                snprintf(d->contig_names[d->n_chunks], HFG_CONTIG_NAME_MAX, "%s", ctg);
+                d->n_chunks++;
+                have_chunk = 1;
+            }
+            const hfg_chunk_desc *c = &d->chunks[d->n_chunks - 1];
+            /* bases of this block that fall into the window being filled */
+            long room = window_len - win->n;
+            long upto = pos + room - 1;
+            if (upto > e) upto = e;
+            if (upto > c->e) upto = c->e;
+            const int nb = (int) (upto - pos + 1);
+            add_n(&win->sum_cov, v_cov, nb);
+            add_n(&win->sum_mapq, v_mapq, nb);
+            add_n(&win->sum_clip, v_clip, nb);
+            win->flag |= flag;
+            win->region_count[rbin] += nb;
+            win->truth_count[tbin] += nb;
+            win->pred_count[pbin] += nb;
+            win->n += nb;
+            pos = upto + 1;
+            if (win->n == window_len || upto == c->e) { /* full window, or the short last window of the chunk */
+                if (!emit_window(&g, win, window_len, d->start_only)) {
+                    status = HFG_ERR_NOMEM;
+                    goto done;
+                }
+            }
+        }
+        next_base = e + 1;
+    }
+    if (have_chunk && next_base != ctg_len) {
+        status = fail_io(err, errlen, "%s: file ended before the contig's declared length%.0ld", ctg, 0);
+        goto done;
+    }
+    if (d->n_annotations <= 0) {
+        status = fail_io(err, errlen, "no '#annotation:len:' in the header of %s%.0ld", path, 0); /* track_reader.c:239-249 */
+        goto done;
+    }
+done:
+    gzclose(fp);
+    free(line);
+    free(win);
+    if (status != HFG_OK) {
+        if (status == HFG_ERR_NOMEM) snprintf(err, errlen, "out of memory reading %s", path);
+        hfg_cov_free(d);
+        d = NULL;
+    }
+    *out = d;
+    return status;
+}
+
+/* ChunksCreator_parseChunksFromBinaryFile, chunk.c:713-828 (little-endian, C bool = 1 byte) */
+int hfg_read_bin(const char *path, hfg_cov_data **out, char *err, size_t errlen) {
+    if (!path || !out) return fail_io(err, errlen, "hfg_read_bin: bad argument%s%ld", "", 0);
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return fail_io(err, errlen, "cannot open %s%.0ld", path, 0);
+    hfg_cov_data *d = calloc(1, sizeof(*d));
+    Growable g = {d, 0, 0};
+    int status = HFG_OK;
+    int32_t v;
+#define RD(ptr, size, count)                                   \
+    do {                                                       \
+        if (fread(ptr, size, count, fp) != (size_t) (count)) { \
+            status = HFG_ERR_INVALID;                          \
+            goto done;                                         \
+        }                                                      \
+    } while (0)
+    RD(&d->n_annotations, 4, 1);
+    if (d->n_annotations < 0 || d->n_annotations > 64) {
+        status = HFG_ERR_INVALID;
+        goto done;
+    }
+    d->annotation_names = calloc((size_t) (d->n_annotations > 0 ? d->n_annotations : 1), sizeof(char *));
+    for (int i = 0; i < d->n_annotations; i++) {
+        RD(&v, 4, 1);
+        if (v <= 0 || v > 4096) {
+            status = HFG_ERR_INVALID;
+            goto done;
+        }
+        d->annotation_names[i] = malloc((size_t) v);
+        RD(d->annotation_names[i], 1, v);
+    }
+    RD(&d->n_regions, 4, 1);
+    if (d->n_regions < 0 || d->n_regions > 4096) {
+        status = HFG_ERR_INVALID;
+        goto done;
+    }
+    d->region_coverages = calloc((size_t) (d->n_regions > 0 ? d->n_regions : 1), sizeof(int32_t));
+    RD(d->region_coverages, 4, d->n_regions);
+    RD(&d->n_labels, 4, 1);
+    {
+        uint8_t b[3];
+        RD(b, 1, 3);
+        d->truth_available = b[0];
+        d->prediction_available = b[1];
+        d->start_only = b[2];
+    }
+    RD(&d->avg_alignment_len, 4, 1);
+    RD(&d->chunk_len, 4, 1);
+    RD(&d->window_len, 4, 1);
+    while (fread(&v, 4, 1, fp) == 1) {
+        if (v <= 0 || v > HFG_CONTIG_NAME_MAX || !grow_chunks(&g, d->n_chunks + 1)) {
+            status = v <= 0 || v > HFG_CONTIG_NAME_MAX ? HFG_ERR_INVALID : HFG_ERR_NOMEM;
+            goto done;
+        }
+        hfg_chunk_desc *c = &d->chunks[d->n_chunks];
+        memset(c, 0, sizeof(*c));
+        RD(d->contig_names[d->n_chunks], 1, v);
+        d->contig_names[d->n_chunks][HFG_CONTIG_NAME_MAX - 1] = '\0';
+        RD(&c->ctg_len, 4, 1);
+        RD(&c->s, 4, 1);
+        RD(&c->e, 4, 1);
+        RD(&c->n_windows, 4, 1);
+        if (c->n_windows < 0) {
+            status = HFG_ERR_INVALID;
+            goto done;
+        }
+        c->window_len = d->window_len;
+        c->offset = d->n_windows;
+        if (!grow_windows(&g, d->n_windows + c->n_windows)) {
+            status = HFG_ERR_NOMEM;
+            goto done;
+        }
+        const int64_t o = d->n_windows;
+        const int L = c->n_windows;
+        RD(d->cov + o, 2, L);
+        RD(d->cov_high_mapq + o, 2, L);
+        RD(d->cov_high_clip + o, 2, L);
+        RD(d->annotation_flag + o, 8, L);
+        RD(d->truth + o, 1, L);
+        RD(d->prediction + o, 1, L);
+        for (int i = 0; i < L; i++) d->region[o + i] = (uint8_t) (d->annotation_flag[o + i] >> 58); /* ptBlock.c:294-298 */
+        d->n_windows += L;
+        d->n_chunks++;
+    }
+#undef RD
+done:
+    fclose(fp);
+    if (status != HFG_OK) {
+        snprintf(err, errlen, status == HFG_ERR_NOMEM ? "out of memory reading %s" : "%s is not a valid chunk dump", path);
+        hfg_cov_free(d);
+        d = NULL;
+    }
+    *out = d;
+    return status;
+}

@@ -1,0 +1,55 @@
+/*
+ * hfg_io.h -- the data formats on either side of the hot path: readers for the inputs
+ * `hmm_flagger` accepts.  Plain C, no GPU involved.  The arrays a reader returns are exactly what hfg_set_chunks
+ * (include/hfg.h) takes.
+ *
+ * Replaces, with the same window semantics:
+ *   ChunksCreator_constructFromCov + ChunksCreator_parseChunks      programs/submodules/chunk/chunk.c:141-236,486-547
+ *   TrackReader_readNextTrackCov, CoverageHeader_construct          programs/submodules/track_reader/track_reader.c:48-96,751-818
+ *   Chunk_addTrack / Chunk_addWindow                                programs/submodules/chunk/chunk.c:393-481
+ *   ChunksCreator_parseChunksFromBinaryFile                         programs/submodules/chunk/chunk.c:713-828
+ */
+#ifndef HFG_IO_H
+#define HFG_IO_H
+
+#include "hfg.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HFG_CONTIG_NAME_MAX 200 /* Chunk.ctg, chunk.h:16 */
+
+/* Everything a coverage input holds once cut into chunks of windows (CoverageHeader, track_reader.h:42-54, + the
+ * ChunksCreator's chunk list, chunk.h:36-50), as flat arrays. */
+typedef struct hfg_cov_data {
+    int32_t n_annotations;
+    char **annotation_names;
+    int32_t n_regions;
+    int32_t *region_coverages;
+    int32_t n_labels, truth_available, prediction_available, start_only, avg_alignment_len;
+    int32_t chunk_len, window_len;
+    int32_t n_chunks;
+    hfg_chunk_desc *chunks;                         /* [n_chunks], offsets into the window arrays */
+    char (*contig_names)[HFG_CONTIG_NAME_MAX];      /* [n_chunks] */
+    int64_t n_windows;
+    uint16_t *cov, *cov_high_mapq, *cov_high_clip;  /* [n_windows] CoverageInfo.coverage* (ptBlock.h:79-92) */
+    uint64_t *annotation_flag;                      /* [n_windows] incl. the region index in bits 58..63 */
+    uint8_t *region;                                /* [n_windows] CoverageInfo_getRegionIndex */
+    int8_t *truth, *prediction;                     /* [n_windows] Inference labels, -1 = none (ptBlock.h:50-55) */
+} hfg_cov_data;
+
+/* `.cov` or `.cov.gz` (run-length blocks tiling every contig) -> chunks of `chunk_len` bases cut into windows of
+ * `window_len` bases.  One sequential pass, O(blocks + windows).  Returns hfg_status; on failure *out is NULL and err
+ * holds a message. */
+int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_cov_data **out, char *err, size_t errlen);
+
+/* `.bin` chunk dump written by `hmm_flagger --dumpBin` (chunk.c:596-709); chunk and window lengths come from the file. */
+int hfg_read_bin(const char *path, hfg_cov_data **out, char *err, size_t errlen);
+
+void hfg_cov_free(hfg_cov_data *data);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

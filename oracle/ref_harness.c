@@ -360,3 +360,60 @@ int ref_best_num_collapsed_comps(int max_coverage, const int32_t *region_coverag
     free(header.regionCoverages);
     return k;
 }
+
+/* ---- the reference's own .cov / .cov.gz chunk builder, flattened (checker for flagger_b200/csrc/hfg_cov_reader.c) ----
+ * ChunksCreator_constructFromCov + ChunksCreator_parseChunks (chunk.c:141-236,486-547).  Note: the reference writes
+ * `<path>.index` next to the input, so point it at a writable copy. */
+void *ref_cov_open(const char *path, int chunkLen, int windowLen, int threads) {
+    ChunksCreator *cc = ChunksCreator_constructFromCov((char *) path, NULL, chunkLen, threads, windowLen);
+    if (ChunksCreator_parseChunks(cc) != 0) return NULL;
+    ChunksCreator_sortChunks(cc);
+    return cc;
+}
+
+void ref_cov_counts(void *handle, int32_t *n_chunks, int64_t *n_windows, int32_t *header /* 8 ints */) {
+    ChunksCreator *cc = handle;
+    int64_t W = 0;
+    for (int c = 0; c < stList_length(cc->chunks); c++) W += ((Chunk *) stList_get(cc->chunks, c))->coverageInfoSeqLen;
+    *n_chunks = (int32_t) stList_length(cc->chunks);
+    *n_windows = W;
+    CoverageHeader *h = cc->header;
+    header[0] = h->numberOfAnnotations;
+    header[1] = h->numberOfRegions;
+    header[2] = h->numberOfLabels;
+    header[3] = h->isTruthAvailable;
+    header[4] = h->isPredictionAvailable;
+    header[5] = h->startOnlyMode;
+    header[6] = h->averageAlignmentLength;
+    header[7] = h->numberOfRegions > 0 ? h->regionCoverages[0] : 0;
+}
+
+void ref_cov_fill(void *handle, hfg_chunk_desc *chunks, char *names /* n_chunks x 200 */, uint16_t *cov, uint16_t *mapq,
+                  uint16_t *clip, uint64_t *flags, int8_t *truth, int8_t *prediction, int32_t *region_coverages) {
+    ChunksCreator *cc = handle;
+    int64_t o = 0;
+    for (int c = 0; c < stList_length(cc->chunks); c++) {
+        Chunk *ch = stList_get(cc->chunks, c);
+        memset(&chunks[c], 0, sizeof(hfg_chunk_desc));
+        chunks[c].ctg_len = ch->ctgLen;
+        chunks[c].s = ch->s;
+        chunks[c].e = ch->e;
+        chunks[c].window_len = ch->windowLen;
+        chunks[c].n_windows = ch->coverageInfoSeqLen;
+        chunks[c].offset = o;
+        strncpy(names + (size_t) c * 200, ch->ctg, 199);
+        for (int i = 0; i < ch->coverageInfoSeqLen; i++, o++) {
+            CoverageInfo *ci = ch->coverageInfoSeq[i];
+            cov[o] = ci->coverage;
+            mapq[o] = ci->coverage_high_mapq;
+            clip[o] = ci->coverage_high_clip;
+            flags[o] = ci->annotation_flag;
+            Inference *inf = ci->data;
+            truth[o] = inf ? inf->truth : -1;
+            prediction[o] = inf ? inf->prediction : -1;
+        }
+    }
+    for (int r = 0; r < cc->header->numberOfRegions; r++) region_coverages[r] = cc->header->regionCoverages[r];
+}
+
+void ref_cov_close(void *handle) { ChunksCreator_destruct(handle); }

@@ -7,7 +7,8 @@ import numpy as np
 from flagger_b200 import synth
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+               if not p.endswith(".golden.npz"))  # *.golden.npz belong to the .cov reader (tests/test_cov_reader.py)
 
 
 def load(name):

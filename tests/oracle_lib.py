@@ -135,3 +135,29 @@ class CpuRun:
         if self.h:
             getattr(self.lib, f"{self.prefix}_close")(self.h)
             self.h = None
+
+
+def reference_parse_cov(path, chunk_len, window_len, threads=2):
+    """The reference's own chunk builder on a .cov/.cov.gz (writes <path>.index next to it!).  None when oracle/_ref is
+    not built.  Returns dict(chunks, names, cov, mapq, clip, flags, truth, prediction, region_coverages, header)."""
+    lib = _load(os.path.join(ORACLE_DIR, "_ref", "libref_harness.so"))
+    if lib is None:
+        return None
+    lib.ref_cov_open.restype = C.c_void_p
+    h = C.c_void_p(lib.ref_cov_open(str(path).encode(), C.c_int(chunk_len), C.c_int(window_len), C.c_int(threads)))
+    n_chunks, n_windows = C.c_int32(0), C.c_int64(0)
+    header = np.zeros(8, np.int32)
+    lib.ref_cov_counts(h, C.byref(n_chunks), C.byref(n_windows), ptr(header))
+    Cn, W = n_chunks.value, n_windows.value
+    out = dict(chunks=np.zeros(Cn, _abi.chunk_desc_dtype), names=np.zeros(Cn * 200, np.uint8), cov=np.zeros(W, np.uint16),
+               mapq=np.zeros(W, np.uint16), clip=np.zeros(W, np.uint16), flags=np.zeros(W, np.uint64),
+               truth=np.zeros(W, np.int8), prediction=np.zeros(W, np.int8),
+               region_coverages=np.zeros(max(int(header[1]), 1), np.int32))
+    lib.ref_cov_fill(h, ptr(out["chunks"]), ptr(out["names"]), ptr(out["cov"]), ptr(out["mapq"]), ptr(out["clip"]),
+                     ptr(out["flags"]), ptr(out["truth"]), ptr(out["prediction"]), ptr(out["region_coverages"]))
+    lib.ref_cov_close(h)
+    raw = out["names"].tobytes()
+    out["names"] = [raw[i * 200:(i + 1) * 200].split(b"\0", 1)[0].decode() for i in range(Cn)]
+    out["region_coverages"] = out["region_coverages"][: int(header[1])]
+    out["header"] = header
+    return out
