@@ -366,8 +366,7 @@ int ref_best_num_collapsed_comps(int max_coverage, const int32_t *region_coverag
  * `<path>.index` next to the input, so point it at a writable copy. */
 void *ref_cov_open(const char *path, int chunkLen, int windowLen, int threads) {
     ChunksCreator *cc = ChunksCreator_constructFromCov((char *) path, NULL, chunkLen, threads, windowLen);
-    if (ChunksCreator_parseChunks(cc) != 0) return NULL;
-    ChunksCreator_sortChunks(cc);
+    if (ChunksCreator_parseChunks(cc) != 0) return NULL; /* chunks stay in file order, as in getChunksCreator (src/hmm_flagger.c:60-103) */
     return cc;
 }
 
