@@ -53,6 +53,8 @@ EXPORTED_SYMBOLS = (
     "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
     "hfg_run_em", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
     "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_read_cov", "hfg_read_bin", "hfg_cov_free",
+    "hfg_params_feasible", "hfg_squarem_alpha_rate", "hfg_squarem_prime", "hfg_squarem_shrink", "hfg_squarem_iteration",
+    "hfg_run_em_accelerated",
 )
 
 
@@ -96,6 +98,29 @@ def mstep(cfg, params, stats, tol=1e-3):
     if rc != 0:
         raise HfgError(rc, "hfg_mstep: invalid arguments")
     return params, bool(conv.value)
+
+
+def params_feasible(cfg, params):
+    """HMM_isFeasible (hmm.c:80-87)."""
+    return bool(lib().hfg_params_feasible(ptr(cfg), ptr(np.ascontiguousarray(params))))
+
+
+def squarem(cfg, p0, p1, p2, n_shrinks=0, margin=1e-2):
+    """The SQUAREM candidate of SquareAccelerator (hmm.c:820-1098): step length from (p0, p1, p2), extrapolated and
+    renormalised parameters, then `n_shrinks` step halvings.  Returns (prime, alpha_rate, feasible)."""
+    L = lib()
+    L.hfg_squarem_alpha_rate.restype = C.c_double
+    p0, p1, p2 = (np.ascontiguousarray(p) for p in (p0, p1, p2))
+    rate = C.c_double(L.hfg_squarem_alpha_rate(ptr(cfg), ptr(p0), ptr(p1), ptr(p2)))
+    prime = np.zeros_like(p0)
+    rc = L.hfg_squarem_prime(ptr(cfg), ptr(p0), ptr(p1), ptr(p2), rate, ptr(prime))
+    for _ in range(n_shrinks):
+        if rc != 0:
+            break
+        rc = L.hfg_squarem_shrink(ptr(cfg), ptr(p0), ptr(p1), ptr(p2), C.c_double(margin), C.byref(rate), ptr(prime))
+    if rc != 0:
+        raise HfgError(rc, "hfg_squarem: the extrapolated mixture weights do not sum to > 0")
+    return prime, rate.value, params_feasible(cfg, prime)
 
 
 class HmmFlaggerGPU:
@@ -208,6 +233,18 @@ class HmmFlaggerGPU:
         self._check(lib().hfg_run_em(self._h, ptr(alpha), ptr(params), C.c_int(max_iterations), C.c_double(tol),
                                      ptr(logliks), C.byref(n), ptr(labels)))
         return params, logliks[:n.value].copy(), labels
+
+    def run_em_accelerated(self, alpha, params, max_iterations, tol=1e-3, want_labels=True):
+        """The EM loop of runHMMFlagger with --accelerate (SQUAREM): returns (params, logliks, alpha_rates, labels)."""
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        params = params.copy()
+        logliks = np.zeros(max_iterations + 1, np.float64)
+        rates = np.zeros(max_iterations + 1, np.float64)
+        n = C.c_int(0)
+        labels = np.empty(self.n_windows, np.int8) if want_labels else None
+        self._check(lib().hfg_run_em_accelerated(self._h, ptr(alpha), ptr(params), C.c_int(max_iterations),
+                                                 C.c_double(tol), ptr(logliks), ptr(rates), C.byref(n), ptr(labels)))
+        return params, logliks[:n.value + 1].copy(), rates[:n.value].copy(), labels
 
     def debug_exp(self, q):
         q = np.ascontiguousarray(q, np.float64)

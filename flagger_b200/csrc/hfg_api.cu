@@ -670,6 +670,74 @@ extern "C" int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *
     return rc;
 }
 
+/* One outer iteration of the `acceleration` branch of runHMMFlagger (src/hmm_flagger.c:344-416) up to, and excluding,
+ * its closing M-step: E(p0) -> M -> E(p1) -> M -> p' by SquareAccelerator_getModelPrime (hmm.c:885-918; forward-only
+ * passes choose the step length) -> E(p').  In: params = p0.  Out: params = p', stats = statistics of E(p'),
+ * *loglik0 = log-likelihood of p0, *alpha_rate = accepted step. */
+extern "C" int hfg_squarem_iteration(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, hfg_region_stats *stats,
+                                     double convergence_tol, double *loglik0, double *alpha_rate) {
+    if (!ctx || !params || !stats || !loglik0) return HFG_ERR_INVALID;
+    const int R = ctx->cfg.n_regions;
+    const size_t pb = sizeof(hfg_region_params) * (size_t) R;
+    hfg_region_params *p0 = (hfg_region_params *) malloc(4 * pb);
+    if (!p0) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+    hfg_region_params *p1 = p0 + R, *p2 = p1 + R, *prime = p2 + R;
+    int rc = HFG_OK, ignored = 0, weights_failed = 0;
+    double ll0 = 0.0, llp = 0.0, rate = -1.0;
+    do {
+        if ((rc = hfg_em_iteration(ctx, alpha, params, stats, &ll0, NULL)) != HFG_OK) break;
+        memcpy(p0, params, pb);
+        memcpy(p1, params, pb);
+        if ((rc = hfg_mstep(&ctx->cfg, p1, stats, convergence_tol, &ignored)) != HFG_OK) break;
+        if ((rc = hfg_em_iteration(ctx, alpha, p1, stats, &llp, NULL)) != HFG_OK) break;
+        memcpy(p2, p1, pb);
+        if ((rc = hfg_mstep(&ctx->cfg, p2, stats, convergence_tol, &ignored)) != HFG_OK) break;
+        rate = hfg_squarem_alpha_rate(&ctx->cfg, p0, p1, p2);
+        rc = hfg_squarem_prime(&ctx->cfg, p0, p1, p2, rate, prime);
+        while (rc == HFG_OK && !hfg_params_feasible(&ctx->cfg, prime))
+            rc = hfg_squarem_shrink(&ctx->cfg, p0, p1, p2, 1e-2, &rate, prime);
+        if (rc != HFG_OK) { weights_failed = 1; break; }
+        if ((rc = hfg_forward_only(ctx, alpha, prime, &llp)) != HFG_OK) break;
+        while (llp < ll0) { /* shrink the step until the likelihood does not drop below p0's */
+            do {
+                rc = hfg_squarem_shrink(&ctx->cfg, p0, p1, p2, 1e-2, &rate, prime);
+            } while (rc == HFG_OK && !hfg_params_feasible(&ctx->cfg, prime));
+            if (rc != HFG_OK) { weights_failed = 1; break; }
+            if ((rc = hfg_forward_only(ctx, alpha, prime, &llp)) != HFG_OK) break;
+        }
+        if (rc != HFG_OK) break;
+        if ((rc = hfg_em_iteration(ctx, alpha, prime, stats, &llp, NULL)) != HFG_OK) break;
+        memcpy(params, prime, pb);
+    } while (0);
+    if (weights_failed) fail(ctx, rc, "SQUAREM: the extrapolated mixture weights do not sum to > 0");
+    *loglik0 = ll0;
+    if (alpha_rate) *alpha_rate = rate;
+    free(p0);
+    return rc;
+}
+
+/* The accelerated EM loop: while (iter <= n && !converged) { squarem iteration; M-step }, then the final inference. */
+extern "C" int hfg_run_em_accelerated(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,
+                                      double convergence_tol, double *logliks, double *alpha_rates, int *n_outer,
+                                      int8_t *labels) {
+    if (!ctx || !params || !logliks || !n_outer) return HFG_ERR_INVALID;
+    hfg_region_stats *stats = (hfg_region_stats *) malloc(sizeof(hfg_region_stats) * (size_t) ctx->cfg.n_regions);
+    if (!stats) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+    int iter = 1, converged = 0, k = 0, rc = HFG_OK;
+    while (iter <= max_iterations && !converged) {
+        double rate = 0.0;
+        if ((rc = hfg_squarem_iteration(ctx, alpha, params, stats, convergence_tol, &logliks[k], &rate)) != HFG_OK) break;
+        if (alpha_rates) alpha_rates[k] = rate;
+        k++;
+        if ((rc = hfg_mstep(&ctx->cfg, params, stats, convergence_tol, &converged)) != HFG_OK) break;
+        iter++;
+    }
+    if (rc == HFG_OK) rc = hfg_em_iteration(ctx, alpha, params, stats, &logliks[k], labels); /* final inference (:464) */
+    *n_outer = k;
+    free(stats);
+    return rc;
+}
+
 /* ---- instrumentation / test hooks (not part of the reference-facing surface) ------------------------------------- */
 
 /* clock64() of thread 0 of every CTA at the six phase boundaries of the last E-step kernel: start, end of phase A,

@@ -7,8 +7,8 @@
  * Outputs written into --outputDir (formats as the reference):
  *   loglikelihood.tsv, transition_{initial,iteration_k,final}.tsv, emission_{...}.tsv, final_flagger_prediction.bed,
  *   posterior_prediction_final.bed (-P), chunks.c_<C>.w_<W>.bin (-B).
- * NOT written: prediction_summary_*.tsv (the reference's 1700-line summary_table module; link libhfg into the reference
- * binary instead when you need them -- INTEGRATION.md) and --accelerate (SQUAREM; same remark).
+ * --accelerate (SQUAREM) runs through hfg_squarem_iteration.  NOT written: prediction_summary_*.tsv (the reference's
+ * 1700-line summary_table module; link libhfg into the reference binary instead when you need them -- INTEGRATION.md).
  */
 #include <getopt.h>
 #include <math.h>
@@ -312,7 +312,7 @@ static struct option long_options[] = {{"input", required_argument, NULL, 'i'},
 int main(int argc, char *argv[]) {
     const char *track = "final_hmm_flagger", *preset = "hifi", *input = NULL, *alpha_tsv = NULL, *contigs = NULL, *out_dir = NULL;
     int iterations = 100, adjust_ends = 1, collapsed = -1, write_params = 0, write_post = 0, chunk_len = 20000000;
-    int window_len = -1, dump_bin = 0, device = 0, model_type = -1;
+    int window_len = -1, dump_bin = 0, device = 0, model_type = -1, accelerate = 0;
     double tol = 0.001, max_mapq = 0.25, min_mapq = 0.75, min_frac = -1.0;
     int min_len[4] = {0, 0, 0, 0};
     int c;
@@ -348,7 +348,7 @@ int main(int argc, char *argv[]) {
                 min_len[0] = a; min_len[1] = b; min_len[3] = d3; /* Err, Dup, Col (src/hmm_flagger.c:744-746) */
                 break;
             }
-            case 's': die("--accelerate is not available in the stand-alone binary; link libhfg into the reference binary (INTEGRATION.md)");
+            case 's': accelerate = 1; break;
             case '@': case 'a': case 'k': case 'v': case 'l': case 'D':
                 break; /* accepted for command-line compatibility; no summary tables / thread pool here */
             default:
@@ -447,14 +447,19 @@ int main(int argc, char *argv[]) {
     int iter = 1, converged = 0;
     double loglik = 0.0;
     while (iter <= iterations && !converged) {
-        if (hfg_em_iteration(ctx, alpha, params, stats, &loglik, NULL) != HFG_OK) {
+        /* --accelerate: E(p0), M, E(p1), M, SQUAREM candidate p' chosen with forward-only passes, E(p') (:382-416) */
+        double rate = 0.0;
+        const int rc_e = accelerate ? hfg_squarem_iteration(ctx, alpha, params, stats, tol, &loglik, &rate)
+                                    : hfg_em_iteration(ctx, alpha, params, stats, &loglik, NULL);
+        if (rc_e != HFG_OK) {
             fprintf(stderr, "%s\n", hfg_last_error(ctx));
             exit(EXIT_FAILURE);
         }
-        fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, iter - 1, loglik);
+        if (accelerate) fprintf(stderr, "[%s] Computed alpha rate for accelerating EM = %.4f\n", stamp(), rate);
+        fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, accelerate ? 3 * (iter - 1) : iter - 1, loglik);
         hfg_mstep(&cfg, params, stats, tol, &converged);
         if (write_params) {
-            snprintf(suffix, sizeof(suffix), "iteration_%d", iter);
+            snprintf(suffix, sizeof(suffix), accelerate ? "iteration_accelerated_%d" : "iteration_%d", iter);
             write_transition_tsv(out_dir, suffix, &cfg, params);
             write_emission_tsv(out_dir, suffix, &cfg, params);
         }
@@ -467,7 +472,7 @@ int main(int argc, char *argv[]) {
         fprintf(stderr, "%s\n", hfg_last_error(ctx));
         exit(EXIT_FAILURE);
     }
-    fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, iter - 1, loglik);
+    fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, accelerate ? 3 * (iter - 1) : iter - 1, loglik);
     fclose(ll_file);
     write_transition_tsv(out_dir, "final", &cfg, params);
     write_emission_tsv(out_dir, "final", &cfg, params);

@@ -180,6 +180,31 @@ int hfg_mstep(const hfg_config *cfg, hfg_region_params *params, const hfg_region
 int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,
                double convergence_tol, double *logliks, int *n_esteps, int8_t *labels);
 
+/* --accelerate (SQUAREM; SquareAccelerator, hmm.c:820-1098): feasibility of a parameter set (HMM_isFeasible, hmm.c:80-87),
+ * the step length from three successive parameter sets (SquareAccelerator_computeRates, hmm.c:1000-1098), the
+ * extrapolated + renormalised parameters for a step length (SquareAccelerator_computeValuesForModelPrime, hmm.c:921-997)
+ * and the step-halving rule (SquareAccelerator_shrinkAlphaAndRecomputeModelPrime, hmm.c:869-883). */
+int hfg_params_feasible(const hfg_config *cfg, const hfg_region_params *params);
+double hfg_squarem_alpha_rate(const hfg_config *cfg, const hfg_region_params *p0, const hfg_region_params *p1,
+                              const hfg_region_params *p2);
+int hfg_squarem_prime(const hfg_config *cfg, const hfg_region_params *p0, const hfg_region_params *p1,
+                      const hfg_region_params *p2, double alpha_rate, hfg_region_params *prime);
+int hfg_squarem_shrink(const hfg_config *cfg, const hfg_region_params *p0, const hfg_region_params *p1,
+                       const hfg_region_params *p2, double margin, double *alpha_rate, hfg_region_params *prime);
+
+/* One outer iteration of the `acceleration` branch (src/hmm_flagger.c:344-416) without its closing M-step:
+ * E(p0) -> M -> E(p1) -> M -> p' (SquareAccelerator_getModelPrime, hmm.c:885-918) -> E(p').  In: params = p0.
+ * Out: params = p', stats = the statistics of E(p'), *loglik0 = log-likelihood of p0, *alpha_rate (may be NULL). */
+int hfg_squarem_iteration(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, hfg_region_stats *stats,
+                          double convergence_tol, double *loglik0, double *alpha_rate);
+
+/* The accelerated EM loop of runHMMFlagger (src/hmm_flagger.c:337-467 with the `acceleration` branch :382-416): per outer
+ * iteration E(p0) -> M -> E(p1) -> M -> extrapolate p' (forward-only passes choose the step, hmm.c:885-918) -> E(p') -> M.
+ * logliks[k] = log-likelihood of p0 at outer iteration k (what loglikelihood.tsv holds), alpha_rates[k] (may be NULL)
+ * the accepted step; both need max_iterations + 1 slots; the last loglik is the final inference pass. */
+int hfg_run_em_accelerated(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,
+                           double convergence_tol, double *logliks, double *alpha_rates, int *n_outer, int8_t *labels);
+
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 
 /* Number of kernels this context has launched so far. */

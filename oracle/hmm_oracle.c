@@ -496,6 +496,191 @@ done:
     return status;
 }
 
+/* ---- SQUAREM (--accelerate) restated: SquareAccelerator, hmm.c:820-1098 ---------------------------------------- */
+
+/* The accelerated parameters of one region copied into / out of a vector, in the order the reference visits them
+ * (EmissionDistSeriesParamIter_next, hmm_utils.c:1218-1245 over EmissionDistParamIter_next :1151-1195): per state, a
+ * truncated exponential contributes its rate (TRUNC_EXP_LAMBDA, the only type the iterator reaches), a Gaussian
+ * contributes mean, var, weight of comp 0, then of comp 1, ...; then rows 0..3 x columns 0..3 of the transition matrix
+ * (hmm.c:977-992,1072-1090). */
+static int accel_gather(const hfg_config *cfg, const hfg_region_params *p, double *vec) {
+    int n = 0;
+    for (int s = 0; s < NS; s++) {
+        if (!state_is_gaussian(cfg, s)) {
+            vec[n++] = p->lambda;
+            continue;
+        }
+        for (int c = 0; c < cfg->n_comps[s]; c++) {
+            vec[n++] = p->mean[s][c];
+            vec[n++] = p->var[s][c];
+            vec[n++] = p->weight[s][c];
+        }
+    }
+    for (int i = 0; i < NS; i++)
+        for (int j = 0; j < NS; j++) vec[n++] = p->trans[i][j];
+    return n;
+}
+
+static void accel_scatter(const hfg_config *cfg, const double *vec, hfg_region_params *p) {
+    int n = 0;
+    for (int s = 0; s < NS; s++) {
+        if (!state_is_gaussian(cfg, s)) {
+            p->lambda = vec[n++];
+            continue;
+        }
+        for (int c = 0; c < cfg->n_comps[s]; c++) {
+            p->mean[s][c] = vec[n++];
+            p->var[s][c] = vec[n++];
+            p->weight[s][c] = vec[n++];
+        }
+    }
+    for (int i = 0; i < NS; i++)
+        for (int j = 0; j < NS; j++) p->trans[i][j] = vec[n++];
+}
+
+#define ACCEL_MAX (NS * HFG_MAX_COMPS * 3 + NS * NS)
+
+int orc_feasible(const hfg_config *cfg, const hfg_region_params *params) { /* HMM_isFeasible, hmm.c:80-87 */
+    int feasible = 1;
+    for (int r = 0; r < cfg->n_regions; r++) {
+        const hfg_region_params *p = &params[r];
+        for (int s = 0; s < NS; s++) {
+            if (!state_is_gaussian(cfg, s)) { /* hmm_utils.c:920-925 */
+                if (!(0 < p->lambda)) feasible = 0;
+                if (!(0 < p->trunc_point)) feasible = 0;
+                continue;
+            }
+            for (int c = 0; c < cfg->n_comps[s]; c++) { /* hmm_utils.c:685-694 */
+                if (!(0 < p->mean[s][c])) feasible = 0;
+                if (!(0 < p->var[s][c])) feasible = 0;
+                if (!((0 <= p->weight[s][c]) && (p->weight[s][c] <= 1))) feasible = 0;
+            }
+        }
+        for (int i = 0; i < NS; i++) /* hmm_utils.c:2130-2139 */
+            for (int j = 0; j < NS; j++)
+                if (p->trans[i][j] < 0 || 1 < p->trans[i][j]) feasible = 0;
+    }
+    return feasible;
+}
+
+static void accel_candidate(const hfg_config *cfg, const hfg_region_params *p0, const hfg_region_params *p1,
+                            const hfg_region_params *p2, double rate, hfg_region_params *prime) {
+    double v0[ACCEL_MAX], v1[ACCEL_MAX], v2[ACCEL_MAX], vp[ACCEL_MAX];
+    for (int reg = 0; reg < cfg->n_regions; reg++) {
+        const int n = accel_gather(cfg, &p0[reg], v0);
+        accel_gather(cfg, &p1[reg], v1);
+        accel_gather(cfg, &p2[reg], v2);
+        for (int i = 0; i < n; i++) {
+            const double r = v1[i] - v0[i];
+            const double v = v2[i] - v1[i] - r;
+            vp[i] = v0[i] - 2 * r * rate + v * pow(rate, 2); /* hmm.c:960 */
+        }
+        prime[reg] = p0[reg]; /* modelPrime starts as a copy of model 0 (hmm.c:853-858) */
+        accel_scatter(cfg, vp, &prime[reg]);
+        hfg_region_params *q = &prime[reg];
+        for (int s = 0; s < NS; s++) { /* Gaussian_normalizeWeights, hmm_utils.c:675-683 */
+            if (!state_is_gaussian(cfg, s)) continue;
+            double sum = 0.0;
+            for (int c = 0; c < cfg->n_comps[s]; c++) sum += q->weight[s][c];
+            for (int c = 0; c < cfg->n_comps[s]; c++) q->weight[s][c] *= 1.0 / sum;
+        }
+        for (int i = 0; i < NS; i++) { /* Transition_normalizeTransitionRows, hmm_utils.c:2165-2183 */
+            double rowSum = 0.0;
+            for (int j = 0; j < NS; j++) rowSum += q->trans[i][j];
+            for (int j = 0; j < NS; j++) q->trans[i][j] = q->trans[i][j] / rowSum * (1.0 - ORC_TERM);
+        }
+        for (int i = 0; i < NS; i++) q->trans[i][NS] = ORC_TERM;
+        q->trans[NS][NS] = 0.0;
+    }
+}
+
+static double accel_rate(const hfg_config *cfg, const hfg_region_params *p0, const hfg_region_params *p1,
+                         const hfg_region_params *p2) { /* SquareAccelerator_computeRates, hmm.c:1000-1098 */
+    double v0[ACCEL_MAX], v1[ACCEL_MAX], v2[ACCEL_MAX], num = 0.0, den = 0.0;
+    for (int reg = 0; reg < cfg->n_regions; reg++) {
+        const int n = accel_gather(cfg, &p0[reg], v0);
+        accel_gather(cfg, &p1[reg], v1);
+        accel_gather(cfg, &p2[reg], v2);
+        for (int i = 0; i < n; i++) {
+            const double r = v1[i] - v0[i];
+            const double v = v2[i] - v1[i] - r;
+            num += pow(r, 2);
+            den += pow(v, 2);
+        }
+    }
+    double rate = -1 * sqrt(num / den);
+    if (rate > -1) rate = -1;
+    return rate;
+}
+
+static void accel_shrink(const hfg_config *cfg, const hfg_region_params *p0, const hfg_region_params *p1,
+                         const hfg_region_params *p2, double margin, double *rate, hfg_region_params *prime) {
+    *rate = (*rate - 1) / 2; /* hmm.c:869-883 */
+    if (*rate > (-1 - margin)) {
+        *rate = -1.0;
+        memcpy(prime, p0, sizeof(hfg_region_params) * (size_t) cfg->n_regions);
+    } else {
+        accel_candidate(cfg, p0, p1, p2, *rate, prime);
+    }
+}
+
+/* computeRates + computeValuesForModelPrime + n_shrinks x shrinkAlphaAndRecomputeModelPrime; returns feasibility */
+int orc_squarem(const hfg_config *cfg, const hfg_region_params *p0, const hfg_region_params *p1,
+                const hfg_region_params *p2, int n_shrinks, double margin, hfg_region_params *prime, double *alpha_rate) {
+    double rate = accel_rate(cfg, p0, p1, p2);
+    accel_candidate(cfg, p0, p1, p2, rate, prime);
+    for (int i = 0; i < n_shrinks; i++) accel_shrink(cfg, p0, p1, p2, margin, &rate, prime);
+    *alpha_rate = rate;
+    return orc_feasible(cfg, prime);
+}
+
+/* runHMMFlagger with acceleration == true (src/hmm_flagger.c:337-467) + SquareAccelerator_getModelPrime (hmm.c:885-918) */
+int orc_run_em_accelerated(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                           const uint16_t *mapq, const uint16_t *clip, const uint8_t *region, const double *alpha,
+                           hfg_region_params *params, int max_iterations, double tol, double *logliks,
+                           double *alpha_rates, int *n_outer, int8_t *labels) {
+    const int R = cfg->n_regions;
+    hfg_region_stats *stats = calloc((size_t) R, sizeof(hfg_region_stats));
+    hfg_region_params *p0 = calloc((size_t) R * 4, sizeof(hfg_region_params)), *p1 = p0 + R, *p2 = p1 + R, *pp = p2 + R;
+    int iter = 1, converged = 0, k = 0, status = HFG_OK, ignored;
+#define ESTEP(P, LL, FWD) orc_estep(cfg, n_chunks, chunks, cov, mapq, clip, region, alpha, (P), stats, (LL), NULL, NULL, \
+                                    NULL, NULL, NULL, NULL, (FWD))
+    while (iter <= max_iterations && !converged) {
+        double ll0, llp;
+        if ((status = ESTEP(params, &ll0, 0)) != HFG_OK) goto done;
+        logliks[k] = ll0;
+        memcpy(p0, params, sizeof(hfg_region_params) * (size_t) R);
+        memcpy(p1, params, sizeof(hfg_region_params) * (size_t) R);
+        orc_mstep(cfg, p1, stats, tol, &ignored);
+        if ((status = ESTEP(p1, &llp, 0)) != HFG_OK) goto done;
+        memcpy(p2, p1, sizeof(hfg_region_params) * (size_t) R);
+        orc_mstep(cfg, p2, stats, tol, &ignored);
+        double rate = accel_rate(cfg, p0, p1, p2);
+        accel_candidate(cfg, p0, p1, p2, rate, pp);
+        while (!orc_feasible(cfg, pp)) accel_shrink(cfg, p0, p1, p2, 1e-2, &rate, pp);
+        if ((status = ESTEP(pp, &llp, 1)) != HFG_OK) goto done;
+        while (llp < ll0) {
+            accel_shrink(cfg, p0, p1, p2, 1e-2, &rate, pp);
+            while (!orc_feasible(cfg, pp)) accel_shrink(cfg, p0, p1, p2, 1e-2, &rate, pp);
+            if ((status = ESTEP(pp, &llp, 1)) != HFG_OK) goto done;
+        }
+        if (alpha_rates) alpha_rates[k] = rate;
+        k++;
+        if ((status = ESTEP(pp, &llp, 0)) != HFG_OK) goto done;
+        memcpy(params, pp, sizeof(hfg_region_params) * (size_t) R);
+        orc_mstep(cfg, params, stats, tol, &converged);
+        iter++;
+    }
+    status = orc_estep(cfg, n_chunks, chunks, cov, mapq, clip, region, alpha, params, stats, &logliks[k], NULL, labels,
+                       NULL, NULL, NULL, NULL, 0);
+#undef ESTEP
+done:
+    *n_outer = k;
+    free(stats);
+    free(p0);
+    return status;
+}
+
 /* persistent handle for benchmarking (mirrors ref_open/ref_step/ref_close of ref_harness.c): whole EM iterations
  * of the restatement, single-threaded */
 typedef struct OrcRun {

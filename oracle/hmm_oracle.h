@@ -30,6 +30,14 @@ int orc_run_em(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *chunks
                hfg_region_params *params, int max_iterations, double tol, double *logliks, int *n_esteps,
                int8_t *labels);
 
+int orc_feasible(const hfg_config *cfg, const hfg_region_params *params);
+int orc_squarem(const hfg_config *cfg, const hfg_region_params *p0, const hfg_region_params *p1,
+                const hfg_region_params *p2, int n_shrinks, double margin, hfg_region_params *prime, double *alpha_rate);
+int orc_run_em_accelerated(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                           const uint16_t *mapq, const uint16_t *clip, const uint8_t *region, const double *alpha,
+                           hfg_region_params *params, int max_iterations, double tol, double *logliks,
+                           double *alpha_rates, int *n_outer, int8_t *labels);
+
 #ifdef __cplusplus
 }
 #endif

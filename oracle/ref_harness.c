@@ -416,3 +416,79 @@ void ref_cov_fill(void *handle, hfg_chunk_desc *chunks, char *names /* n_chunks 
 }
 
 void ref_cov_close(void *handle) { ChunksCreator_destruct(handle); }
+
+/* ---- SQUAREM host arithmetic (checker for hfg_squarem_* / hfg_params_feasible) ----
+ * The reference's own SquareAccelerator (hmm.c:820-1098) fed with three parameter sets: computeRates +
+ * computeValuesForModelPrime, then `n_shrinks` x shrinkAlphaAndRecomputeModelPrime(margin).  Returns HMM_isFeasible of the
+ * resulting model. */
+/* defined in hmm.c but not declared in hmm.h */
+HMM *SquareAccelerator_shrinkAlphaAndRecomputeModelPrime(SquareAccelerator *accelerator, double alphaMargin);
+
+int ref_squarem(const hfg_config *cfg, const hfg_region_params *p0, const hfg_region_params *p1,
+                const hfg_region_params *p2, int n_shrinks, double margin, hfg_region_params *prime, double *alpha_rate) {
+    HMM *m0 = make_model(cfg, NULL, 4000, 0, NULL), *m1 = make_model(cfg, NULL, 4000, 0, NULL),
+        *m2 = make_model(cfg, NULL, 4000, 0, NULL);
+    params_to_model(cfg, p0, m0);
+    params_to_model(cfg, p1, m1);
+    params_to_model(cfg, p2, m2);
+    SquareAccelerator *acc = SquareAccelerator_construct();
+    SquareAccelerator_setModel0(acc, m0);
+    SquareAccelerator_setModel1(acc, m1);
+    SquareAccelerator_setModel2(acc, m2);
+    SquareAccelerator_computeRates(acc);
+    HMM *mp = SquareAccelerator_computeValuesForModelPrime(acc);
+    for (int i = 0; i < n_shrinks; i++) mp = SquareAccelerator_shrinkAlphaAndRecomputeModelPrime(acc, margin);
+    model_to_params(cfg, mp, prime);
+    *alpha_rate = acc->alphaRate;
+    return HMM_isFeasible(mp) ? 1 : 0;
+}
+
+/* the accelerated EM loop of runHMMFlagger (src/hmm_flagger.c:337-467 with acceleration == true) driven with the reference's
+ * own functions; logliks[k] = what loglikelihood.tsv holds, alpha_rates[k] = the accepted SQUAREM step */
+int ref_run_em_accelerated(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *cd, const uint16_t *cov,
+                           const uint16_t *mapq, const uint16_t *clip, const uint8_t *region, const double *alpha,
+                           hfg_region_params *params, int max_iterations, double tol, double *logliks,
+                           double *alpha_rates, int *n_outer, int8_t *labels, int threads) {
+    RefData *d = build(cfg, n_chunks, cd, cov, mapq, clip, region, alpha, params);
+    HMM *model = d->model;
+    int iter = 1, k = 0;
+    bool converged = false;
+    while (iter <= max_iterations && !converged) {
+        EM_runOneIterationForList(d->ems, model, threads);
+        logliks[k] = model->loglikelihood;
+        SquareAccelerator *accelerator = SquareAccelerator_construct();
+        SquareAccelerator_setModel0(accelerator, model);
+        HMM_estimateParameters(model, tol);
+        SquareAccelerator_setModel1(accelerator, model);
+        HMM_resetEstimators(model);
+        EM_runOneIterationForList(d->ems, model, threads);
+        HMM_estimateParameters(model, tol);
+        SquareAccelerator_setModel2(accelerator, model);
+        HMM *modelPrime = SquareAccelerator_getModelPrime(accelerator, d->ems, threads);
+        if (alpha_rates) alpha_rates[k] = accelerator->alphaRate;
+        k++;
+        HMM_resetEstimators(modelPrime);
+        EM_runOneIterationForList(d->ems, modelPrime, threads);
+        HMM_destruct(model);
+        model = HMM_copy(modelPrime);
+        d->model = model;
+        for (int c = 0; c < stList_length(d->ems); c++) EM_renewParametersAndEstimatorsFromModel(stList_get(d->ems, c), model);
+        SquareAccelerator_destruct(accelerator);
+        converged = HMM_estimateParameters(model, tol);
+        HMM_resetEstimators(model);
+        iter++;
+    }
+    EM_runOneIterationForList(d->ems, model, threads);
+    logliks[k] = model->loglikelihood;
+    *n_outer = k;
+    model_to_params(cfg, model, params);
+    if (labels) {
+        for (int c = 0; c < n_chunks; c++) {
+            EM *em = stList_get(d->ems, c);
+            for (int i = 0; i < cd[c].n_windows; i++)
+                labels[cd[c].offset + i] = ((Inference *) em->coverageInfoSeq[i]->data)->prediction;
+        }
+    }
+    teardown(d);
+    return 0;
+}

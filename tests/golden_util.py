@@ -8,7 +8,12 @@ from flagger_b200 import synth
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NAMES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-               if not p.endswith(".golden.npz"))  # *.golden.npz belong to the .cov reader (tests/test_cov_reader.py)
+               if not p.endswith((".golden.npz", ".squarem.npz")))  # .cov reader / SQUAREM fixtures have their own tests
+
+
+def load_squarem(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".squarem.npz"))
+    return {k: z[k] for k in z.files}
 
 
 def load(name):

@@ -86,6 +86,31 @@ class _Checker:
         rc = self._fn("run_em")(*args)
         return dict(rc=rc, params=params, logliks=logliks[:n.value].copy(), labels=labels, estep_seconds=secs.value)
 
+    def squarem(self, cfg, p0, p1, p2, n_shrinks=0, margin=1e-2):
+        """SquareAccelerator: computeRates + computeValuesForModelPrime + n_shrinks step halvings."""
+        p0, p1, p2 = (np.ascontiguousarray(p) for p in (p0, p1, p2))
+        prime = np.zeros_like(p0)
+        rate = C.c_double(0.0)
+        feasible = self._fn("squarem")(ptr(cfg), ptr(p0), ptr(p1), ptr(p2), C.c_int(n_shrinks), C.c_double(margin),
+                                       ptr(prime), C.byref(rate))
+        return prime, rate.value, bool(feasible)
+
+    def run_em_accelerated(self, cfg, wl, alpha, params, max_iterations, tol=1e-12):
+        params = params.copy()
+        logliks = np.zeros(max_iterations + 1, np.float64)
+        rates = np.zeros(max_iterations + 1, np.float64)
+        n = C.c_int(0)
+        labels = np.full(wl.n_windows, -1, np.int8)
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        args = [ptr(cfg), C.c_int(wl.n_chunks), ptr(wl.chunks), ptr(wl.cov), ptr(wl.cov_high_mapq),
+                ptr(wl.cov_high_clip), ptr(wl.region), ptr(alpha), ptr(params), C.c_int(max_iterations),
+                C.c_double(tol), ptr(logliks), ptr(rates), C.byref(n), ptr(labels)]
+        if self.threads is not None:
+            args.append(C.c_int(self.threads))
+        rc = self._fn("run_em_accelerated")(*args)
+        return dict(rc=rc, params=params, logliks=logliks[:n.value + 1].copy(), alpha_rates=rates[:n.value].copy(),
+                    labels=labels)
+
     def best_num_collapsed_comps(self, max_cov, region_coverages):
         rc_ = np.ascontiguousarray(region_coverages, np.int32)
         return self._fn("best_num_collapsed_comps")(C.c_int(int(max_cov)), ptr(rc_), C.c_int(len(rc_)))

@@ -76,7 +76,7 @@ def test_pre_gpu_outputs_byte_identical(tmp_path, kind, extra):
 
 def test_rejects_bad_arguments(tmp_path):
     inp, alpha = _inputs(tmp_path, "cov")
-    for extra in (("-t", "0"), ("-x", "nanopore"), ("-M", "1,2"), ("-f", "1.5"), ("-s",)):
+    for extra in (("-t", "0"), ("-x", "nanopore"), ("-M", "1,2"), ("-f", "1.5")):
         r = _run(CLI, inp, str(tmp_path / "o"), extra=extra, check=False)
         assert r.returncode != 0 and "Error" in r.stderr, extra
     r = subprocess.run([CLI, "-i", str(tmp_path / "x.txt"), "-o", str(tmp_path)], capture_output=True, text=True)
@@ -116,6 +116,7 @@ def _compare_runs(ref_out, cli_out, posterior=False):
     ("cov", ("-m", "gaussian", "-p", "3")),
     ("cov", ("-e",)),                                # --disableAdjustContigEnds
     ("cov", ("-q", "0.1", "--minHighMapqRatio", "0.9", "-f", "0.5")),
+    ("bin", ("-s", "-w")),                           # --accelerate (SQUAREM)
 ])
 def test_full_run_matches_reference(tmp_path, kind, extra):
     inp, alpha = _inputs(tmp_path, kind)
