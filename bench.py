@@ -78,6 +78,10 @@ class ClockSampler:
         self.idx, self.rows, self.proc = gpu_index, [], None
 
     def start(self):
+        if os.environ.get("BENCH_SAMPLER", "smi") == "none":
+            return
+        if os.environ.get("BENCH_SAMPLER", "smi") == "nvml":
+            return self._start_nvml()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -92,6 +96,27 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _start_nvml(self):
+        """In-process NVML polling (nvidia_ml_py): no nvidia-smi process attaching to the driver next to the job."""
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        self.nvml_stop = threading.Event()
+
+        def loop():
+            while not self.nvml_stop.is_set():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append([str(self.idx), str(sm), str(mx), "", ""] +
+                                 ["Active" if r & b else "Not Active" for b in bits.values()])
+                self.nvml_stop.wait(0.05)
+        self.t = threading.Thread(target=loop, daemon=True)
+        self.t.start()
+        self.proc = "nvml"
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
@@ -99,11 +124,15 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.proc == "nvml":
+            self.nvml_stop.set()
+            self.t.join(timeout=2)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]

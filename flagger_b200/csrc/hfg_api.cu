@@ -9,7 +9,9 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <pthread.h>
 #include <string.h>
+#include <time.h>
 
 #include "hfg_estep.cuh"
 #include "hfg_internal.h"
@@ -37,6 +39,7 @@ struct hfg_ctx {
     int8_t *d_labels;
     long long *d_phase_clock;
     void *d_arena;   /* one device allocation behind all per-run buffers */
+    size_t arena_bytes;
     int8_t *h_labels; /* pinned staging for the label read-back */
     /* pinned host staging */
     hfg_region_params *h_params[STAGE_SLOTS];
@@ -201,12 +204,68 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     return HFG_OK;
 }
 
+/* One released arena per process is kept for the next context on the same device: cudaMalloc of the ~130 MB arena of a
+ * 3 Gbp job costs 0.4 ms on a quiet driver but was measured at 6-60 ms on a freshly booted box, more than the job's upload.
+ * hfg_release_cached_memory() returns it to the driver; HFG_NO_ARENA_CACHE=1 disables the cache. */
+static pthread_mutex_t g_cache_mu = PTHREAD_MUTEX_INITIALIZER;
+static struct { void *ptr; size_t bytes; int device; } g_cache = {NULL, 0, -1};
+
+static void arena_release(void *ptr, size_t bytes, int device) {
+    if (!ptr) return;
+    void *drop = ptr;
+    if (!getenv("HFG_NO_ARENA_CACHE")) {
+        pthread_mutex_lock(&g_cache_mu);
+        if (!g_cache.ptr || g_cache.bytes < bytes) { /* keep the larger one */
+            drop = g_cache.ptr;
+            const int drop_dev = g_cache.device;
+            g_cache.ptr = ptr;
+            g_cache.bytes = bytes;
+            g_cache.device = device;
+            if (drop) cudaSetDevice(drop_dev);
+        }
+        pthread_mutex_unlock(&g_cache_mu);
+    }
+    if (drop) cudaFree(drop);
+    cudaSetDevice(device);
+}
+
+static void *arena_acquire(size_t bytes, int device, size_t *got) {
+    void *ptr = NULL;
+    pthread_mutex_lock(&g_cache_mu);
+    if (g_cache.ptr && g_cache.device == device && g_cache.bytes >= bytes && g_cache.bytes <= 2 * bytes + (1u << 20)) {
+        ptr = g_cache.ptr;
+        *got = g_cache.bytes;
+        g_cache.ptr = NULL;
+        g_cache.bytes = 0;
+        g_cache.device = -1;
+    }
+    pthread_mutex_unlock(&g_cache_mu);
+    if (!ptr) {
+        if (cudaMalloc(&ptr, bytes) != cudaSuccess) return NULL;
+        *got = bytes;
+    }
+    return ptr;
+}
+
+extern "C" void hfg_release_cached_memory(void) {
+    pthread_mutex_lock(&g_cache_mu);
+    if (g_cache.ptr) {
+        cudaSetDevice(g_cache.device);
+        cudaFree(g_cache.ptr);
+        g_cache.ptr = NULL;
+        g_cache.bytes = 0;
+        g_cache.device = -1;
+    }
+    pthread_mutex_unlock(&g_cache_mu);
+}
+
 static void free_device(hfg_ctx *ctx) {
     if (ctx->gexec) { /* the captured graph holds pointers into the buffers released below */
         cudaGraphExecDestroy(ctx->gexec);
         ctx->gexec = NULL;
     }
-    cudaFree(ctx->d_arena);
+    arena_release(ctx->d_arena, ctx->arena_bytes, ctx->device);
+    ctx->arena_bytes = 0;
     cudaFree(ctx->d_post);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_labels) cudaFreeHost(ctx->h_labels);
@@ -250,6 +309,12 @@ extern "C" size_t hfg_stats_device_bytes(const hfg_ctx *ctx) {
     return ctx ? ((size_t) ctx->cfg.n_regions * STATS_DOUBLES + 2) * sizeof(double) : 0;
 }
 
+static double wall_ms() {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return 1e3 * t.tv_sec + 1e-6 * t.tv_nsec;
+}
+
 extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
                               const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region) {
     if (!ctx) return HFG_ERR_INVALID;
@@ -258,6 +323,9 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     free_device(ctx);
+    const bool timing = getenv("HFG_TIMING") != NULL; /* where the set-up time goes, on stderr */
+    double tm[6] = {0};
+    tm[0] = wall_ms();
     int64_t W = 0;
     for (int32_t c = 0; c < n_chunks; c++) W += chunks[c].n_windows;
     /* persistent grid: one CTA per SM, but do not spread a tiny input over the whole chip */
@@ -269,6 +337,7 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     int rc = hfg_layout_build(&ctx->cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, cap, &ctx->lay,
                               ctx->err, sizeof(ctx->err));
     if (rc != HFG_OK) return rc;
+    tm[1] = wall_ms();
     const hfg_layout *l = &ctx->lay;
     const size_t slots = (size_t) l->smax * cap;
     const int R = ctx->cfg.n_regions, G = total_gauss_comps(&ctx->cfg);
@@ -292,7 +361,13 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         const size_t o_err = CARVE(sizeof(int32_t));
         const size_t o_pc = CARVE((size_t) ctx->grid * 10 * sizeof(long long));
 #undef CARVE
-        CU(cudaMalloc(&ctx->d_arena, off));
+        ctx->d_arena = arena_acquire(off, ctx->device, &ctx->arena_bytes);
+        if (!ctx->d_arena) {
+            cudaGetLastError();
+            return fail(ctx, HFG_ERR_NOMEM, "hfg_set_chunks: cannot allocate %zu bytes of device memory", off);
+        }
+        tm[2] = wall_ms();
+        if (timing) fprintf(stderr, "[hfg] arena %.1f MB\n", off / 1e6);
         char *base = (char *) ctx->d_arena;
         ctx->d_obsT = (uint32_t *) (base + o_obs);
         ctx->d_seg_start = (int32_t *) (base + o_ss);
@@ -313,6 +388,7 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     }
     CU(cudaMallocHost((void **) &ctx->h_out, out_doubles * sizeof(double)));
     CU(cudaMallocHost((void **) &ctx->h_labels, (size_t) l->n_windows));
+    tm[3] = wall_ms();
     CU(cudaMemcpyAsync(ctx->d_obsT, l->obsT, slots * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_start, l->seg_start, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_len, l->seg_len, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -323,6 +399,10 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
                            ctx->stream));
     CU(cudaMemsetAsync(ctx->d_labels, 0xff, (size_t) l->n_windows, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    tm[4] = wall_ms();
+    if (timing)
+        fprintf(stderr, "[hfg] set_chunks: layout %.2f ms, cudaMalloc %.2f ms, cudaMallocHost %.2f ms, copies %.2f ms\n",
+                tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3]);
     free(ctx->lay.obsT); /* the packed words now live on the device */
     ctx->lay.obsT = NULL;
     ctx->have_chunks = 1;

@@ -205,6 +205,10 @@ int hfg_squarem_iteration(hfg_ctx *ctx, const double *alpha, hfg_region_params *
 int hfg_run_em_accelerated(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,
                            double convergence_tol, double *logliks, double *alpha_rates, int *n_outer, int8_t *labels);
 
+/* A destroyed context leaves its device arena (one per process) for the next context on the same device, so that a
+ * process running job after job does not pay cudaMalloc per job; this returns it to the driver. */
+void hfg_release_cached_memory(void);
+
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 
 /* Number of kernels this context has launched so far. */
