@@ -328,14 +328,18 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     tm[0] = wall_ms();
     int64_t W = 0;
     for (int32_t c = 0; c < n_chunks; c++) W += chunks[c].n_windows;
-    /* persistent grid: one CTA per SM, but do not spread a tiny input over the whole chip */
-    int64_t blocks = (W + (int64_t) ctx->threads * 4 - 1) / ((int64_t) ctx->threads * 4);
+    /* persistent grid: at most one CTA per SM.  The layout picks the shortest segment length that fits the full grid and
+     * then keeps only the CTAs those segments fill (profiles/grid_sweep.py: idle CTAs cost more at the grid barriers than
+     * they save); HFG_MIN_WPT = minimum windows per thread before another CTA is added (default 1). */
+    int wpt = 1;
+    if (getenv("HFG_MIN_WPT")) wpt = atoi(getenv("HFG_MIN_WPT")) > 0 ? atoi(getenv("HFG_MIN_WPT")) : 1;
+    int64_t blocks = (W + (int64_t) ctx->threads * wpt - 1) / ((int64_t) ctx->threads * wpt);
     if (blocks < 1) blocks = 1;
     if (blocks > ctx->max_blocks) blocks = ctx->max_blocks;
-    ctx->grid = (int) blocks;
-    const int32_t cap = ctx->grid * ctx->threads;
-    int rc = hfg_layout_build(&ctx->cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, cap, &ctx->lay,
-                              ctx->err, sizeof(ctx->err));
+    int rc = hfg_layout_build(&ctx->cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region,
+                              (int32_t) blocks * ctx->threads, ctx->threads, &ctx->lay, ctx->err, sizeof(ctx->err));
+    if (rc == HFG_OK) ctx->grid = ctx->lay.capacity / ctx->threads;
+    const int32_t cap = ctx->lay.capacity;
     if (rc != HFG_OK) return rc;
     tm[1] = wall_ms();
     const hfg_layout *l = &ctx->lay;

@@ -645,43 +645,101 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
     grid.sync(); /* orders the block totals written above (the barrier fences) */
     if (tid == 0) A.phase_clock[blockIdx.x * 10 + 3] = clock64();
 
-    /* messages entering this block: walk to the nearest block that contains a chunk start (its product is rank-1,
-     * so nothing beyond it matters) */
-    if (tid == 0) {
+    /* messages entering this block: the products of the blocks back to (and including) the nearest block that contains a
+     * chunk start -- its product is rank-1, so nothing beyond it matters -- and, for the backward message, forward to the
+     * nearest such block.  Warp 0 builds the forward message, warp 1 the backward one.  A walk of one or two blocks (the
+     * usual case: about one chunk start per block) is done by one lane; longer walks (few chunks spread over many blocks, as
+     * on a small multi-GPU shard) are an ordered warp-parallel matrix product, O(log) instead of O(blocks). */
+    if (warp == 0) {
         const int b = blockIdx.x;
+        int b0 = 0; /* first block whose product is applied */
+        for (int base = b - 1; base >= 0; base -= 32) {
+            const int q = base - lane;
+            const unsigned m = __ballot_sync(0xffffffffu, q >= 0 && __ldcg(&A.block_reset[q]) != 0);
+            if (m) {
+                b0 = base - (__ffs(m) - 1);
+                break;
+            }
+        }
         double v[4] = {0.25, 0.25, 0.25, 0.25};
-        int b0 = b; /* first block whose product is applied */
-        while (b0 > 0) {
-            b0--;
-            if (__ldcg(&A.block_reset[b0])) break;
-        }
-        for (int q = b0; q < b; q++) {
-            double T[16];
+        if (b - b0 <= 2) {
+            if (lane == 0) {
+                for (int q = b0; q < b; q++) {
+                    double T[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
-            vec_mat(v, T);
-            vec_normalize(v);
-        }
+                    for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
+                    vec_mat(v, T);
+                    vec_normalize(v);
+                }
+            }
+        } else {
+            for (int g0 = b0; g0 < b; g0 += 32) {
+                double T[16];
+                const int q = g0 + lane;
+                if (q < b) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) blk_vec[i] = v[i];
-    }
-    if (tid == 32) {
+                    for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
+                } else {
+                    mat_identity(T);
+                }
+                if (b - g0 <= 8) warp_scan_prefix<8>(T, lane); else warp_scan_prefix<32>(T, lane);
+                const int last = b - g0 <= 8 ? 7 : 31;
+#pragma unroll
+                for (int i = 0; i < 16; i++) T[i] = __shfl_sync(0xffffffffu, T[i], last);
+                vec_mat(v, T);
+                vec_normalize(v);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) blk_vec[i] = v[i];
+        }
+    } else if (warp == 1) {
         const int b = blockIdx.x, nb = gridDim.x;
+        int b1 = nb - 1; /* last block whose product is applied */
+        for (int base = b + 1; base < nb; base += 32) {
+            const int q = base + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, q < nb && __ldcg(&A.block_reset[q]) != 0);
+            if (m) {
+                b1 = base + (__ffs(m) - 1);
+                break;
+            }
+        }
         double u[4] = {1.0, 1.0, 1.0, 1.0};
-        int b1 = b; /* last block whose product is applied */
-        while (b1 < nb - 1) {
-            b1++;
-            if (__ldcg(&A.block_reset[b1])) break;
-        }
-        for (int q = b1; q > b; q--) {
-            double T[16];
+        if (b1 - b <= 2) {
+            if (lane == 0) {
+                for (int q = b1; q > b; q--) {
+                    double T[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
-            mat_vec(T, u);
-            vec_normalize(u);
-        }
+                    for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) q * 16 + i]);
+                    mat_vec(T, u);
+                    vec_normalize(u);
+                }
+            }
+        } else {
+            /* groups of 32 blocks, the farthest group first: u <- (T_g0 * ... * T_g0+31) * u */
+            const int n_groups = (b1 - b + 31) / 32;
+            for (int g = n_groups - 1; g >= 0; g--) {
+                const int g0 = b + 1 + 32 * g, cnt = min(32, b1 - g0 + 1);
+                double T[16];
+                if (lane < cnt) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) blk_vec[4 + i] = u[i];
+                    for (int i = 0; i < 16; i++) T[i] = __ldcg(&A.block_tot[(size_t) (g0 + lane) * 16 + i]);
+                } else {
+                    mat_identity(T);
+                }
+                if (cnt <= 8) warp_scan_prefix<8>(T, lane); else warp_scan_prefix<32>(T, lane);
+                const int last = cnt <= 8 ? 7 : 31;
+#pragma unroll
+                for (int i = 0; i < 16; i++) T[i] = __shfl_sync(0xffffffffu, T[i], last);
+                mat_vec(T, u);
+                vec_normalize(u);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) blk_vec[4 + i] = u[i];
+        }
     }
     __syncthreads();
 

@@ -61,10 +61,12 @@ typedef struct hfg_layout {
     int64_t *chunk_offset;   /* [n_chunks + 1] */
 } hfg_layout;
 
-/* Builds the layout (host memory, malloc'd; free with hfg_layout_free).  Returns hfg_status. */
+/* Builds the layout (host memory, malloc'd; free with hfg_layout_free) for at most `capacity` segment slots; with
+ * granule > 0 the slot count is then trimmed to the multiple of `granule` (threads per CTA) the segments need
+ * (out->capacity).  Returns hfg_status. */
 int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
                      const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
-                     int32_t capacity, hfg_layout *out, char *err, size_t errlen);
+                     int32_t capacity, int32_t granule, hfg_layout *out, char *err, size_t errlen);
 void hfg_layout_free(hfg_layout *l);
 
 /* EM_computeAdjustmentBeta (hmm.c:301-316) for window i of a chunk. */

@@ -129,7 +129,7 @@ static int64_t edges_before(int head, int tail, int L, int w) {
 
 int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
                      const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
-                     int32_t capacity, hfg_layout *out, char *err, size_t errlen) {
+                     int32_t capacity, int32_t granule, hfg_layout *out, char *err, size_t errlen) {
     memset(out, 0, sizeof(*out));
     int64_t W = 0;
     for (int32_t c = 0; c < n_chunks; c++) {
@@ -199,6 +199,9 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
     if (smax < 1) smax = 1;
     while (segments_for(runs, n_runs, smax) > capacity) smax += (smax + 7) / 8;
     const int64_t n_seg = segments_for(runs, n_runs, smax);
+    /* keep only as many slots (whole CTAs of `granule` threads) as the segments of this length need: a grid padded with
+     * idle CTAs only makes the grid-wide barriers slower */
+    if (granule > 0) capacity = (int32_t) ((n_seg + granule - 1) / granule) * granule;
 
     out->n_windows = W;
     out->n_chunks = n_chunks;
@@ -301,7 +304,7 @@ int hfg_debug_layout_check(const hfg_config *cfg, int32_t n_chunks, const hfg_ch
                            int32_t capacity, int64_t *summary) {
     hfg_layout l;
     char err[256];
-    int rc = hfg_layout_build(cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, capacity, &l, err,
+    int rc = hfg_layout_build(cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, capacity, 0, &l, err,
                               sizeof(err));
     if (rc != HFG_OK) return rc;
     int64_t next = 0, edges = 0;
