@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--total-bp", type=float, default=3e9)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 3 Gbp PER GPU (an N x 3 Gbp assembly, chunks sharded over the ranks, one model); strong = "
+                         "the 3 Gbp workload itself sharded over the ranks (BASELINE.json configs[4])")
     ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
                     help="N > 1: sum of the EM statistics over ranks inside the E-step kernel through peer memory "
                          "(fused, default) or with one NCCL all-reduce per iteration after it (nccl)")
@@ -230,13 +233,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = make_workload(args.workload, args.total_bp)
+    wl = make_workload(args.workload, args.total_bp * (max(args.gpus, 1) if args.scaling == "weak" else 1))
     cfg, params, alpha, K = model_setup(wl)
     cpu, sample = time_cpu(cfg, wl, alpha, params, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": "HMM windows/sec (EM iter + Viterbi), 3 Gbp @40x w=4000; achieved HBM GB/s",
         "value": cpu["value"], "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl.name, "windows": wl.n_windows, "chunks": wl.n_chunks, "regions": wl.n_regions,
                    "col_components": K, "window_len": wl.window_len, "sample_windows": sample.n_windows,
@@ -263,7 +266,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    wl_full = make_workload(args.workload, args.total_bp)
+    # weak scaling: the per-GPU work is the metric's 3 Gbp workload; the job is an N x 3 Gbp assembly with ONE model, its
+    # chunks sharded over the ranks and its EM statistics summed over them every iteration
+    wl_full = make_workload(args.workload, args.total_bp * (world if args.scaling == "weak" else 1))
     cfg, params0, alpha, K = model_setup(wl_full)
     cfg["device"] = local_rank
     wl = shard_chunks(wl_full, rank, world)
@@ -400,7 +405,7 @@ def run_ours(args):
         line = {
             "metric": "HMM windows/sec (EM iter + Viterbi), 3 Gbp @40x w=4000; achieved HBM GB/s",
             "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "strong",
+            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_full.name, "windows": W_total, "chunks": wl_full.n_chunks, "regions": R,
                        "col_components": K, "window_len": wl_full.window_len, "alpha": "HiFi_DC_1.2",

@@ -8,15 +8,21 @@ from . import _abi
 
 
 def shard_bounds(n_windows_per_chunk, world):
-    """Contiguous chunk ranges in list order, balanced by window count: rank r owns chunks [b[r], b[r+1])."""
+    """Contiguous chunk ranges in list order, balanced by window count: rank r owns chunks [b[r], b[r+1]).  Every rank
+    gets at least one chunk (a chunk is the unit: it cannot be split); fewer chunks than ranks is an error."""
     n = np.asarray(n_windows_per_chunk, dtype=np.int64)
+    if len(n) < world:
+        raise ValueError(f"{len(n)} chunks cannot be sharded over {world} ranks: use at most {len(n)} GPUs "
+                         "(or a smaller --chunkLen)")
     cum = np.cumsum(n)
     total = int(cum[-1])
     bounds = [0]
     for r in range(1, world):
         k = int(np.searchsorted(cum, total * r / world, side="left")) + 1
-        bounds.append(min(max(k, bounds[-1]), len(n)))
+        bounds.append(min(max(k, bounds[-1] + 1), len(n)))
     bounds.append(len(n))
+    for r in range(world - 1, 0, -1):  # leave one chunk for each of the ranks behind
+        bounds[r] = min(bounds[r], bounds[r + 1] - 1)
     return bounds
 
 

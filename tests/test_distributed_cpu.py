@@ -76,3 +76,20 @@ def test_shard_bounds_balanced():
         assert b[0] == 0 and b[-1] == wl.n_chunks and all(x < y for x, y in zip(b, b[1:]))
         sizes = [int(wl.chunks["n_windows"][b[r]:b[r + 1]].sum()) for r in range(world)]
         assert sum(sizes) == wl.n_windows and max(sizes) <= 1.15 * wl.n_windows / world
+
+
+def test_shard_bounds_never_empty():
+    """Ragged chunk sizes (one chunk holding most windows): every rank still owns >= 1 chunk; fewer chunks than ranks is
+    refused with a message instead of producing an empty shard."""
+    import pytest
+    from flagger_b200 import dist as hdist, synth
+    wl = synth.small_mixed(n_regions=3, seed=91)
+    for world in range(1, wl.n_chunks + 1):
+        b = hdist.shard_bounds(wl.chunks["n_windows"], world)
+        assert b[0] == 0 and b[-1] == wl.n_chunks and all(x < y for x, y in zip(b, b[1:])), (world, b)
+        assert sum(hdist.shard_chunks(wl, r, world).n_windows for r in range(world)) == wl.n_windows
+    with pytest.raises(ValueError):
+        hdist.shard_bounds(wl.chunks["n_windows"], wl.n_chunks + 1)
+    assert hdist.shard_bounds([5, 1, 1, 1], 4) == [0, 1, 2, 3, 4]
+    b = hdist.shard_bounds([1, 1, 1, 50], 3)
+    assert b[0] == 0 and b[-1] == 4 and all(x < y for x, y in zip(b, b[1:]))
