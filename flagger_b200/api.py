@@ -59,8 +59,9 @@ EXPORTED_SYMBOLS = (
 
 
 def layout_check(cfg, wl, capacity):
-    """Host-only self-check of the segment layout (returns (ok, summary[n_seg, smax, n_edge, windows]))."""
-    summary = np.zeros(4, np.int64)
+    """Host-only self-check of the segment layout and of the observation keys (returns (ok, summary[n_seg, smax, n_edge,
+    windows, keys, tiles]))."""
+    summary = np.zeros(6, np.int64)
     chunks = np.ascontiguousarray(wl.chunks)
     rc = lib().hfg_debug_layout_check(ptr(np.ascontiguousarray(cfg)), C.c_int32(len(chunks)), ptr(chunks),
                                       ptr(np.ascontiguousarray(wl.cov, np.uint16)),

@@ -32,9 +32,10 @@ struct hfg_ctx {
     cudaEvent_t ev2, ev3; /* around the whole device side of the last blocking call */
     int ev_valid, span_valid;
     /* device */
-    uint32_t *d_obsT;
-    int32_t *d_seg_start, *d_seg_len, *d_seg_edge_begin, *d_block_reset, *d_err;
-    double *d_edge_beta, *d_scrE, *d_scrF, *d_scrC, *d_block_tot, *d_partials, *d_out, *d_seg_loglik, *d_post;
+    uint32_t *d_wkeyT, *d_kdesc;
+    int32_t *d_seg_start, *d_seg_len, *d_block_reset, *d_err;
+    int32_t *d_klist, *d_tile_key, *d_tile_begin, *d_tile_cnt, *d_region_tile_begin;
+    double *d_kbeta, *d_tabM, *d_scrF, *d_scrB, *d_block_tot, *d_partials, *d_out, *d_seg_loglik, *d_post;
     hfg_region_params *d_params[STAGE_SLOTS];
     int8_t *d_labels;
     long long *d_phase_clock;
@@ -91,7 +92,7 @@ static int max_tasks(const hfg_config *cfg) {
 
 static size_t smem_bytes_for(int R, int G, int NT, int threads) {
     size_t doubles = (size_t) R * RT_STRIDE2(G, NT) + 3 * (threads / 32) * 16 + 8 + (size_t) hfg_acc_rows(G) * (threads + 1);
-    return doubles * sizeof(double) + threads * sizeof(int);
+    return doubles * sizeof(double);
 }
 
 static int total_gauss_comps(const hfg_config *cfg) {
@@ -270,8 +271,10 @@ static void free_device(hfg_ctx *ctx) {
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_labels) cudaFreeHost(ctx->h_labels);
     ctx->d_arena = NULL;
-    ctx->d_obsT = NULL; ctx->d_seg_start = ctx->d_seg_len = ctx->d_seg_edge_begin = ctx->d_block_reset = ctx->d_err = NULL;
-    ctx->d_edge_beta = ctx->d_scrE = ctx->d_scrF = ctx->d_scrC = ctx->d_block_tot = ctx->d_partials = NULL;
+    ctx->d_wkeyT = ctx->d_kdesc = NULL;
+    ctx->d_seg_start = ctx->d_seg_len = ctx->d_block_reset = ctx->d_err = NULL;
+    ctx->d_klist = ctx->d_tile_key = ctx->d_tile_begin = ctx->d_tile_cnt = ctx->d_region_tile_begin = NULL;
+    ctx->d_kbeta = ctx->d_tabM = ctx->d_scrF = ctx->d_scrB = ctx->d_block_tot = ctx->d_partials = NULL;
     ctx->d_out = ctx->d_seg_loglik = ctx->d_post = NULL;
     ctx->d_labels = NULL;
     ctx->d_phase_clock = NULL;
@@ -350,12 +353,16 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     {
         size_t off = 0;
 #define CARVE(bytes) (off = (off + 255) & ~(size_t) 255, off += (bytes), off - (bytes))
-        const size_t o_obs = CARVE(slots * sizeof(uint32_t));
+        const size_t P = (size_t) l->n_keys, NT = (size_t) (l->n_tiles > 0 ? l->n_tiles : 1);
+        const size_t o_wk = CARVE(slots * sizeof(uint32_t));
         const size_t o_ss = CARVE(cap * sizeof(int32_t)), o_sl = CARVE(cap * sizeof(int32_t));
-        const size_t o_se = CARVE(((size_t) cap + 1) * sizeof(int32_t));
-        const size_t o_eb = CARVE((size_t) (l->n_edge > 0 ? l->n_edge : 1) * 3 * sizeof(double));
-        const size_t o_E = CARVE(slots * HFG_MAX_CLASSES * sizeof(double));
-        const size_t o_F = CARVE(slots * 4 * sizeof(double)), o_C = CARVE(slots * sizeof(double));
+        const size_t o_kd = CARVE(P * sizeof(uint32_t)), o_kb = CARVE(P * 3 * sizeof(double));
+        const size_t o_kl = CARVE((size_t) (l->n_list > 0 ? l->n_list : 1) * sizeof(int32_t));
+        const size_t o_tk = CARVE(NT * sizeof(int32_t)), o_tb = CARVE(NT * sizeof(int32_t)), o_tc = CARVE(NT * sizeof(int32_t));
+        const size_t o_rt = CARVE((HFG_MAX_REGIONS + 1) * sizeof(int32_t));
+        const size_t o_M = CARVE(P * 16 * sizeof(double));
+        const size_t o_F = CARVE((size_t) l->n_windows * 4 * sizeof(double));
+        const size_t o_B = CARVE((size_t) l->n_windows * 4 * sizeof(double));
         const size_t o_bt = CARVE((size_t) ctx->grid * 16 * sizeof(double));
         const size_t o_br = CARVE((size_t) ctx->grid * sizeof(int32_t));
         const size_t o_pa = CARVE((size_t) ctx->grid * R * hfg_nstat(G) * sizeof(double));
@@ -371,16 +378,23 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
             return fail(ctx, HFG_ERR_NOMEM, "hfg_set_chunks: cannot allocate %zu bytes of device memory", off);
         }
         tm[2] = wall_ms();
-        if (timing) fprintf(stderr, "[hfg] arena %.1f MB\n", off / 1e6);
+        if (timing)
+            fprintf(stderr, "[hfg] arena %.1f MB; %lld windows, %d keys, %d tiles\n", off / 1e6, (long long) l->n_windows,
+                    l->n_keys, l->n_tiles);
         char *base = (char *) ctx->d_arena;
-        ctx->d_obsT = (uint32_t *) (base + o_obs);
+        ctx->d_wkeyT = (uint32_t *) (base + o_wk);
         ctx->d_seg_start = (int32_t *) (base + o_ss);
         ctx->d_seg_len = (int32_t *) (base + o_sl);
-        ctx->d_seg_edge_begin = (int32_t *) (base + o_se);
-        ctx->d_edge_beta = (double *) (base + o_eb);
-        ctx->d_scrE = (double *) (base + o_E);
+        ctx->d_kdesc = (uint32_t *) (base + o_kd);
+        ctx->d_kbeta = (double *) (base + o_kb);
+        ctx->d_klist = (int32_t *) (base + o_kl);
+        ctx->d_tile_key = (int32_t *) (base + o_tk);
+        ctx->d_tile_begin = (int32_t *) (base + o_tb);
+        ctx->d_tile_cnt = (int32_t *) (base + o_tc);
+        ctx->d_region_tile_begin = (int32_t *) (base + o_rt);
+        ctx->d_tabM = (double *) (base + o_M);
         ctx->d_scrF = (double *) (base + o_F);
-        ctx->d_scrC = (double *) (base + o_C);
+        ctx->d_scrB = (double *) (base + o_B);
         ctx->d_block_tot = (double *) (base + o_bt);
         ctx->d_block_reset = (int32_t *) (base + o_br);
         ctx->d_partials = (double *) (base + o_pa);
@@ -393,22 +407,31 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     CU(cudaMallocHost((void **) &ctx->h_out, out_doubles * sizeof(double)));
     CU(cudaMallocHost((void **) &ctx->h_labels, (size_t) l->n_windows));
     tm[3] = wall_ms();
-    CU(cudaMemcpyAsync(ctx->d_obsT, l->obsT, slots * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_wkeyT, l->wkeyT, slots * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_start, l->seg_start, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_len, l->seg_len, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_seg_edge_begin, l->seg_edge_begin, ((size_t) cap + 1) * sizeof(int32_t),
+    CU(cudaMemcpyAsync(ctx->d_kdesc, l->kdesc, (size_t) l->n_keys * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_kbeta, l->kbeta, (size_t) l->n_keys * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (l->n_list > 0)
+        CU(cudaMemcpyAsync(ctx->d_klist, l->klist, (size_t) l->n_list * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (l->n_tiles > 0) {
+        const size_t tb = (size_t) l->n_tiles * sizeof(int32_t);
+        CU(cudaMemcpyAsync(ctx->d_tile_key, l->tile_key, tb, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_tile_begin, l->tile_begin, tb, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_tile_cnt, l->tile_cnt, tb, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->d_region_tile_begin, l->region_tile_begin, (HFG_MAX_REGIONS + 1) * sizeof(int32_t),
                        cudaMemcpyHostToDevice, ctx->stream));
-    if (l->n_edge > 0)
-        CU(cudaMemcpyAsync(ctx->d_edge_beta, l->edge_beta, (size_t) l->n_edge * 3 * sizeof(double), cudaMemcpyHostToDevice,
-                           ctx->stream));
     CU(cudaMemsetAsync(ctx->d_labels, 0xff, (size_t) l->n_windows, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     tm[4] = wall_ms();
     if (timing)
         fprintf(stderr, "[hfg] set_chunks: layout %.2f ms, cudaMalloc %.2f ms, cudaMallocHost %.2f ms, copies %.2f ms\n",
                 tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3]);
-    free(ctx->lay.obsT); /* the packed words now live on the device */
-    ctx->lay.obsT = NULL;
+    /* the per-window tables now live on the device */
+    free(ctx->lay.obsT); ctx->lay.obsT = NULL;
+    free(ctx->lay.wkeyT); ctx->lay.wkeyT = NULL;
+    free(ctx->lay.klist); ctx->lay.klist = NULL;
     ctx->have_chunks = 1;
     ctx->have_last = 0;
     return HFG_OK;
@@ -425,11 +448,17 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     hfg_classes_build(cfg, alpha, &cl);
     EstepArgs &a = *out_args;
     memset(&a, 0, sizeof(a));
-    a.obsT = ctx->d_obsT;
+    a.wkeyT = ctx->d_wkeyT;
     a.seg_start = ctx->d_seg_start;
     a.seg_len = ctx->d_seg_len;
-    a.seg_edge_begin = ctx->d_seg_edge_begin;
-    a.edge_beta = ctx->d_edge_beta;
+    a.n_keys = l->n_keys;
+    a.kdesc = ctx->d_kdesc;
+    a.kbeta = ctx->d_kbeta;
+    a.klist = ctx->d_klist;
+    a.tile_key = ctx->d_tile_key;
+    a.tile_begin = ctx->d_tile_begin;
+    a.tile_cnt = ctx->d_tile_cnt;
+    a.region_tile_begin = ctx->d_region_tile_begin;
     a.capacity = l->capacity;
     a.smax = l->smax;
     a.n_regions = R;
@@ -485,9 +514,9 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
         a.task_comp[0] = 0;
     }
     a.params = ctx->d_params[slot];
-    a.scrE = ctx->d_scrE;
+    a.tabM = ctx->d_tabM;
     a.scrF = ctx->d_scrF;
-    a.scrC = ctx->d_scrC;
+    a.scrB = ctx->d_scrB;
     a.block_tot = ctx->d_block_tot;
     a.block_reset = ctx->d_block_reset;
     a.partials = ctx->d_partials;

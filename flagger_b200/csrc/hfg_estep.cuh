@@ -7,27 +7,35 @@
  * one EM_runOneIterationForList call (hmm.c:739-780), in ONE persistent cooperative launch.
  *
  * Shape of the computation:
- *   The reference walks every chunk serially (5-10k dependent 4x4 steps).  Here the whole genome is one sequence
- *   of windows cut into segments (<= smax windows, never straddling a chunk or a region change); global thread j
- *   owns segment j.  A chunk start is just a window whose transfer matrix is rank-1 (all rows = the start column),
- *   so chunks need no special casing in the scan.
- *     phase A   per thread: evaluate the emission row of each window ONCE (stored segment-transposed for the
- *               later sweeps) and multiply the window transfer matrices M_i = T_i (.) E_i into the segment
- *               product P_j (power-of-two rescaled, so the product is exact up to the matmul roundings).
+ *   The reference walks every chunk serially (5-10k dependent 4x4 steps) and evaluates 16 emission pdfs per window
+ *   four times per iteration.  Here
+ *   (1) observations are small integers, so the window transfer matrix M_i = T_i (.) E_i takes few distinct values
+ *       (~10^4 "keys" (x, px, region, mask, beta) for ~10^6 windows, numbered once on the host): emissions and M are
+ *       evaluated once per KEY per E-step into a table that stays in L2/L1, windows gather their matrix by key id;
+ *   (2) the whole genome is one sequence of windows cut into segments (<= smax windows, never straddling a chunk or
+ *       a region change); global thread j owns segment j.  A chunk start is just a window whose transfer matrix is
+ *       rank-1 (all rows = the start column), so chunks need no special casing in the scan;
+ *   (3) the pair statistics are linear in xi_i[pre][s] = f^_{i-1}[pre] M_i[pre][s] b_i[s], and everything else in
+ *       them depends only on the key: sum_i xi_i = M_key (.) sum_i f^_{i-1} (x) b_i.  The sweeps only store f^ and
+ *       the normalised b; the outer products are summed per key (tiles of <= 16 windows), and the estimator updates of
+ *       the reference run once per tile instead of once per window.
+ *     phase T   per key: emission classes, transfer matrix -> table (grid barrier).
+ *     phase A   per thread: product of the window matrices of the segment (power-of-two rescaled: exact scaling).
  *     phase B   matrix scans: warp shuffles -> warps of a block through shared memory -> blocks through global
- *               memory and ONE grid-wide barrier.  Yields for every segment the forward message entering it and
- *               the backward message entering it from the right (directions only; see below).
- *     phase C   per thread: the reference's own scaled forward recurrence inside the segment (f^, c_i and
- *               sum log c_i), then the backward recurrence fused with the posterior-argmax decode and the pair
- *               statistics.  The absolute scale of the backward message is recovered from the invariant
- *               sum_s f^_i[s] b^_i[s] c_i = terminationProb, which holds for every window of the reference's scaling
- *               (b^_{L-1} = term / c_{L-1}, hmm.c:452-467).
+ *               memory and a grid barrier.  Yields for every segment the forward message entering it and the direction
+ *               of the backward message entering it.
+ *     phase C1  the reference's scaled forward recurrence inside the segment (f^, c_i and sum log c_i).
+ *     phase C2  backward recurrence fused with the posterior-argmax decode.  b is carried as a direction and
+ *               normalised per window so that sum_{pre,s} xi_i = 1, the invariant of the reference's scaling
+ *               (sum_s f^_i[s] b^_i[s] c_i = terminationProb with counts divided by terminationProb, hmm.c:452-467,
+ *               613-614) (grid barrier).
+ *     phase S   per tile: outer-product sum, then the reference's estimator updates with the tile's pooled counts.
  *     phase D   deterministic reduction of the statistics: per-thread -> per-block (fixed order) -> grid (fixed
- *               order, block 0 after a second grid barrier).  No floating-point atomics anywhere.
+ *               order, block 0 after the last grid barrier).  No floating-point atomics anywhere.
  *
- * Inside a segment the operation ORDER of the reference is kept ((f*t)*e accumulated over preState, etc.); the
- * results differ from the reference only through the rounding of the entering messages (~1e-16 relative) and
- * libdevice exp/log (<= 1-2 ulp from glibc).
+ * Results differ from the reference only by rounding (~1e-16 relative per operation): t*e is rounded once per key
+ * instead of (f*t)*e per window, messages enter the segments from a scan, libdevice-free exp (<= 1-2 ulp from glibc),
+ * statistics summed in tile/tree order.
  */
 #pragma once
 
@@ -69,11 +77,17 @@ namespace cg = cooperative_groups;
 
 struct EstepArgs {
     /* run-constant layout */
-    const uint32_t *obsT;
-    const int32_t *seg_start, *seg_len, *seg_edge_begin;
-    const double *edge_beta;
+    const uint32_t *wkeyT;     /* [smax][capacity] key word of every window */
+    const int32_t *seg_start, *seg_len;
     int32_t capacity, smax, n_regions;
     double beta0;
+    /* observation keys and the per-key window lists of the statistics */
+    int32_t n_keys;
+    const uint32_t *kdesc;     /* [n_keys] packed observation word */
+    const double *kbeta;       /* [n_keys][3] beta, beta0/beta, sqrt(beta0/beta) */
+    const int32_t *klist;      /* window indices grouped by key */
+    const int32_t *tile_key, *tile_begin, *tile_cnt;
+    const int32_t *region_tile_begin; /* [HFG_MAX_REGIONS + 1] */
     /* model structure */
     int32_t n_classes;              /* D */
     int32_t cls[HFG_NS][HFG_NS];    /* [pre][s] -> slot */
@@ -93,9 +107,9 @@ struct EstepArgs {
     int32_t texp_slot;                           /* emission slot of the truncated-exponential state, or -1 */
     /* per-call inputs / scratch / outputs (device) */
     const hfg_region_params *params;
-    double *scrE;  /* [smax][D][capacity]  emission rows */
-    double *scrF;  /* [smax][4][capacity]  scaled forward */
-    double *scrC;  /* [smax][capacity]     scales */
+    double *tabM;  /* [n_keys][16]  transfer matrix of every key (row-major [pre][s]) */
+    double *scrF;  /* [W][4]        scaled forward f^ */
+    double *scrB;  /* [W][4]        backward message, normalised so that sum f^_{i-1} (x) b_i (.) M_i = 1 */
     double *block_tot;   /* [grid][16] */
     int32_t *block_reset; /* [grid] */
     double *partials;    /* [grid][R][NSTAT] */
@@ -407,6 +421,37 @@ __device__ __forceinline__ double trans_prob(const double *rt, const Win &w, int
 
 /* ---------------------------------------------------------------------------------------------------------- */
 
+namespace hfgk {
+
+/* one 4x4 transfer matrix of the key table: four 256-bit loads (LDG.E.256).  The table is written in phase T and only
+ * read after the grid barrier that follows it, so the ordinary (L1-cached) path is safe; hot keys stay in L1. */
+__device__ __forceinline__ void load_mat(const double *p, double (&M)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+            : "=d"(M[4 * q]), "=d"(M[4 * q + 1]), "=d"(M[4 * q + 2]), "=d"(M[4 * q + 3])
+            : "l"(p + 4 * q));
+}
+
+__device__ __forceinline__ void store_vec4(double *p, const double (&v)[4]) {
+    double2 *q = reinterpret_cast<double2 *>(p);
+    q[0] = make_double2(v[0], v[1]);
+    q[1] = make_double2(v[2], v[3]);
+}
+__device__ __forceinline__ void load_vec4(const double *p, double (&v)[4]) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = q[0], b = q[1];
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+/* L2 path (written by other SMs before the preceding grid barrier, read once) */
+__device__ __forceinline__ void load_vec4_cg(const double *p, double (&v)[4]) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = __ldcg(q), b = __ldcg(q + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+}  // namespace hfgk
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A) {
     constexpr int WARPS = THREADS / 32;
@@ -420,6 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
     const int rt_stride = RT_STRIDE2(G, A.n_tasks);
     const int NSTAT = hfg_nstat(G);
     const int LD = THREADS + 1;
+    const int n_threads = gridDim.x * THREADS;
 
     /* shared memory carve-up */
     double *rtab = smem;                                   /* [R][rt_stride] */
@@ -427,9 +473,8 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
     double *warp_pre = warp_tot + WARPS * 16;          /* [WARPS][16] exclusive prefix over warps */
     double *warp_suf = warp_pre + WARPS * 16;          /* [WARPS][16] exclusive suffix over warps */
     double *blk_vec = warp_suf + WARPS * 16;           /* [8] entering forward / backward message of the block */
-    double *acc = blk_vec + 8;                             /* [max(NSTAT,32)][LD]: emission staging (phase A), scan stash
-                                                              (phase B), per-thread statistics (phases C, D) */
-    int *treg = (int *) (acc + (size_t) hfg_acc_rows(G) * LD); /* [THREADS] region of each thread's segment */
+    double *acc = blk_vec + 8;                             /* [max(NSTAT,32)][LD]: emission staging (phase T), scan stash
+                                                              (phase B), per-thread statistics (phases S, D) */
     __shared__ int s_reset;
 
     /* ---- prologue: derived per-region tables (redundantly per block; O(R*K) work) ---- */
@@ -496,92 +541,106 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
     __syncthreads();
 
     if (tid == 0) A.phase_clock[blockIdx.x * 10 + 0] = clock64();
+    int nan_flag = 0, uf_flag = 0;
+
+    /* =========================== phase T: emission classes and transfer matrix of every key ================== */
+    for (int p = j; p < A.n_keys; p += n_threads) {
+        Win w = decode_word(A.kdesc[p], A.beta0);
+        if (w.edge) {
+            w.beta = A.kbeta[3 * (size_t) p];
+            w.rb = A.kbeta[3 * (size_t) p + 1];
+            w.sq = A.kbeta[3 * (size_t) p + 2];
+        }
+        const double *rt = rtab + (size_t) w.region * rt_stride;
+        double *es = acc + tid; /* es[d * LD]: this thread's emission row of the current key */
+        /* every distinct (state, alpha) class once (the reference evaluates all 16 (pre,state) pairs of every WINDOW,
+         * three times per iteration, plus once more inside the estimator update) */
+        if (w.start) {
+            /* chunk starts (alpha = 0, preX = 0 for every state): generic path */
+            for (int d = 0; d < D; d++) {
+                if (!((A.slots_start >> d) & 1u)) continue;
+                es[d * LD] = emission(A, rt, A.class_state[d], A.class_alpha[d], w, &nan_flag);
+            }
+        } else {
+            /* per-component constants tabulated for the interior beta; four evaluations in flight */
+            for (int d = 0; d < D; d++) es[d * LD] = 0.0;
+            if (A.texp_slot >= 0) es[A.texp_slot * LD] = trunc_exp_prob(rt, w);
+            const double *tk = rt + RT_TASK(G);
+            const int NT = A.n_tasks;
+            for (int t0 = 0; t0 < NT; t0 += 4) {
+                double pv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int t = min(t0 + u, NT - 1);
+                    const double4 c4 = *reinterpret_cast<const double4 *>(tk + 4 * t);
+                    double mean = c4.x + c4.y * w.px; /* (1-a)*mu + a*px */
+                    mean *= w.beta;
+                    const double dd = w.x - mean;
+                    double pp = (c4.w * w.sq) * exp_nonpos((-0.5 * (dd * dd)) * (c4.z * w.rb));
+                    if (pp != pp) nan_flag = 1;
+                    pv[u] = pp < 1e-40 ? 1e-40 : pp;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (t0 + u < NT) es[A.task_class[t0 + u] * LD] += pv[u]; /* component order, as Gaussian_getProb */
+            }
+        }
+        double M[16];
+        if (w.start) {
+            /* EM_fillFirstColumnForward (hmm.c:333-364): preX = 0, alpha = 0, start probabilities, no mask:
+             * a rank-1 transfer matrix, every row = the unnormalised first column */
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const double f0 = es[s * LD] * rt[RT_START + s];
+#pragma unroll
+                for (int pre = 0; pre < 4; pre++) M[pre * 4 + s] = f0;
+            }
+        } else {
+#pragma unroll
+            for (int pre = 0; pre < 4; pre++)
+#pragma unroll
+                for (int s = 0; s < 4; s++) M[pre * 4 + s] = trans_prob(rt, w, pre, s) * es[A.cls[pre][s] * LD];
+        }
+        double2 *dst = reinterpret_cast<double2 *>(A.tabM + (size_t) p * 16);
+#pragma unroll
+        for (int q = 0; q < 8; q++) dst[q] = make_double2(M[2 * q], M[2 * q + 1]);
+    }
+    grid.sync(); /* the key table is complete */
+    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 1] = clock64();
+
     const int len = A.seg_len[j];
     const int seg_first = A.seg_start[j];
-    int nan_flag = 0, uf_flag = 0;
-    int my_region = 0;
+    const uint32_t *wk = A.wkeyT + j; /* wk[k * cap]: key word of the k-th window of this segment */
 
-    /* =========================== phase A: emission rows + segment transfer product =========================== */
+    /* =========================== phase A: segment transfer product ============================================ */
     {
         double P[16];
         mat_identity(P);
-        int eidx = A.seg_edge_begin[j];
         bool has_start = false;
-        double *es = acc + tid; /* es[d * LD]: this thread's emission row of the current window */
-        for (int k = 0; k < len; k++) {
-            const uint32_t word = A.obsT[(size_t) k * cap + j];
-            Win w = decode_word(word, A.beta0);
-            if (w.edge) {
-                w.beta = A.edge_beta[3 * eidx];
-                w.rb = A.edge_beta[3 * eidx + 1];
-                w.sq = A.edge_beta[3 * eidx + 2];
-                eidx++;
-            }
-            my_region = w.region;
-            const double *rt = rtab + (size_t) w.region * rt_stride;
-            double *erow = A.scrE + (size_t) k * D * cap + j;
-            /* evaluate every distinct (state, alpha) class once (the reference evaluates all 16 (pre,state) pairs,
-             * three times per iteration) */
-            if (w.start) {
-                /* chunk starts (alpha = 0, preX = 0 for every state): generic path */
-                const uint32_t slots = w.start ? A.slots_start : A.slots_other;
-                for (int d = 0; d < D; d++) {
-                    if (!((slots >> d) & 1u)) continue;
-                    const double e = emission(A, rt, A.class_state[d], A.class_alpha[d], w, &nan_flag);
-                    erow[(size_t) d * cap] = e;
-                    es[d * LD] = e;
+        {
+            /* the key word is fetched two windows ahead, the matrix one window ahead of its use */
+            uint32_t w0 = len > 0 ? __ldg(wk) : 0u;
+            uint32_t w1 = len > 1 ? __ldg(wk + cap) : 0u;
+            double Mc[16];
+            if (len > 0) load_mat(A.tabM + (size_t) HFG_KEY_ID(w0) * 16, Mc);
+#pragma unroll 2
+            for (int k = 0; k < len; k++) {
+                const uint32_t w2 = k + 2 < len ? __ldg(wk + (size_t) (k + 2) * cap) : 0u;
+                double Mn[16];
+                if (k + 1 < len) load_mat(A.tabM + (size_t) HFG_KEY_ID(w1) * 16, Mn);
+                if (w0 & HFG_KEY_CHUNK_START) has_start = true;
+                mat_mul_inplace_left(P, Mc);
+                if ((k & 3) == 3) mat_rescale(P); /* a window shrinks the product by < 1e-50: every 4th step is ample */
+                if (k + 1 < len) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) Mc[i] = Mn[i];
                 }
-            } else {
-                /* per-component constants tabulated for the interior beta; four evaluations in flight */
-                for (int d = 0; d < D; d++) es[d * LD] = 0.0;
-                if (A.texp_slot >= 0) es[A.texp_slot * LD] = trunc_exp_prob(rt, w);
-                const double *tk = rt + RT_TASK(G);
-                const int NT = A.n_tasks;
-                for (int t0 = 0; t0 < NT; t0 += 4) {
-                    double pv[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int t = min(t0 + u, NT - 1);
-                        const double4 c4 = *reinterpret_cast<const double4 *>(tk + 4 * t);
-                        double mean = c4.x + c4.y * w.px; /* (1-a)*mu + a*px */
-                        mean *= w.beta;
-                        const double dd = w.x - mean;
-                        double pp = (c4.w * w.sq) * exp_nonpos((-0.5 * (dd * dd)) * (c4.z * w.rb));
-                        if (pp != pp) nan_flag = 1;
-                        pv[u] = pp < 1e-40 ? 1e-40 : pp;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (t0 + u < NT) es[A.task_class[t0 + u] * LD] += pv[u]; /* component order, as Gaussian_getProb */
-                }
-                for (int d = 0; d < D; d++)
-                    if ((A.slots_other >> d) & 1u) erow[(size_t) d * cap] = es[d * LD];
+                w0 = w1;
+                w1 = w2;
             }
-            double M[16];
-            if (w.start) {
-                /* EM_fillFirstColumnForward (hmm.c:333-364): preX = 0, alpha = 0, start probabilities, no mask:
-                 * a rank-1 transfer matrix, every row = the unnormalised first column */
-                has_start = true;
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    const double f0 = es[s * LD] * rt[RT_START + s];
-#pragma unroll
-                    for (int pre = 0; pre < 4; pre++) M[pre * 4 + s] = f0;
-                }
-            } else {
-#pragma unroll
-                for (int pre = 0; pre < 4; pre++)
-#pragma unroll
-                    for (int s = 0; s < 4; s++) M[pre * 4 + s] = trans_prob(rt, w, pre, s) * es[A.cls[pre][s] * LD];
-            }
-            mat_mul_inplace_left(P, M);
-            if ((k & 3) == 3) mat_rescale(P); /* a window shrinks the product by < 1e-50: every 4th step is ample */
         }
         mat_rescale(P);
         if (has_start) s_reset = 1; /* benign race: every writer stores 1 */
-        treg[tid] = my_region;
-        __syncthreads(); /* the emission staging area is reused as the scan stash below */
-        if (tid == 0) A.phase_clock[blockIdx.x * 10 + 1] = clock64();
 
         /* ======================= phase B: scans ============================================================== */
         double S[16], Q[16];
@@ -767,47 +826,48 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
         mat_vec(T, u_in);
         vec_normalize(u_in);
     }
-    __syncthreads(); /* the stash becomes the statistics area */
 
     /* =========================== phase C1: forward inside the segment ======================================== */
     double loglik = 0.0;
+    double f[4] = {v_in[0], v_in[1], v_in[2], v_in[3]};
     {
         /* sum_i log(c_i) = log(prod c_i): the product is carried as mantissa x 2^exponent (exact rescaling), one log
          * per segment instead of one per window */
         double cprod = 1.0;
         int cexp = 0;
-        double f[4] = {v_in[0], v_in[1], v_in[2], v_in[3]};
+        uint32_t w0 = len > 0 ? __ldg(wk) : 0u;
+        uint32_t w1 = len > 1 ? __ldg(wk + cap) : 0u;
+        double Mc[16];
+        if (len > 0) load_mat(A.tabM + (size_t) HFG_KEY_ID(w0) * 16, Mc);
+#pragma unroll 2
         for (int k = 0; k < len; k++) {
-            const uint32_t word = A.obsT[(size_t) k * cap + j];
-            const Win w = decode_word(word, A.beta0);
-            const double *rt = rtab + (size_t) w.region * rt_stride;
-            const double *erow = A.scrE + (size_t) k * D * cap + j;
+            const uint32_t w2 = k + 2 < len ? __ldg(wk + (size_t) (k + 2) * cap) : 0u;
+            double Mn[16];
+            if (k + 1 < len) load_mat(A.tabM + (size_t) HFG_KEY_ID(w1) * 16, Mn);
+            const bool start = (w0 & HFG_KEY_CHUNK_START) != 0;
             double fn[4];
-            if (w.start) {
+            if (start) {
+                /* EM_fillFirstColumnForward: f[0][s] = e * start probability = any row of the rank-1 matrix */
 #pragma unroll
-                for (int s = 0; s < 4; s++) fn[s] = erow[(size_t) s * cap] * rt[RT_START + s];
+                for (int s = 0; s < 4; s++) fn[s] = Mc[s];
             } else {
-                /* f[i][s] = sum_pre (f[i-1][pre] * tProb) * eProb, preState ascending (hmm.c:386-408) */
+                /* f[i][s] = sum_pre f[i-1][pre] * (tProb * eProb), preState ascending (hmm.c:386-408) */
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
                     double a = 0.0;
 #pragma unroll
-                    for (int pre = 0; pre < 4; pre++)
-                        a += (f[pre] * trans_prob(rt, w, pre, s)) * erow[(size_t) A.cls[pre][s] * cap];
+                    for (int pre = 0; pre < 4; pre++) a += f[pre] * Mc[pre * 4 + s];
                     fn[s] = a;
                 }
             }
             const double c = ((fn[0] + fn[1]) + fn[2]) + fn[3];
-            if (!w.start && c < 1e-50) uf_flag = 1; /* "scale is very low" (hmm.c:412-415) */
+            if (!start && c < 1e-50) uf_flag = 1; /* "scale is very low" (hmm.c:412-415) */
             /* f^ = f / c as one correctly rounded reciprocal and four products (<= 1 ulp from the four divisions of
-             * hmm.c:417-419; the divisions were a third of this loop's instructions) */
+             * hmm.c:417-419) */
             const double rc = __drcp_rn(c);
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                f[s] = fn[s] * rc;
-                A.scrF[((size_t) k * 4 + s) * cap + j] = f[s];
-            }
-            A.scrC[(size_t) k * cap + j] = c;
+            for (int s = 0; s < 4; s++) f[s] = fn[s] * rc;
+            store_vec4(A.scrF + (size_t) (seg_first + k) * 4, f);
             cprod *= c;
             {
                 const int hi = __double2hiint(cprod);
@@ -815,57 +875,48 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                 cexp += e;
                 cprod = __hiloint2double(hi - (e << 20), __double2loint(cprod));
             }
+            if (k + 1 < len) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) Mc[i] = Mn[i];
+            }
+            w0 = w1;
+            w1 = w2;
         }
         loglik = log(cprod) + (double) cexp * 0.6931471805599453;
         A.seg_loglik[j] = loglik;
     }
     if (tid == 0) A.phase_clock[blockIdx.x * 10 + 4] = clock64(); /* thread 0's own C1 end (no barrier here) */
 
-    /* per-thread statistics live in column tid of acc: rows 0..15 transition counts, 16..17 truncated exponential,
-     * 18+3g.. (meanNum, den, varNum) of Gaussian component g, last row the log-likelihood */
-    for (int q = 0; q < NSTAT; q++) acc[(size_t) q * LD + tid] = 0.0;
-    double *col = acc + tid;
-
-    /* =========================== phase C2: backward + decode + statistics ===================================== */
+    /* =========================== phase C2: backward + decode ================================================= */
     if (!A.forward_only && len > 0) {
-        int eidx = A.seg_edge_begin[j + 1] - 1;
-        double bh[4], fh[4], c;
-        {
-            const int k = len - 1;
+        /* f[] holds f^ of the segment's last window.  b is a direction: the statistics need it only up to the per-window
+         * normalisation  sum_{pre,s} f^_{i-1}[pre] M_i[pre][s] b_i[s] = 1, the decode only up to a positive factor. */
+        double bh[4], fh[4] = {f[0], f[1], f[2], f[3]};
+        uint32_t w0 = __ldg(wk + (size_t) (len - 1) * cap);
+        uint32_t w1 = len > 1 ? __ldg(wk + (size_t) (len - 2) * cap) : 0u;
+        if (w0 & HFG_KEY_CHUNK_END) {
+            /* EM_fillLastColumnBackward (hmm.c:452-467): b = terminationProb / scale */
+            const double *rt = rtab + (size_t) HFG_OBS_REGION(A.kdesc[HFG_KEY_ID(w0)]) * rt_stride;
 #pragma unroll
-            for (int s = 0; s < 4; s++) fh[s] = A.scrF[((size_t) k * 4 + s) * cap + j];
-            c = A.scrC[(size_t) k * cap + j];
-            const uint32_t word = A.obsT[(size_t) k * cap + j];
-            if (word & HFG_OBS_CHUNK_END) {
-                /* EM_fillLastColumnBackward (hmm.c:452-467): b = terminationProb / scale */
-                const double *rt = rtab + (size_t) HFG_OBS_REGION(word) * rt_stride;
+            for (int s = 0; s < 4; s++) bh[s] = rt[RT_TERM + s] * HFG_INV_TERM;
+        } else {
 #pragma unroll
-                for (int s = 0; s < 4; s++) bh[s] = rt[RT_TERM + s] / c;
-            } else {
-                /* scale of the entering message from  sum_s f^[s] b^[s] c = terminationProb */
-                const double dot = ((fh[0] * u_in[0] + fh[1] * u_in[1]) + fh[2] * u_in[2]) + fh[3] * u_in[3];
-                const double sc = HFG_TERM_PROB / (c * dot);
-#pragma unroll
-                for (int s = 0; s < 4; s++) bh[s] = u_in[s] * sc;
-            }
+            for (int s = 0; s < 4; s++) bh[s] = u_in[s];
         }
+        double Mc[16];
+        load_mat(A.tabM + (size_t) HFG_KEY_ID(w0) * 16, Mc);
+#pragma unroll 2
         for (int k = len - 1; k >= 0; k--) {
-            const uint32_t word = A.obsT[(size_t) k * cap + j];
-            Win w = decode_word(word, A.beta0);
-            if (w.edge) {
-                w.beta = A.edge_beta[3 * eidx];
-                w.rb = A.edge_beta[3 * eidx + 1];
-                w.sq = A.edge_beta[3 * eidx + 2];
-                eidx--;
-            }
-            const double *rt = rtab + (size_t) w.region * rt_stride;
+            const uint32_t w2 = k >= 2 ? __ldg(wk + (size_t) (k - 2) * cap) : 0u;
+            double Mn[16];
+            if (k >= 1) load_mat(A.tabM + (size_t) HFG_KEY_ID(w1) * 16, Mn);
             const int gi = seg_first + k;
 
             /* decode: EM_getPosterior / EM_getMostProbableState (hmm.c:671-692), first maximum (common.c:292-303) */
             {
                 double g[4];
 #pragma unroll
-                for (int s = 0; s < 4; s++) g[s] = fh[s] * bh[s] * c;
+                for (int s = 0; s < 4; s++) g[s] = fh[s] * bh[s];
                 if (A.posteriors) {
                     const double tot = ((g[0] + g[1]) + g[2]) + g[3];
 #pragma unroll
@@ -874,44 +925,96 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                         A.posteriors[(size_t) gi * 4 + s] = g[s];
                     }
                 }
-                /* dividing all four by the same total does not change their order */
+                /* a common positive factor does not change the order */
                 int best = 0;
 #pragma unroll
                 for (int s = 1; s < 4; s++)
                     if (g[best] < g[s]) best = s;
                 A.labels[gi] = (int8_t) best;
             }
-            if (w.start) break; /* first window of a chunk: nothing to the left */
+            if (w0 & HFG_KEY_CHUNK_START) break; /* first window of a chunk: nothing to the left */
 
-            /* f^ and scale of the previous window (last window of the previous segment == the entering message) */
-            double fp[4], cp = 1.0;
+            /* f^ of the previous window (last window of the previous segment == the entering message) */
+            double fp[4];
             if (k > 0) {
-#pragma unroll
-                for (int s = 0; s < 4; s++) fp[s] = A.scrF[((size_t) (k - 1) * 4 + s) * cap + j];
-                cp = A.scrC[(size_t) (k - 1) * cap + j];
+                load_vec4(A.scrF + (size_t) (gi - 1) * 4, fp);
             } else {
 #pragma unroll
                 for (int s = 0; s < 4; s++) fp[s] = v_in[s];
             }
-            const double *erow = A.scrE + (size_t) k * D * cap + j;
-            double bn[4] = {0.0, 0.0, 0.0, 0.0};
-            const bool do_stats = !w.second; /* the pair 0 -> 1 of every chunk is skipped (hmm.c:638-642) */
+            /* b[i-1][pre] = sum_s tProb*eProb*b[i][s] (hmm.c:493-520), then the normalisation */
+            double bn[4];
+#pragma unroll
+            for (int pre = 0; pre < 4; pre++)
+                bn[pre] = ((Mc[pre * 4] * bh[0] + Mc[pre * 4 + 1] * bh[1]) + Mc[pre * 4 + 2] * bh[2]) + Mc[pre * 4 + 3] * bh[3];
+            const double dot = ((fp[0] * bn[0] + fp[1] * bn[1]) + fp[2] * bn[2]) + fp[3] * bn[3];
+            const double r = 1.0 / dot;
+            double bs[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) bs[s] = bh[s] * r;
+            store_vec4(A.scrB + (size_t) gi * 4, bs);
 #pragma unroll
             for (int s = 0; s < 4; s++) {
-                double xi[4]; /* adjusted pair counts into state s, by preState */
+                bh[s] = bn[s] * r;
+                fh[s] = fp[s];
+            }
+            if (k >= 1) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) Mc[i] = Mn[i];
+            }
+            w0 = w1;
+            w1 = w2;
+        }
+    }
+    if (uf_flag) atomicOr(A.err_flags, 1);
+    grid.sync(); /* f^ and b of every window are in place */
+    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 5] = clock64();
+
+    /* =========================== phases S and D, region by region ============================================ */
+    /* per-thread statistics live in column tid of acc: rows 0..15 transition counts, 16..17 truncated exponential,
+     * 18+3g.. (meanNum, den, varNum) of Gaussian component g, last row the log-likelihood */
+    double *col = acc + tid;
+    /* tiles are dealt to warps round-robin over the blocks: 32 consecutive tiles (mostly one key) per warp */
+    const int tile_lane0 = (warp * gridDim.x + blockIdx.x) * 32 + lane;
+    for (int r = 0; r < R; r++) {
+        for (int q = 0; q < NSTAT; q++) col[(size_t) q * LD] = 0.0;
+        if (r == 0) col[(size_t) (NSTAT - 1) * LD] = loglik;
+        const int t_end = A.forward_only ? 0 : __ldg(&A.region_tile_begin[r + 1]);
+        for (int t = __ldg(&A.region_tile_begin[r]) + tile_lane0; t < t_end; t += n_threads) {
+            const int p = __ldg(&A.tile_key[t]), lb = __ldg(&A.tile_begin[t]), ln = __ldg(&A.tile_cnt[t]);
+            /* S[pre][s] = sum over the tile's windows of f^_{i-1}[pre] * b_i[s] */
+            double S[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) S[i] = 0.0;
+#pragma unroll 4
+            for (int i = 0; i < ln; i++) {
+                const int gi = __ldg(&A.klist[lb + i]);
+                double fp[4], bb[4];
+                load_vec4_cg(A.scrF + (size_t) (gi - 1) * 4, fp);
+                load_vec4_cg(A.scrB + (size_t) gi * 4, bb);
+#pragma unroll
+                for (int pre = 0; pre < 4; pre++)
+#pragma unroll
+                    for (int s = 0; s < 4; s++) S[pre * 4 + s] = fma(fp[pre], bb[s], S[pre * 4 + s]);
+            }
+            Win w = decode_word(__ldg(&A.kdesc[p]), A.beta0);
+            if (w.edge) {
+                w.beta = A.kbeta[3 * (size_t) p];
+                w.rb = A.kbeta[3 * (size_t) p + 1];
+                w.sq = A.kbeta[3 * (size_t) p + 2];
+            }
+            const double *rt = rtab + (size_t) w.region * rt_stride;
+            double M[16];
+            load_mat(A.tabM + (size_t) p * 16, M);
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                double xi[4]; /* pooled pair counts into state s, by preState (count / terminationProb, hmm.c:613-614) */
                 double hh[4]; /* the same without the emission factor (multi-component statistics) */
 #pragma unroll
                 for (int pre = 0; pre < 4; pre++) {
-                    const double t = trans_prob(rt, w, pre, s);
-                    const double e = erow[(size_t) A.cls[pre][s] * cap];
-                    /* b[i-1][pre] += tProb*eProb*b[i][s] (state outer, preState inner: hmm.c:493-520) */
-                    bn[pre] += t * e * bh[s];
-                    /* count = f[i][pre]*tProb*eProb*b[i+1][s]; adjusted = count / terminationProb (hmm.c:613-614) */
-                    const double ft = fp[pre] * t;
-                    xi[pre] = ((ft * e) * bh[s]) * HFG_INV_TERM;
-                    hh[pre] = (ft * bh[s]) * HFG_INV_TERM;
+                    xi[pre] = S[pre * 4 + s] * M[pre * 4 + s];
+                    hh[pre] = S[pre * 4 + s] * trans_prob(rt, w, pre, s);
                 }
-                if (!do_stats) continue;
 #pragma unroll
                 for (int pre = 0; pre < 4; pre++) col[(pre * 4 + s) * LD] += xi[pre]; /* hmm_utils.c:2010-2015 */
                 if (!A.is_gauss[s]) {
@@ -965,41 +1068,25 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                     }
                 }
             }
-            if (k > 0) {
-                const double rcp = __drcp_rn(cp); /* b^ = b / scale (hmm.c:526-528), as reciprocal x product */
-#pragma unroll
-                for (int s = 0; s < 4; s++) {
-                    bh[s] = bn[s] * rcp;
-                    fh[s] = fp[s];
-                }
-                c = cp;
-            }
         }
-    }
-    if (uf_flag) atomicOr(A.err_flags, 1);
-    if (nan_flag) atomicOr(A.err_flags, 2);
-
-    /* =========================== phase D: deterministic reduction ============================================ */
-    {
-        col[(size_t) (NSTAT - 1) * LD] = loglik;
         __syncthreads();
-        if (tid == 0) A.phase_clock[blockIdx.x * 10 + 5] = clock64();
-        /* one warp per (region, statistic) column: each lane adds its 8 entries in index order, then a fixed
-         * xor-shuffle tree -- the same association on every run */
-        for (int q = warp; q < R * NSTAT; q += WARPS) {
-            const int r = q / NSTAT, st = q % NSTAT;
-            const bool is_ll = (st == NSTAT - 1);
+        /* deterministic block reduction: one warp per statistic row; each lane adds its THREADS/32 entries in index
+         * order, then a fixed xor-shuffle tree -- the same association on every run */
+        for (int q = warp; q < NSTAT; q += WARPS) {
+            const double *cl = acc + (size_t) q * LD;
             double sum = 0.0;
-            if (!is_ll || r == 0) {
-                const double *cl = acc + (size_t) st * LD;
 #pragma unroll
-                for (int t = lane; t < THREADS; t += 32)
-                    if (is_ll || treg[t] == r) sum += cl[t];
-            }
+            for (int t = lane; t < THREADS; t += 32) sum += cl[t];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-            if (lane == 0) A.partials[((size_t) blockIdx.x * R + r) * NSTAT + st] = sum;
+            if (lane == 0) A.partials[((size_t) blockIdx.x * R + r) * NSTAT + q] = sum;
         }
+        __syncthreads();
+    }
+    if (nan_flag) atomicOr(A.err_flags, 2);
+
+    /* =========================== phase D: grid reduction ===================================================== */
+    {
         if (tid == 0) A.phase_clock[blockIdx.x * 10 + 6] = clock64();
         grid.sync();
         if (tid == 0) {

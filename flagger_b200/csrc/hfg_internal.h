@@ -41,6 +41,19 @@ extern "C" {
 #define HFG_OBS_CHUNK_END (1u << 29)
 #define HFG_OBS_VALID (1u << 31)
 
+/* ---- observation keys -----------------------------------------------------------------------------------
+ * Observations are small integers, so the per-window transfer matrix M_i = T_i (.) E_i takes few distinct values: it
+ * depends only on (x, px, region, validity mask, region change, chunk start, beta).  The host numbers the distinct
+ * combinations ("keys", hottest first inside a region); the kernel evaluates emissions and M once per KEY and per
+ * E-step, the windows gather M by key id, and the pair statistics are accumulated per key (lists of the windows of
+ * each key, cut into tiles of <= HFG_TILE windows).  Per-window key word, stored segment-transposed:
+ *  bits 0..27  key id      bit 30  last window of a chunk      bit 31  first window of a chunk */
+#define HFG_KEY_ID(w) ((w) & 0x0fffffffu)
+#define HFG_KEY_MAX 0x0fffffff
+#define HFG_KEY_CHUNK_END (1u << 30)
+#define HFG_KEY_CHUNK_START (1u << 31)
+#define HFG_TILE 16
+
 /* Host-built, run-constant device layout: the genome is ONE sequence of windows cut into segments that never
  * straddle a chunk or a region change; segment j is owned by global thread j of the E-step kernel and its k-th
  * window lives at obsT[k * capacity + j] (coalesced across threads). */
@@ -51,7 +64,17 @@ typedef struct hfg_layout {
     int32_t smax;      /* windows per segment slot */
     int32_t n_seg;
     double beta0;      /* interior beta: (Lr-1)/Lr, or 1 when contig ends are not adjusted */
-    uint32_t *obsT;          /* [smax][capacity] */
+    uint32_t *obsT;          /* [smax][capacity] packed observation words (host only: the keys are built from them) */
+    uint32_t *wkeyT;         /* [smax][capacity] key word of every window (device) */
+    int32_t n_keys;
+    uint32_t *kdesc;         /* [n_keys] packed observation word of the key (without the chunk-end bit) */
+    double *kbeta;           /* [n_keys][3] (beta, beta0/beta, sqrt(beta0/beta)); (beta0, 1, 1) for interior keys */
+    int64_t n_list;
+    int32_t *klist;          /* [n_list] global window indices grouped by key, ascending inside a key; windows whose pair
+                                is skipped by the statistics (chunk starts, second windows) are not listed */
+    int32_t n_tiles;
+    int32_t *tile_key, *tile_begin, *tile_cnt; /* [n_tiles] <= HFG_TILE consecutive entries of klist, all of one key */
+    int32_t region_tile_begin[HFG_MAX_REGIONS + 1]; /* tiles are grouped by region */
     int32_t *seg_start;      /* [capacity] global index of the segment's first window (0 for idle slots) */
     int32_t *seg_len;        /* [capacity] 0 for idle slots */
     int32_t *seg_chunk;      /* [capacity] */

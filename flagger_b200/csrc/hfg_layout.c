@@ -45,6 +45,13 @@ static uint32_t validity_mask(const hfg_config *cfg, uint16_t cov, uint16_t mapq
 void hfg_layout_free(hfg_layout *l) {
     if (!l) return;
     free(l->obsT);
+    free(l->wkeyT);
+    free(l->kdesc);
+    free(l->kbeta);
+    free(l->klist);
+    free(l->tile_key);
+    free(l->tile_begin);
+    free(l->tile_cnt);
     free(l->seg_start);
     free(l->seg_len);
     free(l->seg_chunk);
@@ -118,6 +125,231 @@ static void *pack_segments(void *arg) {
         }
     }
     return NULL;
+}
+
+
+/* ---- observation keys ----------------------------------------------------------------------------------------------
+ * Everything the kernel needs to know about a window except its position: the packed word without the chunk-end bit,
+ * plus the bits of beta for contig-end windows.  Distinct combinations are numbered through an open-addressing hash
+ * table (a 3 Gbp assembly at 40x has ~10^4 of them for ~10^6 windows). */
+
+typedef struct KeySlot {
+    uint64_t beta_bits;
+    uint32_t word;
+    int32_t id; /* -1 = empty */
+} KeySlot;
+
+typedef struct KeyTab {
+    KeySlot *slots;
+    uint32_t mask; /* capacity - 1 */
+    int32_t n;
+    /* per key, in discovery order */
+    uint32_t *word;
+    uint64_t *beta_bits;
+    int32_t *count;
+    int32_t cap_keys;
+} KeyTab;
+
+static uint32_t key_hash(uint32_t word, uint64_t bb) {
+    uint64_t h = ((uint64_t) word * 0x9E3779B97F4A7C15ull) ^ (bb * 0xC2B2AE3D27D4EB4Full);
+    return (uint32_t) (h >> 32);
+}
+
+static int keytab_init(KeyTab *t, uint32_t capacity) {
+    memset(t, 0, sizeof(*t));
+    t->slots = malloc(sizeof(KeySlot) * (size_t) capacity);
+    t->cap_keys = (int32_t) (capacity / 2);
+    t->word = malloc(sizeof(uint32_t) * (size_t) t->cap_keys);
+    t->beta_bits = malloc(sizeof(uint64_t) * (size_t) t->cap_keys);
+    t->count = malloc(sizeof(int32_t) * (size_t) t->cap_keys);
+    if (!t->slots || !t->word || !t->beta_bits || !t->count) return 0;
+    for (uint32_t i = 0; i < capacity; i++) t->slots[i].id = -1;
+    t->mask = capacity - 1;
+    return 1;
+}
+
+static void keytab_free(KeyTab *t) {
+    free(t->slots);
+    free(t->word);
+    free(t->beta_bits);
+    free(t->count);
+    memset(t, 0, sizeof(*t));
+}
+
+/* doubles the table (keys keep their ids) */
+static int keytab_grow(KeyTab *t) {
+    const uint32_t capacity = (t->mask + 1) * 2;
+    KeySlot *ns = malloc(sizeof(KeySlot) * (size_t) capacity);
+    uint32_t *nw = realloc(t->word, sizeof(uint32_t) * (size_t) (capacity / 2));
+    if (nw) t->word = nw;
+    uint64_t *nb = realloc(t->beta_bits, sizeof(uint64_t) * (size_t) (capacity / 2));
+    if (nb) t->beta_bits = nb;
+    int32_t *nc = realloc(t->count, sizeof(int32_t) * (size_t) (capacity / 2));
+    if (nc) t->count = nc;
+    if (!ns || !nw || !nb || !nc) {
+        free(ns);
+        return 0;
+    }
+    for (uint32_t i = 0; i < capacity; i++) ns[i].id = -1;
+    for (int32_t k = 0; k < t->n; k++) {
+        uint32_t h = key_hash(t->word[k], t->beta_bits[k]) & (capacity - 1);
+        while (ns[h].id >= 0) h = (h + 1) & (capacity - 1);
+        ns[h].word = t->word[k];
+        ns[h].beta_bits = t->beta_bits[k];
+        ns[h].id = k;
+    }
+    free(t->slots);
+    t->slots = ns;
+    t->mask = capacity - 1;
+    t->cap_keys = (int32_t) (capacity / 2);
+    return 1;
+}
+
+/* id of (word, beta_bits), inserting it when new; -1 when out of memory */
+static inline int32_t keytab_lookup(KeyTab *t, uint32_t word, uint64_t bb) {
+    uint32_t h = key_hash(word, bb) & t->mask;
+    for (;;) {
+        KeySlot *s = &t->slots[h];
+        if (s->id < 0) break;
+        if (s->word == word && s->beta_bits == bb) {
+            t->count[s->id]++;
+            return s->id;
+        }
+        h = (h + 1) & t->mask;
+    }
+    if (t->n == t->cap_keys) {
+        if (!keytab_grow(t)) return -1;
+        h = key_hash(word, bb) & t->mask;
+        while (t->slots[h].id >= 0) h = (h + 1) & t->mask;
+    }
+    const int32_t id = t->n++;
+    t->slots[h].word = word;
+    t->slots[h].beta_bits = bb;
+    t->slots[h].id = id;
+    t->word[id] = word;
+    t->beta_bits[id] = bb;
+    t->count[id] = 1;
+    return id;
+}
+
+typedef struct KeyOrder {
+    int32_t old_id, count;
+    uint32_t region;
+} KeyOrder;
+
+static int key_order_cmp(const void *a, const void *b) {
+    const KeyOrder *x = a, *y = b;
+    if (x->region != y->region) return x->region < y->region ? -1 : 1;
+    if (x->count != y->count) return x->count > y->count ? -1 : 1; /* hottest first: their matrices share cache lines */
+    return x->old_id < y->old_id ? -1 : (x->old_id > y->old_id);
+}
+
+/* does the pair (previous window -> this window) enter the statistics?  (hmm.c:638-642: pairs 1->2 .. L-2->L-1) */
+static inline int key_has_stats(uint32_t word) { return !(word & (HFG_OBS_CHUNK_START | HFG_OBS_SECOND)); }
+
+/* builds wkeyT, the key tables, the per-key window lists and their tiles from obsT / edge_beta */
+static int build_keys(hfg_layout *out) {
+    const int64_t W = out->n_windows;
+    const int capacity = out->capacity;
+    KeyTab kt;
+    memset(&kt, 0, sizeof(kt));
+    int32_t *wkid = malloc(sizeof(int32_t) * (size_t) W);
+    KeyOrder *order = NULL;
+    int32_t *new_id = NULL, *kbegin = NULL, *fill = NULL;
+    int ok = 0;
+    if (!wkid || !keytab_init(&kt, 1u << 15)) goto done;
+    /* pass 1: number the keys in discovery order (windows in global order: segment after segment) */
+    for (int32_t seg = 0; seg < out->n_seg; seg++) {
+        int64_t e = out->seg_edge_begin[seg];
+        const int64_t g0 = out->seg_start[seg];
+        for (int k = 0; k < out->seg_len[seg]; k++) {
+            const uint32_t word = out->obsT[(size_t) k * capacity + seg] & ~HFG_OBS_CHUNK_END;
+            uint64_t bb = 0;
+            if (word & HFG_OBS_EDGE) memcpy(&bb, &out->edge_beta[3 * e++], sizeof(bb));
+            const int32_t id = keytab_lookup(&kt, word, bb);
+            if (id < 0) goto done;
+            wkid[g0 + k] = id;
+        }
+    }
+    const int32_t P = kt.n;
+    if (P > HFG_KEY_MAX) goto done;
+    /* pass 2: final numbering by (region, count descending) */
+    order = malloc(sizeof(KeyOrder) * (size_t) P);
+    new_id = malloc(sizeof(int32_t) * (size_t) P);
+    kbegin = malloc(sizeof(int32_t) * ((size_t) P + 1));
+    fill = malloc(sizeof(int32_t) * (size_t) P);
+    out->kdesc = malloc(sizeof(uint32_t) * (size_t) P);
+    out->kbeta = malloc(sizeof(double) * 3 * (size_t) P);
+    if (!order || !new_id || !kbegin || !fill || !out->kdesc || !out->kbeta) goto done;
+    for (int32_t k = 0; k < P; k++) order[k] = (KeyOrder){k, kt.count[k], HFG_OBS_REGION(kt.word[k])};
+    qsort(order, (size_t) P, sizeof(KeyOrder), key_order_cmp);
+    int64_t n_list = 0;
+    int64_t n_tiles = 0;
+    for (int32_t p = 0; p < P; p++) {
+        const int32_t o = order[p].old_id;
+        new_id[o] = p;
+        out->kdesc[p] = kt.word[o];
+        double b = out->beta0;
+        if (kt.word[o] & HFG_OBS_EDGE) memcpy(&b, &kt.beta_bits[o], sizeof(b));
+        out->kbeta[3 * p] = b;
+        out->kbeta[3 * p + 1] = (kt.word[o] & HFG_OBS_EDGE) ? out->beta0 / b : 1.0;
+        out->kbeta[3 * p + 2] = (kt.word[o] & HFG_OBS_EDGE) ? sqrt(out->beta0 / b) : 1.0;
+        kbegin[p] = (int32_t) n_list;
+        if (key_has_stats(kt.word[o])) {
+            n_list += order[p].count;
+            n_tiles += (order[p].count + HFG_TILE - 1) / HFG_TILE;
+        }
+    }
+    kbegin[P] = (int32_t) n_list;
+    out->n_keys = P;
+    out->n_list = n_list;
+    out->n_tiles = (int32_t) n_tiles;
+    out->klist = malloc(sizeof(int32_t) * (size_t) (n_list > 0 ? n_list : 1));
+    out->tile_key = malloc(sizeof(int32_t) * (size_t) (n_tiles > 0 ? n_tiles : 1));
+    out->tile_begin = malloc(sizeof(int32_t) * (size_t) (n_tiles > 0 ? n_tiles : 1));
+    out->tile_cnt = malloc(sizeof(int32_t) * (size_t) (n_tiles > 0 ? n_tiles : 1));
+    out->wkeyT = calloc((size_t) out->smax * capacity, sizeof(uint32_t));
+    if (!out->klist || !out->tile_key || !out->tile_begin || !out->tile_cnt || !out->wkeyT) goto done;
+    /* pass 3: tiles, grouped by region because the keys are */
+    {
+        int32_t t = 0;
+        for (int r = 0; r <= HFG_MAX_REGIONS; r++) out->region_tile_begin[r] = -1;
+        for (int32_t p = 0; p < P; p++) {
+            const int r = (int) HFG_OBS_REGION(out->kdesc[p]);
+            if (out->region_tile_begin[r] < 0) out->region_tile_begin[r] = t;
+            for (int32_t b = kbegin[p]; b < kbegin[p + 1]; b += HFG_TILE, t++) {
+                out->tile_key[t] = p;
+                out->tile_begin[t] = b;
+                out->tile_cnt[t] = kbegin[p + 1] - b < HFG_TILE ? kbegin[p + 1] - b : HFG_TILE;
+            }
+        }
+        out->region_tile_begin[HFG_MAX_REGIONS] = t;
+        for (int r = HFG_MAX_REGIONS - 1; r >= 0; r--)
+            if (out->region_tile_begin[r] < 0) out->region_tile_begin[r] = out->region_tile_begin[r + 1];
+    }
+    /* pass 4: key words (segment-transposed) and the per-key window lists (ascending: windows are visited in order) */
+    memcpy(fill, kbegin, sizeof(int32_t) * (size_t) P);
+    for (int32_t seg = 0; seg < out->n_seg; seg++) {
+        const int64_t g0 = out->seg_start[seg];
+        for (int k = 0; k < out->seg_len[seg]; k++) {
+            const uint32_t word = out->obsT[(size_t) k * capacity + seg];
+            const int32_t p = new_id[wkid[g0 + k]];
+            uint32_t kw = (uint32_t) p;
+            if (word & HFG_OBS_CHUNK_START) kw |= HFG_KEY_CHUNK_START;
+            if (word & HFG_OBS_CHUNK_END) kw |= HFG_KEY_CHUNK_END;
+            out->wkeyT[(size_t) k * capacity + seg] = kw;
+            if (key_has_stats(word)) out->klist[fill[p]++] = (int32_t) (g0 + k);
+        }
+    }
+    ok = 1;
+done:
+    keytab_free(&kt);
+    free(wkid);
+    free(order);
+    free(new_id);
+    free(kbegin);
+    free(fill);
+    return ok;
 }
 
 /* number of edge windows among the first w windows of chunk c */
@@ -256,6 +488,13 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
         for (int t = 1; t < n_threads; t++)
             if (tids[t]) pthread_join(tids[t], NULL);
     }
+    if (W > HFG_KEY_MAX) {
+        free(runs); free(edge_head); free(edge_tail); free(chunk_edge_base);
+        hfg_layout_free(out);
+        snprintf(err, errlen, "number of windows (%lld) above the %d this build addresses per device", (long long) W, HFG_KEY_MAX);
+        return HFG_ERR_INVALID;
+    }
+    if (!build_keys(out)) goto nomem;
     free(runs); free(edge_head); free(edge_tail); free(chunk_edge_base);
     return HFG_OK;
 nomem:
@@ -340,11 +579,68 @@ int hfg_debug_layout_check(const hfg_config *cfg, int32_t n_chunks, const hfg_ch
     for (int32_t j = l.n_seg; j < capacity && !bad; j++)
         if (l.seg_len[j] != 0) bad = 1;
     if (next != l.n_windows || edges != l.n_edge || l.n_seg > capacity) bad = 1;
+    /* keys: every window's key reproduces its packed word and beta; every pair that enters the statistics is listed
+     * exactly once under its key, ascending; the tiles partition the lists and are grouped by region */
+    if (!bad) {
+        int64_t e = 0, listed = 0;
+        uint8_t *seen = calloc((size_t) l.n_windows, 1);
+        for (int32_t j = 0; j < l.n_seg && !bad; j++) {
+            for (int k = 0; k < l.seg_len[j] && !bad; k++) {
+                const uint32_t word = l.obsT[(size_t) k * capacity + j], kw = l.wkeyT[(size_t) k * capacity + j];
+                const uint32_t p = HFG_KEY_ID(kw);
+                if ((int32_t) p >= l.n_keys) { bad = 1; break; }
+                if (l.kdesc[p] != (word & ~HFG_OBS_CHUNK_END)) bad = 1;
+                if (((kw & HFG_KEY_CHUNK_START) != 0) != ((word & HFG_OBS_CHUNK_START) != 0)) bad = 1;
+                if (((kw & HFG_KEY_CHUNK_END) != 0) != ((word & HFG_OBS_CHUNK_END) != 0)) bad = 1;
+                const double b = (word & HFG_OBS_EDGE) ? l.edge_beta[3 * e] : l.beta0;
+                if (l.kbeta[3 * p] != b || l.kbeta[3 * p + 1] != l.beta0 / b) bad = 1;
+                if (word & HFG_OBS_EDGE) e++;
+                if (key_has_stats(word)) listed++;
+            }
+        }
+        if (listed != l.n_list) bad = 1;
+        int32_t at = 0, last_region = -1;
+        for (int32_t t = 0; t < l.n_tiles && !bad; t++) {
+            const int32_t p = l.tile_key[t];
+            if (p < 0 || p >= l.n_keys || l.tile_begin[t] != at || l.tile_cnt[t] < 1 || l.tile_cnt[t] > HFG_TILE) { bad = 1; break; }
+            const int32_t r = (int32_t) HFG_OBS_REGION(l.kdesc[p]);
+            if (r < last_region || t < l.region_tile_begin[r] || t >= l.region_tile_begin[r + 1]) bad = 1;
+            last_region = r;
+            for (int i = 0; i < l.tile_cnt[t] && !bad; i++) {
+                const int32_t g = l.klist[at + i];
+                if (g < 1 || g >= l.n_windows || seen[g]) { bad = 1; break; }
+                if (i > 0 && l.klist[at + i - 1] >= g) bad = 1;
+                seen[g] = 1;
+            }
+            at += l.tile_cnt[t];
+        }
+        if (at != l.n_list) bad = 1;
+        /* the listed windows carry the tile's key */
+        for (int32_t j = 0; j < l.n_seg && !bad; j++)
+            for (int k = 0; k < l.seg_len[j]; k++) {
+                const uint32_t word = l.obsT[(size_t) k * capacity + j];
+                if ((seen[l.seg_start[j] + k] != 0) != (key_has_stats(word) != 0)) bad = 1;
+            }
+        for (int32_t t = 0; t < l.n_tiles && !bad; t++)
+            for (int i = 0; i < l.tile_cnt[t]; i++) {
+                /* locate the window's segment by binary search over seg_start */
+                const int32_t g = l.klist[l.tile_begin[t] + i];
+                int32_t lo = 0, hi = l.n_seg - 1;
+                while (lo < hi) {
+                    const int32_t mid = (lo + hi + 1) / 2;
+                    if (l.seg_start[mid] <= g) lo = mid; else hi = mid - 1;
+                }
+                if ((int32_t) HFG_KEY_ID(l.wkeyT[(size_t) (g - l.seg_start[lo]) * capacity + lo]) != l.tile_key[t]) bad = 1;
+            }
+        free(seen);
+    }
     if (summary) {
         summary[0] = l.n_seg;
         summary[1] = l.smax;
         summary[2] = l.n_edge;
         summary[3] = l.n_windows;
+        summary[4] = l.n_keys;
+        summary[5] = l.n_tiles;
     }
     hfg_layout_free(&l);
     return bad ? HFG_ERR_INVALID : HFG_OK;

@@ -223,8 +223,8 @@ double hfg_last_call_device_ms(hfg_ctx *ctx);
  * values + SM id) and the kernel's exponential applied to n host values. */
 int hfg_debug_phase_clocks(hfg_ctx *ctx, long long *out, int *grid);
 int hfg_debug_exp(hfg_ctx *ctx, const double *in, double *out, int n);
-/* Host-only (no GPU): self-check of the segment layout builder for `capacity` segment slots; summary = {segments, windows
- * per slot, edge windows, windows}.  And EM_computeAdjustmentBeta (hmm.c:301-316) for one window of a chunk. */
+/* Host-only (no GPU): self-check of the segment layout and observation-key builder for `capacity` segment slots;
+ * summary[6] = {segments, windows per slot, edge windows, windows, distinct observation keys, statistics tiles}.  And EM_computeAdjustmentBeta (hmm.c:301-316) for one window of a chunk. */
 int hfg_debug_layout_check(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
                            const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
                            int32_t capacity, int64_t *summary);

@@ -24,8 +24,9 @@ def test_layout_invariants(factory, n_regions, capacity):
         cfg = _abi.make_config(n_regions=n_regions, adjust_contig_ends=adjust, mean_read_length=wl.avg_alignment_len)
         ok, summary = api.layout_check(cfg, wl, capacity)
         assert ok
-        n_seg, smax, n_edge, W = (int(v) for v in summary)
+        n_seg, smax, n_edge, W, n_keys, n_tiles = (int(v) for v in summary)
         assert W == wl.n_windows and n_seg <= capacity and n_seg * smax >= W
+        assert 1 <= n_keys <= W and n_tiles <= W // 16 + n_keys
         assert (n_edge == 0) == (not adjust)
 
 
