@@ -51,7 +51,7 @@ EXPORTED_SYMBOLS = (
     "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_chunks", "hfg_num_windows", "hfg_em_iteration",
     "hfg_forward_only", "hfg_get_posteriors", "hfg_get_chunk_logliks", "hfg_em_iteration_device",
     "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
-    "hfg_run_em", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
+    "hfg_run_em", "hfg_em_begin", "hfg_em_enqueue", "hfg_em_finish", "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
     "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_read_cov", "hfg_read_bin", "hfg_cov_free",
     "hfg_params_feasible", "hfg_squarem_alpha_rate", "hfg_squarem_prime", "hfg_squarem_shrink", "hfg_squarem_iteration",
     "hfg_run_em_accelerated", "hfg_release_cached_memory",
@@ -235,6 +235,34 @@ class HmmFlaggerGPU:
                                      ptr(logliks), C.byref(n), ptr(labels)))
         return params, logliks[:n.value].copy(), labels
 
+    # ---- device-resident EM loop (hfg_em_begin / hfg_em_enqueue / hfg_em_finish) ----
+    def em_begin(self, alpha, params, tol=1e-3, max_esteps=64):
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        self._em_max = int(max_esteps)
+        self._check(lib().hfg_em_begin(self._h, ptr(alpha), ptr(np.ascontiguousarray(params)), C.c_double(tol),
+                                       C.c_int(int(max_esteps))))
+
+    def em_enqueue(self, final_pass=False):
+        """Queues one iteration (E-step + device M-step, or the final inference pass) without waiting."""
+        self._check(lib().hfg_em_enqueue(self._h, C.c_int(1 if final_pass else 0)))
+
+    def em_finish(self, want_labels=True):
+        """Waits for the queued iterations: returns (params, logliks of the E-steps that ran, converged, labels)."""
+        params = np.zeros(self.n_regions, dtype=_abi.region_params_dtype)
+        logliks = np.zeros(self._em_max, np.float64)
+        n, conv = C.c_int(0), C.c_int(0)
+        labels = np.empty(self.n_windows, np.int8) if want_labels else None
+        self._check(lib().hfg_em_finish(self._h, ptr(params), ptr(logliks), C.byref(n), C.byref(conv), ptr(labels)))
+        return params, logliks[:n.value].copy(), bool(conv.value), labels
+
+    def em_enqueued_ms(self, i):
+        f = lib().hfg_em_enqueued_ms
+        f.restype = C.c_double
+        return float(f(self._h, C.c_int(int(i))))
+
+    def l2_flush(self, nbytes=256 << 20):
+        self._check(lib().hfg_debug_l2_flush(self._h, C.c_size_t(int(nbytes))))
+
     def run_em_accelerated(self, alpha, params, max_iterations, tol=1e-3, want_labels=True):
         """The EM loop of runHMMFlagger with --accelerate (SQUAREM): returns (params, logliks, alpha_rates, labels)."""
         alpha = np.ascontiguousarray(alpha, np.float64)
@@ -254,7 +282,7 @@ class HmmFlaggerGPU:
         return out
 
     def debug_phase_clocks(self):
-        buf = np.zeros((4096, 10), np.int64)
+        buf = np.zeros((4096, 12), np.int64)
         g = C.c_int(0)
         self._check(lib().hfg_debug_phase_clocks(self._h, ptr(buf), C.byref(g)))
         return buf[: g.value].copy()

@@ -35,7 +35,7 @@ struct hfg_ctx {
     uint32_t *d_wkeyT, *d_kdesc;
     int32_t *d_seg_start, *d_seg_len, *d_block_reset, *d_err;
     int32_t *d_klist, *d_tile_key, *d_tile_begin, *d_tile_cnt, *d_region_tile_begin;
-    double *d_kbeta, *d_tabM, *d_scrF, *d_scrB, *d_block_tot, *d_partials, *d_out, *d_seg_loglik, *d_post;
+    double *d_kbeta, *d_tabM, *d_scrFT, *d_scrXB, *d_block_tot, *d_partials, *d_out, *d_seg_loglik, *d_post;
     hfg_region_params *d_params[STAGE_SLOTS];
     int8_t *d_labels;
     long long *d_phase_clock;
@@ -61,6 +61,15 @@ struct hfg_ctx {
     double *d_mailbox;                 /* own mailbox (its own allocation: it is shared through CUDA IPC) */
     double *peer_box[HFG_MAX_PEERS];   /* every rank's mailbox as mapped into this process */
     unsigned long long *d_epoch;
+    /* device-resident EM loop (hfg_em_begin / hfg_em_enqueue / hfg_em_finish) */
+    hfg_region_params *d_em_params;
+    int32_t *d_em_state;
+    double *d_em_logliks;
+    int em_active, em_max, em_enqueued, em_ev_cap;
+    double em_alpha[16], em_tol;
+    cudaEvent_t *em_ev; /* [2 * em_ev_cap] */
+    void *d_flush;
+    size_t flush_bytes;
     int64_t launches;
     char err[512];
 };
@@ -274,7 +283,7 @@ static void free_device(hfg_ctx *ctx) {
     ctx->d_wkeyT = ctx->d_kdesc = NULL;
     ctx->d_seg_start = ctx->d_seg_len = ctx->d_block_reset = ctx->d_err = NULL;
     ctx->d_klist = ctx->d_tile_key = ctx->d_tile_begin = ctx->d_tile_cnt = ctx->d_region_tile_begin = NULL;
-    ctx->d_kbeta = ctx->d_tabM = ctx->d_scrF = ctx->d_scrB = ctx->d_block_tot = ctx->d_partials = NULL;
+    ctx->d_kbeta = ctx->d_tabM = ctx->d_scrFT = ctx->d_scrXB = ctx->d_block_tot = ctx->d_partials = NULL;
     ctx->d_out = ctx->d_seg_loglik = ctx->d_post = NULL;
     ctx->d_labels = NULL;
     ctx->d_phase_clock = NULL;
@@ -300,6 +309,12 @@ extern "C" void hfg_destroy(hfg_ctx *ctx) {
         if (p != ctx->rank && ctx->peer_box[p]) cudaIpcCloseMemHandle(ctx->peer_box[p]);
     cudaFree(ctx->d_mailbox);
     cudaFree(ctx->d_epoch);
+    cudaFree(ctx->d_em_params);
+    cudaFree(ctx->d_em_state);
+    cudaFree(ctx->d_em_logliks);
+    cudaFree(ctx->d_flush);
+    for (int i = 0; i < 2 * ctx->em_ev_cap; i++) cudaEventDestroy(ctx->em_ev[i]);
+    free(ctx->em_ev);
     cudaStreamDestroy(ctx->stream);
     free(ctx->last_params);
     free(ctx);
@@ -361,8 +376,8 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         const size_t o_tk = CARVE(NT * sizeof(int32_t)), o_tb = CARVE(NT * sizeof(int32_t)), o_tc = CARVE(NT * sizeof(int32_t));
         const size_t o_rt = CARVE((HFG_MAX_REGIONS + 1) * sizeof(int32_t));
         const size_t o_M = CARVE(P * 16 * sizeof(double));
-        const size_t o_F = CARVE((size_t) l->n_windows * 4 * sizeof(double));
-        const size_t o_B = CARVE((size_t) l->n_windows * 4 * sizeof(double));
+        const size_t o_F = CARVE(slots * 4 * sizeof(double));
+        const size_t o_B = CARVE((size_t) l->n_windows * 8 * sizeof(double));
         const size_t o_bt = CARVE((size_t) ctx->grid * 16 * sizeof(double));
         const size_t o_br = CARVE((size_t) ctx->grid * sizeof(int32_t));
         const size_t o_pa = CARVE((size_t) ctx->grid * R * hfg_nstat(G) * sizeof(double));
@@ -370,7 +385,7 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         const size_t o_ll = CARVE(cap * sizeof(double));
         const size_t o_lab = CARVE((size_t) l->n_windows);
         const size_t o_err = CARVE(sizeof(int32_t));
-        const size_t o_pc = CARVE((size_t) ctx->grid * 10 * sizeof(long long));
+        const size_t o_pc = CARVE((size_t) ctx->grid * HFG_PC_STRIDE * sizeof(long long));
 #undef CARVE
         ctx->d_arena = arena_acquire(off, ctx->device, &ctx->arena_bytes);
         if (!ctx->d_arena) {
@@ -393,8 +408,8 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         ctx->d_tile_cnt = (int32_t *) (base + o_tc);
         ctx->d_region_tile_begin = (int32_t *) (base + o_rt);
         ctx->d_tabM = (double *) (base + o_M);
-        ctx->d_scrF = (double *) (base + o_F);
-        ctx->d_scrB = (double *) (base + o_B);
+        ctx->d_scrFT = (double *) (base + o_F);
+        ctx->d_scrXB = (double *) (base + o_B);
         ctx->d_block_tot = (double *) (base + o_bt);
         ctx->d_block_reset = (int32_t *) (base + o_br);
         ctx->d_partials = (double *) (base + o_pa);
@@ -515,8 +530,8 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     }
     a.params = ctx->d_params[slot];
     a.tabM = ctx->d_tabM;
-    a.scrF = ctx->d_scrF;
-    a.scrB = ctx->d_scrB;
+    a.scrFT = ctx->d_scrFT;
+    a.scrXB = ctx->d_scrXB;
     a.block_tot = ctx->d_block_tot;
     a.block_reset = ctx->d_block_reset;
     a.partials = ctx->d_partials;
@@ -533,6 +548,7 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     a.rank = ctx->rank;
     for (int p = 0; p < HFG_MAX_PEERS; p++) a.peer_box[p] = ctx->peer_box[p];
     a.epoch = ctx->d_epoch;
+    a.model_type = cfg->model_type;
 }
 
 /* Enqueue one E-step (or forward pass) on `stream`; results land in out_dev = [stats | loglik | error flags]. */
@@ -757,30 +773,135 @@ extern "C" double hfg_last_estep_kernel_ms(hfg_ctx *ctx) {
     return (double) ms;
 }
 
+/* ---- device-resident EM loop ------------------------------------------------------------------------------------------ */
+
+extern "C" int hfg_em_begin(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params, double convergence_tol,
+                            int max_esteps) {
+    if (!ctx) return HFG_ERR_INVALID;
+    if (!ctx->have_chunks) return fail(ctx, HFG_ERR_INVALID, "hfg_set_chunks must be called first");
+    if (!alpha || !params || max_esteps < 1) return fail(ctx, HFG_ERR_INVALID, "hfg_em_begin: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const int R = ctx->cfg.n_regions;
+    const size_t pb = sizeof(hfg_region_params) * (size_t) R;
+    if (!ctx->d_em_params) CU(cudaMalloc((void **) &ctx->d_em_params, pb));
+    if (!ctx->d_em_state) CU(cudaMalloc((void **) &ctx->d_em_state, 4 * sizeof(int32_t)));
+    if (ctx->em_max < max_esteps) {
+        cudaFree(ctx->d_em_logliks);
+        ctx->d_em_logliks = NULL;
+        CU(cudaMalloc((void **) &ctx->d_em_logliks, sizeof(double) * (size_t) max_esteps));
+    }
+    ctx->em_max = max_esteps;
+    if (ctx->em_ev_cap < max_esteps) {
+        cudaEvent_t *ne = (cudaEvent_t *) realloc(ctx->em_ev, sizeof(cudaEvent_t) * 2 * (size_t) max_esteps);
+        if (!ne) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+        ctx->em_ev = ne;
+        for (int i = 2 * ctx->em_ev_cap; i < 2 * max_esteps; i++) CU(cudaEventCreate(&ctx->em_ev[i]));
+        ctx->em_ev_cap = max_esteps;
+    }
+    CU(cudaEventSynchronize(ctx->stage_ev[0]));
+    memcpy(ctx->h_params[0], params, pb);
+    CU(cudaMemcpyAsync(ctx->d_em_params, ctx->h_params[0], pb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->stage_ev[0], ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_em_state, 0, 4 * sizeof(int32_t), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream));
+    memcpy(ctx->em_alpha, alpha, sizeof(double) * 16);
+    ctx->em_tol = convergence_tol;
+    ctx->em_enqueued = 0;
+    ctx->em_active = 1;
+    return HFG_OK;
+}
+
+extern "C" int hfg_em_enqueue(hfg_ctx *ctx, int final_pass) {
+    if (!ctx) return HFG_ERR_INVALID;
+    if (!ctx->em_active) return fail(ctx, HFG_ERR_INVALID, "hfg_em_enqueue: call hfg_em_begin first");
+    if (ctx->em_enqueued >= ctx->em_max) return fail(ctx, HFG_ERR_INVALID, "hfg_em_enqueue: more than max_esteps iterations");
+    CU(cudaSetDevice(ctx->device));
+    EstepArgs a;
+    build_args(ctx, ctx->em_alpha, ctx->d_out, NULL, 0, 0, &a);
+    a.params = ctx->d_em_params;
+    a.em_params = ctx->d_em_params;
+    a.em_mode = final_pass ? 2 : 1;
+    a.em_tol = ctx->em_tol;
+    a.em_state = ctx->d_em_state;
+    a.em_logliks = ctx->d_em_logliks;
+    a.em_max_logliks = ctx->em_max;
+    void *kargs[] = {(void *) &a};
+    const int i = ctx->em_enqueued;
+    CU(cudaEventRecord(ctx->em_ev[2 * i], ctx->stream));
+    CU(cudaLaunchCooperativeKernel(ctx->kernel, dim3(ctx->grid), dim3(ctx->threads), kargs, ctx->smem_bytes, ctx->stream));
+    CU(cudaEventRecord(ctx->em_ev[2 * i + 1], ctx->stream));
+    ctx->em_enqueued = i + 1;
+    ctx->launches += 1;
+    return HFG_OK;
+}
+
+extern "C" int hfg_em_finish(hfg_ctx *ctx, hfg_region_params *params, double *logliks, int *n_esteps, int *converged,
+                             int8_t *labels) {
+    if (!ctx) return HFG_ERR_INVALID;
+    if (!ctx->em_active) return fail(ctx, HFG_ERR_INVALID, "hfg_em_finish: call hfg_em_begin first");
+    CU(cudaSetDevice(ctx->device));
+    const int R = ctx->cfg.n_regions;
+    const size_t pb = sizeof(hfg_region_params) * (size_t) R;
+    int32_t state[4] = {0, 0, 0, 0};
+    if (labels) CU(cudaMemcpyAsync(ctx->h_labels, ctx->d_labels, (size_t) ctx->lay.n_windows, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_params[0], ctx->d_em_params, pb, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(state, ctx->d_em_state, sizeof(state), cudaMemcpyDeviceToHost));
+    ctx->em_active = 0;
+    const int n = state[1] < ctx->em_max ? state[1] : ctx->em_max;
+    if (logliks && n > 0) CU(cudaMemcpy(logliks, ctx->d_em_logliks, sizeof(double) * (size_t) n, cudaMemcpyDeviceToHost));
+    if (n_esteps) *n_esteps = n;
+    if (converged) *converged = state[3];
+    if (params) memcpy(params, ctx->h_params[0], pb);
+    if (labels) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
+    /* the parameters of the last E-step that ran, for hfg_get_posteriors */
+    memcpy(ctx->last_alpha, ctx->em_alpha, sizeof(double) * 16);
+    memcpy(ctx->last_params, ctx->h_params[0], pb);
+    ctx->have_last = 1;
+    if (state[2] & 1)
+        return fail(ctx, HFG_ERR_SCALE_UNDERFLOW, "scale is very low! (a forward scale fell below 1e-50; hmm.c:412-415)");
+    if (state[2] & 2) return fail(ctx, HFG_ERR_NAN, "[Error] prob is NAN (an emission pdf evaluated to NaN; hmm_utils.c:782-786)");
+    if (state[2] & 4) return fail(ctx, HFG_ERR_CUDA, "peer all-reduce timed out: a rank did not reach the exchange");
+    return HFG_OK;
+}
+
+extern "C" double hfg_em_enqueued_ms(hfg_ctx *ctx, int i) {
+    if (!ctx || i < 0 || i >= ctx->em_enqueued) return -1.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(ctx->em_ev[2 * i + 1]) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, ctx->em_ev[2 * i], ctx->em_ev[2 * i + 1]) != cudaSuccess) return -1.0;
+    return (double) ms;
+}
+
+extern "C" int hfg_debug_l2_flush(hfg_ctx *ctx, size_t bytes) {
+    if (!ctx || bytes == 0) return HFG_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->flush_bytes < bytes) {
+        cudaFree(ctx->d_flush);
+        ctx->d_flush = NULL;
+        ctx->flush_bytes = 0;
+        CU(cudaMalloc(&ctx->d_flush, bytes));
+        ctx->flush_bytes = bytes;
+    }
+    CU(cudaMemsetAsync(ctx->d_flush, 0x5a, bytes, ctx->stream));
+    return HFG_OK;
+}
+
+/* while (iter <= numberOfIterations && converged == false) { E-step; M-step }  (src/hmm_flagger.c:337-431), then the final
+ * inference with the final parameters (:464) -- all of it queued at once on the device (hfg_em_*). */
 extern "C" int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,
                           double convergence_tol, double *logliks, int *n_esteps, int8_t *labels) {
     if (!ctx || !params || !logliks || !n_esteps) return HFG_ERR_INVALID;
-    const int R = ctx->cfg.n_regions;
-    hfg_region_stats *stats = (hfg_region_stats *) malloc(sizeof(hfg_region_stats) * (size_t) R);
-    if (!stats) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
-    int iter = 1, converged = 0, k = 0, rc = HFG_OK;
-    /* while (iter <= numberOfIterations && converged == false) { E-step; M-step }  (src/hmm_flagger.c:337-431) */
-    while (iter <= max_iterations && !converged) {
-        rc = hfg_em_iteration(ctx, alpha, params, stats, &logliks[k], NULL);
-        if (rc != HFG_OK) break;
-        k++;
-        rc = hfg_mstep(&ctx->cfg, params, stats, convergence_tol, &converged);
-        if (rc != HFG_OK) break;
-        iter++;
+    if (max_iterations < 0) max_iterations = 0;
+    int rc = hfg_em_begin(ctx, alpha, params, convergence_tol, max_iterations + 1);
+    for (int it = 0; it < max_iterations && rc == HFG_OK; it++) rc = hfg_em_enqueue(ctx, 0);
+    if (rc == HFG_OK) rc = hfg_em_enqueue(ctx, 1);
+    if (rc != HFG_OK) {
+        ctx->em_active = 0;
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
     }
-    /* final inference with the final parameters (src/hmm_flagger.c:464) */
-    if (rc == HFG_OK) {
-        rc = hfg_em_iteration(ctx, alpha, params, stats, &logliks[k], labels);
-        if (rc == HFG_OK) k++;
-    }
-    *n_esteps = k;
-    free(stats);
-    return rc;
+    return hfg_em_finish(ctx, params, logliks, n_esteps, NULL, labels);
 }
 
 /* One outer iteration of the `acceleration` branch of runHMMFlagger (src/hmm_flagger.c:344-416) up to, and excluding,
@@ -855,12 +976,12 @@ extern "C" int hfg_run_em_accelerated(hfg_ctx *ctx, const double *alpha, hfg_reg
 
 /* clock64() of thread 0 of every CTA at the six phase boundaries of the last E-step kernel: start, end of phase A,
  * arrival at the grid barrier, release, end of C1 (thread 0 only), end of phase C, arrival at the second barrier (block
- * reduction done), its release, and the SM id.  out: [grid][10]. */
+ * reduction done), its release, and the SM id.  out: [grid][12]; slots 9 and 10 of block 0: totals reduced, M-step done. */
 extern "C" int hfg_debug_phase_clocks(hfg_ctx *ctx, long long *out, int *grid) {
     if (!ctx || !out || !grid || !ctx->have_chunks) return HFG_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(out, ctx->d_phase_clock, (size_t) ctx->grid * 10 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, ctx->d_phase_clock, (size_t) ctx->grid * HFG_PC_STRIDE * sizeof(long long), cudaMemcpyDeviceToHost));
     *grid = ctx->grid;
     return HFG_OK;
 }

@@ -45,6 +45,11 @@
 
 #include "hfg_internal.h"
 
+#define HFG_HD static __device__
+#define HFG_FIT_RATE hfg_fit_rate_warp
+#include "hfg_mstep_inl.h"
+#undef HFG_HD
+
 namespace cg = cooperative_groups;
 
 /* threads per CTA: 512 when the per-thread statistics columns fit shared memory, else 256 (more mixture components /
@@ -69,6 +74,7 @@ namespace cg = cooperative_groups;
 #define RT_STRIDE(G) (RT_GAUSS + 6 * (G))
 #define HFG_INV_TERM 1e4 /* 1 / terminationProb */
 #define HFG_MAX_PEERS 8
+#define HFG_PC_STRIDE 12 /* phase-clock slots per block */
 #define HFG_MAX_TASKS 160
 /* per-(region, task) table after the Gaussian arrays: (1-a)*mu, a, 1/(var*beta0), w/sqrt(var*beta0*2*PI) */
 #define RT_TASK(G) (RT_GAUSS + 6 * (G))
@@ -108,8 +114,9 @@ struct EstepArgs {
     /* per-call inputs / scratch / outputs (device) */
     const hfg_region_params *params;
     double *tabM;  /* [n_keys][16]  transfer matrix of every key (row-major [pre][s]) */
-    double *scrF;  /* [W][4]        scaled forward f^ */
-    double *scrB;  /* [W][4]        backward message, normalised so that sum f^_{i-1} (x) b_i (.) M_i = 1 */
+    double *scrFT; /* [smax][4][capacity]  scaled forward f^, segment-transposed (written in C1, read by the same thread in C2) */
+    double *scrXB; /* [W][8]        per-window record of the statistics: f^ of the previous window, then the backward message
+                                    normalised so that sum_{pre,s} f^_{i-1}[pre] M_i[pre][s] b_i[s] = 1 */
     double *block_tot;   /* [grid][16] */
     int32_t *block_reset; /* [grid] */
     double *partials;    /* [grid][R][NSTAT] */
@@ -119,13 +126,22 @@ struct EstepArgs {
     double *posteriors;  /* [W][4] or NULL */
     int32_t *err_flags;  /* bit0 scale underflow, bit1 NaN */
     int32_t forward_only;
-    long long *phase_clock; /* [grid][10] clock64() of thread 0 at the phase boundaries + SM id (instrumentation) */
+    long long *phase_clock; /* [grid][HFG_PC_STRIDE] clock64() of thread 0 at the phase boundaries + SM id (instrumentation) */
     /* multi-GPU: in-kernel sum all-reduce of [stats | loglik | flags] over peer memory (NVLink P2P).  Every rank owns a
      * mailbox  [2 epochs][HFG_MAX_PEERS senders][out_doubles]  followed by  [2][HFG_MAX_PEERS]  arrival counters;
      * peer_box[r] is rank r's mailbox as mapped into this process (peer_box[rank] is the local one). */
     int32_t n_ranks, rank, out_doubles;
     double *peer_box[HFG_MAX_PEERS];
     unsigned long long *epoch; /* device counter of exchanges done so far (identical on every rank) */
+    /* device-resident EM loop (hfg_em_begin / hfg_em_enqueue): the parameters stay on the device and block 0 runs the
+     * M-step (HMM_estimateParameters) on the reduced statistics in the tail of the kernel, so that successive
+     * iterations are back-to-back launches with no host in between.  em_mode 0 = plain E-step, 1 = E-step + M-step
+     * (skipped entirely once the stop flag is up), 2 = final inference pass (no M-step). */
+    int32_t em_mode, model_type, em_max_logliks;
+    double em_tol;
+    hfg_region_params *em_params; /* the same memory as `params` */
+    int32_t *em_state;            /* [0] stop (converged or failed), [1] E-steps run, [2] error flags, [3] converged */
+    double *em_logliks;           /* log-likelihood of every E-step run */
 };
 
 /* statistic columns per (block, region): 16 transition counts, lambda num/den, then per Gaussian component
@@ -433,21 +449,48 @@ __device__ __forceinline__ void load_mat(const double *p, double (&M)[16]) {
             : "l"(p + 4 * q));
 }
 
+/* ---- warp-cooperative gather of the 32 transfer matrices of one window step -------------------------------------
+ * A thread-private gather (four 256-bit loads per lane) touches 32 different 128-byte lines per instruction: 128 L1
+ * wavefronts per warp and step, and the L1 wavefront queue was the kernel's top unit (profiles/).  Here four adjacent
+ * lanes read the four 32-byte quarters of ONE matrix, so an instruction touches 8 lines and the four instructions of a
+ * step 32 lines in all; the quarters go through a padded shared-memory tile (row stride 18 doubles: conflict-free for
+ * the 128-bit stores and loads) from which every lane then reads its own matrix. */
+#define HFG_STAGE_LD 18
+__device__ __forceinline__ void coop_fetch(const double *tab, uint32_t key, int lane, double (&raw)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t ks = __shfl_sync(0xffffffffu, key, q * 8 + (lane >> 2));
+        const double *p = tab + (size_t) ks * 16 + (lane & 3) * 4;
+        asm("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+            : "=d"(raw[4 * q]), "=d"(raw[4 * q + 1]), "=d"(raw[4 * q + 2]), "=d"(raw[4 * q + 3])
+            : "l"(p));
+    }
+}
+__device__ __forceinline__ void coop_deliver(double *stage, int lane, const double (&raw)[16], double (&M)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        double2 *d = reinterpret_cast<double2 *>(stage + (q * 8 + (lane >> 2)) * HFG_STAGE_LD + (lane & 3) * 4);
+        d[0] = make_double2(raw[4 * q], raw[4 * q + 1]);
+        d[1] = make_double2(raw[4 * q + 2], raw[4 * q + 3]);
+    }
+    __syncwarp();
+    const double2 *sp = reinterpret_cast<const double2 *>(stage + lane * HFG_STAGE_LD);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const double2 v = sp[i];
+        M[2 * i] = v.x;
+        M[2 * i + 1] = v.y;
+    }
+    __syncwarp();
+}
+
+/* 32-byte rows of the per-window records: 256-bit stores, and 256-bit L2 loads in the statistics phase (the records
+ * are written by other SMs before the preceding grid barrier and read once) */
 __device__ __forceinline__ void store_vec4(double *p, const double (&v)[4]) {
-    double2 *q = reinterpret_cast<double2 *>(p);
-    q[0] = make_double2(v[0], v[1]);
-    q[1] = make_double2(v[2], v[3]);
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
-__device__ __forceinline__ void load_vec4(const double *p, double (&v)[4]) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    const double2 a = q[0], b = q[1];
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-}
-/* L2 path (written by other SMs before the preceding grid barrier, read once) */
 __device__ __forceinline__ void load_vec4_cg(const double *p, double (&v)[4]) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-    const double2 a = __ldcg(q), b = __ldcg(q + 1);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
 }
 
 }  // namespace hfgk
@@ -458,6 +501,10 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
     using namespace hfgk;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double smem[];
+
+    /* device-resident EM: the previous launch raised the stop flag (converged, or a fatal condition): nothing to do.
+     * The flag is read by every thread of every block before any barrier, so the whole grid leaves together. */
+    if (A.em_mode == 1 && __ldcg(&A.em_state[0]) != 0) return;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j = blockIdx.x * THREADS + tid; /* segment owned by this thread */
@@ -540,11 +587,13 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
     }
     __syncthreads();
 
-    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 0] = clock64();
+    if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 0] = clock64();
     int nan_flag = 0, uf_flag = 0;
 
     /* =========================== phase T: emission classes and transfer matrix of every key ================== */
-    for (int p = j; p < A.n_keys; p += n_threads) {
+    /* keys (and below, statistics tiles) are dealt to warps round-robin over the blocks, 32 consecutive ones per warp */
+    const int deal0 = (warp * gridDim.x + blockIdx.x) * 32 + lane;
+    for (int p = deal0; p < A.n_keys; p += n_threads) {
         Win w = decode_word(A.kdesc[p], A.beta0);
         if (w.edge) {
             w.beta = A.kbeta[3 * (size_t) p];
@@ -606,11 +655,13 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
         for (int q = 0; q < 8; q++) dst[q] = make_double2(M[2 * q], M[2 * q + 1]);
     }
     grid.sync(); /* the key table is complete */
-    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 1] = clock64();
+    if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 1] = clock64();
 
     const int len = A.seg_len[j];
     const int seg_first = A.seg_start[j];
     const uint32_t *wk = A.wkeyT + j; /* wk[k * cap]: key word of the k-th window of this segment */
+    const int kmax = __reduce_max_sync(0xffffffffu, len); /* longest segment of this warp */
+    double *stage = acc + (size_t) warp * 32 * HFG_STAGE_LD; /* this warp's gather tile (aliases the staging area) */
 
     /* =========================== phase A: segment transfer product ============================================ */
     {
@@ -618,29 +669,32 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
         mat_identity(P);
         bool has_start = false;
         {
-            /* the key word is fetched two windows ahead, the matrix one window ahead of its use */
+            /* the key word is fetched two windows ahead, the matrices one window ahead of their use; lanes whose segment
+             * is shorter than the longest of the warp keep taking part in the cooperative gather (key 0) */
             uint32_t w0 = len > 0 ? __ldg(wk) : 0u;
             uint32_t w1 = len > 1 ? __ldg(wk + cap) : 0u;
-            double Mc[16];
-            if (len > 0) load_mat(A.tabM + (size_t) HFG_KEY_ID(w0) * 16, Mc);
-#pragma unroll 2
-            for (int k = 0; k < len; k++) {
+            double Mc[16], raw[16];
+            if (kmax > 0) {
+                coop_fetch(A.tabM, HFG_KEY_ID(w0), lane, raw);
+                coop_deliver(stage, lane, raw, Mc);
+            }
+#pragma unroll 1
+            for (int k = 0; k < kmax; k++) {
                 const uint32_t w2 = k + 2 < len ? __ldg(wk + (size_t) (k + 2) * cap) : 0u;
-                double Mn[16];
-                if (k + 1 < len) load_mat(A.tabM + (size_t) HFG_KEY_ID(w1) * 16, Mn);
-                if (w0 & HFG_KEY_CHUNK_START) has_start = true;
-                mat_mul_inplace_left(P, Mc);
-                if ((k & 3) == 3) mat_rescale(P); /* a window shrinks the product by < 1e-50: every 4th step is ample */
-                if (k + 1 < len) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) Mc[i] = Mn[i];
+                if (k + 1 < kmax) coop_fetch(A.tabM, HFG_KEY_ID(w1), lane, raw);
+                if (k < len) {
+                    if (w0 & HFG_KEY_CHUNK_START) has_start = true;
+                    mat_mul_inplace_left(P, Mc);
+                    if ((k & 3) == 3) mat_rescale(P); /* a window shrinks the product by < 1e-50: every 4th step is ample */
                 }
+                if (k + 1 < kmax) coop_deliver(stage, lane, raw, Mc);
                 w0 = w1;
                 w1 = w2;
             }
         }
         mat_rescale(P);
         if (has_start) s_reset = 1; /* benign race: every writer stores 1 */
+        __syncthreads(); /* the gather tiles of all warps are done: the area becomes the scan stash */
 
         /* ======================= phase B: scans ============================================================== */
         double S[16], Q[16];
@@ -700,9 +754,9 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
             for (int i = 0; i < 16; i++) warp_suf[lane * 16 + i] = Q[i];
         }
     }
-    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 2] = clock64();
+    if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 2] = clock64();
     grid.sync(); /* orders the block totals written above (the barrier fences) */
-    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 3] = clock64();
+    if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 3] = clock64();
 
     /* messages entering this block: the products of the blocks back to (and including) the nearest block that contains a
      * chunk start -- its product is rank-1, so nothing beyond it matters -- and, for the backward message, forward to the
@@ -826,6 +880,7 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
         mat_vec(T, u_in);
         vec_normalize(u_in);
     }
+    __syncthreads(); /* the scan stash has been read: the area holds the gather tiles again */
 
     /* =========================== phase C1: forward inside the segment ======================================== */
     double loglik = 0.0;
@@ -837,150 +892,172 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
         int cexp = 0;
         uint32_t w0 = len > 0 ? __ldg(wk) : 0u;
         uint32_t w1 = len > 1 ? __ldg(wk + cap) : 0u;
-        double Mc[16];
-        if (len > 0) load_mat(A.tabM + (size_t) HFG_KEY_ID(w0) * 16, Mc);
-#pragma unroll 2
-        for (int k = 0; k < len; k++) {
+        double Mc[16], raw[16];
+        if (kmax > 0) {
+            coop_fetch(A.tabM, HFG_KEY_ID(w0), lane, raw);
+            coop_deliver(stage, lane, raw, Mc);
+        }
+#pragma unroll 1
+        for (int k = 0; k < kmax; k++) {
             const uint32_t w2 = k + 2 < len ? __ldg(wk + (size_t) (k + 2) * cap) : 0u;
-            double Mn[16];
-            if (k + 1 < len) load_mat(A.tabM + (size_t) HFG_KEY_ID(w1) * 16, Mn);
-            const bool start = (w0 & HFG_KEY_CHUNK_START) != 0;
-            double fn[4];
-            if (start) {
-                /* EM_fillFirstColumnForward: f[0][s] = e * start probability = any row of the rank-1 matrix */
+            if (k + 1 < kmax) coop_fetch(A.tabM, HFG_KEY_ID(w1), lane, raw);
+            if (k < len) {
+                const bool start = (w0 & HFG_KEY_CHUNK_START) != 0;
+                double fn[4];
+                if (start) {
+                    /* EM_fillFirstColumnForward: f[0][s] = e * start probability = any row of the rank-1 matrix */
 #pragma unroll
-                for (int s = 0; s < 4; s++) fn[s] = Mc[s];
-            } else {
-                /* f[i][s] = sum_pre f[i-1][pre] * (tProb * eProb), preState ascending (hmm.c:386-408) */
+                    for (int s = 0; s < 4; s++) fn[s] = Mc[s];
+                } else {
+                    /* f[i][s] = sum_pre f[i-1][pre] * (tProb * eProb), preState ascending (hmm.c:386-408) */
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        double a = 0.0;
+#pragma unroll
+                        for (int pre = 0; pre < 4; pre++) a += f[pre] * Mc[pre * 4 + s];
+                        fn[s] = a;
+                    }
+                }
+                const double c = ((fn[0] + fn[1]) + fn[2]) + fn[3];
+                if (!start && c < 1e-50) uf_flag = 1; /* "scale is very low" (hmm.c:412-415) */
+                /* f^ = f / c as one correctly rounded reciprocal and four products (<= 1 ulp from the four divisions of
+                 * hmm.c:417-419) */
+                const double rc = __drcp_rn(c);
 #pragma unroll
                 for (int s = 0; s < 4; s++) {
-                    double a = 0.0;
-#pragma unroll
-                    for (int pre = 0; pre < 4; pre++) a += f[pre] * Mc[pre * 4 + s];
-                    fn[s] = a;
+                    f[s] = fn[s] * rc;
+                    A.scrFT[((size_t) k * 4 + s) * cap + j] = f[s]; /* segment-transposed: read back by this thread in C2 */
+                }
+                cprod *= c;
+                {
+                    const int hi = __double2hiint(cprod);
+                    const int e = ((hi >> 20) & 0x7ff) - 1023;
+                    cexp += e;
+                    cprod = __hiloint2double(hi - (e << 20), __double2loint(cprod));
                 }
             }
-            const double c = ((fn[0] + fn[1]) + fn[2]) + fn[3];
-            if (!start && c < 1e-50) uf_flag = 1; /* "scale is very low" (hmm.c:412-415) */
-            /* f^ = f / c as one correctly rounded reciprocal and four products (<= 1 ulp from the four divisions of
-             * hmm.c:417-419) */
-            const double rc = __drcp_rn(c);
-#pragma unroll
-            for (int s = 0; s < 4; s++) f[s] = fn[s] * rc;
-            store_vec4(A.scrF + (size_t) (seg_first + k) * 4, f);
-            cprod *= c;
-            {
-                const int hi = __double2hiint(cprod);
-                const int e = ((hi >> 20) & 0x7ff) - 1023;
-                cexp += e;
-                cprod = __hiloint2double(hi - (e << 20), __double2loint(cprod));
-            }
-            if (k + 1 < len) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) Mc[i] = Mn[i];
-            }
+            if (k + 1 < kmax) coop_deliver(stage, lane, raw, Mc);
             w0 = w1;
             w1 = w2;
         }
         loglik = log(cprod) + (double) cexp * 0.6931471805599453;
         A.seg_loglik[j] = loglik;
     }
-    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 4] = clock64(); /* thread 0's own C1 end (no barrier here) */
+    if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 4] = clock64(); /* thread 0's own C1 end (no barrier here) */
 
     /* =========================== phase C2: backward + decode ================================================= */
-    if (!A.forward_only && len > 0) {
+    if (!A.forward_only) {
         /* f[] holds f^ of the segment's last window.  b is a direction: the statistics need it only up to the per-window
-         * normalisation  sum_{pre,s} f^_{i-1}[pre] M_i[pre][s] b_i[s] = 1, the decode only up to a positive factor. */
-        double bh[4], fh[4] = {f[0], f[1], f[2], f[3]};
-        uint32_t w0 = __ldg(wk + (size_t) (len - 1) * cap);
-        uint32_t w1 = len > 1 ? __ldg(wk + (size_t) (len - 2) * cap) : 0u;
-        if (w0 & HFG_KEY_CHUNK_END) {
-            /* EM_fillLastColumnBackward (hmm.c:452-467): b = terminationProb / scale */
-            const double *rt = rtab + (size_t) HFG_OBS_REGION(A.kdesc[HFG_KEY_ID(w0)]) * rt_stride;
+         * normalisation  sum_{pre,s} f^_{i-1}[pre] M_i[pre][s] b_i[s] = 1, the decode only up to a positive factor.
+         * All lanes of the warp walk k = kmax-1 .. 0 together (cooperative gather); a lane works while k < len and its
+         * chunk start has not been passed. */
+        double bh[4] = {1.0, 1.0, 1.0, 1.0}, fh[4] = {f[0], f[1], f[2], f[3]};
+        bool done = len == 0;
+        if (len > 0) {
+            const uint32_t wl = __ldg(wk + (size_t) (len - 1) * cap);
+            if (wl & HFG_KEY_CHUNK_END) {
+                /* EM_fillLastColumnBackward (hmm.c:452-467): b = terminationProb / scale */
+                const double *rt = rtab + (size_t) HFG_OBS_REGION(__ldg(&A.kdesc[HFG_KEY_ID(wl)])) * rt_stride;
 #pragma unroll
-            for (int s = 0; s < 4; s++) bh[s] = rt[RT_TERM + s] * HFG_INV_TERM;
-        } else {
-#pragma unroll
-            for (int s = 0; s < 4; s++) bh[s] = u_in[s];
-        }
-        double Mc[16];
-        load_mat(A.tabM + (size_t) HFG_KEY_ID(w0) * 16, Mc);
-#pragma unroll 2
-        for (int k = len - 1; k >= 0; k--) {
-            const uint32_t w2 = k >= 2 ? __ldg(wk + (size_t) (k - 2) * cap) : 0u;
-            double Mn[16];
-            if (k >= 1) load_mat(A.tabM + (size_t) HFG_KEY_ID(w1) * 16, Mn);
-            const int gi = seg_first + k;
-
-            /* decode: EM_getPosterior / EM_getMostProbableState (hmm.c:671-692), first maximum (common.c:292-303) */
-            {
-                double g[4];
-#pragma unroll
-                for (int s = 0; s < 4; s++) g[s] = fh[s] * bh[s];
-                if (A.posteriors) {
-                    const double tot = ((g[0] + g[1]) + g[2]) + g[3];
-#pragma unroll
-                    for (int s = 0; s < 4; s++) {
-                        g[s] /= tot;
-                        A.posteriors[(size_t) gi * 4 + s] = g[s];
-                    }
-                }
-                /* a common positive factor does not change the order */
-                int best = 0;
-#pragma unroll
-                for (int s = 1; s < 4; s++)
-                    if (g[best] < g[s]) best = s;
-                A.labels[gi] = (int8_t) best;
-            }
-            if (w0 & HFG_KEY_CHUNK_START) break; /* first window of a chunk: nothing to the left */
-
-            /* f^ of the previous window (last window of the previous segment == the entering message) */
-            double fp[4];
-            if (k > 0) {
-                load_vec4(A.scrF + (size_t) (gi - 1) * 4, fp);
+                for (int s = 0; s < 4; s++) bh[s] = rt[RT_TERM + s] * HFG_INV_TERM;
             } else {
 #pragma unroll
-                for (int s = 0; s < 4; s++) fp[s] = v_in[s];
+                for (int s = 0; s < 4; s++) bh[s] = u_in[s];
             }
-            /* b[i-1][pre] = sum_s tProb*eProb*b[i][s] (hmm.c:493-520), then the normalisation */
-            double bn[4];
+        }
+        uint32_t w0 = kmax - 1 < len && kmax > 0 ? __ldg(wk + (size_t) (kmax - 1) * cap) : 0u;
+        uint32_t w1 = kmax - 2 < len && kmax > 1 ? __ldg(wk + (size_t) (kmax - 2) * cap) : 0u;
+        double Mc[16], raw[16];
+        if (kmax > 0) {
+            coop_fetch(A.tabM, HFG_KEY_ID(w0), lane, raw);
+            coop_deliver(stage, lane, raw, Mc);
+        }
+#pragma unroll 1
+        for (int k = kmax - 1; k >= 0; k--) {
+            const uint32_t w2 = (k >= 2 && k - 2 < len) ? __ldg(wk + (size_t) (k - 2) * cap) : 0u;
+            if (k >= 1) coop_fetch(A.tabM, HFG_KEY_ID(w1), lane, raw);
+            if (k < len && !done) {
+                const int gi = seg_first + k;
+                /* decode: EM_getPosterior / EM_getMostProbableState (hmm.c:671-692), first maximum (common.c:292-303) */
+                {
+                    double g[4];
 #pragma unroll
-            for (int pre = 0; pre < 4; pre++)
-                bn[pre] = ((Mc[pre * 4] * bh[0] + Mc[pre * 4 + 1] * bh[1]) + Mc[pre * 4 + 2] * bh[2]) + Mc[pre * 4 + 3] * bh[3];
-            const double dot = ((fp[0] * bn[0] + fp[1] * bn[1]) + fp[2] * bn[2]) + fp[3] * bn[3];
-            const double r = 1.0 / dot;
-            double bs[4];
+                    for (int s = 0; s < 4; s++) g[s] = fh[s] * bh[s];
+                    if (A.posteriors) {
+                        const double tot = ((g[0] + g[1]) + g[2]) + g[3];
 #pragma unroll
-            for (int s = 0; s < 4; s++) bs[s] = bh[s] * r;
-            store_vec4(A.scrB + (size_t) gi * 4, bs);
+                        for (int s = 0; s < 4; s++) {
+                            g[s] /= tot;
+                            A.posteriors[(size_t) gi * 4 + s] = g[s];
+                        }
+                    }
+                    /* a common positive factor does not change the order */
+                    int best = 0;
 #pragma unroll
-            for (int s = 0; s < 4; s++) {
-                bh[s] = bn[s] * r;
-                fh[s] = fp[s];
+                    for (int s = 1; s < 4; s++)
+                        if (g[best] < g[s]) best = s;
+                    A.labels[gi] = (int8_t) best;
+                }
+                if (w0 & HFG_KEY_CHUNK_START) {
+                    done = true; /* first window of a chunk: nothing to the left */
+                } else {
+                    /* f^ of the previous window (last window of the previous segment == the entering message) */
+                    double fp[4];
+                    if (k > 0) {
+#pragma unroll
+                        for (int s = 0; s < 4; s++) fp[s] = A.scrFT[((size_t) (k - 1) * 4 + s) * cap + j];
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < 4; s++) fp[s] = v_in[s];
+                    }
+                    /* b[i-1][pre] = sum_s tProb*eProb*b[i][s] (hmm.c:493-520), then the normalisation */
+                    double bn[4];
+#pragma unroll
+                    for (int pre = 0; pre < 4; pre++)
+                        bn[pre] = ((Mc[pre * 4] * bh[0] + Mc[pre * 4 + 1] * bh[1]) + Mc[pre * 4 + 2] * bh[2]) +
+                                  Mc[pre * 4 + 3] * bh[3];
+                    const double dot = ((fp[0] * bn[0] + fp[1] * bn[1]) + fp[2] * bn[2]) + fp[3] * bn[3];
+                    const double r = 1.0 / dot;
+                    double bs[4];
+#pragma unroll
+                    for (int s = 0; s < 4; s++) bs[s] = bh[s] * r;
+                    /* the window's record for the statistics: (f^ of the previous window, normalised b) */
+                    store_vec4(A.scrXB + (size_t) gi * 8, fp);
+                    store_vec4(A.scrXB + (size_t) gi * 8 + 4, bs);
+#pragma unroll
+                    for (int s = 0; s < 4; s++) {
+                        bh[s] = bn[s] * r;
+                        fh[s] = fp[s];
+                    }
+                }
             }
-            if (k >= 1) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) Mc[i] = Mn[i];
-            }
+            if (k >= 1) coop_deliver(stage, lane, raw, Mc);
             w0 = w1;
             w1 = w2;
         }
     }
+    __syncthreads(); /* gather tiles done: the area becomes the statistics columns */
     if (uf_flag) atomicOr(A.err_flags, 1);
     grid.sync(); /* f^ and b of every window are in place */
-    if (tid == 0) A.phase_clock[blockIdx.x * 10 + 5] = clock64();
+    if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 5] = clock64();
 
     /* =========================== phases S and D, region by region ============================================ */
     /* per-thread statistics live in column tid of acc: rows 0..15 transition counts, 16..17 truncated exponential,
      * 18+3g.. (meanNum, den, varNum) of Gaussian component g, last row the log-likelihood */
     double *col = acc + tid;
-    /* tiles are dealt to warps round-robin over the blocks: 32 consecutive tiles (mostly one key) per warp */
-    const int tile_lane0 = (warp * gridDim.x + blockIdx.x) * 32 + lane;
+    /* every block takes a contiguous, equal share of the tiles (they are sorted by region): a block meets one or two
+     * regions, not all R */
+    const long long n_tiles_all = A.forward_only ? 0 : __ldg(&A.region_tile_begin[HFG_MAX_REGIONS]);
+    const int blk_t0 = (int) (n_tiles_all * blockIdx.x / gridDim.x), blk_t1 = (int) (n_tiles_all * (blockIdx.x + 1) / gridDim.x);
     for (int r = 0; r < R; r++) {
+        const int t_begin = max(blk_t0, __ldg(&A.region_tile_begin[r])), t_end = min(blk_t1, __ldg(&A.region_tile_begin[r + 1]));
+        if (r > 0 && t_begin >= t_end) { /* (block-uniform) none of this region's tiles here; region 0 carries the log-likelihood */
+            for (int q = tid; q < NSTAT; q += THREADS) A.partials[((size_t) blockIdx.x * R + r) * NSTAT + q] = 0.0;
+            continue;
+        }
         for (int q = 0; q < NSTAT; q++) col[(size_t) q * LD] = 0.0;
         if (r == 0) col[(size_t) (NSTAT - 1) * LD] = loglik;
-        const int t_end = A.forward_only ? 0 : __ldg(&A.region_tile_begin[r + 1]);
-        for (int t = __ldg(&A.region_tile_begin[r]) + tile_lane0; t < t_end; t += n_threads) {
+        for (int t = t_begin + tid; t < t_end; t += THREADS) {
             const int p = __ldg(&A.tile_key[t]), lb = __ldg(&A.tile_begin[t]), ln = __ldg(&A.tile_cnt[t]);
             /* S[pre][s] = sum over the tile's windows of f^_{i-1}[pre] * b_i[s] */
             double S[16];
@@ -990,8 +1067,8 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
             for (int i = 0; i < ln; i++) {
                 const int gi = __ldg(&A.klist[lb + i]);
                 double fp[4], bb[4];
-                load_vec4_cg(A.scrF + (size_t) (gi - 1) * 4, fp);
-                load_vec4_cg(A.scrB + (size_t) gi * 4, bb);
+                load_vec4_cg(A.scrXB + (size_t) gi * 8, fp);
+                load_vec4_cg(A.scrXB + (size_t) gi * 8 + 4, bb);
 #pragma unroll
                 for (int pre = 0; pre < 4; pre++)
 #pragma unroll
@@ -1087,22 +1164,25 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
 
     /* =========================== phase D: grid reduction ===================================================== */
     {
-        if (tid == 0) A.phase_clock[blockIdx.x * 10 + 6] = clock64();
+        if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 6] = clock64();
         grid.sync();
         if (tid == 0) {
-            A.phase_clock[blockIdx.x * 10 + 7] = clock64();
+            A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 7] = clock64();
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            A.phase_clock[blockIdx.x * 10 + 8] = (long long) smid;
+            A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 8] = (long long) smid;
         }
         if (blockIdx.x == 0) {
             const int SD = (int) (sizeof(hfg_region_stats) / sizeof(double));
             const int nb = gridDim.x;
-            for (int q = tid; q < R * NSTAT; q += THREADS) {
-                const int r = q / NSTAT, st = q % NSTAT;
+            /* one warp per total: the lanes add the blocks' partials with stride 32 (loads in flight together), then a
+             * fixed xor-shuffle tree -- the same association on every run */
+            for (int q = warp; q < R * NSTAT; q += WARPS) {
                 double sum = 0.0;
-                for (int b = 0; b < nb; b++) sum += __ldcg(&A.partials[((size_t) b * R + r) * NSTAT + st]);
-                acc[q] = sum; /* reuse shared memory: [R][NSTAT] totals */
+                for (int b = lane; b < nb; b += 32) sum += __ldcg(&A.partials[(size_t) b * R * NSTAT + q]);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                if (lane == 0) acc[q] = sum; /* reuse shared memory: [R][NSTAT] totals */
             }
             for (int q = tid; q < R * SD; q += THREADS) A.out[q] = 0.0;
             __syncthreads();
@@ -1200,6 +1280,67 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                 if (tid == 0) {
                     if (__ldcg(A.err_flags) & 4) A.out[n - 1] = (double) ((int) A.out[n - 1] | 4);
                     *A.epoch = e;
+                }
+            }
+
+            /* ---- device-resident EM: M-step of every region (one thread each), bookkeeping ------------------------ */
+            if (tid == 0) A.phase_clock[9] = clock64(); /* block 0: totals reduced (and exchanged) */
+            if (A.em_mode) {
+                __syncthreads();
+                const int flags = (int) A.out[(size_t) R * SD + 1];
+                int settled = 1;
+                if (A.em_mode == 1 && flags == 0) {
+                    /* Three warps per region -- Gaussian parameters, rate fit (warp-parallel), transition rows: disjoint
+                     * parameters -- on a shared-memory copy of the region's parameters and statistics (the M-step is a
+                     * chain of dependent loads, divisions and stores).  Every lane of a warp computes and stores the
+                     * same values. */
+                    constexpr int PD = (int) (sizeof(hfg_region_params) / sizeof(double));
+                    constexpr int GROUPS = WARPS / 3;
+                    const int grp = warp / 3, role = warp % 3;
+                    for (int r0 = 0; r0 < R; r0 += GROUPS) {
+                        const int r = r0 + grp;
+                        const bool mine = grp < GROUPS && r < R;
+                        double *mp = acc + (size_t) grp * (PD + SD);
+                        double *gp = reinterpret_cast<double *>(&A.em_params[mine ? r : 0]);
+                        if (mine) {
+                            for (int i = role * 32 + lane; i < PD; i += 96) mp[i] = gp[i];
+                            for (int i = role * 32 + lane; i < SD; i += 96) mp[PD + i] = A.out[(size_t) r * SD + i];
+                        }
+                        __syncthreads();
+                        if (mine) {
+                            hfg_region_params *p = reinterpret_cast<hfg_region_params *>(mp);
+                            const hfg_region_stats *st = reinterpret_cast<const hfg_region_stats *>(mp + PD);
+                            if (role == 0) settled &= hfg_mstep_rate(A.model_type, p, st, A.em_tol);
+                            else if (role == 1) settled &= hfg_mstep_gauss(A.model_type, A.ncomp, p, st, A.em_tol);
+                            else settled &= hfg_mstep_trans(p, st, A.em_tol);
+                        }
+                        __syncthreads();
+                        if (mine) {
+                            /* the truncation point follows the NEW Hap mean, after the fit used the old one */
+                            if (role == 0 && lane == 0 && A.model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN)
+                                mp[1] = reinterpret_cast<hfg_region_params *>(mp)->mean[HFG_STATE_HAP][0] * TRUNC_POINT_FRACTION;
+                            __syncwarp();
+                        }
+                        __syncthreads();
+                        if (mine)
+                            for (int i = role * 32 + lane; i < PD; i += 96) gp[i] = mp[i];
+                        __syncthreads();
+                    }
+                }
+                const int all_settled = __syncthreads_and(settled);
+                if (tid == 0) {
+                    const int k = A.em_state[1];
+                    if (k < A.em_max_logliks) A.em_logliks[k] = A.out[(size_t) R * SD];
+                    A.em_state[1] = k + 1;
+                    if (flags) {
+                        A.em_state[2] |= flags;
+                        A.em_state[0] = 1;
+                    } else if (A.em_mode == 1 && all_settled) {
+                        A.em_state[3] = 1;
+                        A.em_state[0] = 1;
+                    }
+                    *A.err_flags = 0; /* for the next launch of the loop */
+                    A.phase_clock[10] = clock64(); /* block 0: M-step done */
                 }
             }
         }

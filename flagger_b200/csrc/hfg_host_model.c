@@ -10,20 +10,13 @@
 
 #include "hfg_internal.h"
 
-#define MIN_COUNT_FOR_UPDATE 10.0  /* hmm_utils.h:11 */
-#define TRUNC_POINT_FRACTION 0.25  /* hmm_utils.h:12 */
+#define HFG_HD static inline
+#include "hfg_mstep_inl.h"
+
 #define INITIAL_DIAG_PROB 0.99     /* hmm.c:15 */
-#define PSEUDO_COUNT 0.001         /* hmm.c:16 */
-#define GOLDEN_TOL 1e-6            /* hmm_utils.c:86 */
 
 static int gaussian_state(const hfg_config *cfg, int s) {
     return !(cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && s == HFG_STATE_ERR);
-}
-
-/* mean/var binding coefficient of component c of state s (hmm_utils.c:191-238): Err 0.1, Dup 0.5, Hap 1, Col 2,3,.. */
-static double binding(int s, int c) {
-    static const double single[3] = {0.1, 0.5, 1.0};
-    return s < HFG_STATE_COL ? single[s] : 2.0 + 1.0 * c;
 }
 
 int hfg_best_num_collapsed_comps(int max_coverage, const int32_t *region_coverages, int n_regions) {
@@ -78,108 +71,12 @@ int hfg_model_init(const hfg_config *cfg, const int32_t *region_coverages, int w
     return HFG_OK;
 }
 
-/* log-likelihood of the truncated exponential as a function of the rate (hmm_utils.c:949-956) */
-static double trunc_exp_objective(double rate, double trunc, double sum_x, double sum_w) {
-    return sum_w * log(rate) - sum_w * log(1.0 - exp(-rate * trunc)) - sum_x * rate;
-}
-
-/* golden-section maximiser on (0, trunc] (hmm_utils.c:969-1011) */
-static double fit_rate(double trunc, double sum_x, double sum_w) {
-    const double inv_phi = (sqrt(5.0) - 1.0) / 2.0, inv_phi2 = (3.0 - sqrt(5.0)) / 2.0;
-    double lo = 0.0, hi = trunc, span = hi - lo;
-    if (span <= GOLDEN_TOL) return (hi + lo) / 2.0;
-    const int steps = (int) ceil(log(GOLDEN_TOL / span) / log(inv_phi));
-    double x1 = lo + inv_phi2 * span, x2 = lo + inv_phi * span;
-    double y1 = trunc_exp_objective(x1, trunc, sum_x, sum_w), y2 = trunc_exp_objective(x2, trunc, sum_x, sum_w);
-    for (int k = 0; k < steps - 1; k++) {
-        span = inv_phi * span;
-        if (y1 > y2) {
-            hi = x2; x2 = x1; y2 = y1;
-            x1 = lo + inv_phi2 * span;
-            y1 = trunc_exp_objective(x1, trunc, sum_x, sum_w);
-        } else {
-            lo = x1; x1 = x2; y1 = y2;
-            x2 = lo + inv_phi * span;
-            y2 = trunc_exp_objective(x2, trunc, sum_x, sum_w);
-        }
-    }
-    return y1 > y2 ? (lo + x2) / 2.0 : (x1 + hi) / 2.0;
-}
-
-/* relative-change test of Gaussian_updateParameter / TruncExponential_updateParameter (hmm_utils.c:855-858,1051-1053) */
-static int settled(double before, double after, double tol, double floor_) {
-    const double change = floor_ < before ? fabs(after / before - 1.0) : 0.0;
-    return change < tol;
-}
-
 int hfg_mstep(const hfg_config *cfg, hfg_region_params *params, const hfg_region_stats *stats,
               double convergence_tol, int *converged) {
     if (!cfg || !params || !stats || !converged) return HFG_ERR_INVALID;
     int all_settled = 1;
-    for (int r = 0; r < cfg->n_regions; r++) {
-        hfg_region_params *p = &params[r];
-        const hfg_region_stats *st = &stats[r];
-
-        /* mean, then variance: ONE pooled ("bound") estimate shared by every Gaussian component through its binding
-         * coefficient (EmissionDistSeries_getBoundParameterEstimator / _estimateOneParameterType, hmm_utils.c:1791-1858) */
-        for (int which = 0; which < 2; which++) {
-            const double (*num)[HFG_MAX_COMPS] = which == 0 ? st->mean_num : st->var_num;
-            const double (*den)[HFG_MAX_COMPS] = which == 0 ? st->mean_den : st->var_den;
-            double (*dst)[HFG_MAX_COMPS] = which == 0 ? p->mean : p->var;
-            double pooled_num = 0.0, pooled_den = 0.0;
-            for (int s = 0; s < HFG_NS; s++) {
-                if (!gaussian_state(cfg, s)) continue;
-                for (int c = 0; c < cfg->n_comps[s]; c++) {
-                    pooled_num += num[s][c] / binding(s, c);
-                    pooled_den += den[s][c];
-                }
-            }
-            if (!(MIN_COUNT_FOR_UPDATE < pooled_den)) continue; /* hmm_utils.c:1846 */
-            const double unit = pooled_num / pooled_den;
-            for (int s = 0; s < HFG_NS; s++) {
-                if (!gaussian_state(cfg, s)) continue;
-                for (int c = 0; c < cfg->n_comps[s]; c++) {
-                    const double v = unit * binding(s, c);
-                    all_settled &= settled(dst[s][c], v, convergence_tol, 1.0e-4);
-                    dst[s][c] = v;
-                }
-            }
-        }
-        /* mixture weights: unbound, each component from its own estimator (binding coefficient 0) */
-        for (int s = 0; s < HFG_NS; s++) {
-            if (!gaussian_state(cfg, s)) continue;
-            for (int c = 0; c < cfg->n_comps[s]; c++) {
-                const double d = st->weight_den[s][c];
-                if (!(MIN_COUNT_FOR_UPDATE < d)) continue;
-                const double v = st->weight_num[s][c] / d;
-                all_settled &= settled(p->weight[s][c], v, convergence_tol, 1.0e-4);
-                p->weight[s][c] = v;
-            }
-        }
-        if (cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN) {
-            /* rate: golden-section fit against the truncation point still in force, THEN the truncation point follows
-             * the new Hap mean (hmm_utils.c:1872-1882) */
-            if (MIN_COUNT_FOR_UPDATE < st->lambda_den) {
-                const double v = fit_rate(p->trunc_point, st->lambda_num, st->lambda_den);
-                all_settled &= settled(p->lambda, v, convergence_tol, 1.0e-4);
-                p->lambda = v;
-            }
-            p->trunc_point = p->mean[HFG_STATE_HAP][0] * TRUNC_POINT_FRACTION;
-        }
-        /* transition rows (Transition_estimateTransitionMatrix, hmm_utils.c:2185-2219) */
-        for (int a = 0; a < HFG_NS; a++) {
-            double row = 0.0;
-            for (int b = 0; b < HFG_NS; b++) row += st->trans_count[a][b] + PSEUDO_COUNT;
-            for (int b = 0; b < HFG_NS; b++) {
-                const double v = (st->trans_count[a][b] + PSEUDO_COUNT) / row * (1.0 - HFG_TERM_PROB);
-                all_settled &= settled(p->trans[a][b], v, convergence_tol, 1.0e-6);
-                p->trans[a][b] = v;
-            }
-            p->trans[a][HFG_NS] = HFG_TERM_PROB;
-        }
-        for (int b = 0; b < HFG_NS; b++) p->trans[HFG_NS][b] = 1.0 / HFG_NS;
-        p->trans[HFG_NS][HFG_NS] = 0.0;
-    }
+    for (int r = 0; r < cfg->n_regions; r++)
+        all_settled &= hfg_mstep_region(cfg->model_type, cfg->n_comps, &params[r], &stats[r], convergence_tol);
     *converged = all_settled;
     return HFG_OK;
 }

@@ -180,6 +180,25 @@ int hfg_mstep(const hfg_config *cfg, hfg_region_params *params, const hfg_region
 int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,
                double convergence_tol, double *logliks, int *n_esteps, int8_t *labels);
 
+/* Device-resident EM loop: what hfg_run_em is made of.  The parameters stay in device memory between iterations and
+ * the M-step (the same code as hfg_mstep, compiled for the device) runs in the tail of the E-step kernel, so successive
+ * iterations are back-to-back kernel launches with no host round trip (the reference's loop, src/hmm_flagger.c:337-431,
+ * pays a host M-step and a thread-pool start per iteration).
+ *   hfg_em_begin    uploads alpha / parameters, clears the loop state (max_esteps = log-likelihood slots to keep);
+ *   hfg_em_enqueue  queues one iteration on the context's stream WITHOUT waiting: E-step + M-step, or with final_pass != 0
+ *                   the final inference E-step (no M-step).  Once an iteration has converged (the reference's test,
+ *                   convergence_tol) or hit a fatal condition, later non-final iterations return at once on the device;
+ *   hfg_em_finish   waits, then returns the parameters, the log-likelihood of every E-step that ran, their number,
+ *                   whether the loop converged, and (nullable) the labels of the last E-step.
+ * In a multi-GPU job (hfg_peer_connect) every rank queues the same sequence; the statistics are all-reduced inside the
+ * kernel and every rank's M-step sees identical bits. */
+int hfg_em_begin(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params, double convergence_tol, int max_esteps);
+int hfg_em_enqueue(hfg_ctx *ctx, int final_pass);
+int hfg_em_finish(hfg_ctx *ctx, hfg_region_params *params, double *logliks, int *n_esteps, int *converged, int8_t *labels);
+/* Device time (ms) of the i-th hfg_em_enqueue since hfg_em_begin (CUDA events on the context's stream around the
+ * kernel); valid after hfg_em_finish. */
+double hfg_em_enqueued_ms(hfg_ctx *ctx, int i);
+
 /* --accelerate (SQUAREM; SquareAccelerator, hmm.c:820-1098): feasibility of a parameter set (HMM_isFeasible, hmm.c:80-87),
  * the step length from three successive parameter sets (SquareAccelerator_computeRates, hmm.c:1000-1098), the
  * extrapolated + renormalised parameters for a step length (SquareAccelerator_computeValuesForModelPrime, hmm.c:921-997)
@@ -219,9 +238,12 @@ double hfg_last_estep_kernel_ms(hfg_ctx *ctx);
  * read-back of statistics (and labels). */
 double hfg_last_call_device_ms(hfg_ctx *ctx);
 
-/* Test / profiling hooks (no reference counterpart): phase timeline of the last E-step kernel ([grid][10]: eight clock64
+/* Test / profiling hooks (no reference counterpart): phase timeline of the last E-step kernel ([grid][12]: eight clock64
  * values + SM id) and the kernel's exponential applied to n host values. */
 int hfg_debug_phase_clocks(hfg_ctx *ctx, long long *out, int *grid);
+/* Benchmark hook: queues a write of `bytes` of scratch device memory on the context's stream (evicts the L2 between
+ * timed iterations of the device-resident loop). */
+int hfg_debug_l2_flush(hfg_ctx *ctx, size_t bytes);
 int hfg_debug_exp(hfg_ctx *ctx, const double *in, double *out, int n);
 /* Host-only (no GPU): self-check of the segment layout and observation-key builder for `capacity` segment slots;
  * summary[6] = {segments, windows per slot, edge windows, windows, distinct observation keys, statistics tiles}.  And EM_computeAdjustmentBeta (hmm.c:301-316) for one window of a chunk. */

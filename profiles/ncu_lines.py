@@ -10,6 +10,11 @@ hdr = rows[hi]
 col = {h: i for i, h in enumerate(hdr)}
 stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 data = []
+def fix(r):
+    # source text with embedded quotes (inline asm) is split into extra cells: merge them back into the Source column
+    extra = len(r) - len(hdr)
+    return r if extra <= 0 else [r[0], ",".join(r[1:2 + extra])] + r[2 + extra:]
+rows = rows[:hi + 1] + [fix(r) for r in rows[hi + 1:]]
 for r in rows[hi + 1:]:
     if len(r) < len(hdr) or not r[0].isdigit():
         continue

@@ -217,3 +217,39 @@ def test_large_models_use_the_smaller_cta(orc, n_regions, K):
     out2 = orc.estep(cfg, wl, synth.HIFI_ALPHA, p2)
     _check_estep(gpu, out2, wl, synth.HIFI_ALPHA, p2)
     gpu.close()
+
+
+def test_device_em_loop_stops_at_convergence_like_the_reference_loop(orc):
+    """hfg_run_em queues every iteration on the device (M-step in the kernel's tail, hfg_em_*): with a loose tolerance
+    it must stop after the same number of E-steps as the host loop of the reference (src/hmm_flagger.c:337-431) and
+    return the same parameters and labels; the hand-driven hfg_em_begin/enqueue/finish sequence must agree with it."""
+    wl = synth.small_mixed(n_regions=3, seed=5)
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=3, n_col_comps=K)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    n_seen = set()
+    for tol in (0.9, 0.5, 1e-12):
+        eo = orc.run_em(cfg, wl, synth.HIFI_ALPHA, params, 12, tol=tol)
+        pg, llg, labg = gpu.run_em(synth.HIFI_ALPHA, params, 12, tol=tol)
+        n_seen.add(len(llg))
+        assert len(llg) == len(eo["logliks"])
+        assert np.all(np.abs(llg - eo["logliks"]) <= TOL_LOGLIK * np.abs(eo["logliks"]))
+        assert np.array_equal(labg, eo["labels"])
+        assert np.allclose(_abi.params_as_flat(pg), _abi.params_as_flat(eo["params"]), rtol=1e-8, atol=0)
+    assert len(n_seen) > 1 and max(n_seen) == 13  # the loose tolerances did stop early
+    # by hand: 4 iterations + final pass, per-iteration device times available afterwards
+    gpu.em_begin(synth.HIFI_ALPHA, params, tol=1e-12, max_esteps=5)
+    for _ in range(4):
+        gpu.em_enqueue()
+    gpu.em_enqueue(final_pass=True)
+    p2, ll2, conv, lab2 = gpu.em_finish()
+    eo = orc.run_em(cfg, wl, synth.HIFI_ALPHA, params, 4, tol=1e-12)
+    assert not conv and len(ll2) == 5
+    assert np.all(np.abs(ll2 - eo["logliks"]) <= TOL_LOGLIK * np.abs(eo["logliks"]))
+    assert np.array_equal(lab2, eo["labels"])
+    assert all(gpu.em_enqueued_ms(i) > 0 for i in range(5))
+    # the posteriors of the last E-step are those of the final parameters
+    post = gpu.posteriors()
+    assert np.array_equal(post.argmax(axis=1).astype(np.int8), lab2)
+    gpu.close()
