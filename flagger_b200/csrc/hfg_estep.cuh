@@ -1184,48 +1184,32 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                 for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
                 if (lane == 0) acc[q] = sum; /* reuse shared memory: [R][NSTAT] totals */
             }
-            for (int q = tid; q < R * SD; q += THREADS) A.out[q] = 0.0;
             __syncthreads();
-            /* scatter into the hfg_region_stats layout (include/hfg.h) */
-            for (int q = tid; q < R * NSTAT; q += THREADS) {
-                const int r = q / NSTAT, st = q % NSTAT;
-                double *o = A.out + (size_t) r * SD;
-                const double v = acc[q];
+            /* the hfg_region_stats layout (include/hfg.h), one output element per thread: no zero-fill, no read-back */
+            for (int q = tid; q < R * SD; q += THREADS) {
+                const int r = q / SD, i = q % SD;
+                const double *tot = acc + (size_t) r * NSTAT;
                 const int MC = HFG_MAX_COMPS, BL = HFG_NS * HFG_MAX_COMPS;
-                if (st < 16) o[st] = v;                         /* trans_count[pre][s] */
-                else if (st == 16) o[16] = v;                   /* lambda_num */
-                else if (st == 17) o[17] = v;                   /* lambda_den */
-                else if (st == NSTAT - 1) {
-                    if (r == 0) A.out[(size_t) R * SD] = v;     /* log-likelihood */
+                double v = 0.0;
+                if (i < 18) {
+                    v = tot[i]; /* trans_count[pre][s], lambda_num, lambda_den */
                 } else {
-                    const int g = (st - 18) / 3, kind = (st - 18) % 3;
-                    int s = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        if (A.is_gauss[k] && g >= A.gbase[k] && g < A.gbase[k] + A.ncomp[k]) s = k;
-                    const int cc = g - A.gbase[s];
-                    const int at = s * MC + cc;
-                    if (kind == 0) o[18 + 0 * BL + at] = v;      /* mean_num */
-                    else if (kind == 2) o[18 + 2 * BL + at] = v; /* var_num */
-                    else {
-                        o[18 + 1 * BL + at] = v;                 /* mean_den */
-                        o[18 + 3 * BL + at] = v;                 /* var_den  (same addends, same order) */
-                        o[18 + 4 * BL + at] = v;                 /* weight_num */
+                    const int kind = (i - 18) / BL, at = (i - 18) % BL, s = at / MC, cc = at % MC;
+                    if (A.is_gauss[s] && cc < A.ncomp[s]) {
+                        const int g = A.gbase[s] + cc;
+                        if (kind == 0) v = tot[18 + 3 * g];          /* mean_num */
+                        else if (kind == 2) v = tot[18 + 3 * g + 2]; /* var_num */
+                        else if (kind < 5) v = tot[18 + 3 * g + 1];  /* mean_den = var_den = weight_num (same addends) */
+                        else {
+                            /* weight_den[s][c'] = sum over the components of s
+                             * (ParameterEstimator_incrementDenominatorForAllComps) */
+                            for (int c2 = 0; c2 < A.ncomp[s]; c2++) v += tot[18 + 3 * (A.gbase[s] + c2) + 1];
+                        }
                     }
                 }
+                A.out[q] = v;
             }
-            __syncthreads();
-            /* weight_den[s][c'] = sum over the components of s (ParameterEstimator_incrementDenominatorForAllComps) */
-            if (tid < HFG_NS * R) {
-                const int r = tid / HFG_NS, s = tid % HFG_NS;
-                if (A.is_gauss[s]) {
-                    double *o = A.out + (size_t) r * SD;
-                    const int MC = HFG_MAX_COMPS, BL = HFG_NS * HFG_MAX_COMPS;
-                    double tot = 0.0;
-                    for (int cc = 0; cc < A.ncomp[s]; cc++) tot += o[18 + 1 * BL + s * MC + cc];
-                    for (int cc = 0; cc < A.ncomp[s]; cc++) o[18 + 5 * BL + s * MC + cc] = tot;
-                }
-            }
+            if (tid == 0) A.out[(size_t) R * SD] = acc[NSTAT - 1]; /* log-likelihood (kept in region 0's row) */
             if (tid == 0) A.out[(size_t) R * SD + 1] = (double) __ldcg(A.err_flags);
 
             /* ---- fused collective: sum the block over all ranks through peer memory ------------------------------

@@ -16,6 +16,13 @@
 
 #define HFG_PACK_THREADS 16
 
+#include <time.h>
+static double lay_ms(void) {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return 1e3 * t.tv_sec + 1e-6 * t.tv_nsec;
+}
+
 /* submodules/common/common.c:142-148: min/max are int functions; double arguments are truncated at the call */
 static int imin_(int a, int b) { return a < b ? a : b; }
 static int imax_(int a, int b) { return a < b ? b : a; }
@@ -147,6 +154,7 @@ typedef struct KeyTab {
     uint32_t *word;
     uint64_t *beta_bits;
     int32_t *count;
+    int32_t *first; /* smallest global window index carrying the key */
     int32_t cap_keys;
 } KeyTab;
 
@@ -162,7 +170,8 @@ static int keytab_init(KeyTab *t, uint32_t capacity) {
     t->word = malloc(sizeof(uint32_t) * (size_t) t->cap_keys);
     t->beta_bits = malloc(sizeof(uint64_t) * (size_t) t->cap_keys);
     t->count = malloc(sizeof(int32_t) * (size_t) t->cap_keys);
-    if (!t->slots || !t->word || !t->beta_bits || !t->count) return 0;
+    t->first = malloc(sizeof(int32_t) * (size_t) t->cap_keys);
+    if (!t->slots || !t->word || !t->beta_bits || !t->count || !t->first) return 0;
     for (uint32_t i = 0; i < capacity; i++) t->slots[i].id = -1;
     t->mask = capacity - 1;
     return 1;
@@ -173,6 +182,7 @@ static void keytab_free(KeyTab *t) {
     free(t->word);
     free(t->beta_bits);
     free(t->count);
+    free(t->first);
     memset(t, 0, sizeof(*t));
 }
 
@@ -186,7 +196,9 @@ static int keytab_grow(KeyTab *t) {
     if (nb) t->beta_bits = nb;
     int32_t *nc = realloc(t->count, sizeof(int32_t) * (size_t) (capacity / 2));
     if (nc) t->count = nc;
-    if (!ns || !nw || !nb || !nc) {
+    int32_t *nf = realloc(t->first, sizeof(int32_t) * (size_t) (capacity / 2));
+    if (nf) t->first = nf;
+    if (!ns || !nw || !nb || !nc || !nf) {
         free(ns);
         return 0;
     }
@@ -205,8 +217,8 @@ static int keytab_grow(KeyTab *t) {
     return 1;
 }
 
-/* id of (word, beta_bits), inserting it when new; -1 when out of memory */
-static inline int32_t keytab_lookup(KeyTab *t, uint32_t word, uint64_t bb) {
+/* id of (word, beta_bits) seen at global window g, inserting it when new; -1 when out of memory */
+static inline int32_t keytab_lookup(KeyTab *t, uint32_t word, uint64_t bb, int32_t g) {
     uint32_t h = key_hash(word, bb) & t->mask;
     for (;;) {
         KeySlot *s = &t->slots[h];
@@ -229,62 +241,179 @@ static inline int32_t keytab_lookup(KeyTab *t, uint32_t word, uint64_t bb) {
     t->word[id] = word;
     t->beta_bits[id] = bb;
     t->count[id] = 1;
+    t->first[id] = g;
     return id;
 }
 
+/* Final key order: by region, then hottest first (their matrices share cache lines), ties by the first window that
+ * carries the key -- a function of the data alone, whatever the slicing.  One 64-bit sort key per table entry
+ * (region 6 bits | 2^28-1-count 28 bits | first window 28 bits), LSD radix sort with the old id as payload. */
 typedef struct KeyOrder {
+    uint64_t sort_key;
     int32_t old_id, count;
-    uint32_t region;
 } KeyOrder;
 
-static int key_order_cmp(const void *a, const void *b) {
-    const KeyOrder *x = a, *y = b;
-    if (x->region != y->region) return x->region < y->region ? -1 : 1;
-    if (x->count != y->count) return x->count > y->count ? -1 : 1; /* hottest first: their matrices share cache lines */
-    return x->old_id < y->old_id ? -1 : (x->old_id > y->old_id);
+static int key_order_sort(KeyOrder *a, int32_t n) {
+    KeyOrder *tmp = malloc(sizeof(KeyOrder) * (size_t) (n > 0 ? n : 1));
+    if (!tmp) return 0;
+    KeyOrder *src = a, *dst = tmp;
+    for (int shift = 0; shift < 64; shift += 8) {
+        size_t hist[257];
+        memset(hist, 0, sizeof(hist));
+        for (int32_t i = 0; i < n; i++) hist[((src[i].sort_key >> shift) & 0xff) + 1]++;
+        if (hist[((src[0].sort_key >> shift) & 0xff) + 1] == (size_t) n) continue; /* all equal in this digit */
+        for (int d = 0; d < 256; d++) hist[d + 1] += hist[d];
+        for (int32_t i = 0; i < n; i++) dst[hist[(src[i].sort_key >> shift) & 0xff]++] = src[i];
+        KeyOrder *sw = src;
+        src = dst;
+        dst = sw;
+    }
+    if (src != a) memcpy(a, src, sizeof(KeyOrder) * (size_t) n);
+    free(tmp);
+    return 1;
 }
 
 /* does the pair (previous window -> this window) enter the statistics?  (hmm.c:638-642: pairs 1->2 .. L-2->L-1) */
 static inline int key_has_stats(uint32_t word) { return !(word & (HFG_OBS_CHUNK_START | HFG_OBS_SECOND)); }
 
-/* builds wkeyT, the key tables, the per-key window lists and their tiles from obsT / edge_beta */
-static int build_keys(hfg_layout *out) {
-    const int64_t W = out->n_windows;
+/* id of (word, beta_bits) with `cnt` more windows, inserting it when new */
+static int32_t keytab_add(KeyTab *t, uint32_t word, uint64_t bb, int32_t cnt, int32_t first) {
+    const int32_t id = keytab_lookup(t, word, bb, first);
+    if (id >= 0) {
+        t->count[id] += cnt - 1;
+        if (first < t->first[id]) t->first[id] = first;
+    }
+    return id;
+}
+
+/* one slice of consecutive segments (= consecutive windows) per thread */
+typedef struct KeyJob {
+    hfg_layout *out;
+    int32_t seg_begin, seg_end;
+    int32_t *wkid;     /* [W] local key id of every window of the slice (shared array, disjoint ranges) */
+    KeyTab kt;         /* the slice's own table */
+    int32_t *final_id; /* [kt.n] local id -> final key id */
+    int32_t *fill;     /* [kt.n] local id -> next free entry of klist for this slice's windows of the key */
+    int ok;
+} KeyJob;
+
+/* pass 1: number the keys of the slice in discovery order */
+static void *keys_number_slice(void *arg) {
+    KeyJob *jb = arg;
+    hfg_layout *out = jb->out;
     const int capacity = out->capacity;
-    KeyTab kt;
-    memset(&kt, 0, sizeof(kt));
-    int32_t *wkid = malloc(sizeof(int32_t) * (size_t) W);
-    KeyOrder *order = NULL;
-    int32_t *new_id = NULL, *kbegin = NULL, *fill = NULL;
-    int ok = 0;
-    if (!wkid || !keytab_init(&kt, 1u << 15)) goto done;
-    /* pass 1: number the keys in discovery order (windows in global order: segment after segment) */
-    for (int32_t seg = 0; seg < out->n_seg; seg++) {
+    jb->ok = keytab_init(&jb->kt, 1u << 14);
+    if (!jb->ok) return NULL;
+    for (int32_t seg = jb->seg_begin; seg < jb->seg_end; seg++) {
         int64_t e = out->seg_edge_begin[seg];
         const int64_t g0 = out->seg_start[seg];
         for (int k = 0; k < out->seg_len[seg]; k++) {
             const uint32_t word = out->obsT[(size_t) k * capacity + seg] & ~HFG_OBS_CHUNK_END;
             uint64_t bb = 0;
             if (word & HFG_OBS_EDGE) memcpy(&bb, &out->edge_beta[3 * e++], sizeof(bb));
-            const int32_t id = keytab_lookup(&kt, word, bb);
-            if (id < 0) goto done;
-            wkid[g0 + k] = id;
+            const int32_t id = keytab_lookup(&jb->kt, word, bb, (int32_t) (g0 + k));
+            if (id < 0) {
+                jb->ok = 0;
+                return NULL;
+            }
+            jb->wkid[g0 + k] = id;
         }
     }
-    const int32_t P = kt.n;
+    return NULL;
+}
+
+/* pass 4: key words (segment-transposed) and the per-key window lists of the slice (ascending: windows in order) */
+static void *keys_scatter_slice(void *arg) {
+    KeyJob *jb = arg;
+    hfg_layout *out = jb->out;
+    const int capacity = out->capacity;
+    for (int32_t seg = jb->seg_begin; seg < jb->seg_end; seg++) {
+        const int64_t g0 = out->seg_start[seg];
+        for (int k = 0; k < out->seg_len[seg]; k++) {
+            const uint32_t word = out->obsT[(size_t) k * capacity + seg];
+            const int32_t lid = jb->wkid[g0 + k];
+            uint32_t kw = (uint32_t) jb->final_id[lid];
+            if (word & HFG_OBS_CHUNK_START) kw |= HFG_KEY_CHUNK_START;
+            if (word & HFG_OBS_CHUNK_END) kw |= HFG_KEY_CHUNK_END;
+            out->wkeyT[(size_t) k * capacity + seg] = kw;
+            if (key_has_stats(word)) out->klist[jb->fill[lid]++] = (int32_t) (g0 + k);
+        }
+    }
+    return NULL;
+}
+
+static void run_key_jobs(KeyJob *jobs, int n, void *(*fn)(void *)) {
+    pthread_t tids[HFG_PACK_THREADS];
+    for (int t = 1; t < n; t++)
+        if (pthread_create(&tids[t], NULL, fn, &jobs[t]) != 0) {
+            fn(&jobs[t]); /* could not spawn: do the slice here */
+            tids[t] = 0;
+        }
+    fn(&jobs[0]);
+    for (int t = 1; t < n; t++)
+        if (tids[t]) pthread_join(tids[t], NULL);
+}
+
+/* builds wkeyT, the key tables, the per-key window lists and their tiles from obsT / edge_beta */
+static int build_keys(hfg_layout *out) {
+    const int64_t W = out->n_windows;
+    const int capacity = out->capacity;
+    int n_jobs = (int) (W / 65536) + 1;
+    if (n_jobs > HFG_PACK_THREADS) n_jobs = HFG_PACK_THREADS;
+    if (n_jobs > out->n_seg) n_jobs = out->n_seg > 0 ? out->n_seg : 1;
+    KeyJob jobs[HFG_PACK_THREADS];
+    KeyTab kt;
+    memset(&kt, 0, sizeof(kt));
+    memset(jobs, 0, sizeof(jobs));
+    int32_t *wkid = malloc(sizeof(int32_t) * (size_t) W);
+    KeyOrder *order = NULL;
+    int32_t *new_id = NULL, *kbegin = NULL, *running = NULL;
+    int32_t P = 0;
+    int64_t n_list = 0, n_tiles = 0;
+    int ok = 0;
+    if (!wkid) goto done;
+    double tk[6];
+    tk[0] = lay_ms();
+    /* pass 1 (parallel): per-slice key tables */
+    for (int t = 0; t < n_jobs; t++) {
+        jobs[t].out = out;
+        jobs[t].seg_begin = (int32_t) ((int64_t) out->n_seg * t / n_jobs);
+        jobs[t].seg_end = (int32_t) ((int64_t) out->n_seg * (t + 1) / n_jobs);
+        jobs[t].wkid = wkid;
+    }
+    run_key_jobs(jobs, n_jobs, keys_number_slice);
+    for (int t = 0; t < n_jobs; t++)
+        if (!jobs[t].ok) goto done;
+    tk[1] = lay_ms();
+    /* merge the slice tables (O(#keys) each) */
+    if (!keytab_init(&kt, 1u << 15)) goto done;
+    for (int t = 0; t < n_jobs; t++) {
+        KeyTab *lt = &jobs[t].kt;
+        jobs[t].final_id = malloc(sizeof(int32_t) * (size_t) (lt->n > 0 ? lt->n : 1));
+        jobs[t].fill = malloc(sizeof(int32_t) * (size_t) (lt->n > 0 ? lt->n : 1));
+        if (!jobs[t].final_id || !jobs[t].fill) goto done;
+        for (int32_t k = 0; k < lt->n; k++) {
+            const int32_t gid = keytab_add(&kt, lt->word[k], lt->beta_bits[k], lt->count[k], lt->first[k]);
+            if (gid < 0) goto done;
+            jobs[t].final_id[k] = gid; /* merged id for now */
+        }
+    }
+    P = kt.n;
     if (P > HFG_KEY_MAX) goto done;
+    tk[2] = lay_ms();
     /* pass 2: final numbering by (region, count descending) */
     order = malloc(sizeof(KeyOrder) * (size_t) P);
     new_id = malloc(sizeof(int32_t) * (size_t) P);
     kbegin = malloc(sizeof(int32_t) * ((size_t) P + 1));
-    fill = malloc(sizeof(int32_t) * (size_t) P);
+    running = malloc(sizeof(int32_t) * (size_t) P);
     out->kdesc = malloc(sizeof(uint32_t) * (size_t) P);
     out->kbeta = malloc(sizeof(double) * 3 * (size_t) P);
-    if (!order || !new_id || !kbegin || !fill || !out->kdesc || !out->kbeta) goto done;
-    for (int32_t k = 0; k < P; k++) order[k] = (KeyOrder){k, kt.count[k], HFG_OBS_REGION(kt.word[k])};
-    qsort(order, (size_t) P, sizeof(KeyOrder), key_order_cmp);
-    int64_t n_list = 0;
-    int64_t n_tiles = 0;
+    if (!order || !new_id || !kbegin || !running || !out->kdesc || !out->kbeta) goto done;
+    for (int32_t k = 0; k < P; k++)
+        order[k] = (KeyOrder){((uint64_t) HFG_OBS_REGION(kt.word[k]) << 56) | ((uint64_t) (HFG_KEY_MAX - kt.count[k]) << 28) |
+                                  (uint64_t) kt.first[k],
+                              k, kt.count[k]};
+    if (!key_order_sort(order, P)) goto done;
     for (int32_t p = 0; p < P; p++) {
         const int32_t o = order[p].old_id;
         new_id[o] = p;
@@ -308,6 +437,7 @@ static int build_keys(hfg_layout *out) {
     out->tile_key = malloc(sizeof(int32_t) * (size_t) (n_tiles > 0 ? n_tiles : 1));
     out->tile_begin = malloc(sizeof(int32_t) * (size_t) (n_tiles > 0 ? n_tiles : 1));
     out->tile_cnt = malloc(sizeof(int32_t) * (size_t) (n_tiles > 0 ? n_tiles : 1));
+    tk[3] = lay_ms();
     out->wkeyT = calloc((size_t) out->smax * capacity, sizeof(uint32_t));
     if (!out->klist || !out->tile_key || !out->tile_begin || !out->tile_cnt || !out->wkeyT) goto done;
     /* pass 3: tiles, grouped by region because the keys are */
@@ -327,28 +457,38 @@ static int build_keys(hfg_layout *out) {
         for (int r = HFG_MAX_REGIONS - 1; r >= 0; r--)
             if (out->region_tile_begin[r] < 0) out->region_tile_begin[r] = out->region_tile_begin[r + 1];
     }
-    /* pass 4: key words (segment-transposed) and the per-key window lists (ascending: windows are visited in order) */
-    memcpy(fill, kbegin, sizeof(int32_t) * (size_t) P);
-    for (int32_t seg = 0; seg < out->n_seg; seg++) {
-        const int64_t g0 = out->seg_start[seg];
-        for (int k = 0; k < out->seg_len[seg]; k++) {
-            const uint32_t word = out->obsT[(size_t) k * capacity + seg];
-            const int32_t p = new_id[wkid[g0 + k]];
-            uint32_t kw = (uint32_t) p;
-            if (word & HFG_OBS_CHUNK_START) kw |= HFG_KEY_CHUNK_START;
-            if (word & HFG_OBS_CHUNK_END) kw |= HFG_KEY_CHUNK_END;
-            out->wkeyT[(size_t) k * capacity + seg] = kw;
-            if (key_has_stats(word)) out->klist[fill[p]++] = (int32_t) (g0 + k);
+    /* where each slice's windows of a key go in the key's list: the slices are consecutive stretches of the genome, so
+     * slice t's windows follow those of the slices before it */
+    memcpy(running, kbegin, sizeof(int32_t) * (size_t) P);
+    for (int t = 0; t < n_jobs; t++) {
+        KeyTab *lt = &jobs[t].kt;
+        for (int32_t k = 0; k < lt->n; k++) {
+            const int32_t p = new_id[jobs[t].final_id[k]];
+            jobs[t].final_id[k] = p;
+            jobs[t].fill[k] = running[p];
+            if (key_has_stats(lt->word[k])) running[p] += lt->count[k];
         }
     }
+    tk[4] = lay_ms();
+    /* pass 4 (parallel): key words and lists */
+    run_key_jobs(jobs, n_jobs, keys_scatter_slice);
+    tk[5] = lay_ms();
+    if (getenv("HFG_TIMING"))
+        fprintf(stderr, "[hfg] keys: number %.2f ms (%d slices), merge %.2f, sort+tables %.2f, alloc+tiles+offsets %.2f, scatter %.2f\n",
+                tk[1] - tk[0], n_jobs, tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4]);
     ok = 1;
 done:
+    for (int t = 0; t < n_jobs; t++) {
+        keytab_free(&jobs[t].kt);
+        free(jobs[t].final_id);
+        free(jobs[t].fill);
+    }
     keytab_free(&kt);
     free(wkid);
     free(order);
     free(new_id);
     free(kbegin);
-    free(fill);
+    free(running);
     return ok;
 }
 
@@ -363,6 +503,7 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
                      const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
                      int32_t capacity, int32_t granule, hfg_layout *out, char *err, size_t errlen) {
     memset(out, 0, sizeof(*out));
+    const double t_lay0 = lay_ms();
     int64_t W = 0;
     for (int32_t c = 0; c < n_chunks; c++) {
         if (chunks[c].n_windows <= 0 || chunks[c].offset != W || chunks[c].window_len <= 0) {
@@ -494,7 +635,11 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
         snprintf(err, errlen, "number of windows (%lld) above the %d this build addresses per device", (long long) W, HFG_KEY_MAX);
         return HFG_ERR_INVALID;
     }
+    const double t_keys0 = lay_ms();
     if (!build_keys(out)) goto nomem;
+    if (getenv("HFG_TIMING"))
+        fprintf(stderr, "[hfg] layout: segments+pack %.2f ms, keys %.2f ms (%d keys, %d tiles)\n", t_keys0 - t_lay0,
+                lay_ms() - t_keys0, out->n_keys, out->n_tiles);
     free(runs); free(edge_head); free(edge_tail); free(chunk_edge_base);
     return HFG_OK;
 nomem:

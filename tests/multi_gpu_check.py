@@ -9,7 +9,9 @@ Every rank owns a contiguous range of chunks (flagger_b200.dist.shard_chunks).  
     single-GPU run over all chunks to 1e-10 relative;
   * labels of the shard == labels of the same windows in the single-GPU run over all chunks (bit-exact);
   * the NCCL variant (hfg_em_iteration_device + dist.all_reduce) gives the same sums to 1e-12 relative;
-  * forward-only passes (SQUAREM) sum the log-likelihood the same way.
+  * forward-only passes (SQUAREM) sum the log-likelihood the same way;
+  * the device-resident EM loop (hfg_run_em: M-step in the kernel tail on the all-reduced statistics) ends with the same
+    parameters on every rank (bitwise), and with the log-likelihoods / labels of the single-GPU loop.
 Prints "MULTI_GPU_CHECK OK ranks=N" on rank 0."""
 import argparse
 import os
@@ -54,6 +56,7 @@ def main():
     cfg["device"] = local
     alpha = synth.HIFI_ALPHA
     params = api.model_init(cfg, wl_full.region_coverages, wl_full.window_len)
+    params0 = params.copy()
     b = hdist.shard_bounds(wl_full.chunks["n_windows"], world)
     wl = hdist.shard_chunks(wl_full, rank, world)
     lo = int(wl_full.chunks["offset"][b[rank]]) if wl.n_chunks else 0
@@ -102,6 +105,16 @@ def main():
         llf = fused.forward_only(alpha, params)
         check(close([llf], [ll_f], 1e-13), f"iter {it}: fused forward-only log-likelihood {llf} != {ll_f}")
         params, _ = api.mstep(cfg, params, s_f, tol=1e-12)
+    # device-resident EM loop over the ranks
+    p_all, ll_loop_all, lab_loop_all = solo_all.run_em(alpha, params0, args.iters, tol=1e-12)
+    p_f, ll_loop_f, lab_loop_f = fused.run_em(alpha, params0, args.iters, tol=1e-12)
+    pf = torch.from_numpy(_abi.params_as_flat(p_f).copy()).to(dev)
+    g = [torch.zeros_like(pf) for _ in range(world)]
+    dist.all_gather(g, pf)
+    check(all(torch.equal(g[0], x) for x in g), "device EM loop: parameters differ between ranks")
+    check(len(ll_loop_f) == args.iters + 1 and close(ll_loop_f, ll_loop_all, 1e-10), "device EM loop: log-likelihoods differ")
+    check(close(_abi.params_as_flat(p_f), _abi.params_as_flat(p_all), 1e-8), "device EM loop: parameters != single-GPU loop")
+    check(np.array_equal(lab_loop_f, lab_loop_all[lo:lo + wl.n_windows]), "device EM loop: shard labels differ")
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     for g_ in (fused, solo_own, solo_all):
