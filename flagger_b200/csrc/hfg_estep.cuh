@@ -119,7 +119,7 @@ struct EstepArgs {
                                     normalised so that sum_{pre,s} f^_{i-1}[pre] M_i[pre][s] b_i[s] = 1 */
     double *block_tot;   /* [grid][16] */
     int32_t *block_reset; /* [grid] */
-    double *partials;    /* [grid][R][NSTAT] */
+    double *partials;    /* [R][NSTAT][grid] */
     double *out;         /* [R * sizeof(hfg_region_stats)/8 + 2]: stats | loglik | error flags (as double) */
     double *seg_loglik;  /* [capacity] */
     int8_t *labels;      /* [W] */
@@ -489,8 +489,15 @@ __device__ __forceinline__ void coop_deliver(double *stage, int lane, const doub
 __device__ __forceinline__ void store_vec4(double *p, const double (&v)[4]) {
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
 }
-__device__ __forceinline__ void load_vec4_cg(const double *p, double (&v)[4]) {
-    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p) : "memory");
+/* `after` is a value produced behind the grid barrier that precedes the reads (hfgk::fence_token): the load is an ordinary
+ * (non-volatile) asm, so the compiler may batch several of them, but none can move above the barrier */
+__device__ __forceinline__ void load_vec4_cg(const double *p, unsigned after, double (&v)[4]) {
+    asm("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p + after));
+}
+__device__ __forceinline__ unsigned fence_token() {
+    unsigned t;
+    asm volatile("mov.u32 %0, 0;" : "=r"(t)::"memory");
+    return t;
 }
 
 }  // namespace hfgk
@@ -539,7 +546,8 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
         for (int s = 0; s < 4; s++)
             rtab[(size_t) r * rt_stride + RT_TC + mask * 16 + pre * 4 + s] = valid[s] ? p.trans[pre][s] / tot : 0.0;
     }
-    for (int idx = tid; idx < R * (12 + G); idx += THREADS) {
+    /* (the three table loops start on different warps so that, for few regions, they run side by side) */
+    for (int idx = (tid + THREADS - 64) % THREADS; idx < R * (12 + G); idx += THREADS) {
         const int r = idx / (12 + G), q = idx % (12 + G);
         const hfg_region_params &p = A.params[r];
         double *rt = rtab + (size_t) r * rt_stride;
@@ -573,7 +581,7 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
             ga[5 * G + g] = p.weight[s][c] / sqrt(vb * 2 * HFG_PI);
         }
     }
-    for (int idx = tid; idx < R * A.n_tasks; idx += THREADS) {
+    for (int idx = (tid + THREADS - 128) % THREADS; idx < R * A.n_tasks; idx += THREADS) {
         const int r = idx / A.n_tasks, t = idx % A.n_tasks;
         const hfg_region_params &p = A.params[r];
         const int d = A.task_class[t], c = A.task_comp[t], s = A.class_state[d];
@@ -951,8 +959,28 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
          * normalisation  sum_{pre,s} f^_{i-1}[pre] M_i[pre][s] b_i[s] = 1, the decode only up to a positive factor.
          * All lanes of the warp walk k = kmax-1 .. 0 together (cooperative gather); a lane works while k < len and its
          * chunk start has not been passed. */
-        double bh[4] = {1.0, 1.0, 1.0, 1.0}, fh[4] = {f[0], f[1], f[2], f[3]};
+        double bh[4] = {1.0, 1.0, 1.0, 1.0};
         bool done = len == 0;
+        /* decode of one window: EM_getPosterior / EM_getMostProbableState (hmm.c:671-692), first maximum
+         * (common.c:292-303); a common positive factor of b does not change the order */
+        auto decode = [&](const double (&fw)[4], const double (&bw)[4], int gi) {
+            double g[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) g[s] = fw[s] * bw[s];
+            if (A.posteriors) {
+                const double tot = ((g[0] + g[1]) + g[2]) + g[3];
+#pragma unroll
+                for (int s = 0; s < 4; s++) {
+                    g[s] /= tot;
+                    A.posteriors[(size_t) gi * 4 + s] = g[s];
+                }
+            }
+            int best = 0;
+#pragma unroll
+            for (int s = 1; s < 4; s++)
+                if (g[best] < g[s]) best = s;
+            A.labels[gi] = (int8_t) best;
+        };
         if (len > 0) {
             const uint32_t wl = __ldg(wk + (size_t) (len - 1) * cap);
             if (wl & HFG_KEY_CHUNK_END) {
@@ -964,6 +992,8 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
 #pragma unroll
                 for (int s = 0; s < 4; s++) bh[s] = u_in[s];
             }
+            decode(f, bh, seg_first + len - 1); /* the segment's last window; every other window is decoded at the end of
+                                                   the step that produces its b */
         }
         uint32_t w0 = kmax - 1 < len && kmax > 0 ? __ldg(wk + (size_t) (kmax - 1) * cap) : 0u;
         uint32_t w1 = kmax - 2 < len && kmax > 1 ? __ldg(wk + (size_t) (kmax - 2) * cap) : 0u;
@@ -972,32 +1002,24 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
             coop_fetch(A.tabM, HFG_KEY_ID(w0), lane, raw);
             coop_deliver(stage, lane, raw, Mc);
         }
+        /* f^ of window k-1 is fetched one step ahead of its use as well (it feeds the normalisation, the head of the
+         * step's dependent chain) */
+        double fq[4] = {0.0, 0.0, 0.0, 0.0};
+        if (kmax >= 2 && kmax - 2 < len) {
+#pragma unroll
+            for (int s = 0; s < 4; s++) fq[s] = A.scrFT[((size_t) (kmax - 2) * 4 + s) * cap + j];
+        }
 #pragma unroll 1
         for (int k = kmax - 1; k >= 0; k--) {
             const uint32_t w2 = (k >= 2 && k - 2 < len) ? __ldg(wk + (size_t) (k - 2) * cap) : 0u;
             if (k >= 1) coop_fetch(A.tabM, HFG_KEY_ID(w1), lane, raw);
+            double fq_next[4] = {0.0, 0.0, 0.0, 0.0}; /* f^ of window k-2, for the next step */
+            if (k >= 2 && k - 2 < len) {
+#pragma unroll
+                for (int s = 0; s < 4; s++) fq_next[s] = A.scrFT[((size_t) (k - 2) * 4 + s) * cap + j];
+            }
             if (k < len && !done) {
                 const int gi = seg_first + k;
-                /* decode: EM_getPosterior / EM_getMostProbableState (hmm.c:671-692), first maximum (common.c:292-303) */
-                {
-                    double g[4];
-#pragma unroll
-                    for (int s = 0; s < 4; s++) g[s] = fh[s] * bh[s];
-                    if (A.posteriors) {
-                        const double tot = ((g[0] + g[1]) + g[2]) + g[3];
-#pragma unroll
-                        for (int s = 0; s < 4; s++) {
-                            g[s] /= tot;
-                            A.posteriors[(size_t) gi * 4 + s] = g[s];
-                        }
-                    }
-                    /* a common positive factor does not change the order */
-                    int best = 0;
-#pragma unroll
-                    for (int s = 1; s < 4; s++)
-                        if (g[best] < g[s]) best = s;
-                    A.labels[gi] = (int8_t) best;
-                }
                 if (w0 & HFG_KEY_CHUNK_START) {
                     done = true; /* first window of a chunk: nothing to the left */
                 } else {
@@ -1005,7 +1027,7 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                     double fp[4];
                     if (k > 0) {
 #pragma unroll
-                        for (int s = 0; s < 4; s++) fp[s] = A.scrFT[((size_t) (k - 1) * 4 + s) * cap + j];
+                        for (int s = 0; s < 4; s++) fp[s] = fq[s];
                     } else {
 #pragma unroll
                         for (int s = 0; s < 4; s++) fp[s] = v_in[s];
@@ -1025,13 +1047,13 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                     store_vec4(A.scrXB + (size_t) gi * 8, fp);
                     store_vec4(A.scrXB + (size_t) gi * 8 + 4, bs);
 #pragma unroll
-                    for (int s = 0; s < 4; s++) {
-                        bh[s] = bn[s] * r;
-                        fh[s] = fp[s];
-                    }
+                    for (int s = 0; s < 4; s++) bh[s] = bn[s] * r;
+                    if (k > 0) decode(fp, bh, gi - 1);
                 }
             }
             if (k >= 1) coop_deliver(stage, lane, raw, Mc);
+#pragma unroll
+            for (int s = 0; s < 4; s++) fq[s] = fq_next[s];
             w0 = w1;
             w1 = w2;
         }
@@ -1040,6 +1062,7 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
     if (uf_flag) atomicOr(A.err_flags, 1);
     grid.sync(); /* f^ and b of every window are in place */
     if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 5] = clock64();
+    const unsigned tok = fence_token();
 
     /* =========================== phases S and D, region by region ============================================ */
     /* per-thread statistics live in column tid of acc: rows 0..15 transition counts, 16..17 truncated exponential,
@@ -1052,27 +1075,34 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
     for (int r = 0; r < R; r++) {
         const int t_begin = max(blk_t0, __ldg(&A.region_tile_begin[r])), t_end = min(blk_t1, __ldg(&A.region_tile_begin[r + 1]));
         if (r > 0 && t_begin >= t_end) { /* (block-uniform) none of this region's tiles here; region 0 carries the log-likelihood */
-            for (int q = tid; q < NSTAT; q += THREADS) A.partials[((size_t) blockIdx.x * R + r) * NSTAT + q] = 0.0;
+            for (int q = tid; q < NSTAT; q += THREADS) A.partials[((size_t) r * NSTAT + q) * gridDim.x + blockIdx.x] = 0.0;
             continue;
         }
         for (int q = 0; q < NSTAT; q++) col[(size_t) q * LD] = 0.0;
         if (r == 0) col[(size_t) (NSTAT - 1) * LD] = loglik;
         for (int t = t_begin + tid; t < t_end; t += THREADS) {
             const int p = __ldg(&A.tile_key[t]), lb = __ldg(&A.tile_begin[t]), ln = __ldg(&A.tile_cnt[t]);
-            /* S[pre][s] = sum over the tile's windows of f^_{i-1}[pre] * b_i[s] */
+            /* S[pre][s] = sum over the tile's windows of f^_{i-1}[pre] * b_i[s]; two windows' records in flight */
             double S[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) S[i] = 0.0;
-#pragma unroll 4
-            for (int i = 0; i < ln; i++) {
-                const int gi = __ldg(&A.klist[lb + i]);
-                double fp[4], bb[4];
-                load_vec4_cg(A.scrXB + (size_t) gi * 8, fp);
-                load_vec4_cg(A.scrXB + (size_t) gi * 8 + 4, bb);
+            for (int i0 = 0; i0 < ln; i0 += 2) {
+                double fp[2][4], bb[2][4];
 #pragma unroll
-                for (int pre = 0; pre < 4; pre++)
+                for (int u = 0; u < 2; u++) {
+                    const int gi = __ldg(&A.klist[lb + min(i0 + u, ln - 1)]);
+                    load_vec4_cg(A.scrXB + (size_t) gi * 8, tok, fp[u]);
+                    load_vec4_cg(A.scrXB + (size_t) gi * 8 + 4, tok, bb[u]);
+                }
 #pragma unroll
-                    for (int s = 0; s < 4; s++) S[pre * 4 + s] = fma(fp[pre], bb[s], S[pre * 4 + s]);
+                for (int u = 0; u < 2; u++) {
+                    if (i0 + u < ln) {
+#pragma unroll
+                        for (int pre = 0; pre < 4; pre++)
+#pragma unroll
+                            for (int s = 0; s < 4; s++) S[pre * 4 + s] = fma(fp[u][pre], bb[u][s], S[pre * 4 + s]);
+                    }
+                }
             }
             Win w = decode_word(__ldg(&A.kdesc[p]), A.beta0);
             if (w.edge) {
@@ -1156,7 +1186,7 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
             for (int t = lane; t < THREADS; t += 32) sum += cl[t];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-            if (lane == 0) A.partials[((size_t) blockIdx.x * R + r) * NSTAT + q] = sum;
+            if (lane == 0) A.partials[((size_t) r * NSTAT + q) * gridDim.x + blockIdx.x] = sum; /* [R][NSTAT][grid] */
         }
         __syncthreads();
     }
@@ -1175,16 +1205,40 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
         if (blockIdx.x == 0) {
             const int SD = (int) (sizeof(hfg_region_stats) / sizeof(double));
             const int nb = gridDim.x;
-            /* one warp per total: the lanes add the blocks' partials with stride 32 (loads in flight together), then a
-             * fixed xor-shuffle tree -- the same association on every run */
-            for (int q = warp; q < R * NSTAT; q += WARPS) {
-                double sum = 0.0;
-                for (int b = lane; b < nb; b += 32) sum += __ldcg(&A.partials[(size_t) b * R * NSTAT + q]);
+            /* four totals per warp at a time: the lanes add the blocks' partials with stride 32 (all loads of a round are
+             * independent and in flight together), then a fixed xor-shuffle tree -- the same association on every run */
+            {
+                constexpr int QU = 4;
+                const int NQ = R * NSTAT;
+                for (int q0 = warp * QU; q0 < NQ; q0 += WARPS * QU) {
+                    double sum[QU];
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-                if (lane == 0) acc[q] = sum; /* reuse shared memory: [R][NSTAT] totals */
+                    for (int u = 0; u < QU; u++) sum[u] = 0.0;
+                    /* up to 5 x QU loads per lane issued before the first add (grids of up to 160 blocks in one go) */
+                    for (int b0 = 0; b0 < nb; b0 += 160) {
+                        double v[5][QU];
+#pragma unroll
+                        for (int i = 0; i < 5; i++) {
+                            const int b = b0 + 32 * i + lane;
+#pragma unroll
+                            for (int u = 0; u < QU; u++)
+                                v[i][u] = (b < nb && q0 + u < NQ) ? __ldcg(&A.partials[(size_t) (q0 + u) * nb + b]) : 0.0;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 5; i++)
+#pragma unroll
+                            for (int u = 0; u < QU; u++) sum[u] += v[i][u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < QU; u++) {
+#pragma unroll
+                        for (int off = 16; off > 0; off >>= 1) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], off);
+                        if (lane == 0 && q0 + u < NQ) acc[q0 + u] = sum[u]; /* reuse shared memory: [R][NSTAT] totals */
+                    }
+                }
             }
             __syncthreads();
+            if (tid == 0) A.phase_clock[11] = clock64(); /* block 0: grid totals in shared memory */
             /* the hfg_region_stats layout (include/hfg.h), one output element per thread: no zero-fill, no read-back */
             for (int q = tid; q < R * SD; q += THREADS) {
                 const int r = q / SD, i = q % SD;

@@ -46,7 +46,8 @@ extern "C" {
  * depends only on (x, px, region, validity mask, region change, chunk start, beta).  The host numbers the distinct
  * combinations ("keys", hottest first inside a region); the kernel evaluates emissions and M once per KEY and per
  * E-step, the windows gather M by key id, and the pair statistics are accumulated per key (lists of the windows of
- * each key, cut into tiles of <= HFG_TILE windows).  Per-window key word, stored segment-transposed:
+ * each key, cut into tiles of HFG_TILE windows, or longer ones when that
+ * leaves every thread of the grid at most one tile).  Per-window key word, stored segment-transposed:
  *  bits 0..27  key id      bit 30  last window of a chunk      bit 31  first window of a chunk */
 #define HFG_KEY_ID(w) ((w) & 0x0fffffffu)
 #define HFG_KEY_MAX 0x0fffffff
@@ -73,7 +74,7 @@ typedef struct hfg_layout {
     int32_t *klist;          /* [n_list] global window indices grouped by key, ascending inside a key; windows whose pair
                                 is skipped by the statistics (chunk starts, second windows) are not listed */
     int32_t n_tiles;
-    int32_t *tile_key, *tile_begin, *tile_cnt; /* [n_tiles] <= HFG_TILE consecutive entries of klist, all of one key */
+    int32_t *tile_key, *tile_begin, *tile_cnt; /* [n_tiles] consecutive entries of klist (at most 4 * HFG_TILE), all of one key */
     int32_t region_tile_begin[HFG_MAX_REGIONS + 1]; /* tiles are grouped by region */
     int32_t *seg_start;      /* [capacity] global index of the segment's first window (0 for idle slots) */
     int32_t *seg_len;        /* [capacity] 0 for idle slots */

@@ -424,10 +424,16 @@ static int build_keys(hfg_layout *out) {
         out->kbeta[3 * p + 1] = (kt.word[o] & HFG_OBS_EDGE) ? out->beta0 / b : 1.0;
         out->kbeta[3 * p + 2] = (kt.word[o] & HFG_OBS_EDGE) ? sqrt(out->beta0 / b) : 1.0;
         kbegin[p] = (int32_t) n_list;
-        if (key_has_stats(kt.word[o])) {
-            n_list += order[p].count;
-            n_tiles += (order[p].count + HFG_TILE - 1) / HFG_TILE;
-        }
+        if (key_has_stats(kt.word[o])) n_list += order[p].count;
+    }
+    /* tile length: HFG_TILE, or the shortest one for which every thread of the grid gets at most ONE tile (a block whose
+     * share is a few tiles over its thread count would spend a second round on them) */
+    int tile_len = HFG_TILE;
+    for (;; tile_len++) {
+        n_tiles = 0;
+        for (int32_t p = 0; p < P; p++)
+            if (key_has_stats(out->kdesc[p])) n_tiles += (order[p].count + tile_len - 1) / tile_len;
+        if (n_tiles <= (int64_t) capacity - capacity / 16 || tile_len >= 4 * HFG_TILE) break;
     }
     kbegin[P] = (int32_t) n_list;
     out->n_keys = P;
@@ -447,10 +453,10 @@ static int build_keys(hfg_layout *out) {
         for (int32_t p = 0; p < P; p++) {
             const int r = (int) HFG_OBS_REGION(out->kdesc[p]);
             if (out->region_tile_begin[r] < 0) out->region_tile_begin[r] = t;
-            for (int32_t b = kbegin[p]; b < kbegin[p + 1]; b += HFG_TILE, t++) {
+            for (int32_t b = kbegin[p]; b < kbegin[p + 1]; b += tile_len, t++) {
                 out->tile_key[t] = p;
                 out->tile_begin[t] = b;
-                out->tile_cnt[t] = kbegin[p + 1] - b < HFG_TILE ? kbegin[p + 1] - b : HFG_TILE;
+                out->tile_cnt[t] = kbegin[p + 1] - b < tile_len ? kbegin[p + 1] - b : tile_len;
             }
         }
         out->region_tile_begin[HFG_MAX_REGIONS] = t;
@@ -747,7 +753,7 @@ int hfg_debug_layout_check(const hfg_config *cfg, int32_t n_chunks, const hfg_ch
         int32_t at = 0, last_region = -1;
         for (int32_t t = 0; t < l.n_tiles && !bad; t++) {
             const int32_t p = l.tile_key[t];
-            if (p < 0 || p >= l.n_keys || l.tile_begin[t] != at || l.tile_cnt[t] < 1 || l.tile_cnt[t] > HFG_TILE) { bad = 1; break; }
+            if (p < 0 || p >= l.n_keys || l.tile_begin[t] != at || l.tile_cnt[t] < 1 || l.tile_cnt[t] > 4 * HFG_TILE) { bad = 1; break; }
             const int32_t r = (int32_t) HFG_OBS_REGION(l.kdesc[p]);
             if (r < last_region || t < l.region_tile_begin[r] || t >= l.region_tile_begin[r + 1]) bad = 1;
             last_region = r;

@@ -19,3 +19,10 @@ print(which, "grid",len(c),"kernel_ms",[round(m,4) for m in ms])
 names=["T+bar1","A+B","wait2","C1(t0)","C2+bar3","S+Dred","wait4"]
 for i in range(7): print(f"{names[i]:8s} mean {d[:,i].mean():9.0f} p10 {np.percentile(d[:,i],10):9.0f} p50 {np.percentile(d[:,i],50):9.0f} p90 {np.percentile(d[:,i],90):9.0f} max {d[:,i].max():9.0f}")
 print("total cycles (max over CTAs of end-start)", int((c[:,7]-c[:,0]).max()))
+print("block 0 tail: barrier-4 release -> grid totals", int(c[0,11]-c[0,7]), "-> statistics block written", int(c[0,9]-c[0,11]), "cycles; kernel", round(ms[-1]*1.965e3), "kcycles; block 0 start->barrier-4 release", int(c[0,7]-c[0,0]))
+# device-resident iteration (E-step + M-step in the tail)
+g.em_begin(synth.HIFI_ALPHA, p, tol=1e-12, max_esteps=4)
+for i in range(4): g.em_enqueue()
+g.em_finish(want_labels=False)
+c=g.debug_phase_clocks()
+print("device EM iteration ms", [round(g.em_enqueued_ms(i),4) for i in range(4)], "; block 0: tail", int(c[0,9]-c[0,7]), "M-step", int(c[0,10]-c[0,9]), "cycles")

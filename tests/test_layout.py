@@ -26,7 +26,7 @@ def test_layout_invariants(factory, n_regions, capacity):
         assert ok
         n_seg, smax, n_edge, W, n_keys, n_tiles = (int(v) for v in summary)
         assert W == wl.n_windows and n_seg <= capacity and n_seg * smax >= W
-        assert 1 <= n_keys <= W and n_tiles <= W // 16 + n_keys
+        assert 1 <= n_keys <= W and n_tiles <= W // 16 + n_keys + 1
         assert (n_edge == 0) == (not adjust)
 
 
