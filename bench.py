@@ -81,10 +81,17 @@ class ClockSampler:
         self.idx, self.rows, self.proc = gpu_index, [], None
 
     def start(self):
-        if os.environ.get("BENCH_SAMPLER", "smi") == "none":
+        # default: in-process NVML polling (no nvidia-smi process attaching to the driver and taking its locks every 100 ms
+        # next to the job -- that showed up as sporadic 30-50 ms stalls of cudaMallocHost/cudaFree in the end-to-end legs);
+        # BENCH_SAMPLER=smi forces the nvidia-smi loop, =none disables sampling
+        mode = os.environ.get("BENCH_SAMPLER", "nvml")
+        if mode == "none":
             return
-        if os.environ.get("BENCH_SAMPLER", "smi") == "nvml":
-            return self._start_nvml()
+        if mode == "nvml":
+            try:
+                return self._start_nvml()
+            except Exception:
+                pass  # no pynvml / NVML failure: fall back to nvidia-smi
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -115,7 +122,7 @@ class ClockSampler:
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 self.rows.append([str(self.idx), str(sm), str(mx), "", ""] +
                                  ["Active" if r & b else "Not Active" for b in bits.values()])
-                self.nvml_stop.wait(0.05)
+                self.nvml_stop.wait(0.005)
         self.t = threading.Thread(target=loop, daemon=True)
         self.t.start()
         self.proc = "nvml"
@@ -371,8 +378,9 @@ def run_ours(args):
     # ---- end to end through the blocking C-ABI call with host buffers ----
     # one "job" = hfg_create + hfg_set_chunks (host windows -> HBM, once) + K x [hfg_em_iteration with host parameters in,
     # host statistics and labels out, + host M-step]; the job is run E2E_REPEATS times and the median job time is reported
-    E2E_REPEATS = 3
-    labels = np.empty(wl.n_windows, np.int8)
+    E2E_REPEATS = 5
+    labels_pinned = api.PinnedArray(wl.n_windows, np.int8)  # page-locked result buffer (hfg_host_alloc): no staging copy
+    labels = labels_pinned.array
     jobs = []
     for rep in range(E2E_REPEATS):
         params = params0.copy()
@@ -422,6 +430,8 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(job, op=dist.ReduceOp.MAX)
         run_jobs.append(float(job.item()))
+        if rank == 0:
+            print(f"[bench] hfg_run_em job {rep}: {1e3 * run_jobs[-1]:.2f} ms", file=sys.stderr)
         gpu3.close()
     run_job_total = float(np.median(run_jobs))
     barrier()
@@ -451,7 +461,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(params.nbytes + obs_bytes / args.steps),
                     "d2h_bytes_per_step": int(stats.nbytes + 16 + wl.n_windows),
                     "includes": "hfg_create + hfg_set_chunks once, then hfg_em_iteration (host params in, host "
-                                "statistics + labels out) + host M-step per step; median of 3 such jobs",
+                                "statistics + labels out, labels into a page-locked buffer) + host M-step per step; "
+                                "median of 5 such jobs",
                     "job_ms": [1e3 * j for j in jobs]},
             "e2e_job": {"value": W_total * args.steps / run_job_total, "unit": "windows/s",
                         "call": f"hfg_create + hfg_set_chunks + hfg_run_em({args.steps - 1} EM iterations + final inference) with "

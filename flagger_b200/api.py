@@ -51,7 +51,7 @@ EXPORTED_SYMBOLS = (
     "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_chunks", "hfg_num_windows", "hfg_em_iteration",
     "hfg_forward_only", "hfg_get_posteriors", "hfg_get_chunk_logliks", "hfg_em_iteration_device",
     "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
-    "hfg_run_em", "hfg_em_begin", "hfg_em_enqueue", "hfg_em_finish", "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
+    "hfg_host_alloc", "hfg_host_free", "hfg_run_em", "hfg_em_begin", "hfg_em_enqueue", "hfg_em_finish", "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta", "hfg_debug_layout_compare",
     "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_read_cov", "hfg_read_bin", "hfg_cov_free",
     "hfg_params_feasible", "hfg_squarem_alpha_rate", "hfg_squarem_prime", "hfg_squarem_shrink", "hfg_squarem_iteration",
     "hfg_run_em_accelerated", "hfg_release_cached_memory",
@@ -75,6 +75,32 @@ def beta(cfg, chunk_desc, window):
     f = lib().hfg_debug_beta
     f.restype = C.c_double
     return float(f(ptr(np.ascontiguousarray(cfg)), ptr(np.ascontiguousarray(chunk_desc)), C.c_int(window)))
+
+
+class PinnedArray:
+    """A numpy view (`.array`) over page-locked host memory from hfg_host_alloc: result buffers the device writes
+    directly.  Freed with .free() or on garbage collection."""
+
+    def __init__(self, n, dtype=np.int8):
+        L = lib()
+        L.hfg_host_alloc.restype = C.c_void_p
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        self._p = L.hfg_host_alloc(C.c_size_t(nbytes))
+        if not self._p:
+            raise HfgError(_abi.ERR_NOMEM, "hfg_host_alloc failed (no usable CUDA device?)")
+        self.array = np.frombuffer((C.c_char * nbytes).from_address(self._p), dtype=dtype, count=int(n))
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().hfg_host_free(C.c_void_p(self._p))
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def best_num_collapsed_comps(max_coverage, region_coverages):
@@ -163,6 +189,16 @@ class HmmFlaggerGPU:
                                          ptr(np.ascontiguousarray(wl.region, np.uint8))))
         self.n_windows = int(lib().hfg_num_windows(self._h))
         self.n_chunks = len(chunks)
+
+    def layout_matches_host(self, wl):
+        """Are the device-built keys / lists / tiles bit-identical to the host builder's for this workload?  (ok, message)"""
+        chunks = np.ascontiguousarray(wl.chunks)
+        rc = lib().hfg_debug_layout_compare(self._h, C.c_int32(len(chunks)), ptr(chunks),
+                                            ptr(np.ascontiguousarray(wl.cov, np.uint16)),
+                                            ptr(np.ascontiguousarray(wl.cov_high_mapq, np.uint16)),
+                                            ptr(np.ascontiguousarray(wl.cov_high_clip, np.uint16)),
+                                            ptr(np.ascontiguousarray(wl.region, np.uint8)))
+        return rc == 0, lib().hfg_last_error(self._h).decode()
 
     def em_iteration(self, alpha, params, want_labels=True, stats=None, labels=None):
         """EM_runOneIterationForList: returns (stats, loglik, labels)."""

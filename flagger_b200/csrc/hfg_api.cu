@@ -15,8 +15,10 @@
 
 #include "hfg_estep.cuh"
 #include "hfg_internal.h"
+#include "hfg_layout_dev.cuh"
 
 #define STAGE_SLOTS 4
+#define HFG_EM_LOGLIK_SLOTS 4096 /* E-steps a device-resident EM loop can record (carved from the arena) */
 #define STATS_DOUBLES ((int) (sizeof(hfg_region_stats) / sizeof(double)))
 
 struct hfg_ctx {
@@ -41,6 +43,9 @@ struct hfg_ctx {
     long long *d_phase_clock;
     void *d_arena;   /* one device allocation behind all per-run buffers */
     size_t arena_bytes;
+    void *d_keyblock; /* the buffers sized by the number of observation keys (key table, descriptors, betas) */
+    size_t keyblock_bytes;
+    int32_t capacity_arg; /* the slot count the layout was asked for (before trimming): hfg_debug_layout_compare */
     int8_t *h_labels; /* pinned staging for the label read-back */
     /* pinned host staging */
     hfg_region_params *h_params[STAGE_SLOTS];
@@ -54,7 +59,7 @@ struct hfg_ctx {
     /* the blocking entry points replay a captured graph (parameter upload -> kernel -> result read-back): one launch
      * call per E-step instead of six */
     cudaGraphExec_t gexec;
-    int graph_disabled, graph_labels;
+    int graph_disabled;
     EstepArgs graph_args;
     /* multi-GPU peer exchange (hfg_peer_export / hfg_peer_connect) */
     int n_ranks, rank;
@@ -65,7 +70,7 @@ struct hfg_ctx {
     hfg_region_params *d_em_params;
     int32_t *d_em_state;
     double *d_em_logliks;
-    int em_active, em_max, em_enqueued, em_ev_cap;
+    int em_active, em_max, em_limit, em_enqueued, em_ev_cap;
     double em_alpha[16], em_tol;
     cudaEvent_t *em_ev; /* [2 * em_ev_cap] */
     void *d_flush;
@@ -218,36 +223,41 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
  * 3 Gbp job costs 0.4 ms on a quiet driver but was measured at 6-60 ms on a freshly booted box, more than the job's upload.
  * hfg_release_cached_memory() returns it to the driver; HFG_NO_ARENA_CACHE=1 disables the cache. */
 static pthread_mutex_t g_cache_mu = PTHREAD_MUTEX_INITIALIZER;
-static struct { void *ptr; size_t bytes; int device; } g_cache = {NULL, 0, -1};
+#define HFG_CACHE_SLOTS 2 /* the per-run arena and the key-table block */
+static struct { void *ptr; size_t bytes; int device; } g_cache[HFG_CACHE_SLOTS] = {{NULL, 0, -1}, {NULL, 0, -1}};
 
-static void arena_release(void *ptr, size_t bytes, int device) {
+/* kind 0: the per-run arena; kind 1: the key block.  One cached block of each kind; a newly released block replaces the
+ * cached one of its kind (the next job most likely looks like the last one). */
+static void arena_release(void *ptr, size_t bytes, int device, int kind) {
     if (!ptr) return;
     void *drop = ptr;
+    int drop_dev = device;
     if (!getenv("HFG_NO_ARENA_CACHE")) {
         pthread_mutex_lock(&g_cache_mu);
-        if (!g_cache.ptr || g_cache.bytes < bytes) { /* keep the larger one */
-            drop = g_cache.ptr;
-            const int drop_dev = g_cache.device;
-            g_cache.ptr = ptr;
-            g_cache.bytes = bytes;
-            g_cache.device = device;
-            if (drop) cudaSetDevice(drop_dev);
-        }
+        drop = g_cache[kind].ptr;
+        drop_dev = g_cache[kind].device;
+        g_cache[kind].ptr = ptr;
+        g_cache[kind].bytes = bytes;
+        g_cache[kind].device = device;
         pthread_mutex_unlock(&g_cache_mu);
     }
-    if (drop) cudaFree(drop);
+    if (drop) {
+        cudaSetDevice(drop_dev);
+        cudaFree(drop);
+    }
     cudaSetDevice(device);
 }
 
-static void *arena_acquire(size_t bytes, int device, size_t *got) {
+static void *arena_acquire(size_t bytes, int device, size_t *got, int kind) {
     void *ptr = NULL;
     pthread_mutex_lock(&g_cache_mu);
-    if (g_cache.ptr && g_cache.device == device && g_cache.bytes >= bytes && g_cache.bytes <= 2 * bytes + (1u << 20)) {
-        ptr = g_cache.ptr;
-        *got = g_cache.bytes;
-        g_cache.ptr = NULL;
-        g_cache.bytes = 0;
-        g_cache.device = -1;
+    if (g_cache[kind].ptr && g_cache[kind].device == device && g_cache[kind].bytes >= bytes &&
+        g_cache[kind].bytes <= 2 * bytes + (1u << 20)) {
+        ptr = g_cache[kind].ptr;
+        *got = g_cache[kind].bytes;
+        g_cache[kind].ptr = NULL;
+        g_cache[kind].bytes = 0;
+        g_cache[kind].device = -1;
     }
     pthread_mutex_unlock(&g_cache_mu);
     if (!ptr) {
@@ -259,13 +269,14 @@ static void *arena_acquire(size_t bytes, int device, size_t *got) {
 
 extern "C" void hfg_release_cached_memory(void) {
     pthread_mutex_lock(&g_cache_mu);
-    if (g_cache.ptr) {
-        cudaSetDevice(g_cache.device);
-        cudaFree(g_cache.ptr);
-        g_cache.ptr = NULL;
-        g_cache.bytes = 0;
-        g_cache.device = -1;
-    }
+    for (int i = 0; i < HFG_CACHE_SLOTS; i++)
+        if (g_cache[i].ptr) {
+            cudaSetDevice(g_cache[i].device);
+            cudaFree(g_cache[i].ptr);
+            g_cache[i].ptr = NULL;
+            g_cache[i].bytes = 0;
+            g_cache[i].device = -1;
+        }
     pthread_mutex_unlock(&g_cache_mu);
 }
 
@@ -274,8 +285,11 @@ static void free_device(hfg_ctx *ctx) {
         cudaGraphExecDestroy(ctx->gexec);
         ctx->gexec = NULL;
     }
-    arena_release(ctx->d_arena, ctx->arena_bytes, ctx->device);
+    arena_release(ctx->d_arena, ctx->arena_bytes, ctx->device, 0);
     ctx->arena_bytes = 0;
+    arena_release(ctx->d_keyblock, ctx->keyblock_bytes, ctx->device, 1);
+    ctx->d_keyblock = NULL;
+    ctx->keyblock_bytes = 0;
     cudaFree(ctx->d_post);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_labels) cudaFreeHost(ctx->h_labels);
@@ -287,6 +301,8 @@ static void free_device(hfg_ctx *ctx) {
     ctx->d_out = ctx->d_seg_loglik = ctx->d_post = NULL;
     ctx->d_labels = NULL;
     ctx->d_phase_clock = NULL;
+    ctx->d_em_params = NULL; ctx->d_em_state = NULL; ctx->d_em_logliks = NULL;
+    ctx->em_active = 0;
     ctx->h_out = NULL;
     ctx->h_labels = NULL;
     hfg_layout_free(&ctx->lay);
@@ -309,15 +325,25 @@ extern "C" void hfg_destroy(hfg_ctx *ctx) {
         if (p != ctx->rank && ctx->peer_box[p]) cudaIpcCloseMemHandle(ctx->peer_box[p]);
     cudaFree(ctx->d_mailbox);
     cudaFree(ctx->d_epoch);
-    cudaFree(ctx->d_em_params);
-    cudaFree(ctx->d_em_state);
-    cudaFree(ctx->d_em_logliks);
     cudaFree(ctx->d_flush);
     for (int i = 0; i < 2 * ctx->em_ev_cap; i++) cudaEventDestroy(ctx->em_ev[i]);
     free(ctx->em_ev);
     cudaStreamDestroy(ctx->stream);
     free(ctx->last_params);
     free(ctx);
+}
+
+/* page-locked host memory: result buffers allocated here are written by the device directly (no staging copy) */
+extern "C" void *hfg_host_alloc(size_t bytes) {
+    void *p = NULL;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return NULL;
+    }
+    return p;
+}
+extern "C" void hfg_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 extern "C" int64_t hfg_num_windows(const hfg_ctx *ctx) { return ctx && ctx->have_chunks ? ctx->lay.n_windows : 0; }
@@ -342,6 +368,8 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     CU(cudaStreamSynchronize(ctx->stream));
     free_device(ctx);
     const bool timing = getenv("HFG_TIMING") != NULL; /* where the set-up time goes, on stderr */
+    /* HFG_HOST_LAYOUT=1: build keys, lists and tiles with the host builder (hfg_layout.c) instead of on the device */
+    const bool host_layout = getenv("HFG_HOST_LAYOUT") != NULL;
     double tm[6] = {0};
     tm[0] = wall_ms();
     int64_t W = 0;
@@ -354,62 +382,64 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     int64_t blocks = (W + (int64_t) ctx->threads * wpt - 1) / ((int64_t) ctx->threads * wpt);
     if (blocks < 1) blocks = 1;
     if (blocks > ctx->max_blocks) blocks = ctx->max_blocks;
-    int rc = hfg_layout_build(&ctx->cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region,
-                              (int32_t) blocks * ctx->threads, ctx->threads, &ctx->lay, ctx->err, sizeof(ctx->err));
-    if (rc == HFG_OK) ctx->grid = ctx->lay.capacity / ctx->threads;
-    const int32_t cap = ctx->lay.capacity;
+    ctx->capacity_arg = (int32_t) blocks * ctx->threads;
+    int rc = hfg_layout_build_ex(&ctx->cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, ctx->capacity_arg,
+                                 ctx->threads, host_layout ? 0 : 1, &ctx->lay, ctx->err, sizeof(ctx->err));
     if (rc != HFG_OK) return rc;
+    ctx->grid = ctx->lay.capacity / ctx->threads;
+    const int32_t cap = ctx->lay.capacity;
     tm[1] = wall_ms();
-    const hfg_layout *l = &ctx->lay;
+    hfg_layout *l = &ctx->lay;
     const size_t slots = (size_t) l->smax * cap;
     const int R = ctx->cfg.n_regions, G = total_gauss_comps(&ctx->cfg);
     const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
+    const size_t w = (size_t) W;
+    /* device-side build: raw inputs + temporaries share the region that holds the per-E-step scratch afterwards */
+    const size_t raw_bytes = 3 * hfgl::align256(2 * w) + hfgl::align256(w) + hfgl::align256(sizeof(hfg_chunk_desc) * (size_t) n_chunks) +
+                             2 * hfgl::align256(4 * (size_t) n_chunks) + hfgl::align256(4 * (size_t) cap);
+    const size_t build_bytes = host_layout ? 0 : raw_bytes + hfgl::temp_bytes(W, NULL);
+    const size_t scratch_bytes = hfgl::align256(slots * 4 * sizeof(double)) + hfgl::align256(w * 8 * sizeof(double));
+    const size_t max_tiles = w / HFG_TILE + w + 1;
+    size_t o_scr = 0;
     /* one device allocation carved into the per-run buffers (cudaMalloc is the slow part of a short job) */
     {
         size_t off = 0;
 #define CARVE(bytes) (off = (off + 255) & ~(size_t) 255, off += (bytes), off - (bytes))
-        const size_t P = (size_t) l->n_keys, NT = (size_t) (l->n_tiles > 0 ? l->n_tiles : 1);
         const size_t o_wk = CARVE(slots * sizeof(uint32_t));
         const size_t o_ss = CARVE(cap * sizeof(int32_t)), o_sl = CARVE(cap * sizeof(int32_t));
-        const size_t o_kd = CARVE(P * sizeof(uint32_t)), o_kb = CARVE(P * 3 * sizeof(double));
-        const size_t o_kl = CARVE((size_t) (l->n_list > 0 ? l->n_list : 1) * sizeof(int32_t));
-        const size_t o_tk = CARVE(NT * sizeof(int32_t)), o_tb = CARVE(NT * sizeof(int32_t)), o_tc = CARVE(NT * sizeof(int32_t));
+        const size_t o_kl = CARVE((w > 0 ? w : 1) * sizeof(int32_t));
+        const size_t o_tk = CARVE(max_tiles * sizeof(int32_t)), o_tb = CARVE(max_tiles * sizeof(int32_t));
+        const size_t o_tc = CARVE(max_tiles * sizeof(int32_t));
         const size_t o_rt = CARVE((HFG_MAX_REGIONS + 1) * sizeof(int32_t));
-        const size_t o_M = CARVE(P * 16 * sizeof(double));
-        const size_t o_F = CARVE(slots * 4 * sizeof(double));
-        const size_t o_B = CARVE((size_t) l->n_windows * 8 * sizeof(double));
+        o_scr = CARVE(scratch_bytes > build_bytes ? scratch_bytes : build_bytes);
         const size_t o_bt = CARVE((size_t) ctx->grid * 16 * sizeof(double));
         const size_t o_br = CARVE((size_t) ctx->grid * sizeof(int32_t));
         const size_t o_pa = CARVE((size_t) ctx->grid * R * hfg_nstat(G) * sizeof(double));
         const size_t o_out = CARVE(out_doubles * sizeof(double));
         const size_t o_ll = CARVE(cap * sizeof(double));
-        const size_t o_lab = CARVE((size_t) l->n_windows);
+        const size_t o_lab = CARVE(w);
         const size_t o_err = CARVE(sizeof(int32_t));
         const size_t o_pc = CARVE((size_t) ctx->grid * HFG_PC_STRIDE * sizeof(long long));
+        const size_t o_emp = CARVE(sizeof(hfg_region_params) * (size_t) R), o_ems = CARVE(4 * sizeof(int32_t));
+        const size_t o_eml = CARVE(sizeof(double) * HFG_EM_LOGLIK_SLOTS);
 #undef CARVE
-        ctx->d_arena = arena_acquire(off, ctx->device, &ctx->arena_bytes);
+        ctx->d_arena = arena_acquire(off, ctx->device, &ctx->arena_bytes, 0);
         if (!ctx->d_arena) {
             cudaGetLastError();
             return fail(ctx, HFG_ERR_NOMEM, "hfg_set_chunks: cannot allocate %zu bytes of device memory", off);
         }
-        tm[2] = wall_ms();
-        if (timing)
-            fprintf(stderr, "[hfg] arena %.1f MB; %lld windows, %d keys, %d tiles\n", off / 1e6, (long long) l->n_windows,
-                    l->n_keys, l->n_tiles);
+        if (timing) fprintf(stderr, "[hfg] arena %.1f MB; %lld windows\n", off / 1e6, (long long) W);
         char *base = (char *) ctx->d_arena;
         ctx->d_wkeyT = (uint32_t *) (base + o_wk);
         ctx->d_seg_start = (int32_t *) (base + o_ss);
         ctx->d_seg_len = (int32_t *) (base + o_sl);
-        ctx->d_kdesc = (uint32_t *) (base + o_kd);
-        ctx->d_kbeta = (double *) (base + o_kb);
         ctx->d_klist = (int32_t *) (base + o_kl);
         ctx->d_tile_key = (int32_t *) (base + o_tk);
         ctx->d_tile_begin = (int32_t *) (base + o_tb);
         ctx->d_tile_cnt = (int32_t *) (base + o_tc);
         ctx->d_region_tile_begin = (int32_t *) (base + o_rt);
-        ctx->d_tabM = (double *) (base + o_M);
-        ctx->d_scrFT = (double *) (base + o_F);
-        ctx->d_scrXB = (double *) (base + o_B);
+        ctx->d_scrFT = (double *) (base + o_scr);
+        ctx->d_scrXB = (double *) (base + o_scr + hfgl::align256(slots * 4 * sizeof(double)));
         ctx->d_block_tot = (double *) (base + o_bt);
         ctx->d_block_reset = (int32_t *) (base + o_br);
         ctx->d_partials = (double *) (base + o_pa);
@@ -418,31 +448,116 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         ctx->d_labels = (int8_t *) (base + o_lab);
         ctx->d_err = (int32_t *) (base + o_err);
         ctx->d_phase_clock = (long long *) (base + o_pc);
+        ctx->d_em_params = (hfg_region_params *) (base + o_emp);
+        ctx->d_em_state = (int32_t *) (base + o_ems);
+        ctx->d_em_logliks = (double *) (base + o_eml);
+        ctx->em_max = HFG_EM_LOGLIK_SLOTS;
     }
+    tm[2] = wall_ms();
     CU(cudaMallocHost((void **) &ctx->h_out, out_doubles * sizeof(double)));
-    CU(cudaMallocHost((void **) &ctx->h_labels, (size_t) l->n_windows));
-    tm[3] = wall_ms();
-    CU(cudaMemcpyAsync(ctx->d_wkeyT, l->wkeyT, slots * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMallocHost((void **) &ctx->h_labels, w));
     CU(cudaMemcpyAsync(ctx->d_seg_start, l->seg_start, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_len, l->seg_len, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_kdesc, l->kdesc, (size_t) l->n_keys * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_kbeta, l->kbeta, (size_t) l->n_keys * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (l->n_list > 0)
-        CU(cudaMemcpyAsync(ctx->d_klist, l->klist, (size_t) l->n_list * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    if (l->n_tiles > 0) {
-        const size_t tb = (size_t) l->n_tiles * sizeof(int32_t);
-        CU(cudaMemcpyAsync(ctx->d_tile_key, l->tile_key, tb, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_tile_begin, l->tile_begin, tb, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_tile_cnt, l->tile_cnt, tb, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_labels, 0xff, w, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream)); /* every launch leaves the flags cleared */
+
+    /* the key block: key table, key descriptors, betas -- sized by the number of keys */
+    auto acquire_keyblock = [&](int32_t n_keys) -> int {
+        const size_t P = (size_t) n_keys;
+        const size_t o_M = 0, o_kd = hfgl::align256(P * 16 * sizeof(double)), o_kb = o_kd + hfgl::align256(P * sizeof(uint32_t));
+        const size_t total = o_kb + hfgl::align256(P * 3 * sizeof(double));
+        ctx->d_keyblock = arena_acquire(total, ctx->device, &ctx->keyblock_bytes, 1);
+        if (!ctx->d_keyblock) {
+            cudaGetLastError();
+            return fail(ctx, HFG_ERR_NOMEM, "hfg_set_chunks: cannot allocate %zu bytes of device memory for %d keys", total, n_keys);
+        }
+        char *kb = (char *) ctx->d_keyblock;
+        ctx->d_tabM = (double *) (kb + o_M);
+        ctx->d_kdesc = (uint32_t *) (kb + o_kd);
+        ctx->d_kbeta = (double *) (kb + o_kb);
+        return HFG_OK;
+    };
+
+    if (host_layout) {
+        if ((rc = acquire_keyblock(l->n_keys)) != HFG_OK) return rc;
+        CU(cudaMemcpyAsync(ctx->d_wkeyT, l->wkeyT, slots * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_kdesc, l->kdesc, (size_t) l->n_keys * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_kbeta, l->kbeta, (size_t) l->n_keys * 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        if (l->n_list > 0)
+            CU(cudaMemcpyAsync(ctx->d_klist, l->klist, (size_t) l->n_list * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (l->n_tiles > 0) {
+            const size_t tb = (size_t) l->n_tiles * sizeof(int32_t);
+            CU(cudaMemcpyAsync(ctx->d_tile_key, l->tile_key, tb, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->d_tile_begin, l->tile_begin, tb, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(ctx->d_tile_cnt, l->tile_cnt, tb, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CU(cudaMemcpyAsync(ctx->d_region_tile_begin, l->region_tile_begin, (HFG_MAX_REGIONS + 1) * sizeof(int32_t),
+                           cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        tm[3] = tm[4] = wall_ms();
+    } else {
+        /* raw inputs -> device, then the build (hfg_layout_dev.cuh) */
+        char *rb = (char *) ctx->d_arena + o_scr;
+        size_t ro = 0;
+#define RAW(type, name, bytes) type *name = (type *) (rb + ro); ro += hfgl::align256(bytes)
+        RAW(uint16_t, d_cov, 2 * w);
+        RAW(uint16_t, d_mapq, 2 * w);
+        RAW(uint16_t, d_clip, 2 * w);
+        RAW(uint8_t, d_region, w);
+        RAW(hfg_chunk_desc, d_chunks, sizeof(hfg_chunk_desc) * (size_t) n_chunks);
+        RAW(int32_t, d_head, 4 * (size_t) n_chunks);
+        RAW(int32_t, d_tail, 4 * (size_t) n_chunks);
+        RAW(int32_t, d_seg_chunk, 4 * (size_t) cap);
+#undef RAW
+        CU(cudaMemcpyAsync(d_cov, cov, 2 * w, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_mapq, cov_high_mapq, 2 * w, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_clip, cov_high_clip, 2 * w, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_region, region, w, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_chunks, chunks, sizeof(hfg_chunk_desc) * (size_t) n_chunks, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_head, l->edge_head, 4 * (size_t) n_chunks, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_tail, l->edge_tail, 4 * (size_t) n_chunks, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(d_seg_chunk, l->seg_chunk, 4 * (size_t) cap, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_wkeyT, 0, slots * sizeof(uint32_t), ctx->stream));
+        tm[3] = wall_ms();
+        hfgl::PackArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.cov = d_cov; pa.mapq = d_mapq; pa.clip = d_clip; pa.region = d_region;
+        pa.chunks = d_chunks; pa.edge_head = d_head; pa.edge_tail = d_tail;
+        pa.seg_start = ctx->d_seg_start; pa.seg_len = ctx->d_seg_len; pa.seg_chunk = d_seg_chunk;
+        pa.n_seg = l->n_seg; pa.capacity = cap;
+        pa.adjust_contig_ends = ctx->cfg.adjust_contig_ends; pa.mean_read_length = ctx->cfg.mean_read_length;
+        pa.min_read_fraction_at_ends = ctx->cfg.min_read_fraction_at_ends;
+        pa.max_high_mapq_ratio = ctx->cfg.max_high_mapq_ratio; pa.min_high_mapq_ratio = ctx->cfg.min_high_mapq_ratio;
+        pa.min_highly_clipped_ratio = ctx->cfg.min_highly_clipped_ratio;
+        hfgl::DeviceLayoutTemp tmp;
+        memset(&tmp, 0, sizeof(tmp));
+        CU(hfgl::layout_build_device_keys(pa, W, rb + raw_bytes, ctx->stream, &tmp));
+        const double t_keys = wall_ms();
+        if ((rc = acquire_keyblock(tmp.P)) != HFG_OK) return rc;
+        const double t_kb = wall_ms();
+        hfgl::DeviceLayoutOut lo;
+        lo.wkeyT = ctx->d_wkeyT; lo.klist = ctx->d_klist;
+        lo.tile_key = ctx->d_tile_key; lo.tile_begin = ctx->d_tile_begin; lo.tile_cnt = ctx->d_tile_cnt;
+        lo.region_tile_begin = ctx->d_region_tile_begin; lo.kdesc = ctx->d_kdesc; lo.kbeta = ctx->d_kbeta;
+        int64_t n_list = 0;
+        int32_t n_tiles = 0, tile_len = 0;
+        CU(hfgl::layout_build_device_lists(&tmp, l->beta0, lo, ctx->stream, &n_list, &n_tiles, &tile_len));
+        CU(cudaStreamSynchronize(ctx->stream));
+        l->n_keys = tmp.P;
+        l->n_list = n_list;
+        l->n_tiles = n_tiles;
+        l->tile_len = tile_len;
+        ctx->launches += 12; /* the layout kernels (CUB's own passes not counted) */
+        tm[4] = wall_ms();
+        if (timing)
+            fprintf(stderr, "[hfg] device build: pack + sorts + run heads %.2f ms, key block %.2f ms, numbering + lists + tiles %.2f ms\n",
+                    t_keys - tm[3], t_kb - t_keys, tm[4] - t_kb);
     }
-    CU(cudaMemcpyAsync(ctx->d_region_tile_begin, l->region_tile_begin, (HFG_MAX_REGIONS + 1) * sizeof(int32_t),
-                       cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_labels, 0xff, (size_t) l->n_windows, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    tm[4] = wall_ms();
     if (timing)
-        fprintf(stderr, "[hfg] set_chunks: layout %.2f ms, cudaMalloc %.2f ms, cudaMallocHost %.2f ms, copies %.2f ms\n",
-                tm[1] - tm[0], tm[2] - tm[1], tm[3] - tm[2], tm[4] - tm[3]);
+        fprintf(stderr, "[hfg] set_chunks (%s keys): segments%s %.2f ms, arena %.2f ms, uploads queued %.2f ms, %s %.2f ms; %d keys, "
+                "%d tiles of <= %d windows\n", host_layout ? "host" : "device", host_layout ? " + keys" : "", tm[1] - tm[0],
+                tm[2] - tm[1], tm[3] - tm[2], host_layout ? "copies" : "device build", tm[4] - tm[3], l->n_keys, l->n_tiles,
+                l->tile_len);
     /* the per-window tables now live on the device */
     free(ctx->lay.obsT); ctx->lay.obsT = NULL;
     free(ctx->lay.wkeyT); ctx->lay.wkeyT = NULL;
@@ -536,8 +651,12 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     a.block_reset = ctx->d_block_reset;
     a.partials = ctx->d_partials;
     a.out = out_dev;
+    a.out_host = (out_dev == ctx->d_out) ? ctx->h_out : NULL; /* the blocking calls read their results from pinned memory */
     a.seg_loglik = ctx->d_seg_loglik;
     a.labels = ctx->d_labels;
+    a.labels_host = NULL;
+    a.n_seg = l->n_seg;
+    a.n_windows = l->n_windows;
     a.posteriors = post_dev;
     a.err_flags = ctx->d_err;
     a.forward_only = forward_only;
@@ -566,7 +685,6 @@ static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_par
     memcpy(ctx->h_params[slot], params, sizeof(hfg_region_params) * (size_t) R);
     CU(cudaMemcpyAsync(ctx->d_params[slot], ctx->h_params[slot], sizeof(hfg_region_params) * (size_t) R,
                        cudaMemcpyHostToDevice, stream));
-    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), stream));
 
     EstepArgs a;
     build_args(ctx, alpha, out_dev, post_dev, forward_only, slot, &a);
@@ -602,22 +720,9 @@ static int parse_out(hfg_ctx *ctx, hfg_region_stats *stats, double *loglik) {
     return HFG_OK;
 }
 
-/* fetch [stats | loglik | flags] from the context's own output buffer and translate the error flags */
-static int fetch_out(hfg_ctx *ctx, hfg_region_stats *stats, double *loglik, int8_t *labels, int with_labels) {
+/* (re)capture  upload params -> kernel  as one graph (the kernel delivers its results into pinned memory itself) */
+static int capture_graph(hfg_ctx *ctx, const EstepArgs *a) {
     const int R = ctx->cfg.n_regions;
-    const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
-    CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (with_labels && labels)
-        CU(cudaMemcpyAsync(ctx->h_labels, ctx->d_labels, (size_t) ctx->lay.n_windows, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (with_labels && labels) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
-    return parse_out(ctx, stats, loglik);
-}
-
-/* (re)capture  upload params -> clear flags -> kernel -> read back results [-> read back labels]  as one graph */
-static int capture_graph(hfg_ctx *ctx, const EstepArgs *a, int with_labels) {
-    const int R = ctx->cfg.n_regions;
-    const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
     if (ctx->gexec) {
         cudaGraphExecDestroy(ctx->gexec);
         ctx->gexec = NULL;
@@ -629,16 +734,14 @@ static int capture_graph(hfg_ctx *ctx, const EstepArgs *a, int with_labels) {
     void *kargs[] = {(void *) &copy};
     e = cudaMemcpyAsync(ctx->d_params[0], ctx->h_params[0], sizeof(hfg_region_params) * (size_t) R, cudaMemcpyHostToDevice,
                         ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecordWithFlags(ctx->ev0, ctx->stream, cudaEventRecordExternal); /* event-record node */
     if (e == cudaSuccess)
         e = cudaLaunchCooperativeKernel(ctx->kernel, dim3(ctx->grid), dim3(ctx->threads), kargs, ctx->smem_bytes,
                                         ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecordWithFlags(ctx->ev1, ctx->stream, cudaEventRecordExternal);
-    if (e == cudaSuccess)
-        e = cudaMemcpyAsync(ctx->h_out, ctx->d_out, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && with_labels)
-        e = cudaMemcpyAsync(ctx->h_labels, ctx->d_labels, (size_t) ctx->lay.n_windows, cudaMemcpyDeviceToHost, ctx->stream);
+    /* no read-back nodes: statistics, log-likelihood and flags arrive through the kernel's own stores into pinned memory,
+     * and so do the labels (EstepArgs.labels_host: the caller's buffer when it is page-locked, hfg_host_alloc, else the
+     * pinned staging buffer) */
     cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
     if (e == cudaSuccess) e = e2;
     if (e == cudaSuccess) e = cudaGraphInstantiate(&ctx->gexec, graph, 0);
@@ -649,8 +752,17 @@ static int capture_graph(hfg_ctx *ctx, const EstepArgs *a, int with_labels) {
         return 0;
     }
     ctx->graph_args = *a;
-    ctx->graph_labels = with_labels;
     return 1;
+}
+
+/* is p page-locked host memory the device can write directly? */
+static int is_pinned_host(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return at.type == cudaMemoryTypeHost;
 }
 
 /* blocking E-step with host buffers: graph replay when possible, plain launches otherwise (same kernel either way) */
@@ -659,36 +771,42 @@ static int run_blocking(hfg_ctx *ctx, const double *alpha, const hfg_region_para
     if (!ctx->have_chunks) return fail(ctx, HFG_ERR_INVALID, "hfg_set_chunks must be called first");
     if (!alpha || !params) return fail(ctx, HFG_ERR_INVALID, "NULL alpha/params");
     const int with_labels = labels != NULL;
+    CU(cudaSetDevice(ctx->device));
+    /* where the kernel streams the labels: the caller's buffer when it is page-locked, else the pinned staging buffer */
+    int8_t *label_dst = !with_labels ? NULL : (is_pinned_host(labels) ? labels : ctx->h_labels);
+    const int R = ctx->cfg.n_regions;
+    EstepArgs a;
+    build_args(ctx, alpha, ctx->d_out, NULL, forward_only, 0, &a);
+    a.labels_host = label_dst;
+    CU(cudaEventSynchronize(ctx->stage_ev[0])); /* slot 0 may still feed an asynchronous device-variant call */
+    memcpy(ctx->h_params[0], params, sizeof(hfg_region_params) * (size_t) R);
     if (!ctx->graph_disabled) {
-        CU(cudaSetDevice(ctx->device));
-        const int R = ctx->cfg.n_regions;
-        EstepArgs a;
-        build_args(ctx, alpha, ctx->d_out, NULL, forward_only, 0, &a);
-        CU(cudaEventSynchronize(ctx->stage_ev[0])); /* slot 0 may still feed an asynchronous device-variant call */
-        memcpy(ctx->h_params[0], params, sizeof(hfg_region_params) * (size_t) R);
-        if (!ctx->gexec || ctx->graph_labels != with_labels || memcmp(&a, &ctx->graph_args, sizeof(a)) != 0) {
-            if (!capture_graph(ctx, &a, with_labels)) ctx->graph_disabled = 1;
-        }
-        if (ctx->gexec) {
-            CU(cudaEventRecord(ctx->ev2, ctx->stream));
-            CU(cudaGraphLaunch(ctx->gexec, ctx->stream));
-            CU(cudaEventRecord(ctx->ev3, ctx->stream));
-            ctx->ev_valid = ctx->span_valid = 1;
-            ctx->launches += 1;
-            memcpy(ctx->last_alpha, alpha, sizeof(double) * 16);
-            memcpy(ctx->last_params, params, sizeof(hfg_region_params) * (size_t) R);
-            ctx->have_last = 1;
-            CU(cudaStreamSynchronize(ctx->stream));
-            if (with_labels) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
-            return parse_out(ctx, stats, loglik);
+        if (!ctx->gexec || memcmp(&a, &ctx->graph_args, sizeof(a)) != 0) {
+            if (!capture_graph(ctx, &a)) ctx->graph_disabled = 1;
         }
     }
     CU(cudaEventRecord(ctx->ev2, ctx->stream));
-    int rc = enqueue_estep(ctx, alpha, params, ctx->d_out, NULL, forward_only, ctx->stream, 1);
-    if (rc != HFG_OK) return rc;
-    rc = fetch_out(ctx, stats, loglik, labels, with_labels);
-    if (cudaEventRecord(ctx->ev3, ctx->stream) == cudaSuccess) ctx->span_valid = 1;
-    return rc;
+    if (ctx->gexec && !ctx->graph_disabled) {
+        CU(cudaGraphLaunch(ctx->gexec, ctx->stream));
+    } else {
+        /* plain launches of the same sequence */
+        void *kargs[] = {(void *) &a};
+        CU(cudaMemcpyAsync(ctx->d_params[0], ctx->h_params[0], sizeof(hfg_region_params) * (size_t) R, cudaMemcpyHostToDevice,
+                           ctx->stream));
+        CU(cudaEventRecord(ctx->ev0, ctx->stream));
+        CU(cudaLaunchCooperativeKernel(ctx->kernel, dim3(ctx->grid), dim3(ctx->threads), kargs, ctx->smem_bytes, ctx->stream));
+        CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    }
+    CU(cudaEventRecord(ctx->ev3, ctx->stream));
+    CU(cudaEventRecord(ctx->stage_ev[0], ctx->stream));
+    ctx->ev_valid = ctx->span_valid = 1;
+    ctx->launches += 1;
+    memcpy(ctx->last_alpha, alpha, sizeof(double) * 16);
+    memcpy(ctx->last_params, params, sizeof(hfg_region_params) * (size_t) R);
+    ctx->have_last = 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (with_labels && label_dst != labels) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
+    return parse_out(ctx, stats, loglik);
 }
 
 extern "C" int hfg_em_iteration(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params,
@@ -783,14 +901,8 @@ extern "C" int hfg_em_begin(hfg_ctx *ctx, const double *alpha, const hfg_region_
     CU(cudaSetDevice(ctx->device));
     const int R = ctx->cfg.n_regions;
     const size_t pb = sizeof(hfg_region_params) * (size_t) R;
-    if (!ctx->d_em_params) CU(cudaMalloc((void **) &ctx->d_em_params, pb));
-    if (!ctx->d_em_state) CU(cudaMalloc((void **) &ctx->d_em_state, 4 * sizeof(int32_t)));
-    if (ctx->em_max < max_esteps) {
-        cudaFree(ctx->d_em_logliks);
-        ctx->d_em_logliks = NULL;
-        CU(cudaMalloc((void **) &ctx->d_em_logliks, sizeof(double) * (size_t) max_esteps));
-    }
-    ctx->em_max = max_esteps;
+    if (max_esteps > HFG_EM_LOGLIK_SLOTS)
+        return fail(ctx, HFG_ERR_INVALID, "hfg_em_begin: at most %d E-steps per loop", HFG_EM_LOGLIK_SLOTS);
     if (ctx->em_ev_cap < max_esteps) {
         cudaEvent_t *ne = (cudaEvent_t *) realloc(ctx->em_ev, sizeof(cudaEvent_t) * 2 * (size_t) max_esteps);
         if (!ne) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
@@ -806,6 +918,7 @@ extern "C" int hfg_em_begin(hfg_ctx *ctx, const double *alpha, const hfg_region_
     CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream));
     memcpy(ctx->em_alpha, alpha, sizeof(double) * 16);
     ctx->em_tol = convergence_tol;
+    ctx->em_limit = max_esteps;
     ctx->em_enqueued = 0;
     ctx->em_active = 1;
     return HFG_OK;
@@ -814,17 +927,18 @@ extern "C" int hfg_em_begin(hfg_ctx *ctx, const double *alpha, const hfg_region_
 extern "C" int hfg_em_enqueue(hfg_ctx *ctx, int final_pass) {
     if (!ctx) return HFG_ERR_INVALID;
     if (!ctx->em_active) return fail(ctx, HFG_ERR_INVALID, "hfg_em_enqueue: call hfg_em_begin first");
-    if (ctx->em_enqueued >= ctx->em_max) return fail(ctx, HFG_ERR_INVALID, "hfg_em_enqueue: more than max_esteps iterations");
+    if (ctx->em_enqueued >= ctx->em_limit) return fail(ctx, HFG_ERR_INVALID, "hfg_em_enqueue: more than max_esteps iterations");
     CU(cudaSetDevice(ctx->device));
     EstepArgs a;
     build_args(ctx, ctx->em_alpha, ctx->d_out, NULL, 0, 0, &a);
     a.params = ctx->d_em_params;
     a.em_params = ctx->d_em_params;
+    a.out_host = NULL; /* the loop's results are fetched once, by hfg_em_finish */
     a.em_mode = final_pass ? 2 : 1;
     a.em_tol = ctx->em_tol;
     a.em_state = ctx->d_em_state;
     a.em_logliks = ctx->d_em_logliks;
-    a.em_max_logliks = ctx->em_max;
+    a.em_max_logliks = ctx->em_limit;
     void *kargs[] = {(void *) &a};
     const int i = ctx->em_enqueued;
     CU(cudaEventRecord(ctx->em_ev[2 * i], ctx->stream));
@@ -848,7 +962,7 @@ extern "C" int hfg_em_finish(hfg_ctx *ctx, hfg_region_params *params, double *lo
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaMemcpy(state, ctx->d_em_state, sizeof(state), cudaMemcpyDeviceToHost));
     ctx->em_active = 0;
-    const int n = state[1] < ctx->em_max ? state[1] : ctx->em_max;
+    const int n = state[1] < ctx->em_limit ? state[1] : ctx->em_limit;
     if (logliks && n > 0) CU(cudaMemcpy(logliks, ctx->d_em_logliks, sizeof(double) * (size_t) n, cudaMemcpyDeviceToHost));
     if (n_esteps) *n_esteps = n;
     if (converged) *converged = state[3];
@@ -1005,6 +1119,66 @@ extern "C" int hfg_debug_exp(hfg_ctx *ctx, const double *in, double *out, int n)
     cudaFree(d_in);
     cudaFree(d_out);
     return HFG_OK;
+}
+
+/* Test hook: rebuilds keys, lists and tiles with the HOST builder (hfg_layout.c) for the inputs this context was given and
+ * compares them, bit for bit, with what lives on the device (normally built there, hfg_layout_dev.cuh).  Returns HFG_OK
+ * when identical; otherwise HFG_ERR_INVALID with the first differing table named in hfg_last_error(). */
+extern "C" int hfg_debug_layout_compare(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                                        const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region) {
+    if (!ctx || !ctx->have_chunks) return HFG_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    hfg_layout h;
+    char err[256];
+    int rc = hfg_layout_build_ex(&ctx->cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, ctx->capacity_arg,
+                                 ctx->threads, 0, &h, err, sizeof(err));
+    if (rc != HFG_OK) return fail(ctx, rc, "host layout build failed: %s", err);
+    const hfg_layout *d = &ctx->lay;
+    const char *bad = NULL;
+    if (h.capacity != d->capacity || h.smax != d->smax || h.n_seg != d->n_seg || h.n_windows != d->n_windows) bad = "segmentation";
+    else if (h.n_keys != d->n_keys) bad = "number of keys";
+    else if (h.n_list != d->n_list) bad = "list length";
+    else if (h.n_tiles != d->n_tiles || h.tile_len != d->tile_len) bad = "tile count / length";
+    if (!bad) {
+        const size_t slots = (size_t) h.smax * h.capacity, NT = (size_t) h.n_tiles, P = (size_t) h.n_keys;
+        size_t cap_bytes = slots * 4;
+        if (P * 24 > cap_bytes) cap_bytes = P * 24;
+        if ((size_t) h.n_list * 4 > cap_bytes) cap_bytes = (size_t) h.n_list * 4;
+        if (NT * 4 > cap_bytes) cap_bytes = NT * 4;
+        if (cap_bytes < 1024) cap_bytes = 1024;
+        void *buf = malloc(cap_bytes);
+        if (!buf) {
+            hfg_layout_free(&h);
+            return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+        }
+        struct { const char *name; const void *dev; const void *host; size_t bytes; } tabs[] = {
+            {"wkeyT", ctx->d_wkeyT, h.wkeyT, slots * 4},
+            {"kdesc", ctx->d_kdesc, h.kdesc, P * 4},
+            {"kbeta", ctx->d_kbeta, h.kbeta, P * 24},
+            {"klist", ctx->d_klist, h.klist, (size_t) h.n_list * 4},
+            {"tile_key", ctx->d_tile_key, h.tile_key, NT * 4},
+            {"tile_begin", ctx->d_tile_begin, h.tile_begin, NT * 4},
+            {"tile_cnt", ctx->d_tile_cnt, h.tile_cnt, NT * 4},
+            {"region_tile_begin", ctx->d_region_tile_begin, h.region_tile_begin, (HFG_MAX_REGIONS + 1) * 4},
+        };
+        for (size_t i = 0; i < sizeof(tabs) / sizeof(tabs[0]) && !bad; i++) {
+            if (tabs[i].bytes == 0) continue;
+            if (cudaMemcpy(buf, tabs[i].dev, tabs[i].bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+                bad = "cudaMemcpy";
+                cudaGetLastError();
+            } else if (memcmp(buf, tabs[i].host, tabs[i].bytes) != 0) {
+                bad = tabs[i].name;
+            }
+        }
+        free(buf);
+    }
+    if (bad)
+        fail(ctx, HFG_ERR_INVALID, "device layout differs from the host builder's: %s (device: %d keys, %lld listed, %d tiles of %d; "
+             "host: %d keys, %lld listed, %d tiles of %d)", bad, d->n_keys, (long long) d->n_list, d->n_tiles, d->tile_len, h.n_keys,
+             (long long) h.n_list, h.n_tiles, h.tile_len);
+    hfg_layout_free(&h);
+    return bad ? HFG_ERR_INVALID : HFG_OK;
 }
 
 /* ---- multi-GPU: peer exchange set-up ------------------------------------------------------------------------------- */

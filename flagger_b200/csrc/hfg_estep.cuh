@@ -121,8 +121,13 @@ struct EstepArgs {
     int32_t *block_reset; /* [grid] */
     double *partials;    /* [R][NSTAT][grid] */
     double *out;         /* [R * sizeof(hfg_region_stats)/8 + 2]: stats | loglik | error flags (as double) */
+    double *out_host;    /* optional mirror of `out` in mapped pinned host memory (blocking calls: no read-back copy) */
     double *seg_loglik;  /* [capacity] */
     int8_t *labels;      /* [W] */
+    int8_t *labels_host; /* optional: mapped pinned host buffer; every block copies its own labels there while the
+                            statistics phase runs (no device-to-host copy after the kernel) */
+    int32_t n_seg;
+    int64_t n_windows;
     double *posteriors;  /* [W][4] or NULL */
     int32_t *err_flags;  /* bit0 scale underflow, bit1 NaN */
     int32_t forward_only;
@@ -1059,6 +1064,26 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
         }
     }
     __syncthreads(); /* gather tiles done: the area becomes the statistics columns */
+    if (A.labels_host != NULL && !A.forward_only && warp >= WARPS - 2) {
+        /* The labels of this block's windows (one contiguous range: segments are in genome order) are final.  The last two
+         * warps -- the statistics tiles fill the block from thread 0 up -- stream them into the caller's page-locked buffer
+         * over PCIe with 16-byte stores while the other warps run phase S. */
+        const int s0 = blockIdx.x * THREADS;
+        if (s0 < A.n_seg) {
+            const long long w_begin = A.seg_start[s0];
+            const long long w_end = s0 + THREADS < A.n_seg ? (long long) A.seg_start[s0 + THREADS] : (long long) A.n_windows;
+            const int t = (warp - (WARPS - 2)) * 32 + lane; /* 0..63 */
+            const long long a16 = (w_begin + 15) & ~15LL, b16 = w_end & ~15LL;
+            if (a16 < b16) {
+                for (long long o = a16 + 16LL * t; o < b16; o += 16 * 64)
+                    *reinterpret_cast<int4 *>(A.labels_host + o) = __ldcg(reinterpret_cast<const int4 *>(A.labels + o));
+                for (long long o = w_begin + t; o < a16; o += 64) A.labels_host[o] = __ldcg(A.labels + o);
+                for (long long o = b16 + t; o < w_end; o += 64) A.labels_host[o] = __ldcg(A.labels + o);
+            } else {
+                for (long long o = w_begin + t; o < w_end; o += 64) A.labels_host[o] = __ldcg(A.labels + o);
+            }
+        }
+    }
     if (uf_flag) atomicOr(A.err_flags, 1);
     grid.sync(); /* f^ and b of every window are in place */
     if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 5] = clock64();
@@ -1377,10 +1402,14 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                         A.em_state[3] = 1;
                         A.em_state[0] = 1;
                     }
-                    *A.err_flags = 0; /* for the next launch of the loop */
                     A.phase_clock[10] = clock64(); /* block 0: M-step done */
                 }
             }
+            /* results straight into the caller-visible pinned block, error flags cleared for the next launch */
+            __syncthreads();
+            if (A.out_host)
+                for (int q = tid; q < A.out_doubles; q += THREADS) A.out_host[q] = A.out[q];
+            if (tid == 0) *A.err_flags = 0;
         }
     }
 }

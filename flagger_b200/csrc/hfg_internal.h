@@ -83,6 +83,8 @@ typedef struct hfg_layout {
     double *edge_beta;       /* [n_edge][3] (beta, beta0/beta, sqrt(beta0/beta)) of every edge window, in window order */
     int64_t n_edge;
     int64_t *chunk_offset;   /* [n_chunks + 1] */
+    int32_t *edge_head, *edge_tail; /* [n_chunks] leading / trailing contig-end windows of every chunk (segments-only build) */
+    int32_t tile_len;        /* windows per statistics tile */
 } hfg_layout;
 
 /* Builds the layout (host memory, malloc'd; free with hfg_layout_free) for at most `capacity` segment slots; with
@@ -91,6 +93,9 @@ typedef struct hfg_layout {
 int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
                      const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
                      int32_t capacity, int32_t granule, hfg_layout *out, char *err, size_t errlen);
+int hfg_layout_build_ex(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                        const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
+                        int32_t capacity, int32_t granule, int segments_only, hfg_layout *out, char *err, size_t errlen);
 void hfg_layout_free(hfg_layout *l);
 
 /* EM_computeAdjustmentBeta (hmm.c:301-316) for window i of a chunk. */

@@ -23,30 +23,16 @@ static double lay_ms(void) {
     return 1e3 * t.tv_sec + 1e-6 * t.tv_nsec;
 }
 
-/* submodules/common/common.c:142-148: min/max are int functions; double arguments are truncated at the call */
-static int imin_(int a, int b) { return a < b ? a : b; }
-static int imax_(int a, int b) { return a < b ? b : a; }
+#define HFG_LHD static inline
+#include "hfg_layout_inl.h"
 
 double hfg_beta(const hfg_config *cfg, const hfg_chunk_desc *ch, int i) {
-    if (!cfg->adjust_contig_ends) return 1.0;
-    const double frac = cfg->min_read_fraction_at_ends;
-    const int Lr = cfg->mean_read_length;
-    const int mid = imin_((int) (ch->s + (double) ch->window_len * (i + 0.5)),
-                          (int) ((ch->s + (double) ch->window_len * i + ch->e) / 2));
-    const int lo = imax_(mid - Lr + 1, (int) (-(1 - frac) * Lr));
-    const int hi = imin_(mid, (int) (ch->ctg_len - frac * Lr));
-    const double b = (double) (hi - lo) / Lr;
-    return b <= 0.25 ? 0.25 : b;
+    return hfg_beta_of(cfg->adjust_contig_ends, cfg->min_read_fraction_at_ends, cfg->mean_read_length, ch->ctg_len, ch->s,
+                       ch->e, ch->window_len, i);
 }
 
 static uint32_t validity_mask(const hfg_config *cfg, uint16_t cov, uint16_t mapq, uint16_t clip) {
-    const double rm = (double) mapq / (0.1 + cov);
-    const double rc = (double) clip / (0.1 + cov);
-    uint32_t m = 0;
-    if (rm > cfg->max_high_mapq_ratio) m |= 1u;          /* Dup invalid */
-    if (rm < cfg->min_high_mapq_ratio) m |= 2u;          /* Col invalid */
-    if (!(rc < cfg->min_highly_clipped_ratio)) m |= 4u;  /* END column valid */
-    return m;
+    return hfg_validity_mask(cfg->max_high_mapq_ratio, cfg->min_high_mapq_ratio, cfg->min_highly_clipped_ratio, cov, mapq, clip);
 }
 
 void hfg_layout_free(hfg_layout *l) {
@@ -59,6 +45,8 @@ void hfg_layout_free(hfg_layout *l) {
     free(l->tile_key);
     free(l->tile_begin);
     free(l->tile_cnt);
+    free(l->edge_head);
+    free(l->edge_tail);
     free(l->seg_start);
     free(l->seg_len);
     free(l->seg_chunk);
@@ -110,19 +98,13 @@ static void *pack_segments(void *arg) {
         for (int k = 0; k < len; k++) {
             const int w = a + k;
             const int64_t g = o + w;
-            uint32_t word = HFG_OBS_VALID;
-            word |= (uint32_t) (uint8_t) jb->cov[g];
-            if (w > 0) word |= (uint32_t) (uint8_t) jb->cov[g - 1] << 8;
-            word |= (uint32_t) jb->region[g] << 16;
-            word |= validity_mask(jb->cfg, jb->cov[g], jb->mapq[g], jb->clip[g]) << 22;
-            if (w > 0 && jb->region[g] != jb->region[g - 1]) word |= HFG_OBS_REGION_CHANGE;
-            if (w == 0) word |= HFG_OBS_CHUNK_START;
-            if (w == 1) word |= HFG_OBS_SECOND;
-            if (w == L - 1) word |= HFG_OBS_CHUNK_END;
-            if (w < jb->edge_head[c] || w >= L - jb->edge_tail[c]) {
+            const int is_edge = w < jb->edge_head[c] || w >= L - jb->edge_tail[c];
+            const uint32_t word = hfg_pack_word(validity_mask(jb->cfg, jb->cov[g], jb->mapq[g], jb->clip[g]), jb->cov[g],
+                                                w > 0 ? jb->cov[g - 1] : 0, jb->region[g], w > 0 ? jb->region[g - 1] : 0, w,
+                                                L, is_edge);
+            if (is_edge) {
                 /* (beta, beta0/beta, sqrt(beta0/beta)) */
                 const double b = hfg_beta(jb->cfg, ch, w);
-                word |= HFG_OBS_EDGE;
                 out->edge_beta[3 * e] = b;
                 out->edge_beta[3 * e + 1] = out->beta0 / b;
                 out->edge_beta[3 * e + 2] = sqrt(out->beta0 / b);
@@ -439,6 +421,7 @@ static int build_keys(hfg_layout *out) {
     out->n_keys = P;
     out->n_list = n_list;
     out->n_tiles = (int32_t) n_tiles;
+    out->tile_len = tile_len;
     out->klist = malloc(sizeof(int32_t) * (size_t) (n_list > 0 ? n_list : 1));
     out->tile_key = malloc(sizeof(int32_t) * (size_t) (n_tiles > 0 ? n_tiles : 1));
     out->tile_begin = malloc(sizeof(int32_t) * (size_t) (n_tiles > 0 ? n_tiles : 1));
@@ -508,6 +491,15 @@ static int64_t edges_before(int head, int tail, int L, int w) {
 int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
                      const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
                      int32_t capacity, int32_t granule, hfg_layout *out, char *err, size_t errlen) {
+    return hfg_layout_build_ex(cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, capacity, granule, 0, out, err,
+                               errlen);
+}
+
+/* segments_only != 0: stop after the segment table and the per-chunk contig-end extents (the device builds the packed
+ * words, the keys, their lists and tiles itself: hfg_layout_dev.cuh); only `region` is read then. */
+int hfg_layout_build_ex(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                        const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
+                        int32_t capacity, int32_t granule, int segments_only, hfg_layout *out, char *err, size_t errlen) {
     memset(out, 0, sizeof(*out));
     const double t_lay0 = lay_ms();
     int64_t W = 0;
@@ -589,15 +581,15 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
     out->n_seg = (int32_t) n_seg;
     out->beta0 = beta0;
     out->n_edge = n_edge;
-    out->obsT = calloc((size_t) smax * capacity, sizeof(uint32_t));
+    out->obsT = segments_only ? NULL : calloc((size_t) smax * capacity, sizeof(uint32_t));
     out->seg_start = calloc((size_t) capacity, sizeof(int32_t));
     out->seg_len = calloc((size_t) capacity, sizeof(int32_t));
     out->seg_chunk = calloc((size_t) capacity, sizeof(int32_t));
     out->seg_edge_begin = calloc((size_t) capacity + 1, sizeof(int32_t));
     out->chunk_offset = calloc((size_t) n_chunks + 1, sizeof(int64_t));
     out->edge_beta = malloc(sizeof(double) * 3 * (size_t) (n_edge > 0 ? n_edge : 1));
-    if (!out->obsT || !out->seg_start || !out->seg_len || !out->seg_chunk || !out->seg_edge_begin || !out->edge_beta ||
-        !out->chunk_offset)
+    if ((!segments_only && !out->obsT) || !out->seg_start || !out->seg_len || !out->seg_chunk || !out->seg_edge_begin ||
+        !out->edge_beta || !out->chunk_offset)
         goto nomem;
 
     /* pass 2: the segment table (O(#segments)) */
@@ -617,6 +609,19 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
     }
     for (int32_t c = 0; c <= n_chunks; c++) out->chunk_offset[c] = c < n_chunks ? chunks[c].offset : W;
 
+    if (W > HFG_KEY_MAX) {
+        free(runs); free(edge_head); free(edge_tail); free(chunk_edge_base);
+        hfg_layout_free(out);
+        snprintf(err, errlen, "number of windows (%lld) above the %d this build addresses per device", (long long) W, HFG_KEY_MAX);
+        return HFG_ERR_INVALID;
+    }
+    if (segments_only) {
+        out->edge_head = edge_head; /* ownership moves to the layout */
+        out->edge_tail = edge_tail;
+        free(runs); free(chunk_edge_base);
+        if (getenv("HFG_TIMING")) fprintf(stderr, "[hfg] layout: segments %.2f ms (host); keys on the device\n", lay_ms() - t_lay0);
+        return HFG_OK;
+    }
     /* pass 3: pack the observation words, in parallel over segments (pthreads, as the reference's own parser) */
     {
         int n_threads = (int) (W / 65536) + 1;
@@ -634,12 +639,6 @@ int hfg_layout_build(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk_de
         pack_segments(&jobs[0]);
         for (int t = 1; t < n_threads; t++)
             if (tids[t]) pthread_join(tids[t], NULL);
-    }
-    if (W > HFG_KEY_MAX) {
-        free(runs); free(edge_head); free(edge_tail); free(chunk_edge_base);
-        hfg_layout_free(out);
-        snprintf(err, errlen, "number of windows (%lld) above the %d this build addresses per device", (long long) W, HFG_KEY_MAX);
-        return HFG_ERR_INVALID;
     }
     const double t_keys0 = lay_ms();
     if (!build_keys(out)) goto nomem;

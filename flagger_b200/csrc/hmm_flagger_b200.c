@@ -446,7 +446,24 @@ int main(int argc, char *argv[]) {
     int8_t *labels = malloc((size_t) d->n_windows);
     int iter = 1, converged = 0;
     double loglik = 0.0;
-    while (iter <= iterations && !converged) {
+    if (!accelerate && !write_params) {
+        /* plain EM with nothing to write between iterations: the whole loop -- every E-step, the M-steps, the convergence
+         * test and the final inference -- is queued on the device at once (hfg_em_*: parameters stay in HBM, the M-step runs
+         * in the tail of the E-step kernel); the host comes back for the log-likelihoods, the parameters and the labels */
+        double *lls = malloc(sizeof(double) * ((size_t) iterations + 1));
+        int n_esteps = 0, rc_e = hfg_em_begin(ctx, alpha, params, tol, iterations + 1);
+        for (int it = 0; it < iterations && rc_e == HFG_OK; it++) rc_e = hfg_em_enqueue(ctx, 0);
+        if (rc_e == HFG_OK) rc_e = hfg_em_enqueue(ctx, 1);
+        if (rc_e == HFG_OK) rc_e = hfg_em_finish(ctx, params, lls, &n_esteps, &converged, labels);
+        if (rc_e != HFG_OK) {
+            fprintf(stderr, "%s\n", hfg_last_error(ctx));
+            exit(EXIT_FAILURE);
+        }
+        for (int k = 0; k < n_esteps; k++) fprintf(ll_file, "%d\t%d\t%.4f\n", k, k, lls[k]);
+        iter = n_esteps; /* n_esteps - 1 EM iterations, then the final inference */
+        free(lls);
+    }
+    while ((accelerate || write_params) && iter <= iterations && !converged) {
         /* --accelerate: E(p0), M, E(p1), M, SQUAREM candidate p' chosen with forward-only passes, E(p') (:382-416) */
         double rate = 0.0;
         const int rc_e = accelerate ? hfg_squarem_iteration(ctx, alpha, params, stats, tol, &loglik, &rate)
@@ -468,11 +485,13 @@ int main(int argc, char *argv[]) {
     if (converged) fprintf(stderr, "[%s] Parameters converged after %d iterations (tol=%.2e)\n", stamp(), iter - 1, tol);
     else fprintf(stderr, "[%s] Parameter estimation stopped (not yet converged based on the given tolerance) after %d iterations (tol=%.2e)\n", stamp(), iter - 1, tol);
     /* final inference with the final parameters (:464) */
-    if (hfg_em_iteration(ctx, alpha, params, stats, &loglik, labels) != HFG_OK) {
-        fprintf(stderr, "%s\n", hfg_last_error(ctx));
-        exit(EXIT_FAILURE);
+    if (accelerate || write_params) {
+        if (hfg_em_iteration(ctx, alpha, params, stats, &loglik, labels) != HFG_OK) {
+            fprintf(stderr, "%s\n", hfg_last_error(ctx));
+            exit(EXIT_FAILURE);
+        }
+        fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, accelerate ? 3 * (iter - 1) : iter - 1, loglik);
     }
-    fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, accelerate ? 3 * (iter - 1) : iter - 1, loglik);
     fclose(ll_file);
     write_transition_tsv(out_dir, "final", &cfg, params);
     write_emission_tsv(out_dir, "final", &cfg, params);

@@ -117,6 +117,11 @@ int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_desc *chunks,
 
 int64_t hfg_num_windows(const hfg_ctx *ctx);
 
+/* Page-locked host memory (cudaMallocHost / cudaFreeHost behind a plain-C face).  A `labels` buffer obtained here is
+ * written by the device directly; any other host pointer works too and costs one staging copy per call. */
+void *hfg_host_alloc(size_t bytes);
+void hfg_host_free(void *p);
+
 /* ---- the hot path ------------------------------------------------------------------------------ */
 
 /* One E-step over all chunks == EM_runOneIterationForList (hmm.c:739-780):
@@ -251,6 +256,10 @@ int hfg_debug_layout_check(const hfg_config *cfg, int32_t n_chunks, const hfg_ch
                            const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
                            int32_t capacity, int64_t *summary);
 double hfg_debug_beta(const hfg_config *cfg, const hfg_chunk_desc *chunk, int window);
+/* GPU: hfg_set_chunks builds the observation keys, their window lists and tiles on the device; this rebuilds them with the
+ * host builder from the same inputs and compares every table bit for bit (HFG_OK = identical). */
+int hfg_debug_layout_compare(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                             const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region);
 
 #ifdef __cplusplus
 }

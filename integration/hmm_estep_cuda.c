@@ -119,7 +119,7 @@ static void bind(stList *emList, HMM *model) {
     Binding *b = &g_bind;
     if (b->ctx) {
         hfg_destroy(b->ctx);
-        free(b->ems); free(b->offsets); free(b->labels); free(b->params); free(b->stats); free(b->posteriors);
+        free(b->ems); free(b->offsets); hfg_host_free(b->labels); free(b->params); free(b->stats); free(b->posteriors);
         memset(b, 0, sizeof(*b));
     }
     if (model->modelType == MODEL_NEGATIVE_BINOMIAL || model->numberOfStates != HFG_NUM_STATES) {
@@ -176,7 +176,7 @@ static void bind(stList *emList, HMM *model) {
     if (hfg_create(&b->ctx, &b->cfg) != HFG_OK) die("hfg_create", NULL);
     if (hfg_set_chunks(b->ctx, b->nChunks, desc, cov, mq, cl, reg) != HFG_OK) die("hfg_set_chunks", b->ctx);
     free(desc); free(cov); free(mq); free(cl); free(reg);
-    b->labels = malloc(W);
+    b->labels = hfg_host_alloc(W); /* page-locked: the device writes the labels into it directly */
     b->params = malloc(sizeof(hfg_region_params) * model->numberOfRegions);
     b->stats = malloc(sizeof(hfg_region_stats) * model->numberOfRegions);
     b->posteriors = NULL;

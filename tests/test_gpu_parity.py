@@ -253,3 +253,75 @@ def test_device_em_loop_stops_at_convergence_like_the_reference_loop(orc):
     post = gpu.posteriors()
     assert np.array_equal(post.argmax(axis=1).astype(np.int8), lab2)
     gpu.close()
+
+
+def test_pinned_label_buffer_and_repeated_calls(orc):
+    """Labels written by the device straight into a page-locked caller buffer (hfg_host_alloc) equal those delivered
+    through the staging copy, call after call (the kernel clears its own error flags and writes the statistics block
+    into pinned memory itself), also when the two kinds of buffer alternate."""
+    wl = synth.small_mixed(n_regions=3, seed=17)
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=3, n_col_comps=K)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    out = orc.estep(cfg, wl, synth.HIFI_ALPHA, params)
+    pinned = api.PinnedArray(wl.n_windows, np.int8)
+    for rep in range(3):
+        pinned.array[:] = -7
+        s1, ll1, lab1 = gpu.em_iteration(synth.HIFI_ALPHA, params, labels=pinned.array)
+        assert lab1 is pinned.array and np.array_equal(pinned.array, out["labels"])
+        s2, ll2, lab2 = gpu.em_iteration(synth.HIFI_ALPHA, params)
+        assert np.array_equal(lab2, out["labels"]) and ll1 == ll2
+        assert np.array_equal(_abi.stats_as_flat(s1), _abi.stats_as_flat(s2))
+        assert abs(ll1 - out["loglik"]) <= TOL_LOGLIK * abs(out["loglik"])
+    gpu.close()
+    pinned.free()
+
+
+def test_many_distinct_observation_keys(orc):
+    """The kernel evaluates emissions once per distinct (x, previous x, region, mask, beta) key.  Coverage drawn uniformly
+    from 0..250 with random MAPQ / clipping fractions makes almost every window its own key (the worst case for the key
+    table and the per-key statistics lists, one window per tile): results must not depend on how many keys there are."""
+    import dataclasses
+    wl = synth.small_mixed(n_regions=3, seed=23)
+    rng = np.random.default_rng(7)
+    W = wl.n_windows
+    cov = rng.integers(0, 251, W).astype(np.uint16)
+    mapq = (cov * rng.choice([0.0, 0.1, 0.5, 0.9, 1.0], W)).astype(np.uint16)
+    clip = (cov * rng.choice([0.0, 0.0, 0.0, 1.0], W)).astype(np.uint16)
+    wl = dataclasses.replace(wl, cov=cov, cov_high_mapq=mapq, cov_high_clip=clip)
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=3, n_col_comps=K)
+    ok, summary = api.layout_check(cfg, wl, 2048)
+    assert ok and summary[4] > 0.8 * W  # nearly one key per window
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    out = orc.estep(cfg, wl, synth.HIFI_ALPHA, params)
+    assert out["rc"] == 0
+    _check_estep(gpu, out, wl, synth.HIFI_ALPHA, params)
+    pg, llg, labg = gpu.run_em(synth.HIFI_ALPHA, params, 3, tol=1e-12)
+    eo = orc.run_em(cfg, wl, synth.HIFI_ALPHA, params, 3, tol=1e-12)
+    assert eo["rc"] == 0 and len(llg) == len(eo["logliks"])
+    assert np.all(np.abs(llg - eo["logliks"]) <= TOL_LOGLIK * np.abs(eo["logliks"]))
+    assert np.array_equal(labg, eo["labels"])
+    gpu.close()
+
+
+@pytest.mark.parametrize("factory,n_regions,adjust", [
+    (lambda: synth.small_mixed(n_regions=3, seed=1), 3, True),
+    (lambda: synth.small_mixed(n_regions=7, seed=2), 7, False),
+    (lambda: synth.config1(), 1, True),
+    (lambda: synth.config3(n_contigs=700, seed=3), 1, True),
+    (lambda: synth.config2(total_bp=400_000_000, seed=4), 1, True),
+    (lambda: synth.config4(total_bp=300_000_000, seed=5), 7, True),
+])
+def test_device_layout_equals_host_layout(factory, n_regions, adjust):
+    """hfg_set_chunks builds the observation keys, their window lists and the statistics tiles on the device (radix sorts
+    and scans, hfg_layout_dev.cuh); the host builder (pthread hash tables, hfg_layout.c) must produce the same bits in
+    every table: key words, key descriptors, betas, lists, tiles, region offsets."""
+    wl = factory()
+    cfg = _abi.make_config(n_regions=n_regions, adjust_contig_ends=adjust, mean_read_length=wl.avg_alignment_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    ok, msg = gpu.layout_matches_host(wl)
+    assert ok, msg
+    gpu.close()
