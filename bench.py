@@ -122,7 +122,7 @@ class ClockSampler:
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
                 self.rows.append([str(self.idx), str(sm), str(mx), "", ""] +
                                  ["Active" if r & b else "Not Active" for b in bits.values()])
-                self.nvml_stop.wait(0.005)
+                self.nvml_stop.wait(0.02)
         self.t = threading.Thread(target=loop, daemon=True)
         self.t.start()
         self.proc = "nvml"

@@ -43,6 +43,7 @@ struct hfg_ctx {
     long long *d_phase_clock;
     void *d_arena;   /* one device allocation behind all per-run buffers */
     size_t arena_bytes;
+    size_t h_out_bytes, h_labels_bytes;
     void *d_keyblock; /* the buffers sized by the number of observation keys (key table, descriptors, betas) */
     size_t keyblock_bytes;
     int32_t capacity_arg; /* the slot count the layout was asked for (before trimming): hfg_debug_layout_compare */
@@ -223,8 +224,12 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
  * 3 Gbp job costs 0.4 ms on a quiet driver but was measured at 6-60 ms on a freshly booted box, more than the job's upload.
  * hfg_release_cached_memory() returns it to the driver; HFG_NO_ARENA_CACHE=1 disables the cache. */
 static pthread_mutex_t g_cache_mu = PTHREAD_MUTEX_INITIALIZER;
-#define HFG_CACHE_SLOTS 2 /* the per-run arena and the key-table block */
-static struct { void *ptr; size_t bytes; int device; } g_cache[HFG_CACHE_SLOTS] = {{NULL, 0, -1}, {NULL, 0, -1}};
+#define HFG_CACHE_SLOTS 4 /* kinds: 0 per-run arena, 1 key block (device); 2 result block, 3 label staging (pinned host) */
+static struct { void *ptr; size_t bytes; int device; } g_cache[HFG_CACHE_SLOTS] = {{NULL, 0, -1}, {NULL, 0, -1}, {NULL, 0, -1},
+                                                                                     {NULL, 0, -1}};
+static void cache_free(void *p, int kind) {
+    if (kind >= 2) cudaFreeHost(p); else cudaFree(p);
+}
 
 /* kind 0: the per-run arena; kind 1: the key block.  One cached block of each kind; a newly released block replaces the
  * cached one of its kind (the next job most likely looks like the last one). */
@@ -243,7 +248,7 @@ static void arena_release(void *ptr, size_t bytes, int device, int kind) {
     }
     if (drop) {
         cudaSetDevice(drop_dev);
-        cudaFree(drop);
+        cache_free(drop, kind);
     }
     cudaSetDevice(device);
 }
@@ -261,7 +266,7 @@ static void *arena_acquire(size_t bytes, int device, size_t *got, int kind) {
     }
     pthread_mutex_unlock(&g_cache_mu);
     if (!ptr) {
-        if (cudaMalloc(&ptr, bytes) != cudaSuccess) return NULL;
+        if ((kind >= 2 ? cudaMallocHost(&ptr, bytes) : cudaMalloc(&ptr, bytes)) != cudaSuccess) return NULL;
         *got = bytes;
     }
     return ptr;
@@ -272,7 +277,7 @@ extern "C" void hfg_release_cached_memory(void) {
     for (int i = 0; i < HFG_CACHE_SLOTS; i++)
         if (g_cache[i].ptr) {
             cudaSetDevice(g_cache[i].device);
-            cudaFree(g_cache[i].ptr);
+            cache_free(g_cache[i].ptr, i);
             g_cache[i].ptr = NULL;
             g_cache[i].bytes = 0;
             g_cache[i].device = -1;
@@ -291,8 +296,8 @@ static void free_device(hfg_ctx *ctx) {
     ctx->d_keyblock = NULL;
     ctx->keyblock_bytes = 0;
     cudaFree(ctx->d_post);
-    if (ctx->h_out) cudaFreeHost(ctx->h_out);
-    if (ctx->h_labels) cudaFreeHost(ctx->h_labels);
+    arena_release(ctx->h_out, ctx->h_out_bytes, ctx->device, 2);
+    arena_release(ctx->h_labels, ctx->h_labels_bytes, ctx->device, 3);
     ctx->d_arena = NULL;
     ctx->d_wkeyT = ctx->d_kdesc = NULL;
     ctx->d_seg_start = ctx->d_seg_len = ctx->d_block_reset = ctx->d_err = NULL;
@@ -454,8 +459,12 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         ctx->em_max = HFG_EM_LOGLIK_SLOTS;
     }
     tm[2] = wall_ms();
-    CU(cudaMallocHost((void **) &ctx->h_out, out_doubles * sizeof(double)));
-    CU(cudaMallocHost((void **) &ctx->h_labels, w));
+    ctx->h_out = (double *) arena_acquire(out_doubles * sizeof(double), ctx->device, &ctx->h_out_bytes, 2);
+    ctx->h_labels = (int8_t *) arena_acquire(w, ctx->device, &ctx->h_labels_bytes, 3);
+    if (!ctx->h_out || !ctx->h_labels) {
+        cudaGetLastError();
+        return fail(ctx, HFG_ERR_NOMEM, "hfg_set_chunks: cannot allocate page-locked host memory");
+    }
     CU(cudaMemcpyAsync(ctx->d_seg_start, l->seg_start, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_len, l->seg_len, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_labels, 0xff, w, ctx->stream));
