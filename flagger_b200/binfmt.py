@@ -252,3 +252,36 @@ def write_random_rle_cov(path, contig_lens, seed=0, n_regions=3, with_truth=True
                     line += f"\t{int(rng.integers(-1, 4))}"
                 f.write(line + "\n")
                 pos += ln
+
+
+def write_summary_native(inp, out_path, prediction=None, use_truth=True, label_names=_abi.STATE_NAMES + ("Unk",),
+                         overlap_ratio_threshold=0.4, chunk_len=20_000_000, window_len=4000):
+    """prediction_summary_<suffix>.tsv through the C writer (hfg_write_summary_tsv, csrc/hfg_summary.c) for the input file
+    `inp` (.cov / .cov.gz / .bin), the per-window `prediction` labels (int8, or None) and the file's own truth labels."""
+    L = _io_lib()
+    out = _C.POINTER(_CovData)()
+    err = _C.create_string_buffer(512)
+    if str(inp).endswith(".bin"):
+        rc = L.hfg_read_bin(str(inp).encode(), _C.byref(out), err, _C.c_size_t(512))
+    else:
+        rc = L.hfg_read_cov(str(inp).encode(), _C.c_int32(chunk_len), _C.c_int32(window_len), _C.byref(out), err, _C.c_size_t(512))
+    if rc != 0:
+        raise ValueError(f"reader: {err.value.decode()}")
+    try:
+        d = out.contents
+        truth = d.truth if (use_truth and d.truth_available) else None
+        pred = None
+        if prediction is not None:
+            pred = np.ascontiguousarray(prediction, np.int8)
+            assert pred.shape[0] == int(d.n_windows)
+        names = None
+        n_labels = len(_abi.STATE_NAMES)
+        if label_names is not None:
+            names = (_C.c_char_p * len(label_names))(*[s.encode() for s in label_names])
+            n_labels = len(label_names) - 1
+        rc = L.hfg_write_summary_tsv(str(out_path).encode(), out, _abi.ptr(pred), truth, names, _C.c_int(n_labels),
+                                     _C.c_double(overlap_ratio_threshold), err, _C.c_size_t(512))
+        if rc != 0:
+            raise ValueError(f"hfg_write_summary_tsv: {err.value.decode()}")
+    finally:
+        L.hfg_cov_free(out)

@@ -609,11 +609,9 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
         a.ncomp[s] = cfg->n_comps[s];
         a.gbase[s] = g;
         if (cl.is_gaussian[s]) g += cfg->n_comps[s];
-        a.zero_slot_used[s] = 0;
         for (int pre = 0; pre < HFG_NS; pre++) {
             a.cls[pre][s] = cl.cls[pre][s];
             a.alpha[pre][s] = cl.is_gaussian[s] ? alpha[pre * HFG_NS + s] : 0.0;
-            if (cl.cls[pre][s] == s) a.zero_slot_used[s] = 1;
         }
     }
     a.G = g;
@@ -1016,6 +1014,23 @@ extern "C" int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *
                           double convergence_tol, double *logliks, int *n_esteps, int8_t *labels) {
     if (!ctx || !params || !logliks || !n_esteps) return HFG_ERR_INVALID;
     if (max_iterations < 0) max_iterations = 0;
+    if (max_iterations + 1 > HFG_EM_LOGLIK_SLOTS) {
+        /* longer than the device loop records: the same loop with the host between the iterations */
+        const int R = ctx->cfg.n_regions;
+        hfg_region_stats *stats = (hfg_region_stats *) malloc(sizeof(hfg_region_stats) * (size_t) R);
+        if (!stats) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+        int iter = 1, converged = 0, k = 0, rc = HFG_OK;
+        while (iter <= max_iterations && !converged) {
+            if ((rc = hfg_em_iteration(ctx, alpha, params, stats, &logliks[k], NULL)) != HFG_OK) break;
+            k++;
+            if ((rc = hfg_mstep(&ctx->cfg, params, stats, convergence_tol, &converged)) != HFG_OK) break;
+            iter++;
+        }
+        if (rc == HFG_OK && (rc = hfg_em_iteration(ctx, alpha, params, stats, &logliks[k], labels)) == HFG_OK) k++;
+        *n_esteps = k;
+        free(stats);
+        return rc;
+    }
     int rc = hfg_em_begin(ctx, alpha, params, convergence_tol, max_iterations + 1);
     for (int it = 0; it < max_iterations && rc == HFG_OK; it++) rc = hfg_em_enqueue(ctx, 0);
     if (rc == HFG_OK) rc = hfg_em_enqueue(ctx, 1);

@@ -100,7 +100,6 @@ struct EstepArgs {
     double alpha[HFG_NS][HFG_NS];   /* [pre][s]; 0 for non-Gaussian states */
     int32_t class_state[HFG_MAX_CLASSES];
     double class_alpha[HFG_MAX_CLASSES];
-    int32_t zero_slot_used[HFG_NS]; /* does any preState use the alpha==0 slot of state s */
     int32_t is_gauss[HFG_NS], ncomp[HFG_NS], gbase[HFG_NS];
     int32_t G;                      /* total Gaussian components */
     double inv_one_minus_alpha[HFG_NS][HFG_NS]; /* 1 / (1 - alpha[pre][s]) */

@@ -6,9 +6,10 @@
  *
  * Outputs written into --outputDir (formats as the reference):
  *   loglikelihood.tsv, transition_{initial,iteration_k,final}.tsv, emission_{...}.tsv, final_flagger_prediction.bed,
- *   posterior_prediction_final.bed (-P), chunks.c_<C>.w_<W>.bin (-B).
- * --accelerate (SQUAREM) runs through hfg_squarem_iteration.  NOT written: prediction_summary_*.tsv (the reference's
- * 1700-line summary_table module; link libhfg into the reference binary instead when you need them -- INTEGRATION.md).
+ *   posterior_prediction_final.bed (-P), chunks.c_<C>.w_<W>.bin (-B), prediction_summary_{initial,iteration_k,final}.tsv
+ *   (overlap_based and base_level tables on the flat label array, hfg_write_summary_tsv; -k for every iteration).
+ * --accelerate (SQUAREM) runs through hfg_squarem_iteration.  NOT written: the truth_based_auN rows and the
+ * *.benchmarking*.tsv files (inputs with truth labels only), --binArrayFile size bins.
  */
 #include <getopt.h>
 #include <math.h>
@@ -279,6 +280,16 @@ static int ends_with(const char *s, const char *suffix) {
     return a >= b && strcmp(s + a - b, suffix) == 0;
 }
 
+/* writeBenchmarkingStats (src/hmm_flagger.c:134-161) on the flat label array */
+static void write_summary(const char *dir, const char *suffix, const hfg_cov_data *d, const int8_t *labels,
+                          char *const *label_names, double overlap_thr) {
+    char path[4096], err[512];
+    snprintf(path, sizeof(path), "%s/prediction_summary_%s.tsv", dir, suffix);
+    if (hfg_write_summary_tsv(path, d, labels, d->truth_available ? d->truth : NULL, (const char *const *) label_names,
+                              HFG_NUM_STATES, overlap_thr, err, sizeof(err)) != HFG_OK)
+        die(err);
+}
+
 static struct option long_options[] = {{"input", required_argument, NULL, 'i'},
                                        {"preset", required_argument, NULL, 'x'},
                                        {"iterations", required_argument, NULL, 'n'},
@@ -312,7 +323,11 @@ static struct option long_options[] = {{"input", required_argument, NULL, 'i'},
 int main(int argc, char *argv[]) {
     const char *track = "final_hmm_flagger", *preset = "hifi", *input = NULL, *alpha_tsv = NULL, *contigs = NULL, *out_dir = NULL;
     int iterations = 100, adjust_ends = 1, collapsed = -1, write_params = 0, write_post = 0, chunk_len = 20000000;
-    int window_len = -1, dump_bin = 0, device = 0, model_type = -1, accelerate = 0;
+    int window_len = -1, dump_bin = 0, device = 0, model_type = -1, accelerate = 0, write_bench = 0;
+    double overlap_thr = 0.4; /* --overlapRatioThreshold (src/hmm_flagger.c:632) */
+    char *label_names[64];
+    int n_label_names = 0;
+    const char *bin_array_file = NULL;
     double tol = 0.001, max_mapq = 0.25, min_mapq = 0.75, min_frac = -1.0;
     int min_len[4] = {0, 0, 0, 0};
     int c;
@@ -349,8 +364,18 @@ int main(int argc, char *argv[]) {
                 break;
             }
             case 's': accelerate = 1; break;
-            case '@': case 'a': case 'k': case 'v': case 'l': case 'D':
-                break; /* accepted for command-line compatibility; no summary tables / thread pool here */
+            case 'k': write_bench = 1; break;
+            case 'v': overlap_thr = atof(optarg); break;
+            case 'a': bin_array_file = optarg; break;
+            case 'l': {
+                /* --labelNames: comma-separated, "Unk" appended (src/hmm_flagger.c:721-724) */
+                char *copy = strdup(optarg);
+                for (char *tok = strtok(copy, ","); tok && n_label_names < 62; tok = strtok(NULL, ",")) label_names[n_label_names++] = tok;
+                label_names[n_label_names++] = "Unk";
+                break;
+            }
+            case '@': case 'D':
+                break; /* accepted for command-line compatibility: no thread pool here, --initialRandomDev 0 only */
             default:
                 fprintf(stderr, "Usage: %s -i <INPUT.cov|.cov.gz|.bin> -o <OUTPUT_DIR> [options of hmm_flagger v1.2.0] [--device N]\n", argv[0]);
                 return 1;
@@ -358,6 +383,10 @@ int main(int argc, char *argv[]) {
     }
     const double t_start = now_s();
     if (!input) die("Input path cannot be NULL.");
+    if (n_label_names && n_label_names - 1 != HFG_NUM_STATES)
+        die("Number of label names does not match the number of labels (4: Err,Dup,Hap,Col)."); /* summary_table.c:1682-1689 */
+    if (bin_array_file)
+        fprintf(stderr, "[%s] Warning: --binArrayFile is not supported here; the summary tables use the single size bin ALL_SIZES.\n", stamp());
     if (tol <= 0.0 || tol > 1.0) die("convergence tol should be between 0 and 1.");
     struct stat st;
     if (!out_dir) die("--outputDir, -o should be specified.");
@@ -444,36 +473,50 @@ int main(int argc, char *argv[]) {
     if (hfg_set_chunks(ctx, d->n_chunks, d->chunks, d->cov, d->cov_high_mapq, d->cov_high_clip, d->region) != HFG_OK)
         die(hfg_last_error(ctx));
     int8_t *labels = malloc((size_t) d->n_windows);
-    int iter = 1, converged = 0;
+    int iter = 1, converged = 0, final_done = 0;
     double loglik = 0.0;
-    if (!accelerate && !write_params) {
-        /* plain EM with nothing to write between iterations: the whole loop -- every E-step, the M-steps, the convergence
-         * test and the final inference -- is queued on the device at once (hfg_em_*: parameters stay in HBM, the M-step runs
-         * in the tail of the E-step kernel); the host comes back for the log-likelihoods, the parameters and the labels */
-        double *lls = malloc(sizeof(double) * ((size_t) iterations + 1));
-        int n_esteps = 0, rc_e = hfg_em_begin(ctx, alpha, params, tol, iterations + 1);
-        for (int it = 0; it < iterations && rc_e == HFG_OK; it++) rc_e = hfg_em_enqueue(ctx, 0);
-        if (rc_e == HFG_OK) rc_e = hfg_em_enqueue(ctx, 1);
-        if (rc_e == HFG_OK) rc_e = hfg_em_finish(ctx, params, lls, &n_esteps, &converged, labels);
-        if (rc_e != HFG_OK) {
-            fprintf(stderr, "%s\n", hfg_last_error(ctx));
-            exit(EXIT_FAILURE);
+    /* Iterations whose results are needed on the host between E-steps run through the blocking call + host M-step: the first
+     * one always (its labels are prediction_summary_initial.tsv, src/hmm_flagger.c:361-379), all of them with
+     * --accelerate, -w or -k.  Otherwise the REST of the loop -- every further E-step, the M-steps, the convergence test and
+     * the final inference -- is queued on the device at once (hfg_em_*: parameters stay in HBM, the M-step runs in the tail
+     * of the E-step kernel) and the host comes back for the log-likelihoods, the parameters and the labels. */
+    const int per_iteration_outputs = accelerate || write_params || write_bench;
+    while (iter <= iterations && !converged) {
+        if (!per_iteration_outputs && iter > 1 && iterations - iter + 2 <= 4096) {
+            const int remaining = iterations - iter + 1;
+            double *lls = malloc(sizeof(double) * ((size_t) remaining + 1));
+            int n_esteps = 0, rc_d = hfg_em_begin(ctx, alpha, params, tol, remaining + 1);
+            for (int it = 0; it < remaining && rc_d == HFG_OK; it++) rc_d = hfg_em_enqueue(ctx, 0);
+            if (rc_d == HFG_OK) rc_d = hfg_em_enqueue(ctx, 1);
+            if (rc_d == HFG_OK) rc_d = hfg_em_finish(ctx, params, lls, &n_esteps, &converged, labels);
+            if (rc_d != HFG_OK) {
+                fprintf(stderr, "%s\n", hfg_last_error(ctx));
+                exit(EXIT_FAILURE);
+            }
+            for (int k = 0; k < n_esteps; k++) fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1 + k, iter - 1 + k, lls[k]);
+            iter += n_esteps - 1; /* n_esteps - 1 EM iterations, then the final inference */
+            free(lls);
+            final_done = 1;
+            break;
         }
-        for (int k = 0; k < n_esteps; k++) fprintf(ll_file, "%d\t%d\t%.4f\n", k, k, lls[k]);
-        iter = n_esteps; /* n_esteps - 1 EM iterations, then the final inference */
-        free(lls);
-    }
-    while ((accelerate || write_params) && iter <= iterations && !converged) {
         /* --accelerate: E(p0), M, E(p1), M, SQUAREM candidate p' chosen with forward-only passes, E(p') (:382-416) */
         double rate = 0.0;
+        const int want_labels = iter == 1 || write_bench;
         const int rc_e = accelerate ? hfg_squarem_iteration(ctx, alpha, params, stats, tol, &loglik, &rate)
-                                    : hfg_em_iteration(ctx, alpha, params, stats, &loglik, NULL);
+                                    : hfg_em_iteration(ctx, alpha, params, stats, &loglik, want_labels ? labels : NULL);
         if (rc_e != HFG_OK) {
             fprintf(stderr, "%s\n", hfg_last_error(ctx));
             exit(EXIT_FAILURE);
         }
         if (accelerate) fprintf(stderr, "[%s] Computed alpha rate for accelerating EM = %.4f\n", stamp(), rate);
         fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, accelerate ? 3 * (iter - 1) : iter - 1, loglik);
+        if (want_labels) {
+            /* the labels of this iteration's (last) E-step (src/hmm_flagger.c:361-379) */
+            if (accelerate && hfg_get_labels(ctx, labels) != HFG_OK) die(hfg_last_error(ctx));
+            if (iter == 1) snprintf(suffix, sizeof(suffix), "initial");
+            else snprintf(suffix, sizeof(suffix), accelerate ? "iteration_accelerated_%d" : "iteration_%d", iter - 1);
+            write_summary(out_dir, suffix, d, labels, n_label_names ? label_names : NULL, overlap_thr);
+        }
         hfg_mstep(&cfg, params, stats, tol, &converged);
         if (write_params) {
             snprintf(suffix, sizeof(suffix), accelerate ? "iteration_accelerated_%d" : "iteration_%d", iter);
@@ -485,13 +528,14 @@ int main(int argc, char *argv[]) {
     if (converged) fprintf(stderr, "[%s] Parameters converged after %d iterations (tol=%.2e)\n", stamp(), iter - 1, tol);
     else fprintf(stderr, "[%s] Parameter estimation stopped (not yet converged based on the given tolerance) after %d iterations (tol=%.2e)\n", stamp(), iter - 1, tol);
     /* final inference with the final parameters (:464) */
-    if (accelerate || write_params) {
+    if (!final_done) {
         if (hfg_em_iteration(ctx, alpha, params, stats, &loglik, labels) != HFG_OK) {
             fprintf(stderr, "%s\n", hfg_last_error(ctx));
             exit(EXIT_FAILURE);
         }
         fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, accelerate ? 3 * (iter - 1) : iter - 1, loglik);
     }
+    write_summary(out_dir, "final", d, labels, n_label_names ? label_names : NULL, overlap_thr);
     fclose(ll_file);
     write_transition_tsv(out_dir, "final", &cfg, params);
     write_emission_tsv(out_dir, "final", &cfg, params);

@@ -1,6 +1,6 @@
 /*
  * hfg_io.h -- the data formats on either side of the hot path: readers for the inputs
- * `hmm_flagger` accepts.  Plain C, no GPU involved.  The arrays a reader returns are exactly what hfg_set_chunks
+ * `hmm_flagger` accepts, and the summary-table writer on flat labels.  Plain C, no GPU involved.  The arrays a reader returns are exactly what hfg_set_chunks
  * (include/hfg.h) takes.
  *
  * Replaces, with the same window semantics:
@@ -48,6 +48,19 @@ int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_co
 int hfg_read_bin(const char *path, hfg_cov_data **out, char *err, size_t errlen);
 
 void hfg_cov_free(hfg_cov_data *data);
+
+/* ---- writers ------------------------------------------------------------------------------------------------------ */
+
+/* prediction_summary_<suffix>.tsv (writeBenchmarkingStats, programs/src/hmm_flagger.c:134-161;
+ * SummaryTableList_createAndWriteAllTables, programs/submodules/summary_table/summary_table.c:1663-1747) from FLAT label
+ * arrays: per region and per annotation, the number of label blocks (overlap_based) and of bases (base_level) for every
+ * label, counts then percentages, in the reference's row order and formats.  prediction / truth: one int8 per window
+ * (-1 = none, counted as "Unk"); either may be NULL (that comparison is left out).  label_names: n_labels + 1 names, the
+ * last one for "Unk" (NULL: label_0 ... label_unk).  Single size bin ALL_SIZES; the truth_based_auN metric and the
+ * *.benchmarking*.tsv files (only written by the reference when truth labels exist) are not produced. */
+int hfg_write_summary_tsv(const char *path, const hfg_cov_data *data, const int8_t *prediction, const int8_t *truth,
+                          const char *const *label_names, int n_labels, double overlap_ratio_threshold, char *err,
+                          size_t errlen);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ wl_full = synth.config2()
 K = api.best_num_collapsed_comps(int(wl_full.cov.max()), wl_full.region_coverages)
 cfg = _abi.make_config(n_col_comps=K)
 p = api.model_init(cfg, wl_full.region_coverages, wl_full.window_len)
-names = ["A", "B", "wait1", "C1(t0)", "C2", "Dreduce", "wait2"]
+names = ["T+bar1", "A+B", "wait2", "C1(t0)", "C2+bar3", "S+Dred", "wait4"]  # see profiles/phase_timeline.py
 for world, wpt in ((8, 1), (8, 2), (16, 1), (4, 1), (4, 4)):
     wl = hdist.shard_chunks(wl_full, 0, world)
     os.environ["HFG_MIN_WPT"] = str(wpt)

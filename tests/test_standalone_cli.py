@@ -22,9 +22,9 @@ needs_ref = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/hmm_
 
 def _run(binary, inp, out, extra=(), check=True):
     os.makedirs(out, exist_ok=True)
-    cmd = [binary, "-i", inp, "-o", out, "-W", "4000", "-C", "1000000", "-n", "6", "-t", "1e-12", *extra]
+    cmd = [binary, "-i", inp, "-o", out, "-W", "4000", "-C", "1000000", "-n", "6", "-t", "1e-12", "-l", "Err,Dup,Hap,Col", *extra]
     if binary == REF:
-        cmd += ["-l", "Err,Dup,Hap,Col", "-@", "4"]
+        cmd += ["-@", "4"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     if check:
         assert r.returncode == 0, r.stderr[-2000:]
@@ -98,6 +98,12 @@ def _compare_runs(ref_out, cli_out, posterior=False):
         assert len(la) == len(lb) and la[0] == lb[0], name
         a, b = _table(os.path.join(ref_out, name)), _table(os.path.join(cli_out, name))
         assert a.shape == b.shape and np.allclose(a, b, rtol=2e-5, atol=1e-12), name
+    # summary tables on the flat labels: byte-identical (these inputs carry no truth labels, so the reference writes no
+    # truth_based_auN rows and the files hold exactly what hfg_write_summary_tsv covers)
+    summaries = [n for n in sorted(os.listdir(ref_out)) if n.startswith("prediction_summary_")]
+    assert "prediction_summary_initial.tsv" in summaries and "prediction_summary_final.tsv" in summaries
+    for name in summaries:
+        assert _read(os.path.join(ref_out, name)) == _read(os.path.join(cli_out, name)), name
     if posterior:
         name = "posterior_prediction_final.bed"
         ra, rb = open(os.path.join(ref_out, name)).readlines(), open(os.path.join(cli_out, name)).readlines()
@@ -117,6 +123,8 @@ def _compare_runs(ref_out, cli_out, posterior=False):
     ("cov", ("-e",)),                                # --disableAdjustContigEnds
     ("cov", ("-q", "0.1", "--minHighMapqRatio", "0.9", "-f", "0.5")),
     ("bin", ("-s", "-w")),                           # --accelerate (SQUAREM)
+    ("bin", ("-k",)),                                # --writeBenchmarkingStatsPerIteration
+    ("cov", ("-k", "-s")),
 ])
 def test_full_run_matches_reference(tmp_path, kind, extra):
     inp, alpha = _inputs(tmp_path, kind)

@@ -1,0 +1,58 @@
+"""CPU: the summary-table writer on flat labels (flagger_b200/csrc/hfg_summary.c, include/hfg_io.h) against the
+unmodified reference binary: prediction_summary_final.tsv of a real `hmm_flagger` run, reproduced from the run's own
+final BED (expanded to one label per window) and the input's truth labels.  Every row of the metric types the writer
+covers (overlap_based, base_level; all four comparison types) must be byte-identical, in the reference's order."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from flagger_b200 import _abi, binfmt
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "hmm_flagger_ref")
+needs_ref = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/hmm_flagger_ref was not built")
+
+
+def _labels_from_bed(bed, wl):
+    """One label per window from the reference's final BED (blocks tile every contig; default --minimumLengths 0)."""
+    idx = {n: i for i, n in enumerate(_abi.STATE_NAMES + ("Unk",))}
+    blocks = {}
+    for line in open(bed):
+        if line.startswith("track"):
+            continue
+        t = line.split("\t")
+        blocks.setdefault(t[0], []).append((int(t[1]), int(t[2]), idx[t[3]]))
+    labels = np.full(wl.n_windows, -1, np.int8)
+    for c, name in zip(wl.chunks, wl.contig_names):
+        starts = np.array([b[0] for b in blocks[name]])
+        for i in range(int(c["n_windows"])):
+            s = int(c["s"]) + i * int(c["window_len"])
+            b = blocks[name][int(np.searchsorted(starts, s, side="right")) - 1]
+            assert b[0] <= s < b[1]
+            labels[int(c["offset"]) + i] = b[2] if b[2] < 4 else -1
+    return labels
+
+
+@needs_ref
+@pytest.mark.parametrize("with_truth,kind,seed", [(False, "cov", 5), (True, "cov.gz", 6), (True, "cov", 7)])
+def test_summary_tsv_matches_reference_run(tmp_path, with_truth, kind, seed):
+    inp = str(tmp_path / f"in.{kind}")
+    binfmt.write_random_rle_cov(inp, [4000, 9000, 310_000, 1_250_000, 123_457], seed=seed, n_regions=3, with_truth=with_truth)
+    out = str(tmp_path / "ref")
+    os.makedirs(out)
+    cmd = [REF, "-i", inp, "-o", out, "-W", "4000", "-C", "1000000", "-n", "2", "-t", "1e-12", "-l", "Err,Dup,Hap,Col", "-@", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    wl, _ = binfmt.read_cov_native(inp, 1_000_000, 4000)
+    labels = _labels_from_bed(os.path.join(out, "final_flagger_prediction.bed"), wl)
+    mine = str(tmp_path / "mine.tsv")
+    binfmt.write_summary_native(inp, mine, prediction=labels, chunk_len=1_000_000, window_len=4000)
+    want = [ln for ln in open(os.path.join(out, "prediction_summary_final.tsv")) if "truth_based_auN" not in ln]
+    got = open(mine).readlines()
+    assert len(want) > 30 and got == want
+    if not with_truth:  # no truth labels: the reference writes nothing else into this file
+        assert open(mine).read() == open(os.path.join(out, "prediction_summary_final.tsv")).read()
+    else:
+        assert any(ln.startswith("TRUTH_VS_PREDICTION\t") for ln in got) and any(ln.startswith("TRUTH\t") for ln in got)
