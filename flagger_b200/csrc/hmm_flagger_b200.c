@@ -475,6 +475,8 @@ int main(int argc, char *argv[]) {
     int8_t *labels = malloc((size_t) d->n_windows);
     int iter = 1, converged = 0, final_done = 0;
     double loglik = 0.0;
+    hfg_region_params *params_before = malloc(sizeof(hfg_region_params) * (size_t) cfg.n_regions);
+    hfg_region_stats *stats_scratch = malloc(sizeof(hfg_region_stats) * (size_t) cfg.n_regions);
     /* Iterations whose results are needed on the host between E-steps run through the blocking call + host M-step: the first
      * one always (its labels are prediction_summary_initial.tsv, src/hmm_flagger.c:361-379), all of them with
      * --accelerate, -w or -k.  Otherwise the REST of the loop -- every further E-step, the M-steps, the convergence test and
@@ -502,6 +504,7 @@ int main(int argc, char *argv[]) {
         /* --accelerate: E(p0), M, E(p1), M, SQUAREM candidate p' chosen with forward-only passes, E(p') (:382-416) */
         double rate = 0.0;
         const int want_labels = iter == 1 || write_bench;
+        if (accelerate && want_labels) memcpy(params_before, params, sizeof(hfg_region_params) * (size_t) cfg.n_regions);
         const int rc_e = accelerate ? hfg_squarem_iteration(ctx, alpha, params, stats, tol, &loglik, &rate)
                                     : hfg_em_iteration(ctx, alpha, params, stats, &loglik, want_labels ? labels : NULL);
         if (rc_e != HFG_OK) {
@@ -511,8 +514,13 @@ int main(int argc, char *argv[]) {
         if (accelerate) fprintf(stderr, "[%s] Computed alpha rate for accelerating EM = %.4f\n", stamp(), rate);
         fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, accelerate ? 3 * (iter - 1) : iter - 1, loglik);
         if (want_labels) {
-            /* the labels of this iteration's (last) E-step (src/hmm_flagger.c:361-379) */
-            if (accelerate && hfg_get_labels(ctx, labels) != HFG_OK) die(hfg_last_error(ctx));
+            /* the summary holds the labels of the E-step with the iteration's STARTING parameters, written before any
+             * acceleration (src/hmm_flagger.c:344-379): with --accelerate that pass ran inside hfg_squarem_iteration
+             * without keeping its labels, so it is repeated here (first iteration, or every one with -k) */
+            if (accelerate) {
+                double ll0;
+                if (hfg_em_iteration(ctx, alpha, params_before, stats_scratch, &ll0, labels) != HFG_OK) die(hfg_last_error(ctx));
+            }
             if (iter == 1) snprintf(suffix, sizeof(suffix), "initial");
             else snprintf(suffix, sizeof(suffix), accelerate ? "iteration_accelerated_%d" : "iteration_%d", iter - 1);
             write_summary(out_dir, suffix, d, labels, n_label_names ? label_names : NULL, overlap_thr);
@@ -554,7 +562,9 @@ int main(int argc, char *argv[]) {
     hfg_destroy(ctx);
     hfg_cov_free(d);
     free(params);
+    free(params_before);
     free(stats);
+    free(stats_scratch);
     free(labels);
     fprintf(stderr, "[%s] Done! \n", stamp());
     struct rusage ru;
