@@ -4,13 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|...]
 
 A *step* is one EM iteration over the whole synthetic workload: the E-step of every chunk (forward, backward, pair
-statistics, posterior-argmax labels) plus the host M-step -- what runHMMFlagger does once per iteration
-(reference src/hmm_flagger.c:337-431).  The default K=51 is the job BASELINE.json names: 50 EM iterations + the
+statistics, posterior-argmax labels) plus the M-step -- what runHMMFlagger does once per iteration (reference
+src/hmm_flagger.c:337-431).  The default K=51 is the job BASELINE.json names: 50 EM iterations + the
 final decode pass, on configs[1] (3 Gbp diploid, 46 chr-sized contigs, 40x, w=4000; ~750k windows).
 
-Prints ONE JSON line (rank 0).  `value` = windows x steps / time with the windows resident in HBM; `e2e` = the same
-through the blocking C-ABI call a host program makes (hfg_set_chunks once + hfg_em_iteration per step: host
-parameters in, host statistics + labels out).  `--impl reference` times the reference's own CPU implementation
+Prints ONE JSON line (rank 0).  `value` = windows x steps / time with the windows resident in HBM (device-resident EM
+loop: one kernel per iteration, M-step in its tail, each iteration timed with its own CUDA-event pair); `e2e` = the same
+through the blocking C-ABI call a host program makes (hfg_set_chunks once + hfg_em_iteration per step: host parameters
+in, host statistics + labels out, + host M-step); `e2e_job` = the whole job as one hfg_run_em call, set-up included.  `--impl reference` times the reference's own CPU implementation
 (oracle/_ref, all host threads) on the same workload/metric.
 """
 import argparse

@@ -534,7 +534,20 @@ int hfg_layout_build_ex(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk
                 return HFG_ERR_INVALID;
             }
             int j = i + 1;
-            while (j < L && r[j] == r[i]) j++;
+            {
+                /* end of the run of equal region indices, eight windows per comparison */
+                uint64_t pat = r[i];
+                pat |= pat << 8;
+                pat |= pat << 16;
+                pat |= pat << 32;
+                while (j + 8 <= L) {
+                    uint64_t v;
+                    memcpy(&v, r + j, 8);
+                    if (v != pat) break;
+                    j += 8;
+                }
+                while (j < L && r[j] == r[i]) j++;
+            }
             if (n_runs == run_cap) {
                 run_cap *= 2;
                 Run *nr = realloc(runs, sizeof(Run) * (size_t) run_cap);
