@@ -7,9 +7,10 @@
  * Outputs written into --outputDir (formats as the reference):
  *   loglikelihood.tsv, transition_{initial,iteration_k,final}.tsv, emission_{...}.tsv, final_flagger_prediction.bed,
  *   posterior_prediction_final.bed (-P), chunks.c_<C>.w_<W>.bin (-B), prediction_summary_{initial,iteration_k,final}.tsv
- *   (overlap_based and base_level tables on the flat label array, hfg_write_summary_tsv; -k for every iteration).
- * --accelerate (SQUAREM) runs through hfg_squarem_iteration.  NOT written: the truth_based_auN rows and the
- * *.benchmarking*.tsv files (inputs with truth labels only), --binArrayFile size bins.
+ *   and, for inputs with truth labels, their .benchmarking.tsv / .benchmarking.auN_ratio.tsv companions (all on the flat
+ *   label array, hfg_write_summary_tsv; -k for every iteration).
+ * --accelerate (SQUAREM) runs through hfg_squarem_iteration.  Not supported: --binArrayFile size bins (single bin
+ * ALL_SIZES), --modelType negative_binomial, --initialRandomDev other than 0.
  */
 #include <getopt.h>
 #include <math.h>

@@ -54,10 +54,12 @@ void hfg_cov_free(hfg_cov_data *data);
 /* prediction_summary_<suffix>.tsv (writeBenchmarkingStats, programs/src/hmm_flagger.c:134-161;
  * SummaryTableList_createAndWriteAllTables, programs/submodules/summary_table/summary_table.c:1663-1747) from FLAT label
  * arrays: per region and per annotation, the number of label blocks (overlap_based) and of bases (base_level) for every
- * label, counts then percentages, in the reference's row order and formats.  prediction / truth: one int8 per window
- * (-1 = none, counted as "Unk"); either may be NULL (that comparison is left out).  label_names: n_labels + 1 names, the
- * last one for "Unk" (NULL: label_0 ... label_unk).  Single size bin ALL_SIZES; the truth_based_auN metric and the
- * *.benchmarking*.tsv files (only written by the reference when truth labels exist) are not produced. */
+ * label -- and, with truth labels, the confusion tables and the truth_based_auN metric -- counts then percentages, in the
+ * reference's row order and formats.  prediction / truth: one int8 per window (-1 = none, counted as "Unk"); either may
+ * be NULL (the comparisons that need it are left out).  When both are given, <path minus .tsv>.benchmarking.tsv
+ * (precision / recall / F1 / accuracy) and .benchmarking.auN_ratio.tsv are written next to it, as the reference does.
+ * label_names: n_labels + 1 names, the last one for "Unk" (NULL: label_0 ... label_unk).  Single size bin ALL_SIZES
+ * (--binArrayFile is not supported). */
 int hfg_write_summary_tsv(const char *path, const hfg_cov_data *data, const int8_t *prediction, const int8_t *truth,
                           const char *const *label_names, int n_labels, double overlap_ratio_threshold, char *err,
                           size_t errlen);

@@ -1,7 +1,8 @@
 """CPU: the summary-table writer on flat labels (flagger_b200/csrc/hfg_summary.c, include/hfg_io.h) against the
-unmodified reference binary: prediction_summary_final.tsv of a real `hmm_flagger` run, reproduced from the run's own
-final BED (expanded to one label per window) and the input's truth labels.  Every row of the metric types the writer
-covers (overlap_based, base_level; all four comparison types) must be byte-identical, in the reference's order."""
+unmodified reference binary: prediction_summary_final.tsv of a real `hmm_flagger` run -- and, for inputs with truth
+labels, prediction_summary_final.benchmarking.tsv / .benchmarking.auN_ratio.tsv -- reproduced from the run's own final
+BED (expanded to one label per window) and the input's truth labels.  Byte-identical files: all three metric types
+(overlap_based, base_level, truth_based_auN), all four comparison types, the reference's row order and formats."""
 import os
 import subprocess
 
@@ -36,7 +37,7 @@ def _labels_from_bed(bed, wl):
 
 
 @needs_ref
-@pytest.mark.parametrize("with_truth,kind,seed", [(False, "cov", 5), (True, "cov.gz", 6), (True, "cov", 7)])
+@pytest.mark.parametrize("with_truth,kind,seed", [(False, "cov", 5), (True, "cov.gz", 6), (True, "cov", 7), (True, "cov", 8), (False, "cov.gz", 9)])
 def test_summary_tsv_matches_reference_run(tmp_path, with_truth, kind, seed):
     inp = str(tmp_path / f"in.{kind}")
     binfmt.write_random_rle_cov(inp, [4000, 9000, 310_000, 1_250_000, 123_457], seed=seed, n_regions=3, with_truth=with_truth)
@@ -49,10 +50,13 @@ def test_summary_tsv_matches_reference_run(tmp_path, with_truth, kind, seed):
     labels = _labels_from_bed(os.path.join(out, "final_flagger_prediction.bed"), wl)
     mine = str(tmp_path / "mine.tsv")
     binfmt.write_summary_native(inp, mine, prediction=labels, chunk_len=1_000_000, window_len=4000)
-    want = [ln for ln in open(os.path.join(out, "prediction_summary_final.tsv")) if "truth_based_auN" not in ln]
-    got = open(mine).readlines()
-    assert len(want) > 30 and got == want
-    if not with_truth:  # no truth labels: the reference writes nothing else into this file
-        assert open(mine).read() == open(os.path.join(out, "prediction_summary_final.tsv")).read()
-    else:
-        assert any(ln.startswith("TRUTH_VS_PREDICTION\t") for ln in got) and any(ln.startswith("TRUTH\t") for ln in got)
+    names = ["prediction_summary_final.tsv"]
+    if with_truth:
+        names += ["prediction_summary_final.benchmarking.tsv", "prediction_summary_final.benchmarking.auN_ratio.tsv"]
+    for name in names:
+        want = open(os.path.join(out, name)).read()
+        got = open(str(tmp_path / name.replace("prediction_summary_final", "mine"))).read()
+        assert len(want.splitlines()) > (30 if name.endswith("final.tsv") else 10), name
+        assert got == want, name
+    main = open(mine).read()
+    assert ("truth_based_auN" in main) == with_truth and ("TRUTH_VS_PREDICTION\t" in main) == with_truth
