@@ -255,7 +255,7 @@ def write_random_rle_cov(path, contig_lens, seed=0, n_regions=3, with_truth=True
 
 
 def write_summary_native(inp, out_path, prediction=None, use_truth=True, label_names=_abi.STATE_NAMES + ("Unk",),
-                         overlap_ratio_threshold=0.4, chunk_len=20_000_000, window_len=4000):
+                         overlap_ratio_threshold=0.4, chunk_len=20_000_000, window_len=4000, bin_array_file=None):
     """prediction_summary_<suffix>.tsv through the C writer (hfg_write_summary_tsv, csrc/hfg_summary.c) for the input file
     `inp` (.cov / .cov.gz / .bin), the per-window `prediction` labels (int8, or None) and the file's own truth labels."""
     L = _io_lib()
@@ -280,7 +280,8 @@ def write_summary_native(inp, out_path, prediction=None, use_truth=True, label_n
             names = (_C.c_char_p * len(label_names))(*[s.encode() for s in label_names])
             n_labels = len(label_names) - 1
         rc = L.hfg_write_summary_tsv(str(out_path).encode(), out, _abi.ptr(pred), truth, names, _C.c_int(n_labels),
-                                     _C.c_double(overlap_ratio_threshold), err, _C.c_size_t(512))
+                                     _C.c_double(overlap_ratio_threshold),
+                                     str(bin_array_file).encode() if bin_array_file else None, err, _C.c_size_t(512))
         if rc != 0:
             raise ValueError(f"hfg_write_summary_tsv: {err.value.decode()}")
     finally:

@@ -1,7 +1,7 @@
 /*
  * hfg_summary.c -- the prediction summary tables of `hmm_flagger` (prediction_summary_<suffix>.tsv) on FLAT label arrays.
  *
- * Replaces, for the single default size bin (ALL_SIZES):
+ * Replaces:
  *   writeBenchmarkingStats                         programs/src/hmm_flagger.c:134-161
  *   SummaryTableList_createAndWriteAllTables       programs/submodules/summary_table/summary_table.c:1663-1747
  *   SummaryTableList_updateByUpdaterArgs           summary_table.c:930-1224   (the block scan)
@@ -11,7 +11,7 @@
  *   SummaryTableList_writeFinalAunStatisticsIntoFile summary_table.c:744-813  (<prefix>.benchmarking.auN_ratio.tsv)
  * The reference walks 750k heap-allocated CoverageInfo/Inference objects once per (category, metric, comparison) on a
  * thread pool; here the labels are the flat int8 array the E-step returns and the window coordinates come from the chunk
- * descriptors.  Not supported: --binArrayFile size bins.
+ * descriptors.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -43,6 +43,65 @@ static int in_category(const hfg_cov_data *d, int64_t g, int cat_type, int index
 #define TBL_ROWTOT(t, n, r) ((t)[(size_t) (n) * (n) + (r)])
 #define TBL_TOTAL(t, n) ((t)[(size_t) (n) * (n) + (n)])
 
+/* size bins of the reference-label blocks (IntBinArray, submodules/common/common.c:670-750): a block of length len is
+ * counted in every bin with start <= len < end */
+typedef struct SizeBins {
+    int n;
+    int *start, *end;
+    char **name;
+} SizeBins;
+
+static void bins_free(SizeBins *b) {
+    for (int i = 0; i < b->n; i++) free(b->name[i]);
+    free(b->start);
+    free(b->end);
+    free(b->name);
+}
+
+/* NULL path: the single bin [0, 1e9) "ALL_SIZES" (summary_table.c:1672-1678); else a tab-delimited file
+ * "start<TAB>end<TAB>name", '#' lines skipped, numbers read with atof (IntBinArray_constructFromFile) */
+static int bins_load(const char *path, SizeBins *b) {
+    memset(b, 0, sizeof(*b));
+    if (!path) {
+        b->n = 1;
+        b->start = malloc(sizeof(int));
+        b->end = malloc(sizeof(int));
+        b->name = malloc(sizeof(char *));
+        b->start[0] = 0;
+        b->end[0] = (int) 1e9;
+        b->name[0] = strdup("ALL_SIZES");
+        return 1;
+    }
+    FILE *f = fopen(path, "r");
+    if (!f) return 0;
+    char line[4096];
+    int cap = 0;
+    while (fgets(line, sizeof(line), f)) {
+        size_t len = strlen(line);
+        if (len && line[len - 1] == '\n') line[--len] = '\0';
+        if (line[0] == '#' || len == 0) continue;
+        char *t1 = strchr(line, '\t');
+        if (!t1) continue;
+        char *t2 = strchr(t1 + 1, '\t');
+        if (!t2) continue;
+        if (b->n == cap) {
+            cap = cap ? 2 * cap : 8;
+            b->start = realloc(b->start, sizeof(int) * (size_t) cap);
+            b->end = realloc(b->end, sizeof(int) * (size_t) cap);
+            b->name = realloc(b->name, sizeof(char *) * (size_t) cap);
+        }
+        *t1 = *t2 = '\0';
+        char *t3 = strchr(t2 + 1, '\t');
+        if (t3) *t3 = '\0';
+        b->start[b->n] = (int) atof(line);
+        b->end[b->n] = (int) atof(t1 + 1);
+        b->name[b->n] = strdup(t2 + 1);
+        b->n++;
+    }
+    fclose(f);
+    return b->n > 0;
+}
+
 /* growable list of block lengths (the auN metric keeps the query-label blocks of the current reference block) */
 typedef struct IntList {
     int *v;
@@ -57,9 +116,10 @@ static void intlist_push(IntList *l, int x) {
     l->v[l->n++] = x;
 }
 
-/* adds one finished reference-label block to the table (summary_table.c:1040-1102 and :1150-1214) */
-static void flush_block(double *table, double *row, int n, int metric, double overlap_threshold, int pre_ref, int len,
-                        IntList *qlen, int pre_query, int pre_end, int query_start, const double *aux) {
+/* adds one finished reference-label block to the tables of the size bins it falls in (summary_table.c:1040-1102 and
+ * :1150-1214).  tables / aux: [n_bins] consecutive tables of this category index. */
+static void flush_block(double *tables, double *row, int n, int metric, double overlap_threshold, int pre_ref, int len,
+                        IntList *qlen, int pre_query, int pre_end, int query_start, const double *aux, const SizeBins *bins) {
     if (metric == METRIC_OVERLAP) {
         int hit = 0;
         for (int k = 0; k < n; k++) {
@@ -69,27 +129,30 @@ static void flush_block(double *table, double *row, int n, int metric, double ov
         }
         if (!hit) row[n - 1] = 1;
     }
-    double denom = 1.0;
     if (metric == METRIC_AUN) {
-        /* the last query block of the reference block, then sum of squared query-block lengths per query label, over the
-         * total length of this reference label in the category (base_level truth-vs-truth table) */
+        /* the last query block of the reference block, then the sum of squared query-block lengths per query label */
         if (pre_query != -1) intlist_push(&qlen[pre_query], pre_end - query_start + 1);
         for (int k = 0; k < n; k++)
             for (int b = 0; b < qlen[k].n; b++) row[k] += (double) qlen[k].v[b] * qlen[k].v[b];
-        denom = aux[(size_t) pre_ref * n + pre_ref];
     }
-    for (int k = 0; k < n; k++) {
-        const double v = row[k] / denom;
-        table[(size_t) pre_ref * n + k] += v;
-        TBL_ROWTOT(table, n, pre_ref) += v;
-        TBL_TOTAL(table, n) += v;
+    for (int bi = 0; bi < bins->n; bi++) {
+        if (!(bins->start[bi] <= len && len < bins->end[bi])) continue;
+        double *table = tables + (size_t) bi * TBL_STRIDE(n);
+        /* auN: over the total length of this reference label in the category and bin (base_level truth-vs-truth table) */
+        const double denom = metric == METRIC_AUN ? (aux + (size_t) bi * TBL_STRIDE(n))[(size_t) pre_ref * n + pre_ref] : 1.0;
+        for (int k = 0; k < n; k++) {
+            const double v = row[k] / denom;
+            table[(size_t) pre_ref * n + k] += v;
+            TBL_ROWTOT(table, n, pre_ref) += v;
+            TBL_TOTAL(table, n) += v;
+        }
     }
 }
 
-/* one confusion table [n][n] for one category index, filled by the block scan (SummaryTableList_updateByUpdaterArgs,
+/* the confusion tables [n_bins][n][n] of one category index, filled by the block scan (SummaryTableList_updateByUpdaterArgs,
  * summary_table.c:930-1224).  aux: the base_level truth-vs-truth table of the same category index (auN only). */
 static void scan_category(const hfg_cov_data *d, const int8_t *ref, const int8_t *query, int n, int cat_type, int index,
-                          int metric, double overlap_threshold, const double *aux, double *table) {
+                          int metric, double overlap_threshold, const double *aux, const SizeBins *bins, double *table) {
     double *row = calloc((size_t) n, sizeof(double));
     IntList *qlen = calloc((size_t) n, sizeof(IntList));
     int pre_ref = -1, pre_query = -1, ref_start = -1, query_start = -1, pre_end = -1;
@@ -113,7 +176,7 @@ static void scan_category(const hfg_cov_data *d, const int8_t *ref, const int8_t
             /* a block of one reference label inside the category has ended: add it to the table */
             if (pre_ref != -1 && ((continued && ref_changed) || (prev_in && ctg_changed) || ended))
                 flush_block(table, row, n, metric, overlap_threshold, pre_ref, pre_end - ref_start + 1, qlen, pre_query, pre_end,
-                            query_start, aux);
+                            query_start, aux, bins);
             /* the query label changed inside a reference block */
             if (cur_in && metric == METRIC_AUN && pre_query != -1 && query_changed && (continued && !ref_changed) && !ctg_changed)
                 intlist_push(&qlen[pre_query], pre_end - query_start + 1);
@@ -139,7 +202,7 @@ static void scan_category(const hfg_cov_data *d, const int8_t *ref, const int8_t
     }
     if (have_prev && prev_in && pre_ref != -1)
         flush_block(table, row, n, metric, overlap_threshold, pre_ref, pre_end - ref_start + 1, qlen, pre_query, pre_end, query_start,
-                    aux);
+                    aux, bins);
     for (int k = 0; k < n; k++) free(qlen[k].v);
     free(qlen);
     free(row);
@@ -164,10 +227,13 @@ static void pct_or_na(char *out, size_t len, int defined, double value) {
  * (SummaryTableList_writeFinalStatisticsIntoFile, summary_table.c:461-742).  recall: tables with the truth as reference,
  * precision: tables with the prediction as reference; [n_cat][n][n] each. */
 static void write_final_statistics(FILE *f, const double *recall, const double *precision, int n_cat, int n, const char *metric,
-                                   const char *category, const char *const *cat_names, const char *const *label_names) {
+                                   const char *category, const char *const *cat_names, const char *const *label_names,
+                                   const SizeBins *bins) {
     const int n_labels = n - 1, HAP = 2;
-    for (int ci = 0; ci < n_cat; ci++) {
-        const double *rt = recall + (size_t) ci * TBL_STRIDE(n), *pt = precision + (size_t) ci * TBL_STRIDE(n);
+    for (int cb = 0; cb < n_cat * bins->n; cb++) {
+        const int ci = cb / bins->n;
+        const char *bname = bins->name[cb % bins->n];
+        const double *rt = recall + (size_t) cb * TBL_STRIDE(n), *pt = precision + (size_t) cb * TBL_STRIDE(n);
         double tot_tp_r = 0, tot_tp_p = 0, tot_r = 0, tot_p = 0, sum_r = 0, sum_p = 0, sum_r_nh = 0, sum_p_nh = 0;
         double rec_r = 0, rec_p = 0, rec_r_nh = 0, rec_p_nh = 0;
         int nz_r = 0, nz_p = 0, nz_r_nh = 0, nz_p_nh = 0;
@@ -208,7 +274,7 @@ static void write_final_statistics(FILE *f, const double *recall, const double *
             pct_or_na(rs, sizeof(rs), def_r, rp);
             pct_or_na(ps, sizeof(ps), def_p, pp);
             pct_or_na(fs, sizeof(fs), def_r && def_p, f1);
-            fprintf(f, "%s\t%s\t%s\tALL_SIZES\t%s\t%.2f\t%.2f\t%.2f\t%.2f\t%.2f\t%.2f\t%s\t%s\t%s\tNA\tNA\n", metric, category, cname,
+            fprintf(f, "%s\t%s\t%s\t%s\t%s\t%.2f\t%.2f\t%.2f\t%.2f\t%.2f\t%.2f\t%s\t%s\t%s\tNA\tNA\n", metric, category, cname, bname,
                     row_name(label_names, r, nbuf, sizeof(nbuf)), tp_p, tp_r, fp, fn, tp_p + fp, tp_r + fn, ps, rs, fs);
         }
         const double mac_r = 0 < nz_r ? sum_r / nz_r : 0.0, mac_p = 0 < nz_p ? sum_p / nz_p : 0.0;
@@ -225,19 +291,21 @@ static void write_final_statistics(FILE *f, const double *recall, const double *
             pct_or_na(ps, sizeof(ps), avg[k].dp, avg[k].p);
             pct_or_na(rs, sizeof(rs), avg[k].dr, avg[k].r);
             pct_or_na(fs, sizeof(fs), avg[k].dp && avg[k].dr, 2 * avg[k].r * avg[k].p / (avg[k].r + avg[k].p + 1.0e-9));
-            fprintf(f, "%s\t%s\t%s\tALL_SIZES\t%s\tNA\tNA\tNA\tNA\tNA\tNA\t%s\t%s\t%s\tNA\tNA\n", metric, category, cname, avg[k].name, ps,
-                    rs, fs);
+            fprintf(f, "%s\t%s\t%s\t%s\t%s\tNA\tNA\tNA\tNA\tNA\tNA\t%s\t%s\t%s\tNA\tNA\n", metric, category, cname, bname, avg[k].name,
+                    ps, rs, fs);
         }
-        fprintf(f, "%s\t%s\t%s\tALL_SIZES\tACCURACY\t%.2f\t%.2f\tNA\tNA\t%.2f\t%.2f\tNA\tNA\tNA\t%.2f\t%.2f\n", metric, category, cname,
+        fprintf(f, "%s\t%s\t%s\t%s\tACCURACY\t%.2f\t%.2f\tNA\tNA\t%.2f\t%.2f\tNA\tNA\tNA\t%.2f\t%.2f\n", metric, category, cname, bname,
                 tot_tp_p, tot_tp_r, tot_p, tot_r, tot_tp_p / (tot_p + 1.0e-9) * 100.0, tot_tp_r / (tot_r + 1e-9) * 100.0);
     }
 }
 
 /* <prefix>.benchmarking.auN_ratio.tsv (SummaryTableList_writeFinalAunStatisticsIntoFile, summary_table.c:744-813) */
 static void write_aun_statistics(FILE *f, const double *num, const double *den, int n_cat, int n, const char *category,
-                                 const char *const *cat_names, const char *const *label_names) {
-    for (int ci = 0; ci < n_cat; ci++) {
-        const double *nt = num + (size_t) ci * TBL_STRIDE(n), *dt = den + (size_t) ci * TBL_STRIDE(n);
+                                 const char *const *cat_names, const char *const *label_names, const SizeBins *bins) {
+    for (int cb = 0; cb < n_cat * bins->n; cb++) {
+        const int ci = cb / bins->n;
+        const char *bname = bins->name[cb % bins->n];
+        const double *nt = num + (size_t) cb * TBL_STRIDE(n), *dt = den + (size_t) cb * TBL_STRIDE(n);
         char cbuf[64], nbuf[32], s1[20], s2[20];
         const char *cname = cat_names ? cat_names[ci] : (snprintf(cbuf, sizeof(cbuf), "region_%d", ci), cbuf);
         double sum = 0.0, rec = 0.0;
@@ -247,25 +315,32 @@ static void write_aun_statistics(FILE *f, const double *num, const double *den, 
             nz += 0 < de ? 1 : 0;
             sum += aun;
             if (0 < de) rec += 0.0 < aun ? 1.0 / aun : 1.0e9;
-            fprintf(f, "%s\t%s\tALL_SIZES\t%s\t%.2f\n", category, cname, row_name(label_names, r, nbuf, sizeof(nbuf)), aun);
+            fprintf(f, "%s\t%s\t%s\t%s\t%.2f\n", category, cname, bname, row_name(label_names, r, nbuf, sizeof(nbuf)), aun);
         }
         pct_or_na(s1, sizeof(s1), 0 < nz, 0 < nz ? sum / nz : 0.0);
         pct_or_na(s2, sizeof(s2), 0 < nz, 0 < nz ? (double) nz / rec : 0.0);
-        fprintf(f, "%s\t%s\tALL_SIZES\tAVERAGE\t%s\n", category, cname, s1);
-        fprintf(f, "%s\t%s\tALL_SIZES\tHARMONIC_MEAN\t%s\n", category, cname, s2);
+        fprintf(f, "%s\t%s\t%s\tAVERAGE\t%s\n", category, cname, bname, s1);
+        fprintf(f, "%s\t%s\t%s\tHARMONIC_MEAN\t%s\n", category, cname, bname, s2);
     }
 }
 
 int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t *prediction, const int8_t *truth,
-                          const char *const *label_names, int n_labels, double overlap_ratio_threshold, char *err,
-                          size_t errlen) {
+                          const char *const *label_names, int n_labels, double overlap_ratio_threshold,
+                          const char *bin_array_file, char *err, size_t errlen) {
     if (!path || !d || n_labels < 1 || (!prediction && !truth)) {
         snprintf(err, errlen, "hfg_write_summary_tsv: bad argument");
+        return HFG_ERR_INVALID;
+    }
+    SizeBins bins;
+    if (!bins_load(bin_array_file, &bins)) {
+        snprintf(err, errlen, "Error: Unable to read size bins from %s", bin_array_file);
+        bins_free(&bins);
         return HFG_ERR_INVALID;
     }
     FILE *f = fopen(path, "w");
     if (!f) {
         snprintf(err, errlen, "Error: %s cannot be opened.", path);
+        bins_free(&bins);
         return HFG_ERR_INVALID;
     }
     const int n = n_labels + 1; /* + "Unk" */
@@ -290,6 +365,7 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
             fclose(f);
             if (f_stats) fclose(f_stats);
             if (f_aun) fclose(f_aun);
+            bins_free(&bins);
             return HFG_ERR_INVALID;
         }
         fprintf(f_stats, "#Metric_Type\tCategory_Type\tCategory_Name\tSize_Bin_Name\tLabel\tTP_Prediction_Ref\tTP_Truth_Ref\tFP\tFN\t"
@@ -310,11 +386,11 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
                 if (metric == METRIC_AUN && (cmp == CMP_PREDICTION || cmp == CMP_PREDICTION_VS_TRUTH)) continue;
                 const int8_t *ref = (cmp == CMP_TRUTH_VS_PREDICTION || cmp == CMP_TRUTH) ? truth : prediction;
                 const int8_t *query = (cmp == CMP_TRUTH_VS_PREDICTION || cmp == CMP_PREDICTION) ? prediction : truth;
-                tab[metric][cmp] = calloc((size_t) n_cat * TBL_STRIDE(n), sizeof(double));
+                tab[metric][cmp] = calloc((size_t) n_cat * bins.n * TBL_STRIDE(n), sizeof(double));
                 for (int ci = 0; ci < n_cat; ci++)
                     scan_category(d, ref, query, n, cat_type, ci, metric, overlap_ratio_threshold,
-                                  metric == METRIC_AUN ? tab[METRIC_BASE][CMP_TRUTH] + (size_t) ci * TBL_STRIDE(n) : NULL,
-                                  tab[metric][cmp] + (size_t) ci * TBL_STRIDE(n));
+                                  metric == METRIC_AUN ? tab[METRIC_BASE][CMP_TRUTH] + (size_t) ci * bins.n * TBL_STRIDE(n) : NULL, &bins,
+                                  tab[metric][cmp] + (size_t) ci * bins.n * TBL_STRIDE(n));
             }
         }
         for (int metric = 0; metric < 3; metric++) {
@@ -324,8 +400,10 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
                 const int single_row = cmp == CMP_TRUTH || cmp == CMP_PREDICTION;
                 /* the reference writes all counts of a (category type, metric, comparison) first, then all percentages */
                 for (int pct = 0; pct < 2; pct++) {
-                    for (int ci = 0; ci < n_cat; ci++) {
-                        const double *t = all + (size_t) ci * TBL_STRIDE(n);
+                    for (int cb = 0; cb < n_cat * bins.n; cb++) {
+                        const int ci = cb / bins.n;
+                        const char *bname = bins.name[cb % bins.n];
+                        const double *t = all + (size_t) cb * TBL_STRIDE(n);
                         char cname[64], nbuf[32];
                         const char *cat_name = cat_names ? cat_names[ci] : (snprintf(cname, sizeof(cname), "region_%d", ci), cname);
                         const double total = TBL_TOTAL(t, n);
@@ -335,8 +413,8 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
                                 const double s = TBL_ROWTOT(t, n, r);
                                 vals[r] = pct ? (0 < total ? s / total * 100.0 : 0.0) : s;
                             }
-                            fprintf(f, "%s\t%s\t%s\t%s\t%s\tALL_SIZES\tALL_LABELS\t", COMPARISON_NAME[cmp], METRIC_NAME[metric],
-                                    pct ? "percentage" : "count", CATEGORY_NAME[cat_type], cat_name);
+                            fprintf(f, "%s\t%s\t%s\t%s\t%s\t%s\tALL_LABELS\t", COMPARISON_NAME[cmp], METRIC_NAME[metric],
+                                    pct ? "percentage" : "count", CATEGORY_NAME[cat_type], cat_name, bname);
                             write_values(f, vals, n);
                             fprintf(f, "\n");
                         } else {
@@ -344,8 +422,8 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
                                 const double s = TBL_ROWTOT(t, n, r);
                                 for (int k = 0; k < n; k++)
                                     vals[k] = pct ? (0 < s ? t[(size_t) r * n + k] / s * 100.0 : 0.0) : t[(size_t) r * n + k];
-                                fprintf(f, "%s\t%s\t%s\t%s\t%s\tALL_SIZES\t%s\t", COMPARISON_NAME[cmp], METRIC_NAME[metric],
-                                        pct ? "percentage" : "count", CATEGORY_NAME[cat_type], cat_name,
+                                fprintf(f, "%s\t%s\t%s\t%s\t%s\t%s\t%s\t", COMPARISON_NAME[cmp], METRIC_NAME[metric],
+                                        pct ? "percentage" : "count", CATEGORY_NAME[cat_type], cat_name, bname,
                                         row_name(label_names, r, nbuf, sizeof(nbuf)));
                                 write_values(f, vals, n);
                                 fprintf(f, "\n");
@@ -356,15 +434,16 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
             }
             if (f_stats && metric != METRIC_AUN)
                 write_final_statistics(f_stats, tab[metric][CMP_TRUTH_VS_PREDICTION], tab[metric][CMP_PREDICTION_VS_TRUTH], n_cat, n,
-                                       METRIC_NAME[metric], CATEGORY_NAME[cat_type], cat_names, label_names);
+                                       METRIC_NAME[metric], CATEGORY_NAME[cat_type], cat_names, label_names, &bins);
         }
         if (f_aun)
             write_aun_statistics(f_aun, tab[METRIC_AUN][CMP_TRUTH_VS_PREDICTION], tab[METRIC_AUN][CMP_TRUTH], n_cat, n,
-                                 CATEGORY_NAME[cat_type], cat_names, label_names);
+                                 CATEGORY_NAME[cat_type], cat_names, label_names, &bins);
         for (int metric = 0; metric < 3; metric++)
             for (int cmp = 0; cmp < 4; cmp++) free(tab[metric][cmp]);
     }
     free(vals);
+    bins_free(&bins);
     fclose(f);
     if (f_stats) fclose(f_stats);
     if (f_aun) fclose(f_aun);

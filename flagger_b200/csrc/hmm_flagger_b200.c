@@ -9,8 +9,8 @@
  *   posterior_prediction_final.bed (-P), chunks.c_<C>.w_<W>.bin (-B), prediction_summary_{initial,iteration_k,final}.tsv
  *   and, for inputs with truth labels, their .benchmarking.tsv / .benchmarking.auN_ratio.tsv companions (all on the flat
  *   label array, hfg_write_summary_tsv; -k for every iteration).
- * --accelerate (SQUAREM) runs through hfg_squarem_iteration.  Not supported: --binArrayFile size bins (single bin
- * ALL_SIZES), --modelType negative_binomial, --initialRandomDev other than 0.
+ * --accelerate (SQUAREM) runs through hfg_squarem_iteration.  Not supported: --modelType negative_binomial,
+ * --initialRandomDev other than 0.
  */
 #include <getopt.h>
 #include <math.h>
@@ -283,11 +283,11 @@ static int ends_with(const char *s, const char *suffix) {
 
 /* writeBenchmarkingStats (src/hmm_flagger.c:134-161) on the flat label array */
 static void write_summary(const char *dir, const char *suffix, const hfg_cov_data *d, const int8_t *labels,
-                          char *const *label_names, double overlap_thr) {
+                          char *const *label_names, double overlap_thr, const char *bin_array_file) {
     char path[4096], err[512];
     snprintf(path, sizeof(path), "%s/prediction_summary_%s.tsv", dir, suffix);
     if (hfg_write_summary_tsv(path, d, labels, d->truth_available ? d->truth : NULL, (const char *const *) label_names,
-                              HFG_NUM_STATES, overlap_thr, err, sizeof(err)) != HFG_OK)
+                              HFG_NUM_STATES, overlap_thr, bin_array_file, err, sizeof(err)) != HFG_OK)
         die(err);
 }
 
@@ -386,8 +386,6 @@ int main(int argc, char *argv[]) {
     if (!input) die("Input path cannot be NULL.");
     if (n_label_names && n_label_names - 1 != HFG_NUM_STATES)
         die("Number of label names does not match the number of labels (4: Err,Dup,Hap,Col)."); /* summary_table.c:1682-1689 */
-    if (bin_array_file)
-        fprintf(stderr, "[%s] Warning: --binArrayFile is not supported here; the summary tables use the single size bin ALL_SIZES.\n", stamp());
     if (tol <= 0.0 || tol > 1.0) die("convergence tol should be between 0 and 1.");
     struct stat st;
     if (!out_dir) die("--outputDir, -o should be specified.");
@@ -524,7 +522,7 @@ int main(int argc, char *argv[]) {
             }
             if (iter == 1) snprintf(suffix, sizeof(suffix), "initial");
             else snprintf(suffix, sizeof(suffix), accelerate ? "iteration_accelerated_%d" : "iteration_%d", iter - 1);
-            write_summary(out_dir, suffix, d, labels, n_label_names ? label_names : NULL, overlap_thr);
+            write_summary(out_dir, suffix, d, labels, n_label_names ? label_names : NULL, overlap_thr, bin_array_file);
         }
         hfg_mstep(&cfg, params, stats, tol, &converged);
         if (write_params) {
@@ -544,7 +542,7 @@ int main(int argc, char *argv[]) {
         }
         fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, accelerate ? 3 * (iter - 1) : iter - 1, loglik);
     }
-    write_summary(out_dir, "final", d, labels, n_label_names ? label_names : NULL, overlap_thr);
+    write_summary(out_dir, "final", d, labels, n_label_names ? label_names : NULL, overlap_thr, bin_array_file);
     fclose(ll_file);
     write_transition_tsv(out_dir, "final", &cfg, params);
     write_emission_tsv(out_dir, "final", &cfg, params);

@@ -58,11 +58,12 @@ void hfg_cov_free(hfg_cov_data *data);
  * reference's row order and formats.  prediction / truth: one int8 per window (-1 = none, counted as "Unk"); either may
  * be NULL (the comparisons that need it are left out).  When both are given, <path minus .tsv>.benchmarking.tsv
  * (precision / recall / F1 / accuracy) and .benchmarking.auN_ratio.tsv are written next to it, as the reference does.
- * label_names: n_labels + 1 names, the last one for "Unk" (NULL: label_0 ... label_unk).  Single size bin ALL_SIZES
- * (--binArrayFile is not supported). */
+ * label_names: n_labels + 1 names, the last one for "Unk" (NULL: label_0 ... label_unk).  bin_array_file: the size bins
+ * of --binArrayFile ("start<TAB>end<TAB>name" lines; a block is counted in every bin with start <= length < end), or
+ * NULL for the single bin ALL_SIZES. */
 int hfg_write_summary_tsv(const char *path, const hfg_cov_data *data, const int8_t *prediction, const int8_t *truth,
-                          const char *const *label_names, int n_labels, double overlap_ratio_threshold, char *err,
-                          size_t errlen);
+                          const char *const *label_names, int n_labels, double overlap_ratio_threshold,
+                          const char *bin_array_file, char *err, size_t errlen);
 
 #ifdef __cplusplus
 }

@@ -149,3 +149,22 @@ def test_preset_without_alpha_and_contig_subset(tmp_path):
         _run(REF, inp, ref_out, extra=extra)
         _run(CLI, inp, cli_out, extra=extra)
         _compare_runs(ref_out, cli_out)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_truth_labelled_input_writes_the_benchmarking_files(tmp_path):
+    """An input with truth labels and --binArrayFile: besides the prediction summaries the reference writes confusion
+    tables, the truth_based_auN metric and the .benchmarking.tsv / .benchmarking.auN_ratio.tsv files; the stand-alone
+    binary must write the same bytes (its labels come from the GPU, the tables from hfg_write_summary_tsv)."""
+    inp = str(tmp_path / "truth.cov.gz")
+    binfmt.write_random_rle_cov(inp, [4000, 9000, 310_000, 1_250_000, 123_457], seed=11, n_regions=3, with_truth=True)
+    bins = str(tmp_path / "bins.tsv")
+    open(bins, "w").write("#start\tend\tname\n0\t20000\t0-20Kb\n20000\t1e9\t20Kb<\n0\t1e9\tALL\n")
+    ref_out, cli_out = str(tmp_path / "ref"), str(tmp_path / "cli")
+    _run(REF, inp, ref_out, extra=("-a", bins, "-k"))
+    _run(CLI, inp, cli_out, extra=("-a", bins, "-k"))
+    _compare_runs(ref_out, cli_out)
+    names = [n for n in sorted(os.listdir(ref_out)) if n.startswith("prediction_summary_")]
+    assert any(n.endswith(".benchmarking.tsv") for n in names) and any(n.endswith(".auN_ratio.tsv") for n in names)
+    assert "truth_based_auN" in open(os.path.join(cli_out, "prediction_summary_final.tsv")).read()

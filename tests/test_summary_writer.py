@@ -37,19 +37,25 @@ def _labels_from_bed(bed, wl):
 
 
 @needs_ref
-@pytest.mark.parametrize("with_truth,kind,seed", [(False, "cov", 5), (True, "cov.gz", 6), (True, "cov", 7), (True, "cov", 8), (False, "cov.gz", 9)])
-def test_summary_tsv_matches_reference_run(tmp_path, with_truth, kind, seed):
+@pytest.mark.parametrize("with_truth,kind,seed,bins", [(False, "cov", 5, False), (True, "cov.gz", 6, False), (True, "cov", 7, True),
+                                                         (True, "cov", 8, False), (False, "cov.gz", 9, True)])
+def test_summary_tsv_matches_reference_run(tmp_path, with_truth, kind, seed, bins):
     inp = str(tmp_path / f"in.{kind}")
     binfmt.write_random_rle_cov(inp, [4000, 9000, 310_000, 1_250_000, 123_457], seed=seed, n_regions=3, with_truth=with_truth)
     out = str(tmp_path / "ref")
     os.makedirs(out)
     cmd = [REF, "-i", inp, "-o", out, "-W", "4000", "-C", "1000000", "-n", "2", "-t", "1e-12", "-l", "Err,Dup,Hap,Col", "-@", "2"]
+    bin_file = None
+    if bins:  # --binArrayFile: overlapping size bins, one of them open-ended
+        bin_file = str(tmp_path / "bins.tsv")
+        open(bin_file, "w").write("#start\tend\tname\n0\t8000\t0-8Kb\n8000\t40000\t8-40Kb\n20000\t1e9\t20Kb<\n0\t1e9\tALL\n")
+        cmd += ["-a", bin_file]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     wl, _ = binfmt.read_cov_native(inp, 1_000_000, 4000)
     labels = _labels_from_bed(os.path.join(out, "final_flagger_prediction.bed"), wl)
     mine = str(tmp_path / "mine.tsv")
-    binfmt.write_summary_native(inp, mine, prediction=labels, chunk_len=1_000_000, window_len=4000)
+    binfmt.write_summary_native(inp, mine, prediction=labels, chunk_len=1_000_000, window_len=4000, bin_array_file=bin_file)
     names = ["prediction_summary_final.tsv"]
     if with_truth:
         names += ["prediction_summary_final.benchmarking.tsv", "prediction_summary_final.benchmarking.auN_ratio.tsv"]
