@@ -325,3 +325,25 @@ def test_device_layout_equals_host_layout(factory, n_regions, adjust):
     ok, msg = gpu.layout_matches_host(wl)
     assert ok, msg
     gpu.close()
+
+
+def test_host_built_layout_gives_the_same_results(orc, monkeypatch):
+    """HFG_HOST_LAYOUT=1 makes hfg_set_chunks use the host key builder (the checker of the device build): same results,
+    bit for bit, as the default device-built layout."""
+    wl = synth.small_mixed(n_regions=3, seed=29)
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=3, n_col_comps=K)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    dev = api.HmmFlaggerGPU(cfg, wl)
+    s_dev, ll_dev, lab_dev = dev.em_iteration(synth.HIFI_ALPHA, params)
+    dev.close()
+    monkeypatch.setenv("HFG_HOST_LAYOUT", "1")
+    host = api.HmmFlaggerGPU(cfg, wl)
+    ok, msg = host.layout_matches_host(wl)
+    assert ok, msg
+    s_host, ll_host, lab_host = host.em_iteration(synth.HIFI_ALPHA, params)
+    host.close()
+    assert ll_dev == ll_host and np.array_equal(lab_dev, lab_host)
+    assert np.array_equal(_abi.stats_as_flat(s_dev), _abi.stats_as_flat(s_host))
+    out = orc.estep(cfg, wl, synth.HIFI_ALPHA, params)
+    assert np.array_equal(lab_host, out["labels"]) and abs(ll_host - out["loglik"]) <= TOL_LOGLIK * abs(out["loglik"])
