@@ -51,10 +51,13 @@ EXPORTED_SYMBOLS = (
     "hfg_create", "hfg_destroy", "hfg_last_error", "hfg_set_chunks", "hfg_num_windows", "hfg_em_iteration",
     "hfg_forward_only", "hfg_get_posteriors", "hfg_get_chunk_logliks", "hfg_em_iteration_device",
     "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
-    "hfg_host_alloc", "hfg_host_free", "hfg_run_em", "hfg_em_begin", "hfg_em_enqueue", "hfg_em_finish", "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_kernel_launches", "hfg_last_estep_kernel_ms", "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta", "hfg_debug_layout_compare",
-    "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_read_cov", "hfg_read_bin", "hfg_cov_free", "hfg_write_summary_tsv",
-    "hfg_params_feasible", "hfg_squarem_alpha_rate", "hfg_squarem_prime", "hfg_squarem_shrink", "hfg_squarem_iteration",
-    "hfg_run_em_accelerated", "hfg_release_cached_memory",
+    "hfg_host_alloc", "hfg_host_free", "hfg_run_em", "hfg_em_begin", "hfg_em_enqueue", "hfg_em_finish",
+    "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_kernel_launches", "hfg_last_estep_kernel_ms",
+    "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
+    "hfg_debug_layout_compare", "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_read_cov",
+    "hfg_read_bin", "hfg_cov_free", "hfg_write_summary_tsv", "hfg_params_feasible", "hfg_squarem_alpha_rate",
+    "hfg_squarem_prime", "hfg_squarem_shrink", "hfg_squarem_iteration", "hfg_run_em_accelerated",
+    "hfg_release_cached_memory",
 )
 
 

@@ -762,14 +762,14 @@ static int capture_graph(hfg_ctx *ctx, const EstepArgs *a) {
     return 1;
 }
 
-/* is p page-locked host memory the device can write directly? */
-static int is_pinned_host(const void *p) {
+/* the device-side address of p when p is page-locked host memory the device can write directly, else NULL */
+static int8_t *pinned_device_alias(const void *p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();
-        return 0;
+        return NULL;
     }
-    return at.type == cudaMemoryTypeHost;
+    return at.type == cudaMemoryTypeHost ? (int8_t *) at.devicePointer : NULL;
 }
 
 /* blocking E-step with host buffers: graph replay when possible, plain launches otherwise (same kernel either way) */
@@ -780,7 +780,8 @@ static int run_blocking(hfg_ctx *ctx, const double *alpha, const hfg_region_para
     const int with_labels = labels != NULL;
     CU(cudaSetDevice(ctx->device));
     /* where the kernel streams the labels: the caller's buffer when it is page-locked, else the pinned staging buffer */
-    int8_t *label_dst = !with_labels ? NULL : (is_pinned_host(labels) ? labels : ctx->h_labels);
+    int8_t *label_alias = with_labels ? pinned_device_alias(labels) : NULL;
+    int8_t *label_dst = !with_labels ? NULL : (label_alias ? label_alias : ctx->h_labels);
     const int R = ctx->cfg.n_regions;
     EstepArgs a;
     build_args(ctx, alpha, ctx->d_out, NULL, forward_only, 0, &a);
@@ -812,7 +813,7 @@ static int run_blocking(hfg_ctx *ctx, const double *alpha, const hfg_region_para
     memcpy(ctx->last_params, params, sizeof(hfg_region_params) * (size_t) R);
     ctx->have_last = 1;
     CU(cudaStreamSynchronize(ctx->stream));
-    if (with_labels && label_dst != labels) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
+    if (with_labels && !label_alias) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
     return parse_out(ctx, stats, loglik);
 }
 

@@ -71,15 +71,13 @@ namespace cg = cooperative_groups;
 #define RT_TERM 148
 #define RT_TEXP 152
 #define RT_GAUSS 156
-#define RT_STRIDE(G) (RT_GAUSS + 6 * (G))
 #define HFG_INV_TERM 1e4 /* 1 / terminationProb */
 #define HFG_MAX_PEERS 8
 #define HFG_PC_STRIDE 12 /* phase-clock slots per block */
 #define HFG_MAX_TASKS 160
 /* per-(region, task) table after the Gaussian arrays: (1-a)*mu, a, 1/(var*beta0), w/sqrt(var*beta0*2*PI) */
 #define RT_TASK(G) (RT_GAUSS + 6 * (G))
-#undef RT_STRIDE
-#define RT_STRIDE2(G, NT) (RT_TASK(G) + 4 * (NT))
+#define RT_STRIDE2(G, NT) (RT_TASK(G) + 4 * (NT)) /* doubles per region */
 
 struct EstepArgs {
     /* run-constant layout */
