@@ -55,7 +55,7 @@ EXPORTED_SYMBOLS = (
     "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_kernel_launches", "hfg_last_estep_kernel_ms",
     "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
     "hfg_debug_layout_compare", "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_read_cov",
-    "hfg_read_bin", "hfg_cov_free", "hfg_write_summary_tsv", "hfg_params_feasible", "hfg_squarem_alpha_rate",
+    "hfg_read_bin", "hfg_cov_free", "hfg_write_summary_tsv", "hfg_benchmark_scores", "hfg_params_feasible", "hfg_squarem_alpha_rate",
     "hfg_squarem_prime", "hfg_squarem_shrink", "hfg_squarem_iteration", "hfg_run_em_accelerated",
     "hfg_release_cached_memory",
 )

@@ -286,3 +286,64 @@ def write_summary_native(inp, out_path, prediction=None, use_truth=True, label_n
             raise ValueError(f"hfg_write_summary_tsv: {err.value.decode()}")
     finally:
         L.hfg_cov_free(out)
+
+
+class NativeCov:
+    """An input file parsed ONCE by the C reader and kept alive: `.workload` (numpy view of the windows, what
+    HmmFlaggerGPU takes), `.truth_available`, and the writers / scorers that need the parsed structure
+    (`write_summary`, `benchmark_scores`).  Call `.close()` (or let it be collected) to free the C side."""
+
+    def __init__(self, path, chunk_len=20_000_000, window_len=4000):
+        self._L = _io_lib()
+        self._p = _C.POINTER(_CovData)()
+        err = _C.create_string_buffer(512)
+        if str(path).endswith(".bin"):
+            rc = self._L.hfg_read_bin(str(path).encode(), _C.byref(self._p), err, _C.c_size_t(512))
+        else:
+            rc = self._L.hfg_read_cov(str(path).encode(), _C.c_int32(chunk_len), _C.c_int32(window_len), _C.byref(self._p), err,
+                                      _C.c_size_t(512))
+        if rc != 0:
+            raise ValueError(f"reader: {err.value.decode()}")
+        d = self._p.contents
+        self.path = str(path)
+        self.n_windows = int(d.n_windows)
+        self.truth_available = bool(d.truth_available)
+        W, Cn = self.n_windows, int(d.n_chunks)
+        arr = lambda p, dt: np.ctypeslib.as_array(p, shape=(W,)).astype(dt, copy=True) if W else np.zeros(0, dt)
+        chunks = np.frombuffer(_C.string_at(d.chunks, Cn * _abi.chunk_desc_dtype.itemsize), dtype=_abi.chunk_desc_dtype).copy()
+        raw = _C.string_at(d.contig_names, Cn * 200)
+        names = [raw[i * 200:(i + 1) * 200].split(b"\0", 1)[0].decode() for i in range(Cn)]
+        self.workload = Workload(self.path, int(d.window_len), int(d.chunk_len), int(d.avg_alignment_len),
+                                 np.array([d.region_coverages[i] for i in range(d.n_regions)], np.int32), names, chunks,
+                                 arr(d.cov, np.uint16), arr(d.cov_high_mapq, np.uint16), arr(d.cov_high_clip, np.uint16),
+                                 arr(d.region, np.uint8), arr(d.truth, np.int8),
+                                 [d.annotation_names[i].decode() for i in range(d.n_annotations)])
+
+    def close(self):
+        if self._p:
+            self._L.hfg_cov_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def benchmark_scores(self, prediction, annotation_label="whole_genome", size_label="ALL_SIZES",
+                         overlap_ratio_threshold=0.4, bin_array_file=None):
+        """(overlap-based F1, base-level F1, contiguity) of `prediction` against the file's truth labels: the three numbers
+        the reference's alpha-tuning driver reads from the benchmarking files of a run (hfg_benchmark_scores)."""
+        if not self.truth_available:
+            raise ValueError(f"{self.path} carries no truth labels")
+        pred = np.ascontiguousarray(prediction, np.int8)
+        assert pred.shape[0] == self.n_windows
+        scores = (_C.c_double * 3)()
+        err = _C.create_string_buffer(512)
+        rc = self._L.hfg_benchmark_scores(self._p, _abi.ptr(pred), self._p.contents.truth, _C.c_int(len(_abi.STATE_NAMES)),
+                                          _C.c_double(overlap_ratio_threshold),
+                                          str(bin_array_file).encode() if bin_array_file else None, annotation_label.encode(),
+                                          size_label.encode(), scores, err, _C.c_size_t(512))
+        if rc != 0:
+            raise ValueError(f"hfg_benchmark_scores: {err.value.decode()}")
+        return tuple(float(v) for v in scores)

@@ -449,3 +449,103 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
     if (f_aun) fclose(f_aun);
     return HFG_OK;
 }
+
+/* ---- the scores of the alpha-tuning driver ---------------------------------------------------------------------------- */
+
+/* F1-Score of the HARMONIC_MEAN_NO_HAP row (write_final_statistics above), rounded as printed; NaN for "NA" */
+static double harmonic_f1_no_hap(const double *rt, const double *pt, int n) {
+    const int HAP = 2;
+    double rec_r = 0, rec_p = 0;
+    int nz_r = 0, nz_p = 0;
+    for (int r = 0; r < n - 1; r++) {
+        if (r == HAP) continue;
+        const double all_r = TBL_ROWTOT(rt, n, r), all_p = TBL_ROWTOT(pt, n, r);
+        const double tp_r = rt[(size_t) r * n + r], tp_p = pt[(size_t) r * n + r];
+        const double fn = all_r - tp_r, fp = all_p - tp_p;
+        const double rp = tp_r / (tp_r + fn + 1.0e-9) * 100.0, pp = tp_p / (tp_p + fp + 1.0e-9) * 100.0;
+        if (1e-9 < (tp_r + fn)) {
+            nz_r++;
+            rec_r += 0.0 < rp ? 1.0 / rp : 1.0e9;
+        }
+        if (1e-9 < (tp_p + fp)) {
+            nz_p++;
+            rec_p += 0.0 < pp ? 1.0 / pp : 1.0e9;
+        }
+    }
+    if (!(0 < nz_r && 0 < nz_p)) return 0.0 / 0.0;
+    const double har_r = (double) nz_r / rec_r, har_p = (double) nz_p / rec_p;
+    char buf[32];
+    snprintf(buf, sizeof(buf), "%.2f", 2 * har_r * har_p / (har_r + har_p + 1.0e-9));
+    return atof(buf);
+}
+
+int hfg_benchmark_scores(const hfg_cov_data *d, const int8_t *prediction, const int8_t *truth, int n_labels,
+                         double overlap_ratio_threshold, const char *bin_array_file, const char *annotation_label,
+                         const char *size_label, double scores[3], char *err, size_t errlen) {
+    if (!d || !prediction || !truth || !annotation_label || !size_label || !scores || n_labels < 3) {
+        snprintf(err, errlen, "hfg_benchmark_scores: bad argument");
+        return HFG_ERR_INVALID;
+    }
+    SizeBins bins;
+    if (!bins_load(bin_array_file, &bins)) {
+        snprintf(err, errlen, "Error: Unable to read size bins from %s", bin_array_file);
+        bins_free(&bins);
+        return HFG_ERR_INVALID;
+    }
+    int ci = -1, bi = -1;
+    for (int k = 0; k < d->n_annotations; k++)
+        if (strcmp(d->annotation_names[k], annotation_label) == 0) ci = k;
+    for (int k = 0; k < bins.n; k++)
+        if (strcmp(bins.name[k], size_label) == 0) bi = k;
+    if (ci < 0 || bi < 0) {
+        snprintf(err, errlen, "hfg_benchmark_scores: annotation '%s' or size bin '%s' not found", annotation_label, size_label);
+        bins_free(&bins);
+        return HFG_ERR_INVALID;
+    }
+    const int n = n_labels + 1;
+    const size_t stride = (size_t) bins.n * TBL_STRIDE(n);
+    /* tables of this annotation only: [metric 0..1][T-vs-P, P-vs-T], base_level truth-vs-truth, auN T-vs-P and truth */
+    double *tp[2], *pt_[2], *tt = calloc(stride, sizeof(double)), *aun_tp = calloc(stride, sizeof(double)),
+                            *aun_tt = calloc(stride, sizeof(double));
+    for (int metric = 0; metric < 2; metric++) {
+        tp[metric] = calloc(stride, sizeof(double));
+        pt_[metric] = calloc(stride, sizeof(double));
+        scan_category(d, truth, prediction, n, CAT_ANNOTATION, ci, metric, overlap_ratio_threshold, NULL, &bins, tp[metric]);
+        scan_category(d, prediction, truth, n, CAT_ANNOTATION, ci, metric, overlap_ratio_threshold, NULL, &bins, pt_[metric]);
+    }
+    scan_category(d, truth, truth, n, CAT_ANNOTATION, ci, METRIC_BASE, overlap_ratio_threshold, NULL, &bins, tt);
+    scan_category(d, truth, prediction, n, CAT_ANNOTATION, ci, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tp);
+    scan_category(d, truth, truth, n, CAT_ANNOTATION, ci, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tt);
+    const size_t off = (size_t) bi * TBL_STRIDE(n);
+    scores[0] = harmonic_f1_no_hap(tp[METRIC_OVERLAP] + off, pt_[METRIC_OVERLAP] + off, n);
+    scores[1] = harmonic_f1_no_hap(tp[METRIC_BASE] + off, pt_[METRIC_BASE] + off, n);
+    {
+        /* 100 x the HARMONIC_MEAN row of the auN ratio file (write_aun_statistics), rounded as printed */
+        const double *nt = aun_tp + off, *dt = aun_tt + off;
+        double rec = 0.0;
+        int nz = 0;
+        for (int r = 0; r < n - 1; r++) {
+            const double de = dt[(size_t) r * n + r], aun = nt[(size_t) r * n + r] / (de + 1e-9);
+            if (0 < de) {
+                nz++;
+                rec += 0.0 < aun ? 1.0 / aun : 1.0e9;
+            }
+        }
+        if (0 < nz) {
+            char buf[32];
+            snprintf(buf, sizeof(buf), "%.2f", (double) nz / rec);
+            scores[2] = 100 * atof(buf);
+        } else {
+            scores[2] = 0.0 / 0.0;
+        }
+    }
+    for (int metric = 0; metric < 2; metric++) {
+        free(tp[metric]);
+        free(pt_[metric]);
+    }
+    free(tt);
+    free(aun_tp);
+    free(aun_tt);
+    bins_free(&bins);
+    return HFG_OK;
+}

@@ -65,6 +65,15 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *data, const int8
                           const char *const *label_names, int n_labels, double overlap_ratio_threshold,
                           const char *bin_array_file, char *err, size_t errlen);
 
+/* The three scores the reference's alpha-tuning driver reads back from the *.benchmarking*.tsv files of a run
+ * (programs/src/tune_alpha_hmm_flagger.py:82-111): the F1-Score of the HARMONIC_MEAN_NO_HAP row of the overlap_based and
+ * of the base_level table, and 100 x the HARMONIC_MEAN auN ratio, for one annotation and one size bin (default names
+ * "whole_genome" / "ALL_SIZES"), each rounded to two decimals as the files print them (NaN where they print NA).
+ * Computed from the flat label arrays without writing any file: what a tuning loop needs per candidate alpha matrix. */
+int hfg_benchmark_scores(const hfg_cov_data *data, const int8_t *prediction, const int8_t *truth, int n_labels,
+                         double overlap_ratio_threshold, const char *bin_array_file, const char *annotation_label,
+                         const char *size_label, double scores[3], char *err, size_t errlen);
+
 #ifdef __cplusplus
 }
 #endif

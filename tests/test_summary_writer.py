@@ -66,3 +66,30 @@ def test_summary_tsv_matches_reference_run(tmp_path, with_truth, kind, seed, bin
         assert got == want, name
     main = open(mine).read()
     assert ("truth_based_auN" in main) == with_truth and ("TRUTH_VS_PREDICTION\t" in main) == with_truth
+
+
+@needs_ref
+def test_benchmark_scores_equal_the_numbers_the_tuning_driver_reads(tmp_path):
+    """hfg_benchmark_scores (no files written) against the three numbers programs/src/tune_alpha_hmm_flagger.py:82-111
+    parses out of the reference run's *.benchmarking*.tsv files."""
+    import pandas as pd
+    inp = str(tmp_path / "in.cov")
+    binfmt.write_random_rle_cov(inp, [9000, 310_000, 1_250_000, 123_457], seed=13, n_regions=3, with_truth=True)
+    out = str(tmp_path / "ref")
+    os.makedirs(out)
+    cmd = [REF, "-i", inp, "-o", out, "-W", "4000", "-C", "1000000", "-n", "2", "-t", "1e-12", "-l", "Err,Dup,Hap,Col", "-@", "2"]
+    assert subprocess.run(cmd, capture_output=True, text=True, timeout=600).returncode == 0
+    cov = binfmt.NativeCov(inp, 1_000_000, 4000)
+    labels = _labels_from_bed(os.path.join(out, "final_flagger_prediction.bed"), cov.workload)
+    got = cov.benchmark_scores(labels)
+    t = pd.read_csv(os.path.join(out, "prediction_summary_final.benchmarking.tsv"), sep="\t").rename(columns={"#Metric_Type": "Metric_Type"})
+    want = []
+    for metric in ("overlap_based", "base_level"):
+        row = t[(t.Metric_Type == metric) & (t.Category_Name == "whole_genome") & (t.Size_Bin_Name == "ALL_SIZES") &
+                (t.Label == "HARMONIC_MEAN_NO_HAP")]
+        want.append(float(row["F1-Score"].item()))
+    a = pd.read_csv(os.path.join(out, "prediction_summary_final.benchmarking.auN_ratio.tsv"), sep="\t")
+    row = a[(a.Category_Name == "whole_genome") & (a.Size_Bin_Name == "ALL_SIZES") & (a.Label == "HARMONIC_MEAN")]
+    want.append(100 * float(row["auN_Ratio"].item()))
+    assert all(abs(g - w) < 1e-9 for g, w in zip(got, want)), (got, want)
+    cov.close()
