@@ -30,6 +30,7 @@
 #define ORC_PI 3.14159          /* submodules/common/common.h:15 */
 #define ORC_TERM 1e-4           /* Transition.terminationProb, hmm_utils.c:2112 */
 #define ORC_MIN_COUNT 10        /* MIN_COUNT_FOR_PARAMETER_UPDATE, hmm_utils.h:11 */
+#define ORC_MAX_COV 250         /* MAX_COVERAGE_VALUE, hmm_utils.h:15 */
 #define ORC_TRUNC_FRACTION 0.25 /* EXP_TRUNC_POINT_COV_FRACTION, hmm_utils.h:12 */
 #define ORC_ERR_COEF 0.1        /* ERR_COMP_BINDING_COEF, hmm_utils.h:14 */
 #define ORC_PSEUDO 0.001        /* TRANSITION_PSEUDO_COUNT_VALUE, hmm.c:16 */
@@ -53,8 +54,91 @@ double orc_beta(const hfg_config *cfg, const hfg_chunk_desc *ch, int i) {
     return beta;
 }
 
+/* true for the states whose parameters live in the mixture slots mean/var/weight of hfg_region_params: the Gaussians, and
+ * every state of the negative-binomial model (theta in .mean, lambda in .var, see hmm_oracle.h) */
 static int state_is_gaussian(const hfg_config *cfg, int s) {
     return !(cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && s == HFG_STATE_ERR);
+}
+
+static int is_nb(const hfg_config *cfg) { return cfg->model_type == ORC_MODEL_NEGATIVE_BINOMIAL; }
+
+/* ---- negative-binomial model (MODEL_NEGATIVE_BINOMIAL; hmm_utils.c:320-640) ------------------------------------- */
+
+#include "digamma_coef.h" /* generated: oracle/tools/gen_digamma_coef.py */
+
+/* digamma in long double, restating the routine the reference vendors under submodules/digamma (digamma.c:36-116,
+ * R. J. Mathar 2005): reflection below 0, psi(x) = psi(1+x) - 1/x below 1, the duplication formula above 3, exact values at
+ * 1, 2, 3 and the Chebyshev series in T_n(x - 2) on (1, 3).  Same operations in the same order, so the long-double results
+ * agree bit for bit (tests/test_oracle_nb.py). */
+long double orc_digammal(long double x) {
+    const long double pi = 3.14159265358979323846264338327950288L;
+    const long double euler = 0.577215664901532860606512090082402431L;
+    const long double ln2 = 0.693147180559945309417232121458176568L;
+    if (x < 0.0L) return orc_digammal(1.0L - x) + pi / tanl(pi * (1.0L - x));
+    if (x < 1.0L) return orc_digammal(1.0L + x) - 1.0L / x;
+    if (x == 1.0L) return -euler;
+    if (x == 2.0L) return 1.0L - euler;
+    if (x == 3.0L) return 1.5L - euler;
+    if (x > 3.0L) return 0.5L * (orc_digammal(x / 2.0L) + orc_digammal((x + 1.0L) / 2.0L)) + ln2;
+    long double t = x - 2.0L;
+    long double prev = 1.0L, cur = t;
+    long double acc = orc_digamma_coef[0] + orc_digamma_coef[1] * cur;
+    for (int n = 2; n < ORC_DIGAMMA_NCOEF; n++) {
+        long double next = 2.0L * t * cur - prev; /* T_{n} = 2 t T_{n-1} - T_{n-2} */
+        acc += orc_digamma_coef[n] * next;
+        prev = cur;
+        cur = next;
+    }
+    return acc;
+}
+
+/* NegativeBinomial_getR, hmm_utils.c:455-458 */
+static double nb_r(double theta, double lambda) { return -1 * lambda / log(theta); }
+
+/* NegativeBinomial_getComponentProbs, hmm_utils.c:494-515.  Returns 1 if a pmf was NaN (the reference exits). */
+static int nb_comp_probs(const hfg_region_params *p, int s, int ncomp, uint8_t x, double *probs) {
+    int nan = 0;
+    for (int c = 0; c < ncomp; c++) {
+        double theta = p->mean[s][c];
+        double r = nb_r(theta, p->var[s][c]);
+        double w = p->weight[s][c];
+        probs[c] = w * exp(lgamma(r + x) - lgamma(r) - lgamma(x + 1) + r * log(theta) + (double) x * log(1 - theta));
+        if (probs[c] != probs[c]) nan = 1;
+        if (probs[c] < 1e-40) probs[c] = 1e-40;
+    }
+    return nan;
+}
+
+/* NegativeBinomial_fillDigammaTable, hmm_utils.c:392-406: table[x] = digamma(r + x), x = 0..MAX_COVERAGE_VALUE */
+static void nb_digamma_table(double theta, double lambda, double *table) {
+    double r = nb_r(theta, lambda);
+    table[0] = (double) orc_digammal(r);
+    for (int x = 1; x <= ORC_MAX_COV; x++) table[x] = table[x - 1] + 1.0 / (r + x - 1);
+}
+
+/* NegativeBinomial_updateEstimator, hmm_utils.c:536-563, for one (state, x) cell of the count histogram.
+ * theta statistics go to mean_*, lambda statistics to var_* (hmm_oracle.h). */
+static int nb_update_estimator(const hfg_region_params *p, int s, int ncomp, uint8_t x, double count,
+                               hfg_region_stats *st, const double *dig /* [ncomp][ORC_MAX_COV + 1] */) {
+    double probs[HFG_MAX_COMPS];
+    int nan = nb_comp_probs(p, s, ncomp, x, probs);
+    double tot = 0.0;
+    for (int c = 0; c < ncomp; c++) tot += probs[c];
+    for (int c = 0; c < ncomp; c++) {
+        double theta = p->mean[s][c];
+        double r = nb_r(theta, p->var[s][c]);
+        double bt = -1 * theta / (1 - theta) - 1 / log(theta);
+        double w = count * probs[c] / tot;
+        const double *table = dig + (size_t) c * (ORC_MAX_COV + 1);
+        double delta = r * (table[x] - table[0]);
+        st->var_num[s][c] += w * delta; /* lambdaEstimator */
+        st->var_den[s][c] += w;
+        st->mean_num[s][c] += w * delta * bt; /* thetaEstimator */
+        st->mean_den[s][c] += w * delta * bt + w * (x - delta);
+        st->weight_num[s][c] += w; /* ParameterEstimator_incrementDenominatorForAllComps, hmm_utils.c:66-74 */
+        for (int k = 0; k < ncomp; k++) st->weight_den[s][k] += w;
+    }
+    return nan;
 }
 
 /* Gaussian_getComponentProbs, hmm_utils.c:768-793.  Returns 1 if a pdf was NaN (the reference exits). */
@@ -88,7 +172,10 @@ static double emission(const hfg_config *cfg, const hfg_region_params *p, int s,
                        double alpha, double beta, int *nan) {
     if (!state_is_gaussian(cfg, s)) return trunc_exp_prob(p, x, beta);
     double probs[HFG_MAX_COMPS];
-    *nan |= gaussian_comp_probs(p, s, cfg->n_comps[s], x, preX, alpha, beta, probs);
+    if (is_nb(cfg)) /* NegativeBinomial_getProb, hmm_utils.c:479-484: no dependence on preX, alpha or beta */
+        *nan |= nb_comp_probs(p, s, cfg->n_comps[s], x, probs);
+    else
+        *nan |= gaussian_comp_probs(p, s, cfg->n_comps[s], x, preX, alpha, beta, probs);
     double tot = 0.0;
     for (int c = 0; c < cfg->n_comps[s]; c++) tot += probs[c];
     return tot;
@@ -120,7 +207,9 @@ static double trans_cond(const hfg_config *cfg, const hfg_region_params *p, int 
 static int run_chunk(const hfg_config *cfg, const hfg_chunk_desc *ch, const uint16_t *cov, const uint16_t *mapq,
                      const uint16_t *clip, const uint8_t *region, const double *alpha,
                      const hfg_region_params *params, hfg_region_stats *stats, double *loglik_out, int8_t *labels,
-                     double *post, double *f, double *b, double *scales, int forward_only) {
+                     double *post, double *f, double *b, double *scales, int forward_only,
+                     double *nb_counts /* [R][NS][ORC_MAX_COV], zeroed; NULL unless negative binomial */,
+                     const double *nb_dig /* [R][NS][HFG_MAX_COMPS][ORC_MAX_COV + 1] */) {
     const int L = ch->n_windows;
     int nan = 0;
     double loglik = 0.0;
@@ -201,7 +290,11 @@ static int run_chunk(const hfg_config *cfg, const hfg_chunk_desc *ch, const uint
                                            : trans_cond(cfg, p, pre, s, cov[i + 1], mapq[i + 1], clip[i + 1]);
                 double count = f[i * NS + pre] * tProb * eProb * b[(i + 1) * NS + s];
                 double adj = count / ORC_TERM;
-                if (!state_is_gaussian(cfg, s)) { /* TruncExponential_updateEstimator, hmm_utils.c:1027-1034 */
+                if (is_nb(cfg)) { /* hmm.c:615-617 -> CountData_increment, count_data.c:56-64: histogram of x per state,
+                                     values past the last bin (x = 250) land in bin 249 */
+                    int bin = x < ORC_MAX_COV ? x : ORC_MAX_COV - 1;
+                    nb_counts[((size_t) r * NS + s) * ORC_MAX_COV + bin] += adj;
+                } else if (!state_is_gaussian(cfg, s)) { /* TruncExponential_updateEstimator, hmm_utils.c:1027-1034 */
                     st->lambda_num += adj * x;
                     st->lambda_den += adj;
                 } else { /* Gaussian_updateEstimator, hmm_utils.c:812-839 */
@@ -225,6 +318,17 @@ static int run_chunk(const hfg_config *cfg, const hfg_chunk_desc *ch, const uint
                 st->trans_count[pre][s] += adj; /* TransitionCountData_increment, hmm_utils.c:2010-2015 */
             }
         }
+    }
+    if (is_nb(cfg)) { /* EM_updateEstimators tail, hmm.c:643-649 -> EmissionDistSeries_updateAllEstimatorsUsingCountData,
+                         hmm_utils.c:1662-1672: region, state, x ascending, cells with a positive count only */
+        for (int r = 0; r < cfg->n_regions; r++)
+            for (int s = 0; s < NS; s++)
+                for (int x = 0; x < ORC_MAX_COV; x++) {
+                    double count = nb_counts[((size_t) r * NS + s) * ORC_MAX_COV + x];
+                    if (0 < count)
+                        nan |= nb_update_estimator(&params[r], s, cfg->n_comps[s], (uint8_t) x, count, &stats[r],
+                                                   nb_dig + ((size_t) r * NS + s) * HFG_MAX_COMPS * (ORC_MAX_COV + 1));
+                }
     }
     if (nan) return HFG_ERR_NAN;
 
@@ -263,14 +367,26 @@ int orc_estep(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *chunks,
     double *f = malloc(sizeof(double) * NS * (size_t) maxL);
     double *b = malloc(sizeof(double) * NS * (size_t) maxL);
     double *sc = malloc(sizeof(double) * (size_t) maxL);
+    double *nb_counts = NULL, *nb_dig = NULL;
+    const size_t n_counts = (size_t) R * NS * ORC_MAX_COV;
+    if (is_nb(cfg) && !forward_only) {
+        nb_counts = malloc(sizeof(double) * n_counts);
+        nb_dig = calloc((size_t) R * NS * HFG_MAX_COMPS * (ORC_MAX_COV + 1), sizeof(double));
+        for (int r = 0; r < R; r++) /* every chunk's copy of the model refills the same table (hmm_utils.c:377-390) */
+            for (int s = 0; s < NS; s++)
+                for (int k = 0; k < cfg->n_comps[s]; k++)
+                    nb_digamma_table(params[r].mean[s][k], params[r].var[s][k],
+                                     nb_dig + (((size_t) r * NS + s) * HFG_MAX_COMPS + k) * (ORC_MAX_COV + 1));
+    }
     for (int c = 0; c < n_chunks && status == HFG_OK; c++) {
         const hfg_chunk_desc *ch = &chunks[c];
         const int64_t o = ch->offset;
         double ll = 0.0;
         memset(priv, 0, (size_t) R * sizeof(hfg_region_stats));
+        if (nb_counts) memset(nb_counts, 0, sizeof(double) * n_counts);
         status = run_chunk(cfg, ch, cov + o, mapq + o, clip + o, region + o, alpha, params, priv, &ll,
                            labels ? labels + o : NULL, posteriors ? posteriors + o * NS : NULL, f, b, sc,
-                           forward_only);
+                           forward_only, nb_counts, nb_dig);
         if (status != HFG_OK) break;
         total += ll;
         if (chunk_logliks) chunk_logliks[c] = ll;
@@ -288,6 +404,8 @@ int orc_estep(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *chunks,
     free(f);
     free(b);
     free(sc);
+    free(nb_counts);
+    free(nb_dig);
     if (loglik) *loglik = total;
     return status;
 }
@@ -327,6 +445,13 @@ int orc_model_init(const hfg_config *cfg, const int32_t *region_coverages, int w
                 p->mean[s][c] = means[s][c] * scale;   /* Double_multiply2DArray, hmm.c:43-47 */
                 p->var[s][c] = p->mean[s][c] * 1.0;    /* Gaussian_constructByMean(mean, 1.0, n), hmm_utils.c:733-741 */
                 p->weight[s][c] = 1.0 / cfg->n_comps[s]; /* hmm_utils.c:667 */
+                if (is_nb(cfg)) { /* NegativeBinomial_constructByMean(mean, 1.5, n), hmm_utils.c:335-342,433-453,1635-1639 */
+                    double mean = p->mean[s][c], var = mean * 1.5;
+                    double theta = mean / var;
+                    double r = pow(mean, 2) / (var - mean);
+                    p->mean[s][c] = theta;
+                    p->var[s][c] = -1 * r * log(theta);
+                }
             }
         }
         if (cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN) {
@@ -390,6 +515,14 @@ static double bind_coef(int s, int c) {
     }
 }
 
+/* type 0 = Gaussian mean / NB theta, type 1 = Gaussian var / NB lambda.  The NB theta is bound with coefficient 1 in every
+ * state and component (ParameterBinding_getDefault1DArrayForNegativeBinomial, hmm_utils.c:240-290); everything else uses
+ * the 0.1 / 0.5 / 1 / 2+c ladder. */
+static double bind_factor(const hfg_config *cfg, int type, int s, int c) {
+    if (is_nb(cfg) && type == 0) return 1.0;
+    return bind_coef(s, c);
+}
+
 /* Gaussian_updateParameter / TruncExponential_updateParameter convergence rule, hmm_utils.c:855-858,1051-1053 */
 static int conv_emission(double oldv, double newv, double tol) {
     double diffRatio = 1.0e-4 < oldv ? fabs(newv / oldv - 1.0) : 0.0;
@@ -410,7 +543,7 @@ int orc_mstep(const hfg_config *cfg, hfg_region_params *params, const hfg_region
             for (int s = 0; s < NS; s++) {
                 if (!state_is_gaussian(cfg, s)) continue;
                 for (int c = 0; c < cfg->n_comps[s]; c++) {
-                    double factor = bind_coef(s, c);
+                    double factor = bind_factor(cfg, type, s, c);
                     double num = type == 0 ? st->mean_num[s][c] : st->var_num[s][c];
                     double den = type == 0 ? st->mean_den[s][c] : st->var_den[s][c];
                     bnum += num / factor;
@@ -421,7 +554,7 @@ int orc_mstep(const hfg_config *cfg, hfg_region_params *params, const hfg_region
             for (int s = 0; s < NS; s++) {
                 if (!state_is_gaussian(cfg, s)) continue;
                 for (int c = 0; c < cfg->n_comps[s]; c++) {
-                    double value = est * bind_coef(s, c);
+                    double value = est * bind_factor(cfg, type, s, c);
                     if (ORC_MIN_COUNT < bden) {
                         double *dst = type == 0 ? &p->mean[s][c] : &p->var[s][c];
                         converged &= conv_emission(*dst, value, tol);
@@ -550,7 +683,8 @@ int orc_feasible(const hfg_config *cfg, const hfg_region_params *params) { /* HM
                 if (!(0 < p->trunc_point)) feasible = 0;
                 continue;
             }
-            for (int c = 0; c < cfg->n_comps[s]; c++) { /* hmm_utils.c:685-694 */
+            for (int c = 0; c < cfg->n_comps[s]; c++) { /* hmm_utils.c:685-694; NB: hmm_utils.c:366-375 */
+                if (is_nb(cfg) && !(p->mean[s][c] < 1)) feasible = 0;
                 if (!(0 < p->mean[s][c])) feasible = 0;
                 if (!(0 < p->var[s][c])) feasible = 0;
                 if (!((0 <= p->weight[s][c]) && (p->weight[s][c] <= 1))) feasible = 0;

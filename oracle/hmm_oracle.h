@@ -10,6 +10,13 @@
 extern "C" {
 #endif
 
+/* The negative-binomial model (reference `--modelType negative_binomial`, MODEL_NEGATIVE_BINOMIAL) is restated by the
+ * oracle ahead of the product: cfg->model_type == ORC_MODEL_NEGATIVE_BINOMIAL selects it in every orc_ and ref_ entry point.
+ * hfg_region_params.mean[s][c] then holds theta, .var[s][c] lambda, .weight[s][c] the mixture weights (NegativeBinomial,
+ * hmm_utils.h); hfg_region_stats.mean_* hold the theta estimator, .var_* the lambda estimator, .weight_* the weights'. */
+#define ORC_MODEL_NEGATIVE_BINOMIAL 2
+long double orc_digammal(long double x);
+
 double orc_beta(const hfg_config *cfg, const hfg_chunk_desc *ch, int i);
 
 int orc_estep(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,

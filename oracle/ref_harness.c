@@ -48,7 +48,10 @@ static MatrixDouble *make_alpha(const double *alpha) {
     return m;
 }
 
+/* model_type 2 = negative binomial (oracle/hmm_oracle.h ORC_MODEL_NEGATIVE_BINOMIAL; not part of the product ABI yet):
+ * hfg_region_params.mean holds theta, .var holds lambda, .weight the mixture weights (NegativeBinomial, hmm_utils.h) */
 static ModelType model_type(const hfg_config *cfg) {
+    if (cfg->model_type == 2) return MODEL_NEGATIVE_BINOMIAL;
     return cfg->model_type == HFG_MODEL_GAUSSIAN ? MODEL_GAUSSIAN : MODEL_TRUNC_EXP_GAUSSIAN;
 }
 
@@ -74,6 +77,14 @@ static void params_to_model(const hfg_config *cfg, const hfg_region_params *para
                 TruncExponential *te = ed->dist;
                 te->lambda = params[r].lambda;
                 te->truncPoint = params[r].trunc_point;
+            } else if (ed->distType == DIST_NEGATIVE_BINOMIAL) {
+                NegativeBinomial *nb = ed->dist;
+                for (int c = 0; c < nb->numberOfComps; c++) {
+                    nb->theta[c] = params[r].mean[s][c];
+                    nb->lambda[c] = params[r].var[s][c];
+                    nb->weights[c] = params[r].weight[s][c];
+                }
+                NegativeBinomial_fillDigammaTable(nb); /* as after every parameter update (hmm_utils.c:1893-1899) */
             } else {
                 Gaussian *g = ed->dist;
                 for (int c = 0; c < g->numberOfComps; c++) {
@@ -99,6 +110,13 @@ static void model_to_params(const hfg_config *cfg, HMM *model, hfg_region_params
                 TruncExponential *te = ed->dist;
                 params[r].lambda = te->lambda;
                 params[r].trunc_point = te->truncPoint;
+            } else if (ed->distType == DIST_NEGATIVE_BINOMIAL) {
+                NegativeBinomial *nb = ed->dist;
+                for (int c = 0; c < nb->numberOfComps; c++) {
+                    params[r].mean[s][c] = nb->theta[c];
+                    params[r].var[s][c] = nb->lambda[c];
+                    params[r].weight[s][c] = nb->weights[c];
+                }
             } else {
                 Gaussian *g = ed->dist;
                 for (int c = 0; c < g->numberOfComps; c++) {
@@ -124,6 +142,16 @@ static void model_to_stats(const hfg_config *cfg, HMM *model, hfg_region_stats *
                 TruncExponential *te = ed->dist;
                 stats[r].lambda_num = te->lambdaEstimator->numeratorPerComp[0];
                 stats[r].lambda_den = te->lambdaEstimator->denominatorPerComp[0];
+            } else if (ed->distType == DIST_NEGATIVE_BINOMIAL) {
+                NegativeBinomial *nb = ed->dist; /* theta -> mean_*, lambda -> var_* */
+                for (int c = 0; c < nb->numberOfComps; c++) {
+                    stats[r].mean_num[s][c] = nb->thetaEstimator->numeratorPerComp[c];
+                    stats[r].mean_den[s][c] = nb->thetaEstimator->denominatorPerComp[c];
+                    stats[r].var_num[s][c] = nb->lambdaEstimator->numeratorPerComp[c];
+                    stats[r].var_den[s][c] = nb->lambdaEstimator->denominatorPerComp[c];
+                    stats[r].weight_num[s][c] = nb->weightsEstimator->numeratorPerComp[c];
+                    stats[r].weight_den[s][c] = nb->weightsEstimator->denominatorPerComp[c];
+                }
             } else {
                 Gaussian *g = ed->dist;
                 for (int c = 0; c < g->numberOfComps; c++) {
@@ -151,6 +179,16 @@ static void stats_to_model(const hfg_config *cfg, const hfg_region_stats *stats,
                 TruncExponential *te = ed->dist;
                 te->lambdaEstimator->numeratorPerComp[0] = stats[r].lambda_num;
                 te->lambdaEstimator->denominatorPerComp[0] = stats[r].lambda_den;
+            } else if (ed->distType == DIST_NEGATIVE_BINOMIAL) {
+                NegativeBinomial *nb = ed->dist;
+                for (int c = 0; c < nb->numberOfComps; c++) {
+                    nb->thetaEstimator->numeratorPerComp[c] = stats[r].mean_num[s][c];
+                    nb->thetaEstimator->denominatorPerComp[c] = stats[r].mean_den[s][c];
+                    nb->lambdaEstimator->numeratorPerComp[c] = stats[r].var_num[s][c];
+                    nb->lambdaEstimator->denominatorPerComp[c] = stats[r].var_den[s][c];
+                    nb->weightsEstimator->numeratorPerComp[c] = stats[r].weight_num[s][c];
+                    nb->weightsEstimator->denominatorPerComp[c] = stats[r].weight_den[s][c];
+                }
             } else {
                 Gaussian *g = ed->dist;
                 for (int c = 0; c < g->numberOfComps; c++) {

@@ -111,6 +111,15 @@ class _Checker:
         return dict(rc=rc, params=params, logliks=logliks[:n.value + 1].copy(), alpha_rates=rates[:n.value].copy(),
                     labels=labels)
 
+    def digamma(self, x):
+        """digamma of a double argument in long double, returned as (hi, lo) doubles with hi + lo exact -- the routine
+        behind the negative-binomial model's table (orc_digammal / the reference's digammal)."""
+        f = getattr(self.lib, "orc_digammal" if self.prefix == "orc" else "digammal")
+        f.restype, f.argtypes = C.c_longdouble, [C.c_longdouble]
+        v = np.longdouble(f(np.longdouble(x)))
+        hi = np.float64(v)
+        return float(hi), float(v - np.longdouble(hi))
+
     def best_num_collapsed_comps(self, max_cov, region_coverages):
         rc_ = np.ascontiguousarray(region_coverages, np.int32)
         return self._fn("best_num_collapsed_comps")(C.c_int(int(max_cov)), ptr(rc_), C.c_int(len(rc_)))
