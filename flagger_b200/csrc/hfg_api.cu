@@ -186,11 +186,13 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         return HFG_ERR_CUDA;
     }
     ctx->max_blocks = ctx->num_sms; /* one persistent 512-thread CTA per SM, all co-resident (cooperative launch) */
+    ctx->n_ranks = 1;
+    /* from here on a failure releases whatever exists already through hfg_destroy (it skips what is still NULL) */
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaEventCreate(&ctx->ev2) != cudaSuccess || cudaEventCreate(&ctx->ev3) != cudaSuccess) {
         fail(NULL, HFG_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
-        free(ctx);
+        hfg_destroy(ctx);
         return HFG_ERR_CUDA;
     }
     const size_t pbytes = sizeof(hfg_region_params) * (size_t) cfg->n_regions;
@@ -200,21 +202,27 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         if (cudaMallocHost((void **) &hp, pbytes * STAGE_SLOTS) != cudaSuccess ||
             cudaMalloc((void **) &dp, pbytes * STAGE_SLOTS) != cudaSuccess) {
             fail(NULL, HFG_ERR_CUDA, "parameter staging allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
-            free(ctx);
+            if (hp) cudaFreeHost(hp);
+            hfg_destroy(ctx);
             return HFG_ERR_CUDA;
         }
         for (int i = 0; i < STAGE_SLOTS; i++) {
             ctx->h_params[i] = (hfg_region_params *) (hp + pbytes * i);
             ctx->d_params[i] = (hfg_region_params *) (dp + pbytes * i);
+        }
+        for (int i = 0; i < STAGE_SLOTS; i++)
             if (cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming) != cudaSuccess) {
                 fail(NULL, HFG_ERR_CUDA, "event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
-                free(ctx);
+                hfg_destroy(ctx);
                 return HFG_ERR_CUDA;
             }
-        }
     }
     ctx->last_params = (hfg_region_params *) malloc(pbytes);
-    ctx->n_ranks = 1;
+    if (!ctx->last_params) {
+        fail(NULL, HFG_ERR_NOMEM, "hfg_create: out of memory");
+        hfg_destroy(ctx);
+        return HFG_ERR_NOMEM;
+    }
     ctx->graph_disabled = getenv("HFG_NO_GRAPH") != NULL; /* A/B switch: plain stream launches instead of graph replay */
     *out = ctx;
     return HFG_OK;
@@ -314,27 +322,38 @@ static void free_device(hfg_ctx *ctx) {
     ctx->have_chunks = 0;
 }
 
+/* unmaps every peer mailbox opened by hfg_peer_connect (the own one is a plain allocation) */
+static void close_peers(hfg_ctx *ctx) {
+    for (int p = 0; p < HFG_MAX_PEERS; p++) {
+        if (ctx->peer_box[p] && ctx->peer_box[p] != ctx->d_mailbox) cudaIpcCloseMemHandle(ctx->peer_box[p]);
+        ctx->peer_box[p] = NULL;
+    }
+    ctx->n_ranks = 1;
+    ctx->rank = 0;
+}
+
 extern "C" void hfg_destroy(hfg_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_device(ctx);
     cudaFreeHost(ctx->h_params[0]);
     cudaFree(ctx->d_params[0]);
-    for (int i = 0; i < STAGE_SLOTS; i++) cudaEventDestroy(ctx->stage_ev[i]);
-    cudaEventDestroy(ctx->ev0);
-    cudaEventDestroy(ctx->ev1);
-    cudaEventDestroy(ctx->ev2);
-    cudaEventDestroy(ctx->ev3);
-    for (int p = 0; p < ctx->n_ranks; p++)
-        if (p != ctx->rank && ctx->peer_box[p]) cudaIpcCloseMemHandle(ctx->peer_box[p]);
+    for (int i = 0; i < STAGE_SLOTS; i++)
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    close_peers(ctx);
     cudaFree(ctx->d_mailbox);
     cudaFree(ctx->d_epoch);
     cudaFree(ctx->d_flush);
     for (int i = 0; i < 2 * ctx->em_ev_cap; i++) cudaEventDestroy(ctx->em_ev[i]);
     free(ctx->em_ev);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx->last_params);
+    cudaGetLastError(); /* a context torn down half-built must not leave a sticky-looking error behind */
     free(ctx);
 }
 
@@ -853,6 +872,7 @@ extern "C" int hfg_get_posteriors(hfg_ctx *ctx, double *posteriors) {
     if (!ctx->d_post) CU(cudaMalloc((void **) &ctx->d_post, bytes));
     /* the E-step is deterministic: re-running it with the same parameters reproduces the same f^, b^, scales */
     hfg_region_params *p = (hfg_region_params *) malloc(sizeof(hfg_region_params) * (size_t) ctx->cfg.n_regions);
+    if (!p) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
     double al[16];
     memcpy(p, ctx->last_params, sizeof(hfg_region_params) * (size_t) ctx->cfg.n_regions);
     memcpy(al, ctx->last_alpha, sizeof(al));
@@ -915,8 +935,16 @@ extern "C" int hfg_em_begin(hfg_ctx *ctx, const double *alpha, const hfg_region_
         cudaEvent_t *ne = (cudaEvent_t *) realloc(ctx->em_ev, sizeof(cudaEvent_t) * 2 * (size_t) max_esteps);
         if (!ne) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
         ctx->em_ev = ne;
-        for (int i = 2 * ctx->em_ev_cap; i < 2 * max_esteps; i++) CU(cudaEventCreate(&ctx->em_ev[i]));
-        ctx->em_ev_cap = max_esteps;
+        while (ctx->em_ev_cap < max_esteps) { /* pair by pair, so that a failure leaves only complete pairs to destroy */
+            const int i = 2 * ctx->em_ev_cap;
+            CU(cudaEventCreate(&ctx->em_ev[i]));
+            cudaError_t e = cudaEventCreate(&ctx->em_ev[i + 1]);
+            if (e != cudaSuccess) {
+                cudaEventDestroy(ctx->em_ev[i]);
+                return fail(ctx, HFG_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e));
+            }
+            ctx->em_ev_cap++;
+        }
     }
     CU(cudaEventSynchronize(ctx->stage_ev[0]));
     memcpy(ctx->h_params[0], params, pb);
@@ -1135,14 +1163,18 @@ extern "C" int hfg_debug_exp(hfg_ctx *ctx, const double *in, double *out, int n)
     if (!ctx || !in || !out || n < 1) return HFG_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     double *d_in = NULL, *d_out = NULL;
-    CU(cudaMalloc((void **) &d_in, sizeof(double) * (size_t) n));
-    CU(cudaMalloc((void **) &d_out, sizeof(double) * (size_t) n));
-    CU(cudaMemcpy(d_in, in, sizeof(double) * (size_t) n, cudaMemcpyHostToDevice));
-    hfg_debug_exp_kernel<<<(n + 255) / 256, 256>>>(d_in, d_out, n);
-    ctx->launches += 1;
-    CU(cudaMemcpy(out, d_out, sizeof(double) * (size_t) n, cudaMemcpyDeviceToHost));
+    const size_t bytes = sizeof(double) * (size_t) n;
+    cudaError_t e = cudaMalloc((void **) &d_in, bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void **) &d_out, bytes);
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        hfg_debug_exp_kernel<<<(n + 255) / 256, 256>>>(d_in, d_out, n);
+        ctx->launches += 1;
+        e = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost);
+    }
     cudaFree(d_in);
     cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ctx, HFG_ERR_CUDA, "hfg_debug_exp: %s", cudaGetErrorString(e));
     return HFG_OK;
 }
 
@@ -1238,6 +1270,12 @@ extern "C" int hfg_peer_connect(hfg_ctx *ctx, int n_ranks, int rank, const void 
         return fail(ctx, HFG_ERR_INVALID, "hfg_peer_connect: %d ranks (limit %d), rank %d", n_ranks, HFG_MAX_PEERS, rank);
     if (!ctx->d_mailbox) return fail(ctx, HFG_ERR_INVALID, "hfg_peer_connect: call hfg_peer_export first");
     CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    close_peers(ctx); /* a second connect replaces the first; a failure below leaves the context single-rank */
+    if (ctx->gexec) { /* the captured graph was built for the previous set of peers */
+        cudaGraphExecDestroy(ctx->gexec);
+        ctx->gexec = NULL;
+    }
     for (int p = 0; p < n_ranks; p++) {
         if (p == rank) {
             ctx->peer_box[p] = ctx->d_mailbox;
@@ -1246,14 +1284,14 @@ extern "C" int hfg_peer_connect(hfg_ctx *ctx, int n_ranks, int rank, const void 
         cudaIpcMemHandle_t h;
         memcpy(&h, (const char *) handles + (size_t) p * sizeof(h), sizeof(h));
         void *ptr = NULL;
-        CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            close_peers(ctx);
+            return fail(ctx, HFG_ERR_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", p, cudaGetErrorString(e));
+        }
         ctx->peer_box[p] = (double *) ptr;
     }
     ctx->n_ranks = n_ranks;
     ctx->rank = rank;
-    if (ctx->gexec) { /* the captured graph was built without the exchange */
-        cudaGraphExecDestroy(ctx->gexec);
-        ctx->gexec = NULL;
-    }
     return HFG_OK;
 }
