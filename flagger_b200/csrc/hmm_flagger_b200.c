@@ -48,6 +48,12 @@ static void die(const char *msg) {
     exit(EXIT_FAILURE);
 }
 
+static void *xmalloc(size_t bytes) {
+    void *p = malloc(bytes ? bytes : 1);
+    if (!p) die("out of host memory");
+    return p;
+}
+
 static int is_gauss(const hfg_config *cfg, int s) {
     return !(cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && s == HFG_STATE_ERR);
 }
@@ -129,7 +135,7 @@ static void write_final_bed(const char *path, const char *track, const hfg_cov_d
     FILE *f = fopen(path, "w");
     if (!f) die("cannot write the final BED");
     fprintf(f, "track name=%s visibility=1 itemRgb=\"On\"\n", track);
-    Block *blocks = malloc(sizeof(Block) * (size_t) (d->n_windows + 1));
+    Block *blocks = xmalloc(sizeof(Block) * (size_t) (d->n_windows + 1));
     int nb = 0, bed_start = 0, pre_end = 0, pre_label = -1;
     const char *pre_ctg = NULL;
     for (int c = 0; c < d->n_chunks; c++) {
@@ -246,6 +252,7 @@ static void subset_contigs(hfg_cov_data *d, const char *list_path) {
         line[strcspn(line, "\r\n")] = '\0';
         if (!line[0]) continue;
         names = realloc(names, sizeof(char *) * (size_t) (n + 1));
+        if (!names) die("out of host memory");
         names[n++] = strdup(line);
     }
     fclose(f);
@@ -453,8 +460,8 @@ int main(int argc, char *argv[]) {
     cfg.min_high_mapq_ratio = min_mapq;
     cfg.min_highly_clipped_ratio = 1.0; /* src/hmm_flagger.c:222 */
     cfg.device = device;
-    hfg_region_params *params = malloc(sizeof(hfg_region_params) * (size_t) cfg.n_regions);
-    hfg_region_stats *stats = malloc(sizeof(hfg_region_stats) * (size_t) cfg.n_regions);
+    hfg_region_params *params = xmalloc(sizeof(hfg_region_params) * (size_t) cfg.n_regions);
+    hfg_region_stats *stats = xmalloc(sizeof(hfg_region_stats) * (size_t) cfg.n_regions);
     if (hfg_model_init(&cfg, d->region_coverages, d->window_len, d->start_only, params) != HFG_OK) die("invalid model configuration");
 
     /* 4. EM (runHMMFlagger, src/hmm_flagger.c:285-488) */
@@ -471,11 +478,11 @@ int main(int argc, char *argv[]) {
     if (hfg_create(&ctx, &cfg) != HFG_OK) die(hfg_last_error(NULL));
     if (hfg_set_chunks(ctx, d->n_chunks, d->chunks, d->cov, d->cov_high_mapq, d->cov_high_clip, d->region) != HFG_OK)
         die(hfg_last_error(ctx));
-    int8_t *labels = malloc((size_t) d->n_windows);
+    int8_t *labels = xmalloc((size_t) d->n_windows);
     int iter = 1, converged = 0, final_done = 0;
     double loglik = 0.0;
-    hfg_region_params *params_before = malloc(sizeof(hfg_region_params) * (size_t) cfg.n_regions);
-    hfg_region_stats *stats_scratch = malloc(sizeof(hfg_region_stats) * (size_t) cfg.n_regions);
+    hfg_region_params *params_before = xmalloc(sizeof(hfg_region_params) * (size_t) cfg.n_regions);
+    hfg_region_stats *stats_scratch = xmalloc(sizeof(hfg_region_stats) * (size_t) cfg.n_regions);
     /* Iterations whose results are needed on the host between E-steps run through the blocking call + host M-step: the first
      * one always (its labels are prediction_summary_initial.tsv, src/hmm_flagger.c:361-379), all of them with
      * --accelerate, -w or -k.  Otherwise the REST of the loop -- every further E-step, the M-steps, the convergence test and
@@ -485,7 +492,7 @@ int main(int argc, char *argv[]) {
     while (iter <= iterations && !converged) {
         if (!per_iteration_outputs && iter > 1 && iterations - iter + 2 <= 4096) {
             const int remaining = iterations - iter + 1;
-            double *lls = malloc(sizeof(double) * ((size_t) remaining + 1));
+            double *lls = xmalloc(sizeof(double) * ((size_t) remaining + 1));
             int n_esteps = 0, rc_d = hfg_em_begin(ctx, alpha, params, tol, remaining + 1);
             for (int it = 0; it < remaining && rc_d == HFG_OK; it++) rc_d = hfg_em_enqueue(ctx, 0);
             if (rc_d == HFG_OK) rc_d = hfg_em_enqueue(ctx, 1);
@@ -547,7 +554,7 @@ int main(int argc, char *argv[]) {
     write_transition_tsv(out_dir, "final", &cfg, params);
     write_emission_tsv(out_dir, "final", &cfg, params);
     if (write_post) {
-        double *post = malloc(sizeof(double) * 4 * (size_t) d->n_windows);
+        double *post = xmalloc(sizeof(double) * 4 * (size_t) d->n_windows);
         if (hfg_get_posteriors(ctx, post) != HFG_OK) die(hfg_last_error(ctx));
         write_posterior_bed(out_dir, d, post, labels);
         free(post);
