@@ -13,6 +13,8 @@ MAX_REGIONS = 64
 
 MODEL_TRUNC_EXP_GAUSSIAN = 0
 MODEL_GAUSSIAN = 1
+MODEL_NEGATIVE_BINOMIAL = 2  # host functions only so far (include/hfg.h)
+NB_TABLE_X, NB_BINS = 251, 250  # HFG_NB_TABLE_X, HFG_NB_BINS
 
 OK, ERR_INVALID, ERR_CUDA, ERR_SCALE_UNDERFLOW, ERR_NAN, ERR_NOMEM = range(6)
 

@@ -57,7 +57,7 @@ EXPORTED_SYMBOLS = (
     "hfg_debug_layout_compare", "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_read_cov",
     "hfg_read_bin", "hfg_cov_free", "hfg_write_summary_tsv", "hfg_benchmark_scores", "hfg_params_feasible", "hfg_squarem_alpha_rate",
     "hfg_squarem_prime", "hfg_squarem_shrink", "hfg_squarem_iteration", "hfg_run_em_accelerated",
-    "hfg_release_cached_memory",
+    "hfg_release_cached_memory", "hfg_nb_emission_table", "hfg_nb_stats_from_histogram", "hfg_digammal",
 )
 
 
@@ -151,6 +151,37 @@ def squarem(cfg, p0, p1, p2, n_shrinks=0, margin=1e-2):
     if rc != 0:
         raise HfgError(rc, "hfg_squarem: the extrapolated mixture weights do not sum to > 0")
     return prime, rate.value, params_feasible(cfg, prime)
+
+
+def nb_emission_table(cfg, params):
+    """Negative-binomial pmf of every (region, state, x): [R, 4, 251] (hfg_nb_emission_table; host only)."""
+    R = int(cfg["n_regions"][0])
+    table = np.zeros((R, 4, _abi.NB_TABLE_X))
+    rc = lib().hfg_nb_emission_table(ptr(cfg), ptr(np.ascontiguousarray(params)), ptr(table))
+    if rc != 0:
+        raise HfgError(rc, "hfg_nb_emission_table: invalid arguments or a NaN pmf")
+    return table
+
+
+def nb_stats_from_histogram(cfg, params, histogram, stats=None):
+    """theta / lambda / weight estimator sums from the [R, 4, 250] pair-mass histogram (hfg_nb_stats_from_histogram)."""
+    R = int(cfg["n_regions"][0])
+    hist = np.ascontiguousarray(histogram, np.float64)
+    assert hist.shape == (R, 4, _abi.NB_BINS)
+    stats = np.zeros(R, dtype=_abi.region_stats_dtype) if stats is None else stats
+    rc = lib().hfg_nb_stats_from_histogram(ptr(cfg), ptr(np.ascontiguousarray(params)), ptr(hist), ptr(stats))
+    if rc != 0:
+        raise HfgError(rc, "hfg_nb_stats_from_histogram: invalid arguments or a NaN pmf")
+    return stats
+
+
+def digamma(x):
+    """hfg_digammal(x) as (hi, lo) doubles with hi + lo the exact long-double result."""
+    f = lib().hfg_digammal
+    f.restype, f.argtypes = C.c_longdouble, [C.c_longdouble]
+    v = np.longdouble(f(np.longdouble(x)))
+    hi = np.float64(v)
+    return float(hi), float(v - np.longdouble(hi))
 
 
 class HmmFlaggerGPU:

@@ -124,7 +124,7 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     if (!out || !cfg) return fail(NULL, HFG_ERR_INVALID, "hfg_create: NULL argument");
     *out = NULL;
     if (cfg->model_type != HFG_MODEL_TRUNC_EXP_GAUSSIAN && cfg->model_type != HFG_MODEL_GAUSSIAN)
-        return fail(NULL, HFG_ERR_INVALID, "hfg_create: model_type %d not supported (negative_binomial is out of scope)",
+        return fail(NULL, HFG_ERR_INVALID, "hfg_create: model_type %d has no device path (negative_binomial: host functions only so far)",
                     cfg->model_type);
     if (cfg->n_regions < 1 || cfg->n_regions > HFG_MAX_REGIONS)
         return fail(NULL, HFG_ERR_INVALID, "hfg_create: n_regions %d outside 1..%d", cfg->n_regions, HFG_MAX_REGIONS);

@@ -54,6 +54,8 @@ int hfg_model_init(const hfg_config *cfg, const int32_t *region_coverages, int w
                 p->mean[s][c] = m * region_scale;          /* hmm.c:43-47 */
                 p->var[s][c] = p->mean[s][c] * 1.0;        /* hmm_utils.c:733-741 with factor 1.0 (:1622,1630) */
                 p->weight[s][c] = 1.0 / cfg->n_comps[s];   /* hmm_utils.c:667 */
+                if (cfg->model_type == HFG_MODEL_NEGATIVE_BINOMIAL) /* same means, as (theta, lambda) (hfg_nb.c) */
+                    hfg_nb_init_component(p->mean[s][c], &p->mean[s][c], &p->var[s][c]);
             }
         }
         if (cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN) {
@@ -76,7 +78,9 @@ int hfg_mstep(const hfg_config *cfg, hfg_region_params *params, const hfg_region
     if (!cfg || !params || !stats || !converged) return HFG_ERR_INVALID;
     int all_settled = 1;
     for (int r = 0; r < cfg->n_regions; r++)
-        all_settled &= hfg_mstep_region(cfg->model_type, cfg->n_comps, &params[r], &stats[r], convergence_tol);
+        all_settled &= cfg->model_type == HFG_MODEL_NEGATIVE_BINOMIAL
+                           ? hfg_nb_mstep_region(cfg->n_comps, &params[r], &stats[r], convergence_tol)
+                           : hfg_mstep_region(cfg->model_type, cfg->n_comps, &params[r], &stats[r], convergence_tol);
     *converged = all_settled;
     return HFG_OK;
 }
@@ -95,6 +99,7 @@ int hfg_params_feasible(const hfg_config *cfg, const hfg_region_params *params) 
                 ok &= 0 < p->trunc_point;
             } else {
                 for (int c = 0; c < cfg->n_comps[s]; c++) {
+                    if (cfg->model_type == HFG_MODEL_NEGATIVE_BINOMIAL) ok &= p->mean[s][c] < 1; /* theta, hmm_utils.c:366-375 */
                     ok &= 0 < p->mean[s][c];
                     ok &= 0 < p->var[s][c];
                     ok &= (0 <= p->weight[s][c]) && (p->weight[s][c] <= 1);

@@ -116,6 +116,10 @@ typedef struct hfg_classes {
 
 void hfg_classes_build(const hfg_config *cfg, const double *alpha, hfg_classes *out);
 
+/* negative-binomial model, host side (hfg_nb.c) */
+void hfg_nb_init_component(double mean, double *theta, double *lambda);
+int hfg_nb_mstep_region(const int32_t *n_comps, hfg_region_params *p, const hfg_region_stats *st, double tol);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,8 +33,9 @@ extern "C" {
 
 enum hfg_state { HFG_STATE_ERR = 0, HFG_STATE_DUP = 1, HFG_STATE_HAP = 2, HFG_STATE_COL = 3 };
 
-/* submodules/hmm_utils/hmm_utils.h:43-48 (negative_binomial is out of scope) */
-enum hfg_model_type { HFG_MODEL_TRUNC_EXP_GAUSSIAN = 0, HFG_MODEL_GAUSSIAN = 1 };
+/* submodules/hmm_utils/hmm_utils.h:43-48.  HFG_MODEL_NEGATIVE_BINOMIAL: only the host functions know it so far
+ * (hfg_model_init, hfg_mstep, hfg_params_feasible, hfg_squarem_*, hfg_nb_*); hfg_create rejects it -- no device path yet. */
+enum hfg_model_type { HFG_MODEL_TRUNC_EXP_GAUSSIAN = 0, HFG_MODEL_GAUSSIAN = 1, HFG_MODEL_NEGATIVE_BINOMIAL = 2 };
 
 enum hfg_status {
     HFG_OK = 0,
@@ -76,7 +77,9 @@ typedef struct hfg_chunk_desc {
 } hfg_chunk_desc;
 
 /* Parameters of one region (EmissionDistSeries + Transition of that region; hmm.h:14-25).
- * Row index of mean/var/weight is the state; row HFG_STATE_ERR is used only by HFG_MODEL_GAUSSIAN.
+ * Row index of mean/var/weight is the state; row HFG_STATE_ERR is used only by HFG_MODEL_GAUSSIAN and
+ * HFG_MODEL_NEGATIVE_BINOMIAL.  For the negative binomial, mean[s][c] holds theta and var[s][c] lambda of the
+ * (theta, lambda) parametrisation (NegativeBinomial, hmm_utils.h), and hfg_region_stats.mean_x / var_x their estimators.
  * trans is the 5x5 matrix with row 4 = start and column 4 = end (hmm_utils.c:2109-2128). */
 typedef struct hfg_region_params {
     double lambda;      /* TruncExponential.lambda     (hmm_utils.h:393-397) */
@@ -228,6 +231,22 @@ int hfg_squarem_iteration(hfg_ctx *ctx, const double *alpha, hfg_region_params *
  * the accepted step; both need max_iterations + 1 slots; the last loglik is the final inference pass. */
 int hfg_run_em_accelerated(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,
                            double convergence_tol, double *logliks, double *alpha_rates, int *n_outer, int8_t *labels);
+
+/* ---- negative-binomial model: host side (hmm_utils.c:320-640).  No device path yet -- hfg_create rejects the model ---- */
+#define HFG_NB_TABLE_X 251 /* coverage values 0..MAX_COVERAGE_VALUE (hmm_utils.h:15) */
+#define HFG_NB_BINS 250    /* bins of the per-state count histogram; x = 250 falls into bin 249 (count_data.c:56-64) */
+/* pmf of every (region, state, x), summed over the weighted components and floored at 1e-40 per component
+ * (NegativeBinomial_getProb / _getComponentProbs, hmm_utils.c:479-515): table[(r * 4 + s) * HFG_NB_TABLE_X + x].
+ * HFG_ERR_NAN where the reference would exit ("prob is NAN"). */
+int hfg_nb_emission_table(const hfg_config *cfg, const hfg_region_params *params, double *table);
+/* The theta / lambda / weight estimator sums (stats[r].mean_x / var_x / weight_x, OVERWRITTEN; the other fields are left
+ * alone) from histogram[(r * 4 + s) * HFG_NB_BINS + x] = pair mass of state s at coverage x in region r, i.e. what
+ * EmissionDistSeries_updateAllEstimatorsUsingCountData (hmm_utils.c:1662-1672) makes of one chunk's CountData through
+ * NegativeBinomial_updateEstimator (:536-563) with the digamma table of :392-406. */
+int hfg_nb_stats_from_histogram(const hfg_config *cfg, const hfg_region_params *params, const double *histogram,
+                                hfg_region_stats *stats);
+/* digamma in long double (the routine behind the table above; submodules/digamma/digamma.c:36-116 restated) */
+long double hfg_digammal(long double x);
 
 /* A destroyed context leaves its device arena (one per process) for the next context on the same device, so that a
  * process running job after job does not pay cudaMalloc per job; this returns it to the driver. */

@@ -64,7 +64,7 @@ static int is_nb(const hfg_config *cfg) { return cfg->model_type == ORC_MODEL_NE
 
 /* ---- negative-binomial model (MODEL_NEGATIVE_BINOMIAL; hmm_utils.c:320-640) ------------------------------------- */
 
-#include "digamma_coef.h" /* generated: oracle/tools/gen_digamma_coef.py */
+#include "digamma_coef.h" /* generated: tools/gen_digamma_coef.py */
 
 /* digamma in long double, restating the routine the reference vendors under submodules/digamma (digamma.c:36-116,
  * R. J. Mathar 2005): reflection below 0, psi(x) = psi(1+x) - 1/x below 1, the duplication formula above 3, exact values at
@@ -350,6 +350,11 @@ static int run_chunk(const hfg_config *cfg, const hfg_chunk_desc *ch, const uint
     return HFG_OK;
 }
 
+/* Test hook: when set, orc_estep adds every chunk's negative-binomial count histogram ([R][4][ORC_MAX_COV], zeroed by the
+ * caller) into it, in list order -- the input the product's hfg_nb_stats_from_histogram is checked with. */
+static double *g_nb_histogram_out = NULL;
+void orc_nb_histogram_out(double *out) { g_nb_histogram_out = out; }
+
 /* EM_runOneIterationForList / EM_runForwardForList, hmm.c:739-816: chunks in list order, per-chunk private
  * accumulators merged in list order (EM_updateModelEstimators, hmm.c:548-560).  Optional outputs may be NULL. */
 int orc_estep(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
@@ -388,6 +393,8 @@ int orc_estep(const hfg_config *cfg, int n_chunks, const hfg_chunk_desc *chunks,
                            labels ? labels + o : NULL, posteriors ? posteriors + o * NS : NULL, f, b, sc,
                            forward_only, nb_counts, nb_dig);
         if (status != HFG_OK) break;
+        if (nb_counts && g_nb_histogram_out)
+            for (size_t k = 0; k < n_counts; k++) g_nb_histogram_out[k] += nb_counts[k];
         total += ll;
         if (chunk_logliks) chunk_logliks[c] = ll;
         if (fwd) memcpy(fwd + o * NS, f, sizeof(double) * NS * (size_t) ch->n_windows);

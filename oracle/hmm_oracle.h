@@ -16,6 +16,7 @@ extern "C" {
  * hmm_utils.h); hfg_region_stats.mean_* hold the theta estimator, .var_* the lambda estimator, .weight_* the weights'. */
 #define ORC_MODEL_NEGATIVE_BINOMIAL 2
 long double orc_digammal(long double x);
+void orc_nb_histogram_out(double *out); /* test hook, see hmm_oracle.c */
 
 double orc_beta(const hfg_config *cfg, const hfg_chunk_desc *ch, int i);
 

@@ -111,6 +111,19 @@ class _Checker:
         return dict(rc=rc, params=params, logliks=logliks[:n.value + 1].copy(), alpha_rates=rates[:n.value].copy(),
                     labels=labels)
 
+    def nb_histogram(self, cfg, wl, alpha, params):
+        """(E-step result, [R, 4, 250] histogram of the pair mass over the coverage value summed over chunks): the
+        negative-binomial model's CountData (oracle only)."""
+        assert self.prefix == "orc"
+        hist = np.zeros((int(cfg["n_regions"][0]), 4, 250))
+        self.lib.orc_nb_histogram_out.restype = None
+        self.lib.orc_nb_histogram_out(ptr(hist))
+        try:
+            e = self.estep(cfg, wl, alpha, params)
+        finally:
+            self.lib.orc_nb_histogram_out(None)
+        return e, hist
+
     def digamma(self, x):
         """digamma of a double argument in long double, returned as (hi, lo) doubles with hi + lo exact -- the routine
         behind the negative-binomial model's table (orc_digammal / the reference's digammal)."""
