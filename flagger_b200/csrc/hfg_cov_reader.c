@@ -24,7 +24,6 @@
 #include "../../include/hfg_io.h"
 
 #define MAX_COVERAGE 250.0 /* chunk.c:8 */
-#define LINE_CAP (1 << 16)
 #define REGION_BINS 101    /* Int_getModeValue1DArray(.., 0, 100), chunk.c:388-390 */
 #define LABEL_BINS 12      /* Int_getModeValue1DArray(.., -1, 10), chunk.c:376-385 */
 
@@ -164,9 +163,98 @@ static const char *nth_field(const char *line, char sep, int n) {
     return p;
 }
 
+/* Number tokens of a data line.  bam2cov writes plain decimal integers; those are converted by hand (a run of at most 15
+ * digits is exact in a double and equals what atof / atol / atoi return), anything else goes through the libc routine the
+ * reference uses, so the values are the reference's for every input. */
+static inline long tok_long(const char *p) {
+    const char *q = p;
+    long v = 0;
+    while ((unsigned) (*q - '0') <= 9u && q - p < 18) v = v * 10 + (*q++ - '0');
+    if (q == p || q - p >= 18) return atol(p); /* sign, blanks, overlong: libc */
+    return v;
+}
+
+static inline int tok_int(const char *p) {
+    const char *q = p;
+    int neg = 0;
+    if (*q == '-') {
+        neg = 1;
+        q++;
+    }
+    const char *d0 = q;
+    int v = 0;
+    while ((unsigned) (*q - '0') <= 9u && q - d0 < 9) v = v * 10 + (*q++ - '0');
+    if (q == d0 || q - d0 >= 9) return atoi(p);
+    return neg ? -v : v;
+}
+
+static inline double tok_double(const char *p) {
+    const char *q = p;
+    long v = 0;
+    while ((unsigned) (*q - '0') <= 9u && q - p < 15) v = v * 10 + (*q++ - '0');
+    /* a pure digit run that ends the token: exact.  A '.', exponent, sign, blank, "nan", more digits: strtod as atof */
+    if (q == p || *q != '\0') return atof(p);
+    return (double) v;
+}
+
 static int fail_io(char *err, size_t errlen, const char *fmt, const char *a, long b) {
     snprintf(err, errlen, fmt, a, b);
     return HFG_ERR_INVALID;
+}
+
+/* Line source: the file is read (and inflated) in large blocks and lines are handed out in place, NUL-terminated, without
+ * a copy.  zlib's gzgets costs little, but the per-line strlen / strchr / strtod around it were two thirds of the parse
+ * time (profiles/cov_reader_timing.txt). */
+typedef struct LineSrc {
+    gzFile fp;
+    char *buf;
+    size_t cap, len, pos;
+    int eof;
+} LineSrc;
+
+#define SRC_BLOCK ((size_t) 4 << 20)
+
+/* next line -> *line (NUL-terminated in place, CR / LF stripped), *n = its length.  0 at the end of the file, -1 when out
+ * of memory. */
+static int src_next(LineSrc *s, char **line, size_t *n) {
+    for (;;) {
+        char *start = s->buf + s->pos;
+        char *nl = s->len > s->pos ? memchr(start, '\n', s->len - s->pos) : NULL;
+        if (nl || (s->eof && s->len > s->pos)) {
+            char *end = nl ? nl : s->buf + s->len; /* the last line may lack its newline; buf has room for the NUL */
+            s->pos = (size_t) (end - s->buf) + 1;
+            while (end > start && (end[-1] == '\r' || end[-1] == '\n')) end--;
+            *end = '\0';
+            *line = start;
+            *n = (size_t) (end - start);
+            return 1;
+        }
+        if (s->eof) return 0;
+        /* keep the unfinished line, refill behind it */
+        const size_t rest = s->len - s->pos;
+        if (s->pos > 0) memmove(s->buf, start, rest);
+        s->pos = 0;
+        s->len = rest;
+        if (s->cap - s->len < SRC_BLOCK + 1) {
+            char *nb = realloc(s->buf, s->cap * 2);
+            if (!nb) return -1;
+            s->buf = nb;
+            s->cap *= 2;
+        }
+        const int got = gzread(s->fp, s->buf + s->len, (unsigned) SRC_BLOCK);
+        if (got <= 0) s->eof = 1;
+        else s->len += (size_t) got;
+    }
+}
+
+/* digits at *pp -> value, *pp moved past them; 0 digits or more than 15 leave *pp where it was (caller falls back) */
+static inline long scan_digits(char **pp) {
+    char *q = *pp;
+    long v = 0;
+    while ((unsigned) (*q - '0') <= 9u) v = v * 10 + (*q++ - '0');
+    if (q == *pp || q - *pp > 15) return -1;
+    *pp = q;
+    return v;
 }
 
 int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_cov_data **out, char *err,
@@ -177,10 +265,11 @@ int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_co
     gzbuffer(fp, 1 << 20);
     hfg_cov_data *d = calloc(1, sizeof(*d));
     Growable g = {d, 0, 0};
-    char *line = malloc(LINE_CAP);
+    LineSrc src = {fp, malloc(2 * SRC_BLOCK + 2), 2 * SRC_BLOCK + 2, 0, 0, 0};
+    char *line = NULL;
     Window *win = malloc(sizeof(Window));
     int status = HFG_OK;
-    if (!d || !line || !win) {
+    if (!d || !src.buf || !win) {
         status = HFG_ERR_NOMEM;
         goto done;
     }
@@ -192,10 +281,10 @@ int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_co
     long ctg_len = 0, next_base = 0; /* next base of the contig that must come */
     int have_chunk = 0;
     long line_no = 0;
-    while (gzgets(fp, line, LINE_CAP)) {
+    size_t n = 0;
+    int more;
+    while ((more = src_next(&src, &line, &n)) > 0) {
         line_no++;
-        size_t n = strlen(line);
-        while (n && (line[n - 1] == '\n' || line[n - 1] == '\r')) line[--n] = '\0';
         if (n == 0) continue;
         if (line[0] == '#') { /* header keys, track_reader.c:220-457 */
             if (starts_with(line, "#annotation:len:")) {
@@ -247,33 +336,99 @@ int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_co
             continue;
         }
         /* data line: start end cov cov_high_mapq cov_high_clip annot[,annot..] region [truth [prediction]] (1-based) */
-        char *f[9];
-        int nf = 0;
-        for (char *p = line; p && nf < 9;) {
-            f[nf++] = p;
-            p = strchr(p, '\t');
-            if (p) *p++ = '\0';
+        long s, e;
+        double v_cov, v_mapq, v_clip;
+        uint64_t flag = 0; /* CoverageInfo_getAnnotationFlagFromArray, ptBlock.c:225-236 */
+        int region_v, truth_v = -1, pred_v = -1;
+        int fast = 0;
+        {
+            /* the canonical line -- unsigned decimal integers, tabs, comma-separated annotation indices, optional labels
+             * that may be -1 -- is scanned in one pass; anything else takes the general route below */
+            char *p = line;
+            long v[5];
+            int k = 0;
+            for (; k < 5; k++) {
+                if ((v[k] = scan_digits(&p)) < 0 || *p != '\t') break;
+                p++;
+            }
+            if (k == 5) {
+                for (;;) {
+                    const long a = scan_digits(&p);
+                    if (a < 0) break;
+                    if (a > 0 && a <= 64) flag |= 1ULL << (a - 1);
+                    else if (a > 64) { p = NULL; break; }
+                    if (*p != ',') break;
+                    p++;
+                }
+                long rv = -1;
+                if (p && *p == '\t' && (p++, (rv = scan_digits(&p)) >= 0) && rv < 1000000) {
+                    int ok = 1, nlab = 0;
+                    long lab[2] = {-1, -1};
+                    while (ok && *p == '\t' && nlab < 2) {
+                        p++;
+                        int neg = 0;
+                        if (*p == '-') {
+                            neg = 1;
+                            p++;
+                        }
+                        const long t = scan_digits(&p);
+                        if (t < 0 || t > 1000000) ok = 0;
+                        else lab[nlab++] = neg ? -t : t;
+                    }
+                    /* a third tab keeps the general route's reading of the ninth field ("rest of the line") */
+                    if (ok && *p == '\0') {
+                        fast = 1;
+                        s = v[0] - 1;
+                        e = v[1] - 1;
+                        v_cov = (double) v[2];
+                        v_mapq = (double) v[3];
+                        v_clip = (double) v[4];
+                        region_v = (int) rv;
+                        if (nlab > 0) truth_v = (int) lab[0];
+                        if (nlab > 1) pred_v = (int) lab[1];
+                    }
+                }
+            }
         }
-        if (nf < 7 || ctg[0] == '\0') {
+        if (!fast) {
+            char *f[9];
+            int nf = 0;
+            flag = 0;
+            for (char *p = line; p && nf < 9;) {
+                f[nf++] = p;
+                p = strchr(p, '\t');
+                if (p) *p++ = '\0';
+            }
+            if (nf < 7) {
+                status = fail_io(err, errlen, "malformed data line%s at line %ld", "", line_no);
+                goto done;
+            }
+            s = tok_long(f[0]) - 1;
+            e = tok_long(f[1]) - 1;
+            v_cov = tok_double(f[2]);
+            v_mapq = tok_double(f[3]);
+            v_clip = tok_double(f[4]);
+            for (char *p = f[5]; p && *p;) {
+                const int a = tok_int(p);
+                if (a > 0) flag |= 1ULL << (a - 1);
+                p = strchr(p, ',');
+                if (p) p++;
+            }
+            region_v = tok_int(f[6]);
+            truth_v = nf >= 8 ? tok_int(f[7]) : -1;
+            pred_v = nf >= 9 ? tok_int(f[8]) : -1;
+        }
+        if (ctg[0] == '\0') {
             status = fail_io(err, errlen, "malformed data line%s at line %ld", "", line_no);
             goto done;
         }
-        long s = atol(f[0]) - 1, e = atol(f[1]) - 1;
         if (s != next_base || e < s || e >= ctg_len) {
             status = fail_io(err, errlen, "%s: blocks must tile the contig in order (line %ld)", ctg, line_no);
             goto done;
         }
-        const double v_cov = atof(f[2]), v_mapq = atof(f[3]), v_clip = atof(f[4]);
-        uint64_t flag = 0; /* CoverageInfo_getAnnotationFlagFromArray, ptBlock.c:225-236 */
-        for (char *p = f[5]; p && *p;) {
-            const int a = atoi(p);
-            if (a > 0) flag |= 1ULL << (a - 1);
-            p = strchr(p, ',');
-            if (p) p++;
-        }
-        const int rbin = bin_of(atoi(f[6]), 0, REGION_BINS);
-        const int tbin = bin_of(nf >= 8 ? atoi(f[7]) : -1, -1, LABEL_BINS);
-        const int pbin = bin_of(nf >= 9 ? atoi(f[8]) : -1, -1, LABEL_BINS);
+        const int rbin = bin_of(region_v, 0, REGION_BINS);
+        const int tbin = bin_of(truth_v, -1, LABEL_BINS);
+        const int pbin = bin_of(pred_v, -1, LABEL_BINS);
         long pos = s;
         while (pos <= e) {
             if (!have_chunk || pos > d->chunks[d->n_chunks - 1].e) {
@@ -320,6 +475,10 @@ int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_co
         }
         next_base = e + 1;
     }
+    if (more < 0) {
+        status = HFG_ERR_NOMEM;
+        goto done;
+    }
     if (have_chunk && next_base != ctg_len) {
         status = fail_io(err, errlen, "%s: file ended before the contig's declared length%.0ld", ctg, 0);
         goto done;
@@ -330,7 +489,7 @@ int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_co
     }
 done:
     gzclose(fp);
-    free(line);
+    free(src.buf);
     free(win);
     if (status != HFG_OK) {
         if (status == HFG_ERR_NOMEM) snprintf(err, errlen, "out of memory reading %s", path);
