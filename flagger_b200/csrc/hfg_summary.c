@@ -13,9 +13,12 @@
  * thread pool; here the labels are the flat int8 array the E-step returns and the window coordinates come from the chunk
  * descriptors.
  */
+#include <pthread.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "../../include/hfg_io.h"
 
@@ -116,6 +119,92 @@ static void intlist_push(IntList *l, int x) {
     l->v[l->n++] = x;
 }
 
+/* Window coordinates and contig runs, built once per call; the scans below then need no chunk look-up, no strcmp. */
+typedef struct WinIndex {
+    int64_t n;
+    int32_t *start, *end, *ctg; /* ctg: run id of the contig name, +1 whenever a chunk's name differs from the previous one's */
+} WinIndex;
+
+static void winindex_free(WinIndex *w) {
+    free(w->start);
+    free(w->end);
+    free(w->ctg);
+    memset(w, 0, sizeof(*w));
+}
+
+static int winindex_build(const hfg_cov_data *d, WinIndex *w) {
+    memset(w, 0, sizeof(*w));
+    int64_t total = 0;
+    for (int c = 0; c < d->n_chunks; c++) total += d->chunks[c].n_windows;
+    if (total >= INT32_MAX) return 0;
+    w->n = total;
+    const size_t cap = (size_t) (total > 0 ? total : 1);
+    w->start = malloc(sizeof(int32_t) * cap);
+    w->end = malloc(sizeof(int32_t) * cap);
+    w->ctg = malloc(sizeof(int32_t) * cap);
+    if (!w->start || !w->end || !w->ctg) {
+        winindex_free(w);
+        return 0;
+    }
+    int64_t g = 0;
+    int32_t run = 0;
+    for (int c = 0; c < d->n_chunks; c++) {
+        const hfg_chunk_desc *ch = &d->chunks[c];
+        if (c > 0 && strcmp(d->contig_names[c - 1], d->contig_names[c]) != 0) run++;
+        for (int i = 0; i < ch->n_windows; i++, g++) {
+            const int end = ch->s + (i + 1) * ch->window_len - 1;
+            w->start[g] = ch->s + i * ch->window_len;
+            w->end[g] = end > ch->e ? ch->e : end;
+            w->ctg[g] = run;
+        }
+    }
+    return 1;
+}
+
+/* The windows the scan of one category has to look at: those inside the category and, to close its last block, the window
+ * right after each run of them.  Everything else only hands state from window to window that nothing reads (a block can
+ * neither grow nor end outside the category), so a sparse category -- a bias annotation, a region -- costs its own size,
+ * not the genome's.  g: window numbers in scan order; in: 1 inside the category. */
+typedef struct Visit {
+    int64_t n;
+    int32_t *g;
+    uint8_t *in;
+} Visit;
+
+static void visit_free(Visit *v) {
+    free(v->g);
+    free(v->in);
+    memset(v, 0, sizeof(*v));
+}
+
+static int visit_build(const hfg_cov_data *d, const WinIndex *w, int cat_type, int index, Visit *v) {
+    memset(v, 0, sizeof(*v));
+    int64_t count = 0;
+    int prev_in = 0;
+    for (int64_t g = 0; g < w->n; g++) {
+        const int cur = in_category(d, g, cat_type, index);
+        count += cur || prev_in;
+        prev_in = cur;
+    }
+    v->g = malloc(sizeof(int32_t) * (size_t) (count > 0 ? count : 1));
+    v->in = malloc((size_t) (count > 0 ? count : 1));
+    if (!v->g || !v->in) {
+        visit_free(v);
+        return 0;
+    }
+    prev_in = 0;
+    for (int64_t g = 0; g < w->n; g++) {
+        const int cur = in_category(d, g, cat_type, index);
+        if (cur || prev_in) {
+            v->g[v->n] = (int32_t) g;
+            v->in[v->n] = (uint8_t) cur;
+            v->n++;
+        }
+        prev_in = cur;
+    }
+    return 1;
+}
+
 /* adds one finished reference-label block to the tables of the size bins it falls in (summary_table.c:1040-1102 and
  * :1150-1214).  tables / aux: [n_bins] consecutive tables of this category index. */
 static void flush_block(double *tables, double *row, int n, int metric, double overlap_threshold, int pre_ref, int len,
@@ -150,62 +239,82 @@ static void flush_block(double *tables, double *row, int n, int metric, double o
 }
 
 /* the confusion tables [n_bins][n][n] of one category index, filled by the block scan (SummaryTableList_updateByUpdaterArgs,
- * summary_table.c:930-1224).  aux: the base_level truth-vs-truth table of the same category index (auN only). */
-static void scan_category(const hfg_cov_data *d, const int8_t *ref, const int8_t *query, int n, int cat_type, int index,
-                          int metric, double overlap_threshold, const double *aux, const SizeBins *bins, double *table) {
+ * summary_table.c:930-1224).  aux: the base_level truth-vs-truth table of the same category index (auN only).  The scan is
+ * the reference's window-by-window state machine, run over the windows of `visit` only: a visited window whose predecessor
+ * was skipped starts a block exactly as the first window of the genome does.  Returns 0 when out of memory. */
+static int scan_category(const WinIndex *w, const Visit *visit, const int8_t *ref, const int8_t *query, int n, int metric,
+                         double overlap_threshold, const double *aux, const SizeBins *bins, double *table) {
     double *row = calloc((size_t) n, sizeof(double));
     IntList *qlen = calloc((size_t) n, sizeof(IntList));
+    if (!row || !qlen) {
+        free(row);
+        free(qlen);
+        return 0;
+    }
     int pre_ref = -1, pre_query = -1, ref_start = -1, query_start = -1, pre_end = -1;
     int have_prev = 0, prev_in = 0;
-    const char *pre_ctg = NULL;
-    for (int c = 0; c < d->n_chunks; c++) {
-        const hfg_chunk_desc *ch = &d->chunks[c];
-        const char *ctg = d->contig_names[c];
-        for (int i = 0; i < ch->n_windows; i++) {
-            const int64_t g = ch->offset + i;
-            const int start = ch->s + i * ch->window_len;
-            int end = ch->s + (i + 1) * ch->window_len - 1;
-            if (end > ch->e) end = ch->e;
-            int r = ref[g], q = query[g];
-            if (r == -1) r = n - 1; /* the last row / column is "Unk" */
-            if (q == -1) q = n - 1;
-            const int ctg_changed = have_prev && strcmp(pre_ctg, ctg) != 0;
-            const int ref_changed = r != pre_ref, query_changed = q != pre_query;
-            const int cur_in = in_category(d, g, cat_type, index);
-            const int continued = cur_in && prev_in, started = cur_in && !prev_in, ended = !cur_in && prev_in;
-            /* a block of one reference label inside the category has ended: add it to the table */
-            if (pre_ref != -1 && ((continued && ref_changed) || (prev_in && ctg_changed) || ended))
-                flush_block(table, row, n, metric, overlap_threshold, pre_ref, pre_end - ref_start + 1, qlen, pre_query, pre_end,
-                            query_start, aux, bins);
-            /* the query label changed inside a reference block */
-            if (cur_in && metric == METRIC_AUN && pre_query != -1 && query_changed && (continued && !ref_changed) && !ctg_changed)
-                intlist_push(&qlen[pre_query], pre_end - query_start + 1);
-            if ((!cur_in && ctg_changed) || ended) {
-                ref_start = -1;
-                query_start = -1;
-                memset(row, 0, sizeof(double) * (size_t) n);
+    int32_t pre_ctg = -1, pre_g = -2;
+    for (int64_t k = 0; k < visit->n; k++) {
+        const int32_t g = visit->g[k];
+        const int cur_in = visit->in[k];
+        if (g != pre_g + 1) { /* the windows in between were outside the category */
+            have_prev = 0;
+            prev_in = 0;
+        }
+        const int start = w->start[g], end = w->end[g];
+        const int32_t ctg = w->ctg[g];
+        int r = ref[g], q = query[g];
+        if (r == -1) r = n - 1; /* the last row / column is "Unk" */
+        if (q == -1) q = n - 1;
+        const int ctg_changed = have_prev && pre_ctg != ctg;
+        const int ref_changed = r != pre_ref, query_changed = q != pre_query;
+        const int continued = cur_in && prev_in, started = cur_in && !prev_in, ended = !cur_in && prev_in;
+        /* a block of one reference label inside the category has ended: add it to the table */
+        if (pre_ref != -1 && ((continued && ref_changed) || (prev_in && ctg_changed) || ended))
+            flush_block(table, row, n, metric, overlap_threshold, pre_ref, pre_end - ref_start + 1, qlen, pre_query, pre_end,
+                        query_start, aux, bins);
+        /* the query label changed inside a reference block */
+        if (cur_in && metric == METRIC_AUN && pre_query != -1 && query_changed && (continued && !ref_changed) && !ctg_changed)
+            intlist_push(&qlen[pre_query], pre_end - query_start + 1);
+        if ((!cur_in && ctg_changed) || ended) {
+            ref_start = -1;
+            query_start = -1;
+            memset(row, 0, sizeof(double) * (size_t) n);
+        }
+        if ((continued && ref_changed) || (cur_in && ctg_changed) || started) {
+            ref_start = start;
+            memset(row, 0, sizeof(double) * (size_t) n);
+            for (int j = 0; j < n; j++) qlen[j].n = 0;
+        }
+        if ((continued && ref_changed) || (continued && query_changed) || (cur_in && ctg_changed) || started) query_start = start;
+        if (cur_in && metric != METRIC_AUN) row[q] += end - start + 1;
+        have_prev = 1;
+        prev_in = cur_in;
+        pre_ref = r;
+        pre_query = q;
+        pre_ctg = ctg;
+        pre_end = end;
+        pre_g = g;
+        /* the windows that follow with nothing changed -- next in scan order, inside the category, same contig, same pair of
+         * labels -- take none of the branches above: they only lengthen the current block */
+        if (cur_in) {
+            const int8_t r8 = ref[g], q8 = query[g];
+            while (k + 1 < visit->n && visit->g[k + 1] == pre_g + 1 && visit->in[k + 1] && ref[pre_g + 1] == r8 &&
+                   query[pre_g + 1] == q8 && w->ctg[pre_g + 1] == ctg) {
+                k++;
+                pre_g++;
+                if (metric != METRIC_AUN) row[q] += w->end[pre_g] - w->start[pre_g] + 1;
             }
-            if ((continued && ref_changed) || (cur_in && ctg_changed) || started) {
-                ref_start = start;
-                memset(row, 0, sizeof(double) * (size_t) n);
-                for (int k = 0; k < n; k++) qlen[k].n = 0;
-            }
-            if ((continued && ref_changed) || (continued && query_changed) || (cur_in && ctg_changed) || started) query_start = start;
-            if (cur_in && metric != METRIC_AUN) row[q] += end - start + 1;
-            have_prev = 1;
-            prev_in = cur_in;
-            pre_ref = r;
-            pre_query = q;
-            pre_ctg = ctg;
-            pre_end = end;
+            pre_end = w->end[pre_g];
         }
     }
     if (have_prev && prev_in && pre_ref != -1)
         flush_block(table, row, n, metric, overlap_threshold, pre_ref, pre_end - ref_start + 1, qlen, pre_query, pre_end, query_start,
                     aux, bins);
-    for (int k = 0; k < n; k++) free(qlen[k].v);
+    for (int j = 0; j < n; j++) free(qlen[j].v);
     free(qlen);
     free(row);
+    return 1;
 }
 
 static void write_values(FILE *f, const double *v, int n) {
@@ -324,6 +433,51 @@ static void write_aun_statistics(FILE *f, const double *num, const double *den, 
     }
 }
 
+/* the scans of one category type, one category per job */
+typedef struct CatJobs {
+    const hfg_cov_data *d;
+    const WinIndex *wi;
+    const int8_t *prediction, *truth;
+    const SizeBins *bins;
+    int n, n_cat[2]; /* categories per type: regions, annotations */
+    double overlap_threshold;
+    double *tab[2][3][4]; /* [category type][metric][comparison] -> [n_cat][n_bins] tables, NULL where not applicable */
+    int next, oom;
+    pthread_mutex_t mu;
+} CatJobs;
+
+static void *cat_worker(void *arg) {
+    CatJobs *j = arg;
+    for (;;) {
+        const int n_jobs = j->n_cat[0] + j->n_cat[1];
+        pthread_mutex_lock(&j->mu);
+        const int job = j->oom ? n_jobs : j->next++;
+        pthread_mutex_unlock(&j->mu);
+        if (job >= n_jobs) return NULL;
+        /* annotations first: "whole_genome" covers every window and is the longest job */
+        const int cat_type = job < j->n_cat[CAT_ANNOTATION] ? CAT_ANNOTATION : CAT_REGION;
+        const int ci = cat_type == CAT_ANNOTATION ? job : job - j->n_cat[CAT_ANNOTATION];
+        double *(*tab)[4] = j->tab[cat_type];
+        Visit visit;
+        int ok = visit_build(j->d, j->wi, cat_type, ci, &visit);
+        const size_t off = (size_t) ci * j->bins->n * TBL_STRIDE(j->n);
+        for (int metric = 0; metric < 3 && ok; metric++) /* base_level before truth_based_auN, which divides by it */
+            for (int cmp = 0; cmp < 4 && ok; cmp++) {
+                if (!tab[metric][cmp]) continue;
+                const int8_t *ref = (cmp == CMP_TRUTH_VS_PREDICTION || cmp == CMP_TRUTH) ? j->truth : j->prediction;
+                const int8_t *query = (cmp == CMP_TRUTH_VS_PREDICTION || cmp == CMP_PREDICTION) ? j->prediction : j->truth;
+                ok = scan_category(j->wi, &visit, ref, query, j->n, metric, j->overlap_threshold,
+                                   metric == METRIC_AUN ? tab[METRIC_BASE][CMP_TRUTH] + off : NULL, j->bins, tab[metric][cmp] + off);
+            }
+        visit_free(&visit);
+        if (!ok) {
+            pthread_mutex_lock(&j->mu);
+            j->oom = 1;
+            pthread_mutex_unlock(&j->mu);
+        }
+    }
+}
+
 int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t *prediction, const int8_t *truth,
                           const char *const *label_names, int n_labels, double overlap_ratio_threshold,
                           const char *bin_array_file, char *err, size_t errlen) {
@@ -373,26 +527,38 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
         fprintf(f_aun, "#Category_Type\tCategory_Name\tSize_Bin_Name\tLabel\tauN_Ratio\n");
     }
     double *vals = malloc(sizeof(double) * (size_t) n);
-    for (int cat_type = 0; cat_type < 2; cat_type++) {
-        const int n_cat = cat_type == CAT_REGION ? d->n_regions : d->n_annotations;
-        const char *const *cat_names = cat_type == CAT_ANNOTATION ? (const char *const *) d->annotation_names : NULL;
-        double *tab[3][4];
-        memset(tab, 0, sizeof(tab));
-        /* all tables of this category type first (the auN tables need the base_level truth table) */
-        for (int metric = 0; metric < 3; metric++) {
+    WinIndex wi;
+    memset(&wi, 0, sizeof(wi));
+    int oom = !vals || !winindex_build(d, &wi);
+    /* all tables first (the auN tables need the base_level truth table): one job per category, each building the list of
+     * windows to visit once for its ten scans, on a few threads (the reference uses its thread pool here) */
+    CatJobs jobs = {d, &wi, prediction, truth, &bins, n, {d->n_regions, d->n_annotations}, overlap_ratio_threshold, {{{NULL}}}, 0, 0,
+                    PTHREAD_MUTEX_INITIALIZER};
+    for (int cat_type = 0; cat_type < 2; cat_type++)
+        for (int metric = 0; metric < 3; metric++)
             for (int cmp = 0; cmp < 4; cmp++) {
                 const int need_truth = cmp != CMP_PREDICTION, need_pred = cmp != CMP_TRUTH;
                 if ((need_truth && !truth) || (need_pred && !prediction)) continue;
                 if (metric == METRIC_AUN && (cmp == CMP_PREDICTION || cmp == CMP_PREDICTION_VS_TRUTH)) continue;
-                const int8_t *ref = (cmp == CMP_TRUTH_VS_PREDICTION || cmp == CMP_TRUTH) ? truth : prediction;
-                const int8_t *query = (cmp == CMP_TRUTH_VS_PREDICTION || cmp == CMP_PREDICTION) ? prediction : truth;
-                tab[metric][cmp] = calloc((size_t) n_cat * bins.n * TBL_STRIDE(n), sizeof(double));
-                for (int ci = 0; ci < n_cat; ci++)
-                    scan_category(d, ref, query, n, cat_type, ci, metric, overlap_ratio_threshold,
-                                  metric == METRIC_AUN ? tab[METRIC_BASE][CMP_TRUTH] + (size_t) ci * bins.n * TBL_STRIDE(n) : NULL, &bins,
-                                  tab[metric][cmp] + (size_t) ci * bins.n * TBL_STRIDE(n));
+                jobs.tab[cat_type][metric][cmp] = calloc((size_t) jobs.n_cat[cat_type] * bins.n * TBL_STRIDE(n), sizeof(double));
+                if (!jobs.tab[cat_type][metric][cmp]) oom = 1;
             }
-        }
+    if (!oom) {
+        int n_threads = (int) sysconf(_SC_NPROCESSORS_ONLN);
+        if (n_threads > 8) n_threads = 8;
+        if (n_threads > jobs.n_cat[0] + jobs.n_cat[1]) n_threads = jobs.n_cat[0] + jobs.n_cat[1];
+        pthread_t th[8];
+        int started = 0;
+        for (int t = 1; t < n_threads; t++)
+            if (pthread_create(&th[started], NULL, cat_worker, &jobs) == 0) started++;
+        cat_worker(&jobs); /* this thread works too, and alone if no thread could be started */
+        for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+        oom = jobs.oom;
+    }
+    for (int cat_type = 0; cat_type < 2 && !oom; cat_type++) {
+        const int n_cat = jobs.n_cat[cat_type];
+        const char *const *cat_names = cat_type == CAT_ANNOTATION ? (const char *const *) d->annotation_names : NULL;
+        double *(*tab)[4] = jobs.tab[cat_type];
         for (int metric = 0; metric < 3; metric++) {
             for (int cmp = 0; cmp < 4; cmp++) {
                 const double *all = tab[metric][cmp];
@@ -439,14 +605,20 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
         if (f_aun)
             write_aun_statistics(f_aun, tab[METRIC_AUN][CMP_TRUTH_VS_PREDICTION], tab[METRIC_AUN][CMP_TRUTH], n_cat, n,
                                  CATEGORY_NAME[cat_type], cat_names, label_names, &bins);
-        for (int metric = 0; metric < 3; metric++)
-            for (int cmp = 0; cmp < 4; cmp++) free(tab[metric][cmp]);
     }
+    for (int cat_type = 0; cat_type < 2; cat_type++)
+        for (int metric = 0; metric < 3; metric++)
+            for (int cmp = 0; cmp < 4; cmp++) free(jobs.tab[cat_type][metric][cmp]);
     free(vals);
+    winindex_free(&wi);
     bins_free(&bins);
     fclose(f);
     if (f_stats) fclose(f_stats);
     if (f_aun) fclose(f_aun);
+    if (oom) {
+        snprintf(err, errlen, "hfg_write_summary_tsv: out of memory (or more than 2^31 windows)");
+        return HFG_ERR_NOMEM;
+    }
     return HFG_OK;
 }
 
@@ -505,17 +677,38 @@ int hfg_benchmark_scores(const hfg_cov_data *d, const int8_t *prediction, const 
     const int n = n_labels + 1;
     const size_t stride = (size_t) bins.n * TBL_STRIDE(n);
     /* tables of this annotation only: [metric 0..1][T-vs-P, P-vs-T], base_level truth-vs-truth, auN T-vs-P and truth */
-    double *tp[2], *pt_[2], *tt = calloc(stride, sizeof(double)), *aun_tp = calloc(stride, sizeof(double)),
-                            *aun_tt = calloc(stride, sizeof(double));
+    double *tp[2] = {NULL, NULL}, *pt_[2] = {NULL, NULL}, *tt = calloc(stride, sizeof(double)),
+           *aun_tp = calloc(stride, sizeof(double)), *aun_tt = calloc(stride, sizeof(double));
+    WinIndex wi;
+    Visit visit;
+    memset(&visit, 0, sizeof(visit));
+    int ok = tt && aun_tp && aun_tt && winindex_build(d, &wi);
+    if (!ok) memset(&wi, 0, sizeof(wi));
+    ok = ok && visit_build(d, &wi, CAT_ANNOTATION, ci, &visit);
     for (int metric = 0; metric < 2; metric++) {
         tp[metric] = calloc(stride, sizeof(double));
         pt_[metric] = calloc(stride, sizeof(double));
-        scan_category(d, truth, prediction, n, CAT_ANNOTATION, ci, metric, overlap_ratio_threshold, NULL, &bins, tp[metric]);
-        scan_category(d, prediction, truth, n, CAT_ANNOTATION, ci, metric, overlap_ratio_threshold, NULL, &bins, pt_[metric]);
+        ok = ok && tp[metric] && pt_[metric];
+        ok = ok && scan_category(&wi, &visit, truth, prediction, n, metric, overlap_ratio_threshold, NULL, &bins, tp[metric]);
+        ok = ok && scan_category(&wi, &visit, prediction, truth, n, metric, overlap_ratio_threshold, NULL, &bins, pt_[metric]);
     }
-    scan_category(d, truth, truth, n, CAT_ANNOTATION, ci, METRIC_BASE, overlap_ratio_threshold, NULL, &bins, tt);
-    scan_category(d, truth, prediction, n, CAT_ANNOTATION, ci, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tp);
-    scan_category(d, truth, truth, n, CAT_ANNOTATION, ci, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tt);
+    ok = ok && scan_category(&wi, &visit, truth, truth, n, METRIC_BASE, overlap_ratio_threshold, NULL, &bins, tt);
+    ok = ok && scan_category(&wi, &visit, truth, prediction, n, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tp);
+    ok = ok && scan_category(&wi, &visit, truth, truth, n, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tt);
+    visit_free(&visit);
+    winindex_free(&wi);
+    if (!ok) {
+        for (int metric = 0; metric < 2; metric++) {
+            free(tp[metric]);
+            free(pt_[metric]);
+        }
+        free(tt);
+        free(aun_tp);
+        free(aun_tt);
+        bins_free(&bins);
+        snprintf(err, errlen, "hfg_benchmark_scores: out of memory (or more than 2^31 windows)");
+        return HFG_ERR_NOMEM;
+    }
     const size_t off = (size_t) bi * TBL_STRIDE(n);
     scores[0] = harmonic_f1_no_hap(tp[METRIC_OVERLAP] + off, pt_[METRIC_OVERLAP] + off, n);
     scores[1] = harmonic_f1_no_hap(tp[METRIC_BASE] + off, pt_[METRIC_BASE] + off, n);
