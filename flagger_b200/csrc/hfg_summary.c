@@ -123,16 +123,21 @@ static void intlist_push(IntList *l, int x) {
 typedef struct WinIndex {
     int64_t n;
     int32_t *start, *end, *ctg; /* ctg: run id of the contig name, +1 whenever a chunk's name differs from the previous one's */
+    int64_t *cum;               /* cum[g] = bases in the windows before g (n + 1 entries) */
+    int32_t *run_end;           /* last window of the stretch around g in which neither label array nor the contig changes */
 } WinIndex;
 
 static void winindex_free(WinIndex *w) {
     free(w->start);
     free(w->end);
     free(w->ctg);
+    free(w->cum);
+    free(w->run_end);
     memset(w, 0, sizeof(*w));
 }
 
-static int winindex_build(const hfg_cov_data *d, WinIndex *w) {
+/* a, b: the label arrays the scans will compare (either may be NULL) */
+static int winindex_build(const hfg_cov_data *d, const int8_t *a, const int8_t *b, WinIndex *w) {
     memset(w, 0, sizeof(*w));
     int64_t total = 0;
     for (int c = 0; c < d->n_chunks; c++) total += d->chunks[c].n_windows;
@@ -142,7 +147,9 @@ static int winindex_build(const hfg_cov_data *d, WinIndex *w) {
     w->start = malloc(sizeof(int32_t) * cap);
     w->end = malloc(sizeof(int32_t) * cap);
     w->ctg = malloc(sizeof(int32_t) * cap);
-    if (!w->start || !w->end || !w->ctg) {
+    w->cum = malloc(sizeof(int64_t) * (cap + 1));
+    w->run_end = malloc(sizeof(int32_t) * cap);
+    if (!w->start || !w->end || !w->ctg || !w->cum || !w->run_end) {
         winindex_free(w);
         return 0;
     }
@@ -158,6 +165,12 @@ static int winindex_build(const hfg_cov_data *d, WinIndex *w) {
             w->ctg[g] = run;
         }
     }
+    w->cum[0] = 0;
+    for (g = 0; g < total; g++) w->cum[g + 1] = w->cum[g] + (w->end[g] - w->start[g] + 1);
+    for (g = total - 1; g >= 0; g--) {
+        const int same = g + 1 < total && w->ctg[g] == w->ctg[g + 1] && (!a || a[g] == a[g + 1]) && (!b || b[g] == b[g + 1]);
+        w->run_end[g] = same ? w->run_end[g + 1] : (int32_t) g;
+    }
     return 1;
 }
 
@@ -169,11 +182,13 @@ typedef struct Visit {
     int64_t n;
     int32_t *g;
     uint8_t *in;
+    int32_t *stretch_last; /* for an entry inside the category: the last window of its run of consecutive such entries */
 } Visit;
 
 static void visit_free(Visit *v) {
     free(v->g);
     free(v->in);
+    free(v->stretch_last);
     memset(v, 0, sizeof(*v));
 }
 
@@ -188,7 +203,8 @@ static int visit_build(const hfg_cov_data *d, const WinIndex *w, int cat_type, i
     }
     v->g = malloc(sizeof(int32_t) * (size_t) (count > 0 ? count : 1));
     v->in = malloc((size_t) (count > 0 ? count : 1));
-    if (!v->g || !v->in) {
+    v->stretch_last = malloc(sizeof(int32_t) * (size_t) (count > 0 ? count : 1));
+    if (!v->g || !v->in || !v->stretch_last) {
         visit_free(v);
         return 0;
     }
@@ -202,6 +218,8 @@ static int visit_build(const hfg_cov_data *d, const WinIndex *w, int cat_type, i
         }
         prev_in = cur;
     }
+    for (int64_t k = v->n - 1; k >= 0; k--)
+        v->stretch_last[k] = (v->in[k] && k + 1 < v->n && v->in[k + 1] && v->g[k + 1] == v->g[k] + 1) ? v->stretch_last[k + 1] : v->g[k];
     return 1;
 }
 
@@ -296,16 +314,17 @@ static int scan_category(const WinIndex *w, const Visit *visit, const int8_t *re
         pre_end = end;
         pre_g = g;
         /* the windows that follow with nothing changed -- next in scan order, inside the category, same contig, same pair of
-         * labels -- take none of the branches above: they only lengthen the current block */
+         * labels -- take none of the branches above: they only lengthen the current block.  Their end is known from the
+         * two precomputed run tables, their bases from the prefix sums (integers: one addition equals the many) */
         if (cur_in) {
-            const int8_t r8 = ref[g], q8 = query[g];
-            while (k + 1 < visit->n && visit->g[k + 1] == pre_g + 1 && visit->in[k + 1] && ref[pre_g + 1] == r8 &&
-                   query[pre_g + 1] == q8 && w->ctg[pre_g + 1] == ctg) {
-                k++;
-                pre_g++;
-                if (metric != METRIC_AUN) row[q] += w->end[pre_g] - w->start[pre_g] + 1;
+            int32_t last = w->run_end[g];
+            if (visit->stretch_last[k] < last) last = visit->stretch_last[k];
+            if (last > g) {
+                if (metric != METRIC_AUN) row[q] += (double) (w->cum[last + 1] - w->cum[g + 1]);
+                k += last - g;
+                pre_g = last;
+                pre_end = w->end[last];
             }
-            pre_end = w->end[pre_g];
         }
     }
     if (have_prev && prev_in && pre_ref != -1)
@@ -529,7 +548,7 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
     double *vals = malloc(sizeof(double) * (size_t) n);
     WinIndex wi;
     memset(&wi, 0, sizeof(wi));
-    int oom = !vals || !winindex_build(d, &wi);
+    int oom = !vals || !winindex_build(d, prediction, truth, &wi);
     /* all tables first (the auN tables need the base_level truth table): one job per category, each building the list of
      * windows to visit once for its ten scans, on a few threads (the reference uses its thread pool here) */
     CatJobs jobs = {d, &wi, prediction, truth, &bins, n, {d->n_regions, d->n_annotations}, overlap_ratio_threshold, {{{NULL}}}, 0, 0,
@@ -622,6 +641,39 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
     return HFG_OK;
 }
 
+/* a handful of independent scans, one thread each (the calling thread takes the first) */
+typedef struct ScanJob {
+    const WinIndex *w;
+    const Visit *visit;
+    const int8_t *ref, *query;
+    int n, metric;
+    double overlap_threshold;
+    const double *aux;
+    const SizeBins *bins;
+    double *table;
+    int ok;
+} ScanJob;
+
+static void *scan_job_run(void *arg) {
+    ScanJob *j = arg;
+    j->ok = scan_category(j->w, j->visit, j->ref, j->query, j->n, j->metric, j->overlap_threshold, j->aux, j->bins, j->table);
+    return NULL;
+}
+
+static int run_scans(ScanJob *jobs, int count) {
+    pthread_t th[8];
+    int threaded[8] = {0};
+    for (int i = 1; i < count && i < 8; i++) threaded[i] = pthread_create(&th[i], NULL, scan_job_run, &jobs[i]) == 0;
+    for (int i = 0; i < count; i++)
+        if (!threaded[i < 8 ? i : 0] || i == 0 || i >= 8) scan_job_run(&jobs[i]);
+    int ok = 1;
+    for (int i = 0; i < count; i++) {
+        if (i > 0 && i < 8 && threaded[i]) pthread_join(th[i], NULL);
+        ok &= jobs[i].ok;
+    }
+    return ok;
+}
+
 /* ---- the scores of the alpha-tuning driver ---------------------------------------------------------------------------- */
 
 /* F1-Score of the HARMONIC_MEAN_NO_HAP row (write_final_statistics above), rounded as printed; NaN for "NA" */
@@ -682,19 +734,26 @@ int hfg_benchmark_scores(const hfg_cov_data *d, const int8_t *prediction, const 
     WinIndex wi;
     Visit visit;
     memset(&visit, 0, sizeof(visit));
-    int ok = tt && aun_tp && aun_tt && winindex_build(d, &wi);
+    int ok = tt && aun_tp && aun_tt && winindex_build(d, prediction, truth, &wi);
     if (!ok) memset(&wi, 0, sizeof(wi));
     ok = ok && visit_build(d, &wi, CAT_ANNOTATION, ci, &visit);
     for (int metric = 0; metric < 2; metric++) {
         tp[metric] = calloc(stride, sizeof(double));
         pt_[metric] = calloc(stride, sizeof(double));
         ok = ok && tp[metric] && pt_[metric];
-        ok = ok && scan_category(&wi, &visit, truth, prediction, n, metric, overlap_ratio_threshold, NULL, &bins, tp[metric]);
-        ok = ok && scan_category(&wi, &visit, prediction, truth, n, metric, overlap_ratio_threshold, NULL, &bins, pt_[metric]);
     }
-    ok = ok && scan_category(&wi, &visit, truth, truth, n, METRIC_BASE, overlap_ratio_threshold, NULL, &bins, tt);
-    ok = ok && scan_category(&wi, &visit, truth, prediction, n, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tp);
-    ok = ok && scan_category(&wi, &visit, truth, truth, n, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tt);
+    if (ok) {
+        /* five independent scans side by side, then the two auN scans, which divide by the base_level truth table */
+        ScanJob jobs[7] = {
+            {&wi, &visit, truth, prediction, n, METRIC_OVERLAP, overlap_ratio_threshold, NULL, &bins, tp[METRIC_OVERLAP], 0},
+            {&wi, &visit, prediction, truth, n, METRIC_OVERLAP, overlap_ratio_threshold, NULL, &bins, pt_[METRIC_OVERLAP], 0},
+            {&wi, &visit, truth, prediction, n, METRIC_BASE, overlap_ratio_threshold, NULL, &bins, tp[METRIC_BASE], 0},
+            {&wi, &visit, prediction, truth, n, METRIC_BASE, overlap_ratio_threshold, NULL, &bins, pt_[METRIC_BASE], 0},
+            {&wi, &visit, truth, truth, n, METRIC_BASE, overlap_ratio_threshold, NULL, &bins, tt, 0},
+            {&wi, &visit, truth, prediction, n, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tp, 0},
+            {&wi, &visit, truth, truth, n, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tt, 0}};
+        ok = run_scans(jobs, 5) && run_scans(jobs + 5, 2);
+    }
     visit_free(&visit);
     winindex_free(&wi);
     if (!ok) {
