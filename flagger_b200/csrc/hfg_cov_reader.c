@@ -205,7 +205,7 @@ static int fail_io(char *err, size_t errlen, const char *fmt, const char *a, lon
 
 /* Line source: the file is read (and inflated) in large blocks and lines are handed out in place, NUL-terminated, without
  * a copy.  zlib's gzgets costs little, but the per-line strlen / strchr / strtod around it were two thirds of the parse
- * time (profiles/cov_reader_timing.txt). */
+ * time (profiles/host_timing_r1d.txt). */
 typedef struct LineSrc {
     gzFile fp;
     char *buf;
