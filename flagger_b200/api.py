@@ -57,7 +57,7 @@ EXPORTED_SYMBOLS = (
     "hfg_debug_layout_compare", "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_read_cov",
     "hfg_read_bin", "hfg_cov_free", "hfg_write_summary_tsv", "hfg_benchmark_scores", "hfg_params_feasible", "hfg_squarem_alpha_rate",
     "hfg_squarem_prime", "hfg_squarem_shrink", "hfg_squarem_iteration", "hfg_run_em_accelerated",
-    "hfg_release_cached_memory", "hfg_nb_emission_table", "hfg_nb_stats_from_histogram", "hfg_digammal",
+    "hfg_release_cached_memory", "hfg_nb_emission_table", "hfg_nb_stats_from_histogram", "hfg_digammal", "hfg_debug_gunzip",
 )
 
 

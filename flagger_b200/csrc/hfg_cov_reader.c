@@ -23,6 +23,7 @@
 #include <zlib.h>
 
 #include "../../include/hfg_io.h"
+#include "hfg_inflate.h"
 
 #define MAX_COVERAGE 250.0 /* chunk.c:8 */
 #define REGION_BINS 101    /* Int_getModeValue1DArray(.., 0, 100), chunk.c:388-390 */
@@ -217,10 +218,15 @@ typedef struct LineSrc {
     pthread_mutex_t mu;
     pthread_cond_t cv;
     char *slot[2];
-    int got[2];   /* bytes in the slot; <= 0: end of file / error */
+    long got[2];  /* bytes in the slot; 0: end of file; < 0: error */
     int full[2];
     int stop, threaded;
     unsigned long produced, consumed;
+    /* gzip input goes through the own decoder (hfg_inflate.c: about twice zlib's speed on the Huffman-only streams the
+     * reference writes); plain text, or HFG_ZLIB_INFLATE=1, through zlib's gzread */
+    hfg_inflate *inflate;
+    size_t block; /* most bytes one fill delivers */
+    int bad_gzip;
 } LineSrc;
 
 #define SRC_BLOCK ((size_t) 4 << 20)
@@ -234,7 +240,8 @@ static void *src_producer(void *arg) {
         const int stop = s->stop;
         pthread_mutex_unlock(&s->mu);
         if (stop) break;
-        const int got = gzread(s->fp, s->slot[k], (unsigned) SRC_BLOCK);
+        const long got = s->inflate ? hfg_inflate_next(s->inflate, (uint8_t *) s->slot[k])
+                                    : (long) gzread(s->fp, s->slot[k], (unsigned) SRC_BLOCK);
         pthread_mutex_lock(&s->mu);
         s->got[k] = got;
         s->full[k] = 1;
@@ -247,14 +254,17 @@ static void *src_producer(void *arg) {
 }
 
 /* 1 on success; the reader works without the thread (inline gzread) when it cannot be started */
-static int src_open(LineSrc *s, gzFile fp) {
+static int src_open(LineSrc *s, gzFile fp, const char *path) {
     memset(s, 0, sizeof(*s));
     s->fp = fp;
-    s->cap = 2 * SRC_BLOCK + 2;
+    s->block = SRC_BLOCK;
+    if (!getenv("HFG_ZLIB_INFLATE")) s->inflate = hfg_inflate_open(path, SRC_BLOCK); /* NULL for anything but gzip */
+    if (s->inflate) s->block = hfg_inflate_piece_capacity(s->inflate);
+    s->cap = 2 * s->block + 2;
     s->buf = malloc(s->cap);
     if (!s->buf) return 0;
-    s->slot[0] = malloc(SRC_BLOCK);
-    s->slot[1] = malloc(SRC_BLOCK);
+    s->slot[0] = malloc(s->block);
+    s->slot[1] = malloc(s->block);
     if (s->slot[0] && s->slot[1] && pthread_mutex_init(&s->mu, NULL) == 0) {
         if (pthread_cond_init(&s->cv, NULL) == 0) {
             if (pthread_create(&s->thread, NULL, src_producer, s) == 0) s->threaded = 1;
@@ -278,16 +288,20 @@ static void src_close(LineSrc *s) {
     free(s->slot[0]);
     free(s->slot[1]);
     free(s->buf);
+    hfg_inflate_close(s->inflate);
 }
 
-/* appends the next block behind s->len (room for SRC_BLOCK + 1 bytes is there); returns the byte count, <= 0 at the end */
-static int src_fill(LineSrc *s) {
-    if (!s->threaded) return gzread(s->fp, s->buf + s->len, (unsigned) SRC_BLOCK);
+/* appends the next block behind s->len (room for s->block + 1 bytes is there); returns the byte count, 0 at the end,
+ * < 0 on a read / inflate error */
+static long src_fill(LineSrc *s) {
+    if (!s->threaded)
+        return s->inflate ? hfg_inflate_next(s->inflate, (uint8_t *) s->buf + s->len)
+                          : (long) gzread(s->fp, s->buf + s->len, (unsigned) SRC_BLOCK);
     const int k = (int) (s->consumed & 1);
     pthread_mutex_lock(&s->mu);
     while (!s->full[k]) pthread_cond_wait(&s->cv, &s->mu);
     pthread_mutex_unlock(&s->mu);
-    const int got = s->got[k];
+    const long got = s->got[k];
     if (got > 0) memcpy(s->buf + s->len, s->slot[k], (size_t) got);
     pthread_mutex_lock(&s->mu);
     s->full[k] = 0;
@@ -318,13 +332,14 @@ static int src_next(LineSrc *s, char **line, size_t *n) {
         if (s->pos > 0) memmove(s->buf, start, rest);
         s->pos = 0;
         s->len = rest;
-        if (s->cap - s->len < SRC_BLOCK + 1) {
+        if (s->cap - s->len < s->block + 1) {
             char *nb = realloc(s->buf, s->cap * 2);
             if (!nb) return -1;
             s->buf = nb;
             s->cap *= 2;
         }
-        const int got = src_fill(s);
+        const long got = src_fill(s);
+        if (got < 0) s->bad_gzip = 1;
         if (got <= 0) s->eof = 1;
         else s->len += (size_t) got;
     }
@@ -349,7 +364,7 @@ int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_co
     hfg_cov_data *d = calloc(1, sizeof(*d));
     Growable g = {d, 0, 0};
     LineSrc src;
-    const int src_ok = src_open(&src, fp);
+    const int src_ok = src_open(&src, fp, path);
     char *line = NULL;
     Window *win = malloc(sizeof(Window));
     int status = HFG_OK;
@@ -561,6 +576,12 @@ int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_co
     }
     if (more < 0) {
         status = HFG_ERR_NOMEM;
+        goto done;
+    }
+    if (src.bad_gzip) {
+        if (src.inflate) snprintf(err, errlen, "%s: corrupt gzip data (%s)", path, hfg_inflate_error(src.inflate));
+        else snprintf(err, errlen, "%s: read error", path);
+        status = HFG_ERR_INVALID;
         goto done;
     }
     if (have_chunk && next_base != ctg_len) {

@@ -74,6 +74,10 @@ int hfg_benchmark_scores(const hfg_cov_data *data, const int8_t *prediction, con
                          double overlap_ratio_threshold, const char *bin_array_file, const char *annotation_label,
                          const char *size_label, double scores[3], char *err, size_t errlen);
 
+/* Test hook: gunzip `path` with the reader's own gzip decoder (csrc/hfg_inflate.c) into out[cap], in pieces of piece_bytes
+ * (0 = the reader's 4 MB); *len = bytes written.  0 on success, 1 with a message otherwise (not gzip, corrupt, CRC). */
+int hfg_debug_gunzip(const char *path, uint8_t *out, size_t cap, size_t *len, size_t piece_bytes, char *err, size_t errlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,6 @@
     one region / seven regions + eight annotations, with and without truth labels.
 Nothing here touches the GPU; the E-step numbers are bench.py's."""
 import argparse
-import gzip
 import os
 import shutil
 import sys
@@ -76,15 +75,28 @@ def main():
         total = args.mbp * 1_000_000
         plain = os.path.join(tmp, "c.cov")
         write_rle_cov(plain, [total // 4] * 4)
-        with open(plain, "rb") as fi, gzip.open(plain + ".gz", "wb", compresslevel=6) as fo:
-            shutil.copyfileobj(fi, fo)
-        n_lines = sum(1 for _ in open(plain))
+        import zlib
+        with open(plain, "rb") as fi:
+            text = fi.read()
+        # the reference writes coverage files with gzopen(path, "w6h"): level 6, Huffman-only (ptBlock.c:2271)
+        for name, strategy in (("c.huffman.cov.gz", zlib.Z_HUFFMAN_ONLY), ("c.default.cov.gz", zlib.Z_DEFAULT_STRATEGY)):
+            co = zlib.compressobj(6, zlib.DEFLATED, 31, 8, strategy)
+            with open(os.path.join(tmp, name), "wb") as fo:
+                fo.write(co.compress(text) + co.flush())
+        n_lines = text.count(b"\n")
+        del text
         print(f"coverage file: {args.mbp} Mbp, {n_lines} lines, {os.path.getsize(plain) / 1e6:.1f} MB text, "
-              f"{os.path.getsize(plain + '.gz') / 1e6:.1f} MB gz; {os.cpu_count()} host threads")
-        for path in (plain, plain + ".gz"):
-            dt, (wl, _) = best(lambda: binfmt.read_cov_native(path, 20_000_000, 4000))
-            print(f"  hfg_read_cov {os.path.basename(path):10s} {dt:7.3f} s  ({dt / n_lines * 1e9:5.0f} ns/line, {wl.n_windows} windows) "
-                  f"-> 3 Gbp: {dt * 3000 / args.mbp:5.1f} s")
+              f"{os.path.getsize(os.path.join(tmp, 'c.huffman.cov.gz')) / 1e6:.1f} MB gzip as the reference writes it (Huffman-only), "
+              f"{os.path.getsize(os.path.join(tmp, 'c.default.cov.gz')) / 1e6:.1f} MB gzip -6; {os.cpu_count()} host threads")
+        for name in ("c.cov", "c.huffman.cov.gz", "c.default.cov.gz"):
+            path = os.path.join(tmp, name)
+            for zl in ((False, True) if name.endswith(".gz") else (False,)):
+                if zl:
+                    os.environ["HFG_ZLIB_INFLATE"] = "1"
+                dt, (wl, _) = best(lambda: binfmt.read_cov_native(path, 20_000_000, 4000), reps=5)
+                os.environ.pop("HFG_ZLIB_INFLATE", None)
+                print(f"  hfg_read_cov {name:18s}{' (zlib inflate)' if zl else '               '} {dt:7.3f} s  ({dt / n_lines * 1e9:5.0f} ns/line, "
+                      f"{wl.n_windows} windows) -> 3 Gbp: {dt * 3000 / args.mbp:5.1f} s")
         import oracle_lib
         if oracle_lib.reference() is not None:
             small = os.path.join(tmp, "s.cov")
