@@ -72,8 +72,11 @@ static int grow_chunks(Growable *g, int32_t need) {
     return 1;
 }
 
+void hfg_score_cache_free(void *cache); /* hfg_summary.c */
+
 void hfg_cov_free(hfg_cov_data *d) {
     if (!d) return;
+    hfg_score_cache_free(d->score_cache);
     for (int i = 0; i < d->n_annotations; i++) free(d->annotation_names ? d->annotation_names[i] : NULL);
     free(d->annotation_names);
     free(d->region_coverages);

@@ -136,6 +136,14 @@ static void winindex_free(WinIndex *w) {
     memset(w, 0, sizeof(*w));
 }
 
+/* run_end[g] for the label arrays a, b (either may be NULL) */
+static void winindex_set_runs(const WinIndex *w, const int8_t *a, const int8_t *b, int32_t *run_end) {
+    for (int64_t g = w->n - 1; g >= 0; g--) {
+        const int same = g + 1 < w->n && w->ctg[g] == w->ctg[g + 1] && (!a || a[g] == a[g + 1]) && (!b || b[g] == b[g + 1]);
+        run_end[g] = same ? run_end[g + 1] : (int32_t) g;
+    }
+}
+
 /* a, b: the label arrays the scans will compare (either may be NULL) */
 static int winindex_build(const hfg_cov_data *d, const int8_t *a, const int8_t *b, WinIndex *w) {
     memset(w, 0, sizeof(*w));
@@ -167,10 +175,7 @@ static int winindex_build(const hfg_cov_data *d, const int8_t *a, const int8_t *
     }
     w->cum[0] = 0;
     for (g = 0; g < total; g++) w->cum[g + 1] = w->cum[g] + (w->end[g] - w->start[g] + 1);
-    for (g = total - 1; g >= 0; g--) {
-        const int same = g + 1 < total && w->ctg[g] == w->ctg[g + 1] && (!a || a[g] == a[g + 1]) && (!b || b[g] == b[g + 1]);
-        w->run_end[g] = same ? w->run_end[g + 1] : (int32_t) g;
-    }
+    winindex_set_runs(w, a, b, w->run_end);
     return 1;
 }
 
@@ -641,6 +646,23 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *d, const int8_t 
     return HFG_OK;
 }
 
+/* what hfg_benchmark_scores keeps with a data object between calls */
+typedef struct ScoreCache {
+    int ci;      /* annotation index the visit list was built for */
+    WinIndex wi; /* its run_end belongs to no prediction (all-NULL labels) and is not used */
+    Visit visit;
+} ScoreCache;
+
+static pthread_mutex_t g_score_cache_mu = PTHREAD_MUTEX_INITIALIZER;
+
+void hfg_score_cache_free(void *cache) {
+    ScoreCache *sc = cache;
+    if (!sc) return;
+    winindex_free(&sc->wi);
+    visit_free(&sc->visit);
+    free(sc);
+}
+
 /* a handful of independent scans, one thread each (the calling thread takes the first) */
 typedef struct ScanJob {
     const WinIndex *w;
@@ -731,12 +753,40 @@ int hfg_benchmark_scores(const hfg_cov_data *d, const int8_t *prediction, const 
     /* tables of this annotation only: [metric 0..1][T-vs-P, P-vs-T], base_level truth-vs-truth, auN T-vs-P and truth */
     double *tp[2] = {NULL, NULL}, *pt_[2] = {NULL, NULL}, *tt = calloc(stride, sizeof(double)),
            *aun_tp = calloc(stride, sizeof(double)), *aun_tt = calloc(stride, sizeof(double));
+    /* the window coordinates and the windows of the annotation do not change between candidates of an alpha-tuning run:
+     * kept with the data object (d->score_cache); only the run table depends on the prediction */
     WinIndex wi;
     Visit visit;
+    memset(&wi, 0, sizeof(wi));
     memset(&visit, 0, sizeof(visit));
-    int ok = tt && aun_tp && aun_tt && winindex_build(d, prediction, truth, &wi);
-    if (!ok) memset(&wi, 0, sizeof(wi));
-    ok = ok && visit_build(d, &wi, CAT_ANNOTATION, ci, &visit);
+    int ok = tt && aun_tp && aun_tt;
+    int32_t *run_end = NULL;
+    if (ok) {
+        pthread_mutex_lock(&g_score_cache_mu);
+        ScoreCache *sc = ((hfg_cov_data *) d)->score_cache;
+        if (!sc || sc->ci != ci || sc->wi.n != d->n_windows) {
+            hfg_score_cache_free(sc);
+            ((hfg_cov_data *) d)->score_cache = sc = calloc(1, sizeof(ScoreCache));
+            if (sc) {
+                sc->ci = ci;
+                if (!winindex_build(d, NULL, NULL, &sc->wi) || !visit_build(d, &sc->wi, CAT_ANNOTATION, ci, &sc->visit)) {
+                    hfg_score_cache_free(sc);
+                    ((hfg_cov_data *) d)->score_cache = sc = NULL;
+                }
+            }
+        }
+        if (sc) {
+            wi = sc->wi; /* shared, read-only; the run table below is this call's own */
+            visit = sc->visit;
+        }
+        pthread_mutex_unlock(&g_score_cache_mu);
+        run_end = sc ? malloc(sizeof(int32_t) * (size_t) (wi.n > 0 ? wi.n : 1)) : NULL;
+        ok = sc && run_end;
+        if (ok) {
+            winindex_set_runs(&wi, prediction, truth, run_end);
+            wi.run_end = run_end;
+        }
+    }
     for (int metric = 0; metric < 2; metric++) {
         tp[metric] = calloc(stride, sizeof(double));
         pt_[metric] = calloc(stride, sizeof(double));
@@ -754,8 +804,7 @@ int hfg_benchmark_scores(const hfg_cov_data *d, const int8_t *prediction, const 
             {&wi, &visit, truth, truth, n, METRIC_AUN, overlap_ratio_threshold, tt, &bins, aun_tt, 0}};
         ok = run_scans(jobs, 5) && run_scans(jobs + 5, 2);
     }
-    visit_free(&visit);
-    winindex_free(&wi);
+    free(run_end);
     if (!ok) {
         for (int metric = 0; metric < 2; metric++) {
             free(tp[metric]);

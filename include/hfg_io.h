@@ -37,6 +37,8 @@ typedef struct hfg_cov_data {
     uint64_t *annotation_flag;                      /* [n_windows] incl. the region index in bits 58..63 */
     uint8_t *region;                                /* [n_windows] CoverageInfo_getRegionIndex */
     int8_t *truth, *prediction;                     /* [n_windows] Inference labels, -1 = none (ptBlock.h:50-55) */
+    void *score_cache; /* owned by the library: what hfg_benchmark_scores keeps between calls (window coordinates, the
+                          windows of the scored annotation); freed by hfg_cov_free.  Objects must come from the readers. */
 } hfg_cov_data;
 
 /* `.cov` or `.cov.gz` (run-length blocks tiling every contig) -> chunks of `chunk_len` bases cut into windows of
@@ -69,7 +71,9 @@ int hfg_write_summary_tsv(const char *path, const hfg_cov_data *data, const int8
  * (programs/src/tune_alpha_hmm_flagger.py:82-111): the F1-Score of the HARMONIC_MEAN_NO_HAP row of the overlap_based and
  * of the base_level table, and 100 x the HARMONIC_MEAN auN ratio, for one annotation and one size bin (default names
  * "whole_genome" / "ALL_SIZES"), each rounded to two decimals as the files print them (NaN where they print NA).
- * Computed from the flat label arrays without writing any file: what a tuning loop needs per candidate alpha matrix. */
+ * Computed from the flat label arrays without writing any file: what a tuning loop needs per candidate alpha matrix.
+ * The window coordinates and the annotation's windows are kept with `data` after the first call (data->score_cache), so
+ * later calls cost only the label-run scans (~6 ms at 750k windows); calls on one data object must not run concurrently. */
 int hfg_benchmark_scores(const hfg_cov_data *data, const int8_t *prediction, const int8_t *truth, int n_labels,
                          double overlap_ratio_threshold, const char *bin_array_file, const char *annotation_label,
                          const char *size_label, double scores[3], char *err, size_t errlen);
