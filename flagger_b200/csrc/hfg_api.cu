@@ -77,6 +77,12 @@ struct hfg_ctx {
     void *d_flush;
     size_t flush_bytes;
     int64_t launches;
+    /* negative-binomial model (EXPERIMENTAL: accepted only with HFG_EXPERIMENTAL_NB=1, not validated on hardware yet) */
+    int nb;
+    double *d_nb_table, *h_nb_table;     /* [R][4][HFG_NB_XSTRIDE] device / pinned */
+    double *d_nb_tile_col, *h_nb_tile_col; /* [n_tiles][4] */
+    int32_t *h_tile_key;                 /* [n_tiles] host copies for folding the tile masses into the histogram */
+    uint32_t *h_kdesc;                   /* [n_keys] */
     char err[512];
 };
 
@@ -123,9 +129,13 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     hfg_ctx *ctx = NULL;
     if (!out || !cfg) return fail(NULL, HFG_ERR_INVALID, "hfg_create: NULL argument");
     *out = NULL;
-    if (cfg->model_type != HFG_MODEL_TRUNC_EXP_GAUSSIAN && cfg->model_type != HFG_MODEL_GAUSSIAN)
-        return fail(NULL, HFG_ERR_INVALID, "hfg_create: model_type %d has no device path (negative_binomial: host functions only so far)",
+    const int nb = cfg->model_type == HFG_MODEL_NEGATIVE_BINOMIAL;
+    if (nb && !getenv("HFG_EXPERIMENTAL_NB"))
+        return fail(NULL, HFG_ERR_INVALID, "hfg_create: model_type %d has no device path that was validated on hardware "
+                    "(negative_binomial: host functions; HFG_EXPERIMENTAL_NB=1 enables the untested kernel instantiation)",
                     cfg->model_type);
+    if (!nb && cfg->model_type != HFG_MODEL_TRUNC_EXP_GAUSSIAN && cfg->model_type != HFG_MODEL_GAUSSIAN)
+        return fail(NULL, HFG_ERR_INVALID, "hfg_create: model_type %d not supported", cfg->model_type);
     if (cfg->n_regions < 1 || cfg->n_regions > HFG_MAX_REGIONS)
         return fail(NULL, HFG_ERR_INVALID, "hfg_create: n_regions %d outside 1..%d", cfg->n_regions, HFG_MAX_REGIONS);
     for (int s = 0; s < HFG_NS; s++)
@@ -154,12 +164,13 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     prop.sharedMemPerBlockOptin = (size_t) optin;
     ctx->num_sms = prop.multiProcessorCount;
     const int G = total_gauss_comps(cfg);
+    ctx->nb = nb;
     ctx->threads = HFG_THREADS_MAX;
-    ctx->kernel = (const void *) hfg_estep_kernel<HFG_THREADS_MAX>;
+    ctx->kernel = nb ? (const void *) hfg_estep_kernel<HFG_THREADS_MAX, true> : (const void *) hfg_estep_kernel<HFG_THREADS_MAX>;
     ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg), ctx->threads);
     if (ctx->smem_bytes > (size_t) optin) { /* many components / regions: halve the CTA, halving the statistics area */
         ctx->threads = HFG_THREADS_MIN;
-        ctx->kernel = (const void *) hfg_estep_kernel<HFG_THREADS_MIN>;
+        ctx->kernel = nb ? (const void *) hfg_estep_kernel<HFG_THREADS_MIN, true> : (const void *) hfg_estep_kernel<HFG_THREADS_MIN>;
         ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg), ctx->threads);
     }
     if (max_tasks(cfg) > HFG_MAX_TASKS) {
@@ -224,6 +235,15 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         return HFG_ERR_NOMEM;
     }
     ctx->graph_disabled = getenv("HFG_NO_GRAPH") != NULL; /* A/B switch: plain stream launches instead of graph replay */
+    if (nb) {
+        const size_t tb = sizeof(double) * (size_t) cfg->n_regions * 4 * HFG_NB_XSTRIDE;
+        if (cudaMalloc((void **) &ctx->d_nb_table, tb) != cudaSuccess || cudaMallocHost((void **) &ctx->h_nb_table, tb) != cudaSuccess) {
+            fail(NULL, HFG_ERR_CUDA, "negative-binomial table allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            hfg_destroy(ctx);
+            return HFG_ERR_CUDA;
+        }
+        memset(ctx->h_nb_table, 0, tb);
+    }
     *out = ctx;
     return HFG_OK;
 }
@@ -318,6 +338,13 @@ static void free_device(hfg_ctx *ctx) {
     ctx->em_active = 0;
     ctx->h_out = NULL;
     ctx->h_labels = NULL;
+    cudaFree(ctx->d_nb_tile_col);
+    cudaFreeHost(ctx->h_nb_tile_col);
+    free(ctx->h_tile_key);
+    free(ctx->h_kdesc);
+    ctx->d_nb_tile_col = ctx->h_nb_tile_col = NULL;
+    ctx->h_tile_key = NULL;
+    ctx->h_kdesc = NULL;
     hfg_layout_free(&ctx->lay);
     ctx->have_chunks = 0;
 }
@@ -349,6 +376,8 @@ extern "C" void hfg_destroy(hfg_ctx *ctx) {
     cudaFree(ctx->d_mailbox);
     cudaFree(ctx->d_epoch);
     cudaFree(ctx->d_flush);
+    cudaFree(ctx->d_nb_table);
+    cudaFreeHost(ctx->h_nb_table);
     for (int i = 0; i < 2 * ctx->em_ev_cap; i++) cudaEventDestroy(ctx->em_ev[i]);
     free(ctx->em_ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -586,6 +615,18 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
                 "%d tiles of <= %d windows\n", host_layout ? "host" : "device", host_layout ? " + keys" : "", tm[1] - tm[0],
                 tm[2] - tm[1], tm[3] - tm[2], host_layout ? "copies" : "device build", tm[4] - tm[3], l->n_keys, l->n_tiles,
                 l->tile_len);
+    if (ctx->nb) {
+        /* per-tile pair masses come back to the host, which folds them into the (region, state, x) histogram: it needs
+         * every tile's key and every key's observation word */
+        const size_t nt = (size_t) (l->n_tiles > 0 ? l->n_tiles : 1), nk = (size_t) (l->n_keys > 0 ? l->n_keys : 1);
+        ctx->h_tile_key = (int32_t *) malloc(sizeof(int32_t) * nt);
+        ctx->h_kdesc = (uint32_t *) malloc(sizeof(uint32_t) * nk);
+        if (!ctx->h_tile_key || !ctx->h_kdesc) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+        CU(cudaMalloc((void **) &ctx->d_nb_tile_col, sizeof(double) * 4 * nt));
+        CU(cudaMallocHost((void **) &ctx->h_nb_tile_col, sizeof(double) * 4 * nt));
+        if (l->n_tiles > 0) CU(cudaMemcpy(ctx->h_tile_key, ctx->d_tile_key, sizeof(int32_t) * (size_t) l->n_tiles, cudaMemcpyDeviceToHost));
+        if (l->n_keys > 0) CU(cudaMemcpy(ctx->h_kdesc, ctx->d_kdesc, sizeof(uint32_t) * (size_t) l->n_keys, cudaMemcpyDeviceToHost));
+    }
     /* the per-window tables now live on the device */
     free(ctx->lay.obsT); ctx->lay.obsT = NULL;
     free(ctx->lay.wkeyT); ctx->lay.wkeyT = NULL;
@@ -602,6 +643,8 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     const hfg_config *cfg = &ctx->cfg;
     const hfg_layout *l = &ctx->lay;
     const int R = cfg->n_regions;
+    static const double zero_alpha[16] = {0};
+    if (ctx->nb) alpha = zero_alpha; /* the model has no previous-window dependency (hmm_utils.c:1409-1417) */
     hfg_classes cl;
     hfg_classes_build(cfg, alpha, &cl);
     EstepArgs &a = *out_args;
@@ -694,6 +737,31 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     for (int p = 0; p < HFG_MAX_PEERS; p++) a.peer_box[p] = ctx->peer_box[p];
     a.epoch = ctx->d_epoch;
     a.model_type = cfg->model_type;
+    a.nb_table = ctx->d_nb_table;
+    a.nb_tile_col = ctx->d_nb_tile_col;
+}
+
+/* negative binomial: the pmf of every (region, state, x) for these parameters (host, libm: hfg_nb.c) -> pinned staging
+ * -> device table, queued on `stream`.  The staging buffer is reused, so the stream is drained first. */
+static int nb_upload_table(hfg_ctx *ctx, const hfg_region_params *params, cudaStream_t stream) {
+    const int R = ctx->cfg.n_regions;
+    double *tmp = (double *) malloc(sizeof(double) * (size_t) R * 4 * HFG_NB_TABLE_X);
+    if (!tmp) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+    const int rc = hfg_nb_emission_table(&ctx->cfg, params, tmp);
+    if (rc != HFG_OK) {
+        free(tmp);
+        return fail(ctx, rc, rc == HFG_ERR_NAN ? "prob is NAN (a negative-binomial pmf evaluated to NaN; hmm_utils.c:507-510)"
+                                               : "hfg_nb_emission_table: invalid arguments");
+    }
+    cudaError_t e = cudaStreamSynchronize(stream);
+    for (int q = 0; q < R * 4; q++)
+        memcpy(ctx->h_nb_table + (size_t) q * HFG_NB_XSTRIDE, tmp + (size_t) q * HFG_NB_TABLE_X, sizeof(double) * HFG_NB_TABLE_X);
+    free(tmp);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ctx->d_nb_table, ctx->h_nb_table, sizeof(double) * (size_t) R * 4 * HFG_NB_XSTRIDE,
+                            cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return fail(ctx, HFG_ERR_CUDA, "negative-binomial table upload failed: %s", cudaGetErrorString(e));
+    return HFG_OK;
 }
 
 /* Enqueue one E-step (or forward pass) on `stream`; results land in out_dev = [stats | loglik | error flags]. */
@@ -714,6 +782,10 @@ static int enqueue_estep(hfg_ctx *ctx, const double *alpha, const hfg_region_par
 
     EstepArgs a;
     build_args(ctx, alpha, out_dev, post_dev, forward_only, slot, &a);
+    if (ctx->nb) {
+        const int rc_nb = nb_upload_table(ctx, params, stream);
+        if (rc_nb != HFG_OK) return rc_nb;
+    }
 
     void *kargs[] = {(void *) &a};
     if (timed) CU(cudaEventRecord(ctx->ev0, stream));
@@ -791,11 +863,65 @@ static int8_t *pinned_device_alias(const void *p) {
     return at.type == cudaMemoryTypeHost ? (int8_t *) at.devicePointer : NULL;
 }
 
+/* blocking E-step of the negative-binomial model (EXPERIMENTAL, HFG_EXPERIMENTAL_NB=1): emission table from the host,
+ * the NB kernel instantiation, per-tile pair masses back to the host, folded into the (region, state, x) histogram in
+ * tile order and turned into the estimator sums by hfg_nb_stats_from_histogram (hmm.c:615-617,643-649). */
+static int run_blocking_nb(hfg_ctx *ctx, const hfg_region_params *params, int forward_only, hfg_region_stats *stats,
+                           double *loglik, int8_t *labels) {
+    const int with_labels = labels != NULL;
+    const int R = ctx->cfg.n_regions;
+    const hfg_layout *l = &ctx->lay;
+    CU(cudaSetDevice(ctx->device));
+    int8_t *label_alias = with_labels ? pinned_device_alias(labels) : NULL;
+    int8_t *label_dst = !with_labels ? NULL : (label_alias ? label_alias : ctx->h_labels);
+    static const double zero_alpha[16] = {0};
+    EstepArgs a;
+    build_args(ctx, zero_alpha, ctx->d_out, NULL, forward_only, 0, &a);
+    a.labels_host = label_dst;
+    CU(cudaEventSynchronize(ctx->stage_ev[0]));
+    memcpy(ctx->h_params[0], params, sizeof(hfg_region_params) * (size_t) R);
+    int rc = nb_upload_table(ctx, params, ctx->stream);
+    if (rc != HFG_OK) return rc;
+    void *kargs[] = {(void *) &a};
+    CU(cudaEventRecord(ctx->ev2, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_params[0], ctx->h_params[0], sizeof(hfg_region_params) * (size_t) R, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev0, ctx->stream));
+    CU(cudaLaunchCooperativeKernel(ctx->kernel, dim3(ctx->grid), dim3(ctx->threads), kargs, ctx->smem_bytes, ctx->stream));
+    CU(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (!forward_only && l->n_tiles > 0)
+        CU(cudaMemcpyAsync(ctx->h_nb_tile_col, ctx->d_nb_tile_col, sizeof(double) * 4 * (size_t) l->n_tiles, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CU(cudaEventRecord(ctx->ev3, ctx->stream));
+    CU(cudaEventRecord(ctx->stage_ev[0], ctx->stream));
+    ctx->ev_valid = ctx->span_valid = 1;
+    ctx->launches += 1;
+    memcpy(ctx->last_alpha, zero_alpha, sizeof(double) * 16);
+    memcpy(ctx->last_params, params, sizeof(hfg_region_params) * (size_t) R);
+    ctx->have_last = 1;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (with_labels && !label_alias) memcpy(labels, ctx->h_labels, (size_t) l->n_windows);
+    rc = parse_out(ctx, stats, loglik); /* transition counts and log-likelihood; the emission slots are zero */
+    if (rc != HFG_OK || !stats || forward_only) return rc;
+    double *hist = (double *) calloc((size_t) R * 4 * HFG_NB_BINS, sizeof(double));
+    if (!hist) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+    for (int32_t t = 0; t < l->n_tiles; t++) { /* tile order: the same sum on every run */
+        const uint32_t w = ctx->h_kdesc[ctx->h_tile_key[t]];
+        const int x = (int) HFG_OBS_X(w), region = (int) HFG_OBS_REGION(w);
+        const int bin = x < HFG_NB_BINS ? x : HFG_NB_BINS - 1; /* count_data.c:56-64 */
+        for (int s = 0; s < 4; s++) hist[((size_t) region * 4 + s) * HFG_NB_BINS + bin] += ctx->h_nb_tile_col[(size_t) t * 4 + s];
+    }
+    rc = hfg_nb_stats_from_histogram(&ctx->cfg, params, hist, stats);
+    free(hist);
+    if (rc != HFG_OK) return fail(ctx, rc, "prob is NAN (negative-binomial estimator update)");
+    return HFG_OK;
+}
+
 /* blocking E-step with host buffers: graph replay when possible, plain launches otherwise (same kernel either way) */
 static int run_blocking(hfg_ctx *ctx, const double *alpha, const hfg_region_params *params, int forward_only,
                         hfg_region_stats *stats, double *loglik, int8_t *labels) {
     if (!ctx->have_chunks) return fail(ctx, HFG_ERR_INVALID, "hfg_set_chunks must be called first");
     if (!alpha || !params) return fail(ctx, HFG_ERR_INVALID, "NULL alpha/params");
+    if (ctx->nb) return run_blocking_nb(ctx, params, forward_only, stats, loglik, labels);
     const int with_labels = labels != NULL;
     CU(cudaSetDevice(ctx->device));
     /* where the kernel streams the labels: the caller's buffer when it is page-locked, else the pinned staging buffer */
@@ -851,6 +977,7 @@ extern "C" int hfg_em_iteration_device(hfg_ctx *ctx, const double *alpha, const 
                                        void *stats_dev, void *stream) {
     if (!ctx) return HFG_ERR_INVALID;
     if (!stats_dev) return fail(ctx, HFG_ERR_INVALID, "hfg_em_iteration_device: NULL stats_dev");
+    if (ctx->nb) return fail(ctx, HFG_ERR_INVALID, "hfg_em_iteration_device: not available for the negative-binomial model");
     cudaStream_t s = stream ? (cudaStream_t) stream : ctx->stream;
     return enqueue_estep(ctx, alpha, params, (double *) stats_dev, NULL, 0, s, 1);
 }
@@ -926,6 +1053,7 @@ extern "C" int hfg_em_begin(hfg_ctx *ctx, const double *alpha, const hfg_region_
     if (!ctx) return HFG_ERR_INVALID;
     if (!ctx->have_chunks) return fail(ctx, HFG_ERR_INVALID, "hfg_set_chunks must be called first");
     if (!alpha || !params || max_esteps < 1) return fail(ctx, HFG_ERR_INVALID, "hfg_em_begin: bad argument");
+    if (ctx->nb) return fail(ctx, HFG_ERR_INVALID, "hfg_em_begin: the device-resident loop does not serve the negative-binomial model");
     CU(cudaSetDevice(ctx->device));
     const int R = ctx->cfg.n_regions;
     const size_t pb = sizeof(hfg_region_params) * (size_t) R;
@@ -1043,8 +1171,9 @@ extern "C" int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *
                           double convergence_tol, double *logliks, int *n_esteps, int8_t *labels) {
     if (!ctx || !params || !logliks || !n_esteps) return HFG_ERR_INVALID;
     if (max_iterations < 0) max_iterations = 0;
-    if (max_iterations + 1 > HFG_EM_LOGLIK_SLOTS) {
-        /* longer than the device loop records: the same loop with the host between the iterations */
+    if (max_iterations + 1 > HFG_EM_LOGLIK_SLOTS || ctx->nb) {
+        /* longer than the device loop records, or the negative-binomial model (its estimator update and M-step are host
+         * code): the same loop with the host between the iterations */
         const int R = ctx->cfg.n_regions;
         hfg_region_stats *stats = (hfg_region_stats *) malloc(sizeof(hfg_region_stats) * (size_t) R);
         if (!stats) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
@@ -1269,6 +1398,7 @@ extern "C" int hfg_peer_connect(hfg_ctx *ctx, int n_ranks, int rank, const void 
     if (n_ranks < 1 || n_ranks > HFG_MAX_PEERS || rank < 0 || rank >= n_ranks)
         return fail(ctx, HFG_ERR_INVALID, "hfg_peer_connect: %d ranks (limit %d), rank %d", n_ranks, HFG_MAX_PEERS, rank);
     if (!ctx->d_mailbox) return fail(ctx, HFG_ERR_INVALID, "hfg_peer_connect: call hfg_peer_export first");
+    if (ctx->nb && n_ranks > 1) return fail(ctx, HFG_ERR_INVALID, "hfg_peer_connect: the negative-binomial model is single-GPU so far");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     close_peers(ctx); /* a second connect replaces the first; a failure below leaves the context single-rank */

@@ -144,7 +144,13 @@ struct EstepArgs {
     hfg_region_params *em_params; /* the same memory as `params` */
     int32_t *em_state;            /* [0] stop (converged or failed), [1] E-steps run, [2] error flags, [3] converged */
     double *em_logliks;           /* log-likelihood of every E-step run */
+    /* negative-binomial instantiation only (hfg_estep_kernel<THREADS, true>; NOT YET VALIDATED ON HARDWARE, DESIGN.md
+     * section 7).  Appended last so that the offsets the other instantiations read do not move. */
+    const double *nb_table; /* [R][4][HFG_NB_XSTRIDE] pmf of (region, state, x), evaluated on the host (hfg_nb.c) */
+    double *nb_tile_col;    /* [n_tiles][4] pair mass of every statistics tile by state: the host folds it into the
+                               (region, state, x) histogram the model's estimators are fed from */
 };
+#define HFG_NB_XSTRIDE 256
 
 /* statistic columns per (block, region): 16 transition counts, lambda num/den, then per Gaussian component
  * (meanNum, den, varNum), then the log-likelihood (kept in region 0's row). */
@@ -504,7 +510,7 @@ __device__ __forceinline__ unsigned fence_token() {
 
 }  // namespace hfgk
 
-template <int THREADS>
+template <int THREADS, bool NB = false>
 __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A) {
     constexpr int WARPS = THREADS / 32;
     using namespace hfgk;
@@ -614,7 +620,13 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
         double *es = acc + tid; /* es[d * LD]: this thread's emission row of the current key */
         /* every distinct (state, alpha) class once (the reference evaluates all 16 (pre,state) pairs of every WINDOW,
          * three times per iteration, plus once more inside the estimator update) */
-        if (w.start) {
+        if constexpr (NB) {
+            /* the emission depends on (region, state, x) alone (NegativeBinomial_getProb, hmm_utils.c:479-516): a look-up
+             * in the host-built table; the host passes alpha = 0, so slot s is the class of every (pre, s) */
+            const double *tb = A.nb_table + (size_t) w.region * 4 * HFG_NB_XSTRIDE + (int) w.x;
+#pragma unroll
+            for (int s = 0; s < 4; s++) es[s * LD] = tb[s * HFG_NB_XSTRIDE];
+        } else if (w.start) {
             /* chunk starts (alpha = 0, preX = 0 for every state): generic path */
             for (int d = 0; d < D; d++) {
                 if (!((A.slots_start >> d) & 1u)) continue;
@@ -1146,7 +1158,10 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_kernel(const EstepArgs A
                 }
 #pragma unroll
                 for (int pre = 0; pre < 4; pre++) col[(pre * 4 + s) * LD] += xi[pre]; /* hmm_utils.c:2010-2015 */
-                if (!A.is_gauss[s]) {
+                if constexpr (NB) {
+                    /* hmm.c:615-617: the pair mass goes into the state's histogram over x; one tile = one key = one x */
+                    A.nb_tile_col[(size_t) t * 4 + s] = ((xi[0] + xi[1]) + xi[2]) + xi[3];
+                } else if (!A.is_gauss[s]) {
                     /* TruncExponential_updateEstimator (hmm_utils.c:1027-1034) */
                     const double sum = ((xi[0] + xi[1]) + xi[2]) + xi[3];
                     col[16 * LD] += sum * w.x;

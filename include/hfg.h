@@ -33,8 +33,10 @@ extern "C" {
 
 enum hfg_state { HFG_STATE_ERR = 0, HFG_STATE_DUP = 1, HFG_STATE_HAP = 2, HFG_STATE_COL = 3 };
 
-/* submodules/hmm_utils/hmm_utils.h:43-48.  HFG_MODEL_NEGATIVE_BINOMIAL: only the host functions know it so far
- * (hfg_model_init, hfg_mstep, hfg_params_feasible, hfg_squarem_*, hfg_nb_*); hfg_create rejects it -- no device path yet. */
+/* submodules/hmm_utils/hmm_utils.h:43-48.  HFG_MODEL_NEGATIVE_BINOMIAL: the host functions serve it (hfg_model_init,
+ * hfg_mstep, hfg_params_feasible, hfg_squarem_*, hfg_nb_*); its kernel instantiation exists but has not run on hardware
+ * yet, so hfg_create rejects the model unless HFG_EXPERIMENTAL_NB=1 is set (blocking E-steps on one GPU only:
+ * hfg_em_iteration, hfg_forward_only, hfg_get_posteriors, hfg_run_em through the host loop). */
 enum hfg_model_type { HFG_MODEL_TRUNC_EXP_GAUSSIAN = 0, HFG_MODEL_GAUSSIAN = 1, HFG_MODEL_NEGATIVE_BINOMIAL = 2 };
 
 enum hfg_status {
@@ -232,7 +234,7 @@ int hfg_squarem_iteration(hfg_ctx *ctx, const double *alpha, hfg_region_params *
 int hfg_run_em_accelerated(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,
                            double convergence_tol, double *logliks, double *alpha_rates, int *n_outer, int8_t *labels);
 
-/* ---- negative-binomial model: host side (hmm_utils.c:320-640).  No device path yet -- hfg_create rejects the model ---- */
+/* ---- negative-binomial model: host side (hmm_utils.c:320-640); the device side is opt-in, see enum hfg_model_type ---- */
 #define HFG_NB_TABLE_X 251 /* coverage values 0..MAX_COVERAGE_VALUE (hmm_utils.h:15) */
 #define HFG_NB_BINS 250    /* bins of the per-state count histogram; x = 250 falls into bin 249 (count_data.c:56-64) */
 /* pmf of every (region, state, x), summed over the weighted components and floored at 1e-40 per component

@@ -1,0 +1,60 @@
+"""GPU, OPT-IN: the negative-binomial kernel instantiation (hfg_estep_kernel<THREADS, true> + the host fold in
+hfg_api.cu::run_blocking_nb) against the oracle.  The path was written after the round's GPU budget was spent and has
+NOT run on hardware yet, so hfg_create only accepts the model with HFG_EXPERIMENTAL_NB=1 and these tests only run with it:
+
+    HFG_EXPERIMENTAL_NB=1 python -m pytest tests/test_gpu_nb_experimental.py -m gpu -x -q
+
+Bars once it is enabled: labels identical, log-likelihood within 1e-9 relative, statistics within 1e-9 of the region's
+largest (the reference sums the histogram per chunk, the product per tile: rounding only), EM trajectories accordingly."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_util
+from flagger_b200 import _abi, api, synth
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("HFG_EXPERIMENTAL_NB") != "1",
+                                 reason="negative-binomial device path not validated yet: set HFG_EXPERIMENTAL_NB=1 to run it")]
+
+NB = _abi.MODEL_NEGATIVE_BINOMIAL
+
+
+@pytest.mark.parametrize("n_regions,seed", [(1, 81), (3, 82), (7, 83)])
+def test_nb_estep_matches_oracle(orc, n_regions, seed):
+    wl = synth.small_mixed(n_regions=n_regions, seed=seed)
+    wl.cov[7:10] = 250  # folded into bin 249 of the histogram
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=n_regions, n_col_comps=K, model_type=NB, mean_read_length=wl.avg_alignment_len)
+    p = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    want = orc.estep(cfg, wl, np.zeros((4, 4)), p)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    try:
+        stats, ll, labels = gpu.em_iteration(synth.HIFI_ALPHA, p)  # alpha is ignored by this model
+        assert want["rc"] == 0 and abs(ll - want["loglik"]) <= 1e-9 * abs(want["loglik"])
+        assert np.array_equal(labels, want["labels"])
+        sg, so = _abi.stats_as_flat(stats), _abi.stats_as_flat(want["stats"])
+        assert np.all(np.abs(sg - so) <= 1e-9 * np.abs(so).max())
+        post = gpu.posteriors()
+        big = want["posteriors"] > 1e-200
+        assert np.all(np.abs(post[big] - want["posteriors"][big]) <= 1e-5 * want["posteriors"][big])
+        assert abs(gpu.forward_only(synth.HIFI_ALPHA, p) - want["loglik"]) <= 1e-9 * abs(want["loglik"])
+    finally:
+        gpu.close()
+
+
+@pytest.mark.parametrize("name", golden_util.NB_NAMES)
+def test_nb_em_run_matches_reference_golden(name):
+    g, wl = golden_util.load(name, ".nb.npz")
+    cfg = g["cfg"]
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    try:
+        params, logliks, labels = gpu.run_em(g["alpha"], g["params0"], 5, tol=1e-12)
+        assert len(logliks) == len(g["em_logliks"])
+        assert np.all(np.abs(logliks - g["em_logliks"]) <= 1e-9 * np.abs(g["em_logliks"]))
+        assert np.array_equal(labels, g["em_labels"])
+        a, b = params.view(np.float64).reshape(-1), g["em_params"].view(np.float64).reshape(-1)
+        assert np.all(np.abs(a - b) <= 1e-8 * np.maximum(np.abs(b), 1e-12))
+    finally:
+        gpu.close()
