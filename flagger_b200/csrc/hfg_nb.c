@@ -56,17 +56,45 @@ long double hfg_digammal(long double x) {
 /* r of the (theta, lambda) parametrisation, NegativeBinomial_getR (hmm_utils.c:455-458) */
 static double nb_r(double theta, double lambda) { return -1 * lambda / log(theta); }
 
+/* what the pmf of one component needs besides x, evaluated once per component instead of once per (component, x): the
+ * same libm calls on the same arguments, so the values -- and the sum below, taken in the reference's order -- do not change */
+typedef struct NbComp {
+    double theta, r, w, lgamma_r, r_log_theta, log_1m_theta;
+    double bt; /* -theta / (1 - theta) - 1 / log(theta), the factor of the theta estimator (hmm_utils.c:545) */
+} NbComp;
+
+static void nb_comp_setup(const hfg_region_params *p, int s, int n_comps, NbComp *c) {
+    for (int k = 0; k < n_comps; k++) {
+        c[k].theta = p->mean[s][k];
+        c[k].r = nb_r(c[k].theta, p->var[s][k]);
+        c[k].w = p->weight[s][k];
+        c[k].lgamma_r = lgamma(c[k].r);
+        c[k].r_log_theta = c[k].r * log(c[k].theta);
+        c[k].log_1m_theta = log(1 - c[k].theta);
+        c[k].bt = -1 * c[k].theta / (1 - c[k].theta) - 1 / log(c[k].theta);
+    }
+}
+
+/* lgamma(x + 1) for the 251 coverage values */
+static const double *nb_lgamma_x1(void) {
+    static double table[HFG_NB_TABLE_X];
+    static int ready = 0;
+    if (!ready) { /* benign race: every thread writes the same values */
+        for (int x = 0; x < HFG_NB_TABLE_X; x++) table[x] = lgamma(x + 1);
+        __atomic_store_n(&ready, 1, __ATOMIC_RELEASE);
+    }
+    return table;
+}
+
 /* weighted pmf of every component at x, floored at 1e-40 (NegativeBinomial_getComponentProbs, hmm_utils.c:494-515).
  * Returns 1 if one of them is NaN (the reference exits there). */
-static int nb_component_probs(const hfg_region_params *p, int s, int n_comps, int x, double *probs) {
+static int nb_component_probs(const NbComp *c, int n_comps, int x, const double *lg_x1, double *probs) {
     int nan = 0;
-    for (int c = 0; c < n_comps; c++) {
-        const double theta = p->mean[s][c], r = nb_r(theta, p->var[s][c]);
-        double v = p->weight[s][c] *
-                   exp(lgamma(r + x) - lgamma(r) - lgamma(x + 1) + r * log(theta) + (double) x * log(1 - theta));
+    for (int k = 0; k < n_comps; k++) {
+        double v = c[k].w * exp(lgamma(c[k].r + x) - c[k].lgamma_r - lg_x1[x] + c[k].r_log_theta + (double) x * c[k].log_1m_theta);
         if (v != v) nan = 1;
         if (v < 1e-40) v = 1e-40;
-        probs[c] = v;
+        probs[k] = v;
     }
     return nan;
 }
@@ -75,14 +103,18 @@ int hfg_nb_emission_table(const hfg_config *cfg, const hfg_region_params *params
     if (!cfg || !params || !table || cfg->model_type != HFG_MODEL_NEGATIVE_BINOMIAL) return HFG_ERR_INVALID;
     int nan = 0;
     double probs[HFG_MAX_COMPS];
+    NbComp comp[HFG_MAX_COMPS];
+    const double *lg_x1 = nb_lgamma_x1();
     for (int r = 0; r < cfg->n_regions; r++)
-        for (int s = 0; s < HFG_NS; s++)
+        for (int s = 0; s < HFG_NS; s++) {
+            nb_comp_setup(&params[r], s, cfg->n_comps[s], comp);
             for (int x = 0; x < HFG_NB_TABLE_X; x++) {
-                nan |= nb_component_probs(&params[r], s, cfg->n_comps[s], x, probs);
+                nan |= nb_component_probs(comp, cfg->n_comps[s], x, lg_x1, probs);
                 double total = 0.0;
                 for (int c = 0; c < cfg->n_comps[s]; c++) total += probs[c]; /* NegativeBinomial_getProb, :479-484 */
                 table[((size_t) r * HFG_NS + s) * HFG_NB_TABLE_X + x] = total;
             }
+        }
     return nan ? HFG_ERR_NAN : HFG_OK;
 }
 
@@ -91,17 +123,20 @@ int hfg_nb_stats_from_histogram(const hfg_config *cfg, const hfg_region_params *
     if (!cfg || !params || !histogram || !stats || cfg->model_type != HFG_MODEL_NEGATIVE_BINOMIAL) return HFG_ERR_INVALID;
     int nan = 0;
     double probs[HFG_MAX_COMPS], psi[HFG_MAX_COMPS][HFG_NB_TABLE_X];
+    NbComp comp[HFG_MAX_COMPS];
+    const double *lg_x1 = nb_lgamma_x1();
     for (int reg = 0; reg < cfg->n_regions; reg++) {
         const hfg_region_params *p = &params[reg];
         hfg_region_stats *st = &stats[reg];
         for (int s = 0; s < HFG_NS; s++) {
             const int nc = cfg->n_comps[s];
+            nb_comp_setup(p, s, nc, comp);
             for (int c = 0; c < nc; c++) {
                 st->mean_num[s][c] = st->mean_den[s][c] = 0.0;
                 st->var_num[s][c] = st->var_den[s][c] = 0.0;
                 st->weight_num[s][c] = st->weight_den[s][c] = 0.0;
                 /* psi(r + x) by the recurrence from one digamma(r) (NegativeBinomial_fillDigammaTable, :392-406) */
-                const double r = nb_r(p->mean[s][c], p->var[s][c]);
+                const double r = comp[c].r;
                 psi[c][0] = (double) hfg_digammal(r);
                 for (int x = 1; x < HFG_NB_TABLE_X; x++) psi[c][x] = psi[c][x - 1] + 1.0 / (r + x - 1);
             }
@@ -110,12 +145,11 @@ int hfg_nb_stats_from_histogram(const hfg_config *cfg, const hfg_region_params *
             for (int x = 0; x < HFG_NB_BINS; x++) {
                 const double mass = histogram[((size_t) reg * HFG_NS + s) * HFG_NB_BINS + x];
                 if (!(0 < mass)) continue;
-                nan |= nb_component_probs(p, s, nc, x, probs);
+                nan |= nb_component_probs(comp, nc, x, lg_x1, probs);
                 double total = 0.0;
                 for (int c = 0; c < nc; c++) total += probs[c];
                 for (int c = 0; c < nc; c++) {
-                    const double theta = p->mean[s][c], r = nb_r(theta, p->var[s][c]);
-                    const double bt = -1 * theta / (1 - theta) - 1 / log(theta);
+                    const double r = comp[c].r, bt = comp[c].bt;
                     const double w = mass * probs[c] / total;
                     const double delta = r * (psi[c][x] - psi[c][0]);
                     st->var_num[s][c] += w * delta;
