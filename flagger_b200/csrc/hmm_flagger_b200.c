@@ -9,8 +9,8 @@
  *   posterior_prediction_final.bed (-P), chunks.c_<C>.w_<W>.bin (-B), prediction_summary_{initial,iteration_k,final}.tsv
  *   and, for inputs with truth labels, their .benchmarking.tsv / .benchmarking.auN_ratio.tsv companions (all on the flat
  *   label array, hfg_write_summary_tsv; -k for every iteration).
- * --accelerate (SQUAREM) runs through hfg_squarem_iteration.  Not supported: --modelType negative_binomial,
- * --initialRandomDev other than 0.
+ * --accelerate (SQUAREM) runs through hfg_squarem_iteration.  --modelType negative_binomial needs HFG_EXPERIMENTAL_NB=1
+ * (kernel not validated on hardware yet).  Not supported: --initialRandomDev other than 0.
  */
 #include <getopt.h>
 #include <math.h>
@@ -93,12 +93,22 @@ static void write_emission_tsv(const char *dir, const char *suffix, const hfg_co
             }
         } else {
             static const char *names[3] = {"Mean", "Var", "Weight"};
+            const int nb = cfg->model_type == HFG_MODEL_NEGATIVE_BINOMIAL;
             for (int k = 0; k < 3; k++) {
-                fprintf(f, "%s\tGaussian\t%d\t%s", STATE_NAMES[s], cfg->n_comps[s], names[k]);
+                fprintf(f, "%s\t%s\t%d\t%s", STATE_NAMES[s], nb ? "Negative Binomial" : "Gaussian", cfg->n_comps[s], names[k]);
                 for (int r = 0; r < cfg->n_regions; r++) {
                     const double *v = k == 0 ? p[r].mean[s] : (k == 1 ? p[r].var[s] : p[r].weight[s]);
                     fprintf(f, "\t");
-                    for (int c = 0; c < cfg->n_comps[s]; c++) fprintf(f, c ? ",%.5e" : "%.5e", v[c]);
+                    for (int c = 0; c < cfg->n_comps[s]; c++) {
+                        double value = v[c];
+                        if (nb && k < 2) {
+                            /* the table shows mean and variance, the model keeps (theta, lambda) in those slots
+                             * (NegativeBinomial_getMean / _getVar, hmm_utils.c:460-470) */
+                            const double theta = p[r].mean[s][c], rr = -1 * p[r].var[s][c] / log(theta);
+                            value = k == 0 ? rr * (1 - theta) / theta : rr * (1 - theta) / pow(theta, 2);
+                        }
+                        fprintf(f, c ? ",%.5e" : "%.5e", value);
+                    }
                 }
                 fprintf(f, "\n");
             }
@@ -352,7 +362,9 @@ int main(int argc, char *argv[]) {
             case 'm':
                 if (strcmp(optarg, "trunc_exp_gaussian") == 0) model_type = HFG_MODEL_TRUNC_EXP_GAUSSIAN;
                 else if (strcmp(optarg, "gaussian") == 0) model_type = HFG_MODEL_GAUSSIAN;
-                else die("--modelType: only 'trunc_exp_gaussian' and 'gaussian' run on the GPU path");
+                else if (strcmp(optarg, "negative_binomial") == 0) model_type = HFG_MODEL_NEGATIVE_BINOMIAL; /* hfg_create
+                    accepts it only with HFG_EXPERIMENTAL_NB=1: its kernel has not been validated on hardware yet */
+                else die("--modelType should be trunc_exp_gaussian, gaussian or negative_binomial");
                 break;
             case 'c': contigs = optarg; break;
             case 'p': collapsed = atoi(optarg); break;
@@ -488,7 +500,7 @@ int main(int argc, char *argv[]) {
      * --accelerate, -w or -k.  Otherwise the REST of the loop -- every further E-step, the M-steps, the convergence test and
      * the final inference -- is queued on the device at once (hfg_em_*: parameters stay in HBM, the M-step runs in the tail
      * of the E-step kernel) and the host comes back for the log-likelihoods, the parameters and the labels. */
-    const int per_iteration_outputs = accelerate || write_params || write_bench;
+    const int per_iteration_outputs = accelerate || write_params || write_bench || model_type == HFG_MODEL_NEGATIVE_BINOMIAL;
     while (iter <= iterations && !converged) {
         if (!per_iteration_outputs && iter > 1 && iterations - iter + 2 <= 4096) {
             const int remaining = iterations - iter + 1;

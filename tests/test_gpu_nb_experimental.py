@@ -58,3 +58,20 @@ def test_nb_em_run_matches_reference_golden(name):
         assert np.all(np.abs(a - b) <= 1e-8 * np.maximum(np.abs(b), 1e-12))
     finally:
         gpu.close()
+
+
+def test_nb_cli_run_matches_reference_binary(tmp_path):
+    """Whole run of the stand-alone binary with --modelType negative_binomial against the unmodified reference binary."""
+    import test_standalone_cli as cli
+    if not os.path.exists(cli.REF):
+        pytest.skip("oracle/_ref/hmm_flagger_ref was not built")
+    inp, alpha = cli._inputs(tmp_path, "cov")
+    ref_out, out = str(tmp_path / "ref"), str(tmp_path / "cli")
+    cli._run(cli.REF, inp, ref_out, extra=("-m", "negative_binomial"))
+    cli._run(cli.CLI, inp, out, extra=("-m", "negative_binomial"))
+    assert cli._read(os.path.join(ref_out, "final_flagger_prediction.bed")) == cli._read(os.path.join(out, "final_flagger_prediction.bed"))
+    for name in ("loglikelihood.tsv", "emission_final.tsv", "transition_final.tsv"):
+        a, b = cli._table(os.path.join(out, name)), cli._table(os.path.join(ref_out, name))
+        assert a.shape == b.shape and np.allclose(a, b, rtol=1e-4, atol=1e-8), name
+    for name in ("prediction_summary_initial.tsv", "prediction_summary_final.tsv"):
+        assert cli._read(os.path.join(ref_out, name)) == cli._read(os.path.join(out, name)), name
