@@ -338,8 +338,8 @@ static void free_device(hfg_ctx *ctx) {
     ctx->em_active = 0;
     ctx->h_out = NULL;
     ctx->h_labels = NULL;
-    cudaFree(ctx->d_nb_tile_col);
-    cudaFreeHost(ctx->h_nb_tile_col);
+    if (ctx->d_nb_tile_col) cudaFree(ctx->d_nb_tile_col);
+    if (ctx->h_nb_tile_col) cudaFreeHost(ctx->h_nb_tile_col);
     free(ctx->h_tile_key);
     free(ctx->h_kdesc);
     ctx->d_nb_tile_col = ctx->h_nb_tile_col = NULL;
@@ -364,8 +364,8 @@ extern "C" void hfg_destroy(hfg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     free_device(ctx);
-    cudaFreeHost(ctx->h_params[0]);
-    cudaFree(ctx->d_params[0]);
+    if (ctx->h_params[0]) cudaFreeHost(ctx->h_params[0]);
+    if (ctx->d_params[0]) cudaFree(ctx->d_params[0]);
     for (int i = 0; i < STAGE_SLOTS; i++)
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -376,8 +376,8 @@ extern "C" void hfg_destroy(hfg_ctx *ctx) {
     cudaFree(ctx->d_mailbox);
     cudaFree(ctx->d_epoch);
     cudaFree(ctx->d_flush);
-    cudaFree(ctx->d_nb_table);
-    cudaFreeHost(ctx->h_nb_table);
+    if (ctx->d_nb_table) cudaFree(ctx->d_nb_table);
+    if (ctx->h_nb_table) cudaFreeHost(ctx->h_nb_table);
     for (int i = 0; i < 2 * ctx->em_ev_cap; i++) cudaEventDestroy(ctx->em_ev[i]);
     free(ctx->em_ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
