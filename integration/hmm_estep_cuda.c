@@ -69,6 +69,14 @@ static void flatten_params(HMM *model, hfg_region_params *out) {
                 TruncExponential *te = (TruncExponential *) ed->dist;
                 p->lambda = te->lambda;
                 p->trunc_point = te->truncPoint;
+            } else if (ed->distType == DIST_NEGATIVE_BINOMIAL) {
+                /* theta / lambda travel in the mean / var slots (include/hfg.h, enum hfg_model_type) */
+                NegativeBinomial *nb = (NegativeBinomial *) ed->dist;
+                for (int c = 0; c < nb->numberOfComps; c++) {
+                    p->mean[s][c] = nb->theta[c];
+                    p->var[s][c] = nb->lambda[c];
+                    p->weight[s][c] = nb->weights[c];
+                }
             } else {
                 Gaussian *g = (Gaussian *) ed->dist;
                 for (int c = 0; c < g->numberOfComps; c++) {
@@ -96,6 +104,16 @@ static void add_stats(HMM *model, const hfg_region_stats *stats) {
                 TruncExponential *te = (TruncExponential *) ed->dist;
                 te->lambdaEstimator->numeratorPerComp[0] += st->lambda_num;
                 te->lambdaEstimator->denominatorPerComp[0] += st->lambda_den;
+            } else if (ed->distType == DIST_NEGATIVE_BINOMIAL) {
+                NegativeBinomial *nb = (NegativeBinomial *) ed->dist;
+                for (int c = 0; c < nb->numberOfComps; c++) {
+                    nb->thetaEstimator->numeratorPerComp[c] += st->mean_num[s][c];
+                    nb->thetaEstimator->denominatorPerComp[c] += st->mean_den[s][c];
+                    nb->lambdaEstimator->numeratorPerComp[c] += st->var_num[s][c];
+                    nb->lambdaEstimator->denominatorPerComp[c] += st->var_den[s][c];
+                    nb->weightsEstimator->numeratorPerComp[c] += st->weight_num[s][c];
+                    nb->weightsEstimator->denominatorPerComp[c] += st->weight_den[s][c];
+                }
             } else {
                 Gaussian *g = (Gaussian *) ed->dist;
                 for (int c = 0; c < g->numberOfComps; c++) {
@@ -122,10 +140,12 @@ static void bind(stList *emList, HMM *model) {
         free(b->ems); free(b->offsets); hfg_host_free(b->labels); free(b->params); free(b->stats); free(b->posteriors);
         memset(b, 0, sizeof(*b));
     }
-    if (model->modelType == MODEL_NEGATIVE_BINOMIAL || model->numberOfStates != HFG_NUM_STATES) {
-        fprintf(stderr, "[hmm_estep_cuda] only the 4-state trunc_exp_gaussian / gaussian models run on the GPU path\n");
+    if (model->numberOfStates != HFG_NUM_STATES) {
+        fprintf(stderr, "[hmm_estep_cuda] only the 4-state models run on the GPU path\n");
         exit(EXIT_FAILURE);
     }
+    /* negative_binomial: hfg_create decides (it accepts the model only with HFG_EXPERIMENTAL_NB=1 until its kernel has been
+     * validated on hardware) and says so in its error message */
     b->emList = emList;
     b->nChunks = (int) stList_length(emList);
     b->ems = malloc(sizeof(EM *) * b->nChunks);
@@ -162,7 +182,9 @@ static void bind(stList *emList, HMM *model) {
     EM *em0 = b->ems[0];
     TransitionRequirements *req = model->transitionPerRegion[0]->requirements;
     memset(&b->cfg, 0, sizeof(b->cfg));
-    b->cfg.model_type = model->modelType == MODEL_GAUSSIAN ? HFG_MODEL_GAUSSIAN : HFG_MODEL_TRUNC_EXP_GAUSSIAN;
+    b->cfg.model_type = model->modelType == MODEL_GAUSSIAN ? HFG_MODEL_GAUSSIAN
+                        : model->modelType == MODEL_NEGATIVE_BINOMIAL ? HFG_MODEL_NEGATIVE_BINOMIAL
+                                                                      : HFG_MODEL_TRUNC_EXP_GAUSSIAN;
     b->cfg.n_regions = model->numberOfRegions;
     for (int s = 0; s < HFG_NUM_STATES; s++)
         b->cfg.n_comps[s] = EmissionDistSeries_getNumberOfComps(model->emissionDistSeriesPerRegion[0], s);

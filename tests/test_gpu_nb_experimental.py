@@ -75,3 +75,22 @@ def test_nb_cli_run_matches_reference_binary(tmp_path):
         assert a.shape == b.shape and np.allclose(a, b, rtol=1e-4, atol=1e-8), name
     for name in ("prediction_summary_initial.tsv", "prediction_summary_final.tsv"):
         assert cli._read(os.path.join(ref_out, name)) == cli._read(os.path.join(out, name)), name
+
+
+def test_nb_dropin_binary_matches_reference_binary(tmp_path):
+    """The reference's own CLI with its E-step replaced by libhfg (integration/hmm_estep_cuda.c), negative-binomial model."""
+    import test_dropin_binary as dropin
+    if not (os.path.exists(dropin.REF) and os.path.exists(dropin.GPU)):
+        pytest.skip("oracle/_ref binaries were not built")
+    wl = synth.small_mixed(n_regions=3, seed=56)
+    inp, alpha = str(tmp_path / "in.bin"), str(tmp_path / "alpha.tsv")
+    from flagger_b200 import binfmt
+    binfmt.write_bin(wl, inp)
+    binfmt.write_alpha_tsv(np.zeros((4, 4)), alpha)
+    ref_out, gpu_out = str(tmp_path / "ref"), str(tmp_path / "gpu")
+    dropin._run(dropin.REF, inp, ref_out, alpha, extra=("-m", "negative_binomial"))
+    dropin._run(dropin.GPU, inp, gpu_out, alpha, extra=("-m", "negative_binomial"))
+    assert open(os.path.join(ref_out, "final_flagger_prediction.bed")).read() == \
+        open(os.path.join(gpu_out, "final_flagger_prediction.bed")).read()
+    a, b = dropin._table(os.path.join(ref_out, "loglikelihood.tsv")), dropin._table(os.path.join(gpu_out, "loglikelihood.tsv"))
+    assert a.shape == b.shape and np.allclose(a, b, rtol=1e-6, atol=2e-4)
