@@ -168,7 +168,10 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     ctx->threads = HFG_THREADS_MAX;
     ctx->kernel = nb ? (const void *) hfg_estep_kernel<HFG_THREADS_MAX, true> : (const void *) hfg_estep_kernel<HFG_THREADS_MAX>;
     ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg), ctx->threads);
-    if (ctx->smem_bytes > (size_t) optin) { /* many components / regions: halve the CTA, halving the statistics area */
+    /* HFG_THREADS=256: A/B switch, the 256-thread instantiation for every model (half the statistics area in shared memory,
+     * so twice the L1 for the key-table gathers, and no register spills; half the threads per SM) */
+    const int force_small = getenv("HFG_THREADS") && atoi(getenv("HFG_THREADS")) == HFG_THREADS_MIN;
+    if (force_small || ctx->smem_bytes > (size_t) optin) { /* many components / regions: halve the CTA, halving the statistics area */
         ctx->threads = HFG_THREADS_MIN;
         ctx->kernel = nb ? (const void *) hfg_estep_kernel<HFG_THREADS_MIN, true> : (const void *) hfg_estep_kernel<HFG_THREADS_MIN>;
         ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg), ctx->threads);
