@@ -50,6 +50,7 @@ class GpuEngine:
         from . import api
         wl = cov.workload
         K = collapsed_comps if collapsed_comps > 0 else api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+        # (negative_binomial has no alpha dependence: nothing to tune)
         mt = {"trunc_exp_gaussian": _abi.MODEL_TRUNC_EXP_GAUSSIAN, "gaussian": _abi.MODEL_GAUSSIAN}[model_type]
         self.cfg = _abi.make_config(n_regions=wl.n_regions, n_col_comps=K, model_type=mt, mean_read_length=wl.avg_alignment_len,
                                     device=device, **config)
