@@ -108,3 +108,14 @@ def test_create_rejects_negative_binomial_until_a_device_path_exists():
     assert rc == 1 and not ctx.value  # HFG_ERR_INVALID
     api.lib().hfg_last_error.restype = C.c_char_p
     assert b"no device path" in api.lib().hfg_last_error(None)
+
+
+def test_host_nb_table_reports_nan_like_the_reference_exit():
+    """theta outside (0, 1) makes the pmf NaN: the reference exits with "prob is NAN"; the table builder says HFG_ERR_NAN."""
+    cfg = _abi.make_config(n_regions=1, n_col_comps=2, model_type=NB)
+    p = api.model_init(cfg, np.array([40], np.int32), 4000)
+    p["mean"][0][2][0] = 1.5
+    with pytest.raises(api.HfgError):
+        api.nb_emission_table(cfg, p)
+    with pytest.raises(api.HfgError):  # wrong model type for these entry points
+        api.nb_emission_table(_abi.make_config(n_regions=1, n_col_comps=2), p)
