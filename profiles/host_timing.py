@@ -8,7 +8,9 @@
   * `.bin` -> windows;
   * prediction summary tables (hfg_write_summary_tsv) and the alpha-tuning scores (hfg_benchmark_scores) at 750 024 windows,
     one region / seven regions + eight annotations, with and without truth labels.
-Nothing here touches the GPU; the E-step numbers are bench.py's."""
+Nothing here touches the GPU; the E-step numbers are bench.py's.  Like bench.py's cpu_baseline leg, this measuring script
+times the unmodified reference (oracle/_ref, through tests/oracle_lib.py) BESIDE the product; the product itself
+(flagger_b200/) never loads anything from oracle/."""
 import argparse
 import os
 import shutil
