@@ -682,15 +682,17 @@ static void *scan_job_run(void *arg) {
     return NULL;
 }
 
+#define MAX_SCAN_JOBS 8
 static int run_scans(ScanJob *jobs, int count) {
-    pthread_t th[8];
-    int threaded[8] = {0};
-    for (int i = 1; i < count && i < 8; i++) threaded[i] = pthread_create(&th[i], NULL, scan_job_run, &jobs[i]) == 0;
+    pthread_t th[MAX_SCAN_JOBS];
+    int threaded[MAX_SCAN_JOBS] = {0};
+    if (count > MAX_SCAN_JOBS) count = MAX_SCAN_JOBS; /* (callers pass 5 and 2) */
+    for (int i = 1; i < count; i++) threaded[i] = pthread_create(&th[i], NULL, scan_job_run, &jobs[i]) == 0;
     for (int i = 0; i < count; i++)
-        if (!threaded[i < 8 ? i : 0] || i == 0 || i >= 8) scan_job_run(&jobs[i]);
+        if (!threaded[i]) scan_job_run(&jobs[i]); /* job 0, and any job whose thread could not be started */
     int ok = 1;
     for (int i = 0; i < count; i++) {
-        if (i > 0 && i < 8 && threaded[i]) pthread_join(th[i], NULL);
+        if (threaded[i]) pthread_join(th[i], NULL);
         ok &= jobs[i].ok;
     }
     return ok;
