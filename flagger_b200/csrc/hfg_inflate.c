@@ -91,7 +91,7 @@ static uint32_t reverse_bits(uint32_t code, int len) {
 }
 
 /* canonical Huffman code -> decode table.  lens[n]: code lengths (0 = unused).  primary_bits: size of the first-level table;
- * longer codes go through subtables appended behind it.  kind_of(sym) supplies the entry.  Returns 0 / -1. */
+ * longer codes go through subtables appended behind it.  is_dist selects the meaning of the symbols.  Returns 0 / -1. */
 static int build_table(uint32_t *table, int table_cap, int primary_bits, const uint8_t *lens, int n, int is_dist) {
     int count[MAX_CODE_LEN + 1] = {0};
     for (int i = 0; i < n; i++) count[lens[i]]++;
