@@ -519,11 +519,20 @@ long hfg_inflate_next(hfg_inflate *z, uint8_t *dst) {
                     break;
                 }
                 const uint8_t *src = out - dist;
-                if (dist >= len) {
-                    memcpy(out, src, (size_t) len);
+                if (dist >= 8) {
+                    /* eight bytes at a time, each read at least eight bytes behind its write; may run up to seven bytes past
+                     * the match into the slack, which the next symbols overwrite */
+                    uint8_t *o = out;
+                    int n = len;
+                    do {
+                        memcpy(o, src, 8);
+                        o += 8;
+                        src += 8;
+                        n -= 8;
+                    } while (n > 0);
                     out += len;
                 } else {
-                    while (len--) *out++ = *src++;
+                    while (len--) *out++ = *src++; /* short period: the copy feeds on its own output */
                 }
                 if (ip > z->in_len && 8 * (ip - z->in_len) > (size_t) bc) {
                     bad = "truncated input";
