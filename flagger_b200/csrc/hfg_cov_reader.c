@@ -98,9 +98,35 @@ typedef struct Window {
     double sum_cov, sum_mapq, sum_clip;
     uint64_t flag;
     int32_t region_count[REGION_BINS], truth_count[LABEL_BINS], pred_count[LABEL_BINS];
+    /* lowest / highest bin touched since the last reset: a window nearly always sees one region and one label, so the
+     * mode and the reset look at that one bin instead of all 101 + 12 + 12 */
+    int r_lo, r_hi, t_lo, t_hi, p_lo, p_hi;
 } Window;
 
-static void window_reset(Window *w) { memset(w, 0, sizeof(*w)); }
+static void window_init(Window *w) {
+    memset(w, 0, sizeof(*w));
+    w->r_lo = REGION_BINS;
+    w->t_lo = w->p_lo = LABEL_BINS;
+    w->r_hi = w->t_hi = w->p_hi = -1;
+}
+
+static void window_reset(Window *w) {
+    for (int i = w->r_lo; i <= w->r_hi; i++) w->region_count[i] = 0;
+    for (int i = w->t_lo; i <= w->t_hi; i++) w->truth_count[i] = 0;
+    for (int i = w->p_lo; i <= w->p_hi; i++) w->pred_count[i] = 0;
+    w->n = 0;
+    w->sum_cov = w->sum_mapq = w->sum_clip = 0.0;
+    w->flag = 0;
+    w->r_lo = REGION_BINS;
+    w->t_lo = w->p_lo = LABEL_BINS;
+    w->r_hi = w->t_hi = w->p_hi = -1;
+}
+
+static inline void window_count(int32_t *counts, int *lo, int *hi, int bin, int n) {
+    counts[bin] += n;
+    if (bin < *lo) *lo = bin;
+    if (bin > *hi) *hi = bin;
+}
 
 /* sum += n copies of v, bit-identical to adding v n times */
 static void add_n(double *sum, double v, int n) {
@@ -111,9 +137,11 @@ static void add_n(double *sum, double v, int n) {
     }
 }
 
-static int mode_of(const int32_t *counts, int bins, int min_value) {
-    int best = 0;
-    for (int i = 1; i < bins; i++)
+/* the most frequent value, ties -> the lowest (Int_getModeValue1DArray); bins outside [lo, hi] are empty, and at least one
+ * base was counted, so scanning the touched range gives what scanning all bins gives */
+static int mode_of(const int32_t *counts, int lo, int hi, int min_value) {
+    int best = lo;
+    for (int i = lo + 1; i <= hi; i++)
         if (counts[best] < counts[i]) best = i;
     return min_value + best;
 }
@@ -146,12 +174,12 @@ static int emit_window(Growable *g, Window *w, int window_len, int start_only) {
     d->cov[i] = clip_round(c);
     d->cov_high_mapq[i] = clip_round(m);
     d->cov_high_clip[i] = clip_round(k);
-    const int region = mode_of(w->region_count, REGION_BINS, 0);
+    const int region = mode_of(w->region_count, w->r_lo, w->r_hi, 0);
     d->region[i] = (uint8_t) region;
     /* CoverageInfo_setRegionIndex, ptBlock.c:300-304 */
     d->annotation_flag[i] = (w->flag & 0x03FFFFFFFFFFFFFFULL) | ((uint64_t) region << 58);
-    d->truth[i] = (int8_t) mode_of(w->truth_count, LABEL_BINS, -1);
-    d->prediction[i] = (int8_t) mode_of(w->pred_count, LABEL_BINS, -1);
+    d->truth[i] = (int8_t) mode_of(w->truth_count, w->t_lo, w->t_hi, -1);
+    d->prediction[i] = (int8_t) mode_of(w->pred_count, w->p_lo, w->p_hi, -1);
     d->chunks[d->n_chunks - 1].n_windows++;
     window_reset(w);
     return 1;
@@ -377,7 +405,7 @@ int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_co
     }
     d->chunk_len = chunk_len;
     d->window_len = window_len;
-    window_reset(win);
+    window_init(win);
 
     char ctg[HFG_CONTIG_NAME_MAX] = "";
     long ctg_len = 0, next_base = 0; /* next base of the contig that must come */
@@ -563,9 +591,9 @@ int hfg_read_cov(const char *path, int32_t chunk_len, int32_t window_len, hfg_co
             add_n(&win->sum_mapq, v_mapq, nb);
             add_n(&win->sum_clip, v_clip, nb);
             win->flag |= flag;
-            win->region_count[rbin] += nb;
-            win->truth_count[tbin] += nb;
-            win->pred_count[pbin] += nb;
+            window_count(win->region_count, &win->r_lo, &win->r_hi, rbin, nb);
+            window_count(win->truth_count, &win->t_lo, &win->t_hi, tbin, nb);
+            window_count(win->pred_count, &win->p_lo, &win->p_hi, pbin, nb);
             win->n += nb;
             pos = upto + 1;
             if (win->n == window_len || upto == c->e) { /* full window, or the short last window of the chunk */
