@@ -352,10 +352,10 @@ class HmmFlaggerGPU:
         return out
 
     def debug_phase_clocks(self):
-        buf = np.zeros((4096, 12), np.int64)
+        buf = np.zeros((4096, 16), np.int64)
         g = C.c_int(0)
         self._check(lib().hfg_debug_phase_clocks(self._h, ptr(buf), C.byref(g)))
-        return buf[: g.value].copy()
+        return buf[: g.value + 1].copy()  # last row: the tail clocks of the quad kernel
 
     def kernel_launches(self):
         return int(lib().hfg_kernel_launches(self._h))

@@ -14,6 +14,8 @@
 #include <time.h>
 
 #include "hfg_estep.cuh"
+#include "hfg_estep_quad.cuh"
+#include "hfg_estep_v3.cuh"
 #include "hfg_internal.h"
 #include "hfg_layout_dev.cuh"
 
@@ -26,18 +28,25 @@ struct hfg_ctx {
     hfg_layout lay;
     int have_chunks;
     int device, num_sms, max_blocks, grid;
-    int threads;          /* CTA size: 512, or 256 when the model needs the shared memory */
-    const void *kernel;   /* the matching instantiation of hfg_estep_kernel */
+    int threads;          /* CTA size: 1024 (quad kernel); first-generation kernel: 512, or 256 when the model needs the shared memory */
+    int segs_per_cta;     /* segments a CTA owns: threads / 4 (quad kernel: four lanes per segment) or threads */
+    int quad;             /* kernel generation: 3 = hfg_estep_v3_kernel (default), 2 = hfg_estep_quad_kernel (HFG_KERNEL=quad),
+                             0 = hfg_estep_kernel (HFG_KERNEL=v1) */
+    size_t smem_optin;    /* shared memory a CTA may ask for on this device */
+    int32_t n_hot, lab_bytes;
+    const void *kernel;   /* the matching kernel instantiation */
     size_t smem_bytes;
     cudaStream_t stream;
     cudaEvent_t ev0, ev1; /* around the E-step kernel */
     cudaEvent_t ev2, ev3; /* around the whole device side of the last blocking call */
     int ev_valid, span_valid;
     /* device */
-    uint32_t *d_wkeyT, *d_kdesc;
-    int32_t *d_seg_start, *d_seg_len, *d_block_reset, *d_err;
+    uint32_t *d_wkeyT, *d_kdesc, *d_wposT, *d_wkeyH, *d_khot;
+    int32_t *d_hot_key, *d_hot_range;
+    double *d_scan_stash;
+    int32_t *d_seg_start, *d_seg_len, *d_block_reset, *d_err, *d_ticket;
     int32_t *d_klist, *d_tile_key, *d_tile_begin, *d_tile_cnt, *d_region_tile_begin;
-    double *d_kbeta, *d_tabM, *d_scrFT, *d_scrXB, *d_block_tot, *d_partials, *d_out, *d_seg_loglik, *d_post;
+    double *d_kbeta, *d_tabM, *d_tabMT, *d_scrFT, *d_scrXB, *d_block_tot, *d_partials, *d_out, *d_seg_loglik, *d_post;
     hfg_region_params *d_params[STAGE_SLOTS];
     int8_t *d_labels;
     long long *d_phase_clock;
@@ -116,11 +125,108 @@ static size_t smem_bytes_for(int R, int G, int NT, int threads) {
     return doubles * sizeof(double);
 }
 
+/* shared memory of the quad kernel (hfg_estep_quad.cuh): region tables, second-level scan buffers, the CTA messages, and
+ * the larger of the per-warp statistics rows, the grid totals and -- aliasing everything behind the region tables -- the
+ * M-step work area of the device-resident loop */
+/* the M-step work area of the kernel tail (hfg_estep_tail): per region of a batch its parameters, statistics and 8 doubles,
+ * plus one exchange slot per thread for the rate fits */
+static size_t mstep_work_bytes(int threads, int regions) {
+    return ((size_t) regions * ((sizeof(hfg_region_params) + sizeof(hfg_region_stats)) / sizeof(double) + 8) + (size_t) threads) * sizeof(double);
+}
+
+static size_t smem_bytes_quad(int R, int G, int threads, int smax) {
+    const size_t warps = (size_t) threads / 32, nstat = (size_t) hfg_nstat(G);
+    const size_t rt = ((size_t) R * QRT_STRIDE(G) + 1) & ~(size_t) 1;
+    size_t stat = ((warps * nstat > (size_t) R * nstat ? warps * nstat : (size_t) R * nstat) + 1) & ~(size_t) 1;
+    const size_t labels = smax <= HFGQ_LAB_SMAX ? ((size_t) (threads / 4) * smax + 16 + 7) / 8 : 0; /* staged labels (bytes -> doubles) */
+    size_t work = 4 * warps * 16 + 8 + (size_t) (threads / 4) * 8 + stat + labels;
+    const size_t mstep = mstep_work_bytes(threads, R < 4 ? R : 4) / sizeof(double);
+    if (mstep > work) work = mstep;
+    return (rt + work) * sizeof(double);
+}
+
+/* shared memory of the third-generation kernel before the staged labels and the hot-key table: region tables, second-level
+ * scan buffers, CTA messages, per-warp statistics rows / grid totals */
+static size_t smem_base_v3(int R, int G, int threads) {
+    const size_t warps = (size_t) threads / 32, nstat = (size_t) hfg_nstat(G);
+    const size_t rt = ((size_t) R * QRT_STRIDE(G) + 1) & ~(size_t) 1;
+    const size_t stat = ((warps * nstat > (size_t) R * nstat ? warps * nstat : (size_t) R * nstat) + 1) & ~(size_t) 1;
+    return (rt + 3 * warps * 16 + 8 + stat) * sizeof(double);
+}
+
 static int total_gauss_comps(const hfg_config *cfg) {
     int G = 0;
     for (int s = 0; s < HFG_NS; s++)
         if (!(cfg->model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && s == HFG_STATE_ERR)) G += cfg->n_comps[s];
     return G;
+}
+
+/* quad kernel set-up: slot (k * capacity + j) of every window, then the list position of every listed window at its slot */
+__global__ void hfg_wslot_kernel(const int32_t *seg_start, const int32_t *seg_len, int32_t n_seg, int32_t capacity, uint32_t *wslot) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_seg) return;
+    const int first = seg_start[j], len = seg_len[j];
+    for (int k = 0; k < len; k++) wslot[first + k] = (uint32_t) k * (uint32_t) capacity + (uint32_t) j;
+}
+/* third-generation kernel set-up.  One CTA: region r gets slots in proportion to its statistics tiles (~ its windows), never
+ * more than it has keys, leftovers go to the regions that can still use them; inside a region the keys are numbered hottest
+ * first, so its first h_r keys are taken.  hot_key[slot] = key id, khot[key] = slot (preset to 0xffffffff). */
+__global__ void hfg_hot_assign_kernel(const uint32_t *kdesc, int32_t n_keys, const int32_t *region_tile_begin, int32_t R,
+                                      int32_t n_hot, int32_t *hot_key, uint32_t *khot, int32_t *hot_range) {
+    __shared__ int32_t key_begin[HFG_MAX_REGIONS + 1], h[HFG_MAX_REGIONS], base[HFG_MAX_REGIONS + 1];
+    const int tid = threadIdx.x;
+    if (tid <= R) {
+        /* first key whose region is >= tid (the keys are sorted by region) */
+        int lo = 0, hi = n_keys;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((int) HFG_OBS_REGION(kdesc[mid]) < tid) lo = mid + 1; else hi = mid;
+        }
+        key_begin[tid] = tid == R ? n_keys : lo;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const long long tiles_all = region_tile_begin[HFG_MAX_REGIONS] > 0 ? region_tile_begin[HFG_MAX_REGIONS] : 1;
+        int left = n_hot;
+        for (int r = 0; r < R; r++) {
+            const int keys = key_begin[r + 1] - key_begin[r];
+            const long long tiles = region_tile_begin[r + 1] - region_tile_begin[r];
+            int want = (int) ((long long) n_hot * tiles / tiles_all);
+            h[r] = want < keys ? want : keys;
+            left -= h[r];
+        }
+        for (int r = 0; r < R && left > 0; r++) {
+            const int keys = key_begin[r + 1] - key_begin[r];
+            const int add = keys - h[r] < left ? keys - h[r] : left;
+            h[r] += add;
+            left -= add;
+        }
+        base[0] = 0;
+        for (int r = 0; r < R; r++) base[r + 1] = base[r] + h[r];
+        for (int r = 0; r < R; r++) {
+            hot_range[3 * r] = key_begin[r];
+            hot_range[3 * r + 1] = h[r];
+            hot_range[3 * r + 2] = base[r];
+        }
+    }
+    __syncthreads();
+    for (int r = 0; r < R; r++)
+        for (int i = tid; i < h[r]; i += blockDim.x) {
+            hot_key[base[r] + i] = key_begin[r] + i;
+            khot[key_begin[r] + i] = (uint32_t) (base[r] + i);
+        }
+    /* slots no region could use (fewer keys than slots) keep pointing at key 0: the fill copies a valid row */
+    for (int i = base[R] + tid; i < n_hot; i += blockDim.x) hot_key[i] = 0;
+}
+__global__ void hfg_hot_rewrite_kernel(const uint32_t *wkeyT, const uint32_t *khot, size_t slots, uint32_t *wkeyH) {
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= slots) return;
+    const uint32_t w = wkeyT[i], slot = khot[HFG_KEY_ID(w)];
+    wkeyH[i] = slot == 0xffffffffu ? w : ((w & ~0x0fffffffu) | HFG3_HOT | slot);
+}
+__global__ void hfg_wpos_kernel(const int32_t *klist, int64_t n_list, const uint32_t *wslot, uint32_t *wposT) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_list) wposT[wslot[klist[i]]] = (uint32_t) i;
 }
 
 extern "C" const char *hfg_last_error(const hfg_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
@@ -165,18 +271,49 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     ctx->num_sms = prop.multiProcessorCount;
     const int G = total_gauss_comps(cfg);
     ctx->nb = nb;
-    ctx->threads = HFG_THREADS_MAX;
-    ctx->kernel = nb ? (const void *) hfg_estep_kernel<HFG_THREADS_MAX, true> : (const void *) hfg_estep_kernel<HFG_THREADS_MAX>;
-    ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg), ctx->threads);
-    /* HFG_THREADS=256: A/B switch, the 256-thread instantiation for every model (half the statistics area in shared memory,
-     * so twice the L1 for the key-table gathers, and no register spills; half the threads per SM) */
-    const int force_small = getenv("HFG_THREADS") && atoi(getenv("HFG_THREADS")) == HFG_THREADS_MIN;
-    if (force_small || ctx->smem_bytes > (size_t) optin) { /* many components / regions: halve the CTA, halving the statistics area */
-        ctx->threads = HFG_THREADS_MIN;
-        ctx->kernel = nb ? (const void *) hfg_estep_kernel<HFG_THREADS_MIN, true> : (const void *) hfg_estep_kernel<HFG_THREADS_MIN>;
+    /* HFG_KERNEL=v1: A/B switch, the first-generation kernel (one thread per segment, hfg_estep.cuh) */
+    ctx->quad = 3;
+    if (getenv("HFG_KERNEL") && strcmp(getenv("HFG_KERNEL"), "v1") == 0) ctx->quad = 0;
+    if (getenv("HFG_KERNEL") && strcmp(getenv("HFG_KERNEL"), "quad") == 0) ctx->quad = 2;
+    ctx->smem_optin = (size_t) optin;
+    if (ctx->quad == 3) {
+        ctx->threads = HFG3_THREADS;
+        ctx->kernel = nb ? (const void *) hfg_estep_v3_kernel<HFG3_THREADS, true> : (const void *) hfg_estep_v3_kernel<HFG3_THREADS>;
+        /* HFG_THREADS: A/B switch of the CTA size (fewer, longer segments: cheaper scans, fewer warps to hide latency) */
+        const int want = getenv("HFG_THREADS") ? atoi(getenv("HFG_THREADS")) : 0;
+        if (!nb && (want == 256 || want == 320 || want == 384 || want == 512 || want == 640)) {
+            ctx->threads = want;
+            ctx->kernel = want == 256 ? (const void *) hfg_estep_v3_kernel<256> : want == 320 ? (const void *) hfg_estep_v3_kernel<320>
+                          : want == 384 ? (const void *) hfg_estep_v3_kernel<384> : want == 512 ? (const void *) hfg_estep_v3_kernel<512>
+                                                                                                : (const void *) hfg_estep_v3_kernel<640>;
+        }
+        ctx->segs_per_cta = ctx->threads;
+        ctx->smem_bytes = (size_t) optin - 1024; /* (less static shared memory) the hot-key table takes whatever the rest leaves:
+                                                    sized per run in hfg_set_chunks */
+        if (smem_base_v3(cfg->n_regions, G, ctx->threads) + 16 * 1024 > (size_t) optin) {
+            fail(NULL, HFG_ERR_INVALID, "model too large for shared memory (%d regions x %d components)", cfg->n_regions, G);
+            free(ctx);
+            return HFG_ERR_INVALID;
+        }
+    } else if (ctx->quad == 2) {
+        ctx->threads = HFGQ_THREADS;
+        ctx->segs_per_cta = HFGQ_THREADS / 4;
+        ctx->kernel = nb ? (const void *) hfg_estep_quad_kernel<HFGQ_THREADS, true> : (const void *) hfg_estep_quad_kernel<HFGQ_THREADS>;
+        ctx->smem_bytes = smem_bytes_quad(cfg->n_regions, G, ctx->threads, HFGQ_LAB_SMAX); /* upper bound; per run in hfg_set_chunks */
+    } else {
+        ctx->threads = HFG_THREADS_MAX;
+        ctx->kernel = nb ? (const void *) hfg_estep_kernel<HFG_THREADS_MAX, true> : (const void *) hfg_estep_kernel<HFG_THREADS_MAX>;
         ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg), ctx->threads);
+        /* HFG_THREADS=256: the 256-thread instantiation for every model (half the statistics area in shared memory) */
+        const int force_small = getenv("HFG_THREADS") && atoi(getenv("HFG_THREADS")) == HFG_THREADS_MIN;
+        if (force_small || ctx->smem_bytes > (size_t) optin) { /* many components / regions: halve the CTA, halving the statistics area */
+            ctx->threads = HFG_THREADS_MIN;
+            ctx->kernel = nb ? (const void *) hfg_estep_kernel<HFG_THREADS_MIN, true> : (const void *) hfg_estep_kernel<HFG_THREADS_MIN>;
+            ctx->smem_bytes = smem_bytes_for(cfg->n_regions, G, max_tasks(cfg), ctx->threads);
+        }
+        ctx->segs_per_cta = ctx->threads;
     }
-    if (max_tasks(cfg) > HFG_MAX_TASKS) {
+    if (!ctx->quad && max_tasks(cfg) > HFG_MAX_TASKS) {
         fail(NULL, HFG_ERR_INVALID, "too many mixture components (%d component evaluations per window, limit %d)", max_tasks(cfg), HFG_MAX_TASKS);
         free(ctx);
         return HFG_ERR_INVALID;
@@ -330,8 +467,11 @@ static void free_device(hfg_ctx *ctx) {
     arena_release(ctx->h_out, ctx->h_out_bytes, ctx->device, 2);
     arena_release(ctx->h_labels, ctx->h_labels_bytes, ctx->device, 3);
     ctx->d_arena = NULL;
-    ctx->d_wkeyT = ctx->d_kdesc = NULL;
-    ctx->d_seg_start = ctx->d_seg_len = ctx->d_block_reset = ctx->d_err = NULL;
+    ctx->d_wkeyT = ctx->d_kdesc = ctx->d_wposT = ctx->d_wkeyH = ctx->d_khot = NULL;
+    ctx->d_hot_key = NULL;
+    ctx->d_scan_stash = NULL;
+    ctx->d_tabMT = NULL;
+    ctx->d_seg_start = ctx->d_seg_len = ctx->d_block_reset = ctx->d_err = ctx->d_ticket = NULL;
     ctx->d_klist = ctx->d_tile_key = ctx->d_tile_begin = ctx->d_tile_cnt = ctx->d_region_tile_begin = NULL;
     ctx->d_kbeta = ctx->d_tabM = ctx->d_scrFT = ctx->d_scrXB = ctx->d_block_tot = ctx->d_partials = NULL;
     ctx->d_out = ctx->d_seg_loglik = ctx->d_post = NULL;
@@ -435,14 +575,16 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
      * they save); HFG_MIN_WPT = minimum windows per thread before another CTA is added (default 1). */
     int wpt = 1;
     if (getenv("HFG_MIN_WPT")) wpt = atoi(getenv("HFG_MIN_WPT")) > 0 ? atoi(getenv("HFG_MIN_WPT")) : 1;
-    int64_t blocks = (W + (int64_t) ctx->threads * wpt - 1) / ((int64_t) ctx->threads * wpt);
+    const int spc = ctx->segs_per_cta;
+    int64_t blocks = (W + (int64_t) spc * wpt - 1) / ((int64_t) spc * wpt);
     if (blocks < 1) blocks = 1;
     if (blocks > ctx->max_blocks) blocks = ctx->max_blocks;
-    ctx->capacity_arg = (int32_t) blocks * ctx->threads;
+    ctx->capacity_arg = (int32_t) blocks * spc;
+    hfg_layout_tile_div = ctx->quad == 3 ? 4 : 1; /* v3: four lanes fold the statistics of a tile */
     int rc = hfg_layout_build_ex(&ctx->cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, ctx->capacity_arg,
-                                 ctx->threads, host_layout ? 0 : 1, &ctx->lay, ctx->err, sizeof(ctx->err));
+                                 spc, host_layout ? 0 : 1, &ctx->lay, ctx->err, sizeof(ctx->err));
     if (rc != HFG_OK) return rc;
-    ctx->grid = ctx->lay.capacity / ctx->threads;
+    ctx->grid = ctx->lay.capacity / spc;
     const int32_t cap = ctx->lay.capacity;
     tm[1] = wall_ms();
     hfg_layout *l = &ctx->lay;
@@ -454,7 +596,13 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     const size_t raw_bytes = 3 * hfgl::align256(2 * w) + hfgl::align256(w) + hfgl::align256(sizeof(hfg_chunk_desc) * (size_t) n_chunks) +
                              2 * hfgl::align256(4 * (size_t) n_chunks) + hfgl::align256(4 * (size_t) cap);
     const size_t build_bytes = host_layout ? 0 : raw_bytes + hfgl::temp_bytes(W, NULL);
-    const size_t scratch_bytes = hfgl::align256(slots * 4 * sizeof(double)) + hfgl::align256(w * 8 * sizeof(double));
+    /* forward scratch: segment-transposed [smax][4][capacity] (first generation) or window-major [W][4] (quad kernel) */
+    /* (v3: the scan stash of a thread, 32 doubles, lives in the thread's own column of the forward scratch, rows 0..31, and is
+     * consumed before the thread writes its first forward vector there: one buffer, 24 MB less to keep in L2) */
+    size_t ft_rows = (slots > w ? slots : w) * 4;
+    if (ctx->quad == 3 && ft_rows < (size_t) 32 * cap) ft_rows = (size_t) 32 * cap;
+    const size_t ft_bytes = hfgl::align256(ft_rows * sizeof(double));
+    const size_t scratch_bytes = ft_bytes + hfgl::align256(w * 8 * sizeof(double));
     const size_t max_tiles = w / HFG_TILE + w + 1;
     size_t o_scr = 0;
     /* one device allocation carved into the per-run buffers (cudaMalloc is the slow part of a short job) */
@@ -462,6 +610,11 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         size_t off = 0;
 #define CARVE(bytes) (off = (off + 255) & ~(size_t) 255, off += (bytes), off - (bytes))
         const size_t o_wk = CARVE(slots * sizeof(uint32_t));
+        const size_t o_wp = CARVE(slots * sizeof(uint32_t));
+        const size_t o_wh = CARVE(slots * sizeof(uint32_t));
+        const size_t o_hk = CARVE((size_t) (4096 + 3 * HFG_MAX_REGIONS + 1024) * sizeof(int32_t)); /* hot slots (more than any shared
+                                                                                                    memory holds), ranges, tile split */
+
         const size_t o_ss = CARVE(cap * sizeof(int32_t)), o_sl = CARVE(cap * sizeof(int32_t));
         const size_t o_kl = CARVE((w > 0 ? w : 1) * sizeof(int32_t));
         const size_t o_tk = CARVE(max_tiles * sizeof(int32_t)), o_tb = CARVE(max_tiles * sizeof(int32_t));
@@ -474,8 +627,8 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         const size_t o_out = CARVE(out_doubles * sizeof(double));
         const size_t o_ll = CARVE(cap * sizeof(double));
         const size_t o_lab = CARVE(w);
-        const size_t o_err = CARVE(sizeof(int32_t));
-        const size_t o_pc = CARVE((size_t) ctx->grid * HFG_PC_STRIDE * sizeof(long long));
+        const size_t o_err = CARVE(2 * sizeof(int32_t)); /* error flags, arrival ticket of the grid reduction */
+        const size_t o_pc = CARVE((size_t) (ctx->grid + 1) * HFG_PC_STRIDE * sizeof(long long));
         const size_t o_emp = CARVE(sizeof(hfg_region_params) * (size_t) R), o_ems = CARVE(4 * sizeof(int32_t));
         const size_t o_eml = CARVE(sizeof(double) * HFG_EM_LOGLIK_SLOTS);
 #undef CARVE
@@ -487,6 +640,10 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         if (timing) fprintf(stderr, "[hfg] arena %.1f MB; %lld windows\n", off / 1e6, (long long) W);
         char *base = (char *) ctx->d_arena;
         ctx->d_wkeyT = (uint32_t *) (base + o_wk);
+        ctx->d_wposT = (uint32_t *) (base + o_wp);
+        ctx->d_wkeyH = (uint32_t *) (base + o_wh);
+        ctx->d_hot_key = (int32_t *) (base + o_hk);
+        ctx->d_hot_range = ctx->d_hot_key + 4096;
         ctx->d_seg_start = (int32_t *) (base + o_ss);
         ctx->d_seg_len = (int32_t *) (base + o_sl);
         ctx->d_klist = (int32_t *) (base + o_kl);
@@ -495,7 +652,8 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         ctx->d_tile_cnt = (int32_t *) (base + o_tc);
         ctx->d_region_tile_begin = (int32_t *) (base + o_rt);
         ctx->d_scrFT = (double *) (base + o_scr);
-        ctx->d_scrXB = (double *) (base + o_scr + hfgl::align256(slots * 4 * sizeof(double)));
+        ctx->d_scan_stash = ctx->d_scrFT;
+        ctx->d_scrXB = (double *) (base + o_scr + ft_bytes);
         ctx->d_block_tot = (double *) (base + o_bt);
         ctx->d_block_reset = (int32_t *) (base + o_br);
         ctx->d_partials = (double *) (base + o_pa);
@@ -503,6 +661,7 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         ctx->d_seg_loglik = (double *) (base + o_ll);
         ctx->d_labels = (int8_t *) (base + o_lab);
         ctx->d_err = (int32_t *) (base + o_err);
+        ctx->d_ticket = ctx->d_err + 1;
         ctx->d_phase_clock = (long long *) (base + o_pc);
         ctx->d_em_params = (hfg_region_params *) (base + o_emp);
         ctx->d_em_state = (int32_t *) (base + o_ems);
@@ -519,13 +678,14 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
     CU(cudaMemcpyAsync(ctx->d_seg_start, l->seg_start, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_len, l->seg_len, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_labels, 0xff, w, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int32_t), ctx->stream)); /* every launch leaves the flags cleared */
+    CU(cudaMemsetAsync(ctx->d_err, 0, 2 * sizeof(int32_t), ctx->stream)); /* every launch leaves flags and ticket cleared */
 
     /* the key block: key table, key descriptors, betas -- sized by the number of keys */
     auto acquire_keyblock = [&](int32_t n_keys) -> int {
         const size_t P = (size_t) n_keys;
-        const size_t o_M = 0, o_kd = hfgl::align256(P * 16 * sizeof(double)), o_kb = o_kd + hfgl::align256(P * sizeof(uint32_t));
-        const size_t total = o_kb + hfgl::align256(P * 3 * sizeof(double));
+        const size_t o_M = 0, o_MT = hfgl::align256(P * 16 * sizeof(double)), o_kd = 2 * o_MT, o_kb = o_kd + hfgl::align256(P * sizeof(uint32_t));
+        const size_t o_kh = o_kb + hfgl::align256(P * 3 * sizeof(double));
+        const size_t total = o_kh + hfgl::align256(P * sizeof(uint32_t));
         ctx->d_keyblock = arena_acquire(total, ctx->device, &ctx->keyblock_bytes, 1);
         if (!ctx->d_keyblock) {
             cudaGetLastError();
@@ -533,8 +693,10 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         }
         char *kb = (char *) ctx->d_keyblock;
         ctx->d_tabM = (double *) (kb + o_M);
+        ctx->d_tabMT = (double *) (kb + o_MT);
         ctx->d_kdesc = (uint32_t *) (kb + o_kd);
         ctx->d_kbeta = (double *) (kb + o_kb);
+        ctx->d_khot = (uint32_t *) (kb + o_kh);
         return HFG_OK;
     };
 
@@ -618,6 +780,48 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
                 "%d tiles of <= %d windows\n", host_layout ? "host" : "device", host_layout ? " + keys" : "", tm[1] - tm[0],
                 tm[2] - tm[1], tm[3] - tm[2], host_layout ? "copies" : "device build", tm[4] - tm[3], l->n_keys, l->n_tiles,
                 l->tile_len);
+    if (ctx->quad >= 2) {
+        /* quad kernel: where every window's statistics record goes -- its position in the key lists -- stored like the key
+         * words (segment-transposed); two passes: window -> slot, list position -> slot.  The window -> slot map borrows the
+         * forward scratch. */
+        uint32_t *wslot = (uint32_t *) ctx->d_scrFT;
+        CU(cudaMemsetAsync(ctx->d_wposT, 0xff, slots * sizeof(uint32_t), ctx->stream));
+        hfg_wslot_kernel<<<(l->n_seg + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_seg_start, ctx->d_seg_len, l->n_seg, cap, wslot);
+        if (l->n_list > 0)
+            hfg_wpos_kernel<<<(unsigned) ((l->n_list + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_klist, l->n_list, wslot, ctx->d_wposT);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->launches += 2;
+        if (ctx->quad == 2) ctx->smem_bytes = smem_bytes_quad(R, G, ctx->threads, l->smax);
+    }
+    if (ctx->quad == 3) {
+        /* the shared-memory matrix table: labels are staged when a segment is short enough, the hot keys get the rest.  The
+         * slots go to the regions in proportion to their statistics tiles (~ windows), hottest keys first inside a region;
+         * the windows' key words are rewritten (into a copy) to carry the slot instead of the key id. */
+        const size_t base = smem_base_v3(R, G, ctx->threads);
+        ctx->lab_bytes = l->smax <= HFGQ_LAB_SMAX ? (int32_t) ((((size_t) ctx->threads * l->smax + 16) + 15) & ~(size_t) 15) : 0;
+        /* 1 KB: static shared memory, launch reserve; 16 KB are left to the L1 (prefetched cold matrices, key words) */
+        const size_t room = ctx->smem_optin - 1024 - 16384 - base - (size_t) ctx->lab_bytes;
+        int32_t hot_cap = (int32_t) (room / 128);
+        if (hot_cap > 4096) hot_cap = 4096;
+        if (getenv("HFG_HOT")) hot_cap = atoi(getenv("HFG_HOT")) < hot_cap ? atoi(getenv("HFG_HOT")) : hot_cap; /* A/B: smaller table */
+        ctx->n_hot = hot_cap < l->n_keys ? hot_cap : l->n_keys;
+        ctx->smem_bytes = base + (size_t) ctx->lab_bytes + (size_t) ctx->n_hot * 128;
+        {
+            /* the M-step of the device-resident loop works on shared-memory copies behind the region tables */
+            const size_t need = ((((size_t) R * QRT_STRIDE(G) + 1) & ~(size_t) 1) * sizeof(double)) + mstep_work_bytes(ctx->threads, 1);
+            if (ctx->smem_bytes < need) ctx->smem_bytes = need;
+        }
+        CU(cudaMemsetAsync(ctx->d_khot, 0xff, (size_t) l->n_keys * sizeof(uint32_t), ctx->stream));
+        hfg_hot_assign_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_kdesc, l->n_keys, ctx->d_region_tile_begin, R, ctx->n_hot,
+                                                            ctx->d_hot_key, ctx->d_khot, ctx->d_hot_range);
+        hfg_hot_rewrite_kernel<<<(unsigned) ((slots + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_wkeyT, ctx->d_khot, slots, ctx->d_wkeyH);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->launches += 2;
+        if (timing) fprintf(stderr, "[hfg] v3: %d of %d keys in shared memory (%zu bytes), %d bytes of staged labels\n", ctx->n_hot,
+                            l->n_keys, (size_t) ctx->n_hot * 128, ctx->lab_bytes);
+    }
     if (ctx->nb) {
         /* per-tile pair masses come back to the host, which folds them into the (region, state, x) histogram: it needs
          * every tile's key and every key's observation word */
@@ -731,6 +935,20 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     a.n_windows = l->n_windows;
     a.posteriors = post_dev;
     a.err_flags = ctx->d_err;
+    a.ticket = ctx->d_ticket;
+    a.dbg = getenv("HFG_DBG") ? atoi(getenv("HFG_DBG")) : 0;
+    a.tabMT = ctx->d_tabMT;
+    a.wposT = ctx->d_wposT;
+    if (ctx->quad >= 2)
+        a.work_doubles = (int32_t) (ctx->smem_bytes / sizeof(double) - ((((size_t) R * QRT_STRIDE(total_gauss_comps(cfg)) + 1) & ~(size_t) 1)));
+    if (ctx->quad == 3) {
+        a.wkeyT = ctx->d_wkeyH;
+        a.hot_key = ctx->d_hot_key;
+        a.hot_range = ctx->d_hot_range;
+        a.n_hot = ctx->n_hot;
+        a.lab_bytes = ctx->lab_bytes;
+        a.scan_stash = ctx->d_scan_stash;
+    }
     a.forward_only = forward_only;
     a.phase_clock = ctx->d_phase_clock;
     a.out_doubles = R * STATS_DOUBLES + 2;
@@ -1280,7 +1498,7 @@ extern "C" int hfg_debug_phase_clocks(hfg_ctx *ctx, long long *out, int *grid) {
     if (!ctx || !out || !grid || !ctx->have_chunks) return HFG_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(out, ctx->d_phase_clock, (size_t) ctx->grid * HFG_PC_STRIDE * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out, ctx->d_phase_clock, (size_t) (ctx->grid + 1) * HFG_PC_STRIDE * sizeof(long long), cudaMemcpyDeviceToHost));
     *grid = ctx->grid;
     return HFG_OK;
 }
@@ -1320,8 +1538,9 @@ extern "C" int hfg_debug_layout_compare(hfg_ctx *ctx, int32_t n_chunks, const hf
     CU(cudaDeviceSynchronize());
     hfg_layout h;
     char err[256];
+    hfg_layout_tile_div = ctx->quad == 3 ? 4 : 1;
     int rc = hfg_layout_build_ex(&ctx->cfg, n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region, ctx->capacity_arg,
-                                 ctx->threads, 0, &h, err, sizeof(err));
+                                 ctx->segs_per_cta, 0, &h, err, sizeof(err));
     if (rc != HFG_OK) return fail(ctx, rc, "host layout build failed: %s", err);
     const hfg_layout *d = &ctx->lay;
     const char *bad = NULL;

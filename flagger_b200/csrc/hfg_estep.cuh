@@ -73,7 +73,7 @@ namespace cg = cooperative_groups;
 #define RT_GAUSS 156
 #define HFG_INV_TERM 1e4 /* 1 / terminationProb */
 #define HFG_MAX_PEERS 8
-#define HFG_PC_STRIDE 12 /* phase-clock slots per block */
+#define HFG_PC_STRIDE 16 /* phase-clock slots per block */
 #define HFG_MAX_TASKS 160
 /* per-(region, task) table after the Gaussian arrays: (1-a)*mu, a, 1/(var*beta0), w/sqrt(var*beta0*2*PI) */
 #define RT_TASK(G) (RT_GAUSS + 6 * (G))
@@ -146,6 +146,17 @@ struct EstepArgs {
     double *em_logliks;           /* log-likelihood of every E-step run */
     /* negative-binomial instantiation only (hfg_estep_kernel<THREADS, true>; NOT YET VALIDATED ON HARDWARE, DESIGN.md
      * section 7).  Appended last so that the offsets the other instantiations read do not move. */
+    int32_t *ticket;        /* quad kernel: arrival counter of the grid reduction (zero between launches) */
+    double *tabMT;          /* quad kernel: [n_keys][16] the transposed transfer matrices (row s = column s of tabM) */
+    const uint32_t *wposT;  /* quad kernel: [smax][capacity] position of the window in the key lists (klist), or 0xffffffff */
+    /* third-generation kernel (hfg_estep_v3.cuh) */
+    const int32_t *hot_key; /* [n_hot] key id of every slot of the shared-memory matrix table */
+    int32_t n_hot;          /* slots in use */
+    const int32_t *hot_range; /* [n_regions][3] first hot key of the region, number of hot keys, first slot */
+    int32_t lab_bytes;      /* bytes of shared memory for the staged labels (multiple of 16; 0: labels go straight to global memory) */
+    double *scan_stash;     /* [32][capacity] exclusive prefix / suffix product of every thread inside its warp */
+    int32_t dbg;            /* instrumentation switch (HFG_DBG) */
+    int32_t work_doubles;   /* doubles of shared memory behind the region tables (the M-step work area of the kernel tail) */
     const double *nb_table; /* [R][4][HFG_NB_XSTRIDE] pmf of (region, state, x), evaluated on the host (hfg_nb.c) */
     double *nb_tile_col;    /* [n_tiles][4] pair mass of every statistics tile by state: the host folds it into the
                                (region, state, x) histogram the model's estimators are fed from */

@@ -97,6 +97,10 @@ int hfg_layout_build_ex(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk
                         const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region,
                         int32_t capacity, int32_t granule, int segments_only, hfg_layout *out, char *err, size_t errlen);
 void hfg_layout_free(hfg_layout *l);
+/* Segment slots per statistics worker: the tile length is the shortest one that leaves every WORKER at most one tile
+ * (1: a worker per slot; 4: the E-step kernel folds the statistics with four lanes per tile).  Process-wide; every context
+ * uses the same kernel generation, so the same value. */
+extern int32_t hfg_layout_tile_div;
 
 /* EM_computeAdjustmentBeta (hmm.c:301-316) for window i of a chunk. */
 double hfg_beta(const hfg_config *cfg, const hfg_chunk_desc *ch, int i);

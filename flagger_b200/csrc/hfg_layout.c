@@ -68,6 +68,9 @@ typedef struct Run {
     int32_t len;
 } Run;
 
+/* segment slots per statistics worker (the E-step kernel's threads per tile worker; set by hfg_api.cu before a build) */
+int32_t hfg_layout_tile_div = 1;
+
 static int64_t segments_for(const Run *runs, int64_t n_runs, int smax) {
     int64_t n = 0;
     for (int64_t i = 0; i < n_runs; i++) n += (runs[i].len + smax - 1) / smax;
@@ -411,11 +414,12 @@ static int build_keys(hfg_layout *out) {
     /* tile length: HFG_TILE, or the shortest one for which every thread of the grid gets at most ONE tile (a block whose
      * share is a few tiles over its thread count would spend a second round on them) */
     int tile_len = HFG_TILE;
+    const int tile_workers = capacity / (hfg_layout_tile_div > 0 ? hfg_layout_tile_div : 1);
     for (;; tile_len++) {
         n_tiles = 0;
         for (int32_t p = 0; p < P; p++)
             if (key_has_stats(out->kdesc[p])) n_tiles += (order[p].count + tile_len - 1) / tile_len;
-        if (n_tiles <= (int64_t) capacity - capacity / 16 || tile_len >= 4 * HFG_TILE) break;
+        if (n_tiles <= (int64_t) tile_workers - tile_workers / 16 || tile_len >= 4 * HFG_TILE) break;
     }
     kbegin[P] = (int32_t) n_list;
     out->n_keys = P;
@@ -581,6 +585,15 @@ int hfg_layout_build_ex(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk
     /* smallest smax whose segment count fits the persistent grid */
     int smax = (int) ((W + capacity - 1) / capacity);
     if (smax < 1) smax = 1;
+    if (n_runs > capacity) {
+        /* a segment never straddles a chunk boundary or a region change, so there are at least n_runs of them whatever
+         * their length: no smax can fit */
+        free(runs); free(edge_head); free(edge_tail); free(chunk_edge_base);
+        hfg_layout_free(out);
+        snprintf(err, errlen, "%lld runs of equal region index (chunk boundaries included) exceed the %d segment slots of the grid",
+                 (long long) n_runs, capacity);
+        return HFG_ERR_INVALID;
+    }
     while (segments_for(runs, n_runs, smax) > capacity) smax += (smax + 7) / 8;
     const int64_t n_seg = segments_for(runs, n_runs, smax);
     /* keep only as many slots (whole CTAs of `granule` threads) as the segments of this length need: a grid padded with

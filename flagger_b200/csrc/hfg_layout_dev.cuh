@@ -350,7 +350,7 @@ static cudaError_t layout_build_device_lists(const DeviceLayoutTemp *t, double b
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
     /* tile length: HFG_TILE, or the shortest one that leaves every thread of the grid at most one tile (hfg_layout.c) */
     int tile_len = HFG_TILE;
-    const long long capacity = t->capacity;
+    const long long capacity = t->capacity / (hfg_layout_tile_div > 0 ? hfg_layout_tile_div : 1); /* statistics workers */
     while (!((long long) h_tiles[tile_len - HFG_TILE] <= capacity - capacity / 16 || tile_len >= 4 * HFG_TILE)) tile_len++;
     const int32_t NT = (int32_t) h_tiles[tile_len - HFG_TILE];
 
