@@ -182,9 +182,10 @@ __device__ __forceinline__ double gauss_state_prob(const double *rt, int G, int 
  * threads (a power of two >= 32): the point evaluated at a step depends only on the outcomes of the comparisons so far, so the
  * 2 + 4 + ... + 2^D candidate points of the next D steps (D = 8 for 512 threads) are evaluated one per thread, and every
  * thread then walks the true path through the group's buffer `fb` (gsize doubles): ~5 rounds instead of ~34 dependent
- * objective evaluations, the same bits as the serial routine.  EVERY thread of the CTA must call it (it synchronises the CTA);
- * groups with active == false only take part in the barriers.  `st8` = 8 doubles of group scratch. */
-__device__ __forceinline__ double hfg_fit_rate_cta(bool active, int gtid, int gsize, double trunc, double sum_x, double sum_w,
+ * objective evaluations, the same bits as the serial routine.  The group synchronises on its own named barrier `bar` (1..15):
+ * all gsize threads of the group must call it, other groups and warps are not involved.  `st8` = 8 doubles of group scratch. */
+__device__ __forceinline__ void group_sync(int bar, int n) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory"); }
+__device__ __forceinline__ double hfg_fit_rate_cta(bool active, int gtid, int gsize, int bar, double trunc, double sum_x, double sum_w,
                                                    double *st8, double *fb) {
     const double inv_phi = (sqrt(5.0) - 1.0) / 2.0, inv_phi2 = (3.0 - sqrt(5.0)) / 2.0;
     int D = 0;
@@ -199,7 +200,7 @@ __device__ __forceinline__ double hfg_fit_rate_cta(bool active, int gtid, int gs
         total = steps - 1;
         if (gtid < 2) st8[gtid] = hfg_trunc_exp_objective(gtid == 0 ? x1 : x2, trunc, sum_x, sum_w);
     }
-    __syncthreads();
+    group_sync(bar, gsize);
     if (active) {
         y1 = st8[0];
         y2 = st8[1];
@@ -209,7 +210,8 @@ __device__ __forceinline__ double hfg_fit_rate_cta(bool active, int gtid, int gs
     while ((4 << my_t) - 2 <= gtid) my_t++;
     const int my_bits = gtid - ((2 << my_t) - 2);
     int k = 0;
-    while (__syncthreads_or(active && k < total)) {
+    /* (active, total and k are the same in every thread of the group: uniform loop) */
+    while (active && k < total) {
         const int d = total - k < D ? total - k : D;
         if (active && k < total && my_t < d) {
             /* positions along this node's assumed path (the arithmetic of the serial loop, same order) */
@@ -230,7 +232,7 @@ __device__ __forceinline__ double hfg_fit_rate_cta(bool active, int gtid, int gs
             }
             fb[gtid] = hfg_trunc_exp_objective(xnew, trunc, sum_x, sum_w);
         }
-        __syncthreads();
+        group_sync(bar, gsize);
         if (active && k < total) {
             /* the true path */
             int path = 0;
@@ -251,9 +253,91 @@ __device__ __forceinline__ double hfg_fit_rate_cta(bool active, int gtid, int gs
             }
             k += d;
         }
+        group_sync(bar, gsize); /* the buffer is read before the next round writes it */
     }
     if (active) result = y1 > y2 ? (lo + x2) / 2.0 : (x1 + hi) / 2.0;
     return result;
+}
+
+/* hfg_mstep_gauss / hfg_mstep_trans (hfg_mstep_inl.h) for one WARP: one lane per mixture component / transition entry.  The
+ * pooled sums are added in the serial routine's order (state, then component, ascending) and every division is the serial
+ * routine's division, so the parameters come out with the same bits; what runs side by side are the divisions and the
+ * convergence tests (a single thread needs ~20 000 cycles for them, a chain of ~100 dependent double-precision divisions).
+ * `scr` = 128 doubles of warp-private shared memory.  Return value as the serial routines, identical in every lane. */
+__device__ __forceinline__ int hfg_mstep_gauss_warp(int model_type, const int32_t *n_comps, hfg_region_params *p,
+                                                    const hfg_region_stats *st, double tol, double *scr, int lane) {
+    int ok = 1, G = 0, gs[2] = {0, 0}, gc[2] = {0, 0};
+    /* the lane's components: g = lane and lane + 32 of the list (state ascending, component ascending) */
+    for (int s = 0; s < HFG_NS; s++) {
+        if (!hfg_is_gaussian_state(model_type, s)) continue;
+        for (int u = 0; u < 2; u++) {
+            const int g = lane + 32 * u;
+            if (g >= G && g < G + n_comps[s]) {
+                gs[u] = s;
+                gc[u] = g - G;
+            }
+        }
+        G += n_comps[s];
+    }
+    for (int which = 0; which < 2; which++) {
+        const double (*num)[HFG_MAX_COMPS] = which == 0 ? st->mean_num : st->var_num;
+        const double (*den)[HFG_MAX_COMPS] = which == 0 ? st->mean_den : st->var_den;
+        double (*dst)[HFG_MAX_COMPS] = which == 0 ? p->mean : p->var;
+        for (int u = 0; u < 2; u++) {
+            const int g = lane + 32 * u;
+            if (g < G) {
+                scr[g] = num[gs[u]][gc[u]] / hfg_binding(gs[u], gc[u]);
+                scr[64 + g] = den[gs[u]][gc[u]];
+            }
+        }
+        __syncwarp();
+        double pooled_num = 0.0, pooled_den = 0.0;
+        for (int g = 0; g < G; g++) {
+            pooled_num += scr[g];
+            pooled_den += scr[64 + g];
+        }
+        __syncwarp();
+        if (!(MIN_COUNT_FOR_UPDATE < pooled_den)) continue; /* hmm_utils.c:1846 */
+        const double unit = pooled_num / pooled_den;
+        for (int u = 0; u < 2; u++) {
+            const int g = lane + 32 * u;
+            if (g < G) {
+                const double v = unit * hfg_binding(gs[u], gc[u]);
+                ok &= hfg_settled(dst[gs[u]][gc[u]], v, tol, 1.0e-4);
+                dst[gs[u]][gc[u]] = v;
+            }
+        }
+    }
+    /* mixture weights: unbound, each component from its own estimator */
+    for (int u = 0; u < 2; u++) {
+        const int g = lane + 32 * u;
+        if (g < G) {
+            const double d = st->weight_den[gs[u]][gc[u]];
+            if (MIN_COUNT_FOR_UPDATE < d) {
+                const double v = st->weight_num[gs[u]][gc[u]] / d;
+                ok &= hfg_settled(p->weight[gs[u]][gc[u]], v, tol, 1.0e-4);
+                p->weight[gs[u]][gc[u]] = v;
+            }
+        }
+    }
+    __syncwarp();
+    return __all_sync(0xffffffffu, ok);
+}
+__device__ __forceinline__ int hfg_mstep_trans_warp(hfg_region_params *p, const hfg_region_stats *st, double tol, int lane) {
+    int ok = 1;
+    if (lane < HFG_NS * HFG_NS) {
+        const int a = lane >> 2, b = lane & 3;
+        double row = 0.0;
+        for (int i = 0; i < HFG_NS; i++) row += st->trans_count[a][i] + PSEUDO_COUNT;
+        const double v = (st->trans_count[a][b] + PSEUDO_COUNT) / row * (1.0 - HFG_TERM_PROB);
+        ok &= hfg_settled(p->trans[a][b], v, tol, 1.0e-6);
+        p->trans[a][b] = v;
+        if (b == 0) p->trans[a][HFG_NS] = HFG_TERM_PROB;
+        if (a == 0) p->trans[HFG_NS][b] = 1.0 / HFG_NS;
+        if (lane == 0) p->trans[HFG_NS][HFG_NS] = 0.0;
+    }
+    __syncwarp();
+    return __all_sync(0xffffffffu, ok);
 }
 
 /* Phase D, shared by the kernel generations that end in per-CTA partials [R][NSTAT][grid]: the last CTA to arrive (atomic
@@ -413,46 +497,51 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
                  * follows the new Hap mean afterwards. */
                 constexpr int PD = (int) (sizeof(hfg_region_params) / sizeof(double));
                 const int per_region = PD + SD + 8;
-                int RB = (A.work_doubles - THREADS) / per_region;
+                constexpr int FIT_THREADS = THREADS / 2 >= 256 ? THREADS / 2 : THREADS - 64; /* the rest runs the other updates */
+                int RB = (A.work_doubles - THREADS - WARPS * 128) / per_region;
                 RB = RB < 1 ? 1 : (RB > R ? R : RB);
-                if (RB > THREADS / 32) RB = THREADS / 32;
+                if (RB > FIT_THREADS / 32) RB = FIT_THREADS / 32;
+                if (RB > 15) RB = 15; /* named barriers 1..15 */
                 for (int r0 = 0; r0 < R; r0 += RB) {
                     const int nb = min(RB, R - r0);
+                    double *mscr = work + (size_t) nb * per_region; /* [WARPS][128] warp scratch, then the exchange buffers */
                     for (int i = tid; i < nb * PD; i += THREADS)
                         work[(size_t) (i / PD) * per_region + i % PD] = reinterpret_cast<const double *>(&A.em_params[r0])[i];
                     for (int i = tid; i < nb * SD; i += THREADS) work[(size_t) (i / SD) * per_region + PD + i % SD] = A.out[(size_t) r0 * SD + i];
                     __syncthreads();
                     if (tid == 0) tail_clock[8] = clock64();
-                    for (int task = warp; task < 2 * nb; task += WARPS) {
-                        double *mp = work + (size_t) (task >> 1) * per_region;
-                        hfg_region_params *p = reinterpret_cast<hfg_region_params *>(mp);
-                        const hfg_region_stats *st = reinterpret_cast<const hfg_region_stats *>(mp + PD);
-                        if (task & 1) settled &= hfg_mstep_trans(p, st, A.em_tol);
-                        else settled &= hfg_mstep_gauss(A.model_type, A.ncomp, p, st, A.em_tol);
-                    }
-                    if (tid == 0) tail_clock[9] = clock64();
-                    {
-                        int gsize = 32;
-                        while (gsize * 2 * nb <= THREADS) gsize *= 2;
+                    /* the rate fits of the batch on the first fit_threads threads (one power-of-two group each, own named
+                     * barrier), the Gaussian / transition updates on the remaining warps, side by side */
+                    int gsize = 32;
+                    while (gsize * 2 * nb <= FIT_THREADS) gsize *= 2;
+                    if (tid < nb * gsize) {
                         const int g = tid / gsize, gtid = tid % gsize;
-                        const bool mine = g < nb;
-                        double *mp = work + (size_t) (mine ? g : 0) * per_region;
+                        double *mp = work + (size_t) g * per_region;
                         hfg_region_params *p = reinterpret_cast<hfg_region_params *>(mp);
                         const hfg_region_stats *st = reinterpret_cast<const hfg_region_stats *>(mp + PD);
                         /* TruncExponential: golden-section fit against the truncation point still in force (hmm_utils.c:1872-1882) */
-                        const bool fit = mine && A.model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && MIN_COUNT_FOR_UPDATE < st->lambda_den;
+                        const bool fit = A.model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && MIN_COUNT_FOR_UPDATE < st->lambda_den;
                         const double trunc = p->trunc_point, sx = st->lambda_num, sw = st->lambda_den, old = p->lambda;
-                        double *fb = work + (size_t) nb * per_region + (size_t) g * (gsize < THREADS ? gsize : THREADS); /* the group's exchange buffer */
-                        const double v = hfg_fit_rate_cta(fit, gtid, gsize, trunc, sx, sw, mp + PD + SD, fb);
-                        if (tid == 0) tail_clock[10] = clock64();
-                        /* (the fit ends with a CTA barrier: the Gaussian / transition warps are done as well) */
+                        const double v = hfg_fit_rate_cta(fit, gtid, gsize, 1 + g, trunc, sx, sw, mp + PD + SD, mscr + WARPS * 128 + (size_t) g * gsize);
                         if (fit) {
                             settled &= hfg_settled(old, v, A.em_tol, 1.0e-4);
                             if (gtid == 0) p->lambda = v;
                         }
-                        /* the truncation point follows the NEW Hap mean, after the fit used the old one */
-                        if (mine && gtid == 0 && A.model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN)
-                            p->trunc_point = p->mean[HFG_STATE_HAP][0] * TRUNC_POINT_FRACTION;
+                    } else if (tid >= FIT_THREADS) {
+                        for (int task = warp - FIT_THREADS / 32; task < 2 * nb; task += WARPS - FIT_THREADS / 32) {
+                            double *mp = work + (size_t) (task >> 1) * per_region;
+                            hfg_region_params *p = reinterpret_cast<hfg_region_params *>(mp);
+                            const hfg_region_stats *st = reinterpret_cast<const hfg_region_stats *>(mp + PD);
+                            if (task & 1) settled &= hfg_mstep_trans_warp(p, st, A.em_tol, lane);
+                            else settled &= hfg_mstep_gauss_warp(A.model_type, A.ncomp, p, st, A.em_tol, mscr + (size_t) warp * 128, lane);
+                        }
+                    }
+                    if (tid == 0) tail_clock[10] = clock64();
+                    __syncthreads();
+                    /* the truncation point follows the NEW Hap mean, after the fit used the old one */
+                    if (tid < nb && A.model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN) {
+                        hfg_region_params *p = reinterpret_cast<hfg_region_params *>(work + (size_t) tid * per_region);
+                        p->trunc_point = p->mean[HFG_STATE_HAP][0] * TRUNC_POINT_FRACTION;
                     }
                     __syncthreads();
                     for (int i = tid; i < nb * PD; i += THREADS)
