@@ -44,9 +44,11 @@ def parse_args():
     ap.add_argument("--total-bp", type=float, default=3e9)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = 3 Gbp PER GPU (an N x 3 Gbp assembly, chunks sharded over the ranks, one model); strong = "
-                         "the 3 Gbp workload itself sharded over the ranks (BASELINE.json configs[4])")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong (default) = the 3 Gbp workload itself sharded over the ranks (BASELINE.json configs[4]); "
+                         "weak = 3 Gbp PER GPU (an N x 3 Gbp assembly, chunks sharded over the ranks, one model).  A strong run "
+                         "also reports the weak figure as the extra key `weak`")
+    ap.add_argument("--no-binary", action="store_true", help="skip the whole-binary end-to-end leg (e2e_binary)")
     ap.add_argument("--allreduce", default="fused", choices=["fused", "nccl"],
                     help="N > 1: sum of the EM statistics over ranks inside the E-step kernel through peer memory "
                          "(fused, default) or with one NCCL all-reduce per iteration after it (nccl)")
@@ -202,12 +204,24 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def model_setup(wl):
-    from flagger_b200 import _abi, api, synth
-    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+def model_setup(wl, checker=None):
+    """Configuration and initial model of a workload.  `checker` (an oracle_lib checker: the reference build or the
+    restatement) serves the reference arm, which must not load the product library; the product arm uses libhfg's own
+    host mirrors (the two agree bit for bit, tests/test_oracle_golden.py)."""
+    from flagger_b200 import _abi, synth
+    if checker is None:
+        from flagger_b200 import api as checker
+    K = checker.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
     cfg = _abi.make_config(n_regions=wl.n_regions, n_col_comps=K, mean_read_length=wl.avg_alignment_len)
-    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    params = checker.model_init(cfg, wl.region_coverages, wl.window_len)
     return cfg, params, synth.HIFI_ALPHA.copy(), K
+
+
+def workload_config(wl, K):
+    """The `config` object of the JSON line: the same keys in both arms."""
+    return {"workload": wl.name, "windows": wl.n_windows, "chunks": wl.n_chunks, "regions": wl.n_regions, "col_components": K,
+            "window_len": wl.window_len, "alpha": "HiFi_DC_1.2",
+            "step": "one EM iteration = E-step of all chunks (fwd+bwd+statistics+labels) + M-step"}
 
 
 def time_cpu(cfg, wl, alpha, params, steps, warmup, budget_s=90.0):
@@ -260,22 +274,83 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
     wl = make_workload(args.workload, args.total_bp * (max(args.gpus, 1) if args.scaling == "weak" else 1))
-    cfg, params, alpha, K = model_setup(wl)
+    checker = oracle_lib.reference(threads=host_threads()) or oracle_lib.oracle()  # never the product library
+    cfg, params, alpha, K = model_setup(wl, checker)
     cpu, sample = time_cpu(cfg, wl, alpha, params, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": "HMM windows/sec (EM iter + Viterbi), 3 Gbp @40x w=4000; achieved HBM GB/s",
         "value": cpu["value"], "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl.name, "windows": wl.n_windows, "chunks": wl.n_chunks, "regions": wl.n_regions,
-                   "col_components": K, "window_len": wl.window_len, "sample_windows": sample.n_windows,
-                   "note": "CPU reference path; windows/s is size-independent (per-window cost is constant)"},
+        "config": workload_config(wl, K),
+        "notes": {"sample_windows": sample.n_windows,
+                  "note": "CPU reference path on a bounded sample; windows/s is size-independent (per-window cost is constant)"},
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cpu["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # shared objects of this repository mapped into the process: the checker's only, never the product library
+        "native_libs": sorted({os.path.relpath(ln.split()[-1], ROOT) for ln in open("/proc/self/maps")
+                               if ln.rstrip().endswith(".so") and ln.split()[-1].startswith(ROOT)}),
     }
     _RESULT_LINE.append(json.dumps(line))
+
+
+def binary_e2e(wl, alpha, steps, cores):
+    """Whole-binary end to end: the stand-alone hmm_flagger_b200 and, beside it, the unmodified reference binary
+    (oracle/_ref/hmm_flagger_ref, -@ all host threads) on the same .bin input, `steps - 1` EM iterations + final inference,
+    timed from process start to exit.  Returns a dict for the JSON line (or None when the product binary is missing)."""
+    import re
+    import shutil
+    import tempfile
+    from flagger_b200 import binfmt
+    ours = os.path.join(ROOT, "flagger_b200", "hmm_flagger_b200")
+    ref = os.path.join(ROOT, "oracle", "_ref", "hmm_flagger_ref")
+    if not os.path.exists(ours):
+        return None
+    tmp = tempfile.mkdtemp(prefix="hfg_bench_")
+    try:
+        inp, atsv = os.path.join(tmp, "in.bin"), os.path.join(tmp, "alpha.tsv")
+        binfmt.write_bin(wl, inp)
+        binfmt.write_alpha_tsv(alpha, atsv)
+        out = {"input": f"{wl.name} as .bin ({os.path.getsize(inp) >> 20} MiB)",
+               "command": f"-i in.bin -o out -A alpha.tsv -n {steps - 1} -t 1e-12 -@ {cores}"}
+
+        def one(binary, tag, repeats):
+            best = None
+            for rep in range(repeats):
+                odir = os.path.join(tmp, f"out_{tag}_{rep}")
+                os.makedirs(odir)
+                t0 = time.perf_counter()
+                r = subprocess.run([binary, "-i", inp, "-o", odir, "-A", atsv, "-n", str(steps - 1), "-t", "1e-12", "-@", str(cores)],
+                                   capture_output=True, text=True)
+                wall = time.perf_counter() - t0
+                if r.returncode != 0:
+                    return {"error": r.stderr[-300:]}
+                m = re.search(r"Real time:\s+([0-9.]+) sec", r.stderr)
+                ph = re.search(r"Phases: read ([0-9.]+) s; GPU set-up ([0-9.]+) s; EM ([0-9.]+) s; summary tables ([0-9.]+) s; BED ([0-9.]+) s", r.stderr)
+                rec = {"wall_s": wall, "real_time_line_s": float(m.group(1)) if m else None}
+                if ph:
+                    rec["phases_s"] = dict(zip(("read", "gpu_setup", "em", "summary_tables", "bed"), map(float, ph.groups())))
+                rec["bed"] = open(os.path.join(odir, "final_flagger_prediction.bed"), "rb").read()
+                if best is None or wall < best["wall_s"]:
+                    best = rec
+            return best
+
+        o = one(ours, "ours", 3)  # the first process pays CUDA context creation on a cold driver: best of three
+        out["hmm_flagger_b200"] = {k: v for k, v in o.items() if k != "bed"}
+        if os.path.exists(ref) and "error" not in o:
+            rr = one(ref, "ref", 1)
+            out["hmm_flagger_ref"] = {k: v for k, v in rr.items() if k != "bed"}
+            if "error" not in rr:
+                out["bed_identical"] = rr["bed"] == o["bed"]
+                out["speedup_wall"] = rr["wall_s"] / o["wall_s"]
+        out["windows_per_s"] = wl.n_windows * steps / o["wall_s"] if "error" not in o else None
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def run_ours(args):
@@ -355,6 +430,8 @@ def run_ours(args):
         for _ in range(args.steps):
             if flush is not None:
                 gpu.l2_flush(256 << 20)  # 256 MiB > 126 MB L2: evicts the working set; outside the timed intervals
+            if fused:
+                gpu.peer_barrier()  # device-side rendezvous: every rank's timed interval starts together
             gpu.em_enqueue()
         barrier()
         params, ll_all, _, _ = gpu.em_finish(want_labels=False)
@@ -457,6 +534,65 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- multi-GPU: parity of the sharded run, cost of the exchange, the weak-scaling figure -------------------------------
+    parity = exchange = weak = None
+    if world > 1:
+        # one E-step with the initial parameters: (i) the in-kernel all-reduce against per-rank sums added by NCCL,
+        # (ii) every rank's labels against a single-GPU run of the whole workload on rank 0
+        st_f, ll_f, lab = gpu.em_iteration(alpha, params0)
+        g_local = api.HmmFlaggerGPU(cfg, wl)  # same shard, not connected to the peers
+        st_l, ll_l, _ = g_local.em_iteration(alpha, params0)
+        g_local.close()
+        t = torch.from_numpy(np.concatenate([_abi.stats_as_flat(st_l).ravel(), [ll_l]])).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        nccl_sum = t.cpu().numpy()
+        mine = np.concatenate([_abi.stats_as_flat(st_f).ravel(), [ll_f]]) if fused else nccl_sum
+        rel = float(np.max(np.abs(mine - nccl_sum)) / np.max(np.abs(nccl_sum)))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, lab.tobytes())
+        if rank == 0:
+            g_full = api.HmmFlaggerGPU(cfg, wl_full)
+            st_1, ll_1, lab_1 = g_full.em_iteration(alpha, params0)
+            g_full.close()
+            lab_all = np.frombuffer(b"".join(gathered), np.int8)
+            one = np.concatenate([_abi.stats_as_flat(st_1).ravel(), [ll_1]])
+            parity = {"fused_vs_nccl_max_rel": rel, "label_mismatches_vs_single_gpu": int((lab_all != lab_1).sum()),
+                      "stats_vs_single_gpu_max_rel": float(np.max(np.abs(mine - one)) / np.max(np.abs(one))),
+                      "windows": int(lab_1.size), "ok": bool(rel <= 1e-12 and np.array_equal(lab_all, lab_1))}
+        if fused:
+            # the in-kernel exchange of the last timed iteration, from the kernel's own clocks (tail row: 3 = first store into
+            # the peers' mailboxes, 4 = all N vectors summed): what the all-reduce costs this rank, waiting included
+            tail = gpu.debug_phase_clocks()[-1]
+            ex = torch.tensor([float(tail[4] - tail[3]) / 1.965e3], dtype=torch.float64, device=dev)  # microseconds at 1965 MHz
+            exs = [torch.zeros_like(ex) for _ in range(world)]
+            dist.all_gather(exs, ex)
+            exchange = {"per_rank_us": [round(float(e.item()), 2) for e in exs], "note": "in-kernel all-reduce of the last "
+                        "iteration, kernel clocks at 1965 MHz: stores to the peers + wait for their vectors + sum"}
+        if args.scaling == "strong":
+            # the same loop on an N x 3 Gbp assembly (3 Gbp per GPU): the weak-scaling figure, 20 timed iterations
+            wl_w = shard_chunks(make_workload(args.workload, args.total_bp * world), rank, world)
+            gw = api.HmmFlaggerGPU(cfg, wl_w)
+            if fused:
+                gw.peer_connect(dist)
+            ws, ww = min(20, args.steps), 3
+            gw.em_begin(alpha, params0, tol=1e-12, max_esteps=ws + ww)
+            for i in range(ws + ww):
+                if flush is not None:
+                    gw.l2_flush(256 << 20)
+                if fused:
+                    gw.peer_barrier()
+                gw.em_enqueue()
+            barrier()
+            gw.em_finish(want_labels=False)
+            tw = torch.tensor([sum(gw.em_enqueued_ms(ww + i) for i in range(ws)) * 1e-3], dtype=torch.float64, device=dev)
+            nw_ = torch.tensor([float(wl_w.n_windows)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nw_, op=dist.ReduceOp.SUM)
+            weak = {"value": float(nw_.item()) * ws / float(tw.item()), "unit": "windows/s", "windows": int(nw_.item()), "steps": ws,
+                    "ms_per_step": 1e3 * float(tw.item()) / ws, "workload": f"{world} x {args.total_bp / 1e9:g} Gbp, one model"}
+            gw.close()
+        barrier()
+
     if rank == 0:
         peak, peak_src = measured_peak()
         value = W_total * args.steps / t_total
@@ -468,15 +604,13 @@ def run_ours(args):
             "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_full.name, "windows": W_total, "chunks": wl_full.n_chunks, "regions": R,
-                       "col_components": K, "window_len": wl_full.window_len, "alpha": "HiFi_DC_1.2",
-                       "step": "one EM iteration = E-step of all chunks (fwd+bwd+statistics+labels) + M-step",
-                       "parallelism": ("1 GPU" if world == 1 else
-                                       f"chunks sharded over {world} GPUs, one process per GPU; EM statistics summed over "
-                                       "ranks " + ("inside the E-step kernel through NVLink peer memory (fused all-reduce)"
-                                                   if fused else "with one NCCL all-reduce per iteration")),
-                       "l2": "not flushed" if args.no_flush else "flushed between timed steps (256 MiB fill, untimed)",
-                       "timing": timing_note},
+            "config": workload_config(wl_full, K),
+            "notes": {"parallelism": ("1 GPU" if world == 1 else
+                                      f"chunks sharded over {world} GPUs, one process per GPU; EM statistics summed over "
+                                      "ranks " + ("inside the E-step kernel through NVLink peer memory (fused all-reduce)"
+                                                  if fused else "with one NCCL all-reduce per iteration")),
+                      "l2": "not flushed" if args.no_flush else "flushed between timed steps (256 MiB fill, untimed)",
+                      "timing": timing_note},
             "e2e": {"value": W_total * args.steps / e2e_total, "unit": "windows/s",
                     "h2d_bytes_per_step": int(params.nbytes + obs_bytes / args.steps),
                     "d2h_bytes_per_step": int(stats.nbytes + 16 + wl.n_windows),
@@ -490,13 +624,21 @@ def run_ours(args):
                         "job_ms": [1e3 * j for j in run_jobs]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(wl_full.name), "kernel": "hfg_estep_kernel", "kernel_ms": kernel_s * 1e3,
+                         "traffic": ncu_traffic(wl_full.name), "kernel": "hfg_estep_v3_kernel", "kernel_ms": kernel_s * 1e3,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_WINDOW * wl.n_windows, "peak_source": peak_src},
             "clocks": clocks,
             "loglik_first_last": [logliks[0], logliks[-1]],
         }
+        if parity is not None:
+            line["parity_check"] = parity
+        if exchange is not None:
+            line["exchange"] = exchange
+        if weak is not None:
+            line["weak"] = weak
+        if world == 1 and not args.no_binary and args.workload != "small":
+            line["e2e_binary"] = binary_e2e(wl_full, alpha, args.steps, host_threads())
         if world == 1 and not args.no_cpu_baseline:
-            cpu, _ = time_cpu(cfg, wl_full, alpha, params0, steps=2, warmup=1, budget_s=25.0)
+            cpu, _ = time_cpu(cfg, wl_full, alpha, params0, steps=5, warmup=1, budget_s=30.0)
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         _RESULT_LINE.append(json.dumps(line))
     gpu.close()

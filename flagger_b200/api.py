@@ -54,7 +54,7 @@ EXPORTED_SYMBOLS = (
     "hfg_host_alloc", "hfg_host_free", "hfg_run_em", "hfg_em_begin", "hfg_em_enqueue", "hfg_em_finish",
     "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_kernel_launches", "hfg_last_estep_kernel_ms",
     "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
-    "hfg_debug_layout_compare", "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_read_cov",
+    "hfg_debug_layout_compare", "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_peer_barrier", "hfg_read_cov",
     "hfg_read_bin", "hfg_cov_free", "hfg_write_summary_tsv", "hfg_benchmark_scores", "hfg_params_feasible", "hfg_squarem_alpha_rate",
     "hfg_squarem_prime", "hfg_squarem_shrink", "hfg_squarem_iteration", "hfg_run_em_accelerated",
     "hfg_release_cached_memory", "hfg_nb_emission_table", "hfg_nb_stats_from_histogram", "hfg_digammal", "hfg_debug_gunzip",
@@ -275,6 +275,10 @@ class HmmFlaggerGPU:
         handles = np.ascontiguousarray(np.concatenate([g.cpu().numpy() for g in gathered]))
         self._check(L.hfg_peer_connect(self._h, C.c_int(world), C.c_int(rank), ptr(handles)))
         dist.barrier()
+
+    def peer_barrier(self):
+        """Device-side rendezvous of all ranks on the library's stream (hfg_peer_barrier)."""
+        self._check(lib().hfg_peer_barrier(self._h))
 
     def stats_device_bytes(self):
         return int(lib().hfg_stats_device_bytes(self._h))

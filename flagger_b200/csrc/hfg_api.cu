@@ -86,7 +86,7 @@ struct hfg_ctx {
     void *d_flush;
     size_t flush_bytes;
     int64_t launches;
-    /* negative-binomial model (EXPERIMENTAL: accepted only with HFG_EXPERIMENTAL_NB=1, not validated on hardware yet) */
+    /* negative-binomial model: emission table from the host, per-tile pair masses back (run_blocking_nb) */
     int nb;
     double *d_nb_table, *h_nb_table;     /* [R][4][HFG_NB_XSTRIDE] device / pinned */
     double *d_nb_tile_col, *h_nb_tile_col; /* [n_tiles][4] */
@@ -237,10 +237,6 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     if (!out || !cfg) return fail(NULL, HFG_ERR_INVALID, "hfg_create: NULL argument");
     *out = NULL;
     const int nb = cfg->model_type == HFG_MODEL_NEGATIVE_BINOMIAL;
-    if (nb && !getenv("HFG_EXPERIMENTAL_NB"))
-        return fail(NULL, HFG_ERR_INVALID, "hfg_create: model_type %d has no device path that was validated on hardware "
-                    "(negative_binomial: host functions; HFG_EXPERIMENTAL_NB=1 enables the untested kernel instantiation)",
-                    cfg->model_type);
     if (!nb && cfg->model_type != HFG_MODEL_TRUNC_EXP_GAUSSIAN && cfg->model_type != HFG_MODEL_GAUSSIAN)
         return fail(NULL, HFG_ERR_INVALID, "hfg_create: model_type %d not supported", cfg->model_type);
     if (cfg->n_regions < 1 || cfg->n_regions > HFG_MAX_REGIONS)
@@ -282,9 +278,9 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         ctx->kernel = nb ? (const void *) hfg_estep_v3_kernel<HFG3_THREADS, true> : (const void *) hfg_estep_v3_kernel<HFG3_THREADS>;
         /* HFG_THREADS: A/B switch of the CTA size (fewer, longer segments: cheaper scans, fewer warps to hide latency) */
         const int want = getenv("HFG_THREADS") ? atoi(getenv("HFG_THREADS")) : 0;
-        if (!nb && (want == 256 || want == 320 || want == 384 || want == 512 || want == 640)) {
+        if (!nb && (want == 128 || want == 256 || want == 320 || want == 384 || want == 512 || want == 640)) {
             ctx->threads = want;
-            ctx->kernel = want == 256 ? (const void *) hfg_estep_v3_kernel<256> : want == 320 ? (const void *) hfg_estep_v3_kernel<320>
+            ctx->kernel = want == 128 ? (const void *) hfg_estep_v3_kernel<128> : want == 256 ? (const void *) hfg_estep_v3_kernel<256> : want == 320 ? (const void *) hfg_estep_v3_kernel<320>
                           : want == 384 ? (const void *) hfg_estep_v3_kernel<384> : want == 512 ? (const void *) hfg_estep_v3_kernel<512>
                                                                                                 : (const void *) hfg_estep_v3_kernel<640>;
         }
@@ -1085,7 +1081,7 @@ static int8_t *pinned_device_alias(const void *p) {
     return at.type == cudaMemoryTypeHost ? (int8_t *) at.devicePointer : NULL;
 }
 
-/* blocking E-step of the negative-binomial model (EXPERIMENTAL, HFG_EXPERIMENTAL_NB=1): emission table from the host,
+/* blocking E-step of the negative-binomial model: emission table from the host,
  * the NB kernel instantiation, per-tile pair masses back to the host, folded into the (region, state, x) histogram in
  * tile order and turned into the estimator sums by hfg_nb_stats_from_histogram (hmm.c:615-617,643-649). */
 static int run_blocking_nb(hfg_ctx *ctx, const hfg_region_params *params, int forward_only, hfg_region_stats *stats,
@@ -1594,7 +1590,7 @@ extern "C" int hfg_debug_layout_compare(hfg_ctx *ctx, int32_t n_chunks, const hf
 
 static size_t mailbox_bytes(const hfg_ctx *ctx) {
     const size_t n = (size_t) ctx->cfg.n_regions * STATS_DOUBLES + 2;
-    return (2 * HFG_MAX_PEERS * n + 2 * HFG_MAX_PEERS) * sizeof(double);
+    return (2 * HFG_MAX_PEERS * n + 3 * HFG_MAX_PEERS) * sizeof(double); /* slots, arrival counters, barrier counters */
 }
 
 extern "C" size_t hfg_peer_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
@@ -1607,12 +1603,49 @@ extern "C" int hfg_peer_export(hfg_ctx *ctx, void *handle_out) {
         CU(cudaMemset(ctx->d_mailbox, 0, mailbox_bytes(ctx)));
     }
     if (!ctx->d_epoch) {
-        CU(cudaMalloc((void **) &ctx->d_epoch, sizeof(unsigned long long)));
-        CU(cudaMemset(ctx->d_epoch, 0, sizeof(unsigned long long)));
+        CU(cudaMalloc((void **) &ctx->d_epoch, 2 * sizeof(unsigned long long))); /* exchanges done, barriers done */
+        CU(cudaMemset(ctx->d_epoch, 0, 2 * sizeof(unsigned long long)));
     }
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, ctx->d_mailbox));
     memcpy(handle_out, &h, sizeof(h));
+    return HFG_OK;
+}
+
+/* Device-side rendezvous of the ranks on the context's stream: every rank bumps a counter in every peer's mailbox and waits
+ * for the others' bumps in its own.  Benchmarks put it in front of a timed E-step so that the interval starts at the same
+ * moment on every rank (the all-reduce inside the kernel would otherwise charge the fastest rank with the others' lateness). */
+__global__ void hfg_peer_barrier_kernel(EstepArgs A, size_t bar_base) {
+    const int p = threadIdx.x;
+    unsigned long long *mine_epoch = A.epoch + 1;
+    const unsigned long long e = *mine_epoch + 1;
+    if (p < A.n_ranks) {
+        volatile unsigned long long *c = (volatile unsigned long long *) (A.peer_box[p] + bar_base) + A.rank;
+        *c = e;
+        __threadfence_system();
+        volatile unsigned long long *mine = (volatile unsigned long long *) (A.peer_box[A.rank] + bar_base) + p;
+        const long long t0 = clock64();
+        while (*mine < e)
+            if (clock64() - t0 > 4000000000LL) break; /* ~2 s: a lost peer must not hang the stream */
+    }
+    __syncthreads();
+    if (p == 0) *mine_epoch = e;
+}
+
+extern "C" int hfg_peer_barrier(hfg_ctx *ctx) {
+    if (!ctx) return HFG_ERR_INVALID;
+    if (ctx->n_ranks < 2) return HFG_OK;
+    CU(cudaSetDevice(ctx->device));
+    EstepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_ranks = ctx->n_ranks;
+    a.rank = ctx->rank;
+    a.epoch = ctx->d_epoch;
+    for (int p = 0; p < HFG_MAX_PEERS; p++) a.peer_box[p] = ctx->peer_box[p];
+    const size_t n = (size_t) ctx->cfg.n_regions * STATS_DOUBLES + 2;
+    hfg_peer_barrier_kernel<<<1, 32, 0, ctx->stream>>>(a, 2 * HFG_MAX_PEERS * n + 2 * HFG_MAX_PEERS);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
     return HFG_OK;
 }
 

@@ -9,8 +9,8 @@
  *   posterior_prediction_final.bed (-P), chunks.c_<C>.w_<W>.bin (-B), prediction_summary_{initial,iteration_k,final}.tsv
  *   and, for inputs with truth labels, their .benchmarking.tsv / .benchmarking.auN_ratio.tsv companions (all on the flat
  *   label array, hfg_write_summary_tsv; -k for every iteration).
- * --accelerate (SQUAREM) runs through hfg_squarem_iteration.  --modelType negative_binomial needs HFG_EXPERIMENTAL_NB=1
- * (kernel not validated on hardware yet).  Not supported: --initialRandomDev other than 0.
+ * --accelerate (SQUAREM) runs through hfg_squarem_iteration; --modelType negative_binomial through the host-looped E-steps
+ * (hfg_api.cu::run_blocking_nb).  Not supported: --initialRandomDev other than 0 (refused with a message).
  */
 #include <getopt.h>
 #include <math.h>
@@ -362,8 +362,7 @@ int main(int argc, char *argv[]) {
             case 'm':
                 if (strcmp(optarg, "trunc_exp_gaussian") == 0) model_type = HFG_MODEL_TRUNC_EXP_GAUSSIAN;
                 else if (strcmp(optarg, "gaussian") == 0) model_type = HFG_MODEL_GAUSSIAN;
-                else if (strcmp(optarg, "negative_binomial") == 0) model_type = HFG_MODEL_NEGATIVE_BINOMIAL; /* hfg_create
-                    accepts it only with HFG_EXPERIMENTAL_NB=1: its kernel has not been validated on hardware yet */
+                else if (strcmp(optarg, "negative_binomial") == 0) model_type = HFG_MODEL_NEGATIVE_BINOMIAL;
                 else die("--modelType should be trunc_exp_gaussian, gaussian or negative_binomial");
                 break;
             case 'c': contigs = optarg; break;
@@ -394,8 +393,12 @@ int main(int argc, char *argv[]) {
                 label_names[n_label_names++] = "Unk";
                 break;
             }
-            case '@': case 'D':
-                break; /* accepted for command-line compatibility: no thread pool here, --initialRandomDev 0 only */
+            case '@':
+                break; /* accepted for command-line compatibility: there is no thread pool here */
+            case 'D':
+                /* the reference perturbs the initial means with rand() (src/hmm_flagger.c:207-219): not reproduced here */
+                if (atof(optarg) != 0.0) die("--initialRandomDev other than 0 is not supported by this binary");
+                break;
             default:
                 fprintf(stderr, "Usage: %s -i <INPUT.cov|.cov.gz|.bin> -o <OUTPUT_DIR> [options of hmm_flagger v1.2.0] [--device N]\n", argv[0]);
                 return 1;
@@ -435,6 +438,8 @@ int main(int argc, char *argv[]) {
 
     /* 1. chunks */
     fprintf(stderr, "[%s] Parsing/Creating coverage chunks. \n", stamp());
+    /* where the wall time goes (printed behind the reference's "Real time" line): read, GPU set-up, EM, summary tables, BED */
+    double ph_read = 0, ph_setup = 0, ph_summary = 0, ph_bed = 0, ph_t = now_s();
     hfg_cov_data *d = NULL;
     char err[512] = "";
     int rc;
@@ -450,6 +455,7 @@ int main(int argc, char *argv[]) {
         write_bin(path, d);
     }
     fprintf(stderr, "[%s] %d chunks are parsed (%lld windows). \n", stamp(), d->n_chunks, (long long) d->n_windows);
+    ph_read = now_s() - ph_t;
 
     /* 2. number of collapsed components (src/hmm_flagger.c:1003-1023) */
     if (collapsed == -1) {
@@ -487,9 +493,12 @@ int main(int argc, char *argv[]) {
     write_emission_tsv(out_dir, "initial", &cfg, params);
     /* the GPU context: no CPU fallback -- without a usable device the run stops here */
     hfg_ctx *ctx = NULL;
+    ph_t = now_s();
     if (hfg_create(&ctx, &cfg) != HFG_OK) die(hfg_last_error(NULL));
     if (hfg_set_chunks(ctx, d->n_chunks, d->chunks, d->cov, d->cov_high_mapq, d->cov_high_clip, d->region) != HFG_OK)
         die(hfg_last_error(ctx));
+    ph_setup = now_s() - ph_t;
+    const double ph_em0 = now_s();
     int8_t *labels = xmalloc((size_t) d->n_windows);
     int iter = 1, converged = 0, final_done = 0;
     double loglik = 0.0;
@@ -541,7 +550,9 @@ int main(int argc, char *argv[]) {
             }
             if (iter == 1) snprintf(suffix, sizeof(suffix), "initial");
             else snprintf(suffix, sizeof(suffix), accelerate ? "iteration_accelerated_%d" : "iteration_%d", iter - 1);
+            ph_t = now_s();
             write_summary(out_dir, suffix, d, labels, n_label_names ? label_names : NULL, overlap_thr, bin_array_file);
+            ph_summary += now_s() - ph_t;
         }
         hfg_mstep(&cfg, params, stats, tol, &converged);
         if (write_params) {
@@ -561,7 +572,10 @@ int main(int argc, char *argv[]) {
         }
         fprintf(ll_file, "%d\t%d\t%.4f\n", iter - 1, accelerate ? 3 * (iter - 1) : iter - 1, loglik);
     }
+    const double ph_em = now_s() - ph_em0 - ph_summary;
+    ph_t = now_s();
     write_summary(out_dir, "final", d, labels, n_label_names ? label_names : NULL, overlap_thr, bin_array_file);
+    ph_summary += now_s() - ph_t;
     fclose(ll_file);
     write_transition_tsv(out_dir, "final", &cfg, params);
     write_emission_tsv(out_dir, "final", &cfg, params);
@@ -575,7 +589,9 @@ int main(int argc, char *argv[]) {
     /* 5. final BED */
     fprintf(stderr, "[%s] Writing final BED file. \n", stamp());
     snprintf(path, sizeof(path), "%s/final_flagger_prediction.bed", out_dir);
+    ph_t = now_s();
     write_final_bed(path, track, d, labels, min_len);
+    ph_bed = now_s() - ph_t;
 
     hfg_destroy(ctx);
     hfg_cov_free(d);
@@ -591,5 +607,7 @@ int main(int argc, char *argv[]) {
     const double cpu = ru.ru_utime.tv_sec + ru.ru_stime.tv_sec + 1e-6 * (ru.ru_utime.tv_usec + ru.ru_stime.tv_usec);
     fprintf(stderr, "Real time:  %.3f sec; CPU: %.3f sec; Peak RSS: %.3f GB; CPU usage: %.1f%%\n", real, cpu,
             ru.ru_maxrss / 1024.0 / 1024.0, 100.0 * cpu / (real > 0 ? real : 1));
+    fprintf(stderr, "Phases: read %.4f s; GPU set-up %.4f s; EM %.4f s; summary tables %.4f s; BED %.4f s\n", ph_read, ph_setup, ph_em,
+            ph_summary, ph_bed);
     return 0;
 }

@@ -33,10 +33,10 @@ extern "C" {
 
 enum hfg_state { HFG_STATE_ERR = 0, HFG_STATE_DUP = 1, HFG_STATE_HAP = 2, HFG_STATE_COL = 3 };
 
-/* submodules/hmm_utils/hmm_utils.h:43-48.  HFG_MODEL_NEGATIVE_BINOMIAL: the host functions serve it (hfg_model_init,
- * hfg_mstep, hfg_params_feasible, hfg_squarem_*, hfg_nb_*); its kernel instantiation exists but has not run on hardware
- * yet, so hfg_create rejects the model unless HFG_EXPERIMENTAL_NB=1 is set (blocking E-steps on one GPU only:
- * hfg_em_iteration, hfg_forward_only, hfg_get_posteriors, hfg_run_em through the host loop). */
+/* submodules/hmm_utils/hmm_utils.h:43-48.  HFG_MODEL_NEGATIVE_BINOMIAL is served by the blocking E-steps on one GPU
+ * (hfg_em_iteration, hfg_forward_only, hfg_get_posteriors, hfg_run_em through the host loop): the emission table is built on
+ * the host, the device returns per-tile pair masses, the host folds them into the histogram of hmm.c:615-617 and runs the
+ * estimator update (hfg_nb_*).  The device-resident loop (hfg_em_*) and the multi-GPU exchange do not serve it. */
 enum hfg_model_type { HFG_MODEL_TRUNC_EXP_GAUSSIAN = 0, HFG_MODEL_GAUSSIAN = 1, HFG_MODEL_NEGATIVE_BINOMIAL = 2 };
 
 enum hfg_status {
@@ -167,6 +167,9 @@ int hfg_get_labels(hfg_ctx *ctx, int8_t *labels);
 size_t hfg_peer_handle_bytes(void);
 int hfg_peer_export(hfg_ctx *ctx, void *handle_out);
 int hfg_peer_connect(hfg_ctx *ctx, int n_ranks, int rank, const void *handles);
+/* Device-side rendezvous of all ranks, queued on the context's stream (no host synchronisation): what a benchmark puts in
+ * front of a timed iteration so that every rank's interval starts together.  No-op for a single rank. */
+int hfg_peer_barrier(hfg_ctx *ctx);
 
 /* ---- host mirrors of the O(#parameters) neighbours of the seam ---------------------------------- */
 

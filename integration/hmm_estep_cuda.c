@@ -144,8 +144,6 @@ static void bind(stList *emList, HMM *model) {
         fprintf(stderr, "[hmm_estep_cuda] only the 4-state models run on the GPU path\n");
         exit(EXIT_FAILURE);
     }
-    /* negative_binomial: hfg_create decides (it accepts the model only with HFG_EXPERIMENTAL_NB=1 until its kernel has been
-     * validated on hardware) and says so in its error message */
     b->emList = emList;
     b->nChunks = (int) stList_length(emList);
     b->ems = malloc(sizeof(EM *) * b->nChunks);
@@ -211,10 +209,12 @@ static void flatten_alpha(HMM *model, double *alpha) {
         for (int j = 0; j < HFG_NUM_STATES; j++) alpha[i * HFG_NUM_STATES + j] = model->alpha->data[i][j];
 }
 
+static int still_bound(stList *emList);
+
 void EM_runOneIterationForList(stList *emList, HMM *model, int threads) {
     (void) threads;
     Binding *b = &g_bind;
-    if (b->emList != emList || b->ctx == NULL) bind(emList, model);
+    if (!still_bound(emList)) bind(emList, model);
     double alpha[HFG_NUM_STATES * HFG_NUM_STATES], loglik = 0.0;
     flatten_alpha(model, alpha);
     flatten_params(model, b->params);
@@ -241,7 +241,7 @@ void EM_runOneIterationForList(stList *emList, HMM *model, int threads) {
 void EM_runForwardForList(stList *emList, HMM *model, int threads) {
     (void) threads;
     Binding *b = &g_bind;
-    if (b->emList != emList || b->ctx == NULL) bind(emList, model);
+    if (!still_bound(emList)) bind(emList, model);
     double alpha[HFG_NUM_STATES * HFG_NUM_STATES], loglik = 0.0;
     flatten_alpha(model, alpha);
     flatten_params(model, b->params);
@@ -255,12 +255,31 @@ void EM_runForwardForList(stList *emList, HMM *model, int threads) {
     for (int c = 0; c < b->nChunks; c++) b->ems[c]->model = model;
 }
 
+/* global window of position `pos` of a chunk.  Callers walk a chunk window by window and the chunks in list order, so the
+ * chunk found last time (or the one after it) is tried first: O(1) per call instead of a scan over all chunks */
 static int64_t window_index(EM *em, int pos) {
     Binding *b = &g_bind;
+    static int last = 0;
+    if (last >= b->nChunks) last = 0;
+    if (b->ems[last] == em) return b->offsets[last] + pos;
+    if (last + 1 < b->nChunks && b->ems[last + 1] == em) return b->offsets[++last] + pos;
     for (int c = 0; c < b->nChunks; c++)
-        if (b->ems[c] == em) return b->offsets[c] + pos;
+        if (b->ems[c] == em) {
+            last = c;
+            return b->offsets[c] + pos;
+        }
     fprintf(stderr, "[hmm_estep_cuda] EM_getPosterior on an EM that is not resident\n");
     exit(EXIT_FAILURE);
+}
+
+/* Is the resident copy still the list the caller passes?  The address of the stList alone is not enough: a caller that
+ * runs several jobs in one process (the alpha tuner) may rebuild the list at the same address. */
+static int still_bound(stList *emList) {
+    Binding *b = &g_bind;
+    if (b->ctx == NULL || b->emList != emList || stList_length(emList) != b->nChunks || b->nChunks < 1) return 0;
+    EM *first = stList_get(emList, 0), *last = stList_get(emList, b->nChunks - 1);
+    return first == b->ems[0] && last == b->ems[b->nChunks - 1] &&
+           b->offsets[b->nChunks - 1] + last->seqLen == b->nWindows;
 }
 
 double *EM_getPosterior(EM *em, int pos) {

@@ -29,6 +29,9 @@ def test_reference_arm_prints_one_contract_line():
     assert j["value"] > 0 and j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0
     assert j["cpu_baseline"]["kind"] in ("reference", "port") and j["cpu_baseline"]["cores"] >= 1
     assert j["vs_baseline"] is None and "workload" in j["config"]
+    # the reference arm runs the checker only: the product library is not even mapped
+    assert j["native_libs"] and not any("libhfg" in lib for lib in j["native_libs"]), j["native_libs"]
+    assert set(j["config"]) == {"workload", "windows", "chunks", "regions", "col_components", "window_len", "alpha", "step"}
 
 
 def test_reference_arm_non_zero_ranks_stay_silent():

@@ -1,11 +1,9 @@
-"""GPU, OPT-IN: the negative-binomial kernel instantiation (hfg_estep_kernel<THREADS, true> + the host fold in
-hfg_api.cu::run_blocking_nb) against the oracle.  The path was written after the round's GPU budget was spent and has
-NOT run on hardware yet, so hfg_create only accepts the model with HFG_EXPERIMENTAL_NB=1 and these tests only run with it:
+"""GPU: the negative-binomial kernel instantiation (hfg_estep_v3_kernel<THREADS, true> + the host fold in
+hfg_api.cu::run_blocking_nb) against the oracle, the golden vectors, the reference binary (stand-alone CLI) and the drop-in
+binding.
 
-    HFG_EXPERIMENTAL_NB=1 python -m pytest tests/test_gpu_nb_experimental.py -m gpu -x -q
-
-Bars once it is enabled: labels identical, log-likelihood within 1e-9 relative, statistics within 1e-9 of the region's
-largest (the reference sums the histogram per chunk, the product per tile: rounding only), EM trajectories accordingly."""
+Bars: labels identical, log-likelihood within 1e-9 relative, statistics within 1e-9 of the region's largest (the reference
+sums the histogram per chunk, the product per tile: rounding only), EM trajectories accordingly."""
 import os
 
 import numpy as np
@@ -14,9 +12,7 @@ import pytest
 import golden_util
 from flagger_b200 import _abi, api, synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("HFG_EXPERIMENTAL_NB") != "1",
-                                 reason="negative-binomial device path not validated yet: set HFG_EXPERIMENTAL_NB=1 to run it")]
+pytestmark = pytest.mark.gpu
 
 NB = _abi.MODEL_NEGATIVE_BINOMIAL
 

@@ -98,6 +98,6 @@ def test_invalid_configs_rejected():
     assert lib.hfg_create(ctypes.byref(h), _abi.ptr(bad)) == _abi.ERR_INVALID
     bad = _abi.make_config(n_col_comps=17)
     assert lib.hfg_create(ctypes.byref(h), _abi.ptr(bad)) == _abi.ERR_INVALID
-    bad = _abi.make_config(model_type=2)  # negative_binomial: out of scope
+    bad = _abi.make_config(model_type=3)  # 0 trunc_exp_gaussian, 1 gaussian, 2 negative_binomial
     assert lib.hfg_create(ctypes.byref(h), _abi.ptr(bad)) == _abi.ERR_INVALID
-    assert b"negative_binomial" in lib.hfg_last_error(None)
+    assert b"model_type" in lib.hfg_last_error(None)

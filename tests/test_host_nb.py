@@ -99,15 +99,17 @@ def test_host_nb_stats_from_histogram_match_oracle(orc):
             assert wl.n_chunks == n_chunks_expected
 
 
-def test_create_rejects_negative_binomial_until_a_device_path_exists():
-    """No silent fallback: the model is refused before any device work."""
+def test_create_without_a_gpu_fails_loudly_for_the_negative_binomial_model_too():
+    """No CPU fallback of any kind: on a box without a usable device hfg_create says so (on a GPU box it succeeds)."""
     import ctypes as C
     cfg = _abi.make_config(model_type=NB)
     ctx = C.c_void_p()
     rc = api.lib().hfg_create(C.byref(ctx), api.ptr(cfg))
-    assert rc == 1 and not ctx.value  # HFG_ERR_INVALID
     api.lib().hfg_last_error.restype = C.c_char_p
-    assert b"no device path" in api.lib().hfg_last_error(None)
+    if rc == 0:
+        api.lib().hfg_destroy(ctx)
+    else:
+        assert rc == 2 and not ctx.value and b"no CPU fallback" in api.lib().hfg_last_error(None)  # HFG_ERR_CUDA
 
 
 def test_host_nb_table_reports_nan_like_the_reference_exit():

@@ -37,6 +37,18 @@ def test_layout_rejects_bad_input():
     assert not ok
 
 
+def test_more_region_runs_than_segment_slots_is_an_error_not_a_hang():
+    """A segment never straddles a region change, so runs of equal region index bound the segment count from below:
+    alternating regions with fewer slots than windows used to loop forever in the segment-length search."""
+    wl = synth.small_mixed(n_regions=2, seed=3)
+    wl.region[:] = (np.arange(wl.n_windows) % 2).astype(np.uint8)
+    cfg = _abi.make_config(n_regions=2)
+    ok, _ = api.layout_check(cfg, wl, 512)
+    assert not ok
+    ok, summary = api.layout_check(cfg, wl, 2048)  # enough slots: one window per segment
+    assert ok and summary[0] == wl.n_windows and summary[1] == 1
+
+
 def test_beta_matches_oracle(orc):
     f = orc.lib.orc_beta
     f.restype = C.c_double

@@ -77,7 +77,7 @@ def test_pre_gpu_outputs_byte_identical(tmp_path, kind, extra):
 
 def test_rejects_bad_arguments(tmp_path):
     inp, alpha = _inputs(tmp_path, "cov")
-    for extra in (("-t", "0"), ("-x", "nanopore"), ("-M", "1,2"), ("-f", "1.5")):
+    for extra in (("-t", "0"), ("-x", "nanopore"), ("-M", "1,2"), ("-f", "1.5"), ("-D", "0.1")):  # -D: refused, not ignored
         r = _run(CLI, inp, str(tmp_path / "o"), extra=extra, check=False)
         assert r.returncode != 0 and "Error" in r.stderr, extra
     r = subprocess.run([CLI, "-i", str(tmp_path / "x.txt"), "-o", str(tmp_path)], capture_output=True, text=True)

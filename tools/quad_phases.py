@@ -7,7 +7,13 @@ import numpy as np
 sys.path.insert(0, ".")
 from flagger_b200 import api, synth, _abi
 which = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-wl = {"cfg2": synth.config2, "cfg3": synth.config3, "cfg4": synth.config4,
+if which.startswith("cfg2:"):
+    bp = int(float(which.split(":")[1]))
+    which = "cfg2"
+    synth_cfg2 = lambda: synth.config2(total_bp=bp)
+else:
+    synth_cfg2 = synth.config2
+wl = {"cfg2": synth_cfg2, "cfg3": synth.config3, "cfg4": synth.config4,
       "medium": lambda: synth.config2(total_bp=300_000_000, seed=22), "small": lambda: synth.small_mixed(n_regions=1, seed=12)}[which]()
 K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
 cfg = _abi.make_config(n_regions=len(wl.region_coverages), n_col_comps=K)
