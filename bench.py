@@ -465,6 +465,7 @@ def run_ours(args):
         timing_note = ("sum over steps of [CUDA-event interval on the launching stream (parameter upload, kernel, NCCL "
                        "all-reduce, statistics read-back) + host M-step], max over ranks")
     launches = gpu.kernel_launches() - launches0
+    tail_clocks = gpu.debug_phase_clocks()[-1].copy() if (world > 1 and fused) else None  # of the last timed iteration's kernel
     t_total = torch.tensor([sum(step_s)], dtype=torch.float64, device=dev)
     k_total = torch.tensor([sum(kern_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -562,7 +563,7 @@ def run_ours(args):
         if fused:
             # the in-kernel exchange of the last timed iteration, from the kernel's own clocks (tail row: 3 = first store into
             # the peers' mailboxes, 4 = all N vectors summed): what the all-reduce costs this rank, waiting included
-            tail = gpu.debug_phase_clocks()[-1]
+            tail = tail_clocks
             ex = torch.tensor([float(tail[4] - tail[3]) / 1.965e3], dtype=torch.float64, device=dev)  # microseconds at 1965 MHz
             exs = [torch.zeros_like(ex) for _ in range(world)]
             dist.all_gather(exs, ex)

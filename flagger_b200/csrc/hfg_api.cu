@@ -128,11 +128,12 @@ static size_t smem_bytes_for(int R, int G, int NT, int threads) {
 /* shared memory of the quad kernel (hfg_estep_quad.cuh): region tables, second-level scan buffers, the CTA messages, and
  * the larger of the per-warp statistics rows, the grid totals and -- aliasing everything behind the region tables -- the
  * M-step work area of the device-resident loop */
-/* the M-step work area of the kernel tail (hfg_estep_tail): per region of a batch its parameters, statistics and 8 doubles,
- * plus 128 doubles of scratch per warp and one exchange slot per thread for the rate fits */
+/* the M-step work area of the kernel tail (hfg_estep_tail): per region of a batch its parameters, statistics and 282 doubles,
+ * plus 128 doubles of scratch per warp and one exchange slot per thread for the rate fits, plus 576 doubles (HFG_TAIL_TOP) at the top of the
+ * area for the scout warps and the convergence flag */
 static size_t mstep_work_bytes(int threads, int regions) {
-    return ((size_t) regions * ((sizeof(hfg_region_params) + sizeof(hfg_region_stats)) / sizeof(double) + 8) + (size_t) threads +
-            (size_t) (threads / 32) * 128) * sizeof(double);
+    return ((size_t) regions * ((sizeof(hfg_region_params) + sizeof(hfg_region_stats)) / sizeof(double) + 282) + (size_t) threads +
+            (size_t) (threads / 32) * 128 + 576) * sizeof(double);
 }
 
 static size_t smem_bytes_quad(int R, int G, int threads, int smax) {

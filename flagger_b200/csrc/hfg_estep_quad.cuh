@@ -178,84 +178,286 @@ __device__ __forceinline__ double gauss_state_prob(const double *rt, int G, int 
 
 }  // namespace hfgq
 
-/* The golden-section rate fit of hfg_mstep_inl.h (hfg_fit_rate / hfg_fit_rate_warp) for a GROUP of `gsize` consecutive
- * threads (a power of two >= 32): the point evaluated at a step depends only on the outcomes of the comparisons so far, so the
- * 2 + 4 + ... + 2^D candidate points of the next D steps (D = 8 for 512 threads) are evaluated one per thread, and every
- * thread then walks the true path through the group's buffer `fb` (gsize doubles): ~5 rounds instead of ~34 dependent
- * objective evaluations, the same bits as the serial routine.  The group synchronises on its own named barrier `bar` (1..15):
- * all gsize threads of the group must call it, other groups and warps are not involved.  `st8` = 8 doubles of group scratch. */
-__device__ __forceinline__ void group_sync(int bar, int n) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory"); }
-__device__ __forceinline__ double hfg_fit_rate_cta(bool active, int gtid, int gsize, int bar, double trunc, double sum_x, double sum_w,
-                                                   double *st8, double *fb) {
+/* ---- the rate fit of the kernel tail -------------------------------------------------------------------------------------
+ * The tail runs once per launch, on one CTA, on cold instruction caches: an instruction executed for the first time costs a
+ * fetch from L2 (measured: ~15 cycles per instruction, 11 000 cycles for the first objective evaluation against ~1 000 warm).
+ * Hence (i) one copy of each piece of code (__noinline__ pieces shared by all call sites) and (ii) SCOUT warps: while the
+ * other warps sum the CTAs' partials, four otherwise idle warps run the four pieces on dummy numbers, so that the fit proper
+ * finds its instructions in the SM's cache (hfg_estep_tail). */
+__device__ __noinline__ double hfg_objective_dev(double rate, double trunc, double sum_x, double sum_w) {
+    return hfg_trunc_exp_objective(rate, trunc, sum_x, sum_w);
+}
+__device__ __forceinline__ double *hfg_align16(double *p) { return reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t) 15); }
+#define HFG_TAIL_TOP 576 /* doubles at the top of the tail's work area: 4 x 64 scout scratch, 256 scout snapshots, flags */
+struct HfgFitState {
+    double lo, x1, x2, hi, span, y1, y2;
+};
+/* x*: Newton on g1(x) = w/x - w T q - s (the objective's derivative), q = 1/expm1(xT), steps kept inside the bracket; then
+ * the Taylor coefficients of the objective around x*: co[0] = x*, co[1..4] = derivatives 1..4 over 1!, 2!, 3!, 4!.
+ * Inaccuracy here only costs predictions. */
+__device__ __noinline__ void hfg_fit_newton_dev(double x, double lo, double hi, double trunc, double sum_x, double sum_w, double *co) {
+    bool last = false;
+#pragma unroll 1
+    for (int it = 0; it < 8; it++) {
+        const double q = 1.0 / expm1(x * trunc);
+        const double ix = 1.0 / x, q1 = q * (1.0 + q);
+        const double g1 = sum_w * ix - sum_w * trunc * q - sum_x;
+        const double g2 = -sum_w * ix * ix + sum_w * trunc * trunc * q1;
+        if (last || it == 7) { /* the coefficients at the last iterate */
+            const double T2 = trunc * trunc, ix2 = ix * ix;
+            co[0] = x;
+            co[1] = g1;
+            co[2] = 0.5 * g2;
+            co[3] = (2.0 * sum_w * ix2 * ix - sum_w * T2 * trunc * q1 * (1.0 + 2.0 * q)) * (1.0 / 6.0);
+            co[4] = (-6.0 * sum_w * ix2 * ix2 + sum_w * T2 * T2 * q1 * (1.0 + 6.0 * q1)) * (1.0 / 24.0);
+            break;
+        }
+        double xn = x - g1 * (1.0 / g2);
+        if (!(xn > lo)) xn = 0.5 * (x + lo);
+        if (!(xn < hi)) xn = 0.5 * (x + hi);
+        last = fabs(xn - x) <= 1e-7 * x; /* quadratic convergence: the next iterate is good to ~1e-14 */
+        x = xn;
+    }
+}
+/* PREDICTED round: L <= 32 steps of the serial search by one warp.  The position of x* (and, when x* lies between the two
+ * interior points, the Taylor polynomial) says how each comparison will come out, so the walk needs no objective values:
+ * every lane walks the same predicted path, lane 0 leaves each step's point, bracket and bookkeeping in `snap` ([32][8]
+ * doubles of shared memory); lane t then evaluates the point of step t, and one ballot checks every predicted comparison
+ * against the evaluated values.  Returns m: steps 0 .. m-1 are exactly the serial routine's steps (state updated to after
+ * step m-1); m < L = the prediction of step m was wrong. */
+__device__ __noinline__ int hfg_fit_pred_round_dev(HfgFitState *st, const double *co, double trunc, double sum_x, double sum_w, int lane,
+                                                   int L, double *snap, long long *clk) {
     const double inv_phi = (sqrt(5.0) - 1.0) / 2.0, inv_phi2 = (3.0 - sqrt(5.0)) / 2.0;
+    const unsigned FULLW = 0xffffffffu;
+    const double xs = co[0], c1 = co[1], c2 = co[2], c3 = co[3], c4 = co[4];
+    const double y1 = st->y1, y2 = st->y2;
+    double slo = st->lo, sx1 = st->x1, sx2 = st->x2, shi = st->hi, sspan = st->span;
+    const unsigned snap_s = (unsigned) __cvta_generic_to_shared(snap);
+    /* who holds the value at x1 / x2: 0, 1 the round's y1, y2; 2 + t the point of step t */
+    int i1 = 0, i2 = 1;
+#pragma unroll 1
+    for (int t = 0; t < L; t++) {
+        /* both points on one side of the maximum: the nearer one is higher; x* between them: the polynomial decides */
+        int b;
+        if (sx2 <= xs) b = 0;
+        else if (sx1 >= xs) b = 1;
+        else {
+            const double d1 = sx1 - xs, d2 = sx2 - xs;
+            const double p1 = d1 * fma(d1, fma(d1, fma(d1, c4, c3), c2), c1), p2 = d2 * fma(d2, fma(d2, fma(d2, c4, c3), c2), c1);
+            b = p1 > p2;
+        }
+        int word = i1 | (i2 << 6) | (b << 12); /* the operands and the predicted outcome of step t's comparison */
+        sspan = inv_phi * sspan;
+        double xn;
+        if (b) {
+            shi = sx2; sx2 = sx1; i2 = i1;
+            sx1 = slo + inv_phi2 * sspan;
+            xn = sx1;
+            i1 = 2 + t;
+        } else {
+            slo = sx1; sx1 = sx2; i1 = i2;
+            sx2 = slo + inv_phi * sspan;
+            xn = sx2;
+            i2 = 2 + t;
+        }
+        word |= (i1 << 13) | (i2 << 19); /* the holders after step t */
+        if (lane == 0) {
+            const unsigned row = snap_s + 64u * (unsigned) t;
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row), "d"(xn), "d"(slo) : "memory");
+            asm volatile("st.shared.v2.f64 [%0+16], {%1, %2};" ::"r"(row), "d"(sx1), "d"(sx2) : "memory");
+            asm volatile("st.shared.v2.f64 [%0+32], {%1, %2};" ::"r"(row), "d"(shi), "d"(sspan) : "memory");
+            asm volatile("st.shared.u32 [%0+48], %1;" ::"r"(row), "r"(word) : "memory");
+        }
+    }
+    __syncwarp();
+    if (clk && lane == 0) clk[14] = clock64();
+    double4 ra;
+    double2 rb;
+    int word;
+    {
+        const unsigned row = snap_s + 64u * (unsigned) (lane < L ? lane : 0);
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ra.x), "=d"(ra.y) : "r"(row));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(ra.z), "=d"(ra.w) : "r"(row));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+32];" : "=d"(rb.x), "=d"(rb.y) : "r"(row));
+        asm volatile("ld.shared.u32 %0, [%1+48];" : "=r"(word) : "r"(row));
+    }
+    const int ca = word & 63, cb = (word >> 6) & 63, pb = (word >> 12) & 1, a1 = (word >> 13) & 63, a2 = (word >> 19) & 63;
+    const double ynew = lane < L ? hfg_objective_dev(ra.x, trunc, sum_x, sum_w) : 0.0;
+    if (clk && lane == 0) clk[13] = clock64();
+    /* the evaluated values behind every comparison, then the first step whose prediction was wrong */
+    const double ya_s = __shfl_sync(FULLW, ynew, ca < 2 ? 0 : ca - 2), yb_s = __shfl_sync(FULLW, ynew, cb < 2 ? 0 : cb - 2);
+    const double ya = ca == 0 ? y1 : ca == 1 ? y2 : ya_s, yb = cb == 0 ? y1 : cb == 1 ? y2 : yb_s;
+    const unsigned wrong = __ballot_sync(FULLW, lane < L && (int) (ya > yb) != pb);
+    const int m = wrong ? __ffs(wrong) - 1 : L;
+    const double n1_s = __shfl_sync(FULLW, ynew, a1 < 2 ? 0 : a1 - 2), n2_s = __shfl_sync(FULLW, ynew, a2 < 2 ? 0 : a2 - 2);
+    const double n1 = a1 == 0 ? y1 : a1 == 1 ? y2 : n1_s, n2 = a2 == 0 ? y1 : a2 == 1 ? y2 : n2_s;
+    if (m > 0) {
+        st->lo = __shfl_sync(FULLW, ra.y, m - 1);
+        st->x1 = __shfl_sync(FULLW, ra.z, m - 1);
+        st->x2 = __shfl_sync(FULLW, ra.w, m - 1);
+        st->hi = __shfl_sync(FULLW, rb.x, m - 1);
+        st->span = __shfl_sync(FULLW, rb.y, m - 1);
+        st->y1 = __shfl_sync(FULLW, n1, m - 1);
+        st->y2 = __shfl_sync(FULLW, n2, m - 1);
+    }
+    __syncwarp();
+    return m;
+}
+
+/* The golden-section rate fit of hfg_mstep_inl.h (hfg_fit_rate / hfg_fit_rate_warp) for a GROUP of `gsize` consecutive
+ * threads (a power of two >= 32), with the bits of the serial routine.  The point evaluated at a step depends only on the
+ * outcomes of the comparisons so far, so a step's objective value can be computed before the comparisons that lead to it:
+ *   - TREE round: the 2 + 4 + ... + 2^D candidate points of the next D steps (D = 7 for 256 threads) one per thread, then
+ *     every thread walks the true path through the group's buffer `fb` (gsize doubles);
+ *   - PREDICTED round (hfg_fit_pred_round_dev): the objective is concave with its maximum at x*, which a few Newton steps
+ *     inside the bracket give; a 4th-order Taylor polynomial around x* predicts the comparisons of up to 32 steps, which
+ *     are then all evaluated at once and checked.  A wrong prediction (two values closer than the polynomial's error) ends
+ *     the round there and the next round is a TREE round.  Every warp of the group does the same work on the same values.
+ * ~34 dependent objective evaluations become 1 TREE round + 1 PREDICTED round in the common case.  The group synchronises
+ * on its own named barrier `bar`: all gsize threads of the group must call it, other groups and warps are not involved.
+ * `st8` = 24 doubles of group scratch; st8[7] receives tree rounds | predicted rounds << 8 | serial steps << 16; `snap` = 256 doubles for the predicted rounds.  `x_hint`: where Newton starts
+ * (the rate of the previous EM iteration).
+ * Scouting (see above): start_mode 1 skips the first two evaluations; max_rounds bounds the rounds. */
+__device__ __forceinline__ void group_sync(int bar, int n) { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory"); }
+__device__ __noinline__ double hfg_fit_rate_cta(bool active, int gtid, int gsize, int bar, double trunc, double sum_x, double sum_w,
+                                                double *st8, double *fb, bool predict, long long *clk, int start_mode, int max_rounds, double x_hint, double *snap) {
+    const double inv_phi = (sqrt(5.0) - 1.0) / 2.0, inv_phi2 = (3.0 - sqrt(5.0)) / 2.0;
+    const int lane = gtid & 31;
     int D = 0;
     while ((4 << D) - 2 <= gsize) D++; /* 2^(D+1) - 2 nodes fit the group */
-    double lo = 0.0, hi = trunc, span = hi - lo;
-    double result = (hi + lo) / 2.0;
-    if (active && !(span > GOLDEN_TOL)) active = false; /* hmm_utils.c: the interval is already short */
+    HfgFitState s;
+    s.lo = 0.0;
+    s.hi = trunc;
+    s.span = s.hi - s.lo;
+    double result = (s.hi + s.lo) / 2.0;
+    if (active && !(s.span > GOLDEN_TOL)) active = false; /* hmm_utils.c: the interval is already short */
     int total = 0;
-    double x1 = lo + inv_phi2 * span, x2 = lo + inv_phi * span, y1 = 0.0, y2 = 0.0;
+    s.x1 = s.lo + inv_phi2 * s.span;
+    s.x2 = s.lo + inv_phi * s.span;
+    s.y1 = 1.0;
+    s.y2 = 2.0;
     if (active) {
-        const int steps = (int) ceil(log(GOLDEN_TOL / span) / log(inv_phi));
+        const int steps = (int) ceil(log(GOLDEN_TOL / s.span) / log(inv_phi));
         total = steps - 1;
-        if (gtid < 2) st8[gtid] = hfg_trunc_exp_objective(gtid == 0 ? x1 : x2, trunc, sum_x, sum_w);
+        if (gtid < 2 && start_mode == 0) st8[gtid] = hfg_objective_dev(gtid == 0 ? s.x1 : s.x2, trunc, sum_x, sum_w);
+        if (predict && start_mode == 0 && gsize >= 64 && gtid >= 32 && gtid < 64) {
+            /* x* and the polynomial on the group's second warp, beside the first two evaluations */
+            double c[5];
+            const double x0 = x_hint > s.lo && x_hint < s.hi ? x_hint : 0.5 * (s.lo + s.hi);
+            hfg_fit_newton_dev(x0, s.lo, s.hi, trunc, sum_x, sum_w, c);
+            if (lane == 0) {
+                st8[2] = c[0]; st8[3] = c[1]; st8[4] = c[2]; st8[5] = c[3]; st8[6] = c[4];
+            }
+        }
     }
     group_sync(bar, gsize);
-    if (active) {
-        y1 = st8[0];
-        y2 = st8[1];
+    if (active && start_mode == 0) {
+        s.y1 = st8[0];
+        s.y2 = st8[1];
     }
+    if (clk && gtid == 0) clk[12] = clock64();
     /* node -> (step t of the round, outcomes b_0..b_t of its comparisons, b_0 in the top bit) */
     int my_t = 0;
     while ((4 << my_t) - 2 <= gtid) my_t++;
     const int my_bits = gtid - ((2 << my_t) - 2);
-    int k = 0;
-    /* (active, total and k are the same in every thread of the group: uniform loop) */
-    while (active && k < total) {
-        const int d = total - k < D ? total - k : D;
-        if (active && k < total && my_t < d) {
-            /* positions along this node's assumed path (the arithmetic of the serial loop, same order) */
-            double slo = lo, sx1 = x1, sx2 = x2, sspan = span, xnew = x1;
-            for (int t = 0; t <= my_t; t++) {
-                const int b = (my_bits >> (my_t - t)) & 1;
-                sspan = inv_phi * sspan;
-                if (b) {
-                    sx2 = sx1;
-                    sx1 = slo + inv_phi2 * sspan;
-                    xnew = sx1;
-                } else {
-                    slo = sx1;
-                    sx1 = sx2;
-                    sx2 = slo + inv_phi * sspan;
-                    xnew = sx2;
+    int k = 0, n_tree = 0, n_pred = 0;
+    bool tree = !predict, have_star = false; /* predicted rounds first: x* from the previous rate */
+    double co[5];
+    if (active && predict && start_mode == 0 && gsize >= 64) {
+        have_star = true;
+        co[0] = st8[2]; co[1] = st8[3]; co[2] = st8[4]; co[3] = st8[5]; co[4] = st8[6];
+    }
+    int n_serial = 0;
+    /* (active, total, k and tree are the same in every thread of the group: uniform loop) */
+    while (active && k < total && n_tree + n_pred + n_serial < max_rounds) {
+        if (tree || !predict) {
+            const int d = total - k < D ? total - k : D;
+            if (my_t < d) {
+                /* positions along this node's assumed path (the arithmetic of the serial loop, same order) */
+                double slo = s.lo, sx1 = s.x1, sx2 = s.x2, sspan = s.span, xnew = s.x1;
+                for (int t = 0; t <= my_t; t++) {
+                    const int b = (my_bits >> (my_t - t)) & 1;
+                    sspan = inv_phi * sspan;
+                    if (b) {
+                        sx2 = sx1;
+                        sx1 = slo + inv_phi2 * sspan;
+                        xnew = sx1;
+                    } else {
+                        slo = sx1;
+                        sx1 = sx2;
+                        sx2 = slo + inv_phi * sspan;
+                        xnew = sx2;
+                    }
                 }
+                fb[gtid] = hfg_objective_dev(xnew, trunc, sum_x, sum_w);
             }
-            fb[gtid] = hfg_trunc_exp_objective(xnew, trunc, sum_x, sum_w);
-        }
-        group_sync(bar, gsize);
-        if (active && k < total) {
+            group_sync(bar, gsize);
             /* the true path */
             int path = 0;
             for (int t = 0; t < d; t++) {
-                const int b = y1 > y2;
+                const int b = s.y1 > s.y2;
                 path = (path << 1) | b;
                 const double y = fb[((2 << t) - 2) + path];
-                span = inv_phi * span;
+                s.span = inv_phi * s.span;
                 if (b) {
-                    hi = x2; x2 = x1; y2 = y1;
-                    x1 = lo + inv_phi2 * span;
-                    y1 = y;
+                    s.hi = s.x2; s.x2 = s.x1; s.y2 = s.y1;
+                    s.x1 = s.lo + inv_phi2 * s.span;
+                    s.y1 = y;
                 } else {
-                    lo = x1; x1 = x2; y1 = y2;
-                    x2 = lo + inv_phi * span;
-                    y2 = y;
+                    s.lo = s.x1; s.x1 = s.x2; s.y1 = s.y2;
+                    s.x2 = s.lo + inv_phi * s.span;
+                    s.y2 = y;
                 }
             }
             k += d;
+            n_tree++;
+            tree = false;
+            group_sync(bar, gsize); /* the buffer is read before the next round writes it */
+            continue;
         }
-        group_sync(bar, gsize); /* the buffer is read before the next round writes it */
+        if (have_star && n_pred > 0 && total - k <= 2) {
+            /* one or two steps left over by a full predicted round: the serial routine's steps as they are */
+            const int b = s.y1 > s.y2;
+            s.span = inv_phi * s.span;
+            if (b) {
+                s.hi = s.x2; s.x2 = s.x1; s.y2 = s.y1;
+                s.x1 = s.lo + inv_phi2 * s.span;
+                s.y1 = hfg_objective_dev(s.x1, trunc, sum_x, sum_w);
+            } else {
+                s.lo = s.x1; s.x1 = s.x2; s.y1 = s.y2;
+                s.x2 = s.lo + inv_phi * s.span;
+                s.y2 = hfg_objective_dev(s.x2, trunc, sum_x, sum_w);
+            }
+            k++;
+            n_serial++;
+            continue;
+        }
+        /* warp 0 of the group runs the round, the others pick the result up from the group's scratch (two buffers in turn) */
+        const int L = total - k < 32 ? total - k : 32;
+        double *buf = st8 + 8 + 8 * (n_pred & 1);
+        if (gtid < 32) {
+            if (!have_star) {
+                double x0 = n_tree ? (s.y1 > s.y2 ? s.x1 : s.x2) : x_hint;
+                if (!(x0 > s.lo && x0 < s.hi)) x0 = 0.5 * (s.lo + s.hi);
+                hfg_fit_newton_dev(x0, s.lo, s.hi, trunc, sum_x, sum_w, co);
+            }
+            const int mm = hfg_fit_pred_round_dev(&s, co, trunc, sum_x, sum_w, lane, L, snap, n_pred == 0 ? clk : nullptr);
+            if (lane == 0) {
+                buf[0] = s.lo; buf[1] = s.x1; buf[2] = s.x2; buf[3] = s.hi; buf[4] = s.span; buf[5] = s.y1; buf[6] = s.y2;
+                buf[7] = (double) mm;
+            }
+        }
+        have_star = true;
+        group_sync(bar, gsize);
+        s.lo = buf[0]; s.x1 = buf[1]; s.x2 = buf[2]; s.hi = buf[3]; s.span = buf[4]; s.y1 = buf[5]; s.y2 = buf[6];
+        const int m = (int) buf[7];
+        k += m;
+        if (clk && gtid == 0 && n_pred == 0) clk[15] = clock64();
+        n_pred++;
+        tree = m < L; /* the step the polynomial got wrong is taken by a TREE round */
     }
-    if (active) result = y1 > y2 ? (lo + x2) / 2.0 : (x1 + hi) / 2.0;
+    if (active) result = s.y1 > s.y2 ? (s.lo + s.x2) / 2.0 : (s.x1 + s.hi) / 2.0;
+    if (gtid == 0) st8[7] = (double) (n_tree | (n_pred << 8) | (n_serial << 16));
     return result;
 }
 
@@ -361,9 +563,40 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
     __syncthreads();
     if (!*s_last) return;
     __threadfence();
+    /* SCOUT warps (see hfg_fit_rate_cta): the last four warps of a large CTA pre-execute the four pieces of the rate fit on dummy
+     * numbers while the others -- the NW worker threads, which synchronise on named barrier 14 -- run the tail proper */
+    constexpr int SCOUTS = THREADS >= 512 ? 4 : 0;
+    const int PER_REGION = (int) ((sizeof(hfg_region_params) + sizeof(hfg_region_stats)) / sizeof(double)) + 282;
+    const bool scouting = SCOUTS > 0 && A.em_mode == 1 && A.model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && !(A.dbg & 32) &&
+                          A.work_doubles - HFG_TAIL_TOP >= PER_REGION + THREADS + WARPS * 128;
+    const int NW = scouting ? THREADS - 32 * SCOUTS : THREADS;
+    auto tsync = [&]() { asm volatile("bar.sync 14, %0;" ::"r"(NW) : "memory"); };
+    if (tid >= NW) {
+        const int sc = warp - NW / 32;
+        double *scr = work + A.work_doubles - HFG_TAIL_TOP + sc * 64; /* 24 + 32 doubles of scratch per scout, out of the workers' way */
+        double sink = 0.0;
+        if (sc == 0) sink = hfg_fit_rate_cta(true, lane, 32, 15, 7.25, 1000.0, 2000.0, scr, scr + 24, false, nullptr, 0, 0, 0.0, nullptr);
+        if (sc == 1) sink = hfg_fit_rate_cta(true, lane, 32, 13, 7.25, 1000.0, 2000.0, scr, scr + 24, false, nullptr, 1, 1, 0.0, nullptr);
+        if (sc == 2) {
+            double co[5];
+            hfg_fit_newton_dev(1.7, 1.6, 1.9, 7.25, 1000.0, 2000.0, co);
+            sink = co[0] + co[4];
+        }
+        if (sc == 3) {
+            HfgFitState st = {1.6, 1.7146, 1.7854, 1.9, 0.3, -1.0, -1.01};
+            const double co[5] = {1.74, 1.0e-3, -300.0, 90.0, -40.0};
+            sink = (double) hfg_fit_pred_round_dev(&st, co, 7.25, 1000.0, 2000.0, lane, 26, hfg_align16(work + A.work_doubles - HFG_TAIL_TOP + 256), nullptr) + st.lo;
+        }
+        if (lane == 0) scr[60] = sink;
+        if (lane == 0 && sc == 3) (A.phase_clock + (size_t) gridDim.x * HFG_PC_STRIDE)[9] = clock64(); /* the longest scout's end */
+        return;
+    }
     {
         /* tail clocks live in the row behind the CTAs' rows: 0 tail start, 1 totals in shared memory, 2 statistics block
-         * written, 3 / 4 exchange start / end (multi-GPU), 5 M-step done, 6 end, 7 CTA that ran the tail */
+         * written, 3 / 4 exchange start / end (multi-GPU), 5 M-step done, 6 end, 7 CTA that ran the tail, 8 M-step copy-in
+         * done, 9 last scout done, 10 updates done (thread 0), 11 rate-fit rounds of group 0 (tree | predicted << 8 |
+         * serial << 16), 12-15 inside group 0's rate fit: first evaluations done, predicted round's evaluation done, its
+         * walk done, round done */
         long long *tail_clock = A.phase_clock + (size_t) gridDim.x * HFG_PC_STRIDE;
         if (tid == 0) {
             *A.ticket = 0; /* for the next launch */
@@ -378,7 +611,7 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
         {
             constexpr int QU = 4;
             const int NQ = R * NSTAT;
-            for (int q0 = warp * QU; q0 < NQ; q0 += WARPS * QU) {
+            for (int q0 = warp * QU; q0 < NQ; q0 += (NW / 32) * QU) {
                 double sum[QU];
 #pragma unroll
                 for (int u = 0; u < QU; u++) sum[u] = 0.0;
@@ -403,10 +636,10 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
                 }
             }
         }
-        __syncthreads();
+        tsync();
         if (tid == 0) tail_clock[1] = clock64();
         /* the hfg_region_stats layout (include/hfg.h), one output element per thread: no zero-fill, no read-back */
-        for (int qq = tid; qq < R * SD; qq += THREADS) {
+        for (int qq = tid; qq < R * SD; qq += NW) {
             const int r = qq / SD, i = qq % SD;
             const double *tot = acc + (size_t) r * NSTAT;
             const int MC = HFG_MAX_COMPS, BL = HFG_NS * HFG_MAX_COMPS;
@@ -434,7 +667,7 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
 
         /* ---- fused collective: sum the block over all ranks through peer memory (see hfg_estep.cuh) ---- */
         if (A.n_ranks > 1) {
-            __syncthreads();
+            tsync();
             const int n = A.out_doubles, N = A.n_ranks;
             const unsigned long long e = *A.epoch + 1;
             const size_t box = (size_t) (e & 1) * HFG_MAX_PEERS * n;
@@ -442,10 +675,10 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
             if (tid == 0) tail_clock[3] = clock64();
             for (int p = 0; p < N; p++) {
                 double *dst = A.peer_box[p] + box + (size_t) A.rank * n;
-                for (int qq = tid; qq < n; qq += THREADS) dst[qq] = A.out[qq];
+                for (int qq = tid; qq < n; qq += NW) dst[qq] = A.out[qq];
             }
             __threadfence_system();
-            __syncthreads();
+            tsync();
             if (tid < N) {
                 volatile unsigned long long *c =
                     (volatile unsigned long long *) (A.peer_box[tid] + cnt_base) + (e & 1) * HFG_MAX_PEERS + A.rank;
@@ -463,9 +696,9 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
                 }
             }
             __threadfence_system();
-            __syncthreads();
+            tsync();
             const double *in = A.peer_box[A.rank] + box;
-            for (int qq = tid; qq < n; qq += THREADS) {
+            for (int qq = tid; qq < n; qq += NW) {
                 double sum = 0.0;
                 if (qq == n - 1) { /* error flags: bitwise OR over ranks */
                     int fl = 0;
@@ -476,7 +709,7 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
                 }
                 A.out[qq] = sum;
             }
-            __syncthreads();
+            tsync();
             if (tid == 0) {
                 if (__ldcg(A.err_flags) & 4) A.out[n - 1] = (double) ((int) A.out[n - 1] | 4);
                 *A.epoch = e;
@@ -486,7 +719,7 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
 
         /* ---- device-resident EM: M-step of every region, bookkeeping ------------------------------------------ */
         if (A.em_mode) {
-            __syncthreads();
+            tsync();
             const int flags = (int) A.out[(size_t) R * SD + 1];
             int settled = 1;
             if (A.em_mode == 1 && flags == 0) {
@@ -496,19 +729,19 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
                  * (hfg_fit_rate_cta).  The pieces touch disjoint parameters; the rate fit uses the OLD truncation point, which
                  * follows the new Hap mean afterwards. */
                 constexpr int PD = (int) (sizeof(hfg_region_params) / sizeof(double));
-                const int per_region = PD + SD + 8;
+                const int per_region = PD + SD + 282; /* 24 doubles of group scratch + [32][8] of the predicted rounds, 16-byte aligned */
                 constexpr int FIT_THREADS = THREADS / 2 >= 256 ? THREADS / 2 : THREADS - 64; /* the rest runs the other updates */
-                int RB = (A.work_doubles - THREADS - WARPS * 128) / per_region;
+                int RB = (A.work_doubles - HFG_TAIL_TOP - THREADS - WARPS * 128) / per_region;
                 RB = RB < 1 ? 1 : (RB > R ? R : RB);
                 if (RB > FIT_THREADS / 32) RB = FIT_THREADS / 32;
-                if (RB > 15) RB = 15; /* named barriers 1..15 */
+                if (RB > 12) RB = 12; /* named barriers 1..12 (13-15: the scouts' and the workers') */
                 for (int r0 = 0; r0 < R; r0 += RB) {
                     const int nb = min(RB, R - r0);
                     double *mscr = work + (size_t) nb * per_region; /* [WARPS][128] warp scratch, then the exchange buffers */
-                    for (int i = tid; i < nb * PD; i += THREADS)
+                    for (int i = tid; i < nb * PD; i += NW)
                         work[(size_t) (i / PD) * per_region + i % PD] = reinterpret_cast<const double *>(&A.em_params[r0])[i];
-                    for (int i = tid; i < nb * SD; i += THREADS) work[(size_t) (i / SD) * per_region + PD + i % SD] = A.out[(size_t) r0 * SD + i];
-                    __syncthreads();
+                    for (int i = tid; i < nb * SD; i += NW) work[(size_t) (i / SD) * per_region + PD + i % SD] = A.out[(size_t) r0 * SD + i];
+                    tsync();
                     if (tid == 0) tail_clock[8] = clock64();
                     /* the rate fits of the batch on the first fit_threads threads (one power-of-two group each, own named
                      * barrier), the Gaussian / transition updates on the remaining warps, side by side */
@@ -522,13 +755,15 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
                         /* TruncExponential: golden-section fit against the truncation point still in force (hmm_utils.c:1872-1882) */
                         const bool fit = A.model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN && MIN_COUNT_FOR_UPDATE < st->lambda_den;
                         const double trunc = p->trunc_point, sx = st->lambda_num, sw = st->lambda_den, old = p->lambda;
-                        const double v = hfg_fit_rate_cta(fit, gtid, gsize, 1 + g, trunc, sx, sw, mp + PD + SD, mscr + WARPS * 128 + (size_t) g * gsize);
+                        const double v = hfg_fit_rate_cta(fit, gtid, gsize, 1 + g, trunc, sx, sw, mp + PD + SD, mscr + WARPS * 128 + (size_t) g * gsize,
+                                                          !(A.dbg & 16), g == 0 ? tail_clock : nullptr, 0, 1000, old, hfg_align16(mp + PD + SD + 24));
+                        if (tid == 0) tail_clock[11] = (long long) mp[PD + SD + 7];
                         if (fit) {
                             settled &= hfg_settled(old, v, A.em_tol, 1.0e-4);
                             if (gtid == 0) p->lambda = v;
                         }
                     } else if (tid >= FIT_THREADS) {
-                        for (int task = warp - FIT_THREADS / 32; task < 2 * nb; task += WARPS - FIT_THREADS / 32) {
+                        for (int task = warp - FIT_THREADS / 32; task < 2 * nb; task += NW / 32 - FIT_THREADS / 32) {
                             double *mp = work + (size_t) (task >> 1) * per_region;
                             hfg_region_params *p = reinterpret_cast<hfg_region_params *>(mp);
                             const hfg_region_stats *st = reinterpret_cast<const hfg_region_stats *>(mp + PD);
@@ -537,19 +772,25 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
                         }
                     }
                     if (tid == 0) tail_clock[10] = clock64();
-                    __syncthreads();
+                    tsync();
                     /* the truncation point follows the NEW Hap mean, after the fit used the old one */
                     if (tid < nb && A.model_type == HFG_MODEL_TRUNC_EXP_GAUSSIAN) {
                         hfg_region_params *p = reinterpret_cast<hfg_region_params *>(work + (size_t) tid * per_region);
                         p->trunc_point = p->mean[HFG_STATE_HAP][0] * TRUNC_POINT_FRACTION;
                     }
-                    __syncthreads();
-                    for (int i = tid; i < nb * PD; i += THREADS)
+                    tsync();
+                    for (int i = tid; i < nb * PD; i += NW)
                         reinterpret_cast<double *>(&A.em_params[r0])[i] = work[(size_t) (i / PD) * per_region + i % PD];
-                    __syncthreads();
+                    tsync();
                 }
             }
-            const int all_settled = __syncthreads_and(settled);
+            /* AND over the worker threads (the scouts are gone): through shared memory */
+            int *s_settled = reinterpret_cast<int *>(work + A.work_doubles - 1);
+            if (tid == 0) *s_settled = 1;
+            tsync();
+            if (!__all_sync(0xffffffffu, settled) && lane == 0) atomicAnd(s_settled, 0);
+            tsync();
+            const int all_settled = *s_settled;
             if (tid == 0) {
                 const int k = A.em_state[1];
                 if (k < A.em_max_logliks) A.em_logliks[k] = A.out[(size_t) R * SD];
@@ -565,9 +806,9 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
             }
         }
         /* results straight into the caller-visible pinned block, error flags cleared for the next launch */
-        __syncthreads();
+        tsync();
         if (A.out_host)
-            for (int qq = tid; qq < A.out_doubles; qq += THREADS) A.out_host[qq] = A.out[qq];
+            for (int qq = tid; qq < A.out_doubles; qq += NW) A.out_host[qq] = A.out[qq];
         if (tid == 0) {
             *A.err_flags = 0;
             tail_clock[6] = clock64();

@@ -49,4 +49,4 @@ tail = c[-1]
 print("device EM iteration ms", [round(g.em_enqueued_ms(i), 4) for i in range(4)], "; tail: totals", int(tail[1] - tail[0]),
       "statistics block", int(tail[2] - tail[1]), "M-step", int(tail[5] - tail[2]), "end", int(tail[6] - tail[5]), "cycles;",
       "M-step: copy-in", int(tail[8] - tail[2]), "updates (thread 0)", int(tail[10] - tail[8]),
-      "rest", int(tail[5] - tail[10]))
+      "rest", int(tail[5] - tail[10]), "; rate fit rounds: tree", int(tail[11]) & 255, "predicted", (int(tail[11]) >> 8) & 255, "serial steps", int(tail[11]) >> 16)
