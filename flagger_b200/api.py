@@ -33,6 +33,10 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.hfg_last_error.restype = C.c_char_p
         L.hfg_last_error.argtypes = [C.c_void_p]
+        L.hfg_batch_last_error.restype = C.c_char_p
+        L.hfg_batch_last_error.argtypes = [C.c_void_p]
+        L.hfg_batch_destroy.restype = None
+        L.hfg_batch_destroy.argtypes = [C.c_void_p]
         L.hfg_num_windows.restype = C.c_int64
         L.hfg_kernel_launches.restype = C.c_int64
         L.hfg_last_estep_kernel_ms.restype = C.c_double
@@ -57,7 +61,8 @@ EXPORTED_SYMBOLS = (
     "hfg_debug_layout_compare", "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_peer_barrier", "hfg_read_cov",
     "hfg_read_bin", "hfg_cov_free", "hfg_write_summary_tsv", "hfg_benchmark_scores", "hfg_params_feasible", "hfg_squarem_alpha_rate",
     "hfg_squarem_prime", "hfg_squarem_shrink", "hfg_squarem_iteration", "hfg_run_em_accelerated",
-    "hfg_release_cached_memory", "hfg_nb_emission_table", "hfg_nb_stats_from_histogram", "hfg_digammal", "hfg_debug_gunzip",
+    "hfg_release_cached_memory", "hfg_device_warmup", "hfg_batch_create", "hfg_batch_set_chunks",
+    "hfg_batch_run_em", "hfg_batch_last_error", "hfg_batch_destroy", "hfg_set_max_blocks", "hfg_nb_emission_table", "hfg_nb_stats_from_histogram", "hfg_digammal", "hfg_debug_gunzip",
 )
 
 
@@ -182,6 +187,57 @@ def digamma(x):
     v = np.longdouble(f(np.longdouble(x)))
     hi = np.float64(v)
     return float(hi), float(v - np.longdouble(hi))
+
+
+class HmmFlaggerBatch:
+    """hfg_batch: `n_lanes` contexts over the same chunks on one GPU, each on num_SMs / n_lanes CTAs; run_em fits many
+    (alpha, start parameters) candidates, n_lanes at a time (the alpha tuner's inner loop, tune_alpha_hmm_flagger.py:243-267)."""
+
+    def __init__(self, cfg, workload, n_lanes=8):
+        self.cfg = np.ascontiguousarray(cfg)
+        self._h = C.c_void_p()
+        rc = lib().hfg_batch_create(C.byref(self._h), ptr(self.cfg), C.c_int(int(n_lanes)))
+        if rc != 0:
+            raise HfgError(rc, lib().hfg_last_error(None).decode())
+        self.n_lanes = int(n_lanes)
+        self.n_regions = int(self.cfg["n_regions"][0])
+        chunks = np.ascontiguousarray(workload.chunks)
+        self._check(lib().hfg_batch_set_chunks(self._h, C.c_int32(len(chunks)), ptr(chunks),
+                                               ptr(np.ascontiguousarray(workload.cov, np.uint16)),
+                                               ptr(np.ascontiguousarray(workload.cov_high_mapq, np.uint16)),
+                                               ptr(np.ascontiguousarray(workload.cov_high_clip, np.uint16)),
+                                               ptr(np.ascontiguousarray(workload.region, np.uint8))))
+        self.n_windows = int(workload.n_windows)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HfgError(rc, lib().hfg_batch_last_error(self._h).decode())
+
+    def run_em(self, alphas, params, max_iterations, tol=1e-3, want_labels=True):
+        """alphas [n][4][4]; params: one start set for all runs, or a list of n.  Returns (list of params, list of logliks,
+        labels [n][W] or None), run r exactly what HmmFlaggerGPU.run_em(alphas[r], params[r], ...) returns."""
+        alphas = np.ascontiguousarray(np.asarray(alphas, np.float64).reshape(-1, 16))
+        n = alphas.shape[0]
+        plist = list(params) if isinstance(params, (list, tuple)) else [params] * n
+        pall = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(p).reshape(-1) for p in plist]))
+        logliks = np.zeros((n, max_iterations + 1), np.float64)
+        n_esteps = np.zeros(n, np.int32)
+        labels = np.empty((n, self.n_windows), np.int8) if want_labels else None
+        self._check(lib().hfg_batch_run_em(self._h, C.c_int(n), ptr(alphas), ptr(pall), C.c_int(int(max_iterations)),
+                                           C.c_double(tol), ptr(logliks), ptr(n_esteps), ptr(labels)))
+        R = self.n_regions
+        return ([pall[r * R:(r + 1) * R].copy() for r in range(n)], [logliks[r, :n_esteps[r]].copy() for r in range(n)], labels)
+
+    def close(self):
+        if self._h:
+            lib().hfg_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class HmmFlaggerGPU:

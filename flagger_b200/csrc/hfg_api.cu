@@ -438,6 +438,13 @@ static void *arena_acquire(size_t bytes, int device, size_t *got, int kind) {
     return ptr;
 }
 
+extern "C" int hfg_device_warmup(int device) {
+    if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess)
+        return fail(NULL, HFG_ERR_CUDA, "cannot use CUDA device %d: %s (libhfg has no CPU fallback)", device,
+                    cudaGetErrorString(cudaGetLastError()));
+    return HFG_OK;
+}
+
 extern "C" void hfg_release_cached_memory(void) {
     pthread_mutex_lock(&g_cache_mu);
     for (int i = 0; i < HFG_CACHE_SLOTS; i++)
@@ -1417,6 +1424,105 @@ extern "C" int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *
         return rc;
     }
     return hfg_em_finish(ctx, params, logliks, n_esteps, NULL, labels);
+}
+
+/* ---- batched EM runs (include/hfg.h) ------------------------------------------------------------------------------------ */
+
+struct hfg_batch {
+    int n_lanes;
+    hfg_ctx *lane[16];
+    char err[512];
+};
+
+extern "C" int hfg_set_max_blocks(hfg_ctx *ctx, int max_blocks) {
+    if (!ctx || max_blocks < 0) return HFG_ERR_INVALID;
+    ctx->max_blocks = max_blocks == 0 || max_blocks > ctx->num_sms ? ctx->num_sms : max_blocks;
+    return HFG_OK;
+}
+
+extern "C" const char *hfg_batch_last_error(const hfg_batch *b) { return b ? b->err : g_create_err; }
+
+static int batch_fail(hfg_batch *b, int rc, const hfg_ctx *from) {
+    snprintf(b->err, sizeof(b->err), "%s", hfg_last_error(from));
+    return rc;
+}
+
+extern "C" void hfg_batch_destroy(hfg_batch *b) {
+    if (!b) return;
+    for (int i = 0; i < b->n_lanes; i++) hfg_destroy(b->lane[i]);
+    free(b);
+}
+
+extern "C" int hfg_batch_create(hfg_batch **out, const hfg_config *cfg, int n_lanes) {
+    if (!out || !cfg) return fail(NULL, HFG_ERR_INVALID, "hfg_batch_create: NULL argument");
+    *out = NULL;
+    if (n_lanes < 1 || n_lanes > 16) return fail(NULL, HFG_ERR_INVALID, "hfg_batch_create: n_lanes %d outside 1..16", n_lanes);
+    if (cfg->model_type == HFG_MODEL_NEGATIVE_BINOMIAL)
+        return fail(NULL, HFG_ERR_INVALID, "hfg_batch_create: the negative-binomial model has no device-resident loop to batch");
+    hfg_batch *b = (hfg_batch *) calloc(1, sizeof(hfg_batch));
+    if (!b) return fail(NULL, HFG_ERR_NOMEM, "hfg_batch_create: out of memory");
+    for (int i = 0; i < n_lanes; i++) {
+        const int rc = hfg_create(&b->lane[i], cfg);
+        if (rc != HFG_OK) {
+            hfg_batch_destroy(b);
+            return rc;
+        }
+        b->n_lanes = i + 1;
+        const int per = b->lane[i]->num_sms / n_lanes;
+        hfg_set_max_blocks(b->lane[i], per < 1 ? 1 : per);
+    }
+    *out = b;
+    return HFG_OK;
+}
+
+extern "C" int hfg_batch_set_chunks(hfg_batch *b, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                                    const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region) {
+    if (!b) return HFG_ERR_INVALID;
+    for (int i = 0; i < b->n_lanes; i++) {
+        const int rc = hfg_set_chunks(b->lane[i], n_chunks, chunks, cov, cov_high_mapq, cov_high_clip, region);
+        if (rc != HFG_OK) return batch_fail(b, rc, b->lane[i]);
+    }
+    return HFG_OK;
+}
+
+extern "C" int hfg_batch_run_em(hfg_batch *b, int n_runs, const double *alphas, hfg_region_params *params, int max_iterations,
+                                double convergence_tol, double *logliks, int *n_esteps, int8_t *labels) {
+    if (!b || n_runs < 0 || !alphas || !params || !logliks || !n_esteps) return HFG_ERR_INVALID;
+    if (max_iterations < 0) max_iterations = 0;
+    if (max_iterations + 1 > HFG_EM_LOGLIK_SLOTS) {
+        snprintf(b->err, sizeof(b->err), "hfg_batch_run_em: at most %d iterations per run", HFG_EM_LOGLIK_SLOTS - 1);
+        return HFG_ERR_INVALID;
+    }
+    const int R = b->lane[0]->cfg.n_regions;
+    const int64_t W = b->lane[0]->lay.n_windows;
+    int rc_all = HFG_OK;
+    /* waves of n_lanes runs: every lane's whole loop is queued on its stream before any lane is waited for */
+    for (int r0 = 0; r0 < n_runs; r0 += b->n_lanes) {
+        const int n = n_runs - r0 < b->n_lanes ? n_runs - r0 : b->n_lanes;
+        int rc_lane[16];
+        for (int l = 0; l < n; l++) {
+            hfg_ctx *ctx = b->lane[l];
+            const int r = r0 + l;
+            int rc = hfg_em_begin(ctx, alphas + (size_t) r * 16, params + (size_t) r * R, convergence_tol, max_iterations + 1);
+            for (int it = 0; it < max_iterations && rc == HFG_OK; it++) rc = hfg_em_enqueue(ctx, 0);
+            if (rc == HFG_OK) rc = hfg_em_enqueue(ctx, 1);
+            rc_lane[l] = rc;
+        }
+        for (int l = 0; l < n; l++) {
+            hfg_ctx *ctx = b->lane[l];
+            const int r = r0 + l;
+            int rc = rc_lane[l];
+            if (rc != HFG_OK) {
+                ctx->em_active = 0;
+                cudaStreamSynchronize(ctx->stream);
+            } else {
+                rc = hfg_em_finish(ctx, params + (size_t) r * R, logliks + (size_t) r * (max_iterations + 1), &n_esteps[r], NULL,
+                                   labels ? labels + (size_t) r * W : NULL);
+            }
+            if (rc != HFG_OK && rc_all == HFG_OK) rc_all = batch_fail(b, rc, ctx);
+        }
+    }
+    return rc_all;
 }
 
 /* One outer iteration of the `acceleration` branch of runHMMFlagger (src/hmm_flagger.c:344-416) up to, and excluding,

@@ -14,6 +14,7 @@
  */
 #include <getopt.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,6 +36,12 @@ static const char *stamp(void) {
     time_t t = time(NULL);
     strftime(buf, sizeof(buf), "%Y-%m-%d %H:%M:%S", localtime(&t));
     return buf;
+}
+
+/* the CUDA context (about a second on a B200 box) is created on a thread of its own while the input is read */
+static void *warmup_thread(void *arg) {
+    hfg_device_warmup(*(int *) arg);
+    return NULL;
 }
 
 static double now_s(void) {
@@ -406,6 +413,17 @@ int main(int argc, char *argv[]) {
     }
     const double t_start = now_s();
     if (!input) die("Input path cannot be NULL.");
+    /* one visible device: the driver then initialises that GPU only (an 8-GPU box otherwise pays for all eight) */
+    static int warm_device = 0;
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        char dev[16];
+        snprintf(dev, sizeof(dev), "%d", device);
+        setenv("CUDA_VISIBLE_DEVICES", dev, 1);
+        device = 0;
+    }
+    warm_device = device;
+    pthread_t warm_tid;
+    const int warm_started = pthread_create(&warm_tid, NULL, warmup_thread, &warm_device) == 0;
     if (n_label_names && n_label_names - 1 != HFG_NUM_STATES)
         die("Number of label names does not match the number of labels (4: Err,Dup,Hap,Col)."); /* summary_table.c:1682-1689 */
     if (tol <= 0.0 || tol > 1.0) die("convergence tol should be between 0 and 1.");
@@ -494,6 +512,7 @@ int main(int argc, char *argv[]) {
     /* the GPU context: no CPU fallback -- without a usable device the run stops here */
     hfg_ctx *ctx = NULL;
     ph_t = now_s();
+    if (warm_started) pthread_join(warm_tid, NULL);
     if (hfg_create(&ctx, &cfg) != HFG_OK) die(hfg_last_error(NULL));
     if (hfg_set_chunks(ctx, d->n_chunks, d->chunks, d->cov, d->cov_high_mapq, d->cov_high_clip, d->region) != HFG_OK)
         die(hfg_last_error(ctx));

@@ -212,6 +212,29 @@ int hfg_em_finish(hfg_ctx *ctx, hfg_region_params *params, double *logliks, int 
  * kernel); valid after hfg_em_finish. */
 double hfg_em_enqueued_ms(hfg_ctx *ctx, int i);
 
+/* Batched EM runs: many (alpha, start parameters) candidates over the SAME windows, several at a time on one GPU.  The alpha
+ * tuner of the reference (programs/src/tune_alpha_hmm_flagger.py:243-267) starts one hmm_flagger process per candidate and
+ * input; here a batch holds `n_lanes` contexts over the same chunks, each confined to num_SMs / n_lanes CTAs with its own
+ * stream, so that n_lanes device-resident EM loops (hfg_em_*) run side by side and the fixed per-iteration cost of a small
+ * input (grid barriers, scans, the M-step tail: ~55 us however few the windows) is paid by all of them at once.
+ *   hfg_batch_create      n_lanes in 1..16;
+ *   hfg_batch_set_chunks  the arguments of hfg_set_chunks, given to every lane;
+ *   hfg_batch_run_em      n_runs candidates: alphas [n_runs][16], params [n_runs][n_regions] (in: start, out: fitted),
+ *                         logliks [n_runs][max_iterations + 1], n_esteps [n_runs], labels [n_runs][n_windows] (nullable);
+ *                         each run is exactly hfg_run_em (same loop, same stopping rule) on a smaller grid: labels identical,
+ *                         log-likelihoods equal to rounding (the segment sums associate differently).
+ * Not for HFG_MODEL_NEGATIVE_BINOMIAL (no alpha to tune). */
+typedef struct hfg_batch hfg_batch;
+int hfg_batch_create(hfg_batch **out, const hfg_config *cfg, int n_lanes);
+int hfg_batch_set_chunks(hfg_batch *b, int32_t n_chunks, const hfg_chunk_desc *chunks, const uint16_t *cov,
+                         const uint16_t *cov_high_mapq, const uint16_t *cov_high_clip, const uint8_t *region);
+int hfg_batch_run_em(hfg_batch *b, int n_runs, const double *alphas, hfg_region_params *params, int max_iterations,
+                     double convergence_tol, double *logliks, int *n_esteps, int8_t *labels);
+const char *hfg_batch_last_error(const hfg_batch *b);
+void hfg_batch_destroy(hfg_batch *b);
+/* Upper bound on the CTAs (one per SM) the next hfg_set_chunks of this context may use; 0 = all SMs. */
+int hfg_set_max_blocks(hfg_ctx *ctx, int max_blocks);
+
 /* --accelerate (SQUAREM; SquareAccelerator, hmm.c:820-1098): feasibility of a parameter set (HMM_isFeasible, hmm.c:80-87),
  * the step length from three successive parameter sets (SquareAccelerator_computeRates, hmm.c:1000-1098), the
  * extrapolated + renormalised parameters for a step length (SquareAccelerator_computeValuesForModelPrime, hmm.c:921-997)
@@ -256,6 +279,11 @@ long double hfg_digammal(long double x);
 /* A destroyed context leaves its device arena (one per process) for the next context on the same device, so that a
  * process running job after job does not pay cudaMalloc per job; this returns it to the driver. */
 void hfg_release_cached_memory(void);
+
+/* Creates the CUDA context of `device` (about a second on a B200 box; the reference has no counterpart) so that a host
+ * program can do it on a thread of its own while it reads its input; hfg_create then finds the context in place.
+ * Returns HFG_OK or HFG_ERR_CUDA.  Optional: hfg_create does the same on first use. */
+int hfg_device_warmup(int device);
 
 /* ---- instrumentation ---------------------------------------------------------------------------- */
 

@@ -85,4 +85,10 @@ def test_search_loop_contract(tmp_path, orc):
     assert best == max(h[2] for h in obj.history) and best >= max(h[2] for h in obj.history[:3])
     obj2, best_x2, best2 = run(7)
     assert best2 == best and np.array_equal(best_x2, best_x)  # seeded: reproducible
+    # rounds of proposals (the batched engine's mode): same contract, start points scored as one batch
+    obj3 = tune_alpha.Objective([(cov, OracleEngine(cov, orc, 2, 1e-12))])
+    best_x3, best3 = tune_alpha.optimise(obj3, 0.0, 0.8, n_start=3, n_iter=6, candidate_alpha=synth.HIFI_ALPHA, seed=7, batch=4)
+    assert len(obj3.history) == 9 and [h[0] for h in obj3.history] == ["start"] * 3 + ["iteration"] * 6
+    assert [h[2] for h in obj3.history[:3]] == [h[2] for h in obj.history[:3]]  # same start points, same scores
+    assert best3 == max(h[2] for h in obj3.history) and all(np.all(h[1] >= 0.0) and np.all(h[1] <= 0.8) for h in obj3.history)
     cov.close()
