@@ -594,7 +594,8 @@ int hfg_layout_build_ex(const hfg_config *cfg, int32_t n_chunks, const hfg_chunk
                  (long long) n_runs, capacity);
         return HFG_ERR_INVALID;
     }
-    while (segments_for(runs, n_runs, smax) > capacity) smax += (smax + 7) / 8;
+    /* (one window at a time while segments are short: a step of two windows at ten leaves a sixth of the SMs without work) */
+    while (segments_for(runs, n_runs, smax) > capacity) smax += smax < 64 ? 1 : (smax + 7) / 8;
     const int64_t n_seg = segments_for(runs, n_runs, smax);
     /* keep only as many slots (whole CTAs of `granule` threads) as the segments of this length need: a grid padded with
      * idle CTAs only makes the grid-wide barriers slower */
