@@ -625,7 +625,7 @@ def run_ours(args):
                         "job_ms": [1e3 * j for j in run_jobs]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(wl_full.name), "kernel": "hfg_estep_v3_kernel", "kernel_ms": kernel_s * 1e3,
+                         "traffic": ncu_traffic(wl_full.name) if world == 1 else None, "kernel": "hfg_estep_v3_kernel", "kernel_ms": kernel_s * 1e3,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_WINDOW * wl.n_windows, "peak_source": peak_src},
             "clocks": clocks,
             "loglik_first_last": [logliks[0], logliks[-1]],

@@ -1697,7 +1697,9 @@ extern "C" int hfg_debug_layout_compare(hfg_ctx *ctx, int32_t n_chunks, const hf
 
 static size_t mailbox_bytes(const hfg_ctx *ctx) {
     const size_t n = (size_t) ctx->cfg.n_regions * STATS_DOUBLES + 2;
-    return (2 * HFG_MAX_PEERS * n + 3 * HFG_MAX_PEERS) * sizeof(double); /* slots, arrival counters, barrier counters */
+    /* slots, arrival counters, barrier counters (first-generation protocol: data, fence, flag), then the flagged slots of the
+     * current one: [2 epochs][HFG_MAX_PEERS][n][2] 64-bit words, each 32 bits of data + the 32-bit epoch (hfg_estep_tail) */
+    return (2 * HFG_MAX_PEERS * n + 3 * HFG_MAX_PEERS + 4 * HFG_MAX_PEERS * n) * sizeof(double);
 }
 
 extern "C" size_t hfg_peer_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }

@@ -665,50 +665,61 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
         if (tid == 0) A.out[(size_t) R * SD + 1] = (double) __ldcg(A.err_flags);
         if (tid == 0) tail_clock[2] = clock64();
 
-        /* ---- fused collective: sum the block over all ranks through peer memory (see hfg_estep.cuh) ---- */
+        /* ---- fused collective: sum the block over all ranks through peer memory ---------------------------------------
+         * Every 64-bit word a rank stores into a peer's mailbox carries 32 bits of data and the 32-bit epoch of the exchange,
+         * so data and "it has arrived" travel in ONE store over NVLink (NCCL's LL idea): no fence, no separate counter, no
+         * second trip.  Sender: thread i puts the two halves of out[i] into slot [epoch & 1][own rank][i] of every peer.
+         * Receiver: thread i spins on the two words of [epoch & 1][p][i] for p = 0 .. N-1 (its own value comes straight from
+         * out[i]) and adds them in rank order -- the same order on every rank, so every rank's M-step sees the same bits.
+         * Two epochs' slots suffice: a rank can start exchange e + 2 only after every peer has sent e + 1, i.e. has finished
+         * reading e. */
         if (A.n_ranks > 1) {
             tsync();
             const int n = A.out_doubles, N = A.n_ranks;
             const unsigned long long e = *A.epoch + 1;
-            const size_t box = (size_t) (e & 1) * HFG_MAX_PEERS * n;
-            const size_t cnt_base = (size_t) 2 * HFG_MAX_PEERS * n; /* counters live behind the slots (as u64) */
+            const unsigned long long flag = (e & 0xffffffffull) << 32;
+            const size_t ll_base = (size_t) 2 * HFG_MAX_PEERS * n + 3 * HFG_MAX_PEERS; /* doubles before the flagged slots */
+            const size_t slot0 = ((size_t) (e & 1) * HFG_MAX_PEERS) * n * 2;            /* words */
             if (tid == 0) tail_clock[3] = clock64();
-            for (int p = 0; p < N; p++) {
-                double *dst = A.peer_box[p] + box + (size_t) A.rank * n;
-                for (int qq = tid; qq < n; qq += NW) dst[qq] = A.out[qq];
-            }
-            __threadfence_system();
-            tsync();
-            if (tid < N) {
-                volatile unsigned long long *c =
-                    (volatile unsigned long long *) (A.peer_box[tid] + cnt_base) + (e & 1) * HFG_MAX_PEERS + A.rank;
-                *c = e;
-                __threadfence_system();
-                /* wait for sender `tid` in the local mailbox (bounded: a lost peer becomes an error, not a hang) */
-                volatile unsigned long long *mine =
-                    (volatile unsigned long long *) (A.peer_box[A.rank] + cnt_base) + (e & 1) * HFG_MAX_PEERS + tid;
-                const long long t0 = clock64();
-                while (*mine < e) {
-                    if (clock64() - t0 > 4000000000LL) { /* ~2 s */
-                        atomicOr(A.err_flags, 4);
-                        break;
-                    }
+            for (int qq = tid; qq < n; qq += NW) {
+                const unsigned long long v = (unsigned long long) __double_as_longlong(A.out[qq]);
+                const unsigned long long w0 = (v & 0xffffffffull) | flag, w1 = (v >> 32) | flag;
+                for (int p = 0; p < N; p++) {
+                    if (p == A.rank) continue;
+                    unsigned long long *dst =
+                        reinterpret_cast<unsigned long long *>(A.peer_box[p] + ll_base) + slot0 + ((size_t) A.rank * n + qq) * 2;
+                    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
                 }
             }
-            __threadfence_system();
-            tsync();
-            const double *in = A.peer_box[A.rank] + box;
+            const unsigned long long *in = reinterpret_cast<const unsigned long long *>(A.peer_box[A.rank] + ll_base) + slot0;
+            const long long t0 = clock64();
+            bool lost = false;
             for (int qq = tid; qq < n; qq += NW) {
                 double sum = 0.0;
-                if (qq == n - 1) { /* error flags: bitwise OR over ranks */
-                    int fl = 0;
-                    for (int p = 0; p < N; p++) fl |= (int) __ldcv(in + (size_t) p * n + qq);
-                    sum = (double) fl;
-                } else {
-                    for (int p = 0; p < N; p++) sum += __ldcv(in + (size_t) p * n + qq);
+                int fl = 0;
+                for (int p = 0; p < N; p++) {
+                    double v;
+                    if (p == A.rank) {
+                        v = A.out[qq];
+                    } else {
+                        const unsigned long long *src = in + ((size_t) p * n + qq) * 2;
+                        unsigned long long w0, w1;
+                        for (;;) {
+                            asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(src) : "memory");
+                            if ((w0 & 0xffffffff00000000ull) == flag && (w1 & 0xffffffff00000000ull) == flag) break;
+                            if (clock64() - t0 > 4000000000LL) { /* ~2 s: a lost peer becomes an error, not a hang */
+                                lost = true;
+                                break;
+                            }
+                        }
+                        v = __longlong_as_double((long long) ((w0 & 0xffffffffull) | (w1 << 32)));
+                    }
+                    if (qq == n - 1) fl |= (int) v; /* error flags: bitwise OR over ranks */
+                    else sum += v;
                 }
-                A.out[qq] = sum;
+                A.out[qq] = qq == n - 1 ? (double) fl : sum;
             }
+            if (lost) atomicOr(A.err_flags, 4);
             tsync();
             if (tid == 0) {
                 if (__ldcg(A.err_flags) & 4) A.out[n - 1] = (double) ((int) A.out[n - 1] | 4);
