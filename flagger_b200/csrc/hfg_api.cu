@@ -279,9 +279,9 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         ctx->kernel = nb ? (const void *) hfg_estep_v3_kernel<HFG3_THREADS, true> : (const void *) hfg_estep_v3_kernel<HFG3_THREADS>;
         /* HFG_THREADS: A/B switch of the CTA size (fewer, longer segments: cheaper scans, fewer warps to hide latency) */
         const int want = getenv("HFG_THREADS") ? atoi(getenv("HFG_THREADS")) : 0;
-        if (!nb && (want == 128 || want == 256 || want == 320 || want == 384 || want == 512 || want == 640)) {
+        if (!nb && (want == 256 || want == 320 || want == 384 || want == 512 || want == 640)) {
             ctx->threads = want;
-            ctx->kernel = want == 128 ? (const void *) hfg_estep_v3_kernel<128> : want == 256 ? (const void *) hfg_estep_v3_kernel<256> : want == 320 ? (const void *) hfg_estep_v3_kernel<320>
+            ctx->kernel = want == 256 ? (const void *) hfg_estep_v3_kernel<256> : want == 320 ? (const void *) hfg_estep_v3_kernel<320>
                           : want == 384 ? (const void *) hfg_estep_v3_kernel<384> : want == 512 ? (const void *) hfg_estep_v3_kernel<512>
                                                                                                 : (const void *) hfg_estep_v3_kernel<640>;
         }

@@ -770,10 +770,6 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const EstepArg
             const int t = act ? rb + (int) (((long long) (u - rb) * rstride) % rn) : 0;
             const int p = act ? __ldg(&A.tile_key[t]) : 0, lb = act ? __ldg(&A.tile_begin[t]) : 0;
             const int ln = act ? __ldg(&A.tile_cnt[t]) : 0;
-            const bool dbg_w = (A.dbg & 8) && lane == 0 && blockIdx.x == 0; /* (debug) per-warp clocks, parked in the rows of CTAs 100.. */
-            long long *dbg_c = A.phase_clock + (size_t) (100 + warp) * HFG_PC_STRIDE;
-            const long long dbg_t0 = A.phase_clock[5];
-            if (dbg_w) dbg_c[0] = clock64() - dbg_t0;
             /* The tile's records are consecutive in key-list order.  Lane q takes windows q, q+4, ... of the tile and sums
              * their outer products f (x) b (the four lanes of a quad read 256 contiguous bytes per step); the quad then
              * folds the four sums so that lane pre = q ends with row pre of S[pre][s] = sum_i f_{i-1}[pre] b_i[s]. */
@@ -805,7 +801,6 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const EstepArg
                     }
                 }
                 __syncwarp();
-                if (dbg_w) dbg_c[1] = clock64() - dbg_t0;
                 /* fold over the quad: first the lane pairs (q, q^2) split rows {0,1} / {2,3}, then (q, q^1) split the two rows */
                 const bool up = (q & 2) != 0;
                 double H[8];
@@ -827,7 +822,6 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const EstepArg
              * stragglers needed alone.  Hence a CTA barrier between the memory-bound and the compute-bound half. */
             __syncthreads();
             if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 12] = clock64();
-            if (dbg_w) dbg_c[2] = clock64() - dbg_t0;
             Win w = decode_word(__ldg(&A.kdesc[p]), A.beta0);
             if (w.edge) {
                 w.beta = A.kbeta[3 * (size_t) p];
@@ -893,7 +887,6 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const EstepArg
             }
         }
         if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 13] = clock64();
-        if ((A.dbg & 8) && lane == 0 && blockIdx.x == 0) A.phase_clock[(size_t) (100 + warp) * HFG_PC_STRIDE + 3] = clock64() - A.phase_clock[5];
         __syncthreads();
         if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 14] = clock64();
         /* deterministic CTA reduction: the warps' rows in warp order */

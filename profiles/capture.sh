@@ -24,4 +24,15 @@ done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-binary > $out/${tag}_launches.log 2>&1
 for wl in cfg2 cfg3 cfg4; do python tools/quad_phases.py $wl; done > $out/${tag}_phases.txt 2>&1
+{
+    echo "== scout warps off (HFG_DBG=32), config 2"; HFG_DBG=32 python tools/quad_phases.py cfg2 | tail -1
+    echo "== tree rounds only (HFG_DBG=16), config 2"; HFG_DBG=16 python tools/quad_phases.py cfg2 | tail -1
+    echo "== rate fit: predicted against tree rounds, same bits"; python tools/fit_check.py small cfg2 cfg4 | cut -c1-600
+} > $out/${tag}_mstep_tail.txt 2>&1
+python tools/batch_bench.py 7.5e7 3e8 1.5e9 3e9 > $out/${tag}_batch_bench.txt 2>&1
+{
+    for b in lat_bench pred_bench mio_bench a_bench; do
+        [ -x tools/$b ] && { echo "== tools/$b"; timeout 120 ./tools/$b; }
+    done
+} > $out/${tag}_microbench.txt 2>&1
 echo capture done
