@@ -56,7 +56,7 @@ EXPORTED_SYMBOLS = (
     "hfg_forward_only", "hfg_get_posteriors", "hfg_get_chunk_logliks", "hfg_em_iteration_device",
     "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
     "hfg_host_alloc", "hfg_host_free", "hfg_run_em", "hfg_em_begin", "hfg_em_enqueue", "hfg_em_finish",
-    "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_kernel_launches", "hfg_last_estep_kernel_ms",
+    "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_debug_blocking_steps", "hfg_kernel_launches", "hfg_last_estep_kernel_ms",
     "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
     "hfg_debug_layout_compare", "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_peer_barrier", "hfg_read_cov",
     "hfg_read_bin", "hfg_cov_free", "hfg_write_summary_tsv", "hfg_benchmark_scores", "hfg_params_feasible", "hfg_squarem_alpha_rate",
@@ -389,6 +389,20 @@ class HmmFlaggerGPU:
         f = lib().hfg_em_enqueued_ms
         f.restype = C.c_double
         return float(f(self._h, C.c_int(int(i))))
+
+    def blocking_steps(self, alpha, params, n_steps, stats=None, labels=None, flush_bytes=0, tol=1e-12):
+        """n_steps x [hfg_em_iteration + hfg_mstep] driven from C, as the drop-in binding does: returns (params, stats,
+        logliks, labels, seconds per step)."""
+        alpha = np.ascontiguousarray(alpha, np.float64)
+        params = params.copy()
+        if stats is None:
+            stats = np.zeros(self.n_regions, dtype=_abi.region_stats_dtype)
+        if labels is None:
+            labels = np.empty(self.n_windows, np.int8)
+        secs, ll = np.zeros(n_steps, np.float64), np.zeros(n_steps, np.float64)
+        self._check(lib().hfg_debug_blocking_steps(self._h, ptr(alpha), ptr(params), ptr(stats), ptr(labels), C.c_int(int(n_steps)),
+                                                   C.c_size_t(int(flush_bytes)), C.c_double(tol), ptr(secs), ptr(ll)))
+        return params, stats, ll, labels, secs
 
     def l2_flush(self, nbytes=256 << 20):
         self._check(lib().hfg_debug_l2_flush(self._h, C.c_size_t(int(nbytes))))

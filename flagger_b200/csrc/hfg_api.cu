@@ -1391,6 +1391,28 @@ extern "C" int hfg_debug_l2_flush(hfg_ctx *ctx, size_t bytes) {
     return HFG_OK;
 }
 
+extern "C" int hfg_debug_blocking_steps(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, hfg_region_stats *stats,
+                                        int8_t *labels, int n_steps, size_t flush_bytes, double convergence_tol,
+                                        double *step_seconds, double *logliks) {
+    if (!ctx || !alpha || !params || !stats || !step_seconds || !logliks || n_steps < 0) return HFG_ERR_INVALID;
+    for (int i = 0; i < n_steps; i++) {
+        if (flush_bytes) {
+            int rc = hfg_debug_l2_flush(ctx, flush_bytes);
+            if (rc != HFG_OK) return rc;
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        int rc = hfg_em_iteration(ctx, alpha, params, stats, &logliks[i], labels);
+        int converged = 0;
+        if (rc == HFG_OK) rc = hfg_mstep(&ctx->cfg, params, stats, convergence_tol, &converged);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if (rc != HFG_OK) return rc;
+        step_seconds[i] = (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
+    }
+    return HFG_OK;
+}
+
 /* while (iter <= numberOfIterations && converged == false) { E-step; M-step }  (src/hmm_flagger.c:337-431), then the final
  * inference with the final parameters (:464) -- all of it queued at once on the device (hfg_em_*). */
 extern "C" int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, int max_iterations,

@@ -301,6 +301,13 @@ int hfg_debug_phase_clocks(hfg_ctx *ctx, long long *out, int *grid);
 /* Benchmark hook: queues a write of `bytes` of scratch device memory on the context's stream (evicts the L2 between
  * timed iterations of the device-resident loop). */
 int hfg_debug_l2_flush(hfg_ctx *ctx, size_t bytes);
+/* Benchmark hook: what a C host (the drop-in binding, integration/hmm_estep_cuda.c) does per EM iteration, n_steps times:
+ * hfg_em_iteration (host parameters in; host statistics, log-likelihood and labels out) + hfg_mstep; before every step
+ * `flush_bytes` of scratch are written and waited for (0 = no flush), outside the step's interval.  step_seconds[i] = wall
+ * time of step i (CLOCK_MONOTONIC around the two calls), logliks[i] its log-likelihood; params are updated in place. */
+int hfg_debug_blocking_steps(hfg_ctx *ctx, const double *alpha, hfg_region_params *params, hfg_region_stats *stats,
+                             int8_t *labels, int n_steps, size_t flush_bytes, double convergence_tol, double *step_seconds,
+                             double *logliks);
 int hfg_debug_exp(hfg_ctx *ctx, const double *in, double *out, int n);
 /* Host-only (no GPU): self-check of the segment layout and observation-key builder for `capacity` segment slots;
  * summary[6] = {segments, windows per slot, edge windows, windows, distinct observation keys, statistics tiles}.  And EM_computeAdjustmentBeta (hmm.c:301-316) for one window of a chunk. */
