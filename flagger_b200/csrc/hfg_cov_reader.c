@@ -14,6 +14,12 @@
  * Integer-valued coverages (what bam2cov writes) make n*value exact, so the window sums are bit-identical to the
  * reference's base-by-base accumulation; non-integer values fall back to repeated addition to stay so.
  * No `<input>.index` side file is written (chunk.c:154-162 writes one; it is only a cache of the layout).
+ * ONE deliberate difference: a single run-length block that crosses two or more chunk boundaries.  The reference's index
+ * builder adds at most one chunk per track line, so it drops (or leaves empty) the chunks in between -- a 12 345-base block
+ * with -C 3000 gives it 1 chunk / 30 windows (the assert that would catch it is compiled out of release builds).  Here the
+ * layout follows from the contig length alone: 4 chunks / 124 windows, every base in a window
+ * (tests/test_cov_reader.py::test_one_block_across_several_chunk_boundaries).  bam2cov output (blocks of a few hundred
+ * bases against 20 Mb chunks) never meets the case.
  */
 #include <math.h>
 #include <stdio.h>

@@ -49,6 +49,7 @@ struct hfg_inflate {
     size_t piece_cap;
     /* member / block state */
     int in_member, in_block, last_block, block_kind; /* block_kind: 0 stored, 1 Huffman */
+    int members_done;                                /* complete, CRC-checked members so far */
     size_t stored_left;
     uint32_t crc;
     uint64_t member_bytes;
@@ -350,12 +351,17 @@ long hfg_inflate_next(hfg_inflate *z, uint8_t *dst) {
 
     while (out < limit) {
         if (!z->in_member) {
-            /* between members: more input means another member (zeros / garbage after the last one are ignored as zlib's
-             * gzread does for trailing zeros only; anything else is an error) */
+            /* between members: a gzip magic means another member.  Behind at least one complete, CRC-checked member anything
+             * else -- zero padding or garbage -- ends the stream quietly, as zlib's gzread (the reference's reader) treats it;
+             * a file that does not START with a member is an error */
             byte_align(z);
             REFILL(z);
             const size_t consumed = z->in_pos - (size_t) (z->bitcnt >> 3);
             if (consumed >= z->in_len) {
+                z->finished = 1;
+                break;
+            }
+            if (z->members_done > 0 && !(z->in[consumed] == 0x1f && consumed + 1 < z->in_len && z->in[consumed + 1] == 0x8b)) {
                 z->finished = 1;
                 break;
             }
@@ -561,6 +567,7 @@ long hfg_inflate_next(hfg_inflate *z, uint8_t *dst) {
             if (want_crc != z->crc) return fail(z, "CRC mismatch"), -1;
             if (want_len != (uint32_t) z->member_bytes) return fail(z, "length mismatch"), -1;
             z->in_member = 0;
+            z->members_done++;
             z->last_block = 0;
         }
     }

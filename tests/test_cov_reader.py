@@ -90,3 +90,24 @@ def test_cov_reader_rejects_gaps(tmp_path):
     p.write_text("#annotation:len:1\n#region:len:1\n#region:coverage:0:40\n>c 100\n1\t10\t4\t4\t0\t0\t0\n21\t100\t4\t4\t0\t0\t0\n")
     with pytest.raises(ValueError, match="tile the contig"):
         binfmt.read_cov_native(str(p), 1000, 10)
+
+
+def test_one_block_across_several_chunk_boundaries(tmp_path):
+    """A deliberate difference from the reference (documented in hfg_cov_reader.c and DESIGN.md section 7): one run-length
+    block that crosses two or more chunk boundaries.  ChunksCreator_createCovIndex adds at most one chunk per track line
+    (chunk.c:444-547; the assert that would catch it is compiled out), so the reference drops or empties the chunks in
+    between: a single 12 345-base block with -C 3000 gives it 1 chunk / 30 windows.  This reader cuts the contig at every
+    boundary, the short remainder merged into the last chunk as for any other contig, and every base lands in a window."""
+    p = tmp_path / "long_block.cov"
+    p.write_text("#annotation:len:1\n#region:len:1\n#region:coverage:0:40\n>c 12345\n1\t12345\t37\t30\t2\t0\t0\n")
+    wl, _ = binfmt.read_cov_native(str(p), 3000, 100)
+    assert wl.n_chunks == 4 and wl.n_windows == 124
+    assert [int(v) for v in wl.chunks["n_windows"]] == [30, 30, 30, 34]
+    assert np.all(wl.cov == 37) and np.all(wl.cov_high_mapq == 30) and np.all(wl.cov_high_clip == 2)
+    # the same contig as one block per window gives the same windows
+    q = tmp_path / "per_window.cov"
+    lines = ["#annotation:len:1", "#region:len:1", "#region:coverage:0:40", ">c 12345"]
+    lines += [f"{s}\t{min(s + 99, 12345)}\t37\t30\t2\t0\t0" for s in range(1, 12346, 100)]
+    q.write_text("\n".join(lines) + "\n")
+    w2, _ = binfmt.read_cov_native(str(q), 3000, 100)
+    assert np.array_equal(w2.chunks, wl.chunks) and np.array_equal(w2.cov, wl.cov)
