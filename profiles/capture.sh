@@ -31,7 +31,7 @@ for wl in cfg2 cfg3 cfg4; do python tools/quad_phases.py $wl; done > $out/${tag}
 } > $out/${tag}_mstep_tail.txt 2>&1
 python tools/batch_bench.py 7.5e7 3e8 1.5e9 3e9 > $out/${tag}_batch_bench.txt 2>&1
 {
-    for b in lat_bench pred_bench mio_bench a_bench; do
+    for b in lat_bench pred_bench mio_bench a_bench launch_bench; do
         [ -x tools/$b ] && { echo "== tools/$b"; timeout 120 ./tools/$b; }
     done
 } > $out/${tag}_microbench.txt 2>&1
