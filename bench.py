@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "small"])
     ap.add_argument("--total-bp", type=float, default=3e9)
+    ap.add_argument("--model", default="trunc_exp_gaussian", choices=["trunc_exp_gaussian", "nb"],
+                    help="emission model: the reference's default, or --modelType negative_binomial")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
@@ -204,7 +206,7 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def model_setup(wl, checker=None):
+def model_setup(wl, checker=None, model="trunc_exp_gaussian"):
     """Configuration and initial model of a workload.  `checker` (an oracle_lib checker: the reference build or the
     restatement) serves the reference arm, which must not load the product library; the product arm uses libhfg's own
     host mirrors (the two agree bit for bit, tests/test_oracle_golden.py)."""
@@ -212,15 +214,22 @@ def model_setup(wl, checker=None):
     if checker is None:
         from flagger_b200 import api as checker
     K = checker.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
-    cfg = _abi.make_config(n_regions=wl.n_regions, n_col_comps=K, mean_read_length=wl.avg_alignment_len)
+    if model == "nb":  # --modelType negative_binomial: no previous-window dependency, alpha is ignored
+        cfg = _abi.make_config(n_regions=wl.n_regions, n_col_comps=K, mean_read_length=wl.avg_alignment_len,
+                               model_type=_abi.MODEL_NEGATIVE_BINOMIAL)
+        alpha = np.zeros((4, 4))
+    else:
+        cfg = _abi.make_config(n_regions=wl.n_regions, n_col_comps=K, mean_read_length=wl.avg_alignment_len)
+        alpha = synth.HIFI_ALPHA.copy()
     params = checker.model_init(cfg, wl.region_coverages, wl.window_len)
-    return cfg, params, synth.HIFI_ALPHA.copy(), K
+    return cfg, params, alpha, K
 
 
-def workload_config(wl, K):
+def workload_config(wl, K, model="trunc_exp_gaussian"):
     """The `config` object of the JSON line: the same keys in both arms."""
     return {"workload": wl.name, "windows": wl.n_windows, "chunks": wl.n_chunks, "regions": wl.n_regions, "col_components": K,
-            "window_len": wl.window_len, "alpha": "HiFi_DC_1.2",
+            "window_len": wl.window_len, "alpha": "HiFi_DC_1.2" if model != "nb" else "none (negative binomial)",
+            "model_type": "negative_binomial" if model == "nb" else "trunc_exp_gaussian",
             "step": "one EM iteration = E-step of all chunks (fwd+bwd+statistics+labels) + M-step"}
 
 
@@ -278,14 +287,14 @@ def run_reference(args):
     import oracle_lib
     wl = make_workload(args.workload, args.total_bp * (max(args.gpus, 1) if args.scaling == "weak" else 1))
     checker = oracle_lib.reference(threads=host_threads()) or oracle_lib.oracle()  # never the product library
-    cfg, params, alpha, K = model_setup(wl, checker)
+    cfg, params, alpha, K = model_setup(wl, checker, args.model)
     cpu, sample = time_cpu(cfg, wl, alpha, params, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": "HMM windows/sec (EM iter + Viterbi), 3 Gbp @40x w=4000; achieved HBM GB/s",
         "value": cpu["value"], "unit": "windows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(wl, K),
+        "config": workload_config(wl, K, args.model),
         "notes": {"sample_windows": sample.n_windows,
                   "note": "CPU reference path on a bounded sample; windows/s is size-independent (per-window cost is constant)"},
         "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -298,7 +307,7 @@ def run_reference(args):
     _RESULT_LINE.append(json.dumps(line))
 
 
-def binary_e2e(wl, alpha, steps, cores):
+def binary_e2e(wl, alpha, steps, cores, model="trunc_exp_gaussian"):
     """Whole-binary end to end: the stand-alone hmm_flagger_b200 and, beside it, the unmodified reference binary
     (oracle/_ref/hmm_flagger_ref, -@ all host threads) on the same .bin input, `steps - 1` EM iterations + final inference,
     timed from process start to exit.  Returns a dict for the JSON line (or None when the product binary is missing)."""
@@ -316,7 +325,9 @@ def binary_e2e(wl, alpha, steps, cores):
         binfmt.write_bin(wl, inp)
         binfmt.write_alpha_tsv(alpha, atsv)
         out = {"input": f"{wl.name} as .bin ({os.path.getsize(inp) >> 20} MiB)",
-               "command": f"-i in.bin -o out -A alpha.tsv -n {steps - 1} -t 1e-12 -@ {cores}"}
+               "command": f"-i in.bin -o out -A alpha.tsv -n {steps - 1} -t 1e-12 -@ {cores}" +
+                          (" -m negative_binomial" if model == "nb" else "")}
+        extra = ["--modelType", "negative_binomial"] if model == "nb" else []
 
         def one(binary, tag, repeats):
             best = None
@@ -324,7 +335,7 @@ def binary_e2e(wl, alpha, steps, cores):
                 odir = os.path.join(tmp, f"out_{tag}_{rep}")
                 os.makedirs(odir)
                 t0 = time.perf_counter()
-                r = subprocess.run([binary, "-i", inp, "-o", odir, "-A", atsv, "-n", str(steps - 1), "-t", "1e-12", "-@", str(cores)],
+                r = subprocess.run([binary, "-i", inp, "-o", odir, "-A", atsv, "-n", str(steps - 1), "-t", "1e-12", "-@", str(cores)] + extra,
                                    capture_output=True, text=True)
                 wall = time.perf_counter() - t0
                 if r.returncode != 0:
@@ -371,7 +382,7 @@ def run_ours(args):
     # weak scaling: the per-GPU work is the metric's 3 Gbp workload; the job is an N x 3 Gbp assembly with ONE model, its
     # chunks sharded over the ranks and its EM statistics summed over them every iteration
     wl_full = make_workload(args.workload, args.total_bp * (world if args.scaling == "weak" else 1))
-    cfg, params0, alpha, K = model_setup(wl_full)
+    cfg, params0, alpha, K = model_setup(wl_full, None, args.model)
     cfg["device"] = local_rank
     wl = shard_chunks(wl_full, rank, world)
     W_total = wl_full.n_windows
@@ -613,7 +624,7 @@ def run_ours(args):
             "value": value, "unit": "windows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(wl_full, K),
+            "config": workload_config(wl_full, K, args.model),
             "notes": {"parallelism": ("1 GPU" if world == 1 else
                                       f"chunks sharded over {world} GPUs, one process per GPU; EM statistics summed over "
                                       "ranks " + ("inside the E-step kernel through NVLink peer memory (fused all-reduce)"
@@ -645,7 +656,7 @@ def run_ours(args):
         if weak is not None:
             line["weak"] = weak
         if world == 1 and not args.no_binary and args.workload != "small":
-            line["e2e_binary"] = binary_e2e(wl_full, alpha, args.steps, host_threads())
+            line["e2e_binary"] = binary_e2e(wl_full, alpha, args.steps, host_threads(), args.model)
         if world == 1 and not args.no_cpu_baseline:
             cpu, _ = time_cpu(cfg, wl_full, alpha, params0, steps=5, warmup=1, budget_s=30.0)
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

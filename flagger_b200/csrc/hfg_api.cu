@@ -92,6 +92,8 @@ struct hfg_ctx {
     double *d_nb_tile_col, *h_nb_tile_col; /* [n_tiles][4] */
     int32_t *h_tile_key;                 /* [n_tiles] host copies for folding the tile masses into the histogram */
     uint32_t *h_kdesc;                   /* [n_keys] */
+    int32_t *d_nb_bins;                  /* device-resident loop: [R * 250 + 1] bin offsets, then [n_tiles] the tiles of every bin */
+    double *d_nb_lgx1;                   /* [251] lgamma(x + 1) */
     char err[512];
 };
 
@@ -491,6 +493,10 @@ static void free_device(hfg_ctx *ctx) {
     free(ctx->h_tile_key);
     free(ctx->h_kdesc);
     ctx->d_nb_tile_col = ctx->h_nb_tile_col = NULL;
+    if (ctx->d_nb_bins) cudaFree(ctx->d_nb_bins);
+    if (ctx->d_nb_lgx1) cudaFree(ctx->d_nb_lgx1);
+    ctx->d_nb_bins = NULL;
+    ctx->d_nb_lgx1 = NULL;
     ctx->h_tile_key = NULL;
     ctx->h_kdesc = NULL;
     hfg_layout_free(&ctx->lay);
@@ -814,7 +820,9 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         ctx->smem_bytes = base + (size_t) ctx->lab_bytes + (size_t) ctx->n_hot * 128;
         {
             /* the M-step of the device-resident loop works on shared-memory copies behind the region tables */
-            const size_t need = ((((size_t) R * QRT_STRIDE(G) + 1) & ~(size_t) 1) * sizeof(double)) + mstep_work_bytes(ctx->threads, 1);
+            size_t need = ((((size_t) R * QRT_STRIDE(G) + 1) & ~(size_t) 1) * sizeof(double)) + mstep_work_bytes(ctx->threads, 1);
+            /* negative binomial: the tail's histogram / estimator scratch (hfg_nb_dev.cuh) */
+            if (ctx->nb) need += (size_t) HFG_NB_TAIL_DOUBLES * sizeof(double);
             if (ctx->smem_bytes < need) ctx->smem_bytes = need;
         }
         CU(cudaMemsetAsync(ctx->d_khot, 0xff, (size_t) l->n_keys * sizeof(uint32_t), ctx->stream));
@@ -838,6 +846,40 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         CU(cudaMallocHost((void **) &ctx->h_nb_tile_col, sizeof(double) * 4 * nt));
         if (l->n_tiles > 0) CU(cudaMemcpy(ctx->h_tile_key, ctx->d_tile_key, sizeof(int32_t) * (size_t) l->n_tiles, cudaMemcpyDeviceToHost));
         if (l->n_keys > 0) CU(cudaMemcpy(ctx->h_kdesc, ctx->d_kdesc, sizeof(uint32_t) * (size_t) l->n_keys, cudaMemcpyDeviceToHost));
+        /* device-resident loop (hfg_nb_dev.cuh): the tiles of every (region, coverage bin), in tile order -- the order in which
+         * run_blocking_nb folds them -- and lgamma(x + 1) from libm */
+        {
+            const size_t nbins = (size_t) R * HFG_NB_BINS;
+            int32_t *bins = (int32_t *) calloc(nbins + 1 + nt, sizeof(int32_t));
+            if (!bins) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+            int32_t *begin = bins, *tiles = bins + nbins + 1;
+            for (int32_t t = 0; t < l->n_tiles; t++) {
+                const uint32_t w = ctx->h_kdesc[ctx->h_tile_key[t]];
+                const int x = (int) HFG_OBS_X(w), region = (int) HFG_OBS_REGION(w);
+                begin[(size_t) region * HFG_NB_BINS + (x < HFG_NB_BINS ? x : HFG_NB_BINS - 1) + 1]++;
+            }
+            for (size_t b = 0; b < nbins; b++) begin[b + 1] += begin[b];
+            int32_t *fill = (int32_t *) malloc(sizeof(int32_t) * (nbins + 1));
+            if (!fill) {
+                free(bins);
+                return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
+            }
+            memcpy(fill, begin, sizeof(int32_t) * (nbins + 1));
+            for (int32_t t = 0; t < l->n_tiles; t++) {
+                const uint32_t w = ctx->h_kdesc[ctx->h_tile_key[t]];
+                const int x = (int) HFG_OBS_X(w), region = (int) HFG_OBS_REGION(w);
+                tiles[fill[(size_t) region * HFG_NB_BINS + (x < HFG_NB_BINS ? x : HFG_NB_BINS - 1)]++] = t;
+            }
+            free(fill);
+            cudaError_t e = cudaMalloc((void **) &ctx->d_nb_bins, sizeof(int32_t) * (nbins + 1 + nt));
+            if (e == cudaSuccess) e = cudaMemcpy(ctx->d_nb_bins, bins, sizeof(int32_t) * (nbins + 1 + nt), cudaMemcpyHostToDevice);
+            free(bins);
+            double lgx1[HFG_NB_TABLE_X];
+            for (int x = 0; x < HFG_NB_TABLE_X; x++) lgx1[x] = lgamma(x + 1);
+            if (e == cudaSuccess) e = cudaMalloc((void **) &ctx->d_nb_lgx1, sizeof(lgx1));
+            if (e == cudaSuccess) e = cudaMemcpy(ctx->d_nb_lgx1, lgx1, sizeof(lgx1), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return fail(ctx, HFG_ERR_CUDA, "negative-binomial bin lists: %s", cudaGetErrorString(e));
+        }
     }
     /* the per-window tables now live on the device */
     free(ctx->lay.obsT); ctx->lay.obsT = NULL;
@@ -965,6 +1007,9 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     a.model_type = cfg->model_type;
     a.nb_table = ctx->d_nb_table;
     a.nb_tile_col = ctx->d_nb_tile_col;
+    a.nb_bin_begin = ctx->d_nb_bins;
+    a.nb_bin_tiles = ctx->d_nb_bins ? ctx->d_nb_bins + (size_t) ctx->cfg.n_regions * HFG_NB_BINS + 1 : NULL;
+    a.nb_lgx1 = ctx->d_nb_lgx1;
 }
 
 /* negative binomial: the pmf of every (region, state, x) for these parameters (host, libm: hfg_nb.c) -> pinned staging
@@ -1279,7 +1324,8 @@ extern "C" int hfg_em_begin(hfg_ctx *ctx, const double *alpha, const hfg_region_
     if (!ctx) return HFG_ERR_INVALID;
     if (!ctx->have_chunks) return fail(ctx, HFG_ERR_INVALID, "hfg_set_chunks must be called first");
     if (!alpha || !params || max_esteps < 1) return fail(ctx, HFG_ERR_INVALID, "hfg_em_begin: bad argument");
-    if (ctx->nb) return fail(ctx, HFG_ERR_INVALID, "hfg_em_begin: the device-resident loop does not serve the negative-binomial model");
+    if (ctx->nb && ctx->quad != 3)
+        return fail(ctx, HFG_ERR_INVALID, "hfg_em_begin: the negative-binomial model needs the default kernel for the device-resident loop");
     CU(cudaSetDevice(ctx->device));
     const int R = ctx->cfg.n_regions;
     const size_t pb = sizeof(hfg_region_params) * (size_t) R;
@@ -1419,9 +1465,10 @@ extern "C" int hfg_run_em(hfg_ctx *ctx, const double *alpha, hfg_region_params *
                           double convergence_tol, double *logliks, int *n_esteps, int8_t *labels) {
     if (!ctx || !params || !logliks || !n_esteps) return HFG_ERR_INVALID;
     if (max_iterations < 0) max_iterations = 0;
-    if (max_iterations + 1 > HFG_EM_LOGLIK_SLOTS || ctx->nb) {
-        /* longer than the device loop records, or the negative-binomial model (its estimator update and M-step are host
-         * code): the same loop with the host between the iterations */
+    if (max_iterations + 1 > HFG_EM_LOGLIK_SLOTS || (ctx->nb && getenv("HFG_NB_HOST_LOOP"))) {
+        /* longer than the device loop records (or HFG_NB_HOST_LOOP=1: the negative-binomial model with the host's libm /
+         * long-double estimator update between the iterations, the A/B partner of the device-resident loop): the same loop
+         * with the host between the iterations */
         const int R = ctx->cfg.n_regions;
         hfg_region_stats *stats = (hfg_region_stats *) malloc(sizeof(hfg_region_stats) * (size_t) R);
         if (!stats) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");

@@ -160,6 +160,10 @@ struct EstepArgs {
     const double *nb_table; /* [R][4][HFG_NB_XSTRIDE] pmf of (region, state, x), evaluated on the host (hfg_nb.c) */
     double *nb_tile_col;    /* [n_tiles][4] pair mass of every statistics tile by state: the host folds it into the
                                (region, state, x) histogram the model's estimators are fed from */
+    /* negative binomial, device-resident loop (hfg_nb_dev.cuh) */
+    const int32_t *nb_bin_begin; /* [R * 250 + 1] first entry of every (region, coverage bin) in nb_bin_tiles */
+    const int32_t *nb_bin_tiles; /* [n_tiles] the tiles of every bin, in tile order */
+    const double *nb_lgx1;       /* [251] lgamma(x + 1) (host libm values) */
 };
 #define HFG_NB_XSTRIDE 256
 

@@ -37,6 +37,7 @@
 #pragma once
 
 #include "hfg_estep.cuh"
+#include "hfg_nb_dev.cuh"
 
 #define HFGQ_THREADS 1024 /* 256 segments per CTA, one persistent CTA per SM */
 #define QRT_STRIDE(G) (RT_GAUSS + 6 * (G)) /* per-region table in shared memory: hfg_estep.cuh's layout without the task table */
@@ -546,7 +547,7 @@ __device__ __forceinline__ int hfg_mstep_trans_warp(hfg_region_params *p, const 
  * ticket) sums them in a fixed order, writes the hfg_region_stats block, exchanges it with the other ranks (multi-GPU),
  * runs the M-step of the device-resident loop and clears the flags.  Every other CTA returns at once.  `wstat` (>= R * NSTAT
  * doubles) and `work` (the M-step work area, sized by the host) are shared memory. */
-template <int THREADS>
+template <int THREADS, bool NB = false>
 __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat, double *work, int *s_last) {
     constexpr int WARPS = THREADS / 32;
     using namespace hfgq;
@@ -665,6 +666,18 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
         if (tid == 0) A.out[(size_t) R * SD + 1] = (double) __ldcg(A.err_flags);
         if (tid == 0) tail_clock[2] = clock64();
 
+        /* ---- negative binomial, device-resident loop: histogram -> estimator sums into the statistics block ---- */
+        if constexpr (NB) {
+            if (A.em_mode == 1) {
+                tsync();
+                const int nan = hfgnb::tail_estimators(A.params, R, A.ncomp, A.nb_tile_col, A.nb_bin_begin, A.nb_bin_tiles, A.nb_lgx1,
+                                                       A.out, work, tid, NW, tsync, tail_clock);
+                if (nan) atomicOr(A.err_flags, 2);
+                tsync();
+                if (tid == 0) A.out[(size_t) R * SD + 1] = (double) __ldcg(A.err_flags);
+            }
+        }
+
         /* ---- fused collective: sum the block over all ranks through peer memory ---------------------------------------
          * Every 64-bit word a rank stores into a peer's mailbox carries 32 bits of data and the 32-bit epoch of the exchange,
          * so data and "it has arrived" travel in ONE store over NVLink (NCCL's LL idea): no fence, no separate counter, no
@@ -758,7 +771,16 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
                      * barrier), the Gaussian / transition updates on the remaining warps, side by side */
                     int gsize = 32;
                     while (gsize * 2 * nb <= FIT_THREADS) gsize *= 2;
-                    if (tid < nb * gsize) {
+                    if constexpr (NB) {
+                        /* negative binomial: the host's M-step (hfg_nb_mstep_inl.h), emission and transition halves one warp each */
+                        for (int task = warp; task < 2 * nb; task += NW / 32) {
+                            double *mp = work + (size_t) (task >> 1) * per_region;
+                            hfg_region_params *p = reinterpret_cast<hfg_region_params *>(mp);
+                            const hfg_region_stats *st = reinterpret_cast<const hfg_region_stats *>(mp + PD);
+                            if (task & 1) settled &= hfg_mstep_trans_warp(p, st, A.em_tol, lane);
+                            else settled &= hfgnb::mstep_emis_warp(A.ncomp, p, st, A.em_tol, mscr + (size_t) warp * 128, lane);
+                        }
+                    } else if (tid < nb * gsize) {
                         const int g = tid / gsize, gtid = tid % gsize;
                         double *mp = work + (size_t) g * per_region;
                         hfg_region_params *p = reinterpret_cast<hfg_region_params *>(mp);

@@ -180,6 +180,17 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const EstepArg
                 if (A.is_gauss[k] && g >= A.gbase[k] && g < A.gbase[k] + A.ncomp[k]) s = k;
             const int c = g - A.gbase[s];
             double *ga = rt + RT_GAUSS;
+            if constexpr (NB) {
+                /* negative binomial: theta, log(1 - theta), weight, r, lgamma(r), r log(theta) (hfg_nb_dev.cuh) */
+                const hfgnb::Comp cc = hfgnb::comp_setup(p, s, c);
+                ga[g] = p.mean[s][c];
+                ga[G + g] = cc.log_1m_theta;
+                ga[2 * G + g] = cc.w;
+                ga[3 * G + g] = cc.r;
+                ga[4 * G + g] = cc.lgamma_r;
+                ga[5 * G + g] = cc.r_log_theta;
+                continue;
+            }
             const double vb = p.var[s][c] * A.beta0;
             ga[g] = p.mean[s][c];
             ga[G + g] = p.var[s][c];
@@ -211,7 +222,23 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const EstepArg
             double e;
             if constexpr (NB) {
                 /* the emission depends on (region, state, x) alone (NegativeBinomial_getProb, hmm_utils.c:479-516) */
-                e = A.nb_table[((size_t) w.region * 4 + s) * HFG_NB_XSTRIDE + (int) w.x];
+                if (A.em_mode) { /* device-resident loop: the pmf from the component constants of the prologue (hfg_nb_dev.cuh) */
+                    const double *ga = rt + RT_GAUSS;
+                    const double lgx = __ldg(A.nb_lgx1 + (int) w.x);
+                    e = 0.0;
+                    for (int c = 0; c < A.ncomp[s]; c++) {
+                        const int g = A.gbase[s] + c;
+                        hfgnb::Comp cc;
+                        cc.r = ga[3 * G + g];
+                        cc.w = ga[2 * G + g];
+                        cc.lgamma_r = ga[4 * G + g];
+                        cc.r_log_theta = ga[5 * G + g];
+                        cc.log_1m_theta = ga[G + g];
+                        cc.bt = 0.0;
+                        e += hfgnb::comp_prob(cc, (int) w.x, lgx, &nan_flag);
+                    }
+                } else
+                    e = A.nb_table[((size_t) w.region * 4 + s) * HFG_NB_XSTRIDE + (int) w.x];
             } else if (!A.is_gauss[s]) {
                 e = trunc_exp_prob(rt, w);
             } else {
@@ -901,5 +928,5 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const EstepArg
     }
     if (nan_flag) atomicOr(A.err_flags, 2);
 
-    hfg_estep_tail<THREADS>(A, wstat, warp_tot, &s_last);
+    hfg_estep_tail<THREADS, NB>(A, wstat, warp_tot, &s_last);
 }

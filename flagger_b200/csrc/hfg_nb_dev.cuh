@@ -1,0 +1,273 @@
+/*
+ * hfg_nb_dev.cuh -- the negative-binomial model on the device, for the device-resident EM loop (hfg_em_*, hfg_run_em).
+ *
+ * The blocking calls keep the host in the loop (hfg_nb.c: emission table with libm, histogram fold, long-double digamma: the
+ * bits of the reference).  Here the same formulas run in fp64 on the device so that successive iterations are back-to-back
+ * kernels: the pmf (NegativeBinomial_getComponentProbs, hmm_utils.c:494-515) per observation key in the key-matrix phase,
+ * and in the kernel tail the histogram of the pair mass over the coverage value (hmm.c:615-617, count_data.c:56-64: folded
+ * from the per-tile column sums, one warp per bin), NegativeBinomial_updateEstimator per non-empty bin
+ * (hmm_utils.c:536-563, psi(r + x) by the recurrence of :392-406) and the M-step (hfg_nb_mstep_inl.h, the host's code).
+ * Differences from the host path: CUDA's lgamma / exp / log instead of glibc's, psi(r + x) - psi(r) as a scan of reciprocals
+ * without the long-double digamma(r) the host adds and subtracts again, bins summed by a fixed tree instead of in ascending
+ * order: rounding only (tests/test_gpu_nb.py compares the two loops).
+ */
+#pragma once
+
+#define HFG_HD static __device__
+#include "hfg_nb_mstep_inl.h"
+#undef HFG_HD
+
+#define HFG_NB_DEV_BINS 250  /* HFG_NB_BINS: x = 250 is folded into bin 249 (count_data.c:56-64) */
+#define HFG_NB_DEV_X 251     /* HFG_NB_TABLE_X */
+
+#define HFG_NB_MAX_ITEMS 2048 /* items of <= 256 tiles in the histogram fold of one region: 250 bins + n_tiles / 256 */
+#define HFG_NB_TAIL_DOUBLES ((4 + 2 + HFG_MAX_COMPS) * 256 + 32 * 8 + 6 * 4 * HFG_MAX_COMPS + HFG_NB_MAX_ITEMS * 4 + HFG_NB_MAX_ITEMS / 2 + 32)
+
+namespace hfgnb {
+
+struct Comp {
+    double r, w, lgamma_r, r_log_theta, log_1m_theta, bt;
+};
+__device__ __forceinline__ Comp comp_setup(const hfg_region_params &p, int s, int k) {
+    Comp c;
+    const double theta = p.mean[s][k], lt = log(theta);
+    c.r = -1 * p.var[s][k] / lt; /* NegativeBinomial_getR, hmm_utils.c:455-458 */
+    c.w = p.weight[s][k];
+    c.lgamma_r = lgamma(c.r);
+    c.r_log_theta = c.r * lt;
+    c.log_1m_theta = log(1 - theta);
+    c.bt = -1 * theta / (1 - theta) - 1 / lt; /* hmm_utils.c:545 */
+    return c;
+}
+/* weighted pmf of one component at x, floored at 1e-40 */
+__device__ __forceinline__ double comp_prob(const Comp &c, int x, double lg_x1, int *nan) {
+    double v = c.w * exp(lgamma(c.r + x) - c.lgamma_r - lg_x1 + c.r_log_theta + (double) x * c.log_1m_theta);
+    if (v != v) *nan = 1;
+    return v < 1e-40 ? 1e-40 : v;
+}
+/* emission of (region parameters p, state s) at coverage x: the sum over the components in component order */
+__device__ __forceinline__ double state_prob(const hfg_region_params &p, int s, int n, int x, double lg_x1, int *nan) {
+    double tot = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < n; k++) {
+        const Comp c = comp_setup(p, s, k);
+        tot += comp_prob(c, x, lg_x1, nan);
+    }
+    return tot;
+}
+
+/* Tail of the device-resident loop, run by the NW worker threads of the last CTA: histogram -> estimator sums, written into
+ * the hfg_region_stats block `out` ([R][SD] doubles).  `scr` = shared memory: (4 + 2 + HFG_MAX_COMPS) * 256 + 32 * 8 + 6 * 4 * HFG_MAX_COMPS doubles (HFG_NB_TAIL_DOUBLES).
+ * `sync` = the workers' barrier.  Returns a NaN flag (thread-local; OR it over the threads). */
+template <typename Sync>
+__device__ __forceinline__ int tail_estimators(const hfg_region_params *params, int R, const int32_t *ncomp, const double *tile_col,
+                                               const int32_t *bin_begin, const int32_t *bin_tiles, const double *lg_x1_g,
+                                               double *out, double *scr, int tid, int NW, Sync sync, long long *clk) {
+    const int SD = (int) (sizeof(hfg_region_stats) / sizeof(double));
+    const int lane = tid & 31, warp = tid >> 5, NWARP = NW / 32;
+    int nan = 0;
+    double *hist = scr;                       /* [4][250] of the current region */
+    double *rcp = hist + 4 * 256;             /* [32] the warps' totals of the scan of 1 / (r + x - 1) */
+    double *probs = rcp + 512;                 /* [nc][256] weighted pmf of every component of the current state */
+    double *red = probs + HFG_MAX_COMPS * 256; /* [NWARP][8] cross-warp reduction */
+    Comp *cs = reinterpret_cast<Comp *>(red + 32 * 8); /* [4][HFG_MAX_COMPS] constants of every component of the region */
+    double *part = reinterpret_cast<double *>(cs + HFG_NS * HFG_MAX_COMPS); /* [HFG_NB_MAX_ITEMS][4] item sums of the histogram fold */
+    int *item_bin = reinterpret_cast<int *>(part + HFG_NB_MAX_ITEMS * 4);   /* [HFG_NB_MAX_ITEMS] bin | slice << 8, then [32] scan scratch */
+    for (int reg = 0; reg < R; reg++) {
+        const hfg_region_params &p = params[reg];
+        hfg_region_stats *st = reinterpret_cast<hfg_region_stats *>(out + (size_t) reg * SD);
+        if (tid < HFG_NS * HFG_MAX_COMPS && (tid % HFG_MAX_COMPS) < ncomp[tid / HFG_MAX_COMPS])
+            cs[tid] = comp_setup(p, tid / HFG_MAX_COMPS, tid % HFG_MAX_COMPS);
+        /* histogram of this region: bin x = the column sums of the tiles whose key has coverage x.  The bins differ in size by
+         * orders of magnitude, so the work is cut into items of <= 256 tiles of one bin: a warp adds an item (eight tiles per
+         * lane, all loads in flight, fixed shuffle tree), then one thread per bin adds the bin's items in order. */
+        {
+            const int x = tid;
+            const int b0 = x < HFG_NB_DEV_BINS ? bin_begin[reg * HFG_NB_DEV_BINS + x] : 0;
+            const int b1 = x < HFG_NB_DEV_BINS ? bin_begin[reg * HFG_NB_DEV_BINS + x + 1] : 0;
+            const int cnt = (b1 - b0 + 255) >> 8;
+            int inc = cnt; /* inclusive scan of the item counts over the bins */
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += t;
+            }
+            if (lane == 31) item_bin[HFG_NB_MAX_ITEMS + warp] = inc;
+            sync();
+            int base = 0;
+            for (int wv = 0; wv < warp; wv++) base += item_bin[HFG_NB_MAX_ITEMS + wv];
+            int total = 0;
+            for (int wv = 0; wv < NWARP; wv++) total += item_bin[HFG_NB_MAX_ITEMS + wv];
+            const int first = base + inc - cnt;
+            for (int k = 0; k < cnt && first + k < HFG_NB_MAX_ITEMS; k++) item_bin[first + k] = x | (k << 8);
+            sync();
+            const int n_items = total < HFG_NB_MAX_ITEMS ? total : HFG_NB_MAX_ITEMS;
+            for (int item = warp; item < n_items; item += NWARP) {
+                const int ib = item_bin[item] & 255, ik = item_bin[item] >> 8;
+                const int s0 = bin_begin[reg * HFG_NB_DEV_BINS + ib] + (ik << 8), s1 = min(bin_begin[reg * HFG_NB_DEV_BINS + ib + 1], s0 + 256);
+                int tl[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int i = s0 + lane + 32 * u;
+                    tl[u] = i < s1 ? bin_tiles[i] : -1;
+                }
+                double h[4] = {0.0, 0.0, 0.0, 0.0};
+                double v[8][4];
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) v[u][k] = tl[u] >= 0 ? __ldcg(tile_col + (size_t) tl[u] * 4 + k) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) h[k] += v[u][k];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) h[k] += __shfl_xor_sync(0xffffffffu, h[k], off);
+                    if (lane == 0) part[item * 4 + k] = h[k];
+                }
+            }
+            sync();
+            if (x < HFG_NB_DEV_BINS) {
+                double h[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int k = 0; k < cnt && first + k < HFG_NB_MAX_ITEMS; k++)
+#pragma unroll
+                    for (int q = 0; q < 4; q++) h[q] += part[(first + k) * 4 + q];
+                hist[x] = h[0];
+                hist[256 + x] = h[1];
+                hist[512 + x] = h[2];
+                hist[768 + x] = h[3];
+            }
+        }
+        sync();
+        if (clk && tid == 0 && reg == 0) clk[12] = clock64();
+        for (int s = 0; s < HFG_NS; s++) {
+            const int nc = ncomp[s];
+            const int x = tid; /* one bin per thread (NW >= 250) */
+            const double mass = x < HFG_NB_DEV_BINS ? hist[s * 256 + x] : 0.0;
+            const double lgx = x < HFG_NB_DEV_X ? __ldg(lg_x1_g + x) : 0.0;
+            double total = 0.0;
+            for (int c = 0; c < nc; c++) {
+                const Comp cc = cs[s * HFG_MAX_COMPS + c];
+                const double pr = x < HFG_NB_DEV_BINS ? comp_prob(cc, x, lgx, &nan) : 0.0;
+                if (x < HFG_NB_DEV_BINS) probs[c * 256 + x] = pr;
+                total += pr;
+            }
+            for (int c = 0; c < nc; c++) {
+                const Comp cc = cs[s * HFG_MAX_COMPS + c];
+                /* psi(r + x) - psi(r) = sum_{i < x} 1 / (r + i) (the recurrence of hmm_utils.c:392-406 with the digamma(r) it starts
+                 * from and subtracts again left out): reciprocals side by side, inclusive scan over the bins (warp shuffles, then the
+                 * warps' totals in order) */
+                double psi_x = (x >= 1 && x < HFG_NB_DEV_BINS) ? 1.0 / (cc.r + x - 1) : 0.0;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, psi_x, off);
+                    if (lane >= off) psi_x += t;
+                }
+                if (lane == 31) rcp[warp] = psi_x;
+                sync();
+                for (int wv = 0; wv < warp; wv++) psi_x += rcp[wv];
+                double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+                if (x < HFG_NB_DEV_BINS && 0 < mass) {
+                    const double w = mass * probs[c * 256 + x] / total;
+                    const double delta = cc.r * psi_x;
+                    v[0] = w * delta;                               /* var_num (lambda estimator) */
+                    v[1] = w;                                       /* var_den, weight_num */
+                    v[2] = w * delta * cc.bt;                       /* mean_num (theta estimator) */
+                    v[3] = w * delta * cc.bt + w * (x - delta);     /* mean_den */
+                }
+                /* fixed tree: lanes, then warps in order */
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+                    if (lane == 0) red[warp * 8 + k] = v[k];
+                }
+                sync();
+                if (tid < 4) {
+                    double sum = 0.0;
+                    for (int wv = 0; wv < NWARP; wv++) sum += red[wv * 8 + tid];
+                    if (tid == 0) st->var_num[s][c] = sum;
+                    if (tid == 1) {
+                        st->var_den[s][c] = sum;
+                        st->weight_num[s][c] = sum;
+                    }
+                    if (tid == 2) st->mean_num[s][c] = sum;
+                    if (tid == 3) st->mean_den[s][c] = sum;
+                }
+                sync();
+            }
+            if (clk && tid == 0 && reg == 0 && s < 3) clk[13 + s] = clock64();
+            /* every component's weight estimator has the mass of all components of the state as its denominator */
+            if (tid == 0) {
+                double den = 0.0;
+                for (int c = 0; c < nc; c++) den += st->weight_num[s][c];
+                for (int c = 0; c < nc; c++) st->weight_den[s][c] = den;
+            }
+            sync();
+        }
+    }
+    return nan;
+}
+
+/* EmissionDistSeries_estimateParameters for MODEL_NEGATIVE_BINOMIAL (hfg_nb_mstep_region_inl's emission half) for one WARP:
+ * one lane per component does the divisions, every lane adds the pooled sums in the serial routine's order (state, then
+ * component, ascending), so the parameters come out with its bits.  `scr` = 128 doubles of warp-private shared memory. */
+__device__ __forceinline__ int mstep_emis_warp(const int32_t *n_comps, hfg_region_params *p, const hfg_region_stats *st, double tol,
+                                               double *scr, int lane) {
+    int ok = 1, G = 0, gs[2] = {0, 0}, gc[2] = {0, 0};
+    for (int s = 0; s < HFG_NS; s++) {
+        for (int u = 0; u < 2; u++) {
+            const int g = lane + 32 * u;
+            if (g >= G && g < G + n_comps[s]) {
+                gs[u] = s;
+                gc[u] = g - G;
+            }
+        }
+        G += n_comps[s];
+    }
+    for (int type = 0; type < 2; type++) { /* theta, then lambda: one pooled ("bound") estimate each */
+        for (int u = 0; u < 2; u++) {
+            const int g = lane + 32 * u;
+            if (g < G) {
+                const double f = type == 0 ? 1.0 : nb_lambda_coef(gs[u], gc[u]);
+                scr[g] = (type == 0 ? st->mean_num[gs[u]][gc[u]] : st->var_num[gs[u]][gc[u]]) / f;
+                scr[64 + g] = type == 0 ? st->mean_den[gs[u]][gc[u]] : st->var_den[gs[u]][gc[u]];
+            }
+        }
+        __syncwarp();
+        double num = 0.0, den = 0.0;
+        for (int g = 0; g < G; g++) {
+            num += scr[g];
+            den += scr[64 + g];
+        }
+        __syncwarp();
+        const double pooled = den == 0 ? 0.0 : num / den;
+        if (!(NB_MIN_COUNT < den)) continue;
+        for (int u = 0; u < 2; u++) {
+            const int g = lane + 32 * u;
+            if (g < G) {
+                double *dst = type == 0 ? &p->mean[gs[u]][gc[u]] : &p->var[gs[u]][gc[u]];
+                const double v = pooled * (type == 0 ? 1.0 : nb_lambda_coef(gs[u], gc[u]));
+                ok &= nb_settled(*dst, v, tol);
+                *dst = v;
+            }
+        }
+    }
+    for (int u = 0; u < 2; u++) {
+        const int g = lane + 32 * u;
+        if (g < G) {
+            const double den = st->weight_den[gs[u]][gc[u]];
+            if (NB_MIN_COUNT < den) {
+                const double v = st->weight_num[gs[u]][gc[u]] / den;
+                ok &= nb_settled(p->weight[gs[u]][gc[u]], v, tol);
+                p->weight[gs[u]][gc[u]] = v;
+            }
+        }
+    }
+    __syncwarp();
+    return __all_sync(0xffffffffu, ok);
+}
+
+}  // namespace hfgnb

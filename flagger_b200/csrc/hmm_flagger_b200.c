@@ -9,8 +9,8 @@
  *   posterior_prediction_final.bed (-P), chunks.c_<C>.w_<W>.bin (-B), prediction_summary_{initial,iteration_k,final}.tsv
  *   and, for inputs with truth labels, their .benchmarking.tsv / .benchmarking.auN_ratio.tsv companions (all on the flat
  *   label array, hfg_write_summary_tsv; -k for every iteration).
- * --accelerate (SQUAREM) runs through hfg_squarem_iteration; --modelType negative_binomial through the host-looped E-steps
- * (hfg_api.cu::run_blocking_nb).  Not supported: --initialRandomDev other than 0 (refused with a message).
+ * --accelerate (SQUAREM) runs through hfg_squarem_iteration; --modelType negative_binomial through the same device-resident
+ * loop as the other models (hfg_nb_dev.cuh; its blocking E-steps keep the host's libm table and estimator update).  Not supported: --initialRandomDev other than 0 (refused with a message).
  */
 #include <getopt.h>
 #include <math.h>
@@ -528,7 +528,7 @@ int main(int argc, char *argv[]) {
      * --accelerate, -w or -k.  Otherwise the REST of the loop -- every further E-step, the M-steps, the convergence test and
      * the final inference -- is queued on the device at once (hfg_em_*: parameters stay in HBM, the M-step runs in the tail
      * of the E-step kernel) and the host comes back for the log-likelihoods, the parameters and the labels. */
-    const int per_iteration_outputs = accelerate || write_params || write_bench || model_type == HFG_MODEL_NEGATIVE_BINOMIAL;
+    const int per_iteration_outputs = accelerate || write_params || write_bench;
     while (iter <= iterations && !converged) {
         if (!per_iteration_outputs && iter > 1 && iterations - iter + 2 <= 4096) {
             const int remaining = iterations - iter + 1;

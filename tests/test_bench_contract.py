@@ -31,7 +31,7 @@ def test_reference_arm_prints_one_contract_line():
     assert j["vs_baseline"] is None and "workload" in j["config"]
     # the reference arm runs the checker only: the product library is not even mapped
     assert j["native_libs"] and not any("libhfg" in lib for lib in j["native_libs"]), j["native_libs"]
-    assert set(j["config"]) == {"workload", "windows", "chunks", "regions", "col_components", "window_len", "alpha", "step"}
+    assert set(j["config"]) == {"workload", "windows", "chunks", "regions", "col_components", "window_len", "alpha", "model_type", "step"}
 
 
 def test_reference_arm_non_zero_ranks_stay_silent():

@@ -90,3 +90,35 @@ def test_nb_dropin_binary_matches_reference_binary(tmp_path):
         open(os.path.join(gpu_out, "final_flagger_prediction.bed")).read()
     a, b = dropin._table(os.path.join(ref_out, "loglikelihood.tsv")), dropin._table(os.path.join(gpu_out, "loglikelihood.tsv"))
     assert a.shape == b.shape and np.allclose(a, b, rtol=1e-6, atol=2e-4)
+
+
+@pytest.mark.parametrize("n_regions,seed,iters", [(1, 91, 6), (3, 92, 4), (7, 93, 3)])
+def test_nb_device_resident_loop_equals_host_loop(monkeypatch, n_regions, seed, iters):
+    """hfg_run_em for the negative-binomial model: the device-resident loop (pmf, histogram fold, estimator update and M-step on
+    the device in fp64, hfg_nb_dev.cuh) against the same loop with the host between the iterations (libm table, long-double
+    digamma: HFG_NB_HOST_LOOP=1).  Rounding only: labels identical, log-likelihoods and parameters to 1e-9 / 1e-7."""
+    wl = synth.small_mixed(n_regions=n_regions, seed=seed)
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=n_regions, n_col_comps=K, model_type=NB, mean_read_length=wl.avg_alignment_len)
+    p0 = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    gpu = api.HmmFlaggerGPU(cfg, wl)
+    try:
+        pd, lld, labd = gpu.run_em(np.zeros((4, 4)), p0, iters, tol=1e-12)
+        monkeypatch.setenv("HFG_NB_HOST_LOOP", "1")
+        ph, llh, labh = gpu.run_em(np.zeros((4, 4)), p0, iters, tol=1e-12)
+        monkeypatch.delenv("HFG_NB_HOST_LOOP")
+        assert len(lld) == len(llh) == iters + 1
+        assert np.all(np.abs(lld - llh) <= 1e-9 * np.abs(llh)), (lld, llh)
+        assert np.array_equal(labd, labh), int((labd != labh).sum())
+        a, b = _abi.params_as_flat(pd), _abi.params_as_flat(ph)
+        nz = np.abs(b) > 0
+        assert np.all(np.abs(a[nz] - b[nz]) <= 1e-7 * np.abs(b[nz])), float(np.max(np.abs(a[nz] - b[nz]) / np.abs(b[nz])))
+        # the loop can be driven step by step as for the other models
+        gpu.em_begin(np.zeros((4, 4)), p0, tol=1e-12, max_esteps=3)
+        gpu.em_enqueue()
+        gpu.em_enqueue()
+        gpu.em_enqueue(final_pass=True)
+        p3, ll3, _, lab3 = gpu.em_finish()
+        assert len(ll3) == 3 and np.array_equal(ll3[:2], lld[:2])
+    finally:
+        gpu.close()
