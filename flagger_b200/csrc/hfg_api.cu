@@ -876,7 +876,8 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
             free(bins);
             double lgx1[HFG_NB_TABLE_X];
             for (int x = 0; x < HFG_NB_TABLE_X; x++) lgx1[x] = lgamma(x + 1);
-            if (e == cudaSuccess) e = cudaMalloc((void **) &ctx->d_nb_lgx1, sizeof(lgx1));
+            /* [256] lgamma(x + 1), then the histogram [R][4][256] the grid folds the tile masses into */
+            if (e == cudaSuccess) e = cudaMalloc((void **) &ctx->d_nb_lgx1, sizeof(double) * (256 + (size_t) R * 4 * 256));
             if (e == cudaSuccess) e = cudaMemcpy(ctx->d_nb_lgx1, lgx1, sizeof(lgx1), cudaMemcpyHostToDevice);
             if (e != cudaSuccess) return fail(ctx, HFG_ERR_CUDA, "negative-binomial bin lists: %s", cudaGetErrorString(e));
         }
@@ -1010,6 +1011,7 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     a.nb_bin_begin = ctx->d_nb_bins;
     a.nb_bin_tiles = ctx->d_nb_bins ? ctx->d_nb_bins + (size_t) ctx->cfg.n_regions * HFG_NB_BINS + 1 : NULL;
     a.nb_lgx1 = ctx->d_nb_lgx1;
+    a.nb_hist = ctx->d_nb_lgx1 ? ctx->d_nb_lgx1 + 256 : NULL;
 }
 
 /* negative binomial: the pmf of every (region, state, x) for these parameters (host, libm: hfg_nb.c) -> pinned staging

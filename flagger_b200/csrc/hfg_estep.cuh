@@ -164,6 +164,7 @@ struct EstepArgs {
     const int32_t *nb_bin_begin; /* [R * 250 + 1] first entry of every (region, coverage bin) in nb_bin_tiles */
     const int32_t *nb_bin_tiles; /* [n_tiles] the tiles of every bin, in tile order */
     const double *nb_lgx1;       /* [251] lgamma(x + 1) (host libm values) */
+    double *nb_hist;             /* [R][4][256] pair mass by (region, state, coverage bin): folded by the whole grid */
 };
 #define HFG_NB_XSTRIDE 256
 

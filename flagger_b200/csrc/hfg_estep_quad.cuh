@@ -670,8 +670,7 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
         if constexpr (NB) {
             if (A.em_mode == 1) {
                 tsync();
-                const int nan = hfgnb::tail_estimators(A.params, R, A.ncomp, A.nb_tile_col, A.nb_bin_begin, A.nb_bin_tiles, A.nb_lgx1,
-                                                       A.out, work, tid, NW, tsync, tail_clock);
+                const int nan = hfgnb::tail_estimators(A.params, R, A.ncomp, A.nb_hist, A.nb_lgx1, A.out, work, tid, NW, tsync, tail_clock);
                 if (nan) atomicOr(A.err_flags, 2);
                 tsync();
                 if (tid == 0) A.out[(size_t) R * SD + 1] = (double) __ldcg(A.err_flags);

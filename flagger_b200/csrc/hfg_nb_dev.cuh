@@ -20,8 +20,7 @@
 #define HFG_NB_DEV_BINS 250  /* HFG_NB_BINS: x = 250 is folded into bin 249 (count_data.c:56-64) */
 #define HFG_NB_DEV_X 251     /* HFG_NB_TABLE_X */
 
-#define HFG_NB_MAX_ITEMS 2048 /* items of <= 256 tiles in the histogram fold of one region: 250 bins + n_tiles / 256 */
-#define HFG_NB_TAIL_DOUBLES ((4 + 2 + HFG_MAX_COMPS) * 256 + 32 * 8 + 6 * 4 * HFG_MAX_COMPS + HFG_NB_MAX_ITEMS * 4 + HFG_NB_MAX_ITEMS / 2 + 32)
+#define HFG_NB_TAIL_DOUBLES ((4 + 2 + HFG_MAX_COMPS) * 256 + 32 * 8 + 6 * 4 * HFG_MAX_COMPS)
 
 namespace hfgnb {
 
@@ -56,13 +55,72 @@ __device__ __forceinline__ double state_prob(const hfg_region_params &p, int s, 
     return tot;
 }
 
+/* Histogram of the pair mass over the coverage value (hmm.c:615-617, count_data.c:56-64), folded by the WHOLE grid after the
+ * statistics phase (the caller has passed a grid barrier: every tile's column sums are in tile_col): bin (region, x) = the sum
+ * over the tiles whose key has coverage x, by state.  The (region, bin) pairs are dealt round-robin over the CTAs; a CTA adds a
+ * bin's tiles with one 32-byte load per thread and tile (all loads in flight), then a fixed tree: lanes, then warps in
+ * order -- the same bits on every run.  `red` = [WARPS][4] doubles of shared memory. */
+template <int THREADS>
+__device__ __forceinline__ void grid_fold_histogram(int R, const double *tile_col, const int32_t *bin_begin, const int32_t *bin_tiles,
+                                                    double *hist_g, double *red) {
+    constexpr int WARPS = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int pair = blockIdx.x; pair < R * HFG_NB_DEV_BINS; pair += gridDim.x) {
+        const int b0 = __ldg(bin_begin + pair), b1 = __ldg(bin_begin + pair + 1);
+        const int reg = pair / HFG_NB_DEV_BINS, x = pair % HFG_NB_DEV_BINS;
+        if (b0 == b1) { /* (CTA-uniform) an empty bin */
+            if (tid < 4) hist_g[((size_t) reg * 4 + tid) * 256 + x] = 0.0;
+            continue;
+        }
+        double h[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i0 = b0 + tid; i0 < b1; i0 += 4 * THREADS) {
+            int tl[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) tl[u] = i0 + u * THREADS < b1 ? __ldg(bin_tiles + i0 + u * THREADS) : -1;
+            double v[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (tl[u] >= 0) {
+                    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                 : "=d"(v[u][0]), "=d"(v[u][1]), "=d"(v[u][2]), "=d"(v[u][3])
+                                 : "l"(tile_col + (size_t) tl[u] * 4)
+                                 : "memory");
+                } else {
+                    v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) h[k] += v[u][k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) h[k] += __shfl_xor_sync(0xffffffffu, h[k], off);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) red[warp * 4 + k] = h[k];
+        }
+        __syncthreads();
+        if (tid < 4) {
+            double sum = 0.0;
+#pragma unroll 4
+            for (int wv = 0; wv < WARPS; wv++) sum += red[wv * 4 + tid];
+            hist_g[((size_t) reg * 4 + tid) * 256 + x] = sum;
+        }
+        __syncthreads();
+    }
+}
+
 /* Tail of the device-resident loop, run by the NW worker threads of the last CTA: histogram -> estimator sums, written into
  * the hfg_region_stats block `out` ([R][SD] doubles).  `scr` = shared memory: (4 + 2 + HFG_MAX_COMPS) * 256 + 32 * 8 + 6 * 4 * HFG_MAX_COMPS doubles (HFG_NB_TAIL_DOUBLES).
  * `sync` = the workers' barrier.  Returns a NaN flag (thread-local; OR it over the threads). */
 template <typename Sync>
-__device__ __forceinline__ int tail_estimators(const hfg_region_params *params, int R, const int32_t *ncomp, const double *tile_col,
-                                               const int32_t *bin_begin, const int32_t *bin_tiles, const double *lg_x1_g,
-                                               double *out, double *scr, int tid, int NW, Sync sync, long long *clk) {
+__device__ __forceinline__ int tail_estimators(const hfg_region_params *params, int R, const int32_t *ncomp, const double *hist_g,
+                                               const double *lg_x1_g, double *out, double *scr, int tid, int NW, Sync sync,
+                                               long long *clk) {
     const int SD = (int) (sizeof(hfg_region_stats) / sizeof(double));
     const int lane = tid & 31, warp = tid >> 5, NWARP = NW / 32;
     int nan = 0;
@@ -71,74 +129,15 @@ __device__ __forceinline__ int tail_estimators(const hfg_region_params *params, 
     double *probs = rcp + 512;                 /* [nc][256] weighted pmf of every component of the current state */
     double *red = probs + HFG_MAX_COMPS * 256; /* [NWARP][8] cross-warp reduction */
     Comp *cs = reinterpret_cast<Comp *>(red + 32 * 8); /* [4][HFG_MAX_COMPS] constants of every component of the region */
-    double *part = reinterpret_cast<double *>(cs + HFG_NS * HFG_MAX_COMPS); /* [HFG_NB_MAX_ITEMS][4] item sums of the histogram fold */
-    int *item_bin = reinterpret_cast<int *>(part + HFG_NB_MAX_ITEMS * 4);   /* [HFG_NB_MAX_ITEMS] bin | slice << 8, then [32] scan scratch */
     for (int reg = 0; reg < R; reg++) {
         const hfg_region_params &p = params[reg];
         hfg_region_stats *st = reinterpret_cast<hfg_region_stats *>(out + (size_t) reg * SD);
         if (tid < HFG_NS * HFG_MAX_COMPS && (tid % HFG_MAX_COMPS) < ncomp[tid / HFG_MAX_COMPS])
             cs[tid] = comp_setup(p, tid / HFG_MAX_COMPS, tid % HFG_MAX_COMPS);
-        /* histogram of this region: bin x = the column sums of the tiles whose key has coverage x.  The bins differ in size by
-         * orders of magnitude, so the work is cut into items of <= 256 tiles of one bin: a warp adds an item (eight tiles per
-         * lane, all loads in flight, fixed shuffle tree), then one thread per bin adds the bin's items in order. */
-        {
-            const int x = tid;
-            const int b0 = x < HFG_NB_DEV_BINS ? bin_begin[reg * HFG_NB_DEV_BINS + x] : 0;
-            const int b1 = x < HFG_NB_DEV_BINS ? bin_begin[reg * HFG_NB_DEV_BINS + x + 1] : 0;
-            const int cnt = (b1 - b0 + 255) >> 8;
-            int inc = cnt; /* inclusive scan of the item counts over the bins */
+        /* histogram of this region: folded by the whole grid before the tail (grid_fold_histogram) */
+        if (tid < HFG_NB_DEV_BINS) {
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, off);
-                if (lane >= off) inc += t;
-            }
-            if (lane == 31) item_bin[HFG_NB_MAX_ITEMS + warp] = inc;
-            sync();
-            int base = 0;
-            for (int wv = 0; wv < warp; wv++) base += item_bin[HFG_NB_MAX_ITEMS + wv];
-            int total = 0;
-            for (int wv = 0; wv < NWARP; wv++) total += item_bin[HFG_NB_MAX_ITEMS + wv];
-            const int first = base + inc - cnt;
-            for (int k = 0; k < cnt && first + k < HFG_NB_MAX_ITEMS; k++) item_bin[first + k] = x | (k << 8);
-            sync();
-            const int n_items = total < HFG_NB_MAX_ITEMS ? total : HFG_NB_MAX_ITEMS;
-            for (int item = warp; item < n_items; item += NWARP) {
-                const int ib = item_bin[item] & 255, ik = item_bin[item] >> 8;
-                const int s0 = bin_begin[reg * HFG_NB_DEV_BINS + ib] + (ik << 8), s1 = min(bin_begin[reg * HFG_NB_DEV_BINS + ib + 1], s0 + 256);
-                int tl[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int i = s0 + lane + 32 * u;
-                    tl[u] = i < s1 ? bin_tiles[i] : -1;
-                }
-                double h[4] = {0.0, 0.0, 0.0, 0.0};
-                double v[8][4];
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-#pragma unroll
-                    for (int k = 0; k < 4; k++) v[u][k] = tl[u] >= 0 ? __ldcg(tile_col + (size_t) tl[u] * 4 + k) : 0.0;
-#pragma unroll
-                for (int u = 0; u < 8; u++)
-#pragma unroll
-                    for (int k = 0; k < 4; k++) h[k] += v[u][k];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) h[k] += __shfl_xor_sync(0xffffffffu, h[k], off);
-                    if (lane == 0) part[item * 4 + k] = h[k];
-                }
-            }
-            sync();
-            if (x < HFG_NB_DEV_BINS) {
-                double h[4] = {0.0, 0.0, 0.0, 0.0};
-                for (int k = 0; k < cnt && first + k < HFG_NB_MAX_ITEMS; k++)
-#pragma unroll
-                    for (int q = 0; q < 4; q++) h[q] += part[(first + k) * 4 + q];
-                hist[x] = h[0];
-                hist[256 + x] = h[1];
-                hist[512 + x] = h[2];
-                hist[768 + x] = h[3];
-            }
+            for (int q = 0; q < 4; q++) hist[q * 256 + tid] = __ldcg(hist_g + ((size_t) reg * 4 + q) * 256 + tid);
         }
         sync();
         if (clk && tid == 0 && reg == 0) clk[12] = clock64();
