@@ -388,7 +388,7 @@ def run_ours(args):
     W_total = wl_full.n_windows
     R = wl_full.n_regions
 
-    gpu = api.HmmFlaggerGPU(cfg, wl)
+    gpu = api.HmmFlaggerGPU(cfg, wl, timing=True)
     fused = world > 1 and args.allreduce == "fused"
     if fused:
         gpu.peer_connect(dist)  # CUDA-IPC mailboxes: the kernel itself sums the statistics over the ranks

@@ -56,7 +56,7 @@ EXPORTED_SYMBOLS = (
     "hfg_forward_only", "hfg_get_posteriors", "hfg_get_chunk_logliks", "hfg_em_iteration_device",
     "hfg_stats_device_bytes", "hfg_get_labels", "hfg_best_num_collapsed_comps", "hfg_model_init", "hfg_mstep",
     "hfg_host_alloc", "hfg_host_free", "hfg_run_em", "hfg_em_begin", "hfg_em_enqueue", "hfg_em_finish",
-    "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_debug_blocking_steps", "hfg_kernel_launches", "hfg_last_estep_kernel_ms",
+    "hfg_em_enqueued_ms", "hfg_debug_l2_flush", "hfg_debug_set_timing", "hfg_debug_blocking_steps", "hfg_kernel_launches", "hfg_last_estep_kernel_ms",
     "hfg_last_call_device_ms", "hfg_debug_phase_clocks", "hfg_debug_exp", "hfg_debug_layout_check", "hfg_debug_beta",
     "hfg_debug_layout_compare", "hfg_peer_handle_bytes", "hfg_peer_export", "hfg_peer_connect", "hfg_peer_barrier", "hfg_read_cov",
     "hfg_read_bin", "hfg_cov_free", "hfg_write_summary_tsv", "hfg_benchmark_scores", "hfg_params_feasible", "hfg_squarem_alpha_rate",
@@ -243,12 +243,16 @@ class HmmFlaggerBatch:
 class HmmFlaggerGPU:
     """One libhfg context: a set of chunks resident on one GPU."""
 
-    def __init__(self, cfg, workload=None):
+    def __init__(self, cfg, workload=None, timing=False):
+        """timing=True: the blocking calls record CUDA events (last_estep_kernel_ms / last_call_device_ms) and take the
+        graph path; by default a single-region model takes the one-launch fast path (hfg_api.cu::run_blocking)."""
         self.cfg = np.ascontiguousarray(cfg)
         self._h = C.c_void_p()
         rc = lib().hfg_create(C.byref(self._h), ptr(self.cfg))
         if rc != 0:
             raise HfgError(rc, lib().hfg_last_error(None).decode())
+        if timing:
+            lib().hfg_debug_set_timing(self._h, C.c_int(1))
         self.n_regions = int(self.cfg["n_regions"][0])
         self.n_windows = 0
         self.n_chunks = 0

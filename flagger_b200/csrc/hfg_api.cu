@@ -40,6 +40,9 @@ struct hfg_ctx {
     cudaEvent_t ev0, ev1; /* around the E-step kernel */
     cudaEvent_t ev2, ev3; /* around the whole device side of the last blocking call */
     int ev_valid, span_valid;
+    int dbg;              /* HFG_DBG at hfg_create: instrumentation switches of the kernel */
+    int timing;           /* hfg_debug_set_timing: the blocking calls record ev0..ev3 (and give up their fast path) */
+    unsigned long long done_seq; /* blocking fast path: sequence number of the completion word behind h_out */
     /* device */
     uint32_t *d_wkeyT, *d_kdesc, *d_wposT, *d_wkeyH, *d_khot;
     int32_t *d_hot_key, *d_hot_range;
@@ -374,6 +377,7 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         hfg_destroy(ctx);
         return HFG_ERR_NOMEM;
     }
+    ctx->dbg = getenv("HFG_DBG") ? atoi(getenv("HFG_DBG")) : 0;
     ctx->graph_disabled = getenv("HFG_NO_GRAPH") != NULL; /* A/B switch: plain stream launches instead of graph replay */
     if (nb) {
         const size_t tb = sizeof(double) * (size_t) cfg->n_regions * 4 * HFG_NB_XSTRIDE;
@@ -680,12 +684,14 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
         ctx->em_max = HFG_EM_LOGLIK_SLOTS;
     }
     tm[2] = wall_ms();
-    ctx->h_out = (double *) arena_acquire(out_doubles * sizeof(double), ctx->device, &ctx->h_out_bytes, 2);
+    ctx->h_out = (double *) arena_acquire((out_doubles + 2) * sizeof(double), ctx->device, &ctx->h_out_bytes, 2); /* + the completion word */
     ctx->h_labels = (int8_t *) arena_acquire(w, ctx->device, &ctx->h_labels_bytes, 3);
     if (!ctx->h_out || !ctx->h_labels) {
         cudaGetLastError();
         return fail(ctx, HFG_ERR_NOMEM, "hfg_set_chunks: cannot allocate page-locked host memory");
     }
+    /* the completion word of the blocking fast path: the block may be a recycled one that still holds an old sequence number */
+    *reinterpret_cast<volatile unsigned long long *>(ctx->h_out + out_doubles) = 0ull;
     CU(cudaMemcpyAsync(ctx->d_seg_start, l->seg_start, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_seg_len, l->seg_len, cap * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_labels, 0xff, w, ctx->stream));
@@ -984,7 +990,7 @@ static void build_args(hfg_ctx *ctx, const double *alpha, double *out_dev, doubl
     a.posteriors = post_dev;
     a.err_flags = ctx->d_err;
     a.ticket = ctx->d_ticket;
-    a.dbg = getenv("HFG_DBG") ? atoi(getenv("HFG_DBG")) : 0;
+    a.dbg = ctx->dbg;
     a.tabMT = ctx->d_tabMT;
     a.wposT = ctx->d_wposT;
     if (ctx->quad >= 2)
@@ -1204,6 +1210,38 @@ static int run_blocking(hfg_ctx *ctx, const double *alpha, const hfg_region_para
     EstepArgs a;
     build_args(ctx, alpha, ctx->d_out, NULL, forward_only, 0, &a);
     a.labels_host = label_dst;
+    if (ctx->quad == 3 && R == 1 && !ctx->timing) {
+        /* Fast path (single-region models, the default kernel): ONE launch and nothing else on the stream.  The parameters
+         * travel in the kernel arguments (no upload node, no staging slot), no events are recorded, and the host does not
+         * synchronise the stream: the kernel's tail stores a sequence number behind the results it writes into the pinned
+         * block (after a system-wide fence that also covers the labels every CTA streamed to host memory), and the host
+         * polls that word.  The stream is queried now and then so that a failed launch ends the wait. */
+        const size_t out_doubles = (size_t) R * STATS_DOUBLES + 2;
+        volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(ctx->h_out + out_doubles);
+        static unsigned long long g_done_seq = 0; /* process-wide: a recycled block never sees a number twice */
+        const unsigned long long seq = ctx->done_seq = __atomic_add_fetch(&g_done_seq, 1ull, __ATOMIC_RELAXED);
+        a.params_inline = 1;
+        a.inl_params = params[0];
+        a.done_flag = const_cast<unsigned long long *>(flag);
+        a.done_seq = seq;
+        void *kargs[] = {(void *) &a};
+        CU(cudaLaunchCooperativeKernel(ctx->kernel, dim3(ctx->grid), dim3(ctx->threads), kargs, ctx->smem_bytes, ctx->stream));
+        ctx->ev_valid = ctx->span_valid = 0;
+        ctx->launches += 1;
+        memcpy(ctx->last_alpha, alpha, sizeof(double) * 16);
+        memcpy(ctx->last_params, params, sizeof(hfg_region_params) * (size_t) R);
+        ctx->have_last = 1;
+        for (unsigned spins = 1; *flag != seq; spins++) {
+            if ((spins & 0x3fffu) == 0 && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) break;
+            __builtin_ia32_pause();
+        }
+        if (*flag != seq) { /* the stream is idle or broken and the word never came */
+            CU(cudaStreamSynchronize(ctx->stream));
+            if (*flag != seq) return fail(ctx, HFG_ERR_CUDA, "the E-step kernel ended without delivering its results");
+        }
+        if (with_labels && !label_alias) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
+        return parse_out(ctx, stats, loglik);
+    }
     CU(cudaEventSynchronize(ctx->stage_ev[0])); /* slot 0 may still feed an asynchronous device-variant call */
     memcpy(ctx->h_params[0], params, sizeof(hfg_region_params) * (size_t) R);
     if (!ctx->graph_disabled) {
@@ -1423,6 +1461,12 @@ extern "C" double hfg_em_enqueued_ms(hfg_ctx *ctx, int i) {
     if (cudaEventSynchronize(ctx->em_ev[2 * i + 1]) != cudaSuccess) return -1.0;
     if (cudaEventElapsedTime(&ms, ctx->em_ev[2 * i], ctx->em_ev[2 * i + 1]) != cudaSuccess) return -1.0;
     return (double) ms;
+}
+
+extern "C" int hfg_debug_set_timing(hfg_ctx *ctx, int on) {
+    if (!ctx) return HFG_ERR_INVALID;
+    ctx->timing = on != 0;
+    return HFG_OK;
 }
 
 extern "C" int hfg_debug_l2_flush(hfg_ctx *ctx, size_t bytes) {

@@ -165,6 +165,13 @@ struct EstepArgs {
     const int32_t *nb_bin_tiles; /* [n_tiles] the tiles of every bin, in tile order */
     const double *nb_lgx1;       /* [251] lgamma(x + 1) (host libm values) */
     double *nb_hist;             /* [R][4][256] pair mass by (region, state, coverage bin): folded by the whole grid */
+    /* blocking calls, fast path (hfg_api.cu::run_blocking): a single-region model travels in the kernel arguments instead of
+     * through an upload, and the tail announces the results with one store the host polls instead of synchronising the
+     * stream */
+    unsigned long long *done_flag; /* mapped pinned host word, or NULL */
+    unsigned long long done_seq;   /* the value that says "this call's results are in host memory" */
+    int32_t params_inline;         /* read region 0's parameters from inl_params, not from `params` */
+    hfg_region_params inl_params;
 };
 #define HFG_NB_XSTRIDE 256
 

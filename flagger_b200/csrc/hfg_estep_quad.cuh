@@ -555,7 +555,9 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
     const int R = A.n_regions, NSTAT = hfg_nstat(A.G);
     /* =========================== phase D: grid reduction by the last CTA to arrive ========================== */
     if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 6] = clock64();
-    __threadfence();
+    /* (a polled completion word: this CTA's label stores into host memory are ordered before the word the tail writes) */
+    if (A.done_flag) __threadfence_system();
+    else __threadfence();
     __syncthreads();
     if (tid == 0) {
         const int ticket = atomicAdd(A.ticket, 1);
@@ -844,6 +846,13 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
         if (tid == 0) {
             *A.err_flags = 0;
             tail_clock[6] = clock64();
+        }
+        if (A.done_flag) {
+            /* every result of this call -- the labels of all CTAs (ordered by their fences and the ticket), the block above --
+             * precedes the word the host polls */
+            __threadfence_system();
+            tsync();
+            if (tid == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.done_flag), "l"(A.done_seq) : "memory");
         }
     }
 }

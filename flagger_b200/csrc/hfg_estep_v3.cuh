@@ -91,7 +91,7 @@ __device__ __forceinline__ void st_row_cg(double *p, double a, double b, double 
 }  // namespace hfg3
 
 template <int THREADS, bool NB = false>
-__global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const EstepArgs A) {
+__global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const __grid_constant__ EstepArgs A) {
     constexpr int WARPS = THREADS / 32, QUADS = THREADS / 4;
     using namespace hfg3;
     cg::grid_group grid = cg::this_grid();
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const EstepArg
         /* one (region, mask, pre) row of the conditional transition table (Transition_getProbConditional,
          * hmm_utils.c:2278-2292) */
         const int r = idx >> 5, mask = (idx >> 2) & 7, pre = idx & 3;
-        const hfg_region_params &p = A.params[r];
+        const hfg_region_params &p = A.params_inline ? A.inl_params : A.params[r];
         bool valid[5] = {true, (mask & 1) == 0, true, (mask & 2) == 0, (mask & 4) != 0};
         double tot = 0.0;
 #pragma unroll
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const EstepArg
     }
     for (int idx = (tid + THREADS - 256) % THREADS; idx < R * (12 + G); idx += THREADS) {
         const int r = idx / (12 + G), qq = idx % (12 + G);
-        const hfg_region_params &p = A.params[r];
+        const hfg_region_params &p = A.params_inline ? A.inl_params : A.params[r];
         double *rt = rtab + (size_t) r * rt_stride;
         if (qq < 4) {
             rt[RT_START + qq] = p.trans[HFG_NS][qq];

@@ -295,6 +295,11 @@ double hfg_last_estep_kernel_ms(hfg_ctx *ctx);
  * read-back of statistics (and labels). */
 double hfg_last_call_device_ms(hfg_ctx *ctx);
 
+/* on != 0: the blocking calls record the CUDA events the two functions above read.  Off by default: a single-region model
+ * then takes the one-launch path (parameters in the kernel arguments, completion word polled in pinned memory) and the two
+ * functions return -1. */
+int hfg_debug_set_timing(hfg_ctx *ctx, int on);
+
 /* Test / profiling hooks (no reference counterpart): phase timeline of the last E-step kernel ([grid][12]: eight clock64
  * values + SM id) and the kernel's exponential applied to n host values. */
 int hfg_debug_phase_clocks(hfg_ctx *ctx, long long *out, int *grid);

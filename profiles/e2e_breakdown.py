@@ -6,7 +6,7 @@ import numpy as np
 from flagger_b200 import api, synth, _abi
 wl = synth.config2(); K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
 cfg = _abi.make_config(n_col_comps=K); p = api.model_init(cfg, wl.region_coverages, wl.window_len)
-g = api.HmmFlaggerGPU(cfg, wl)
+g = api.HmmFlaggerGPU(cfg, wl, timing=True)
 stats = np.zeros(1, dtype=_abi.region_stats_dtype); labels = np.empty(wl.n_windows, np.int8)
 for want in (False, True):
     for i in range(5): g.em_iteration(synth.HIFI_ALPHA, p, want_labels=want, stats=stats, labels=labels if want else None)

@@ -6,7 +6,7 @@ import numpy as np
 from flagger_b200 import api, synth, _abi
 wl = synth.config2(); K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
 cfg = _abi.make_config(n_col_comps=K); p = api.model_init(cfg, wl.region_coverages, wl.window_len)
-g = api.HmmFlaggerGPU(cfg, wl)
+g = api.HmmFlaggerGPU(cfg, wl, timing=True)
 ms = []
 for i in range(6):
     g.em_iteration(synth.HIFI_ALPHA, p, want_labels=False); ms.append(g.last_estep_kernel_ms())

@@ -11,7 +11,7 @@ names = ["T+bar1", "A+B", "wait2", "C1(t0)", "C2+bar3", "S+Dred", "wait4"]  # se
 for world, wpt in ((8, 1), (8, 2), (16, 1), (4, 1), (4, 4)):
     wl = hdist.shard_chunks(wl_full, 0, world)
     os.environ["HFG_MIN_WPT"] = str(wpt)
-    g = api.HmmFlaggerGPU(cfg, wl)
+    g = api.HmmFlaggerGPU(cfg, wl, timing=True)
     for i in range(5):
         g.em_iteration(synth.HIFI_ALPHA, p, want_labels=False)
     c = g.debug_phase_clocks(); d = np.diff(c[:, :8], axis=1)

@@ -13,7 +13,7 @@ for world in (1, 2, 4, 8, 16, 64):
     row = []
     for wpt in (1, 2, 4):
         os.environ["HFG_MIN_WPT"] = str(wpt)
-        g = api.HmmFlaggerGPU(cfg, wl)
+        g = api.HmmFlaggerGPU(cfg, wl, timing=True)
         ts = []
         for i in range(12):
             g.em_iteration(synth.HIFI_ALPHA, p, want_labels=False)

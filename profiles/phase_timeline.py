@@ -10,7 +10,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 wl={"cfg2": synth.config2, "cfg3": synth.config3, "cfg4": synth.config4}[which]()
 K=api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
 cfg=_abi.make_config(n_regions=len(wl.region_coverages), n_col_comps=K); p=api.model_init(cfg, wl.region_coverages, wl.window_len)
-g=api.HmmFlaggerGPU(cfg, wl)
+g=api.HmmFlaggerGPU(cfg, wl, timing=True)
 ms=[]
 for i in range(6):
     g.em_iteration(synth.HIFI_ALPHA, p, want_labels=False); ms.append(g.last_estep_kernel_ms())

@@ -33,7 +33,7 @@ def ctx(kernel, cfg, wl):
         os.environ["HFG_KERNEL"] = CANDIDATE
     else:
         os.environ.pop("HFG_KERNEL", None)
-    return api.HmmFlaggerGPU(cfg, wl)
+    return api.HmmFlaggerGPU(cfg, wl, timing=True)
 
 
 def diff_stats(a, b, tag):
