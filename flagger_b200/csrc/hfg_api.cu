@@ -545,16 +545,46 @@ extern "C" void hfg_destroy(hfg_ctx *ctx) {
 }
 
 /* page-locked host memory: result buffers allocated here are written by the device directly (no staging copy) */
+/* the buffers handed out by hfg_host_alloc: the blocking calls recognise them without asking the driver every time */
+#define HFG_HOST_REG 64
+static struct { void *p; size_t bytes; } g_host_reg[HFG_HOST_REG];
+static pthread_mutex_t g_host_reg_lock = PTHREAD_MUTEX_INITIALIZER;
+
 extern "C" void *hfg_host_alloc(size_t bytes) {
     void *p = NULL;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
         cudaGetLastError();
         return NULL;
     }
+    pthread_mutex_lock(&g_host_reg_lock);
+    for (int i = 0; i < HFG_HOST_REG; i++)
+        if (!g_host_reg[i].p) {
+            g_host_reg[i].p = p;
+            g_host_reg[i].bytes = bytes ? bytes : 1;
+            break;
+        }
+    pthread_mutex_unlock(&g_host_reg_lock);
     return p;
 }
 extern "C" void hfg_host_free(void *p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    pthread_mutex_lock(&g_host_reg_lock);
+    for (int i = 0; i < HFG_HOST_REG; i++)
+        if (g_host_reg[i].p == p) g_host_reg[i].p = NULL;
+    pthread_mutex_unlock(&g_host_reg_lock);
+    cudaFreeHost(p);
+}
+/* 1 when [p, p + bytes) lies inside a live hfg_host_alloc buffer (page-locked and, under unified addressing, device-visible at
+ * the same address) */
+static int host_reg_contains(const void *p, size_t bytes) {
+    int hit = 0;
+    pthread_mutex_lock(&g_host_reg_lock);
+    for (int i = 0; i < HFG_HOST_REG && !hit; i++) {
+        const char *b = (const char *) g_host_reg[i].p;
+        if (b && (const char *) p >= b && (const char *) p + bytes <= b + g_host_reg[i].bytes) hit = 1;
+    }
+    pthread_mutex_unlock(&g_host_reg_lock);
+    return hit;
 }
 
 extern "C" int64_t hfg_num_windows(const hfg_ctx *ctx) { return ctx && ctx->have_chunks ? ctx->lay.n_windows : 0; }
@@ -1133,7 +1163,8 @@ static int capture_graph(hfg_ctx *ctx, const EstepArgs *a) {
 }
 
 /* the device-side address of p when p is page-locked host memory the device can write directly, else NULL */
-static int8_t *pinned_device_alias(const void *p) {
+static int8_t *pinned_device_alias(const void *p, size_t bytes) {
+    if (host_reg_contains(p, bytes)) return (int8_t *) p; /* hfg_host_alloc: no driver query */
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
         cudaGetLastError();
@@ -1151,7 +1182,7 @@ static int run_blocking_nb(hfg_ctx *ctx, const hfg_region_params *params, int fo
     const int R = ctx->cfg.n_regions;
     const hfg_layout *l = &ctx->lay;
     CU(cudaSetDevice(ctx->device));
-    int8_t *label_alias = with_labels ? pinned_device_alias(labels) : NULL;
+    int8_t *label_alias = with_labels ? pinned_device_alias(labels, (size_t) ctx->lay.n_windows) : NULL;
     int8_t *label_dst = !with_labels ? NULL : (label_alias ? label_alias : ctx->h_labels);
     static const double zero_alpha[16] = {0};
     EstepArgs a;
@@ -1204,7 +1235,7 @@ static int run_blocking(hfg_ctx *ctx, const double *alpha, const hfg_region_para
     const int with_labels = labels != NULL;
     CU(cudaSetDevice(ctx->device));
     /* where the kernel streams the labels: the caller's buffer when it is page-locked, else the pinned staging buffer */
-    int8_t *label_alias = with_labels ? pinned_device_alias(labels) : NULL;
+    int8_t *label_alias = with_labels ? pinned_device_alias(labels, (size_t) ctx->lay.n_windows) : NULL;
     int8_t *label_dst = !with_labels ? NULL : (label_alias ? label_alias : ctx->h_labels);
     const int R = ctx->cfg.n_regions;
     EstepArgs a;

@@ -555,11 +555,13 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
     const int R = A.n_regions, NSTAT = hfg_nstat(A.G);
     /* =========================== phase D: grid reduction by the last CTA to arrive ========================== */
     if (tid == 0) A.phase_clock[blockIdx.x * HFG_PC_STRIDE + 6] = clock64();
-    /* (a polled completion word: this CTA's label stores into host memory are ordered before the word the tail writes) */
-    if (A.done_flag) __threadfence_system();
-    else __threadfence();
     __syncthreads();
     if (tid == 0) {
+        /* one cumulative fence behind the CTA barrier (the pattern of a cooperative-groups grid barrier) orders every thread's
+         * partials -- and, at system scope when the host polls a completion word, the labels this CTA streamed into host
+         * memory -- before the ticket */
+        if (A.done_flag) __threadfence_system();
+        else __threadfence();
         const int ticket = atomicAdd(A.ticket, 1);
         *s_last = ticket == (int) gridDim.x - 1;
     }
