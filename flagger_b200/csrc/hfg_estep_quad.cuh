@@ -236,33 +236,32 @@ __device__ __noinline__ int hfg_fit_pred_round_dev(HfgFitState *st, const double
     const unsigned snap_s = (unsigned) __cvta_generic_to_shared(snap);
     /* who holds the value at x1 / x2: 0, 1 the round's y1, y2; 2 + t the point of step t */
     int i1 = 0, i2 = 1;
+    /* The walk is one dependent chain, so it is written without branches (a branch on a fresh comparison costs more than the
+     * arithmetic of a step): the polynomial's value at the two interior points is carried like the objective's (one new
+     * evaluation per step, whether the step needs it or not), every update is a select.  The arithmetic that produces the
+     * points is the serial routine's (lo + inv_phi2 * span, lo + inv_phi * span; no contraction). */
+    auto poly = [&](double x) {
+        const double d = x - xs;
+        return d * fma(d, fma(d, fma(d, c4, c3), c2), c1);
+    };
+    double q1 = poly(sx1), q2 = poly(sx2);
 #pragma unroll 1
     for (int t = 0; t < L; t++) {
         /* both points on one side of the maximum: the nearer one is higher; x* between them: the polynomial decides */
-        int b;
-        if (sx2 <= xs) b = 0;
-        else if (sx1 >= xs) b = 1;
-        else {
-            const double d1 = sx1 - xs, d2 = sx2 - xs;
-            const double p1 = d1 * fma(d1, fma(d1, fma(d1, c4, c3), c2), c1), p2 = d2 * fma(d2, fma(d2, fma(d2, c4, c3), c2), c1);
-            b = p1 > p2;
-        }
-        int word = i1 | (i2 << 6) | (b << 12); /* the operands and the predicted outcome of step t's comparison */
+        const bool left = sx2 <= xs, right = sx1 >= xs;
+        const bool b = left ? false : (right ? true : q1 > q2);
+        int word = i1 | (i2 << 6) | ((int) b << 12); /* the operands and the predicted outcome of step t's comparison */
         sspan = inv_phi * sspan;
-        double xn;
-        if (b) {
-            shi = sx2; sx2 = sx1; i2 = i1;
-            sx1 = slo + inv_phi2 * sspan;
-            xn = sx1;
-            i1 = 2 + t;
-        } else {
-            slo = sx1; sx1 = sx2; i1 = i2;
-            sx2 = slo + inv_phi * sspan;
-            xn = sx2;
-            i2 = 2 + t;
-        }
+        const double nlo = b ? slo : sx1, nhi = b ? sx2 : shi;
+        const double xn = nlo + (b ? inv_phi2 : inv_phi) * sspan;
+        const double qn = poly(xn);
+        const double nx1 = b ? xn : sx2, nx2 = b ? sx1 : xn;
+        const double nq1 = b ? qn : q2, nq2 = b ? q1 : qn;
+        const int ni1 = b ? 2 + t : i2, ni2 = b ? i1 : 2 + t;
+        slo = nlo; shi = nhi; sx1 = nx1; sx2 = nx2; q1 = nq1; q2 = nq2; i1 = ni1; i2 = ni2;
         word |= (i1 << 13) | (i2 << 19); /* the holders after step t */
-        if (lane == 0) {
+        {
+            /* (every lane stores the same values: no predicate, no branch) */
             const unsigned row = snap_s + 64u * (unsigned) t;
             asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row), "d"(xn), "d"(slo) : "memory");
             asm volatile("st.shared.v2.f64 [%0+16], {%1, %2};" ::"r"(row), "d"(sx1), "d"(sx2) : "memory");

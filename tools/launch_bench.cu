@@ -81,6 +81,38 @@ int main() {
         }
         printf("%-40s alone %.2f us, right behind a memset %.2f us\n", c.name, 1e3 * alone / 20, 1e3 * after / 20);
     }
+    // everything queued behind a LONG memset (the bench's 256 MiB L2 flush): the host's launch latency is hidden, what remains
+    // is the device's own event -> kernel -> event cost; then the same sequence as a captured graph
+    {
+        void *big; cudaMalloc(&big, 256 << 20);
+        float q = 0;
+        for (int i = 0; i < 30; i++) {
+            cudaMemsetAsync(big, 0x5a, 256 << 20, s);
+            cudaEventRecord(e0, s);
+            cudaLaunchCooperativeKernel((void *) kc, dim3(148), dim3(512), args, smem, s);
+            cudaEventRecord(e1, s);
+            cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (i >= 10) q += ms;
+        }
+        printf("cooperative, queued behind a 256 MiB memset: %.2f us event to event\n", 1e3 * q / 20);
+        cudaGraph_t g; cudaGraphExec_t ge;
+        cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        cudaMemsetAsync(big, 0x5a, 256 << 20, s);
+        cudaEventRecordWithFlags(e0, s, cudaEventRecordExternal);
+        cudaLaunchCooperativeKernel((void *) kc, dim3(148), dim3(512), args, smem, s);
+        cudaEventRecordWithFlags(e1, s, cudaEventRecordExternal);
+        cudaStreamEndCapture(s, &g);
+        cudaGraphInstantiate(&ge, g, 0);
+        q = 0;
+        for (int i = 0; i < 30; i++) {
+            cudaGraphLaunch(ge, s);
+            cudaEventSynchronize(e1);
+            cudaStreamSynchronize(s);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); if (i >= 10) q += ms;
+        }
+        printf("the same as a graph (memset, event, kernel, event): %.2f us event to event\n", 1e3 * q / 20);
+        cudaFree(big);
+    }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
