@@ -858,7 +858,11 @@ extern "C" int hfg_set_chunks(hfg_ctx *ctx, int32_t n_chunks, const hfg_chunk_de
             /* the M-step of the device-resident loop works on shared-memory copies behind the region tables */
             size_t need = ((((size_t) R * QRT_STRIDE(G) + 1) & ~(size_t) 1) * sizeof(double)) + mstep_work_bytes(ctx->threads, 1);
             /* negative binomial: the tail's histogram / estimator scratch (hfg_nb_dev.cuh) */
-            if (ctx->nb) need += (size_t) HFG_NB_TAIL_DOUBLES * sizeof(double);
+            if (ctx->nb) {
+                int np = 0;
+                for (int st = 0; st < HFG_NUM_STATES; st++) np += ctx->cfg.n_comps[st];
+                need += (size_t) HFG_NB_TAIL_DOUBLES(np) * sizeof(double);
+            }
             if (ctx->smem_bytes < need) ctx->smem_bytes = need;
         }
         CU(cudaMemsetAsync(ctx->d_khot, 0xff, (size_t) l->n_keys * sizeof(uint32_t), ctx->stream));

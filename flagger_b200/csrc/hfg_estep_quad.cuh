@@ -613,7 +613,8 @@ __device__ __forceinline__ void hfg_estep_tail(const EstepArgs &A, double *wstat
         /* four totals per warp at a time: the lanes add the CTAs' partials with stride 32 (all loads of a round are
          * independent and in flight together), then a fixed xor-shuffle tree -- the same association on every run */
         {
-            constexpr int QU = 4;
+            constexpr int QU = 4; /* (measured: 8 totals per warp and round -- 40 loads in flight -- is SLOWER, 20 300 against 16 300 cycles
+                                     for 7 regions: the tail runs cold, longer straight-line code costs more instruction fetches) */
             const int NQ = R * NSTAT;
             for (int q0 = warp * QU; q0 < NQ; q0 += (NW / 32) * QU) {
                 double sum[QU];

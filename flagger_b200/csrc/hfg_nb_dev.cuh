@@ -20,7 +20,7 @@
 #define HFG_NB_DEV_BINS 250  /* HFG_NB_BINS: x = 250 is folded into bin 249 (count_data.c:56-64) */
 #define HFG_NB_DEV_X 251     /* HFG_NB_TABLE_X */
 
-#define HFG_NB_TAIL_DOUBLES ((4 + 2 + HFG_MAX_COMPS) * 256 + 32 * 8 + 6 * 4 * HFG_MAX_COMPS)
+#define HFG_NB_TAIL_DOUBLES(NP) ((4 + 1 + (NP)) * 256 + 7 * (NP)) /* histogram, lgamma(x + 1), pmf of NP components, their constants */
 
 namespace hfgnb {
 
@@ -115,8 +115,12 @@ __device__ __forceinline__ void grid_fold_histogram(int R, const double *tile_co
 }
 
 /* Tail of the device-resident loop, run by the NW worker threads of the last CTA: histogram -> estimator sums, written into
- * the hfg_region_stats block `out` ([R][SD] doubles).  `scr` = shared memory: (4 + 2 + HFG_MAX_COMPS) * 256 + 32 * 8 + 6 * 4 * HFG_MAX_COMPS doubles (HFG_NB_TAIL_DOUBLES).
- * `sync` = the workers' barrier.  Returns a NaN flag (thread-local; OR it over the threads). */
+ * the hfg_region_stats block `out` ([R][SD] doubles).  `scr` = shared memory, HFG_NB_TAIL_DOUBLES doubles.  `sync` = the
+ * workers' barrier.  Returns a NaN flag (thread-local; OR it over the threads).
+ * Two parallel steps per region instead of a loop over states and components: (1) the weighted pmf of every (component, bin)
+ * with mass in its state's histogram, dealt over all threads; (2) one WARP per (state, component): eight consecutive bins
+ * per lane, psi(r + x) - psi(r) as a running sum of reciprocals (lane-local, then a shuffle scan of the lanes' totals), the
+ * four estimator sums in bin order per lane and by a fixed shuffle tree over the lanes: no cross-warp reduction. */
 template <typename Sync>
 __device__ __forceinline__ int tail_estimators(const hfg_region_params *params, int R, const int32_t *ncomp, const double *hist_g,
                                                const double *lg_x1_g, double *out, double *scr, int tid, int NW, Sync sync,
@@ -124,88 +128,92 @@ __device__ __forceinline__ int tail_estimators(const hfg_region_params *params, 
     const int SD = (int) (sizeof(hfg_region_stats) / sizeof(double));
     const int lane = tid & 31, warp = tid >> 5, NWARP = NW / 32;
     int nan = 0;
-    double *hist = scr;                       /* [4][250] of the current region */
-    double *rcp = hist + 4 * 256;             /* [32] the warps' totals of the scan of 1 / (r + x - 1) */
-    double *probs = rcp + 512;                 /* [nc][256] weighted pmf of every component of the current state */
-    double *red = probs + HFG_MAX_COMPS * 256; /* [NWARP][8] cross-warp reduction */
-    Comp *cs = reinterpret_cast<Comp *>(red + 32 * 8); /* [4][HFG_MAX_COMPS] constants of every component of the region */
+    const int pb[HFG_NS + 1] = {0, ncomp[0], ncomp[0] + ncomp[1], ncomp[0] + ncomp[1] + ncomp[2], ncomp[0] + ncomp[1] + ncomp[2] + ncomp[3]};
+    const int NP = pb[HFG_NS]; /* (state, component) pairs, state-major */
+    double *hist = scr;                /* [4][256] of the current region */
+    double *lgx = hist + 4 * 256;      /* [256] lgamma(x + 1) */
+    double *probs = lgx + 256;         /* [NP][256] weighted pmf of every component */
+    Comp *cs = reinterpret_cast<Comp *>(probs + (size_t) NP * 256); /* [NP] constants of every component of the region */
+    double *wn = reinterpret_cast<double *>(cs + NP);               /* [NP] weight numerators, for the states' denominators */
+    if (tid < 256) lgx[tid] = tid < HFG_NB_DEV_X ? __ldg(lg_x1_g + tid) : 0.0;
+    auto state_of = [&](int q) { return q < pb[1] ? 0 : (q < pb[2] ? 1 : (q < pb[3] ? 2 : 3)); };
     for (int reg = 0; reg < R; reg++) {
         const hfg_region_params &p = params[reg];
         hfg_region_stats *st = reinterpret_cast<hfg_region_stats *>(out + (size_t) reg * SD);
-        if (tid < HFG_NS * HFG_MAX_COMPS && (tid % HFG_MAX_COMPS) < ncomp[tid / HFG_MAX_COMPS])
-            cs[tid] = comp_setup(p, tid / HFG_MAX_COMPS, tid % HFG_MAX_COMPS);
-        /* histogram of this region: folded by the whole grid before the tail (grid_fold_histogram) */
-        if (tid < HFG_NB_DEV_BINS) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) hist[q * 256 + tid] = __ldcg(hist_g + ((size_t) reg * 4 + q) * 256 + tid);
+        if (tid < NP) {
+            const int sq = state_of(tid);
+            cs[tid] = comp_setup(p, sq, tid - pb[sq]);
         }
+        /* histogram of this region: folded by the whole grid before the tail (grid_fold_histogram) */
+        for (int i = tid; i < 4 * 256; i += NW) hist[i] = (i & 255) < HFG_NB_DEV_BINS ? __ldcg(hist_g + (size_t) reg * 4 * 256 + i) : 0.0;
         sync();
         if (clk && tid == 0 && reg == 0) clk[12] = clock64();
-        for (int s = 0; s < HFG_NS; s++) {
-            const int nc = ncomp[s];
-            const int x = tid; /* one bin per thread (NW >= 250) */
-            const double mass = x < HFG_NB_DEV_BINS ? hist[s * 256 + x] : 0.0;
-            const double lgx = x < HFG_NB_DEV_X ? __ldg(lg_x1_g + x) : 0.0;
-            double total = 0.0;
-            for (int c = 0; c < nc; c++) {
-                const Comp cc = cs[s * HFG_MAX_COMPS + c];
-                const double pr = x < HFG_NB_DEV_BINS ? comp_prob(cc, x, lgx, &nan) : 0.0;
-                if (x < HFG_NB_DEV_BINS) probs[c * 256 + x] = pr;
-                total += pr;
-            }
-            for (int c = 0; c < nc; c++) {
-                const Comp cc = cs[s * HFG_MAX_COMPS + c];
-                /* psi(r + x) - psi(r) = sum_{i < x} 1 / (r + i) (the recurrence of hmm_utils.c:392-406 with the digamma(r) it starts
-                 * from and subtracts again left out): reciprocals side by side, inclusive scan over the bins (warp shuffles, then the
-                 * warps' totals in order) */
-                double psi_x = (x >= 1 && x < HFG_NB_DEV_BINS) ? 1.0 / (cc.r + x - 1) : 0.0;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const double t = __shfl_up_sync(0xffffffffu, psi_x, off);
-                    if (lane >= off) psi_x += t;
-                }
-                if (lane == 31) rcp[warp] = psi_x;
-                sync();
-                for (int wv = 0; wv < warp; wv++) psi_x += rcp[wv];
-                double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-                if (x < HFG_NB_DEV_BINS && 0 < mass) {
-                    const double w = mass * probs[c * 256 + x] / total;
-                    const double delta = cc.r * psi_x;
-                    v[0] = w * delta;                               /* var_num (lambda estimator) */
-                    v[1] = w;                                       /* var_den, weight_num */
-                    v[2] = w * delta * cc.bt;                       /* mean_num (theta estimator) */
-                    v[3] = w * delta * cc.bt + w * (x - delta);     /* mean_den */
-                }
-                /* fixed tree: lanes, then warps in order */
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
-                    if (lane == 0) red[warp * 8 + k] = v[k];
-                }
-                sync();
-                if (tid < 4) {
-                    double sum = 0.0;
-                    for (int wv = 0; wv < NWARP; wv++) sum += red[wv * 8 + tid];
-                    if (tid == 0) st->var_num[s][c] = sum;
-                    if (tid == 1) {
-                        st->var_den[s][c] = sum;
-                        st->weight_num[s][c] = sum;
-                    }
-                    if (tid == 2) st->mean_num[s][c] = sum;
-                    if (tid == 3) st->mean_den[s][c] = sum;
-                }
-                sync();
-            }
-            if (clk && tid == 0 && reg == 0 && s < 3) clk[13 + s] = clock64();
-            /* every component's weight estimator has the mass of all components of the state as its denominator */
-            if (tid == 0) {
-                double den = 0.0;
-                for (int c = 0; c < nc; c++) den += st->weight_num[s][c];
-                for (int c = 0; c < nc; c++) st->weight_den[s][c] = den;
-            }
-            sync();
+        /* (1) the pmf wherever the state's histogram has mass (NegativeBinomial_updateEstimator skips the empty bins) */
+        for (int i = tid; i < NP * 256; i += NW) {
+            const int q = i >> 8, x = i & 255, sq = state_of(q);
+            if (x < HFG_NB_DEV_BINS && 0 < hist[sq * 256 + x]) probs[i] = comp_prob(cs[q], x, lgx[x], &nan);
         }
+        sync();
+        if (clk && tid == 0 && reg == 0) clk[13] = clock64();
+        /* (2) one warp per (state, component) */
+        for (int q = warp; q < NP; q += NWARP) {
+            const int sq = state_of(q), c = q - pb[sq], nc = ncomp[sq];
+            const Comp cc = cs[q];
+            /* running sum of 1 / (r + j), j < x: the lanes before this one (shuffle scan of the lanes' totals), then the lane's
+             * own bins as it goes.  The loops are NOT unrolled: this code runs once per launch on cold instruction caches, where
+             * every distinct instruction costs a fetch -- short loops beat straight-line code here. */
+            double run = 0.0;
+#pragma unroll 1
+            for (int u = 0; u < 8; u++) run += 1.0 / (cc.r + (8 * lane + u));
+            double before = run; /* inclusive scan of the lanes' totals, made exclusive below */
+#pragma unroll 1
+            for (int off = 1; off < 32; off <<= 1) {
+                const double t = __shfl_up_sync(0xffffffffu, before, off);
+                if (lane >= off) before += t;
+            }
+            double psi = before - run; /* psi(r + x) - psi(r) at the lane's first bin */
+            double v[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+            for (int u = 0; u < 8; u++) {
+                const int x = 8 * lane + u;
+                const double mass = x < HFG_NB_DEV_BINS ? hist[sq * 256 + x] : 0.0;
+                if (0 < mass) {
+                    double total = 0.0;
+#pragma unroll 1
+                    for (int c2 = 0; c2 < nc; c2++) total += probs[(pb[sq] + c2) * 256 + x];
+                    const double w = mass * probs[q * 256 + x] / total;
+                    const double delta = cc.r * psi;
+                    v[0] += w * delta;                           /* var_num (lambda estimator) */
+                    v[1] += w;                                   /* var_den, weight_num */
+                    v[2] += w * delta * cc.bt;                   /* mean_num (theta estimator) */
+                    v[3] += w * delta * cc.bt + w * (x - delta); /* mean_den */
+                }
+                psi += 1.0 / (cc.r + x);
+            }
+#pragma unroll 1
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+            }
+            if (lane == 0) {
+                wn[q] = v[1];
+                st->var_num[sq][c] = v[0];
+                st->var_den[sq][c] = v[1];
+                st->weight_num[sq][c] = v[1];
+                st->mean_num[sq][c] = v[2];
+                st->mean_den[sq][c] = v[3];
+            }
+        }
+        sync();
+        if (clk && tid == 0 && reg == 0) clk[14] = clock64();
+        /* every component's weight estimator has the mass of all components of the state as its denominator */
+        if (tid < HFG_NS) {
+            double den = 0.0;
+            for (int c = 0; c < ncomp[tid]; c++) den += wn[pb[tid] + c];
+            for (int c = 0; c < ncomp[tid]; c++) st->weight_den[tid][c] = den;
+        }
+        sync();
+        if (clk && tid == 0 && reg == 0) clk[15] = clock64();
     }
     return nan;
 }

@@ -13,4 +13,5 @@ for i in range(6):
 pp, ll, conv, _ = g.em_finish(want_labels=False)
 t = g.debug_phase_clocks()[-1]
 print("NB cfg2: device EM iteration ms", [round(g.em_enqueued_ms(i), 4) for i in range(6)], "tail: totals", int(t[1] - t[0]), "stats block", int(t[2] - t[1]),
-      "estimators + M-step", int(t[5] - t[2]), "copy-in at", int(t[8] - t[2]), "fold", int(t[12] - t[2]), "Err", int(t[13] - t[12]), "Dup", int(t[14] - t[13]), "Hap", int(t[15] - t[14]), "Col + rest", int(t[8] - t[15]))
+      "estimators + M-step", int(t[5] - t[2]), "of which: constants + histogram in", int(t[12] - t[2]), "pmf", int(t[13] - t[12]), "estimator sums", int(t[14] - t[13]),
+      "weight denominators", int(t[15] - t[14]), "exchange + M-step", int(t[5] - t[15]))
