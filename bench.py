@@ -499,9 +499,13 @@ def run_ours(args):
         gpu2 = api.HmmFlaggerGPU(cfg)
         t_create = time.perf_counter() - t0
         gpu2.set_chunks(wl)  # host windows -> packed, segment-transposed words -> HBM (once per job)
+        t_set = time.perf_counter() - t0
         if fused:
             gpu2.peer_connect(dist)
         t_upload = time.perf_counter() - t0
+        if world > 1 and os.environ.get("BENCH_VERBOSE"):
+            print(f"[bench] rank {rank} e2e job {rep}: create {1e3 * t_create:.2f} ms, + set_chunks {1e3 * t_set:.2f} ms, + peer_connect "
+                  f"{1e3 * t_upload:.2f} ms", file=sys.stderr)
         if world == 1 or fused:
             # the step loop runs in C, as the reference-side binding runs it (integration/hmm_estep_cuda.c: hfg_em_iteration with
             # host buffers, then the M-step on the host); the L2 flush before every step is outside the step's interval

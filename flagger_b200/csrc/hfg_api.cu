@@ -378,6 +378,7 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
         return HFG_ERR_NOMEM;
     }
     ctx->dbg = getenv("HFG_DBG") ? atoi(getenv("HFG_DBG")) : 0;
+    ctx->timing = getenv("HFG_NO_FAST_BLOCKING") != NULL; /* A/B switch: the blocking calls always take the graph path */
     ctx->graph_disabled = getenv("HFG_NO_GRAPH") != NULL; /* A/B switch: plain stream launches instead of graph replay */
     if (nb) {
         const size_t tb = sizeof(double) * (size_t) cfg->n_regions * 4 * HFG_NB_XSTRIDE;

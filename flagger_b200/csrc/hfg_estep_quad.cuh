@@ -234,56 +234,51 @@ __device__ __noinline__ int hfg_fit_pred_round_dev(HfgFitState *st, const double
     const double y1 = st->y1, y2 = st->y2;
     double slo = st->lo, sx1 = st->x1, sx2 = st->x2, shi = st->hi, sspan = st->span;
     const unsigned snap_s = (unsigned) __cvta_generic_to_shared(snap);
-    /* who holds the value at x1 / x2: 0, 1 the round's y1, y2; 2 + t the point of step t */
-    int i1 = 0, i2 = 1;
-    /* The walk is one dependent chain, so it is written without branches (a branch on a fresh comparison costs more than the
-     * arithmetic of a step): the polynomial's value at the two interior points is carried like the objective's (one new
-     * evaluation per step, whether the step needs it or not), every update is a select.  The arithmetic that produces the
-     * points is the serial routine's (lo + inv_phi2 * span, lo + inv_phi * span; no contraction). */
+    /* The walk is ONE dependent chain on one warp: its time is its instruction count (a dependent instruction issues every
+     * ~4 cycles).  So the loop carries only what the next step needs -- the bracket, the two interior points and the
+     * polynomial's value at them (one new evaluation per step, whether the step needs it or not), every update a select, no
+     * branch -- and leaves behind the step's point (one store) and its predicted outcome (one bit).  Who held which value at
+     * which step is replayed from the bits afterwards, by all lanes at once.  The arithmetic that produces the points is the
+     * serial routine's (lo + inv_phi2 * span, lo + inv_phi * span; no contraction). */
     auto poly = [&](double x) {
         const double d = x - xs;
         return d * fma(d, fma(d, fma(d, c4, c3), c2), c1);
     };
     double q1 = poly(sx1), q2 = poly(sx2);
+    unsigned bits = 0u;
 #pragma unroll 1
     for (int t = 0; t < L; t++) {
         /* both points on one side of the maximum: the nearer one is higher; x* between them: the polynomial decides */
         const bool left = sx2 <= xs, right = sx1 >= xs;
         const bool b = left ? false : (right ? true : q1 > q2);
-        int word = i1 | (i2 << 6) | ((int) b << 12); /* the operands and the predicted outcome of step t's comparison */
+        bits |= (unsigned) b << t;
         sspan = inv_phi * sspan;
         const double nlo = b ? slo : sx1, nhi = b ? sx2 : shi;
         const double xn = nlo + (b ? inv_phi2 : inv_phi) * sspan;
         const double qn = poly(xn);
         const double nx1 = b ? xn : sx2, nx2 = b ? sx1 : xn;
         const double nq1 = b ? qn : q2, nq2 = b ? q1 : qn;
-        const int ni1 = b ? 2 + t : i2, ni2 = b ? i1 : 2 + t;
-        slo = nlo; shi = nhi; sx1 = nx1; sx2 = nx2; q1 = nq1; q2 = nq2; i1 = ni1; i2 = ni2;
-        word |= (i1 << 13) | (i2 << 19); /* the holders after step t */
-        {
-            /* (every lane stores the same values: no predicate, no branch) */
-            const unsigned row = snap_s + 64u * (unsigned) t;
-            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(row), "d"(xn), "d"(slo) : "memory");
-            asm volatile("st.shared.v2.f64 [%0+16], {%1, %2};" ::"r"(row), "d"(sx1), "d"(sx2) : "memory");
-            asm volatile("st.shared.v2.f64 [%0+32], {%1, %2};" ::"r"(row), "d"(shi), "d"(sspan) : "memory");
-            asm volatile("st.shared.u32 [%0+48], %1;" ::"r"(row), "r"(word) : "memory");
-        }
+        slo = nlo; shi = nhi; sx1 = nx1; sx2 = nx2; q1 = nq1; q2 = nq2;
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(snap_s + 8u * (unsigned) t), "d"(xn) : "memory"); /* (every lane, same value) */
     }
     __syncwarp();
     if (clk && lane == 0) clk[14] = clock64();
-    double4 ra;
-    double2 rb;
-    int word;
-    {
-        const unsigned row = snap_s + 64u * (unsigned) (lane < L ? lane : 0);
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(ra.x), "=d"(ra.y) : "r"(row));
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(ra.z), "=d"(ra.w) : "r"(row));
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+32];" : "=d"(rb.x), "=d"(rb.y) : "r"(row));
-        asm volatile("ld.shared.u32 %0, [%1+48];" : "=r"(word) : "r"(row));
-    }
-    const int ca = word & 63, cb = (word >> 6) & 63, pb = (word >> 12) & 1, a1 = (word >> 13) & 63, a2 = (word >> 19) & 63;
-    const double ynew = lane < L ? hfg_objective_dev(ra.x, trunc, sum_x, sum_w) : 0.0;
+    double xmine;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(xmine) : "r"(snap_s + 8u * (unsigned) (lane < L ? lane : 0)));
+    const double ynew = lane < L ? hfg_objective_dev(xmine, trunc, sum_x, sum_w) : 0.0;
     if (clk && lane == 0) clk[13] = clock64();
+    /* who holds the value at x1 / x2 when step `lane` compares them (0, 1: the round's y1, y2; 2 + t: the point of step t), and
+     * after it */
+    int ca = 0, cb = 1;
+#pragma unroll 1
+    for (int t = 0; t < lane; t++) {
+        const bool bt = (bits >> t) & 1u;
+        const int n1 = bt ? 2 + t : cb, n2 = bt ? ca : 2 + t;
+        ca = n1;
+        cb = n2;
+    }
+    const int pb = (int) ((bits >> lane) & 1u);
+    const int a1 = pb ? 2 + lane : cb, a2 = pb ? ca : 2 + lane;
     /* the evaluated values behind every comparison, then the first step whose prediction was wrong */
     const double ya_s = __shfl_sync(FULLW, ynew, ca < 2 ? 0 : ca - 2), yb_s = __shfl_sync(FULLW, ynew, cb < 2 ? 0 : cb - 2);
     const double ya = ca == 0 ? y1 : ca == 1 ? y2 : ya_s, yb = cb == 0 ? y1 : cb == 1 ? y2 : yb_s;
@@ -292,11 +287,25 @@ __device__ __noinline__ int hfg_fit_pred_round_dev(HfgFitState *st, const double
     const double n1_s = __shfl_sync(FULLW, ynew, a1 < 2 ? 0 : a1 - 2), n2_s = __shfl_sync(FULLW, ynew, a2 < 2 ? 0 : a2 - 2);
     const double n1 = a1 == 0 ? y1 : a1 == 1 ? y2 : n1_s, n2 = a2 == 0 ? y1 : a2 == 1 ? y2 : n2_s;
     if (m > 0) {
-        st->lo = __shfl_sync(FULLW, ra.y, m - 1);
-        st->x1 = __shfl_sync(FULLW, ra.z, m - 1);
-        st->x2 = __shfl_sync(FULLW, ra.w, m - 1);
-        st->hi = __shfl_sync(FULLW, rb.x, m - 1);
-        st->span = __shfl_sync(FULLW, rb.y, m - 1);
+        if (m < L) {
+            /* (rare) a wrong prediction at step m: the bracket after step m - 1, by replaying the positions of the first m
+             * steps (their predicted outcomes were the true ones) */
+            slo = st->lo; sx1 = st->x1; sx2 = st->x2; shi = st->hi; sspan = st->span;
+#pragma unroll 1
+            for (int t = 0; t < m; t++) {
+                const bool b = (bits >> t) & 1u;
+                sspan = inv_phi * sspan;
+                const double nlo = b ? slo : sx1, nhi = b ? sx2 : shi;
+                const double xn = nlo + (b ? inv_phi2 : inv_phi) * sspan;
+                const double nx1 = b ? xn : sx2, nx2 = b ? sx1 : xn;
+                slo = nlo; shi = nhi; sx1 = nx1; sx2 = nx2;
+            }
+        }
+        st->lo = slo;
+        st->x1 = sx1;
+        st->x2 = sx2;
+        st->hi = shi;
+        st->span = sspan;
         st->y1 = __shfl_sync(FULLW, n1, m - 1);
         st->y2 = __shfl_sync(FULLW, n2, m - 1);
     }
