@@ -93,6 +93,7 @@ struct hfg_ctx {
     int nb;
     double *d_nb_table, *h_nb_table;     /* [R][4][HFG_NB_XSTRIDE] device / pinned */
     double *d_nb_tile_col, *h_nb_tile_col; /* [n_tiles][4] */
+    double *h_nb_hist;                   /* pinned [R][4][256]: the grid-folded histogram of a blocking call */
     int32_t *h_tile_key;                 /* [n_tiles] host copies for folding the tile masses into the histogram */
     uint32_t *h_kdesc;                   /* [n_keys] */
     int32_t *d_nb_bins;                  /* device-resident loop: [R * 250 + 1] bin offsets, then [n_tiles] the tiles of every bin */
@@ -382,12 +383,14 @@ extern "C" int hfg_create(hfg_ctx **out, const hfg_config *cfg) {
     ctx->graph_disabled = getenv("HFG_NO_GRAPH") != NULL; /* A/B switch: plain stream launches instead of graph replay */
     if (nb) {
         const size_t tb = sizeof(double) * (size_t) cfg->n_regions * 4 * HFG_NB_XSTRIDE;
-        if (cudaMalloc((void **) &ctx->d_nb_table, tb) != cudaSuccess || cudaMallocHost((void **) &ctx->h_nb_table, tb) != cudaSuccess) {
+        /* (pinned: the table, then the histogram a blocking call reads back -- the same [R][4][256] shape) */
+        if (cudaMalloc((void **) &ctx->d_nb_table, tb) != cudaSuccess || cudaMallocHost((void **) &ctx->h_nb_table, 2 * tb) != cudaSuccess) {
             fail(NULL, HFG_ERR_CUDA, "negative-binomial table allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
             hfg_destroy(ctx);
             return HFG_ERR_CUDA;
         }
-        memset(ctx->h_nb_table, 0, tb);
+        memset(ctx->h_nb_table, 0, 2 * tb);
+        ctx->h_nb_hist = ctx->h_nb_table + (size_t) cfg->n_regions * 4 * HFG_NB_XSTRIDE;
     }
     *out = ctx;
     return HFG_OK;
@@ -1203,9 +1206,17 @@ static int run_blocking_nb(hfg_ctx *ctx, const hfg_region_params *params, int fo
     CU(cudaEventRecord(ctx->ev0, ctx->stream));
     CU(cudaLaunchCooperativeKernel(ctx->kernel, dim3(ctx->grid), dim3(ctx->threads), kargs, ctx->smem_bytes, ctx->stream));
     CU(cudaEventRecord(ctx->ev1, ctx->stream));
-    if (!forward_only && l->n_tiles > 0)
-        CU(cudaMemcpyAsync(ctx->h_nb_tile_col, ctx->d_nb_tile_col, sizeof(double) * 4 * (size_t) l->n_tiles, cudaMemcpyDeviceToHost,
-                           ctx->stream));
+    /* what comes back: the (region, state, coverage bin) histogram folded by the grid (grid_fold_histogram), [R][4][256]
+     * doubles = 8 KB per region, instead of four doubles per statistics tile (585 KB for config 2) and a host fold */
+    const size_t hist_doubles = (size_t) R * 4 * 256;
+    const int device_fold = ctx->quad == 3; /* the earlier kernel generations (HFG_KERNEL=quad / v1) leave the fold to the host */
+    if (!forward_only && l->n_tiles > 0) {
+        if (device_fold)
+            CU(cudaMemcpyAsync(ctx->h_nb_hist, ctx->d_nb_lgx1 + 256, sizeof(double) * hist_doubles, cudaMemcpyDeviceToHost, ctx->stream));
+        else
+            CU(cudaMemcpyAsync(ctx->h_nb_tile_col, ctx->d_nb_tile_col, sizeof(double) * 4 * (size_t) l->n_tiles, cudaMemcpyDeviceToHost,
+                               ctx->stream));
+    }
     CU(cudaEventRecord(ctx->ev3, ctx->stream));
     CU(cudaEventRecord(ctx->stage_ev[0], ctx->stream));
     ctx->ev_valid = ctx->span_valid = 1;
@@ -1219,11 +1230,17 @@ static int run_blocking_nb(hfg_ctx *ctx, const hfg_region_params *params, int fo
     if (rc != HFG_OK || !stats || forward_only) return rc;
     double *hist = (double *) calloc((size_t) R * 4 * HFG_NB_BINS, sizeof(double));
     if (!hist) return fail(ctx, HFG_ERR_NOMEM, "out of host memory");
-    for (int32_t t = 0; t < l->n_tiles; t++) { /* tile order: the same sum on every run */
-        const uint32_t w = ctx->h_kdesc[ctx->h_tile_key[t]];
-        const int x = (int) HFG_OBS_X(w), region = (int) HFG_OBS_REGION(w);
-        const int bin = x < HFG_NB_BINS ? x : HFG_NB_BINS - 1; /* count_data.c:56-64 */
-        for (int s = 0; s < 4; s++) hist[((size_t) region * 4 + s) * HFG_NB_BINS + bin] += ctx->h_nb_tile_col[(size_t) t * 4 + s];
+    if (device_fold) {
+        if (l->n_tiles > 0)
+            for (int q = 0; q < R * 4; q++) /* device rows are 256 wide, the estimator's HFG_NB_BINS */
+                memcpy(hist + (size_t) q * HFG_NB_BINS, ctx->h_nb_hist + (size_t) q * 256, sizeof(double) * HFG_NB_BINS);
+    } else {
+        for (int32_t t = 0; t < l->n_tiles; t++) { /* tile order: the same sum on every run */
+            const uint32_t w = ctx->h_kdesc[ctx->h_tile_key[t]];
+            const int x = (int) HFG_OBS_X(w), region = (int) HFG_OBS_REGION(w);
+            const int bin = x < HFG_NB_BINS ? x : HFG_NB_BINS - 1; /* count_data.c:56-64 */
+            for (int s = 0; s < 4; s++) hist[((size_t) region * 4 + s) * HFG_NB_BINS + bin] += ctx->h_nb_tile_col[(size_t) t * 4 + s];
+        }
     }
     rc = hfg_nb_stats_from_histogram(&ctx->cfg, params, hist, stats);
     free(hist);

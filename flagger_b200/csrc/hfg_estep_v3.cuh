@@ -929,9 +929,9 @@ __global__ void __launch_bounds__(THREADS, 1) hfg_estep_v3_kernel(const __grid_c
     if (nan_flag) atomicOr(A.err_flags, 2);
 
     if constexpr (NB) {
-        /* device-resident loop: the histogram the estimators are fed from (hmm.c:615-617) is folded by the whole grid, one
-         * (region, coverage bin) at a time per CTA, before the last CTA's tail reads it (hfg_nb_dev.cuh) */
-        if (A.em_mode == 1) {
+        /* the histogram the estimators are fed from (hmm.c:615-617) is folded by the whole grid, one (region, coverage bin) at
+         * a time per CTA (hfg_nb_dev.cuh): the last CTA's tail reads it (device-resident loop) or the host does (blocking calls) */
+        if (A.em_mode != 2 && !A.forward_only) { /* (the blocking calls read the folded histogram back: 8 KB per region) */
             grid.sync(); /* every tile's column sums are in place */
             hfgnb::grid_fold_histogram<THREADS>(R, A.nb_tile_col, A.nb_bin_begin, A.nb_bin_tiles, A.nb_hist, warp_tot);
         }

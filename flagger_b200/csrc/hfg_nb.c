@@ -11,8 +11,9 @@
  *   hfg_nb_stats_from_histogram  the estimator sums from the (region, state, x) histogram the device reduces
  *   the M-step, model initialisation and feasibility test (reached through hfg_mstep / hfg_model_init /
  *   hfg_params_feasible, hfg_host_model.c)
- * The device side is a table look-up in the key-matrix phase and per-tile pair masses out of the statistics phase
- * (hfg_estep_v3_kernel<THREADS, true>, hfg_api.cu::run_blocking_nb; tests/test_gpu_nb.py).  The functions here are checked
+ * The device side of a blocking call is a table look-up in the key-matrix phase, per-tile pair masses out of the statistics
+ * phase and their fold into the histogram by the whole grid (hfg_estep_v3_kernel<THREADS, true>, hfg_nb_dev.cuh,
+ * hfg_api.cu::run_blocking_nb; tests/test_gpu_nb.py); the device-resident loop keeps all of it on the device.  The functions here are checked
  * against the oracle on the CPU (tests/test_host_nb.py).
  *
  * Parameters: hfg_region_params.mean[s][c] = theta, .var[s][c] = lambda, .weight[s][c] = mixture weight; statistics:
