@@ -278,6 +278,52 @@ def test_pinned_label_buffer_and_repeated_calls(orc):
     pinned.free()
 
 
+def test_blocking_fast_path_equals_graph_path(orc):
+    """A single-region model takes the one-launch path of the blocking calls (parameters in the kernel arguments, completion
+    word polled in pinned memory, no events: hfg_api.cu::run_blocking); with timing events requested the same call replays the
+    captured graph (upload node, kernel, events, stream synchronisation).  Same kernel, same bits: statistics, log-likelihood
+    and labels, with a page-locked label buffer and with a pageable one, over changing parameters; and the oracle's values."""
+    wl = synth.small_mixed(n_regions=1, seed=29)
+    K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+    cfg = _abi.make_config(n_regions=1, n_col_comps=K)
+    params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+    fast, graph = api.HmmFlaggerGPU(cfg, wl), api.HmmFlaggerGPU(cfg, wl, timing=True)
+    pinned = api.PinnedArray(wl.n_windows, np.int8)
+    try:
+        for it in range(4):
+            out = orc.estep(cfg, wl, synth.HIFI_ALPHA, params)
+            sf, llf, labf = fast.em_iteration(synth.HIFI_ALPHA, params, labels=pinned.array if it % 2 == 0 else None)
+            labf = labf.copy()
+            sg, llg, labg = graph.em_iteration(synth.HIFI_ALPHA, params)
+            assert fast.last_estep_kernel_ms() < 0 and graph.last_estep_kernel_ms() > 0  # which path each one took
+            assert llf == llg and np.array_equal(labf, labg) and np.array_equal(_abi.stats_as_flat(sf), _abi.stats_as_flat(sg))
+            assert np.array_equal(labf, out["labels"]) and abs(llf - out["loglik"]) <= TOL_LOGLIK * abs(out["loglik"])
+            assert abs(fast.forward_only(synth.HIFI_ALPHA, params) - llf) <= 1e-12 * abs(llf)
+            params, _ = api.mstep(cfg, params, sf, tol=1e-12)
+    finally:
+        fast.close()
+        graph.close()
+        pinned.free()
+
+
+def test_blocking_fast_path_on_recycled_result_blocks(orc):
+    """The completion word lives behind the pinned result block, and those blocks are recycled from context to context: a
+    new context must never take a predecessor's word for its own (contexts opened and closed in turn over different inputs,
+    each checked against the oracle)."""
+    for seed in (31, 32, 33, 34):
+        wl = synth.small_mixed(n_regions=1, seed=seed)
+        K = api.best_num_collapsed_comps(int(wl.cov.max()), wl.region_coverages)
+        cfg = _abi.make_config(n_regions=1, n_col_comps=K)
+        params = api.model_init(cfg, wl.region_coverages, wl.window_len)
+        out = orc.estep(cfg, wl, synth.HIFI_ALPHA, params)
+        gpu = api.HmmFlaggerGPU(cfg, wl)
+        stats, ll, labels = gpu.em_iteration(synth.HIFI_ALPHA, params)
+        gpu.close()
+        assert abs(ll - out["loglik"]) <= TOL_LOGLIK * abs(out["loglik"]) and np.array_equal(labels, out["labels"])
+        so = _abi.stats_as_flat(out["stats"])
+        assert np.all(np.abs(_abi.stats_as_flat(stats) - so) <= TOL_STATS * np.abs(so).max())
+
+
 def test_many_distinct_observation_keys(orc):
     """The kernel evaluates emissions once per distinct (x, previous x, region, mask, beta) key.  Coverage drawn uniformly
     from 0..250 with random MAPQ / clipping fractions makes almost every window its own key (the worst case for the key
