@@ -1,15 +1,17 @@
 /*
- * hfg_nb_dev.cuh -- the negative-binomial model on the device, for the device-resident EM loop (hfg_em_*, hfg_run_em).
+ * hfg_nb_dev.cuh -- the negative-binomial model on the device.
  *
- * The blocking calls keep the host in the loop (hfg_nb.c: emission table with libm, histogram fold, long-double digamma: the
- * bits of the reference).  Here the same formulas run in fp64 on the device so that successive iterations are back-to-back
- * kernels: the pmf (NegativeBinomial_getComponentProbs, hmm_utils.c:494-515) per observation key in the key-matrix phase,
- * and in the kernel tail the histogram of the pair mass over the coverage value (hmm.c:615-617, count_data.c:56-64: folded
- * from the per-tile column sums, one warp per bin), NegativeBinomial_updateEstimator per non-empty bin
- * (hmm_utils.c:536-563, psi(r + x) by the recurrence of :392-406) and the M-step (hfg_nb_mstep_inl.h, the host's code).
- * Differences from the host path: CUDA's lgamma / exp / log instead of glibc's, psi(r + x) - psi(r) as a scan of reciprocals
- * without the long-double digamma(r) the host adds and subtracts again, bins summed by a fixed tree instead of in ascending
- * order: rounding only (tests/test_gpu_nb.py compares the two loops).
+ * Device-resident EM loop (hfg_em_*, hfg_run_em): the formulas of the host half (hfg_nb.c) run in fp64 on the device so that
+ * successive iterations are back-to-back kernels: the pmf (NegativeBinomial_getComponentProbs, hmm_utils.c:494-515) per
+ * observation key in the key-matrix phase; after the statistics phase the histogram of the pair mass over the coverage value
+ * (hmm.c:615-617, count_data.c:56-64), folded from the per-tile column sums by the WHOLE grid, one (region, bin) per CTA at a
+ * time (grid_fold_histogram); and in the last CTA's tail NegativeBinomial_updateEstimator per non-empty bin
+ * (hmm_utils.c:536-563, psi(r + x) by the recurrence of :392-406: tail_estimators) and the M-step (hfg_nb_mstep_inl.h, the
+ * host's code).  Differences from the host path: CUDA's lgamma / exp / log instead of glibc's, psi(r + x) - psi(r) as a
+ * running sum of reciprocals without the long-double digamma(r) the host adds and subtracts again, bins summed by a fixed
+ * tree instead of in ascending order: rounding only (tests/test_gpu_nb.py compares the two loops).
+ * The blocking calls (hfg_em_iteration) use the grid-wide fold as well and read the histogram back; their emission table
+ * (libm) and estimator update (long-double digamma) stay on the host: the bits of the reference.
  */
 #pragma once
 
