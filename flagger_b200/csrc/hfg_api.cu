@@ -1292,6 +1292,7 @@ static int run_blocking(hfg_ctx *ctx, const double *alpha, const hfg_region_para
             CU(cudaStreamSynchronize(ctx->stream));
             if (*flag != seq) return fail(ctx, HFG_ERR_CUDA, "the E-step kernel ended without delivering its results");
         }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE); /* the results are read after the word that announces them */
         if (with_labels && !label_alias) memcpy(labels, ctx->h_labels, (size_t) ctx->lay.n_windows);
         return parse_out(ctx, stats, loglik);
     }
