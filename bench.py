@@ -640,7 +640,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(stats.nbytes + 16 + wl.n_windows),
                     "includes": "hfg_create + hfg_set_chunks once, then per step hfg_em_iteration (host params in, host "
                                 "statistics + labels out, labels into a page-locked buffer) + host hfg_mstep, the step loop driven "
-                                "from C as the drop-in binding drives it (hfg_debug_blocking_steps); median of 5 such jobs",
+                                "from C as the drop-in binding drives it (hfg_debug_blocking_steps); a single-region model takes the "
+                                "call's one-launch path (parameters in the kernel arguments, completion word polled in pinned memory); "
+                                "median of 5 such jobs",
                     "job_ms": [1e3 * j for j in jobs]},
             "e2e_job": {"value": W_total * args.steps / run_job_total, "unit": "windows/s",
                         "call": f"hfg_create + hfg_set_chunks + hfg_run_em({args.steps - 1} EM iterations + final inference) with "
